@@ -1,0 +1,774 @@
+// mg.cu -- device-resident multigrid hierarchy and the MG-PCG driver behind the C ABI
+// of include/ddpca_b200.h (class MGPIS of the reference, MGPIS.h:8-225).
+//
+// Layout in HBM, per level l (all in the stage-permuted numbering of plan.h):
+//   A_l   one CSR (int32 rowptr/colidx, FP64 val) + dpos[n] (diagonal position).  The
+//         reference keeps three copies (consLowe/consDiag/consUppe, MGPIS.h:29-33); the
+//         strictly-lower / strictly-upper halves are sub-ranges of each row here.
+//   P_l-1 realProl[l-1] as CSR (n_l x n_l-1) and its explicit transpose R (gather-based
+//         restriction, no atomics).
+//   x,b,p1,r work vectors.   Level 0 additionally holds the dense inverse of consStif[0].
+// Scalars of the CG recurrence live in a PcgState in HBM; one CG iteration is one CUDA
+// graph launch; the host only polls a `done` flag with a lag (no per-iteration sync).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ddpca_b200.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+using namespace ddpca;
+
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return 1; }
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" +  \
+                    std::to_string(__LINE__) + ")";                                               \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+namespace {
+
+struct DevCsr {
+    int rows = 0, cols = 0;
+    long nnz = 0;
+    int *rp = nullptr, *ci = nullptr;
+    double *v = nullptr;
+    CsrView view() const { return CsrView{rows, rp, ci, v}; }
+    double avg_row() const { return rows ? (double)nnz / rows : 0.0; }
+};
+
+struct Segment {
+    int multi;   // 0: one stage, one launch, one warp per group; 1: run of stages in one CTA
+    int s0, s1;  // stage range
+    int g0, g1;  // group range
+    double bytes_lo, bytes_up;  // algorithmic bytes of the strictly-lower / -upper halves + vectors
+};
+
+struct Level {
+    int n = 0;
+    long nnz = 0;
+    LevelPlan plan;
+    DevCsr A;
+    int *dpos = nullptr, *gstart = nullptr, *stage_group = nullptr, *perm = nullptr;
+    std::vector<Segment> segs;
+    DevCsr P, R;  // level l <-> l-1 (l >= 1)
+    double *x = nullptr, *b = nullptr, *p1 = nullptr, *r = nullptr, *dinv = nullptr;
+    long nnz_lower = 0;
+    LvlView view() const { return LvlView{n, A.rp, A.ci, A.v, dpos, gstart}; }
+};
+
+struct ProfRec {
+    int kclass, level;
+    double bytes;
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct ddpca_mg {
+    int device = 0;
+    int mode = DDPCA_SMOOTH_MC;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int nlev = 0;
+    std::vector<Level> lev;
+    double *Binv = nullptr;  // dense inverse of level 0
+    int n0 = 0;
+    // finest-level CG vectors (device numbering) + staging in reference numbering
+    double *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr, *cg_z = nullptr, *cg_x = nullptr;
+    double *stage_a = nullptr, *stage_b = nullptr;  // max-n staging buffers
+    PcgState *st = nullptr;
+    PcgState *st_host = nullptr;  // pinned, ring of kDepth+1
+    double *partial[3] = {nullptr, nullptr, nullptr};
+    cudaGraphExec_t iter_graph[2] = {nullptr, nullptr};  // per preconditioner
+    long iter_graph_nodes[2] = {0, 0};
+    // bookkeeping
+    long launches = 0;
+    bool capturing = false;
+    long captured_nodes = 0;
+    bool profile = false;
+    std::vector<ProfRec> prof;
+    double prof_ms[DDPCA_K_COUNT][16];
+    long prof_n[DDPCA_K_COUNT][16];
+    double prof_bytes[DDPCA_K_COUNT][16];
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double t_solve = 0, t_h2d = 0, t_d2h = 0;
+    int sms = 148;
+
+    void pre(int kclass, int level, double bytes)
+    {
+        if (capturing) { captured_nodes++; return; }
+        launches++;
+        if (profile) {
+            ProfRec r{kclass, level, bytes, nullptr, nullptr};
+            cudaEventCreate(&r.a);
+            cudaEventCreate(&r.b);
+            cudaEventRecord(r.a, stream);
+            prof.push_back(r);
+        }
+    }
+    void post()
+    {
+        if (profile && !capturing) cudaEventRecord(prof.back().b, stream);
+    }
+    void prof_collect()
+    {
+        if (prof.empty()) return;
+        cudaStreamSynchronize(stream);
+        for (auto &r : prof) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            int l = std::min(std::max(r.level, 0), 15);
+            prof_ms[r.kclass][l] += ms;
+            prof_n[r.kclass][l] += 1;
+            prof_bytes[r.kclass][l] += r.bytes;
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        prof.clear();
+    }
+};
+
+#define KL(h, kc, lvl, bytes, ...) \
+    do {                           \
+        (h)->pre(kc, lvl, bytes);  \
+        __VA_ARGS__;               \
+        (h)->post();               \
+    } while (0)
+
+static const int kDepth = 2;  // CG iterations kept in flight ahead of the host's done-poll
+
+// ------------------------------------------------------------------------------------------
+static int upload_csr(const CsrHost &h, DevCsr &d)
+{
+    d.rows = h.rows; d.cols = h.cols; d.nnz = h.nnz();
+    CU(cudaMalloc(&d.rp, sizeof(int) * (h.rows + 1)));
+    CU(cudaMalloc(&d.ci, sizeof(int) * std::max<long>(1, d.nnz)));
+    CU(cudaMalloc(&d.v, sizeof(double) * std::max<long>(1, d.nnz)));
+    CU(cudaMemcpy(d.rp, h.rp.data(), sizeof(int) * (h.rows + 1), cudaMemcpyHostToDevice));
+    if (d.nnz) {
+        CU(cudaMemcpy(d.ci, h.ci.data(), sizeof(int) * d.nnz, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.v, h.v.data(), sizeof(double) * d.nnz, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+static void free_csr(DevCsr &d)
+{
+    cudaFree(d.rp); cudaFree(d.ci); cudaFree(d.v);
+    d = DevCsr();
+}
+template <class T>
+static int upload_vec(const std::vector<T> &h, T **d)
+{
+    CU(cudaMalloc(d, sizeof(T) * std::max<size_t>(1, h.size())));
+    if (!h.empty()) CU(cudaMemcpy(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ---- kernel launch helpers (all on h->stream) ----------------------------------------------
+static void launch_spmv(ddpca_mg *h, int kclass, int lvl, const DevCsr &A, const double *x, double *y, bool add,
+                        const double *dotw, double *partial, const int *done)
+{
+    // algorithmic bytes, SURVEY.md §8(d): 12 nnz + 4 (rows+1) + 8 cols (x once) + 8 rows (y) [+8 rows for +=]
+    double bytes = 12.0 * A.nnz + 4.0 * (A.rows + 1) + 8.0 * A.cols + 8.0 * A.rows * (add ? 2 : 1) + (dotw ? 8.0 * A.rows : 0.0);
+    const double avg = A.avg_row();
+    const int T = 256;
+    auto grid_for = [&](int lanes) {
+        long need = cdiv((long)A.rows * lanes, T);
+        long cap = dotw ? kNumPart : (long)h->sms * 64;
+        return (int)std::max<long>(1, std::min(need, cap));
+    };
+    if (dotw) {
+        int g = grid_for(32);
+        // stale slots of the partial buffer beyond g are never read: consumers use np = g
+        KL(h, kclass, lvl, bytes, (k_spmv<32, false, true><<<g, T, 0, h->stream>>>(A.view(), x, y, dotw, partial, done)));
+        return;
+    }
+#define SPMV_CASE(L)                                                                                                   \
+    do {                                                                                                               \
+        int g = grid_for(L);                                                                                           \
+        if (add) KL(h, kclass, lvl, bytes, (k_spmv<L, true, false><<<g, T, 0, h->stream>>>(A.view(), x, y, nullptr, nullptr, done)));  \
+        else KL(h, kclass, lvl, bytes, (k_spmv<L, false, false><<<g, T, 0, h->stream>>>(A.view(), x, y, nullptr, nullptr, done)));     \
+    } while (0)
+    if (avg > 40) SPMV_CASE(32);
+    else if (avg > 20) SPMV_CASE(16);
+    else if (avg > 10) SPMV_CASE(8);
+    else SPMV_CASE(4);
+#undef SPMV_CASE
+}
+static int spmv_dot_grid(const ddpca_mg *h, const DevCsr &A)
+{
+    (void)h;
+    long need = cdiv((long)A.rows * 32, 256);
+    return (int)std::max<long>(1, std::min<long>(need, kNumPart));
+}
+
+static void sweep_fwd(ddpca_mg *h, int l, const double *b, double *x, bool zero_x, const int *done)
+{
+    Level &L = h->lev[l];
+    for (const Segment &s : L.segs) {
+        double bytes = s.bytes_lo + (zero_x ? 0.0 : s.bytes_up);
+        if (!s.multi) {
+            int ng = s.g1 - s.g0;
+            int grid = cdiv((long)ng * 32, 256);
+            if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_stage<true><<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, b, x, L.p1, done)));
+            else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_stage<false><<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, b, x, L.p1, done)));
+        } else {
+            if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<true><<<1, 1024, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+            else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<false><<<1, 1024, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+        }
+    }
+}
+static void sweep_bwd(ddpca_mg *h, int l, double *x, const int *done)
+{
+    Level &L = h->lev[l];
+    for (int k = (int)L.segs.size() - 1; k >= 0; k--) {
+        const Segment &s = L.segs[k];
+        if (!s.multi) {
+            int ng = s.g1 - s.g0;
+            int grid = cdiv((long)ng * 32, 256);
+            KL(h, DDPCA_K_SWEEP_BWD, l, s.bytes_up, (k_sweep_bwd_stage<<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, L.p1, x, done)));
+        } else {
+            KL(h, DDPCA_K_SWEEP_BWD, l, s.bytes_up, (k_sweep_bwd_multi<<<1, 1024, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, L.p1, x, done)));
+        }
+    }
+}
+
+// MGPIS::MULT_VCYC (MGPIS.h:55-128) on device vectors in device numbering
+static void vcycle_dev(ddpca_mg *h, int l, const double *b, double *x, bool zero_x, const int *done)
+{
+    if (l == 0) {
+        double bytes = 8.0 * h->n0 * (double)h->n0 + 16.0 * h->n0;
+        KL(h, DDPCA_K_COARSE, 0, bytes, (k_dense_gemv<<<cdiv((long)h->n0 * 32, 256), 256, 0, h->stream>>>(h->n0, h->Binv, b, x, done)));
+        return;
+    }
+    Level &L = h->lev[l];
+    Level &C = h->lev[l - 1];
+    sweep_fwd(h, l, b, x, zero_x, done);  // :65-72
+    sweep_bwd(h, l, x, done);             // :73-76
+    {
+        double bytes = 12.0 * L.nnz_lower + 4.0 * (L.n + 1) + 8.0 * L.n * 4;
+        if (L.A.avg_row() > 40)
+            KL(h, DDPCA_K_RESID, l, bytes, (k_resid_lower<32><<<cdiv((long)L.n * 32, 256), 256, 0, h->stream>>>(L.view(), b, L.p1, x, L.r, done)));
+        else
+            KL(h, DDPCA_K_RESID, l, bytes, (k_resid_lower<8><<<cdiv((long)L.n * 8, 256), 256, 0, h->stream>>>(L.view(), b, L.p1, x, L.r, done)));
+    }
+    launch_spmv(h, DDPCA_K_RESTRICT, l, L.R, L.r, C.b, false, nullptr, nullptr, done);  // :96
+    vcycle_dev(h, l - 1, C.b, C.x, true, done);                                          // :93-99
+    launch_spmv(h, DDPCA_K_PROLONG, l, L.P, C.x, x, true, nullptr, nullptr, done);       // :100
+    sweep_fwd(h, l, b, x, false, done);  // :102-109
+    sweep_bwd(h, l, x, done);            // :110-113
+}
+
+static void precondition(ddpca_mg *h, int prec, const double *r, double *z, const int *done)
+{
+    int Lf = h->nlev - 1;
+    Level &L = h->lev[Lf];
+    if (prec == 0) {
+        KL(h, DDPCA_K_VECTOR, Lf, 24.0 * L.n, (k_jacobi<<<cdiv(L.n, 256), 256, 0, h->stream>>>(L.n, L.dinv, r, z, done)));
+    } else {
+        vcycle_dev(h, Lf, r, z, true, done);
+    }
+}
+
+static int vec_grid(const ddpca_mg *h, int n) { return std::max(1, std::min(cdiv(n, 256), std::min(kNumPart, h->sms * 8))); }
+
+// body of one CG iteration, MGPIS.h:199-219
+static void enqueue_iteration(ddpca_mg *h, int prec)
+{
+    int Lf = h->nlev - 1;
+    Level &L = h->lev[Lf];
+    const int *done = &h->st->done;
+    int n = L.n;
+    int gq = spmv_dot_grid(h, L.A);
+    launch_spmv(h, DDPCA_K_SPMV, Lf, L.A, h->cg_p, h->cg_q, false, h->cg_p, h->partial[0], done);  // :200 + p.q
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_alpha<<<1, 32, 0, h->stream>>>(h->st, h->partial[0], gq)));  // :201
+    int gv = vec_grid(h, n);
+    KL(h, DDPCA_K_VECTOR, Lf, 48.0 * n, (k_update_xr<<<gv, 256, 0, h->stream>>>(n, h->st, h->cg_p, h->cg_q, h->cg_x, h->cg_r, h->partial[1])));  // :202-203
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_rr<<<1, 32, 0, h->stream>>>(h->st, h->partial[1], gv)));
+    precondition(h, prec, h->cg_r, h->cg_z, done);  // :204-210
+    KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, h->cg_r, h->cg_z, h->partial[2], done)));  // :212
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_beta<<<1, 32, 0, h->stream>>>(h->st, h->partial[2], gv)));                       // :211-213
+    KL(h, DDPCA_K_VECTOR, Lf, 24.0 * n, (k_update_p<<<gv, 256, 0, h->stream>>>(n, h->st, h->cg_z, h->cg_p)));            // :214
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_next<<<1, 1, 0, h->stream>>>(h->st)));                                           // :219,198
+}
+
+static int build_iter_graph(ddpca_mg *h, int prec)
+{
+    if (h->iter_graph[prec]) return 0;
+    cudaGraph_t g = nullptr;
+    // capture on the handle's own stream (an external stream may be in use by others)
+    cudaStream_t saved = h->stream;
+    h->stream = h->own_stream;
+    h->capturing = true;
+    h->captured_nodes = 0;
+    cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        enqueue_iteration(h, prec);
+        e = cudaStreamEndCapture(h->stream, &g);
+    }
+    h->capturing = false;
+    h->stream = saved;
+    if (e != cudaSuccess) return fail(std::string("graph capture: ") + cudaGetErrorString(e));
+    h->iter_graph_nodes[prec] = h->captured_nodes;
+    CU(cudaGraphInstantiate(&h->iter_graph[prec], g, 0));
+    CU(cudaGraphDestroy(g));
+    return 0;
+}
+
+// CG_SOLV on device vectors: b_ref/x_ref in REFERENCE numbering, resident on the device
+static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref, double rel_tol, long maxit,
+                      long *iters, double *resid, double *tol_abs)
+{
+    if (prec != 0 && prec != 1) return fail("prec must be 0 (Jacobi) or 1 (V-cycle)");
+    int Lf = h->nlev - 1;
+    Level &L = h->lev[Lf];
+    int n = L.n;
+    const int *done = &h->st->done;
+    if (prec == 0 && !L.dinv) {
+        CU(cudaMalloc(&L.dinv, sizeof(double) * n));
+        k_extract_diag_inv<<<cdiv(n, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
+    }
+    if (!h->profile) {
+        if (build_iter_graph(h, prec)) return 1;
+    }
+    int gv = vec_grid(h, n);
+    // r = b (device numbering), x = 0                                  MGPIS.h:173,189
+    KL(h, DDPCA_K_VECTOR, Lf, 20.0 * n, (k_gather<<<cdiv(n, 256), 256, 0, h->stream>>>(n, L.perm, b_ref, h->cg_r)));
+    CU(cudaMemsetAsync(h->cg_x, 0, sizeof(double) * n, h->stream));
+    CU(cudaMemsetAsync(h->cg_p, 0, sizeof(double) * n, h->stream));
+    KL(h, DDPCA_K_VECTOR, Lf, 8.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, h->cg_r, h->cg_r, h->partial[0], nullptr)));
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_init<<<1, 32, 0, h->stream>>>(h->st, h->partial[0], gv, rel_tol, (long long)maxit)));  // :174-175
+    precondition(h, prec, h->cg_r, h->cg_p, done);                                                                              // :191-196
+    KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, h->cg_r, h->cg_p, h->partial[2], done)));
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_delta0<<<1, 32, 0, h->stream>>>(h->st, h->partial[2], gv)));                            // :197
+    // main loop: enqueue iterations ahead, poll `done` with a lag of kDepth iterations
+    cudaEvent_t evs[kDepth + 1];
+    for (int k = 0; k <= kDepth; k++) CU(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+    long issued = 0;
+    bool finished = false;
+    // state after setup (covers zero RHS: done already set, MGPIS.h:198 never entered)
+    CU(cudaMemcpyAsync(&h->st_host[0], h->st, sizeof(PcgState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(evs[0], h->stream));
+    CU(cudaEventSynchronize(evs[0]));
+    finished = h->st_host[0].done != 0;
+    while (!finished) {
+        int slot = (int)(issued % (kDepth + 1));
+        if (h->profile) {
+            enqueue_iteration(h, prec);
+        } else {
+            CU(cudaGraphLaunch(h->iter_graph[prec], h->stream));
+            h->launches += h->iter_graph_nodes[prec];
+        }
+        CU(cudaMemcpyAsync(&h->st_host[slot], h->st, sizeof(PcgState), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventRecord(evs[slot], h->stream));
+        issued++;
+        if (issued >= kDepth) {
+            int old = (int)((issued - kDepth) % (kDepth + 1));
+            CU(cudaEventSynchronize(evs[old]));
+            if (h->st_host[old].done) finished = true;
+        }
+        if (h->profile && (issued % 8) == 0) h->prof_collect();
+    }
+    // x (device numbering) -> reference numbering
+    KL(h, DDPCA_K_VECTOR, Lf, 20.0 * n, (k_scatter<<<cdiv(n, 256), 256, 0, h->stream>>>(n, L.perm, h->cg_x, x_ref)));
+    CU(cudaMemcpyAsync(&h->st_host[0], h->st, sizeof(PcgState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k <= kDepth; k++) cudaEventDestroy(evs[k]);
+    if (h->profile) h->prof_collect();
+    if (iters) *iters = (long)h->st_host[0].it;
+    if (resid) *resid = std::sqrt(h->st_host[0].rr);
+    if (tol_abs) *tol_abs = h->st_host[0].tol;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+static int build_segments(Level &L, const std::vector<int> &rp_new, const std::vector<int> &dpos_new)
+{
+    const LevelPlan &pl = L.plan;
+    const int kBigStage = 48;  // groups; smaller stages are merged into single-CTA runs
+    int ns = pl.nstages();
+    auto stage_bytes = [&](int s0, int s1, double &lo, double &up) {
+        int ra = pl.group_start[pl.stage_group[s0]], rb = pl.group_start[pl.stage_group[s1]];
+        long nl = 0, nu = 0;
+        for (int i = ra; i < rb; i++) { nl += dpos_new[i] - rp_new[i]; nu += rp_new[i + 1] - dpos_new[i] - 1; }
+        double rows = rb - ra;
+        // 12 nnz(T) + 4 rows (rowptr) + 8 diag + 8 rhs + 16 x (read+write)
+        lo = 12.0 * nl + rows * (4 + 8 + 8 + 16);
+        up = 12.0 * nu + rows * (4 + 8 + 8 + 16);
+    };
+    int s = 0;
+    while (s < ns) {
+        int ng = pl.stage_group[s + 1] - pl.stage_group[s];
+        Segment seg{};
+        if (ng >= kBigStage) {
+            seg.multi = 0; seg.s0 = s; seg.s1 = s + 1;
+        } else {
+            int e = s + 1;
+            while (e < ns && pl.stage_group[e + 1] - pl.stage_group[e] < kBigStage) e++;
+            seg.multi = 1; seg.s0 = s; seg.s1 = e;
+        }
+        seg.g0 = pl.stage_group[seg.s0];
+        seg.g1 = pl.stage_group[seg.s1];
+        stage_bytes(seg.s0, seg.s1, seg.bytes_lo, seg.bytes_up);
+        L.segs.push_back(seg);
+        s = seg.s1;
+    }
+    return 0;
+}
+
+static int invert_level0(ddpca_mg *h)
+{
+    Level &L0 = h->lev[0];
+    int n = L0.n;
+    h->n0 = n;
+    if (n > 32768) return fail("level 0 has " + std::to_string(n) + " rows; the dense direct solver supports <= 32768");
+    CU(cudaMalloc(&h->Binv, sizeof(double) * (size_t)n * n));
+    CU(cudaMemsetAsync(h->Binv, 0, sizeof(double) * (size_t)n * n, h->stream));
+    double *rowk, *colk;
+    CU(cudaMalloc(&rowk, sizeof(double) * n));
+    CU(cudaMalloc(&colk, sizeof(double) * n));
+    k_csr_to_dense<<<cdiv(n, 128), 128, 0, h->stream>>>(L0.A.view(), n, h->Binv);
+    dim3 g2(cdiv(n, 256), n);
+    for (int k = 0; k < n; k++) {
+        k_gj_pivot<<<cdiv(n, 256), 256, 0, h->stream>>>(n, k, h->Binv, rowk, colk);
+        k_gj_update<<<g2, 256, 0, h->stream>>>(n, k, h->Binv, rowk, colk);
+    }
+    k_symmetrize<<<g2, 256, 0, h->stream>>>(n, h->Binv);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    cudaFree(rowk);
+    cudaFree(colk);
+    return 0;
+}
+
+// ==========================================================================================
+extern "C" {
+
+const char *ddpca_last_error(void) { return g_err.c_str(); }
+int ddpca_abi_version(void) { return DDPCA_ABI_VERSION; }
+int ddpca_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+struct ddpca_plan { LevelPlan p; };
+
+int ddpca_plan_create(int n, const int *rowptr, const int *colidx, int smoother_mode, ddpca_plan **out)
+{
+    if (!out || !rowptr || !colidx || n < 0) return fail("ddpca_plan_create: bad argument");
+    ddpca_plan *pl = new ddpca_plan();
+    std::string err;
+    if (!build_level_plan(n, rowptr, colidx, smoother_mode, pl->p, err)) { delete pl; return fail(err); }
+    *out = pl;
+    return 0;
+}
+int ddpca_plan_sizes(const ddpca_plan *p, int *n, int *ngroups, int *nstages)
+{
+    if (!p) return fail("null plan");
+    if (n) *n = p->p.n;
+    if (ngroups) *ngroups = p->p.ngroups();
+    if (nstages) *nstages = p->p.nstages();
+    return 0;
+}
+int ddpca_plan_get(const ddpca_plan *p, int *perm, int *group_start, int *stage_start)
+{
+    if (!p) return fail("null plan");
+    if (perm) std::memcpy(perm, p->p.perm.data(), sizeof(int) * p->p.n);
+    if (group_start) std::memcpy(group_start, p->p.group_start.data(), sizeof(int) * p->p.group_start.size());
+    if (stage_start)
+        for (int s = 0; s <= p->p.nstages(); s++) stage_start[s] = p->p.group_start[p->p.stage_group[s]];
+    return 0;
+}
+int ddpca_plan_destroy(ddpca_plan *p) { delete p; return 0; }
+
+int ddpca_mg_destroy(ddpca_mg *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    for (auto &L : h->lev) {
+        free_csr(L.A); free_csr(L.P); free_csr(L.R);
+        cudaFree(L.dpos); cudaFree(L.gstart); cudaFree(L.stage_group); cudaFree(L.perm);
+        cudaFree(L.x); cudaFree(L.b); cudaFree(L.p1); cudaFree(L.r); cudaFree(L.dinv);
+    }
+    cudaFree(h->Binv);
+    cudaFree(h->cg_r); cudaFree(h->cg_p); cudaFree(h->cg_q); cudaFree(h->cg_z); cudaFree(h->cg_x);
+    cudaFree(h->stage_a); cudaFree(h->stage_b);
+    cudaFree(h->st);
+    if (h->st_host) cudaFreeHost(h->st_host);
+    for (int k = 0; k < 3; k++) cudaFree(h->partial[k]);
+    for (int k = 0; k < 2; k++) if (h->iter_graph[k]) cudaGraphExecDestroy(h->iter_graph[k]);
+    for (int k = 0; k < 4; k++) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 0;
+}
+
+int ddpca_mg_create(int device, int nlevels, const int *n, const int *const *rowptr, const int *const *colidx,
+                    const double *const *val, const int *const *P_rowptr, const int *const *P_colidx,
+                    const double *const *P_val, int smoother_mode, ddpca_mg **out)
+{
+    if (!out || nlevels < 1 || nlevels > 16 || !n || !rowptr || !colidx || !val) return fail("ddpca_mg_create: bad argument");
+    if (smoother_mode != DDPCA_SMOOTH_LEX && smoother_mode != DDPCA_SMOOTH_MC) return fail("unknown smoother mode");
+    int ndev = ddpca_device_count();
+    if (ndev == 0) return fail("no CUDA device: libddpca_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("device index out of range");
+    CU(cudaSetDevice(device));
+    ddpca_mg *h = new ddpca_mg();
+    std::memset(h->prof_ms, 0, sizeof(h->prof_ms));
+    std::memset(h->prof_n, 0, sizeof(h->prof_n));
+    std::memset(h->prof_bytes, 0, sizeof(h->prof_bytes));
+    h->device = device;
+    h->mode = smoother_mode;
+    h->nlev = nlevels;
+    h->lev.resize(nlevels);
+    cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
+#define FAILC(expr) do { if (expr) { ddpca_mg_destroy(h); return 1; } } while (0)
+#define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); ddpca_mg_destroy(h); return 1; } } while (0)
+    CUC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    for (int k = 0; k < 4; k++) CUC(cudaEventCreate(&h->ev[k]));
+    int nmax = 0;
+    for (int l = 0; l < nlevels; l++) {
+        Level &L = h->lev[l];
+        L.n = n[l];
+        nmax = std::max(nmax, n[l]);
+        std::string err;
+        int mode = (l == 0 && nlevels > 1) ? -1 : smoother_mode;
+        if (l == 0 && nlevels == 1) mode = -1;
+        if (!build_level_plan(n[l], rowptr[l], colidx[l], mode, L.plan, err)) {
+            g_err = "level " + std::to_string(l) + ": " + err;
+            ddpca_mg_destroy(h);
+            return 1;
+        }
+        CsrHost Ap;
+        permute_csr(n[l], n[l], rowptr[l], colidx[l], val[l], L.plan.perm, L.plan.iperm, Ap);
+        L.nnz = Ap.nnz();
+        std::vector<int> dpos(n[l]);
+        long nlow = 0;
+        for (int i = 0; i < n[l]; i++) {
+            int p = (int)(std::lower_bound(Ap.ci.begin() + Ap.rp[i], Ap.ci.begin() + Ap.rp[i + 1], i) - Ap.ci.begin());
+            if (p >= Ap.rp[i + 1] || Ap.ci[p] != i) { g_err = "missing diagonal"; ddpca_mg_destroy(h); return 1; }
+            dpos[i] = p;
+            nlow += p - Ap.rp[i];
+        }
+        L.nnz_lower = nlow;
+        if (mode >= 0) build_segments(L, Ap.rp, dpos);
+        FAILC(upload_csr(Ap, L.A));
+        FAILC(upload_vec(dpos, &L.dpos));
+        FAILC(upload_vec(L.plan.group_start, &L.gstart));
+        FAILC(upload_vec(L.plan.stage_group, &L.stage_group));
+        FAILC(upload_vec(L.plan.perm, &L.perm));
+        CUC(cudaMalloc(&L.x, sizeof(double) * std::max(1, n[l])));
+        CUC(cudaMalloc(&L.b, sizeof(double) * std::max(1, n[l])));
+        CUC(cudaMalloc(&L.p1, sizeof(double) * std::max(1, n[l])));
+        CUC(cudaMalloc(&L.r, sizeof(double) * std::max(1, n[l])));
+        if (l >= 1) {
+            if (!P_rowptr || !P_colidx || !P_val) { g_err = "prolongation operators missing"; ddpca_mg_destroy(h); return 1; }
+            CsrHost Pp, Rp;
+            // realProl[l-1]: n_l x n_{l-1}; rows follow level l's permutation, columns level l-1's
+            permute_csr(n[l], n[l - 1], P_rowptr[l - 1], P_colidx[l - 1], P_val[l - 1], L.plan.perm, h->lev[l - 1].plan.iperm, Pp);
+            transpose_csr(Pp, Rp);
+            FAILC(upload_csr(Pp, L.P));
+            FAILC(upload_csr(Rp, L.R));
+        }
+    }
+    CUC(cudaMalloc(&h->cg_r, sizeof(double) * nmax));
+    CUC(cudaMalloc(&h->cg_p, sizeof(double) * nmax));
+    CUC(cudaMalloc(&h->cg_q, sizeof(double) * nmax));
+    CUC(cudaMalloc(&h->cg_z, sizeof(double) * nmax));
+    CUC(cudaMalloc(&h->cg_x, sizeof(double) * nmax));
+    CUC(cudaMalloc(&h->stage_a, sizeof(double) * nmax));
+    CUC(cudaMalloc(&h->stage_b, sizeof(double) * nmax));
+    CUC(cudaMalloc(&h->st, sizeof(PcgState)));
+    CUC(cudaMemset(h->st, 0, sizeof(PcgState)));
+    CUC(cudaMallocHost(&h->st_host, sizeof(PcgState) * (kDepth + 2)));
+    for (int k = 0; k < 3; k++) CUC(cudaMalloc(&h->partial[k], sizeof(double) * kNumPart));
+    FAILC(invert_level0(h));
+#undef FAILC
+#undef CUC
+    *out = h;
+    return 0;
+}
+
+int ddpca_mg_set_stream(ddpca_mg *h, void *stream)
+{
+    if (!h) return fail("null handle");
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return 0;
+}
+
+int ddpca_mg_pcg_dev(ddpca_mg *h, int prec, const double *b_dev, double *x_dev, double rel_tol, long maxit,
+                     long *iters, double *resid, double *tol_abs)
+{
+    if (!h || !b_dev || !x_dev) return fail("ddpca_mg_pcg_dev: bad argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    if (pcg_device(h, prec, b_dev, x_dev, rel_tol, maxit, iters, resid, tol_abs)) return 1;
+    CU(cudaEventRecord(h->ev[1], h->stream));
+    CU(cudaEventSynchronize(h->ev[1]));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    h->t_solve = ms; h->t_h2d = 0; h->t_d2h = 0;
+    return 0;
+}
+
+int ddpca_mg_pcg(ddpca_mg *h, int prec, const double *b, double *x, double rel_tol, long maxit, long *iters,
+                 double *resid, double *tol_abs)
+{
+    if (!h || !b || !x) return fail("ddpca_mg_pcg: bad argument");
+    CU(cudaSetDevice(h->device));
+    int n = h->lev[h->nlev - 1].n;
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    CU(cudaMemcpyAsync(h->stage_a, b, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaEventRecord(h->ev[1], h->stream));
+    if (pcg_device(h, prec, h->stage_a, h->stage_b, rel_tol, maxit, iters, resid, tol_abs)) return 1;
+    CU(cudaEventRecord(h->ev[2], h->stream));
+    CU(cudaMemcpyAsync(x, h->stage_b, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev[3], h->stream));
+    CU(cudaEventSynchronize(h->ev[3]));
+    float a = 0, s = 0, d = 0;
+    cudaEventElapsedTime(&a, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&s, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&d, h->ev[2], h->ev[3]);
+    h->t_h2d = a; h->t_solve = s; h->t_d2h = d;
+    return 0;
+}
+
+// helper for the single-operator entry points: host vector(s) in reference numbering of
+// level `lin` -> device numbering, run, result of level `lout` back
+static int to_dev(ddpca_mg *h, int l, const double *host, double *dev_perm)
+{
+    Level &L = h->lev[l];
+    CU(cudaMemcpyAsync(h->stage_a, host, sizeof(double) * L.n, cudaMemcpyHostToDevice, h->stream));
+    k_gather<<<cdiv(L.n, 256), 256, 0, h->stream>>>(L.n, L.perm, h->stage_a, dev_perm);
+    return 0;
+}
+static int to_host(ddpca_mg *h, int l, const double *dev_perm, double *host)
+{
+    Level &L = h->lev[l];
+    k_scatter<<<cdiv(L.n, 256), 256, 0, h->stream>>>(L.n, L.perm, dev_perm, h->stage_b);
+    CU(cudaMemcpyAsync(host, h->stage_b, sizeof(double) * L.n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ddpca_mg_vcycle(ddpca_mg *h, int level, const double *b, double *x)
+{
+    if (!h || level < 0 || level >= h->nlev || !b || !x) return fail("ddpca_mg_vcycle: bad argument");
+    CU(cudaSetDevice(h->device));
+    // use cg_r / cg_z as the top-level b / x so that lev[level].b/x stay free for the recursion
+    if (to_dev(h, level, b, h->cg_r)) return 1;
+    if (to_dev(h, level, x, h->cg_z)) return 1;
+    vcycle_dev(h, level, h->cg_r, h->cg_z, false, nullptr);
+    if (h->profile) h->prof_collect();
+    return to_host(h, level, h->cg_z, x);
+}
+
+int ddpca_mg_spmv(ddpca_mg *h, int level, const double *x, double *y)
+{
+    if (!h || level < 0 || level >= h->nlev || !x || !y) return fail("ddpca_mg_spmv: bad argument");
+    CU(cudaSetDevice(h->device));
+    if (to_dev(h, level, x, h->cg_p)) return 1;
+    launch_spmv(h, DDPCA_K_SPMV, level, h->lev[level].A, h->cg_p, h->cg_q, false, nullptr, nullptr, nullptr);
+    if (h->profile) h->prof_collect();
+    return to_host(h, level, h->cg_q, y);
+}
+
+int ddpca_mg_restrict(ddpca_mg *h, int level, const double *r_fine, double *r_coarse)
+{
+    if (!h || level < 0 || level + 1 >= h->nlev || !r_fine || !r_coarse) return fail("ddpca_mg_restrict: bad argument");
+    CU(cudaSetDevice(h->device));
+    if (to_dev(h, level + 1, r_fine, h->cg_p)) return 1;
+    launch_spmv(h, DDPCA_K_RESTRICT, level + 1, h->lev[level + 1].R, h->cg_p, h->cg_q, false, nullptr, nullptr, nullptr);
+    if (h->profile) h->prof_collect();
+    return to_host(h, level, h->cg_q, r_coarse);
+}
+
+int ddpca_mg_prolong_add(ddpca_mg *h, int level, const double *e_coarse, double *x_fine)
+{
+    if (!h || level < 0 || level + 1 >= h->nlev || !e_coarse || !x_fine) return fail("ddpca_mg_prolong_add: bad argument");
+    CU(cudaSetDevice(h->device));
+    if (to_dev(h, level, e_coarse, h->cg_p)) return 1;
+    if (to_dev(h, level + 1, x_fine, h->cg_q)) return 1;
+    launch_spmv(h, DDPCA_K_PROLONG, level + 1, h->lev[level + 1].P, h->cg_p, h->cg_q, true, nullptr, nullptr, nullptr);
+    if (h->profile) h->prof_collect();
+    return to_host(h, level + 1, h->cg_q, x_fine);
+}
+
+int ddpca_mg_coarse_solve(ddpca_mg *h, const double *b, double *x)
+{
+    if (!h || !b || !x) return fail("ddpca_mg_coarse_solve: bad argument");
+    CU(cudaSetDevice(h->device));
+    if (to_dev(h, 0, b, h->cg_p)) return 1;
+    vcycle_dev(h, 0, h->cg_p, h->cg_q, true, nullptr);
+    if (h->profile) h->prof_collect();
+    return to_host(h, 0, h->cg_q, x);
+}
+
+int ddpca_mg_mult_solv(ddpca_mg *, const double *, double *, long *, double *) { return fail("ddpca_mg_mult_solv: not implemented yet"); }
+int ddpca_mg_bicgstab(ddpca_mg *, int, const double *, double *, double, long, long *, double *, double *) { return fail("ddpca_mg_bicgstab: not implemented yet"); }
+
+int ddpca_mg_level_info(const ddpca_mg *h, int level, long *n, long *nnz, int *ngroups, int *nstages)
+{
+    if (!h || level < 0 || level >= h->nlev) return fail("ddpca_mg_level_info: bad argument");
+    const Level &L = h->lev[level];
+    if (n) *n = L.n;
+    if (nnz) *nnz = L.nnz;
+    if (ngroups) *ngroups = L.plan.ngroups();
+    if (nstages) *nstages = L.plan.nstages();
+    return 0;
+}
+long ddpca_mg_launch_count(ddpca_mg *h, int reset)
+{
+    if (!h) return -1;
+    long v = h->launches;
+    if (reset) h->launches = 0;
+    return v;
+}
+int ddpca_mg_profile(ddpca_mg *h, int enable)
+{
+    if (!h) return fail("null handle");
+    h->profile = enable != 0;
+    if (enable) {
+        std::memset(h->prof_ms, 0, sizeof(h->prof_ms));
+        std::memset(h->prof_n, 0, sizeof(h->prof_n));
+        std::memset(h->prof_bytes, 0, sizeof(h->prof_bytes));
+    }
+    return 0;
+}
+int ddpca_mg_profile_get(ddpca_mg *h, int kclass, int level, double *ms, long *launches, double *bytes)
+{
+    if (!h || kclass < 0 || kclass >= DDPCA_K_COUNT || level < 0 || level >= 16) return fail("ddpca_mg_profile_get: bad argument");
+    if (ms) *ms = h->prof_ms[kclass][level];
+    if (launches) *launches = h->prof_n[kclass][level];
+    if (bytes) *bytes = h->prof_bytes[kclass][level];
+    return 0;
+}
+int ddpca_mg_last_timing(ddpca_mg *h, double *solve_ms, double *h2d_ms, double *d2h_ms)
+{
+    if (!h) return fail("null handle");
+    if (solve_ms) *solve_ms = h->t_solve;
+    if (h2d_ms) *h2d_ms = h->t_h2d;
+    if (d2h_ms) *d2h_ms = h->t_d2h;
+    return 0;
+}
+
+}  // extern "C"

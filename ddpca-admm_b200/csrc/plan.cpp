@@ -1,0 +1,198 @@
+// plan.cpp -- see plan.h.  Pure host C++, no CUDA.
+#include "plan.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace ddpca {
+
+static const int kMaxGroup = 3;
+
+bool build_level_plan(int n, const int *rp, const int *ci, int mode, LevelPlan &out, std::string &err)
+{
+    out = LevelPlan();
+    out.n = n;
+    if (mode < 0) {
+        out.perm.resize(n);
+        std::iota(out.perm.begin(), out.perm.end(), 0);
+        out.iperm = out.perm;
+        out.group_start.resize(n + 1);
+        std::iota(out.group_start.begin(), out.group_start.end(), 0);
+        out.stage_group = {0, n};
+        return true;
+    }
+    // ---- 0. sanity: sorted columns, diagonal present -------------------------------
+    for (int i = 0; i < n; i++) {
+        bool diag = false;
+        for (int p = rp[i]; p < rp[i + 1]; p++) {
+            if (p > rp[i] && ci[p] <= ci[p - 1]) { err = "columns not strictly increasing in row " + std::to_string(i); return false; }
+            if (ci[p] < 0 || ci[p] >= n) { err = "column index out of range in row " + std::to_string(i); return false; }
+            if (ci[p] == i) diag = true;
+        }
+        if (!diag) { err = "no diagonal entry in row " + std::to_string(i) + " (Gauss-Seidel needs one)"; return false; }
+    }
+    // ---- 1. groups: consecutive rows with one column pattern, at most 3 ------------
+    std::vector<int> gfirst;   // first OLD row of each group
+    std::vector<int> gid(n);   // group of each OLD row
+    for (int i = 0; i < n;) {
+        int len = rp[i + 1] - rp[i];
+        int j = i + 1;
+        while (j < n && j - i < kMaxGroup && rp[j + 1] - rp[j] == len &&
+               std::memcmp(ci + rp[i], ci + rp[j], sizeof(int) * len) == 0)
+            j++;
+        // every row of the group holds its own diagonal, hence (identical patterns) all
+        // in-group columns i..j-1 are present in each row.
+        for (int k = i; k < j; k++) gid[k] = (int)gfirst.size();
+        gfirst.push_back(i);
+        i = j;
+    }
+    int ng = (int)gfirst.size();
+    gfirst.push_back(n);
+    // ---- 2. group graph (from the first row of each group), symmetrised ------------
+    std::vector<int> adj_ptr(ng + 1, 0);
+    std::vector<int> adj;
+    // direct adjacency: columns are sorted and groups are contiguous, so the group ids met
+    // along a row are non-decreasing and de-duplicate by comparing with the previous one.
+    for (int g = 0; g < ng; g++) {
+        int i = gfirst[g];
+        int last = -1, cnt = 0;
+        for (int p = rp[i]; p < rp[i + 1]; p++) {
+            int h = gid[ci[p]];
+            if (h != last) { last = h; if (h != g) cnt++; }
+        }
+        adj_ptr[g + 1] = adj_ptr[g] + cnt;
+    }
+    adj.resize(adj_ptr[ng]);
+    for (int g = 0; g < ng; g++) {
+        int i = gfirst[g];
+        int last = -1, q = adj_ptr[g];
+        for (int p = rp[i]; p < rp[i + 1]; p++) {
+            int h = gid[ci[p]];
+            if (h != last) { last = h; if (h != g) adj[q++] = h; }
+        }
+    }
+    // FE stiffness patterns are structurally symmetric; verify, and only symmetrise if not.
+    bool symmetric = true;
+    for (int g = 0; g < ng && symmetric; g++)
+        for (int p = adj_ptr[g]; p < adj_ptr[g + 1]; p++) {
+            int h = adj[p];
+            if (!std::binary_search(adj.begin() + adj_ptr[h], adj.begin() + adj_ptr[h + 1], g)) { symmetric = false; break; }
+        }
+    if (!symmetric) {
+        std::vector<std::pair<int, int>> edges;  // (g,h), g != h
+        edges.reserve(adj.size() * 2);
+        for (int g = 0; g < ng; g++)
+            for (int p = adj_ptr[g]; p < adj_ptr[g + 1]; p++) { edges.emplace_back(g, adj[p]); edges.emplace_back(adj[p], g); }
+        std::fill(adj_ptr.begin(), adj_ptr.end(), 0);
+        std::sort(edges.begin(), edges.end());
+        edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+        for (auto &e : edges) adj_ptr[e.first + 1]++;
+        for (int g = 0; g < ng; g++) adj_ptr[g + 1] += adj_ptr[g];
+        adj.resize(edges.size());
+        std::vector<int> fill(adj_ptr.begin(), adj_ptr.end() - 1);
+        for (auto &e : edges) adj[fill[e.first]++] = e.second;
+    }
+    // ---- 3. stage of each group ----------------------------------------------------
+    std::vector<int> stage(ng, 0);
+    int nstages = 0;
+    if (mode == 0) {
+        // LEX: wavefront level in the reference ordering
+        for (int g = 0; g < ng; g++) {
+            int lv = 0;
+            for (int p = adj_ptr[g]; p < adj_ptr[g + 1]; p++) {
+                int h = adj[p];
+                if (h < g) lv = std::max(lv, stage[h] + 1);
+            }
+            stage[g] = lv;
+            nstages = std::max(nstages, lv + 1);
+        }
+    } else {
+        // MC: greedy colouring in the reference ordering (smallest colour unused by neighbours)
+        std::vector<int> mark;
+        for (int g = 0; g < ng; g++) {
+            int deg = adj_ptr[g + 1] - adj_ptr[g];
+            if ((int)mark.size() < deg + 2) mark.resize(deg + 2, -1);
+            for (int p = adj_ptr[g]; p < adj_ptr[g + 1]; p++) {
+                int h = adj[p];
+                if (h < g && stage[h] <= deg) mark[stage[h]] = g;
+            }
+            int c = 0;
+            while (c <= deg && mark[c] == g) c++;
+            stage[g] = c;
+            nstages = std::max(nstages, c + 1);
+        }
+    }
+    // ---- 4. order groups by (stage, reference order): counting sort -----------------
+    out.stage_group.assign(nstages + 1, 0);
+    for (int g = 0; g < ng; g++) out.stage_group[stage[g] + 1]++;
+    for (int s = 0; s < nstages; s++) out.stage_group[s + 1] += out.stage_group[s];
+    std::vector<int> gorder(ng);
+    {
+        std::vector<int> fill(out.stage_group.begin(), out.stage_group.end() - 1);
+        for (int g = 0; g < ng; g++) gorder[fill[stage[g]]++] = g;
+    }
+    out.perm.resize(n);
+    out.iperm.resize(n);
+    out.group_start.resize(ng + 1);
+    int row = 0;
+    for (int k = 0; k < ng; k++) {
+        int g = gorder[k];
+        out.group_start[k] = row;
+        for (int i = gfirst[g]; i < gfirst[g + 1]; i++) {
+            out.perm[row] = i;
+            out.iperm[i] = row;
+            row++;
+        }
+    }
+    out.group_start[ng] = n;
+    return true;
+}
+
+void permute_csr(int rows, int cols, const int *rp, const int *ci, const double *v,
+                 const std::vector<int> &prow, const std::vector<int> &icol, CsrHost &out)
+{
+    (void)cols;
+    out.rows = rows;
+    out.cols = (int)icol.size();
+    out.rp.assign(rows + 1, 0);
+    for (int i = 0; i < rows; i++) out.rp[i + 1] = out.rp[i] + (rp[prow[i] + 1] - rp[prow[i]]);
+    long nnz = out.rp[rows];
+    out.ci.resize(nnz);
+    out.v.resize(nnz);
+#pragma omp parallel
+    {
+        std::vector<std::pair<int, double>> tmp;
+#pragma omp for schedule(dynamic, 1024)
+        for (int i = 0; i < rows; i++) {
+            int o = prow[i];
+            int len = rp[o + 1] - rp[o];
+            tmp.resize(len);
+            for (int k = 0; k < len; k++) tmp[k] = {icol[ci[rp[o] + k]], v[rp[o] + k]};
+            std::sort(tmp.begin(), tmp.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; });
+            int base = out.rp[i];
+            for (int k = 0; k < len; k++) { out.ci[base + k] = tmp[k].first; out.v[base + k] = tmp[k].second; }
+        }
+    }
+}
+
+void transpose_csr(const CsrHost &A, CsrHost &out)
+{
+    out.rows = A.cols;
+    out.cols = A.rows;
+    out.rp.assign(A.cols + 1, 0);
+    long nnz = A.nnz();
+    for (long p = 0; p < nnz; p++) out.rp[A.ci[p] + 1]++;
+    for (int j = 0; j < A.cols; j++) out.rp[j + 1] += out.rp[j];
+    out.ci.resize(nnz);
+    out.v.resize(nnz);
+    std::vector<int> fill(out.rp.begin(), out.rp.end() - 1);
+    for (int i = 0; i < A.rows; i++)
+        for (int p = A.rp[i]; p < A.rp[i + 1]; p++) {
+            int q = fill[A.ci[p]]++;
+            out.ci[q] = i;   // rows visited in increasing order => sorted columns
+            out.v[q] = A.v[p];
+        }
+}
+
+}  // namespace ddpca

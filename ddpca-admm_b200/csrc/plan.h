@@ -1,0 +1,56 @@
+// plan.h -- host-side planning of one multigrid level's device layout.
+//
+// The reference smooths with lexicographic symmetric Gauss-Seidel
+// (MGPIS.h:65-77): row i of the forward sweep needs every coupled row j < i.
+// On the GPU a level is therefore split into STAGES: sets of row GROUPS that
+// have no coupling between them and can be relaxed in parallel; stages run in
+// sequence.  A GROUP is a run of <= 3 consecutive rows sharing one column
+// pattern (the DOFs of one mesh node, MULTIGRID.h:1170-1176) and is relaxed
+// sequentially by one warp, in row order.
+//
+//   LEX : stage = wavefront of the dependency DAG of the reference ordering;
+//         the arithmetic is the reference's, row for row.
+//   MC  : stage = colour of a greedy colouring of the group graph; this is the
+//         same algorithm applied to a symmetric permutation of the level.
+//
+// In both modes the level is then permuted symmetrically so that every stage
+// is a contiguous row range (perm[new] = old); within a stage groups keep
+// their original relative order, so strictly-lower / strictly-upper parts of
+// the permuted operator are exactly the coupled-earlier / coupled-later sets.
+#pragma once
+#include <string>
+#include <vector>
+
+namespace ddpca {
+
+struct CsrHost {
+    int rows = 0, cols = 0;
+    std::vector<int> rp, ci;
+    std::vector<double> v;
+    long nnz() const { return (long)ci.size(); }
+};
+
+struct LevelPlan {
+    int n = 0;
+    std::vector<int> perm;         // perm[new] = old
+    std::vector<int> iperm;        // iperm[old] = new
+    std::vector<int> group_start;  // [ngroups+1] first NEW row of each group
+    std::vector<int> stage_group;  // [nstages+1] first group of each stage
+    int ngroups() const { return (int)group_start.size() - 1; }
+    int nstages() const { return (int)stage_group.size() - 1; }
+};
+
+// Build the plan from the sparsity pattern alone.  mode: 0 LEX, 1 MC, -1 identity
+// (no smoothing on this level: one stage, groups of one row, perm = identity).
+// Returns false and fills err on malformed input (unsorted columns, missing diagonal).
+bool build_level_plan(int n, const int *rp, const int *ci, int mode, LevelPlan &out, std::string &err);
+
+// B = Pr * A * Pc^T with sorted columns: row `i` of B is row prow[i] of A, column j of A
+// becomes icol[j].  prow has B.rows entries, icol has A.cols entries.
+void permute_csr(int rows, int cols, const int *rp, const int *ci, const double *v,
+                 const std::vector<int> &prow, const std::vector<int> &icol, CsrHost &out);
+
+// out = A^T (sorted columns)
+void transpose_csr(const CsrHost &A, CsrHost &out);
+
+}  // namespace ddpca

@@ -1,0 +1,55 @@
+"""ctypes binding of include/ddpca_b200.h (the drop-in C ABI)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class DdpcaError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(_HERE), "lib", "libddpca_b200.so")
+
+
+# every symbol include/ddpca_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "ddpca_last_error", "ddpca_abi_version", "ddpca_device_count",
+    "ddpca_plan_create", "ddpca_plan_sizes", "ddpca_plan_get", "ddpca_plan_destroy",
+    "ddpca_mg_create", "ddpca_mg_destroy", "ddpca_mg_pcg", "ddpca_mg_pcg_dev",
+    "ddpca_mg_vcycle", "ddpca_mg_spmv", "ddpca_mg_restrict", "ddpca_mg_prolong_add",
+    "ddpca_mg_coarse_solve", "ddpca_mg_mult_solv", "ddpca_mg_bicgstab",
+    "ddpca_mg_level_info", "ddpca_mg_launch_count", "ddpca_mg_set_stream",
+    "ddpca_mg_profile", "ddpca_mg_profile_get", "ddpca_mg_last_timing",
+]
+
+
+def load_library() -> C.CDLL:
+    """Load libddpca_b200.so; raises (never falls back) if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise DdpcaError(
+            f"{path} is missing: build it with `make -C ddpca-admm_b200` "
+            "(or __graft_entry__.build()); there is no CPU fallback"
+        )
+    lib = C.CDLL(path)
+    lib.ddpca_last_error.restype = C.c_char_p
+    lib.ddpca_mg_launch_count.restype = C.c_long
+    _LIB = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise DdpcaError(load_library().ddpca_last_error().decode())
+
+
+def device_count() -> int:
+    return int(load_library().ddpca_device_count())

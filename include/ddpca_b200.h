@@ -1,0 +1,129 @@
+/*
+ * ddpca_b200.h -- C ABI of libddpca_b200.so: the B200 (sm_100a, FP64) hot path of
+ * DDPCA-ADMM behind plain pointers and sizes.
+ *
+ * The reference has no FFI today: the path is header-inline C++ (class MGPIS,
+ * MGPIS.h:8-38; MCONTACT::CONTACT_ANALYSIS, MCONTACT.h:2493-2723).  Each entry
+ * point below names the reference interface it replaces; the C++ overlay in
+ * ddpca-admm_b200/host/ forwards the reference's own class surface to these
+ * calls.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from ddpca_last_error() (thread-local).  There is NO CPU
+ *     fallback: without a CUDA device every compute call fails.
+ *   - sparse operators are Eigen RowMajor compressed storage
+ *     (SparseMatrix<double,RowMajor>::outerIndexPtr/innerIndexPtr/valuePtr):
+ *     int32 rowptr[rows+1], int32 colidx[nnz] sorted inside a row, double val[nnz].
+ *   - pointers are HOST pointers unless the function name ends in _dev.
+ *   - a handle is bound to one device and owns one non-blocking stream; calls
+ *     on different handles may run concurrently from different host threads
+ *     (the reference calls CG_SOLV from inside an OpenMP loop, MCONTACT.h:2511-2532).
+ */
+#ifndef DDPCA_B200_H
+#define DDPCA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDPCA_ABI_VERSION 1
+
+/* Smoother ordering of the multigrid V-cycle.
+ * LEX: the reference's lexicographic symmetric Gauss-Seidel (MGPIS.h:65-77),
+ *      reproduced exactly by wavefront scheduling -- parity / debug mode.
+ * MC : the same symmetric Gauss-Seidel algebra applied after a multicolour
+ *      symmetric permutation of each level -- throughput mode; same fixed
+ *      point, different (still SPD) preconditioner. */
+enum { DDPCA_SMOOTH_LEX = 0, DDPCA_SMOOTH_MC = 1 };
+
+/* kernel classes, for ddpca_mg_profile() / ddpca_mg_bench_kernel() */
+enum {
+    DDPCA_K_SPMV = 0,      /* K1  y = A x                       MGPIS.h:200        */
+    DDPCA_K_SWEEP_FWD = 1, /* K3  forward  Gauss-Seidel sweep   MGPIS.h:66-72      */
+    DDPCA_K_SWEEP_BWD = 2, /* K4  backward Gauss-Seidel sweep   MGPIS.h:73-76      */
+    DDPCA_K_RESID = 3,     /* K2  r = b - (p1 + L x)            MGPIS.h:92         */
+    DDPCA_K_RESTRICT = 4,  /* K5  r_c = P^T r                   MGPIS.h:96         */
+    DDPCA_K_PROLONG = 5,   /* K6  x += P e                      MGPIS.h:100        */
+    DDPCA_K_COARSE = 6,    /* K7  x0 = A0^-1 b0                 MGPIS.h:58         */
+    DDPCA_K_VECTOR = 7,    /* K8  axpy / dot / norm             MGPIS.h:197-214    */
+    DDPCA_K_COUNT = 8
+};
+
+typedef struct ddpca_mg ddpca_mg;
+typedef struct ddpca_plan ddpca_plan;
+
+const char *ddpca_last_error(void);
+int ddpca_abi_version(void);
+/* number of visible CUDA devices (0 when there is none; never fails) */
+int ddpca_device_count(void);
+
+/* ---- host-side planning (no GPU needed) ------------------------------------
+ * The per-level reordering the device uses: row groups (rows of one mesh node
+ * share a column pattern), stages (sets of mutually independent groups) and the
+ * symmetric permutation that makes every stage a contiguous row range.
+ * Exposed so that the ordering can be inspected and tested on a CPU-only box. */
+int ddpca_plan_create(int n, const int *rowptr, const int *colidx, int smoother_mode, ddpca_plan **out);
+int ddpca_plan_sizes(const ddpca_plan *, int *n, int *ngroups, int *nstages);
+/* perm[new] = old ; group_start[ngroups+1] and stage_start[nstages+1] are in NEW row numbering */
+int ddpca_plan_get(const ddpca_plan *, int *perm, int *group_start, int *stage_start);
+int ddpca_plan_destroy(ddpca_plan *);
+
+/* ---- MGPIS: multigrid hierarchy + solvers ----------------------------------
+ * ddpca_mg_create replaces MGPIS::ESTABLISH (MGPIS.h:40-53) plus the
+ * direSolv.compute(consStif[0]) that CG_SOLV repeats on every call (MGPIS.h:185):
+ * it uploads consStif[0..nlevels-1] and realProl[0..nlevels-2], builds the
+ * diagonal split, the stage schedule and the level-0 direct solver on `device`. */
+int ddpca_mg_create(int device, int nlevels, const int *n,
+                    const int *const *rowptr, const int *const *colidx, const double *const *val,
+                    const int *const *P_rowptr, const int *const *P_colidx, const double *const *P_val,
+                    int smoother_mode, ddpca_mg **out);
+int ddpca_mg_destroy(ddpca_mg *);
+
+/* MGPIS::CG_SOLV(precSwit, totaForc, resuSolu), MGPIS.h:163-225.
+ * prec 0 = Jacobi (DIAG_PREC, PREP.h:393-401), 1 = one V-cycle.  x0 = 0,
+ * stop when it >= maxit or ||r||_2 <= rel_tol*||b||_2 (reference: 1e-14, n).
+ * iters = the reference's iterNumb (it prints iterNumb-1).  b, x: host, length n_L. */
+int ddpca_mg_pcg(ddpca_mg *, int prec, const double *b, double *x, double rel_tol, long maxit,
+                 long *iters, double *resid, double *tol_abs);
+/* same, operands resident in HBM on the handle's device (reference numbering) */
+int ddpca_mg_pcg_dev(ddpca_mg *, int prec, const double *b_dev, double *x_dev, double rel_tol, long maxit,
+                     long *iters, double *resid, double *tol_abs);
+
+/* MGPIS::MULT_VCYC(level, righHand, resuSolu, direSolv), MGPIS.h:55-128; x is in/out */
+int ddpca_mg_vcycle(ddpca_mg *, int level, const double *b, double *x);
+/* consStif[level] * x, MGPIS.h:189,200 */
+int ddpca_mg_spmv(ddpca_mg *, int level, const double *x, double *y);
+/* realProl[level]^T * r  (n_{level+1} -> n_level), MGPIS.h:96 */
+int ddpca_mg_restrict(ddpca_mg *, int level, const double *r_fine, double *r_coarse);
+/* x_fine += realProl[level] * e_coarse, MGPIS.h:100 */
+int ddpca_mg_prolong_add(ddpca_mg *, int level, const double *e_coarse, double *x_fine);
+/* direSolv.solve(b) on consStif[0], MGPIS.h:58 */
+int ddpca_mg_coarse_solve(ddpca_mg *, const double *b, double *x);
+
+/* MGPIS::MULT_SOLV (MGPIS.h:130-160), BiCGSTAB_SOLV (:350-432): same kernels, other drivers */
+int ddpca_mg_mult_solv(ddpca_mg *, const double *b, double *x, long *iters, double *resid);
+int ddpca_mg_bicgstab(ddpca_mg *, int prec, const double *b, double *x, double rel_tol, long maxit,
+                      long *iters, double *resid, double *tol_abs);
+
+/* ---- introspection / measurement -------------------------------------------*/
+/* rows, nnz, number of row groups and stages of a level's device layout */
+int ddpca_mg_level_info(const ddpca_mg *, int level, long *n, long *nnz, int *ngroups, int *nstages);
+/* number of kernels this handle has launched since creation (or last reset) */
+long ddpca_mg_launch_count(ddpca_mg *, int reset);
+/* Run the handle on an external stream (e.g. torch's current stream), so that
+ * CUDA events recorded there bracket the work.  stream = cudaStream_t. */
+int ddpca_mg_set_stream(ddpca_mg *, void *stream);
+/* Per-kernel-class timing: when enabled, pcg/vcycle run un-captured and every
+ * launch is bracketed by CUDA events on the handle's stream. */
+int ddpca_mg_profile(ddpca_mg *, int enable);
+/* accumulated ms, launches and algorithmic bytes per class since enable */
+int ddpca_mg_profile_get(ddpca_mg *, int kclass, int level, double *ms, long *launches, double *bytes);
+/* device time of the last ddpca_mg_pcg / ddpca_mg_pcg_dev call (CUDA events on the handle's
+ * stream): solve only, and upload/download legs of the host variant */
+int ddpca_mg_last_timing(ddpca_mg *, double *solve_ms, double *h2d_ms, double *d2h_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,66 @@
+"""Shared helpers for the parity tests."""
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+from ddpca_b200 import ddpk
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref")
+
+
+def load_golden(name):
+    d = ddpk.load(os.path.join(GOLDEN, name + ".ddpk.gz"))
+    meta = json.load(open(os.path.join(GOLDEN, name + ".json")))
+    A, P = ddpk.get_hierarchy(d)
+    return d, meta, A, P
+
+
+def rel(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / (nb if nb > 0 else 1.0)
+
+
+def have_ref_binary(name="beam_nodd"):
+    return os.access(os.path.join(REF_BIN, name), os.X_OK)
+
+
+_cache = {}
+
+
+def run_ref_beam(glob, divi=None, solve=1):
+    """Run the prebuilt reference driver (oracle/_ref/beam_nodd) and load what it dumps.
+    The binary was compiled from the untouched reference; it does not need /root/reference."""
+    key = (glob, tuple(divi) if divi else None, solve)
+    if key in _cache:
+        return _cache[key]
+    tmp = tempfile.mkdtemp(prefix="ddpca_ref_")
+    out = os.path.join(tmp, "beam.ddpk")
+    cmd = [os.path.join(REF_BIN, "beam_nodd"), "--glob", str(glob), "--out", out, "--solve", str(solve)]
+    if divi:
+        cmd += ["--divi", ",".join(str(v) for v in divi)]
+    txt = subprocess.check_output(cmd, cwd=tmp).decode()
+    meta = json.loads(txt.strip().splitlines()[-1])
+    d = ddpk.load(out)
+    os.remove(out)
+    A, P = ddpk.get_hierarchy(d)
+    _cache[key] = (d, meta, A, P)
+    return _cache[key]
+
+
+def permute_hierarchy(A, P, perms):
+    """Symmetric permutation of every level: A~ = A[p][:,p], P~ = P[p_fine][:,p_coarse]
+    with p[new] = old (the device numbering of ddpca_plan_get)."""
+    As, Ps = [], []
+    for l, a in enumerate(A):
+        m = a.to_scipy()
+        p = perms[l]
+        As.append(ddpk.Csr.from_scipy(m[p][:, p]))
+    for l, pm in enumerate(P):
+        m = pm.to_scipy()
+        Ps.append(ddpk.Csr.from_scipy(m[perms[l + 1]][:, perms[l]]))
+    return As, Ps

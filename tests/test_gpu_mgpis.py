@@ -1,0 +1,188 @@
+"""GPU parity tests: libddpca_b200 (through the C ABI / the MGPIS mirror) against
+  (1) golden vectors written by the untouched reference (tests/golden, oracle/_ref),
+  (2) the CPU oracle (oracle/mgpis_oracle.c) on the same inputs.
+Tolerances: FP64; kernel-level 1e-12 relative (summation order only), anything that
+contains the level-0 direct solve 1e-9 (different but equally exact factorisation),
+solver results 1e-8 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import ddpca_b200 as dd
+from oracle import oracle as orc
+from tests.helpers import have_ref_binary, load_golden, permute_hierarchy, rel, run_ref_beam
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["beam_2lev", "beam_3lev"]
+MODES = [dd.SMOOTH_LEX, dd.SMOOTH_MC]
+
+
+@pytest.fixture(scope="module")
+def solvers():
+    cache = {}
+
+    def get(name, mode):
+        if (name, mode) not in cache:
+            d, meta, A, P = load_golden(name)
+            cache[(name, mode)] = (dd.MGPIS.from_hierarchy(A, P, smoother=mode), d, meta, A, P)
+        return cache[(name, mode)]
+
+    yield get
+    for v in cache.values():
+        v[0].close()
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("mode", MODES)
+def test_spmv_all_levels(solvers, name, mode):
+    mg, d, meta, A, P = solvers(name, mode)
+    rng = np.random.default_rng(1)
+    for l, a in enumerate(A):
+        x = rng.standard_normal(a.shape[0])
+        assert rel(mg.spmv(l, x), orc.spmv(a, x)) < 1e-13
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("mode", MODES)
+def test_transfers(solvers, name, mode):
+    mg, d, meta, A, P = solvers(name, mode)
+    rng = np.random.default_rng(2)
+    for l, p in enumerate(P):
+        pm = p.to_scipy()
+        r = rng.standard_normal(p.shape[0])
+        assert rel(mg.restrict(l, r), pm.T @ r) < 1e-13
+        e = rng.standard_normal(p.shape[1])
+        x = rng.standard_normal(p.shape[0])
+        assert rel(mg.prolong_add(l, e, x), x + pm @ e) < 1e-13
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_coarse_solve_matches_reference_ldlt(solvers, name):
+    mg, d, meta, A, P = solvers(name, dd.SMOOTH_MC)
+    x = mg.coarse_solve(d["coarse_rhs"])
+    assert rel(x, d["coarse_sol"]) < 1e-9
+    # residual of the direct solve
+    assert rel(orc.spmv(A[0], x), d["coarse_rhs"]) < 1e-10
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_vcycle_lex_matches_reference_mult_vcyc(solvers, name):
+    mg, d, meta, A, P = solvers(name, dd.SMOOTH_LEX)
+    z = mg.MULT_VCYC(len(A) - 1, d["consForc"])
+    assert rel(z, d["vcyc_of_consForc"]) < 1e-9       # the reference itself
+    assert rel(z, orc.OracleMG(A, P).vcycle(len(A) - 1, d["consForc"])) < 1e-9
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_vcycle_lex_nonzero_initial_guess_every_level(solvers, name):
+    mg, d, meta, A, P = solvers(name, dd.SMOOTH_LEX)
+    o = orc.OracleMG(A, P)
+    rng = np.random.default_rng(3)
+    for l in range(len(A)):
+        b = rng.standard_normal(A[l].shape[0])
+        x0 = rng.standard_normal(A[l].shape[0]) * 1e-12
+        assert rel(mg.MULT_VCYC(l, b, x0), o.vcycle(l, b, x0)) < 1e-9
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_vcycle_mc_is_reference_algorithm_on_permuted_levels(solvers, name):
+    """MC mode == MGPIS::MULT_VCYC applied to the colour-permuted hierarchy."""
+    mg, d, meta, A, P = solvers(name, dd.SMOOTH_MC)
+    perms = [np.arange(A[0].shape[0])] + [dd.Plan(a, dd.SMOOTH_MC).perm for a in A[1:]]
+    Ap, Pp = permute_hierarchy(A, P, perms)
+    o = orc.OracleMG(Ap, Pp)
+    L = len(A) - 1
+    b = d["consForc"]
+    z_ref = np.empty_like(b)
+    z_ref[perms[L]] = o.vcycle(L, b[perms[L]])
+    assert rel(mg.MULT_VCYC(L, b), z_ref) < 1e-9
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cg_solv_lex_matches_reference(solvers, name):
+    mg, d, meta, A, P = solvers(name, dd.SMOOTH_LEX)
+    x = mg.CG_SOLV(1, d["consForc"])
+    assert abs(mg.last_iterNumb - meta["cg_mg_iters"]) <= 1
+    assert mg.last_resid <= mg.last_tol
+    assert rel(x, d["cg_mg_x"]) < 1e-8
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cg_solv_mc_matches_reference_solution(solvers, name):
+    mg, d, meta, A, P = solvers(name, dd.SMOOTH_MC)
+    x = mg.CG_SOLV(1, d["consForc"])
+    assert mg.last_resid <= mg.last_tol
+    assert rel(x, d["cg_mg_x"]) < 1e-8
+    assert mg.last_iterNumb <= 2 * meta["cg_mg_iters"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cg_solv_jacobi(solvers, name):
+    mg, d, meta, A, P = solvers(name, dd.SMOOTH_MC)
+    x = mg.CG_SOLV(0, d["consForc"])
+    assert rel(x, d["cg_jacobi_x"]) < 1e-8
+    assert abs(mg.last_iterNumb - meta["cg_jacobi_iters"]) <= meta["cg_jacobi_iters"] // 20
+
+
+def test_zero_rhs_takes_zero_iterations(solvers):
+    """MGPIS.h:175,198: tol = 0, loop not entered, x = 0 (ADMM iteration 0 of unloaded bodies)."""
+    mg, d, meta, A, P = solvers("beam_2lev", dd.SMOOTH_MC)
+    x = mg.CG_SOLV(1, np.zeros(A[-1].shape[0]))
+    assert mg.last_iterNumb == 0 and not x.any()
+
+
+def test_maxit_caps_iterations(solvers):
+    mg, d, meta, A, P = solvers("beam_2lev", dd.SMOOTH_MC)
+    mg.CG_SOLV(1, d["consForc"], maxit=5)
+    assert mg.last_iterNumb == 5
+
+
+def test_runs_are_bit_reproducible(solvers):
+    mg, d, meta, A, P = solvers("beam_3lev", dd.SMOOTH_MC)
+    x1 = mg.CG_SOLV(1, d["consForc"]); it1 = mg.last_iterNumb
+    x2 = mg.CG_SOLV(1, d["consForc"]); it2 = mg.last_iterNumb
+    assert it1 == it2 and np.array_equal(x1, x2)
+
+
+def test_linearity_of_the_vcycle(solvers):
+    """The V-cycle is a linear operator: M(a b1 + b2) = a M b1 + M b2 (size-independent property)."""
+    mg, d, meta, A, P = solvers("beam_3lev", dd.SMOOTH_MC)
+    rng = np.random.default_rng(5)
+    n = A[-1].shape[0]
+    b1, b2 = rng.standard_normal(n), rng.standard_normal(n)
+    L = len(A) - 1
+    lhs = mg.MULT_VCYC(L, 2.5 * b1 + b2)
+    rhs = 2.5 * mg.MULT_VCYC(L, b1) + mg.MULT_VCYC(L, b2)
+    assert rel(lhs, rhs) < 1e-10
+
+
+def test_profile_mode_gives_same_answer_and_counts_kernels(solvers):
+    mg, d, meta, A, P = solvers("beam_3lev", dd.SMOOTH_MC)
+    x1 = mg.CG_SOLV(1, d["consForc"])
+    mg.launch_count(reset=True)
+    mg.profile(True)
+    x2 = mg.CG_SOLV(1, d["consForc"])
+    prof = mg.profile_get()
+    mg.profile(False)
+    assert np.array_equal(x1, x2)
+    assert mg.launch_count() > 10 * mg.last_iterNumb
+    assert ("spmv", len(A) - 1) in prof and prof[("spmv", len(A) - 1)][1] == mg.last_iterNumb
+
+
+@pytest.mark.skipif(not have_ref_binary(), reason="oracle/_ref/beam_nodd not built")
+@pytest.mark.parametrize("mode", MODES)
+def test_beam_g2_against_reference_run_here(mode):
+    """BEAM no-DD, globLeve=2 (117 504 DOF): the reference binary runs on
+    this box's CPU, the same hierarchy is solved on the GPU."""
+    d, meta, A, P = run_ref_beam(2)
+    assert meta["levels"][-1][0] == 117504 and meta["cg_mg_iters"] == 23
+    mg = dd.MGPIS.from_hierarchy(A, P, smoother=mode)
+    x = mg.CG_SOLV(1, d["consForc"])
+    assert rel(x, d["cg_mg_x"]) < 1e-8
+    if mode == dd.SMOOTH_LEX:
+        assert abs(mg.last_iterNumb - 23) <= 1
+        assert rel(mg.MULT_VCYC(len(A) - 1, d["consForc"]), d["vcyc_of_consForc"]) < 1e-9
+    # true residual as small as the reference's own
+    r = d["consForc"] - orc.spmv(A[-1], x)
+    assert np.linalg.norm(r) <= 10 * meta["true_resid"]
+    mg.close()

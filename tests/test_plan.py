@@ -1,0 +1,81 @@
+"""Host logic: the stage plan (groups / stages / permutation) the device layout is built from."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import ddpca_b200 as dd
+from ddpca_b200 import ddpk
+from tests.helpers import load_golden
+
+
+def _pattern_rows(a, i):
+    return a.colidx[a.rowptr[i] : a.rowptr[i + 1]]
+
+
+@pytest.mark.parametrize("mode", [dd.SMOOTH_LEX, dd.SMOOTH_MC])
+@pytest.mark.parametrize("name", ["beam_2lev", "beam_3lev"])
+def test_plan_is_valid(name, mode):
+    d, meta, A, P = load_golden(name)
+    for a in A:
+        n = a.shape[0]
+        pl = dd.Plan(a, mode)
+        assert sorted(pl.perm.tolist()) == list(range(n))
+        gs = pl.group_start
+        assert gs[0] == 0 and gs[-1] == n and (np.diff(gs) >= 1).all() and (np.diff(gs) <= 3).all()
+        # rows of a group are consecutive reference rows with one column pattern
+        for g in range(pl.ngroups):
+            rows = pl.perm[gs[g] : gs[g + 1]]
+            assert (np.diff(rows) == 1).all()
+            for r in rows[1:]:
+                assert np.array_equal(_pattern_rows(a, rows[0]), _pattern_rows(a, r))
+        # stages: no coupling between different groups of one stage
+        m = a.to_scipy()
+        mp = m[pl.perm][:, pl.perm].tocsr()
+        grp = np.repeat(np.arange(pl.ngroups), np.diff(gs))
+        stage_of_row = np.repeat(np.arange(pl.nstages), np.diff(pl.stage_start))
+        coo = mp.tocoo()
+        same_stage = stage_of_row[coo.row] == stage_of_row[coo.col]
+        assert (grp[coo.row][same_stage] == grp[coo.col][same_stage]).all()
+
+
+@pytest.mark.parametrize("name", ["beam_2lev", "beam_3lev"])
+def test_lex_plan_keeps_the_reference_lower_upper_split(name):
+    """LEX is a topological re-ordering: every coupled pair keeps its relative order, so
+    strictly-lower(P A P^T) == P strictly-lower(A) P^T and the sweeps are the reference's."""
+    d, meta, A, P = load_golden(name)
+    for a in A:
+        pl = dd.Plan(a, dd.SMOOTH_LEX)
+        iperm = np.empty_like(pl.perm)
+        iperm[pl.perm] = np.arange(a.shape[0], dtype=np.int32)
+        coo = a.to_scipy().tocoo()
+        lower = coo.row > coo.col
+        assert ((iperm[coo.row] > iperm[coo.col]) == lower).all()
+
+
+def test_mc_plan_uses_few_colours():
+    d, meta, A, P = load_golden("beam_3lev")
+    pl = dd.Plan(A[-1], dd.SMOOTH_MC)
+    assert pl.nstages <= 12  # 8 for a structured 27-point hexahedral stencil
+
+
+def test_plan_rejects_missing_diagonal():
+    m = sp.csr_matrix(np.array([[1.0, 2.0], [3.0, 0.0]]))
+    m.eliminate_zeros()
+    with pytest.raises(dd.DdpcaError, match="diagonal"):
+        dd.Plan(ddpk.Csr.from_scipy(m), dd.SMOOTH_MC)
+
+
+def test_plan_handles_ragged_groups():
+    """Individually constrained DOFs (BLOCK side faces, MULTIGRID.h:1188-1193) break the
+    3-row alignment: groups of 1, 2 and 3 rows must all be accepted."""
+    rng = np.random.default_rng(0)
+    d, meta, A, P = load_golden("beam_2lev")
+    m = A[-1].to_scipy()
+    keep = np.ones(m.shape[0], dtype=bool)
+    keep[rng.choice(m.shape[0], size=m.shape[0] // 7, replace=False)] = False
+    sub = m[keep][:, keep]
+    a = ddpk.Csr.from_scipy(sub)
+    for mode in (dd.SMOOTH_LEX, dd.SMOOTH_MC):
+        pl = dd.Plan(a, mode)
+        sizes = np.diff(pl.group_start)
+        assert set(sizes.tolist()) <= {1, 2, 3} and 1 in sizes and 3 in sizes
