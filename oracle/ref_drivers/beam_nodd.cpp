@@ -12,12 +12,14 @@
 //
 // usage: beam_nodd --glob G [--divi a,b,c] [--out file.ddpk] [--nomat]
 //                  [--solve 0|1] [--jacobi 0|1] [--reps R]
+//                  [--bench-steps K --bench-warmup W]   (reference arm of bench.py: W untimed +
+//                   K timed MGPIS::CG_SOLV(1,...) calls, wall clock around the K calls)
 #include "examples/BEAM.h"
 #include "ddpk_io.h"
 #include "ref_capture.h"
 
 int main(int argc, char **argv) {
-	long glob = 2, doSolve = 1, doJacobi = 0, reps = 1, noMat = 0;
+	long glob = 2, doSolve = 1, doJacobi = 0, reps = 1, noMat = 0, benchSteps = 0, benchWarm = 0;
 	std::vector<long> divi;
 	std::string out;
 	for (int i = 1; i < argc; i++) {
@@ -33,6 +35,8 @@ int main(int argc, char **argv) {
 		else if (a == "--jacobi") doJacobi = std::stol(next());
 		else if (a == "--reps") reps = std::stol(next());
 		else if (a == "--nomat") noMat = 1;
+		else if (a == "--bench-steps") benchSteps = std::stol(next());
+		else if (a == "--bench-warmup") benchWarm = std::stol(next());
 		else { std::cerr << "unknown arg " << a << std::endl; return 2; }
 	}
 	double t0 = now_s();
@@ -110,6 +114,21 @@ int main(int argc, char **argv) {
 		long iters = cap.last_iteration_plus1();
 		if (w) { w->vec("cg_jacobi_x", x); w->scalar_i64("cg_jacobi_iters", iters); }
 		js << ",\"cg_jacobi_iters\":" << iters << ",\"cg_jacobi_s\":" << dt;
+	}
+	if (benchSteps > 0) {
+		Eigen::VectorXd x;
+		for (long r = 0; r < benchWarm; r++) mgpi.CG_SOLV(1, mg.consForc, x);
+		long iters = 0;
+		double t1 = now_s();
+		for (long r = 0; r < benchSteps; r++) {
+			cap.buf.str("");
+			mgpi.CG_SOLV(1, mg.consForc, x);
+			iters += cap.last_iteration_plus1();
+		}
+		double dt = now_s() - t1;
+		js << ",\"bench_steps\":" << benchSteps << ",\"bench_warmup\":" << benchWarm
+		   << ",\"bench_s\":" << dt << ",\"bench_iters\":" << iters
+		   << ",\"bench_dof_iter_per_s\":" << (double)n * iters / dt;
 	}
 	js << ",\"threads\":1}";
 	delete w;

@@ -166,7 +166,7 @@ def test_profile_mode_gives_same_answer_and_counts_kernels(solvers):
     mg.profile(False)
     assert np.array_equal(x1, x2)
     assert mg.launch_count() > 10 * mg.last_iterNumb
-    assert ("spmv", len(A) - 1) in prof and prof[("spmv", len(A) - 1)][1] == mg.last_iterNumb
+    assert ("spmv", len(A) - 1) in prof and mg.last_iterNumb <= prof[("spmv", len(A) - 1)][1] <= mg.last_iterNumb + 2  # +look-ahead no-ops
 
 
 @pytest.mark.skipif(not have_ref_binary(), reason="oracle/_ref/beam_nodd not built")
