@@ -13,14 +13,26 @@ namespace ddpca {
 
 constexpr int kNumPart = 1024;   // slots of a partial-sum buffer (one per CTA of a reducing kernel)
 
-// One multigrid level in its device (stage-permuted) layout.
+// One multigrid level in its device layout: stage-permuted, stored per ROW GROUP.
+// The <= 3 rows of a group share one column pattern (plan.h), so the pattern is stored once
+// per group and each row only adds its values ("GCSR"):
+//   meta[g]            : {row0, gs, cptr, len, voff, kd}
+//   ci[cptr .. +len]   : pattern (sorted new column numbers), len padded to an even count
+//   v[voff + r*len ..] : values of row r of the group (r < gs), same order as the pattern
+//   pattern positions [0,kd) are strictly-lower couplings (earlier stages), [kd,kd+gs) the
+//   in-group block (diagonal block), [kd+gs,len) strictly-upper couplings (later stages).
+// HBM traffic per stored entry: 8 B value + 4/gs B index (9.33 B for the usual gs = 3)
+// instead of CSR's 12 B.
+struct __align__(16) GroupMeta {
+    int row0, gs, cptr, len;
+    long long voff;
+    int kd, pad;
+};
 struct LvlView {
-    int n;
-    const int *__restrict__ rp;      // [n+1]
-    const int *__restrict__ ci;      // [nnz] sorted per row
-    const double *__restrict__ v;    // [nnz]
-    const int *__restrict__ dpos;    // [n] position of the diagonal entry of each row
-    const int *__restrict__ gstart;  // [ngroups+1] first row of each group (<= 3 rows)
+    int n, ng;
+    const GroupMeta *__restrict__ meta;  // [ng]
+    const int *__restrict__ ci;
+    const double *__restrict__ v;
 };
 
 struct CsrView {
@@ -92,6 +104,65 @@ __device__ __forceinline__ double warp_reduce_partials(const double *partial, in
     return warp_sum(t);
 }
 
+__device__ __forceinline__ double2 ld_stream2(const double *p)
+{
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int2 ld_stream2(const int *p)
+{
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ GroupMeta ld_meta(const GroupMeta *p)
+{
+    const int4 a = __ldg(reinterpret_cast<const int4 *>(p));
+    const int4 b = __ldg(reinterpret_cast<const int4 *>(p) + 1);
+    GroupMeta m;
+    m.row0 = a.x; m.gs = a.y; m.cptr = a.z; m.len = a.w;
+    m.voff = (long long)(((unsigned long long)(unsigned)b.y << 32) | (unsigned)b.x);
+    m.kd = b.z; m.pad = b.w;
+    return m;
+}
+
+// Partial sums of one row group over the pattern range selected by LOWER / UPPER:
+//   sL[r] = sum_{k <  kd}      a_r[k] x[c_k]      sU[r] = sum_{k >= kd+gs} a_r[k] x[c_k]
+// Each lane owns pattern positions (2*lane, 2*lane+1) + 64*it: one 8-byte index load, one
+// x gather pair and gs 16-byte value loads per step, all issued before the first FMA of the
+// step (two steps are unrolled: rows of a hexahedral mesh have <= 81 entries).
+template <bool LOWER, bool UPPER, bool NC_X>
+__device__ __forceinline__ void group_partial(const LvlView &A, const GroupMeta &m, const double *x, int lane,
+                                              double (&sL)[3], double (&sU)[3])
+{
+    const int *ci = A.ci + m.cptr;
+    const double *v = A.v + m.voff;
+    const int len = m.len, kd = m.kd, ku = m.kd + m.gs, gs = m.gs;
+    const int kbeg = LOWER ? 0 : (ku & ~1);
+    const int kend = UPPER ? len : kd;   // exclusive; entries >= kend are never needed
+#pragma unroll 2
+    for (int k = kbeg + 2 * lane; k < kend; k += 64) {
+        const int2 c = ld_stream2(ci + k);
+        double2 a[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            if (r < gs) a[r] = ld_stream2(v + (size_t)r * len + k);
+        const bool l0 = k < kd, l1 = k + 1 < kd, u0 = k >= ku, u1 = k + 1 >= ku;
+        double x0 = 0.0, x1 = 0.0;
+        if ((LOWER && l0) || (UPPER && u0)) x0 = NC_X ? __ldg(x + c.x) : x[c.x];
+        if ((LOWER && l1) || (UPPER && u1)) x1 = NC_X ? __ldg(x + c.y) : x[c.y];
+        const double xl0 = (LOWER && l0) ? x0 : 0.0, xl1 = (LOWER && l1) ? x1 : 0.0;
+        const double xu0 = (UPPER && u0) ? x0 : 0.0, xu1 = (UPPER && u1) ? x1 : 0.0;
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            if (r < gs) {
+                if (LOWER) sL[r] += a[r].x * xl0 + a[r].y * xl1;
+                if (UPPER) sU[r] += a[r].x * xu0 + a[r].y * xu1;
+            }
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // K3: forward Gauss-Seidel relaxation of one row group (MGPIS.h:66-72 on the permuted level)
 //   x_i   = (b_i - sum_{j<i} a_ij x_j(new) - sum_{j>i} a_ij x_j(old)) / a_ii
@@ -103,37 +174,22 @@ template <bool ZERO_X, bool NC_X>
 __device__ __forceinline__ void group_fwd(const LvlView &A, int g, const double *__restrict__ b,
                                           double *x, double *__restrict__ p1, int lane)
 {
-    const int r0 = A.gstart[g];
-    const int gs = A.gstart[g + 1] - r0;
+    const GroupMeta m = ld_meta(A.meta + g);
+    const int gs = m.gs, r0 = m.row0;
     double sL[3] = {0.0, 0.0, 0.0}, sU[3] = {0.0, 0.0, 0.0};
-    double blk[3][3], bb[3], xo[3], dg[3];
-    int pdv[3];
+    double blk[3][3], bb[3], xo[3];
+    const double *vb = A.v + m.voff + m.kd;
 #pragma unroll
     for (int r = 0; r < 3; r++) {
+        bb[r] = 0.0; xo[r] = 0.0;
         if (r < gs) {
-            const int i = r0 + r;
-            const int pb = A.rp[i], pd = A.dpos[i], pe = A.rp[i + 1];
-            pdv[r] = pd;
-            bb[r] = b[i];
-            xo[r] = ZERO_X ? 0.0 : x[i];
-#pragma unroll
-            for (int c = 0; c < 3; c++) blk[r][c] = (c < gs) ? A.v[pd - r + c] : 0.0;
-            dg[r] = blk[r][r];
-            for (int p = pb + lane; p < pd - r; p += 32) {
-                const int c = ld_stream(A.ci + p);
-                const double a = ld_stream(A.v + p);
-                sL[r] += a * (NC_X ? __ldg(x + c) : x[c]);
-            }
-            if (!ZERO_X) {
-                for (int p = pd + (gs - r) + lane; p < pe; p += 32) {
-                    const int c = ld_stream(A.ci + p);
-                    const double a = ld_stream(A.v + p);
-                    sU[r] += a * (NC_X ? __ldg(x + c) : x[c]);
-                }
-            }
+            bb[r] = b[r0 + r];
+            if (!ZERO_X) xo[r] = x[r0 + r];
         }
+#pragma unroll
+        for (int c = 0; c < 3; c++) blk[r][c] = (r < gs && c < gs) ? __ldg(vb + (size_t)r * m.len + c) : 0.0;
     }
-    (void)pdv;
+    group_partial<true, !ZERO_X, NC_X>(A, m, x, lane, sL, sU);
 #pragma unroll
     for (int r = 0; r < 3; r++) {
         sL[r] = warp_sum(sL[r]);
@@ -148,13 +204,13 @@ __device__ __forceinline__ void group_fwd(const LvlView &A, int g, const double 
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 if (c < r) inL += blk[r][c] * xn[c];
-                if (c > r && c < gs) inU += blk[r][c] * xo[c];
+                if (c > r) inU += blk[r][c] * xo[c];
             }
             const double up = sU[r] + inU;
-            xn[r] = (bb[r] - sL[r] - inL - up) / dg[r];
+            xn[r] = (bb[r] - sL[r] - inL - up) / blk[r][r];
             if (lane == 0) {
                 x[r0 + r] = xn[r];
-                p1[r0 + r] = dg[r] * xn[r] + up;
+                p1[r0 + r] = blk[r][r] * xn[r] + up;
             }
         }
     }
@@ -165,26 +221,18 @@ template <bool NC_X>
 __device__ __forceinline__ void group_bwd(const LvlView &A, int g, const double *__restrict__ p1,
                                           double *x, int lane)
 {
-    const int r0 = A.gstart[g];
-    const int gs = A.gstart[g + 1] - r0;
-    double sU[3] = {0.0, 0.0, 0.0};
-    double blk[3][3], pp[3], dg[3];
+    const GroupMeta m = ld_meta(A.meta + g);
+    const int gs = m.gs, r0 = m.row0;
+    double sL[3] = {0.0, 0.0, 0.0}, sU[3] = {0.0, 0.0, 0.0};
+    double blk[3][3], pp[3];
+    const double *vb = A.v + m.voff + m.kd;
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        if (r < gs) {
-            const int i = r0 + r;
-            const int pd = A.dpos[i], pe = A.rp[i + 1];
-            pp[r] = p1[i];
+        pp[r] = (r < gs) ? p1[r0 + r] : 0.0;
 #pragma unroll
-            for (int c = 0; c < 3; c++) blk[r][c] = (c < gs && c >= r) ? A.v[pd - r + c] : 0.0;
-            dg[r] = blk[r][r];
-            for (int p = pd + (gs - r) + lane; p < pe; p += 32) {
-                const int c = ld_stream(A.ci + p);
-                const double a = ld_stream(A.v + p);
-                sU[r] += a * (NC_X ? __ldg(x + c) : x[c]);
-            }
-        }
+        for (int c = 0; c < 3; c++) blk[r][c] = (r < gs && c < gs && c >= r) ? __ldg(vb + (size_t)r * m.len + c) : 0.0;
     }
+    group_partial<false, true, NC_X>(A, m, x, lane, sL, sU);
 #pragma unroll
     for (int r = 0; r < 3; r++) sU[r] = warp_sum(sU[r]);
     double xn[3] = {0.0, 0.0, 0.0};
@@ -194,8 +242,8 @@ __device__ __forceinline__ void group_bwd(const LvlView &A, int g, const double 
             double inU = 0.0;
 #pragma unroll
             for (int c = 0; c < 3; c++)
-                if (c > r && c < gs) inU += blk[r][c] * xn[c];
-            xn[r] = (pp[r] - sU[r] - inU) / dg[r];
+                if (c > r) inU += blk[r][c] * xn[c];
+            xn[r] = (pp[r] - sU[r] - inU) / blk[r][r];
             if (lane == 0) x[r0 + r] = xn[r];
         }
     }
@@ -224,7 +272,7 @@ __global__ void __launch_bounds__(256) k_sweep_bwd_stage(LvlView A, int g0, int 
 // a run of small stages [s0,s1) relaxed by ONE CTA, __syncthreads() between stages
 // (latency-bound regime: LEX wavefronts, coarse levels)
 template <bool ZERO_X>
-__global__ void __launch_bounds__(1024) k_sweep_fwd_multi(LvlView A, const int *__restrict__ stage_group, int s0, int s1,
+__global__ void __launch_bounds__(512) k_sweep_fwd_multi(LvlView A, const int *__restrict__ stage_group, int s0, int s1,
                                                           const double *__restrict__ b, double *x, double *p1, const int *done)
 {
     if (done && *done) return;
@@ -236,7 +284,7 @@ __global__ void __launch_bounds__(1024) k_sweep_fwd_multi(LvlView A, const int *
     }
 }
 
-__global__ void __launch_bounds__(1024) k_sweep_bwd_multi(LvlView A, const int *__restrict__ stage_group, int s0, int s1,
+__global__ void __launch_bounds__(512) k_sweep_bwd_multi(LvlView A, const int *__restrict__ stage_group, int s0, int s1,
                                                           const double *p1, double *x, const int *done)
 {
     if (done && *done) return;
@@ -248,21 +296,64 @@ __global__ void __launch_bounds__(1024) k_sweep_bwd_multi(LvlView A, const int *
     }
 }
 
-// K2: r = b - (p1 + L x)   (MGPIS.h:92) -- strictly-lower half only, LANES lanes per row
-template <int LANES>
+// K2: r = b - (p1 + L x)   (MGPIS.h:92) -- strictly-lower half only, one warp per group
 __global__ void __launch_bounds__(256) k_resid_lower(LvlView A, const double *__restrict__ b, const double *__restrict__ p1,
                                                      const double *__restrict__ x, double *__restrict__ r, const int *done)
 {
     if (done && *done) return;
-    const int sub = threadIdx.x % LANES;
-    const int i = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / LANES);
-    double s = 0.0;
-    if (i < A.n) {
-        const int pb = A.rp[i], pd = A.dpos[i];
-        for (int p = pb + sub; p < pd; p += LANES) s += ld_stream(A.v + p) * __ldg(x + ld_stream(A.ci + p));
+    const int lane = threadIdx.x & 31;
+    const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (g >= A.ng) return;
+    const GroupMeta m = ld_meta(A.meta + g);
+    double sL[3] = {0.0, 0.0, 0.0}, sU[3] = {0.0, 0.0, 0.0};
+    group_partial<true, false, true>(A, m, x, lane, sL, sU);
+#pragma unroll
+    for (int q = 0; q < 3; q++) sL[q] = warp_sum(sL[q]);
+    if (lane < m.gs) {
+        const int i = m.row0 + lane;
+        double s = lane == 0 ? sL[0] : (lane == 1 ? sL[1] : sL[2]);
+        const double *vb = A.v + m.voff + (size_t)lane * m.len + m.kd;
+        for (int c = 0; c < lane; c++) s += vb[c] * x[m.row0 + c];   // in-group strictly-lower part
+        r[i] = b[i] - (p1[i] + s);
     }
-    s = subwarp_sum<LANES>(s);
-    if (i < A.n && sub == 0) r[i] = b[i] - (p1[i] + s);
+}
+
+// K1: y = A x on the group layout, one warp per group, grid-stride; DOT: partial[blockIdx] = sum_i w_i y_i
+// (the p.q of MGPIS.h:201 fused into the product of :200).  Fixed grid => deterministic.
+template <bool DOT>
+__global__ void __launch_bounds__(256) k_spmv_group(LvlView A, const double *__restrict__ x, double *__restrict__ y,
+                                                    const double *__restrict__ w, double *partial, const int *done)
+{
+    if (done && *done) return;
+    const int lane = threadIdx.x & 31;
+    const int nwarp = (int)((gridDim.x * (unsigned)blockDim.x) >> 5);
+    double acc = 0.0;
+    for (int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5); g < A.ng; g += nwarp) {
+        const GroupMeta m = ld_meta(A.meta + g);
+        const int *ci = A.ci + m.cptr;
+        const double *v = A.v + m.voff;
+        double s[3] = {0.0, 0.0, 0.0};
+#pragma unroll 2
+        for (int k = 2 * lane; k < m.len; k += 64) {
+            const int2 c = ld_stream2(ci + k);
+            double2 a[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                if (r < m.gs) a[r] = ld_stream2(v + (size_t)r * m.len + k);
+            const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y);
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                if (r < m.gs) s[r] += a[r].x * x0 + a[r].y * x1;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; r++) s[r] = warp_sum(s[r]);
+        if (lane < m.gs) {
+            const double yi = lane == 0 ? s[0] : (lane == 1 ? s[1] : s[2]);
+            y[m.row0 + lane] = yi;
+            if (DOT) acc += w[m.row0 + lane] * yi;
+        }
+    }
+    if (DOT) block_sum_to_partial(acc, partial);
 }
 
 // K1/K5/K6: y (=|+=) A x, LANES lanes per row; DOT: partial[blockIdx] = sum_i w_i * y_i
@@ -367,8 +458,10 @@ __global__ void k_fill(int n, double *__restrict__ x, double val, const int *don
 }
 __global__ void k_extract_diag_inv(LvlView A, double *__restrict__ dinv)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < A.n) dinv[i] = 1.0 / A.v[A.dpos[i]];
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= A.ng) return;
+    const GroupMeta m = A.meta[g];
+    for (int r = 0; r < m.gs; r++) dinv[m.row0 + r] = 1.0 / A.v[m.voff + (size_t)r * m.len + m.kd + r];
 }
 // z = dinv .* r   (DIAG_PREC, PREP.h:393-401; MGPIS.h:192,206)
 __global__ void k_jacobi(int n, const double *__restrict__ dinv, const double *__restrict__ r, double *__restrict__ z, const int *done)

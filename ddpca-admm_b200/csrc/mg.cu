@@ -2,9 +2,10 @@
 // of include/ddpca_b200.h (class MGPIS of the reference, MGPIS.h:8-225).
 //
 // Layout in HBM, per level l (all in the stage-permuted numbering of plan.h):
-//   A_l   one CSR (int32 rowptr/colidx, FP64 val) + dpos[n] (diagonal position).  The
-//         reference keeps three copies (consLowe/consDiag/consUppe, MGPIS.h:29-33); the
-//         strictly-lower / strictly-upper halves are sub-ranges of each row here.
+//   A_l   group layout ("GCSR", kernels.cuh): one column pattern per row group (<= 3 rows of
+//         one mesh node) + FP64 values per row.  The reference keeps three copies
+//         (consLowe/consDiag/consUppe, MGPIS.h:29-33); here the strictly-lower / in-group /
+//         strictly-upper parts are position ranges [0,kd) [kd,kd+gs) [kd+gs,len) of a pattern.
 //   P_l-1 realProl[l-1] as CSR (n_l x n_l-1) and its explicit transpose R (gather-based
 //         restriction, no atomics).
 //   x,b,p1,r work vectors.   Level 0 additionally holds the dense inverse of consStif[0].
@@ -58,15 +59,22 @@ struct Segment {
 
 struct Level {
     int n = 0;
-    long nnz = 0;
+    long nnz = 0;          // stored entries of consStif[l] (reference count, without padding)
     LevelPlan plan;
-    DevCsr A;
-    int *dpos = nullptr, *gstart = nullptr, *stage_group = nullptr, *perm = nullptr;
+    DevCsr A;              // plain CSR, kept for level 0 only (input of the dense inversion)
+    // group layout (kernels.cuh: GroupMeta / LvlView)
+    int ng = 0;
+    GroupMeta *meta = nullptr;
+    int *gci = nullptr;
+    double *gv = nullptr;
+    long pat_entries = 0;  // pattern entries stored (sum of padded len over groups)
+    long val_entries = 0;  // values stored (sum of gs * padded len)
+    int *stage_group = nullptr, *perm = nullptr;
     std::vector<Segment> segs;
     DevCsr P, R;  // level l <-> l-1 (l >= 1)
     double *x = nullptr, *b = nullptr, *p1 = nullptr, *r = nullptr, *dinv = nullptr;
-    long nnz_lower = 0;
-    LvlView view() const { return LvlView{n, A.rp, A.ci, A.v, dpos, gstart}; }
+    double bytes_lower = 0, bytes_upper = 0, bytes_full = 0;  // algorithmic bytes of one pass over a half / the whole level
+    LvlView view() const { return LvlView{n, ng, meta, gci, gv}; }
 };
 
 struct ProfRec {
@@ -209,11 +217,16 @@ static void launch_spmv(ddpca_mg *h, int kclass, int lvl, const DevCsr &A, const
     else SPMV_CASE(4);
 #undef SPMV_CASE
 }
-static int spmv_dot_grid(const ddpca_mg *h, const DevCsr &A)
+// y = consStif[l] x on the group layout; returns the grid (= number of partial sums when dotw)
+static int launch_level_spmv(ddpca_mg *h, int l, const double *x, double *y, const double *dotw, double *partial, const int *done)
 {
-    (void)h;
-    long need = cdiv((long)A.rows * 32, 256);
-    return (int)std::max<long>(1, std::min<long>(need, kNumPart));
+    Level &L = h->lev[l];
+    long need = cdiv((long)L.ng * 32, 256);
+    int grid = (int)std::max<long>(1, std::min<long>(need, dotw ? kNumPart : (long)h->sms * 32));
+    double bytes = L.bytes_full + (dotw ? 8.0 * L.n : 0.0);
+    if (dotw) KL(h, DDPCA_K_SPMV, l, bytes, (k_spmv_group<true><<<grid, 256, 0, h->stream>>>(L.view(), x, y, dotw, partial, done)));
+    else KL(h, DDPCA_K_SPMV, l, bytes, (k_spmv_group<false><<<grid, 256, 0, h->stream>>>(L.view(), x, y, nullptr, nullptr, done)));
+    return grid;
 }
 
 static void sweep_fwd(ddpca_mg *h, int l, const double *b, double *x, bool zero_x, const int *done)
@@ -227,8 +240,8 @@ static void sweep_fwd(ddpca_mg *h, int l, const double *b, double *x, bool zero_
             if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_stage<true><<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, b, x, L.p1, done)));
             else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_stage<false><<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, b, x, L.p1, done)));
         } else {
-            if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<true><<<1, 1024, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
-            else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<false><<<1, 1024, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+            if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<true><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+            else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<false><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
         }
     }
 }
@@ -242,7 +255,7 @@ static void sweep_bwd(ddpca_mg *h, int l, double *x, const int *done)
             int grid = cdiv((long)ng * 32, 256);
             KL(h, DDPCA_K_SWEEP_BWD, l, s.bytes_up, (k_sweep_bwd_stage<<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, L.p1, x, done)));
         } else {
-            KL(h, DDPCA_K_SWEEP_BWD, l, s.bytes_up, (k_sweep_bwd_multi<<<1, 1024, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, L.p1, x, done)));
+            KL(h, DDPCA_K_SWEEP_BWD, l, s.bytes_up, (k_sweep_bwd_multi<<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, L.p1, x, done)));
         }
     }
 }
@@ -259,13 +272,7 @@ static void vcycle_dev(ddpca_mg *h, int l, const double *b, double *x, bool zero
     Level &C = h->lev[l - 1];
     sweep_fwd(h, l, b, x, zero_x, done);  // :65-72
     sweep_bwd(h, l, x, done);             // :73-76
-    {
-        double bytes = 12.0 * L.nnz_lower + 4.0 * (L.n + 1) + 8.0 * L.n * 4;
-        if (L.A.avg_row() > 40)
-            KL(h, DDPCA_K_RESID, l, bytes, (k_resid_lower<32><<<cdiv((long)L.n * 32, 256), 256, 0, h->stream>>>(L.view(), b, L.p1, x, L.r, done)));
-        else
-            KL(h, DDPCA_K_RESID, l, bytes, (k_resid_lower<8><<<cdiv((long)L.n * 8, 256), 256, 0, h->stream>>>(L.view(), b, L.p1, x, L.r, done)));
-    }
+    KL(h, DDPCA_K_RESID, l, L.bytes_lower + 8.0 * L.n, (k_resid_lower<<<cdiv((long)L.ng * 32, 256), 256, 0, h->stream>>>(L.view(), b, L.p1, x, L.r, done)));
     launch_spmv(h, DDPCA_K_RESTRICT, l, L.R, L.r, C.b, false, nullptr, nullptr, done);  // :96
     vcycle_dev(h, l - 1, C.b, C.x, true, done);                                          // :93-99
     launch_spmv(h, DDPCA_K_PROLONG, l, L.P, C.x, x, true, nullptr, nullptr, done);       // :100
@@ -293,8 +300,7 @@ static void enqueue_iteration(ddpca_mg *h, int prec)
     Level &L = h->lev[Lf];
     const int *done = &h->st->done;
     int n = L.n;
-    int gq = spmv_dot_grid(h, L.A);
-    launch_spmv(h, DDPCA_K_SPMV, Lf, L.A, h->cg_p, h->cg_q, false, h->cg_p, h->partial[0], done);  // :200 + p.q
+    int gq = launch_level_spmv(h, Lf, h->cg_p, h->cg_q, h->cg_p, h->partial[0], done);  // :200 + p.q
     KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_alpha<<<1, 32, 0, h->stream>>>(h->st, h->partial[0], gq)));  // :201
     int gv = vec_grid(h, n);
     KL(h, DDPCA_K_VECTOR, Lf, 48.0 * n, (k_update_xr<<<gv, 256, 0, h->stream>>>(n, h->st, h->cg_p, h->cg_q, h->cg_x, h->cg_r, h->partial[1])));  // :202-203
@@ -340,7 +346,7 @@ static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref,
     const int *done = &h->st->done;
     if (prec == 0 && !L.dinv) {
         CU(cudaMalloc(&L.dinv, sizeof(double) * n));
-        k_extract_diag_inv<<<cdiv(n, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
+        k_extract_diag_inv<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
     }
     if (!h->profile) {
         if (build_iter_graph(h, prec)) return 1;
@@ -397,25 +403,72 @@ static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref,
 }
 
 // ------------------------------------------------------------------------------------------
-static int build_segments(Level &L, const std::vector<int> &rp_new, const std::vector<int> &dpos_new)
+// Host construction of the group layout of one (already permuted) level + the sweep schedule.
+struct GroupLayoutHost {
+    std::vector<GroupMeta> meta;
+    std::vector<int> ci;
+    std::vector<double> v;
+};
+
+static bool build_group_layout(const CsrHost &Ap, const LevelPlan &pl, GroupLayoutHost &out, std::string &err)
+{
+    int ng = pl.ngroups();
+    out.meta.resize(ng);
+    long pat = 0, val = 0;
+    for (int g = 0; g < ng; g++) {
+        int r0 = pl.group_start[g], gs = pl.group_start[g + 1] - r0;
+        int len = Ap.rp[r0 + 1] - Ap.rp[r0];
+        int lenp = len + (len & 1);
+        const int *c0 = Ap.ci.data() + Ap.rp[r0];
+        int kd = (int)(std::lower_bound(c0, c0 + len, r0) - c0);
+        if (kd + gs > len || c0[kd] != r0 || c0[kd + gs - 1] != r0 + gs - 1) { err = "group " + std::to_string(g) + ": in-group block incomplete"; return false; }
+        GroupMeta m;
+        m.row0 = r0; m.gs = gs; m.cptr = (int)pat; m.len = lenp; m.voff = val; m.kd = kd; m.pad = len;
+        out.meta[g] = m;
+        pat += lenp;
+        val += (long)gs * lenp;
+        if (pat > 0x7fffffffL) { err = "pattern index overflow"; return false; }
+    }
+    out.ci.resize(pat);
+    out.v.assign(val, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int g = 0; g < ng; g++) {
+        const GroupMeta &m = out.meta[g];
+        int len = m.pad;
+        const int *c0 = Ap.ci.data() + Ap.rp[m.row0];
+        for (int k = 0; k < len; k++) out.ci[m.cptr + k] = c0[k];
+        if (m.len > len) out.ci[m.cptr + len] = c0[len - 1];   // padding: value 0 on a valid column
+        for (int r = 0; r < m.gs; r++) {
+            const double *vr = Ap.v.data() + Ap.rp[m.row0 + r];
+            double *dst = out.v.data() + m.voff + (long)r * m.len;
+            for (int k = 0; k < len; k++) dst[k] = vr[k];
+        }
+    }
+    return true;
+}
+
+static int build_segments(Level &L, const GroupLayoutHost &G)
 {
     const LevelPlan &pl = L.plan;
     const int kBigStage = 48;  // groups; smaller stages are merged into single-CTA runs
     int ns = pl.nstages();
-    auto stage_bytes = [&](int s0, int s1, double &lo, double &up) {
-        int ra = pl.group_start[pl.stage_group[s0]], rb = pl.group_start[pl.stage_group[s1]];
-        long nl = 0, nu = 0;
-        for (int i = ra; i < rb; i++) { nl += dpos_new[i] - rp_new[i]; nu += rp_new[i + 1] - dpos_new[i] - 1; }
-        double rows = rb - ra;
-        // 12 nnz(T) + 4 rows (rowptr) + 8 diag + 8 rhs + 16 x (read+write)
-        lo = 12.0 * nl + rows * (4 + 8 + 8 + 16);
-        up = 12.0 * nu + rows * (4 + 8 + 8 + 16);
+    // algorithmic bytes of relaxing groups [ga,gb) over the lower / upper half:
+    // 8 B per value + 4 B per pattern entry of the half + per row: 8 (rhs) + 16 (x read+write) + 8 (p1)
+    // + 32 B group descriptor + the gs*gs in-group block
+    auto seg_bytes = [&](int ga, int gb, double &lo, double &up) {
+        lo = up = 0;
+        for (int g = ga; g < gb; g++) {
+            const GroupMeta &m = G.meta[g];
+            double common = 32.0 + 8.0 * m.gs * m.gs + 32.0 * m.gs;
+            lo += (8.0 * m.gs + 4.0) * m.kd + common;
+            up += (8.0 * m.gs + 4.0) * (m.pad - m.kd - m.gs) + common;
+        }
     };
     int s = 0;
     while (s < ns) {
-        int ng = pl.stage_group[s + 1] - pl.stage_group[s];
+        int ngs = pl.stage_group[s + 1] - pl.stage_group[s];
         Segment seg{};
-        if (ng >= kBigStage) {
+        if (ngs >= kBigStage) {
             seg.multi = 0; seg.s0 = s; seg.s1 = s + 1;
         } else {
             int e = s + 1;
@@ -424,7 +477,7 @@ static int build_segments(Level &L, const std::vector<int> &rp_new, const std::v
         }
         seg.g0 = pl.stage_group[seg.s0];
         seg.g1 = pl.stage_group[seg.s1];
-        stage_bytes(seg.s0, seg.s1, seg.bytes_lo, seg.bytes_up);
+        seg_bytes(seg.g0, seg.g1, seg.bytes_lo, seg.bytes_up);
         L.segs.push_back(seg);
         s = seg.s1;
     }
@@ -504,7 +557,7 @@ int ddpca_mg_destroy(ddpca_mg *h)
     cudaSetDevice(h->device);
     for (auto &L : h->lev) {
         free_csr(L.A); free_csr(L.P); free_csr(L.R);
-        cudaFree(L.dpos); cudaFree(L.gstart); cudaFree(L.stage_group); cudaFree(L.perm);
+        cudaFree(L.meta); cudaFree(L.gci); cudaFree(L.gv); cudaFree(L.stage_group); cudaFree(L.perm);
         cudaFree(L.x); cudaFree(L.b); cudaFree(L.p1); cudaFree(L.r); cudaFree(L.dinv);
     }
     cudaFree(h->Binv);
@@ -560,19 +613,26 @@ int ddpca_mg_create(int device, int nlevels, const int *n, const int *const *row
         CsrHost Ap;
         permute_csr(n[l], n[l], rowptr[l], colidx[l], val[l], L.plan.perm, L.plan.iperm, Ap);
         L.nnz = Ap.nnz();
-        std::vector<int> dpos(n[l]);
-        long nlow = 0;
-        for (int i = 0; i < n[l]; i++) {
-            int p = (int)(std::lower_bound(Ap.ci.begin() + Ap.rp[i], Ap.ci.begin() + Ap.rp[i + 1], i) - Ap.ci.begin());
-            if (p >= Ap.rp[i + 1] || Ap.ci[p] != i) { g_err = "missing diagonal"; ddpca_mg_destroy(h); return 1; }
-            dpos[i] = p;
-            nlow += p - Ap.rp[i];
+        if (l == 0 && nlevels > 1) {
+            FAILC(upload_csr(Ap, L.A));   // level 0 is only ever solved directly
+        } else {
+            GroupLayoutHost G;
+            if (!build_group_layout(Ap, L.plan, G, err)) { g_err = "level " + std::to_string(l) + ": " + err; ddpca_mg_destroy(h); return 1; }
+            if (l == 0) FAILC(upload_csr(Ap, L.A));
+            if (mode >= 0) build_segments(L, G);
+            L.ng = (int)G.meta.size();
+            L.pat_entries = (long)G.ci.size();
+            L.val_entries = (long)G.v.size();
+            for (const GroupMeta &m : G.meta) {
+                double common = 32.0 + 8.0 * m.gs * m.gs + 32.0 * m.gs;
+                L.bytes_lower += (8.0 * m.gs + 4.0) * m.kd + common;
+                L.bytes_upper += (8.0 * m.gs + 4.0) * (m.pad - m.kd - m.gs) + common;
+                L.bytes_full += (8.0 * m.gs + 4.0) * m.pad + 32.0 + 16.0 * m.gs;   // + x once, y once
+            }
+            FAILC(upload_vec(G.meta, &L.meta));
+            FAILC(upload_vec(G.ci, &L.gci));
+            FAILC(upload_vec(G.v, &L.gv));
         }
-        L.nnz_lower = nlow;
-        if (mode >= 0) build_segments(L, Ap.rp, dpos);
-        FAILC(upload_csr(Ap, L.A));
-        FAILC(upload_vec(dpos, &L.dpos));
-        FAILC(upload_vec(L.plan.group_start, &L.gstart));
         FAILC(upload_vec(L.plan.stage_group, &L.stage_group));
         FAILC(upload_vec(L.plan.perm, &L.perm));
         CUC(cudaMalloc(&L.x, sizeof(double) * std::max(1, n[l])));
@@ -687,7 +747,8 @@ int ddpca_mg_spmv(ddpca_mg *h, int level, const double *x, double *y)
     if (!h || level < 0 || level >= h->nlev || !x || !y) return fail("ddpca_mg_spmv: bad argument");
     CU(cudaSetDevice(h->device));
     if (to_dev(h, level, x, h->cg_p)) return 1;
-    launch_spmv(h, DDPCA_K_SPMV, level, h->lev[level].A, h->cg_p, h->cg_q, false, nullptr, nullptr, nullptr);
+    if (h->lev[level].meta) launch_level_spmv(h, level, h->cg_p, h->cg_q, nullptr, nullptr, nullptr);
+    else launch_spmv(h, DDPCA_K_SPMV, level, h->lev[level].A, h->cg_p, h->cg_q, false, nullptr, nullptr, nullptr);
     if (h->profile) h->prof_collect();
     return to_host(h, level, h->cg_q, y);
 }
