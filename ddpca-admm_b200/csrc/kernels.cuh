@@ -450,6 +450,12 @@ __global__ void k_scatter(int n, const int *__restrict__ perm, const double *__r
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[perm[i]] = in[i];
 }
+// out[idx[i]] = in[i] * scale[i]
+__global__ void k_scatter_scaled(int n, const int *__restrict__ idx, const double *__restrict__ scale, const double *__restrict__ in, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[idx[i]] = in[i] * scale[i];
+}
 __global__ void k_fill(int n, double *__restrict__ x, double val, const int *done)
 {
     if (done && *done) return;

@@ -85,23 +85,11 @@ struct ProfRec {
 
 }  // namespace
 
-struct ddpca_mg {
+// Launch context shared by every handle type: device, stream, launch accounting, per-class timing.
+struct Engine {
     int device = 0;
-    int mode = DDPCA_SMOOTH_MC;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    int nlev = 0;
-    std::vector<Level> lev;
-    double *Binv = nullptr;  // dense inverse of level 0
-    int n0 = 0;
-    // finest-level CG vectors (device numbering) + staging in reference numbering
-    double *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr, *cg_z = nullptr, *cg_x = nullptr;
-    double *stage_a = nullptr, *stage_b = nullptr;  // max-n staging buffers
-    PcgState *st = nullptr;
-    PcgState *st_host = nullptr;  // pinned, ring of kDepth+1
-    double *partial[3] = {nullptr, nullptr, nullptr};
-    cudaGraphExec_t iter_graph[2] = {nullptr, nullptr};  // per preconditioner
-    long iter_graph_nodes[2] = {0, 0};
-    // bookkeeping
+    int sms = 148;
     long launches = 0;
     bool capturing = false;
     long captured_nodes = 0;
@@ -110,10 +98,13 @@ struct ddpca_mg {
     double prof_ms[DDPCA_K_COUNT][16];
     long prof_n[DDPCA_K_COUNT][16];
     double prof_bytes[DDPCA_K_COUNT][16];
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    double t_solve = 0, t_h2d = 0, t_d2h = 0;
-    int sms = 148;
-
+    Engine() { prof_reset(); }
+    void prof_reset()
+    {
+        std::memset(prof_ms, 0, sizeof(prof_ms));
+        std::memset(prof_n, 0, sizeof(prof_n));
+        std::memset(prof_bytes, 0, sizeof(prof_bytes));
+    }
     void pre(int kclass, int level, double bytes)
     {
         if (capturing) { captured_nodes++; return; }
@@ -146,6 +137,24 @@ struct ddpca_mg {
         }
         prof.clear();
     }
+};
+
+struct ddpca_mg : Engine {
+    int mode = DDPCA_SMOOTH_MC;
+    int nlev = 0;
+    std::vector<Level> lev;
+    double *Binv = nullptr;  // dense inverse of level 0
+    int n0 = 0;
+    // finest-level CG vectors (device numbering) + staging in reference numbering
+    double *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr, *cg_z = nullptr, *cg_x = nullptr;
+    double *stage_a = nullptr, *stage_b = nullptr;  // max-n staging buffers
+    PcgState *st = nullptr;
+    PcgState *st_host = nullptr;  // pinned, ring of kDepth+1
+    double *partial[3] = {nullptr, nullptr, nullptr};
+    cudaGraphExec_t iter_graph[2] = {nullptr, nullptr};  // per preconditioner
+    long iter_graph_nodes[2] = {0, 0};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double t_solve = 0, t_h2d = 0, t_d2h = 0;
 };
 
 #define KL(h, kc, lvl, bytes, ...) \
@@ -187,7 +196,7 @@ static int upload_vec(const std::vector<T> &h, T **d)
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 // ---- kernel launch helpers (all on h->stream) ----------------------------------------------
-static void launch_spmv(ddpca_mg *h, int kclass, int lvl, const DevCsr &A, const double *x, double *y, bool add,
+static void launch_spmv(Engine *h, int kclass, int lvl, const DevCsr &A, const double *x, double *y, bool add,
                         const double *dotw, double *partial, const int *done)
 {
     // algorithmic bytes, SURVEY.md §8(d): 12 nnz + 4 (rows+1) + 8 cols (x once) + 8 rows (y) [+8 rows for +=]
@@ -218,9 +227,8 @@ static void launch_spmv(ddpca_mg *h, int kclass, int lvl, const DevCsr &A, const
 #undef SPMV_CASE
 }
 // y = consStif[l] x on the group layout; returns the grid (= number of partial sums when dotw)
-static int launch_level_spmv(ddpca_mg *h, int l, const double *x, double *y, const double *dotw, double *partial, const int *done)
+static int launch_level_spmv(Engine *h, Level &L, int l, const double *x, double *y, const double *dotw, double *partial, const int *done)
 {
-    Level &L = h->lev[l];
     long need = cdiv((long)L.ng * 32, 256);
     int grid = (int)std::max<long>(1, std::min<long>(need, dotw ? kNumPart : (long)h->sms * 32));
     double bytes = L.bytes_full + (dotw ? 8.0 * L.n : 0.0);
@@ -229,9 +237,8 @@ static int launch_level_spmv(ddpca_mg *h, int l, const double *x, double *y, con
     return grid;
 }
 
-static void sweep_fwd(ddpca_mg *h, int l, const double *b, double *x, bool zero_x, const int *done)
+static void sweep_fwd(Engine *h, Level &L, int l, const double *b, double *x, bool zero_x, const int *done)
 {
-    Level &L = h->lev[l];
     for (const Segment &s : L.segs) {
         double bytes = s.bytes_lo + (zero_x ? 0.0 : s.bytes_up);
         if (!s.multi) {
@@ -245,9 +252,8 @@ static void sweep_fwd(ddpca_mg *h, int l, const double *b, double *x, bool zero_
         }
     }
 }
-static void sweep_bwd(ddpca_mg *h, int l, double *x, const int *done)
+static void sweep_bwd(Engine *h, Level &L, int l, double *x, const int *done)
 {
-    Level &L = h->lev[l];
     for (int k = (int)L.segs.size() - 1; k >= 0; k--) {
         const Segment &s = L.segs[k];
         if (!s.multi) {
@@ -270,14 +276,14 @@ static void vcycle_dev(ddpca_mg *h, int l, const double *b, double *x, bool zero
     }
     Level &L = h->lev[l];
     Level &C = h->lev[l - 1];
-    sweep_fwd(h, l, b, x, zero_x, done);  // :65-72
-    sweep_bwd(h, l, x, done);             // :73-76
+    sweep_fwd(h, L, l, b, x, zero_x, done);  // :65-72
+    sweep_bwd(h, L, l, x, done);             // :73-76
     KL(h, DDPCA_K_RESID, l, L.bytes_lower + 8.0 * L.n, (k_resid_lower<<<cdiv((long)L.ng * 32, 256), 256, 0, h->stream>>>(L.view(), b, L.p1, x, L.r, done)));
     launch_spmv(h, DDPCA_K_RESTRICT, l, L.R, L.r, C.b, false, nullptr, nullptr, done);  // :96
     vcycle_dev(h, l - 1, C.b, C.x, true, done);                                          // :93-99
     launch_spmv(h, DDPCA_K_PROLONG, l, L.P, C.x, x, true, nullptr, nullptr, done);       // :100
-    sweep_fwd(h, l, b, x, false, done);  // :102-109
-    sweep_bwd(h, l, x, done);            // :110-113
+    sweep_fwd(h, L, l, b, x, false, done);  // :102-109
+    sweep_bwd(h, L, l, x, done);            // :110-113
 }
 
 static void precondition(ddpca_mg *h, int prec, const double *r, double *z, const int *done)
@@ -291,7 +297,7 @@ static void precondition(ddpca_mg *h, int prec, const double *r, double *z, cons
     }
 }
 
-static int vec_grid(const ddpca_mg *h, int n) { return std::max(1, std::min(cdiv(n, 256), std::min(kNumPart, h->sms * 8))); }
+static int vec_grid(const Engine *h, int n) { return std::max(1, std::min(cdiv(n, 256), std::min(kNumPart, h->sms * 8))); }
 
 // body of one CG iteration, MGPIS.h:199-219
 static void enqueue_iteration(ddpca_mg *h, int prec)
@@ -300,7 +306,7 @@ static void enqueue_iteration(ddpca_mg *h, int prec)
     Level &L = h->lev[Lf];
     const int *done = &h->st->done;
     int n = L.n;
-    int gq = launch_level_spmv(h, Lf, h->cg_p, h->cg_q, h->cg_p, h->partial[0], done);  // :200 + p.q
+    int gq = launch_level_spmv(h, L, Lf, h->cg_p, h->cg_q, h->cg_p, h->partial[0], done);  // :200 + p.q
     KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_alpha<<<1, 32, 0, h->stream>>>(h->st, h->partial[0], gq)));  // :201
     int gv = vec_grid(h, n);
     KL(h, DDPCA_K_VECTOR, Lf, 48.0 * n, (k_update_xr<<<gv, 256, 0, h->stream>>>(n, h->st, h->cg_p, h->cg_q, h->cg_x, h->cg_r, h->partial[1])));  // :202-203
@@ -484,6 +490,47 @@ static int build_segments(Level &L, const GroupLayoutHost &G)
     return 0;
 }
 
+// Plan + permute + group layout + upload of one operator level (device must be current).
+static int setup_level(Level &L, int n, const int *rp, const int *ci, const double *v, int mode, bool keep_csr, bool group_layout)
+{
+    L.n = n;
+    std::string err;
+    if (!build_level_plan(n, rp, ci, mode, L.plan, err)) return fail(err);
+    CsrHost Ap;
+    permute_csr(n, n, rp, ci, v, L.plan.perm, L.plan.iperm, Ap);
+    L.nnz = Ap.nnz();
+    if (keep_csr) { if (upload_csr(Ap, L.A)) return 1; }
+    if (group_layout) {
+        GroupLayoutHost G;
+        if (!build_group_layout(Ap, L.plan, G, err)) return fail(err);
+        if (mode >= 0) build_segments(L, G);
+        L.ng = (int)G.meta.size();
+        L.pat_entries = (long)G.ci.size();
+        L.val_entries = (long)G.v.size();
+        for (const GroupMeta &m : G.meta) {
+            double common = 32.0 + 8.0 * m.gs * m.gs + 32.0 * m.gs;
+            L.bytes_lower += (8.0 * m.gs + 4.0) * m.kd + common;
+            L.bytes_upper += (8.0 * m.gs + 4.0) * (m.pad - m.kd - m.gs) + common;
+            L.bytes_full += (8.0 * m.gs + 4.0) * m.pad + 32.0 + 16.0 * m.gs;   // + x once, y once
+        }
+        if (upload_vec(G.meta, &L.meta) || upload_vec(G.ci, &L.gci) || upload_vec(G.v, &L.gv)) return 1;
+    }
+    if (upload_vec(L.plan.stage_group, &L.stage_group) || upload_vec(L.plan.perm, &L.perm)) return 1;
+    CU(cudaMalloc(&L.x, sizeof(double) * std::max(1, n)));
+    CU(cudaMalloc(&L.b, sizeof(double) * std::max(1, n)));
+    CU(cudaMalloc(&L.p1, sizeof(double) * std::max(1, n)));
+    CU(cudaMalloc(&L.r, sizeof(double) * std::max(1, n)));
+    return 0;
+}
+static void free_level(Level &L)
+{
+    free_csr(L.A); free_csr(L.P); free_csr(L.R);
+    cudaFree(L.meta); cudaFree(L.gci); cudaFree(L.gv); cudaFree(L.stage_group); cudaFree(L.perm);
+    cudaFree(L.x); cudaFree(L.b); cudaFree(L.p1); cudaFree(L.r); cudaFree(L.dinv);
+    L.meta = nullptr; L.gci = nullptr; L.gv = nullptr; L.stage_group = nullptr; L.perm = nullptr;
+    L.x = L.b = L.p1 = L.r = L.dinv = nullptr;
+}
+
 static int invert_level0(ddpca_mg *h)
 {
     Level &L0 = h->lev[0];
@@ -506,6 +553,100 @@ static int invert_level0(ddpca_mg *h)
     CU(cudaGetLastError());
     cudaFree(rowk);
     cudaFree(colk);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Sparse direct solver with a host-computed factorisation: x = P^T L^-T D^-1 L^-1 P b, the
+// solve phase of Eigen::SimplicialLDLT (SimplicialCholesky.h:148-171) that the reference uses
+// for the interface mass matrices (MCONTACT.h:2677,2696) and the macroscopic problem (:2553).
+// The two triangular solves reuse the stage machinery: I+L and I+L^T are "levels" whose LEX
+// stages are the exact dependency wavefronts; forward substitution is the forward sweep from
+// zero, back substitution the backward sweep.
+struct ddpca_ldlt : Engine {
+    int n = 0;
+    long nnzL = 0;
+    Level lo, up;
+    int *m_in = nullptr, *m_mid = nullptr, *m_out = nullptr;  // composed index maps
+    double *dinv_lo = nullptr;                                 // 1/D in lo numbering
+};
+
+static void ldlt_solve_on(Engine *e, ddpca_ldlt *s, const double *b_dev, double *x_dev, const int *done)
+{
+    int n = s->n;
+    double tri_bytes = 12.0 * s->nnzL + 44.0 * n;
+    KL(e, DDPCA_K_VECTOR, 0, 20.0 * n, (k_scatter<<<cdiv(n, 256), 256, 0, e->stream>>>(n, s->m_in, b_dev, s->lo.b)));
+    (void)tri_bytes;
+    sweep_fwd(e, s->lo, 0, s->lo.b, s->lo.x, true, done);
+    KL(e, DDPCA_K_VECTOR, 0, 28.0 * n, (k_scatter_scaled<<<cdiv(n, 256), 256, 0, e->stream>>>(n, s->m_mid, s->dinv_lo, s->lo.x, s->up.p1)));
+    sweep_bwd(e, s->up, 0, s->up.x, done);
+    KL(e, DDPCA_K_VECTOR, 0, 20.0 * n, (k_gather<<<cdiv(n, 256), 256, 0, e->stream>>>(n, s->m_out, s->up.x, x_dev)));
+}
+
+static void ldlt_free(ddpca_ldlt *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    free_level(s->lo); free_level(s->up);
+    cudaFree(s->m_in); cudaFree(s->m_mid); cudaFree(s->m_out); cudaFree(s->dinv_lo);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+}
+
+static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const int *Lci, const double *Lv, const double *D, ddpca_ldlt **out)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail("no CUDA device: libddpca_b200 has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail("device index out of range");
+    CU(cudaSetDevice(device));
+    // T_lo = I + L (diagonal last in each row), T_up = I + L^T (diagonal first)
+    CsrHost Tlo, Lh, Lt, Tup;
+    Lh.rows = Lh.cols = n;
+    Lh.rp.assign(Lrp, Lrp + n + 1);
+    Lh.ci.assign(Lci, Lci + Lrp[n]);
+    Lh.v.assign(Lv, Lv + Lrp[n]);
+    for (int i = 0; i < n; i++)
+        for (int p = Lrp[i]; p < Lrp[i + 1]; p++)
+            if (Lci[p] >= i || Lci[p] < 0 || (p > Lrp[i] && Lci[p] <= Lci[p - 1])) return fail("ddpca_ldlt_create: L must be strictly lower with sorted rows");
+    transpose_csr(Lh, Lt);
+    auto add_diag = [&](const CsrHost &T, bool diag_last, CsrHost &o) {
+        o.rows = o.cols = n;
+        o.rp.assign(n + 1, 0);
+        for (int i = 0; i < n; i++) o.rp[i + 1] = o.rp[i] + (T.rp[i + 1] - T.rp[i]) + 1;
+        o.ci.resize(o.rp[n]);
+        o.v.resize(o.rp[n]);
+        for (int i = 0; i < n; i++) {
+            int q = o.rp[i];
+            if (!diag_last) { o.ci[q] = i; o.v[q] = 1.0; q++; }
+            for (int p = T.rp[i]; p < T.rp[i + 1]; p++, q++) { o.ci[q] = T.ci[p]; o.v[q] = T.v[p]; }
+            if (diag_last) { o.ci[q] = i; o.v[q] = 1.0; }
+        }
+    };
+    add_diag(Lh, true, Tlo);
+    add_diag(Lt, false, Tup);
+    ddpca_ldlt *s = new ddpca_ldlt();
+    s->device = device;
+    s->n = n;
+    s->nnzL = Lrp[n];
+    cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail("stream creation failed"); }
+    s->stream = s->own_stream;
+    if (setup_level(s->lo, n, Tlo.rp.data(), Tlo.ci.data(), Tlo.v.data(), DDPCA_SMOOTH_LEX, false, true) ||
+        setup_level(s->up, n, Tup.rp.data(), Tup.ci.data(), Tup.v.data(), DDPCA_SMOOTH_LEX, false, true)) { ldlt_free(s); return 1; }
+    std::vector<int> m_in(n), m_mid(n), m_out(n);
+    std::vector<double> dinv(n);
+    for (int i = 0; i < n; i++) {
+        if (perm[i] < 0 || perm[i] >= n) { ldlt_free(s); return fail("ddpca_ldlt_create: bad permutation"); }
+        m_in[i] = s->lo.plan.iperm[perm[i]];    // (P b)[perm[i]] = b[i], then into lo's stage numbering
+        m_out[i] = s->up.plan.iperm[perm[i]];   // x[i] = y[perm[i]]
+    }
+    for (int j = 0; j < n; j++) {
+        int o = s->lo.plan.perm[j];
+        m_mid[j] = s->up.plan.iperm[o];
+        dinv[j] = 1.0 / D[o];
+    }
+    if (upload_vec(m_in, &s->m_in) || upload_vec(m_mid, &s->m_mid) || upload_vec(m_out, &s->m_out) || upload_vec(dinv, &s->dinv_lo)) { ldlt_free(s); return 1; }
+    *out = s;
     return 0;
 }
 
@@ -555,11 +696,7 @@ int ddpca_mg_destroy(ddpca_mg *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    for (auto &L : h->lev) {
-        free_csr(L.A); free_csr(L.P); free_csr(L.R);
-        cudaFree(L.meta); cudaFree(L.gci); cudaFree(L.gv); cudaFree(L.stage_group); cudaFree(L.perm);
-        cudaFree(L.x); cudaFree(L.b); cudaFree(L.p1); cudaFree(L.r); cudaFree(L.dinv);
-    }
+    for (auto &L : h->lev) free_level(L);
     cudaFree(h->Binv);
     cudaFree(h->cg_r); cudaFree(h->cg_p); cudaFree(h->cg_q); cudaFree(h->cg_z); cudaFree(h->cg_x);
     cudaFree(h->stage_a); cudaFree(h->stage_b);
@@ -584,9 +721,6 @@ int ddpca_mg_create(int device, int nlevels, const int *n, const int *const *row
     if (device < 0 || device >= ndev) return fail("device index out of range");
     CU(cudaSetDevice(device));
     ddpca_mg *h = new ddpca_mg();
-    std::memset(h->prof_ms, 0, sizeof(h->prof_ms));
-    std::memset(h->prof_n, 0, sizeof(h->prof_n));
-    std::memset(h->prof_bytes, 0, sizeof(h->prof_bytes));
     h->device = device;
     h->mode = smoother_mode;
     h->nlev = nlevels;
@@ -600,45 +734,14 @@ int ddpca_mg_create(int device, int nlevels, const int *n, const int *const *row
     int nmax = 0;
     for (int l = 0; l < nlevels; l++) {
         Level &L = h->lev[l];
-        L.n = n[l];
         nmax = std::max(nmax, n[l]);
-        std::string err;
-        int mode = (l == 0 && nlevels > 1) ? -1 : smoother_mode;
-        if (l == 0 && nlevels == 1) mode = -1;
-        if (!build_level_plan(n[l], rowptr[l], colidx[l], mode, L.plan, err)) {
-            g_err = "level " + std::to_string(l) + ": " + err;
+        int mode = (l == 0) ? -1 : smoother_mode;   // level 0 is only ever solved directly
+        bool coarse_only = (l == 0 && nlevels > 1);
+        if (setup_level(L, n[l], rowptr[l], colidx[l], val[l], mode, /*keep_csr=*/l == 0, /*group_layout=*/!coarse_only)) {
+            g_err = "level " + std::to_string(l) + ": " + g_err;
             ddpca_mg_destroy(h);
             return 1;
         }
-        CsrHost Ap;
-        permute_csr(n[l], n[l], rowptr[l], colidx[l], val[l], L.plan.perm, L.plan.iperm, Ap);
-        L.nnz = Ap.nnz();
-        if (l == 0 && nlevels > 1) {
-            FAILC(upload_csr(Ap, L.A));   // level 0 is only ever solved directly
-        } else {
-            GroupLayoutHost G;
-            if (!build_group_layout(Ap, L.plan, G, err)) { g_err = "level " + std::to_string(l) + ": " + err; ddpca_mg_destroy(h); return 1; }
-            if (l == 0) FAILC(upload_csr(Ap, L.A));
-            if (mode >= 0) build_segments(L, G);
-            L.ng = (int)G.meta.size();
-            L.pat_entries = (long)G.ci.size();
-            L.val_entries = (long)G.v.size();
-            for (const GroupMeta &m : G.meta) {
-                double common = 32.0 + 8.0 * m.gs * m.gs + 32.0 * m.gs;
-                L.bytes_lower += (8.0 * m.gs + 4.0) * m.kd + common;
-                L.bytes_upper += (8.0 * m.gs + 4.0) * (m.pad - m.kd - m.gs) + common;
-                L.bytes_full += (8.0 * m.gs + 4.0) * m.pad + 32.0 + 16.0 * m.gs;   // + x once, y once
-            }
-            FAILC(upload_vec(G.meta, &L.meta));
-            FAILC(upload_vec(G.ci, &L.gci));
-            FAILC(upload_vec(G.v, &L.gv));
-        }
-        FAILC(upload_vec(L.plan.stage_group, &L.stage_group));
-        FAILC(upload_vec(L.plan.perm, &L.perm));
-        CUC(cudaMalloc(&L.x, sizeof(double) * std::max(1, n[l])));
-        CUC(cudaMalloc(&L.b, sizeof(double) * std::max(1, n[l])));
-        CUC(cudaMalloc(&L.p1, sizeof(double) * std::max(1, n[l])));
-        CUC(cudaMalloc(&L.r, sizeof(double) * std::max(1, n[l])));
         if (l >= 1) {
             if (!P_rowptr || !P_colidx || !P_val) { g_err = "prolongation operators missing"; ddpca_mg_destroy(h); return 1; }
             CsrHost Pp, Rp;
@@ -747,7 +850,7 @@ int ddpca_mg_spmv(ddpca_mg *h, int level, const double *x, double *y)
     if (!h || level < 0 || level >= h->nlev || !x || !y) return fail("ddpca_mg_spmv: bad argument");
     CU(cudaSetDevice(h->device));
     if (to_dev(h, level, x, h->cg_p)) return 1;
-    if (h->lev[level].meta) launch_level_spmv(h, level, h->cg_p, h->cg_q, nullptr, nullptr, nullptr);
+    if (h->lev[level].meta) launch_level_spmv(h, h->lev[level], level, h->cg_p, h->cg_q, nullptr, nullptr, nullptr);
     else launch_spmv(h, DDPCA_K_SPMV, level, h->lev[level].A, h->cg_p, h->cg_q, false, nullptr, nullptr, nullptr);
     if (h->profile) h->prof_collect();
     return to_host(h, level, h->cg_q, y);
@@ -787,6 +890,44 @@ int ddpca_mg_coarse_solve(ddpca_mg *h, const double *b, double *x)
 int ddpca_mg_mult_solv(ddpca_mg *, const double *, double *, long *, double *) { return fail("ddpca_mg_mult_solv: not implemented yet"); }
 int ddpca_mg_bicgstab(ddpca_mg *, int, const double *, double *, double, long, long *, double *, double *) { return fail("ddpca_mg_bicgstab: not implemented yet"); }
 
+int ddpca_ldlt_create(int device, int n, const int *perm, const int *L_rowptr, const int *L_colidx, const double *L_val,
+                      const double *D, ddpca_ldlt **out)
+{
+    if (!out || n < 1 || !perm || !L_rowptr || !L_colidx || !L_val || !D) return fail("ddpca_ldlt_create: bad argument");
+    return ldlt_build(device, n, perm, L_rowptr, L_colidx, L_val, D, out);
+}
+int ddpca_ldlt_destroy(ddpca_ldlt *s) { ldlt_free(s); return 0; }
+int ddpca_ldlt_solve_dev(ddpca_ldlt *s, const double *b_dev, double *x_dev)
+{
+    if (!s || !b_dev || !x_dev) return fail("ddpca_ldlt_solve_dev: bad argument");
+    CU(cudaSetDevice(s->device));
+    ldlt_solve_on(s, s, b_dev, x_dev, nullptr);
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+int ddpca_ldlt_solve(ddpca_ldlt *s, const double *b, double *x)
+{
+    if (!s || !b || !x) return fail("ddpca_ldlt_solve: bad argument");
+    CU(cudaSetDevice(s->device));
+    // lo.r / up.r are free work vectors of length n
+    CU(cudaMemcpyAsync(s->lo.r, b, sizeof(double) * s->n, cudaMemcpyHostToDevice, s->stream));
+    ldlt_solve_on(s, s, s->lo.r, s->up.r, nullptr);
+    CU(cudaMemcpyAsync(x, s->up.r, sizeof(double) * s->n, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+int ddpca_ldlt_info(const ddpca_ldlt *s, int *n, long *nnzL, int *stages_fwd, int *stages_bwd)
+{
+    if (!s) return fail("null handle");
+    if (n) *n = s->n;
+    if (nnzL) *nnzL = s->nnzL;
+    if (stages_fwd) *stages_fwd = s->lo.plan.nstages();
+    if (stages_bwd) *stages_bwd = s->up.plan.nstages();
+    return 0;
+}
+
 int ddpca_mg_level_info(const ddpca_mg *h, int level, long *n, long *nnz, int *ngroups, int *nstages)
 {
     if (!h || level < 0 || level >= h->nlev) return fail("ddpca_mg_level_info: bad argument");
@@ -808,11 +949,7 @@ int ddpca_mg_profile(ddpca_mg *h, int enable)
 {
     if (!h) return fail("null handle");
     h->profile = enable != 0;
-    if (enable) {
-        std::memset(h->prof_ms, 0, sizeof(h->prof_ms));
-        std::memset(h->prof_n, 0, sizeof(h->prof_n));
-        std::memset(h->prof_bytes, 0, sizeof(h->prof_bytes));
-    }
+    if (enable) h->prof_reset();
     return 0;
 }
 int ddpca_mg_profile_get(ddpca_mg *h, int kclass, int level, double *ms, long *launches, double *bytes)

@@ -106,6 +106,23 @@ int ddpca_mg_mult_solv(ddpca_mg *, const double *b, double *x, long *iters, doub
 int ddpca_mg_bicgstab(ddpca_mg *, int prec, const double *b, double *x, double rel_tol, long maxit,
                       long *iters, double *resid, double *tol_abs);
 
+/* ---- DIRE_SOLV: sparse direct solves with a host-computed factorisation --------
+ * The reference factorises the interface mass matrices and the macroscopic problem
+ * once, on the host, with Eigen::SimplicialLDLT (typedef DIRE_SOLV, PREP.h:107;
+ * MCONTACT.h:837-847, :1229-1230) -- setup, out of scope -- and calls .solve() in
+ * every ADMM iteration (MCONTACT.h:2553,2677,2696).  ddpca_ldlt_* is that solve phase
+ * on the device: x = P^T L^-T D^-1 L^-1 P b (SimplicialCholesky.h:148-171).
+ *   perm[i]  = solver.permutationP().indices()[i]
+ *   L        = strictly-lower unit factor, RowMajor CSR (solver.matrixL() without diagonal)
+ *   D        = solver.vectorD()                                                      */
+typedef struct ddpca_ldlt ddpca_ldlt;
+int ddpca_ldlt_create(int device, int n, const int *perm, const int *L_rowptr, const int *L_colidx, const double *L_val,
+                      const double *D, ddpca_ldlt **out);
+int ddpca_ldlt_solve(ddpca_ldlt *, const double *b, double *x);
+int ddpca_ldlt_solve_dev(ddpca_ldlt *, const double *b_dev, double *x_dev);
+int ddpca_ldlt_info(const ddpca_ldlt *, int *n, long *nnzL, int *stages_fwd, int *stages_bwd);
+int ddpca_ldlt_destroy(ddpca_ldlt *);
+
 /* ---- introspection / measurement -------------------------------------------*/
 /* rows, nnz, number of row groups and stages of a level's device layout */
 int ddpca_mg_level_info(const ddpca_mg *, int level, long *n, long *nnz, int *ngroups, int *nstages);

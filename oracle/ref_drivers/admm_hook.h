@@ -48,6 +48,20 @@ static void DUMP_TABLE(DDPK_WRITER &w, const std::string &name, const std::vecto
 	w.f64(name, flat.data(), flat.size());
 }
 
+// A factorised DIRE_SOLV (Eigen::SimplicialLDLT, PREP.h:107) as plain arrays: fill-reducing
+// permutation p (solve does y[p[i]] = b[i], SimplicialCholesky.h:148-171), strictly-lower unit
+// factor L in RowMajor CSR and the diagonal D.  x = P^T L^-T D^-1 L^-1 P b.
+static void DUMP_LDLT(DDPK_WRITER &w, const std::string &name, const DIRE_SOLV &sol) {
+	if (sol.info() != Eigen::Success || sol.rows() == 0) return;
+	Eigen::SparseMatrix<double, Eigen::RowMajor> L = sol.matrixL().nestedExpression();
+	w.csr(name + ".L", L);
+	Eigen::VectorXd D = sol.vectorD();
+	w.vec(name + ".D", D);
+	std::vector<int> p(sol.rows());
+	for (long i = 0; i < sol.rows(); i++) p[i] = sol.permutationP().indices()(i);
+	w.i32(name + ".perm", p.data(), p.size());
+}
+
 inline long ADMM_HOOK(MCONTACT &mc) {
 	typedef Eigen::SparseMatrix<double, Eigen::RowMajor> SPM;
 	const long nb = mc.multGrid.size(), ni = mc.searCont.size();
@@ -106,6 +120,10 @@ inline long ADMM_HOOK(MCONTACT &mc) {
 				w->csr(q + "inpoLagr", mc.inpoLagr[ts][tv]);
 				w->csr(q + "inteInpo", mc.inteInpo[ts][tv]);
 				w->csr(q + "pemaInpo_r", mc.pemaInpo_r[ts][tv]);
+				if (mc.inteMass[ts][tv].rows() < DIRE_MAXI) {   // MCONTACT.h:837-847
+					DUMP_LDLT(*w, q + "inteDiso", mc.inteDiso[ts][tv]);
+					DUMP_LDLT(*w, q + "inteDiso_pena", mc.inteDiso_pena[ts][tv]);
+				}
 				if (mc.muscSett & 1) {
 					w->csr(q + "globTran", mc.globTran[ts][tv]);
 					w->csr(q + "globTran_pena", mc.globTran_pena[ts][tv]);
@@ -115,6 +133,7 @@ inline long ADMM_HOOK(MCONTACT &mc) {
 		}
 		if (mc.muscSett & 1) {
 			w->csr("globCoup", mc.globCoup);
+			if (mc.globCoup.rows() < DIRE_MAXI) DUMP_LDLT(*w, "coarSolv_D", mc.coarSolv_D);   // MCONTACT.h:1229-1230
 			w->i64("baseReco", mc.baseReco.data(), mc.baseReco.size());
 		}
 	}
