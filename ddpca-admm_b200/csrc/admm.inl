@@ -1,0 +1,431 @@
+// admm.inl -- device-resident ADMM iteration of MCONTACT::CONTACT_ANALYSIS (MCONTACT.h:2493-2723).
+// Included at the end of mg.cu (one translation unit: the kernels of kernels.cuh are shared).
+//
+// State lives in HBM for the whole loop: resuDisp[v], inteAuxi[ts][tv],
+// inteLagr[ts][tv] and their previous-iteration copies (MONITOR needs the differences).
+// Operators (a13) are the reference's own matrices, uploaded once after MCONTACT::ESTABLISH.
+// One ddpca_admm_step() = one pass of the loop body (:2505-2704) + the MONITOR norms
+// (:2737-2833); the stopping logic itself (ring buffers, VECT_MEDI_OSCI, MULT_MAXI) is scalar
+// host logic and stays with the caller (host mirror of MCONTACT).
+
+namespace {
+
+struct AdmmBody {
+    ddpca_mg *mg = nullptr;
+    int nfull = 0, nred = 0;
+    double *consForc = nullptr, *dispCons = nullptr;
+    DevCsr F, FT;          // forcOper (nred x nfull) and its transpose (OUTP_SUB1 = FT u + dispCons)
+    DevCsr accuProl;       // macroscopic problem only
+    double *disp = nullptr, *disp_prev = nullptr, *addi = nullptr, *rhs = nullptr, *u = nullptr;
+    bool set = false;
+};
+struct AdmmSide {
+    DevCsr op[10];
+    DevCsr systTran_penaT;
+    ddpca_ldlt *mass = nullptr, *mass_pena = nullptr;
+    double *aux = nullptr, *lagr = nullptr, *aux_prev = nullptr, *lagr_prev = nullptr, *force = nullptr, *tmp = nullptr;
+    int nc = 0;   // d * n_c
+};
+struct AdmmIface {
+    int body[2] = {-1, -1};
+    double fric = 0.0;
+    int nip = 0, d = 1;
+    double *gap = nullptr, *t = nullptr, *gamma = nullptr;
+    int *stat = nullptr;
+    AdmmSide side[2];
+    bool set = false;
+};
+
+}  // namespace
+
+struct ddpca_admm : Engine {
+    int nb = 0, ni = 0, muscSett = 0;
+    std::vector<AdmmBody> body;
+    std::vector<AdmmIface> iface;
+    int nglob = 0;
+    std::vector<long> baseReco;
+    ddpca_ldlt *coar = nullptr;
+    double *globForc = nullptr, *globSolu = nullptr;
+    double *moni_part = nullptr, *moni_out = nullptr;
+    double *moni_host = nullptr;
+    int nslots = 0;
+    bool finalized = false;
+    long cg_iters = 0;        // CG iterations of the last step, all bodies
+    double cg_dof_iters = 0;  // sum over bodies of n_L * iterations, last step
+};
+
+static void admm_free(ddpca_admm *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto &b : h->body) {
+        if (b.mg) ddpca_mg_destroy(b.mg);
+        cudaFree(b.consForc); cudaFree(b.dispCons); free_csr(b.F); free_csr(b.FT); free_csr(b.accuProl);
+        cudaFree(b.disp); cudaFree(b.disp_prev); cudaFree(b.addi); cudaFree(b.rhs); cudaFree(b.u);
+    }
+    for (auto &f : h->iface) {
+        cudaFree(f.gap); cudaFree(f.t); cudaFree(f.gamma); cudaFree(f.stat);
+        for (auto &s : f.side) {
+            for (auto &o : s.op) free_csr(o);
+            free_csr(s.systTran_penaT);
+            ldlt_free(s.mass); ldlt_free(s.mass_pena);
+            cudaFree(s.aux); cudaFree(s.lagr); cudaFree(s.aux_prev); cudaFree(s.lagr_prev); cudaFree(s.force); cudaFree(s.tmp);
+        }
+    }
+    ldlt_free(h->coar);
+    cudaFree(h->globForc); cudaFree(h->globSolu); cudaFree(h->moni_part); cudaFree(h->moni_out);
+    if (h->moni_host) cudaFreeHost(h->moni_host);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+static int host_csr(int rows, int cols, const int *rp, const int *ci, const double *v, CsrHost &o)
+{
+    if (rows < 0 || cols < 0 || !rp) return fail("bad CSR argument");
+    o.rows = rows; o.cols = cols;
+    o.rp.assign(rp, rp + rows + 1);
+    long nnz = rp[rows];
+    if (nnz && (!ci || !v)) return fail("bad CSR argument");
+    o.ci.assign(ci, ci + nnz);
+    o.v.assign(v, v + nnz);
+    for (long p = 0; p < nnz; p++) if (ci[p] < 0 || ci[p] >= cols) return fail("CSR column index out of range");
+    return 0;
+}
+
+static int dev_vec(const double *host, int n, double **d)
+{
+    CU(cudaMalloc(d, sizeof(double) * std::max(1, n)));
+    if (host) CU(cudaMemcpy(*d, host, sizeof(double) * n, cudaMemcpyHostToDevice));
+    else CU(cudaMemset(*d, 0, sizeof(double) * std::max(1, n)));
+    return 0;
+}
+
+#define ADMM_SPMV(A, x, y, add, alpha) launch_spmv(h, DDPCA_K_VECTOR, 15, (A), (x), (y), (add), nullptr, nullptr, nullptr, (alpha))
+
+// MONITOR's two sums for one state vector -> slot
+static void admm_moni(ddpca_admm *h, int slot, int n, const double *cur, const double *prev)
+{
+    KL(h, DDPCA_K_VECTOR, 15, 16.0 * n, (k_moni_partial<<<kMoniBlocks, 256, 0, h->stream>>>(n, cur, prev, h->moni_part + (size_t)slot * 2 * kMoniBlocks)));
+}
+
+static int admm_step(ddpca_admm *h, int apply_macro, double *monitor_row)
+{
+    cudaStream_t st = h->stream;
+    h->cg_iters = 0;
+    h->cg_dof_iters = 0;
+    // ---- body balance, MCONTACT.h:2511-2538 --------------------------------------------------
+    for (int v = 0; v < h->nb; v++) {
+        AdmmBody &b = h->body[v];
+        CU(cudaMemcpyAsync(b.disp_prev, b.disp, sizeof(double) * b.nfull, cudaMemcpyDeviceToDevice, st));  // :2507
+        CU(cudaMemsetAsync(b.addi, 0, sizeof(double) * b.nfull, st));                                       // :2514
+        for (int ts = 0; ts < h->ni; ts++)
+            for (int ti = 0; ti < 2; ti++) {
+                AdmmIface &f = h->iface[ts];
+                if (f.body[ti] != v) continue;
+                ADMM_SPMV(f.side[ti].op[DDPCA_OP_SYSTTRAN_PENA], f.side[ti].aux, b.addi, true, 1.0);   // :2520
+                ADMM_SPMV(f.side[ti].op[DDPCA_OP_SYSTTRAN], f.side[ti].lagr, b.addi, true, -1.0);      // :2521
+            }
+        CU(cudaMemcpyAsync(b.rhs, b.consForc, sizeof(double) * b.nred, cudaMemcpyDeviceToDevice, st));
+        ADMM_SPMV(b.F, b.addi, b.rhs, true, 1.0);   // ADDITIONAL_FORCE :2524 ; consForc + addiForc :2531
+        long it = 0;
+        ddpca_mg_set_stream(b.mg, (void *)st);
+        if (pcg_device(b.mg, 1, b.rhs, b.u, 1.0e-14, b.nred, &it, nullptr, nullptr)) return 1;   // :2531 (MG-PCG for every body)
+        h->launches += ddpca_mg_launch_count(b.mg, 1);
+        h->cg_iters += it;
+        h->cg_dof_iters += (double)it * b.nred;
+        CU(cudaMemcpyAsync(b.disp, b.dispCons, sizeof(double) * b.nfull, cudaMemcpyDeviceToDevice, st));
+        ADMM_SPMV(b.FT, b.u, b.disp, true, 1.0);    // OUTP_SUB1 :2533
+    }
+    // ---- macroscopic problem, :2540-2573 -----------------------------------------------------------
+    if (apply_macro) {
+        if (!h->coar) return fail("ddpca_admm_step: macroscopic problem requested but not set");
+        CU(cudaMemsetAsync(h->globForc, 0, sizeof(double) * h->nglob, st));
+        for (int ts = 0; ts < h->ni; ts++)
+            for (int tv = 0; tv < 2; tv++) {
+                AdmmIface &f = h->iface[ts];
+                AdmmSide &s = f.side[tv];
+                ADMM_SPMV(s.op[DDPCA_OP_GLOBTRAN], s.lagr, h->globForc, true, 1.0);                       // :2545
+                ADMM_SPMV(s.op[DDPCA_OP_GLOBTRAN_PENA], s.aux, h->globForc, true, -1.0);                  // :2546
+                ADMM_SPMV(s.op[DDPCA_OP_GLOBTRAN_D], h->body[f.body[tv]].disp, h->globForc, true, 1.0);   // :2547
+            }
+        ldlt_solve_on(h, h->coar, h->globForc, h->globSolu, nullptr);   // :2553
+        for (int v = 0; v < h->nb; v++) {
+            AdmmBody &b = h->body[v];
+            ADMM_SPMV(b.accuProl, h->globSolu + h->baseReco[v], b.u, false, 1.0);   // :2564-2567
+            ADMM_SPMV(b.FT, b.u, b.disp, true, 1.0);                                 // :2569-2570 (OUTP_SUB1 ...
+            KL(h, DDPCA_K_VECTOR, 15, 24.0 * b.nfull, (k_axpy<<<cdiv(b.nfull, 256), 256, 0, st>>>(b.nfull, 1.0, b.dispCons, b.disp)));  // ... re-adds prescribed values)
+        }
+    }
+    // ---- interface balance, :2628-2685 ------------------------------------------------------------------
+    for (int ts = 0; ts < h->ni; ts++) {
+        AdmmIface &f = h->iface[ts];
+        int ng = f.d * f.nip;
+        ADMM_SPMV(f.side[0].op[DDPCA_OP_INPOLAGR], f.side[0].lagr, f.t, false, 1.0);                // :2632
+        ADMM_SPMV(f.side[1].op[DDPCA_OP_INPOLAGR], f.side[1].lagr, f.t, true, -1.0);                // :2633
+        ADMM_SPMV(f.side[0].op[DDPCA_OP_PEMAINPO_R], h->body[f.body[0]].disp, f.t, true, 1.0);      // :2634
+        ADMM_SPMV(f.side[1].op[DDPCA_OP_PEMAINPO_R], h->body[f.body[1]].disp, f.t, true, -1.0);     // :2635
+        KL(h, DDPCA_K_VECTOR, 15, 28.0 * ng, (k_gamma_project<<<cdiv(f.nip, 256), 256, 0, st>>>(f.nip, f.d, f.fric, f.t, f.gap, f.gamma, f.stat)));  // :2636-2668
+        for (int tv = 0; tv < 2; tv++) {
+            AdmmSide &s = f.side[tv];
+            ADMM_SPMV(s.systTran_penaT, h->body[f.body[tv]].disp, s.force, false, 1.0);   // :2673
+            ADMM_SPMV(s.op[DDPCA_OP_INTEMASS], s.lagr, s.force, true, 1.0);               // :2674
+            ADMM_SPMV(s.op[DDPCA_OP_INTEINPO], f.gamma, s.force, true, 1.0);              // :2675
+            CU(cudaMemcpyAsync(s.aux_prev, s.aux, sizeof(double) * s.nc, cudaMemcpyDeviceToDevice, st));   // :2508
+            ldlt_solve_on(h, s.mass_pena, s.force, s.aux, nullptr);                       // :2677
+        }
+    }
+    // ---- Lagrange multiplier, :2689-2704 ------------------------------------------------------------------
+    for (int ts = 0; ts < h->ni; ts++) {
+        AdmmIface &f = h->iface[ts];
+        for (int tv = 0; tv < 2; tv++) {
+            AdmmSide &s = f.side[tv];
+            ADMM_SPMV(s.systTran_penaT, h->body[f.body[tv]].disp, s.force, false, 1.0);   // :2693
+            ADMM_SPMV(s.op[DDPCA_OP_INTEMASS_PENA], s.aux, s.force, true, -1.0);          // :2694
+            ldlt_solve_on(h, s.mass, s.force, s.tmp, nullptr);                            // :2696
+            CU(cudaMemcpyAsync(s.lagr_prev, s.lagr, sizeof(double) * s.nc, cudaMemcpyDeviceToDevice, st));   // :2509
+            KL(h, DDPCA_K_VECTOR, 15, 24.0 * s.nc, (k_axpy<<<cdiv(s.nc, 256), 256, 0, st>>>(s.nc, 1.0, s.tmp, s.lagr)));
+        }
+    }
+    // ---- MONITOR sums, :2737-2833 ------------------------------------------------------------------------------
+    for (int v = 0; v < h->nb; v++) admm_moni(h, v, h->body[v].nfull, h->body[v].disp, h->body[v].disp_prev);
+    for (int ts = 0; ts < h->ni; ts++)
+        for (int tv = 0; tv < 2; tv++) {
+            AdmmSide &s = h->iface[ts].side[tv];
+            int slot = h->nb + 4 * ts + 2 * tv;   // tempIndi of :2771
+            admm_moni(h, slot, s.nc, s.aux, s.aux_prev);
+            admm_moni(h, slot + 1, s.nc, s.lagr, s.lagr_prev);
+        }
+    KL(h, DDPCA_K_VECTOR, 15, 0.0, (k_moni_final<<<h->nslots, 32, 0, st>>>(h->moni_part, h->moni_out)));
+    CU(cudaMemcpyAsync(h->moni_host, h->moni_out, sizeof(double) * 2 * h->nslots, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (h->profile) h->prof_collect();
+    if (monitor_row) {
+        // row layout of resuMoni.txt (:2742-2743, :2777-2778, :2807-2808, :2835)
+        double convValu = 0.0, convCrit = 0.0;
+        int c = 0;
+        for (int v = 0; v < h->nb; v++) {
+            monitor_row[c++] = h->moni_host[2 * v];
+            monitor_row[c++] = h->moni_host[2 * v + 1];
+            convValu += h->moni_host[2 * v];
+            convCrit += h->moni_host[2 * v + 1];
+        }
+        for (int ts = 0; ts < h->ni; ts++)
+            for (int tv = 0; tv < 2; tv++) {
+                int slot = h->nb + 4 * ts + 2 * tv;
+                monitor_row[c++] = h->moni_host[2 * slot];
+                monitor_row[c++] = h->moni_host[2 * slot + 1];
+                convValu += h->moni_host[2 * slot];
+                convCrit += h->moni_host[2 * slot + 1];
+                monitor_row[c++] = h->moni_host[2 * (slot + 1)];
+                monitor_row[c++] = h->moni_host[2 * (slot + 1) + 1];
+            }
+        monitor_row[c++] = convValu;
+        monitor_row[c++] = convCrit;
+    }
+    return 0;
+}
+
+extern "C" {
+
+int ddpca_admm_create(int device, int nbody, int niface, int muscSett, ddpca_admm **out)
+{
+    if (!out || nbody < 1 || niface < 0) return fail("ddpca_admm_create: bad argument");
+    if (muscSett & ~1) return fail("ddpca_admm_create: only muscSett bit 0 (macroscopic problem) is supported");
+    int ndev = ddpca_device_count();
+    if (ndev == 0) return fail("no CUDA device: libddpca_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("device index out of range");
+    CU(cudaSetDevice(device));
+    ddpca_admm *h = new ddpca_admm();
+    h->device = device;
+    h->nb = nbody; h->ni = niface; h->muscSett = muscSett;
+    h->body.resize(nbody);
+    h->iface.resize(niface);
+    cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail("stream creation failed"); }
+    h->stream = h->own_stream;
+    *out = h;
+    return 0;
+}
+
+int ddpca_admm_destroy(ddpca_admm *h) { admm_free(h); return 0; }
+
+int ddpca_admm_set_body(ddpca_admm *h, int v, ddpca_mg *mg, int nfull, const double *consForc, const int *F_rowptr,
+                        const int *F_colidx, const double *F_val, const double *dispCons)
+{
+    if (!h || v < 0 || v >= h->nb || !mg || nfull < 1 || !consForc || !F_rowptr || !dispCons) return fail("ddpca_admm_set_body: bad argument");
+    if (mg->device != h->device) return fail("ddpca_admm_set_body: hierarchy lives on another device");
+    CU(cudaSetDevice(h->device));
+    AdmmBody &b = h->body[v];
+    if (b.set) return fail("ddpca_admm_set_body: body already set");
+    b.mg = mg;
+    b.nfull = nfull;
+    b.nred = mg->lev[mg->nlev - 1].n;
+    CsrHost F, FT;
+    if (host_csr(b.nred, nfull, F_rowptr, F_colidx, F_val, F)) return 1;
+    transpose_csr(F, FT);
+    if (upload_csr(F, b.F) || upload_csr(FT, b.FT)) return 1;
+    if (dev_vec(consForc, b.nred, &b.consForc) || dev_vec(dispCons, nfull, &b.dispCons)) return 1;
+    if (dev_vec(nullptr, nfull, &b.disp) || dev_vec(nullptr, nfull, &b.disp_prev) || dev_vec(nullptr, nfull, &b.addi)) return 1;
+    if (dev_vec(nullptr, b.nred, &b.rhs) || dev_vec(nullptr, b.nred, &b.u)) return 1;
+    b.set = true;
+    return 0;
+}
+
+int ddpca_admm_set_body_accuprol(ddpca_admm *h, int v, int rows, int cols, const int *rowptr, const int *colidx, const double *val)
+{
+    if (!h || v < 0 || v >= h->nb || !h->body[v].set) return fail("ddpca_admm_set_body_accuprol: bad argument");
+    if (rows != h->body[v].nred) return fail("accuProl must have n_L rows");
+    CU(cudaSetDevice(h->device));
+    CsrHost A;
+    if (host_csr(rows, cols, rowptr, colidx, val, A)) return 1;
+    return upload_csr(A, h->body[v].accuProl);
+}
+
+int ddpca_admm_set_interface(ddpca_admm *h, int ts, int body0, int body1, double fricCoef, int nip, const double *gapTerm)
+{
+    if (!h || ts < 0 || ts >= h->ni || body0 < 0 || body0 >= h->nb || body1 < 0 || body1 >= h->nb || nip < 0 || !gapTerm)
+        return fail("ddpca_admm_set_interface: bad argument");
+    CU(cudaSetDevice(h->device));
+    AdmmIface &f = h->iface[ts];
+    if (f.set) return fail("interface already set");
+    f.body[0] = body0; f.body[1] = body1;
+    f.fric = fricCoef;
+    f.nip = nip;
+    f.d = (fricCoef == 0.0) ? 1 : 3;   // MCONTACT.h:886-893
+    int ng = f.d * nip;
+    if (dev_vec(gapTerm, ng, &f.gap) || dev_vec(nullptr, ng, &f.t) || dev_vec(nullptr, ng, &f.gamma)) return 1;
+    CU(cudaMalloc(&f.stat, sizeof(int) * std::max(1, ng)));
+    CU(cudaMemset(f.stat, 0, sizeof(int) * std::max(1, ng)));
+    f.set = true;
+    return 0;
+}
+
+int ddpca_admm_set_side_op(ddpca_admm *h, int ts, int tv, int op, int rows, int cols, const int *rowptr, const int *colidx, const double *val)
+{
+    if (!h || ts < 0 || ts >= h->ni || tv < 0 || tv > 1 || op < 0 || op >= DDPCA_OP_COUNT || !h->iface[ts].set) return fail("ddpca_admm_set_side_op: bad argument");
+    CU(cudaSetDevice(h->device));
+    AdmmSide &s = h->iface[ts].side[tv];
+    CsrHost A;
+    if (host_csr(rows, cols, rowptr, colidx, val, A)) return 1;
+    if (op == DDPCA_OP_INTEMASS) s.nc = rows;
+    if (upload_csr(A, s.op[op])) return 1;
+    if (op == DDPCA_OP_SYSTTRAN_PENA) {
+        CsrHost T;
+        transpose_csr(A, T);
+        if (upload_csr(T, s.systTran_penaT)) return 1;
+    }
+    return 0;
+}
+
+int ddpca_admm_set_side_solver(ddpca_admm *h, int ts, int tv, int which, ddpca_ldlt *sol)
+{
+    if (!h || ts < 0 || ts >= h->ni || tv < 0 || tv > 1 || !sol || (which != DDPCA_SOLVER_MASS && which != DDPCA_SOLVER_MASS_PENA)) return fail("ddpca_admm_set_side_solver: bad argument");
+    if (sol->device != h->device) return fail("solver lives on another device");
+    AdmmSide &s = h->iface[ts].side[tv];
+    if (which == DDPCA_SOLVER_MASS) { ldlt_free(s.mass); s.mass = sol; }
+    else { ldlt_free(s.mass_pena); s.mass_pena = sol; }
+    return 0;
+}
+
+int ddpca_admm_set_macro(ddpca_admm *h, int nglob, const long *baseReco, ddpca_ldlt *coarSolv)
+{
+    if (!h || nglob < 1 || !baseReco || !coarSolv) return fail("ddpca_admm_set_macro: bad argument");
+    if (coarSolv->n != nglob) return fail("coarse solver size does not match globCoup");
+    CU(cudaSetDevice(h->device));
+    h->nglob = nglob;
+    h->baseReco.assign(baseReco, baseReco + h->nb + 1);
+    ldlt_free(h->coar);
+    h->coar = coarSolv;
+    if (dev_vec(nullptr, nglob, &h->globForc) || dev_vec(nullptr, nglob, &h->globSolu)) return 1;
+    return 0;
+}
+
+int ddpca_admm_finalize(ddpca_admm *h)
+{
+    if (!h) return fail("null handle");
+    CU(cudaSetDevice(h->device));
+    for (int v = 0; v < h->nb; v++) {
+        if (!h->body[v].set) return fail("body " + std::to_string(v) + " not set");
+        if ((h->muscSett & 1) && h->body[v].accuProl.rows == 0) return fail("body " + std::to_string(v) + ": accuProl missing");
+        if ((h->muscSett & 1) && h->baseReco.size() == (size_t)h->nb + 1 && h->baseReco[v] + h->body[v].accuProl.cols > h->nglob) return fail("baseReco out of range");
+    }
+    if ((h->muscSett & 1) && !h->coar) return fail("macroscopic problem not set");
+    for (int ts = 0; ts < h->ni; ts++) {
+        AdmmIface &f = h->iface[ts];
+        if (!f.set) return fail("interface " + std::to_string(ts) + " not set");
+        for (int tv = 0; tv < 2; tv++) {
+            AdmmSide &s = f.side[tv];
+            int need[] = {DDPCA_OP_SYSTTRAN, DDPCA_OP_SYSTTRAN_PENA, DDPCA_OP_INTEMASS, DDPCA_OP_INTEMASS_PENA, DDPCA_OP_INPOLAGR, DDPCA_OP_INTEINPO, DDPCA_OP_PEMAINPO_R};
+            for (int o : need) if (s.op[o].rows == 0 && s.op[o].rp == nullptr) return fail("interface " + std::to_string(ts) + " side " + std::to_string(tv) + ": operator " + std::to_string(o) + " missing");
+            if (h->muscSett & 1)
+                for (int o : {DDPCA_OP_GLOBTRAN, DDPCA_OP_GLOBTRAN_PENA, DDPCA_OP_GLOBTRAN_D}) if (s.op[o].rp == nullptr) return fail("macroscopic transfer operator missing");
+            if (!s.mass || !s.mass_pena) return fail("interface " + std::to_string(ts) + " side " + std::to_string(tv) + ": mass solvers missing");
+            int ng = f.d * f.nip, nfull = h->body[f.body[tv]].nfull;
+            if (s.op[DDPCA_OP_SYSTTRAN].rows != nfull || s.op[DDPCA_OP_SYSTTRAN].cols != s.nc || s.op[DDPCA_OP_INPOLAGR].rows != ng ||
+                s.op[DDPCA_OP_INTEINPO].rows != s.nc || s.op[DDPCA_OP_INTEINPO].cols != ng || s.op[DDPCA_OP_PEMAINPO_R].rows != ng ||
+                s.op[DDPCA_OP_PEMAINPO_R].cols != nfull || s.mass->n != s.nc || s.mass_pena->n != s.nc)
+                return fail("interface " + std::to_string(ts) + " side " + std::to_string(tv) + ": operator shapes are inconsistent");
+            if (!s.aux) {
+                // zero initial state, MCONTACT.h:875-894
+                if (dev_vec(nullptr, s.nc, &s.aux) || dev_vec(nullptr, s.nc, &s.lagr) || dev_vec(nullptr, s.nc, &s.aux_prev) ||
+                    dev_vec(nullptr, s.nc, &s.lagr_prev) || dev_vec(nullptr, s.nc, &s.force) || dev_vec(nullptr, s.nc, &s.tmp)) return 1;
+            }
+        }
+    }
+    h->nslots = h->nb + 4 * h->ni;
+    if (!h->moni_part) {
+        CU(cudaMalloc(&h->moni_part, sizeof(double) * 2 * kMoniBlocks * h->nslots));
+        CU(cudaMalloc(&h->moni_out, sizeof(double) * 2 * h->nslots));
+        CU(cudaMallocHost(&h->moni_host, sizeof(double) * 2 * h->nslots));
+    }
+    h->finalized = true;
+    return 0;
+}
+
+int ddpca_admm_step(ddpca_admm *h, int apply_macro, double *monitor_row, long *cg_iters, double *cg_dof_iters)
+{
+    if (!h || !h->finalized) return fail("ddpca_admm_step: handle not finalized");
+    CU(cudaSetDevice(h->device));
+    if (admm_step(h, apply_macro, monitor_row)) return 1;
+    if (cg_iters) *cg_iters = h->cg_iters;
+    if (cg_dof_iters) *cg_dof_iters = h->cg_dof_iters;
+    return 0;
+}
+
+int ddpca_admm_row_length(const ddpca_admm *h) { return h ? 2 * h->nb + 8 * h->ni + 2 : -1; }
+
+int ddpca_admm_get_disp(ddpca_admm *h, int v, double *out)
+{
+    if (!h || v < 0 || v >= h->nb || !out) return fail("ddpca_admm_get_disp: bad argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpy(out, h->body[v].disp, sizeof(double) * h->body[v].nfull, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int ddpca_admm_get_side(ddpca_admm *h, int ts, int tv, double *aux, double *lagr)
+{
+    if (!h || ts < 0 || ts >= h->ni || tv < 0 || tv > 1) return fail("ddpca_admm_get_side: bad argument");
+    CU(cudaSetDevice(h->device));
+    AdmmSide &s = h->iface[ts].side[tv];
+    if (aux) CU(cudaMemcpy(aux, s.aux, sizeof(double) * s.nc, cudaMemcpyDeviceToHost));
+    if (lagr) CU(cudaMemcpy(lagr, s.lagr, sizeof(double) * s.nc, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int ddpca_admm_get_gamma(ddpca_admm *h, int ts, double *gamma, int *fricStat)
+{
+    if (!h || ts < 0 || ts >= h->ni) return fail("ddpca_admm_get_gamma: bad argument");
+    CU(cudaSetDevice(h->device));
+    AdmmIface &f = h->iface[ts];
+    if (gamma) CU(cudaMemcpy(gamma, f.gamma, sizeof(double) * f.d * f.nip, cudaMemcpyDeviceToHost));
+    if (fricStat) CU(cudaMemcpy(fricStat, f.stat, sizeof(int) * f.d * f.nip, cudaMemcpyDeviceToHost));
+    return 0;
+}
+long ddpca_admm_launch_count(ddpca_admm *h, int reset)
+{
+    if (!h) return -1;
+    long v = h->launches;
+    if (reset) h->launches = 0;
+    return v;
+}
+
+}  // extern "C"

@@ -11,7 +11,7 @@
 
 namespace ddpca {
 
-constexpr int kNumPart = 1024;   // slots of a partial-sum buffer (one per CTA of a reducing kernel)
+constexpr int kNumPart = 1184;   // 148 SMs x 8:   // slots of a partial-sum buffer (one per CTA of a reducing kernel)
 
 // One multigrid level in its device layout: stage-permuted, stored per ROW GROUP.
 // The <= 3 rows of a group share one column pattern (plan.h), so the pattern is stored once
@@ -127,13 +127,32 @@ __device__ __forceinline__ GroupMeta ld_meta(const GroupMeta *p)
     return m;
 }
 
+// A row group is processed by a SUB-WARP of GL lanes (GL = 8: four groups per warp), so that
+// enough groups -- i.e. enough independent (descriptor -> pattern/values -> x gather) load
+// chains -- are in flight per SM to cover HBM latency; each lane streams 16-byte value loads.
+#ifndef DDPCA_GROUP_LANES
+#define DDPCA_GROUP_LANES 8
+#endif
+constexpr int GL = DDPCA_GROUP_LANES;
+
+__device__ __forceinline__ unsigned subwarp_mask()
+{
+    const unsigned lane = threadIdx.x & 31u;
+    return (GL == 32) ? 0xffffffffu : (((1u << GL) - 1u) << (lane & ~(unsigned)(GL - 1)));
+}
+__device__ __forceinline__ double group_sum(double v, unsigned mask)
+{
+#pragma unroll
+    for (int o = GL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+
 // Partial sums of one row group over the pattern range selected by LOWER / UPPER:
 //   sL[r] = sum_{k <  kd}      a_r[k] x[c_k]      sU[r] = sum_{k >= kd+gs} a_r[k] x[c_k]
-// Each lane owns pattern positions (2*lane, 2*lane+1) + 64*it: one 8-byte index load, one
-// x gather pair and gs 16-byte value loads per step, all issued before the first FMA of the
-// step (two steps are unrolled: rows of a hexahedral mesh have <= 81 entries).
+// Lane sl of the sub-warp owns pattern positions (2*sl, 2*sl+1) + 2*GL*it: one 8-byte index
+// load, gs 16-byte value loads and one x gather pair per step.
 template <bool LOWER, bool UPPER, bool NC_X>
-__device__ __forceinline__ void group_partial(const LvlView &A, const GroupMeta &m, const double *x, int lane,
+__device__ __forceinline__ void group_partial(const LvlView &A, const GroupMeta &m, const double *x, int sl,
                                               double (&sL)[3], double (&sU)[3])
 {
     const int *ci = A.ci + m.cptr;
@@ -141,8 +160,8 @@ __device__ __forceinline__ void group_partial(const LvlView &A, const GroupMeta 
     const int len = m.len, kd = m.kd, ku = m.kd + m.gs, gs = m.gs;
     const int kbeg = LOWER ? 0 : (ku & ~1);
     const int kend = UPPER ? len : kd;   // exclusive; entries >= kend are never needed
-#pragma unroll 2
-    for (int k = kbeg + 2 * lane; k < kend; k += 64) {
+#pragma unroll 3
+    for (int k = kbeg + 2 * sl; k < kend; k += 2 * GL) {
         const int2 c = ld_stream2(ci + k);
         double2 a[3];
 #pragma unroll
@@ -172,7 +191,7 @@ __device__ __forceinline__ void group_partial(const LvlView &A, const GroupMeta 
 // ------------------------------------------------------------------------------------
 template <bool ZERO_X, bool NC_X>
 __device__ __forceinline__ void group_fwd(const LvlView &A, int g, const double *__restrict__ b,
-                                          double *x, double *__restrict__ p1, int lane)
+                                          double *x, double *__restrict__ p1, int sl, unsigned mask)
 {
     const GroupMeta m = ld_meta(A.meta + g);
     const int gs = m.gs, r0 = m.row0;
@@ -189,11 +208,11 @@ __device__ __forceinline__ void group_fwd(const LvlView &A, int g, const double 
 #pragma unroll
         for (int c = 0; c < 3; c++) blk[r][c] = (r < gs && c < gs) ? __ldg(vb + (size_t)r * m.len + c) : 0.0;
     }
-    group_partial<true, !ZERO_X, NC_X>(A, m, x, lane, sL, sU);
+    group_partial<true, !ZERO_X, NC_X>(A, m, x, sl, sL, sU);
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        sL[r] = warp_sum(sL[r]);
-        if (!ZERO_X) sU[r] = warp_sum(sU[r]);
+        sL[r] = group_sum(sL[r], mask);
+        if (!ZERO_X) sU[r] = group_sum(sU[r], mask);
     }
     // sequential in-group solve, done redundantly by every lane (no divergence); lane 0 stores
     double xn[3] = {0.0, 0.0, 0.0};
@@ -208,7 +227,7 @@ __device__ __forceinline__ void group_fwd(const LvlView &A, int g, const double 
             }
             const double up = sU[r] + inU;
             xn[r] = (bb[r] - sL[r] - inL - up) / blk[r][r];
-            if (lane == 0) {
+            if (sl == 0) {
                 x[r0 + r] = xn[r];
                 p1[r0 + r] = blk[r][r] * xn[r] + up;
             }
@@ -219,7 +238,7 @@ __device__ __forceinline__ void group_fwd(const LvlView &A, int g, const double 
 // K4: backward relaxation of one row group (MGPIS.h:73-76):  x_i = (p1_i - sum_{j>i} a_ij x_j) / a_ii
 template <bool NC_X>
 __device__ __forceinline__ void group_bwd(const LvlView &A, int g, const double *__restrict__ p1,
-                                          double *x, int lane)
+                                          double *x, int sl, unsigned mask)
 {
     const GroupMeta m = ld_meta(A.meta + g);
     const int gs = m.gs, r0 = m.row0;
@@ -232,9 +251,9 @@ __device__ __forceinline__ void group_bwd(const LvlView &A, int g, const double 
 #pragma unroll
         for (int c = 0; c < 3; c++) blk[r][c] = (r < gs && c < gs && c >= r) ? __ldg(vb + (size_t)r * m.len + c) : 0.0;
     }
-    group_partial<false, true, NC_X>(A, m, x, lane, sL, sU);
+    group_partial<false, true, NC_X>(A, m, x, sl, sL, sU);
 #pragma unroll
-    for (int r = 0; r < 3; r++) sU[r] = warp_sum(sU[r]);
+    for (int r = 0; r < 3; r++) sU[r] = group_sum(sU[r], mask);
     double xn[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int r = 2; r >= 0; r--) {
@@ -244,42 +263,43 @@ __device__ __forceinline__ void group_bwd(const LvlView &A, int g, const double 
             for (int c = 0; c < 3; c++)
                 if (c > r) inU += blk[r][c] * xn[c];
             xn[r] = (pp[r] - sU[r] - inU) / blk[r][r];
-            if (lane == 0) x[r0 + r] = xn[r];
+            if (sl == 0) x[r0 + r] = xn[r];
         }
     }
 }
 
-// one stage = groups [g0,g1): mutually independent, one warp per group
+// one stage = groups [g0,g1): mutually independent, one sub-warp per group
 template <bool ZERO_X>
 __global__ void __launch_bounds__(256) k_sweep_fwd_stage(LvlView A, int g0, int g1, const double *__restrict__ b,
                                                          double *x, double *__restrict__ p1, const int *done)
 {
     if (done && *done) return;
-    const int g = g0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int g = g0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / GL);
     if (g >= g1) return;
-    group_fwd<ZERO_X, true>(A, g, b, x, p1, threadIdx.x & 31);
+    group_fwd<ZERO_X, true>(A, g, b, x, p1, threadIdx.x % GL, subwarp_mask());
 }
 
 __global__ void __launch_bounds__(256) k_sweep_bwd_stage(LvlView A, int g0, int g1, const double *__restrict__ p1,
                                                          double *x, const int *done)
 {
     if (done && *done) return;
-    const int g = g0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int g = g0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / GL);
     if (g >= g1) return;
-    group_bwd<true>(A, g, p1, x, threadIdx.x & 31);
+    group_bwd<true>(A, g, p1, x, threadIdx.x % GL, subwarp_mask());
 }
 
 // a run of small stages [s0,s1) relaxed by ONE CTA, __syncthreads() between stages
-// (latency-bound regime: LEX wavefronts, coarse levels)
+// (latency-bound regime: LEX wavefronts, coarse levels, triangular solves)
 template <bool ZERO_X>
 __global__ void __launch_bounds__(512) k_sweep_fwd_multi(LvlView A, const int *__restrict__ stage_group, int s0, int s1,
                                                           const double *__restrict__ b, double *x, double *p1, const int *done)
 {
     if (done && *done) return;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int sl = threadIdx.x % GL, w = threadIdx.x / GL, nw = blockDim.x / GL;
+    const unsigned mask = subwarp_mask();
     for (int s = s0; s < s1; s++) {
         const int ga = stage_group[s], gb = stage_group[s + 1];
-        for (int g = ga + w; g < gb; g += nw) group_fwd<ZERO_X, false>(A, g, b, x, p1, lane);
+        for (int g = ga + w; g < gb; g += nw) group_fwd<ZERO_X, false>(A, g, b, x, p1, sl, mask);
         __syncthreads();
     }
 }
@@ -288,53 +308,56 @@ __global__ void __launch_bounds__(512) k_sweep_bwd_multi(LvlView A, const int *_
                                                           const double *p1, double *x, const int *done)
 {
     if (done && *done) return;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int sl = threadIdx.x % GL, w = threadIdx.x / GL, nw = blockDim.x / GL;
+    const unsigned mask = subwarp_mask();
     for (int s = s1 - 1; s >= s0; s--) {
         const int ga = stage_group[s], gb = stage_group[s + 1];
-        for (int g = ga + w; g < gb; g += nw) group_bwd<false>(A, g, p1, x, lane);
+        for (int g = ga + w; g < gb; g += nw) group_bwd<false>(A, g, p1, x, sl, mask);
         __syncthreads();
     }
 }
 
-// K2: r = b - (p1 + L x)   (MGPIS.h:92) -- strictly-lower half only, one warp per group
+// K2: r = b - (p1 + L x)   (MGPIS.h:92) -- strictly-lower half only, one sub-warp per group
 __global__ void __launch_bounds__(256) k_resid_lower(LvlView A, const double *__restrict__ b, const double *__restrict__ p1,
                                                      const double *__restrict__ x, double *__restrict__ r, const int *done)
 {
     if (done && *done) return;
-    const int lane = threadIdx.x & 31;
-    const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int sl = threadIdx.x % GL;
+    const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / GL);
     if (g >= A.ng) return;
+    const unsigned mask = subwarp_mask();
     const GroupMeta m = ld_meta(A.meta + g);
     double sL[3] = {0.0, 0.0, 0.0}, sU[3] = {0.0, 0.0, 0.0};
-    group_partial<true, false, true>(A, m, x, lane, sL, sU);
+    group_partial<true, false, true>(A, m, x, sl, sL, sU);
 #pragma unroll
-    for (int q = 0; q < 3; q++) sL[q] = warp_sum(sL[q]);
-    if (lane < m.gs) {
-        const int i = m.row0 + lane;
-        double s = lane == 0 ? sL[0] : (lane == 1 ? sL[1] : sL[2]);
-        const double *vb = A.v + m.voff + (size_t)lane * m.len + m.kd;
-        for (int c = 0; c < lane; c++) s += vb[c] * x[m.row0 + c];   // in-group strictly-lower part
+    for (int q = 0; q < 3; q++) sL[q] = group_sum(sL[q], mask);
+    if (sl < m.gs) {
+        const int i = m.row0 + sl;
+        double s = sl == 0 ? sL[0] : (sl == 1 ? sL[1] : sL[2]);
+        const double *vb = A.v + m.voff + (size_t)sl * m.len + m.kd;
+        for (int c = 0; c < sl; c++) s += vb[c] * x[m.row0 + c];   // in-group strictly-lower part
         r[i] = b[i] - (p1[i] + s);
     }
 }
 
-// K1: y = A x on the group layout, one warp per group, grid-stride; DOT: partial[blockIdx] = sum_i w_i y_i
+// K1: y = A x on the group layout, one sub-warp per group, grid-stride; DOT: partial[blockIdx] = sum_i w_i y_i
 // (the p.q of MGPIS.h:201 fused into the product of :200).  Fixed grid => deterministic.
 template <bool DOT>
 __global__ void __launch_bounds__(256) k_spmv_group(LvlView A, const double *__restrict__ x, double *__restrict__ y,
                                                     const double *__restrict__ w, double *partial, const int *done)
 {
     if (done && *done) return;
-    const int lane = threadIdx.x & 31;
-    const int nwarp = (int)((gridDim.x * (unsigned)blockDim.x) >> 5);
+    const int sl = threadIdx.x % GL;
+    const unsigned mask = subwarp_mask();
+    const int nsub = (int)((gridDim.x * (unsigned)blockDim.x) / GL);
     double acc = 0.0;
-    for (int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5); g < A.ng; g += nwarp) {
+    for (int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / GL); g < A.ng; g += nsub) {
         const GroupMeta m = ld_meta(A.meta + g);
         const int *ci = A.ci + m.cptr;
         const double *v = A.v + m.voff;
         double s[3] = {0.0, 0.0, 0.0};
-#pragma unroll 2
-        for (int k = 2 * lane; k < m.len; k += 64) {
+#pragma unroll 3
+        for (int k = 2 * sl; k < m.len; k += 2 * GL) {
             const int2 c = ld_stream2(ci + k);
             double2 a[3];
 #pragma unroll
@@ -346,20 +369,20 @@ __global__ void __launch_bounds__(256) k_spmv_group(LvlView A, const double *__r
                 if (r < m.gs) s[r] += a[r].x * x0 + a[r].y * x1;
         }
 #pragma unroll
-        for (int r = 0; r < 3; r++) s[r] = warp_sum(s[r]);
-        if (lane < m.gs) {
-            const double yi = lane == 0 ? s[0] : (lane == 1 ? s[1] : s[2]);
-            y[m.row0 + lane] = yi;
-            if (DOT) acc += w[m.row0 + lane] * yi;
+        for (int r = 0; r < 3; r++) s[r] = group_sum(s[r], mask);
+        if (sl < m.gs) {
+            const double yi = sl == 0 ? s[0] : (sl == 1 ? s[1] : s[2]);
+            y[m.row0 + sl] = yi;
+            if (DOT) acc += w[m.row0 + sl] * yi;
         }
     }
     if (DOT) block_sum_to_partial(acc, partial);
 }
 
-// K1/K5/K6: y (=|+=) A x, LANES lanes per row; DOT: partial[blockIdx] = sum_i w_i * y_i
+// K5/K6 and the ADMM interface operators: y (=|+=) alpha A x, LANES lanes per row; DOT: partial[blockIdx] = sum_i w_i * y_i
 // (fused p.q of MGPIS.h:201).  Grid-stride so that DOT stays deterministic for a fixed grid.
 template <int LANES, bool ADD, bool DOT>
-__global__ void __launch_bounds__(256) k_spmv(CsrView A, const double *__restrict__ x, double *y,
+__global__ void __launch_bounds__(256) k_spmv(CsrView A, double alpha, const double *__restrict__ x, double *y,
                                               const double *__restrict__ w, double *partial, const int *done)
 {
     if (done && *done) return;
@@ -378,6 +401,7 @@ __global__ void __launch_bounds__(256) k_spmv(CsrView A, const double *__restric
         }
         s = subwarp_sum<LANES>(s);
         if (i < A.rows && sub == 0) {
+            s *= alpha;
             if (ADD) s += y[i];
             y[i] = s;
             if (DOT) acc += w[i] * s;
@@ -552,6 +576,81 @@ __global__ void k_s_next(PcgState *st)
     if (st->done) return;
     st->it += 1;
     if (!(st->it < st->maxit && sqrt(st->rr) > st->tol)) st->done = 1;
+}
+
+// ---- ADMM interface kernels (MCONTACT.h:2632-2668, :2737-2833) ---------------------------------
+// gamma = 0.5*(t - gapTerm) followed by the contact projection; t already holds
+// inpoLagr0 l0 - inpoLagr1 l1 + pemaInpo_r0 u0 - pemaInpo_r1 u1.
+//   fric <  0 : tied interface, no projection                               (:2637)
+//   fric == 0 : one component per integration point, gamma = max(0, gamma)  (:2639-2641)
+//   fric >  0 : (n, t1, t2) per point; normal clamp, Coulomb cone on the tangential pair,
+//               status 0 open / 1 slide / 2 stick in stat[3*ip+1]            (:2643-2667)
+__global__ void k_gamma_project(int nip, int d, double fric, const double *__restrict__ t, const double *__restrict__ gap,
+                                double *__restrict__ gamma, int *__restrict__ stat)
+{
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= nip) return;
+    if (d == 1) {
+        double g = 0.5 * (t[ip] - gap[ip]);
+        if (fric >= 0.0) g = fmax(0.0, g);
+        gamma[ip] = g;
+        stat[ip] = 0;
+        return;
+    }
+    double gn = 0.5 * (t[3 * ip] - gap[3 * ip]);
+    double g1 = 0.5 * (t[3 * ip + 1] - gap[3 * ip + 1]);
+    double g2 = 0.5 * (t[3 * ip + 2] - gap[3 * ip + 2]);
+    int st = 0;
+    if (fric >= 0.0) gn = fmax(0.0, gn);
+    if (fric > 0.0) {
+        if (gn > 0.0) {
+            const double slid = fric * gn;
+            const double nrm = sqrt(g1 * g1 + g2 * g2);
+            if (nrm >= slid) { const double f = slid / nrm; g1 = f * g1; g2 = f * g2; st = 1; }
+            else st = 2;
+        } else { g1 = 0.0; g2 = 0.0; st = 0; }
+    }
+    gamma[3 * ip] = gn; gamma[3 * ip + 1] = g1; gamma[3 * ip + 2] = g2;
+    stat[3 * ip] = 0; stat[3 * ip + 1] = st; stat[3 * ip + 2] = 0;
+}
+// y += a*x
+__global__ void k_axpy(int n, double a, const double *__restrict__ x, double *__restrict__ y)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += a * x[i];
+}
+constexpr int kMoniBlocks = 64;
+// part[0..64) = partial sums of (cur-prev)^2, part[64..128) of cur^2   (MONITOR, :2738-2739)
+__global__ void __launch_bounds__(256) k_moni_partial(int n, const double *__restrict__ cur, const double *__restrict__ prev, double *part)
+{
+    double a = 0.0, b = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double c = cur[i], dlt = c - prev[i];
+        a += dlt * dlt;
+        b += c * c;
+    }
+    __shared__ double sa[8], sb[8];
+    a = warp_sum(a); b = warp_sum(b);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sa[w] = a; sb[w] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0.0, tb = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) { ta += sa[k]; tb += sb[k]; }
+        part[blockIdx.x] = ta;
+        part[kMoniBlocks + blockIdx.x] = tb;
+    }
+}
+// out[2s], out[2s+1] = fixed-order sums of slot s
+__global__ void k_moni_final(const double *__restrict__ part, double *__restrict__ out)
+{
+    const int s = blockIdx.x;
+    if (threadIdx.x == 0) {
+        double ta = 0.0, tb = 0.0;
+        for (int k = 0; k < kMoniBlocks; k++) { ta += part[s * 2 * kMoniBlocks + k]; tb += part[s * 2 * kMoniBlocks + kMoniBlocks + k]; }
+        out[2 * s] = ta;
+        out[2 * s + 1] = tb;
+    }
 }
 
 }  // namespace ddpca

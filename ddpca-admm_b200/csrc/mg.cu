@@ -197,7 +197,7 @@ static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 // ---- kernel launch helpers (all on h->stream) ----------------------------------------------
 static void launch_spmv(Engine *h, int kclass, int lvl, const DevCsr &A, const double *x, double *y, bool add,
-                        const double *dotw, double *partial, const int *done)
+                        const double *dotw, double *partial, const int *done, double alpha = 1.0)
 {
     // algorithmic bytes, SURVEY.md §8(d): 12 nnz + 4 (rows+1) + 8 cols (x once) + 8 rows (y) [+8 rows for +=]
     double bytes = 12.0 * A.nnz + 4.0 * (A.rows + 1) + 8.0 * A.cols + 8.0 * A.rows * (add ? 2 : 1) + (dotw ? 8.0 * A.rows : 0.0);
@@ -211,14 +211,14 @@ static void launch_spmv(Engine *h, int kclass, int lvl, const DevCsr &A, const d
     if (dotw) {
         int g = grid_for(32);
         // stale slots of the partial buffer beyond g are never read: consumers use np = g
-        KL(h, kclass, lvl, bytes, (k_spmv<32, false, true><<<g, T, 0, h->stream>>>(A.view(), x, y, dotw, partial, done)));
+        KL(h, kclass, lvl, bytes, (k_spmv<32, false, true><<<g, T, 0, h->stream>>>(A.view(), alpha, x, y, dotw, partial, done)));
         return;
     }
 #define SPMV_CASE(L)                                                                                                   \
     do {                                                                                                               \
         int g = grid_for(L);                                                                                           \
-        if (add) KL(h, kclass, lvl, bytes, (k_spmv<L, true, false><<<g, T, 0, h->stream>>>(A.view(), x, y, nullptr, nullptr, done)));  \
-        else KL(h, kclass, lvl, bytes, (k_spmv<L, false, false><<<g, T, 0, h->stream>>>(A.view(), x, y, nullptr, nullptr, done)));     \
+        if (add) KL(h, kclass, lvl, bytes, (k_spmv<L, true, false><<<g, T, 0, h->stream>>>(A.view(), alpha, x, y, nullptr, nullptr, done)));  \
+        else KL(h, kclass, lvl, bytes, (k_spmv<L, false, false><<<g, T, 0, h->stream>>>(A.view(), alpha, x, y, nullptr, nullptr, done)));     \
     } while (0)
     if (avg > 40) SPMV_CASE(32);
     else if (avg > 20) SPMV_CASE(16);
@@ -229,7 +229,7 @@ static void launch_spmv(Engine *h, int kclass, int lvl, const DevCsr &A, const d
 // y = consStif[l] x on the group layout; returns the grid (= number of partial sums when dotw)
 static int launch_level_spmv(Engine *h, Level &L, int l, const double *x, double *y, const double *dotw, double *partial, const int *done)
 {
-    long need = cdiv((long)L.ng * 32, 256);
+    long need = cdiv((long)L.ng * GL, 256);
     int grid = (int)std::max<long>(1, std::min<long>(need, dotw ? kNumPart : (long)h->sms * 32));
     double bytes = L.bytes_full + (dotw ? 8.0 * L.n : 0.0);
     if (dotw) KL(h, DDPCA_K_SPMV, l, bytes, (k_spmv_group<true><<<grid, 256, 0, h->stream>>>(L.view(), x, y, dotw, partial, done)));
@@ -243,7 +243,7 @@ static void sweep_fwd(Engine *h, Level &L, int l, const double *b, double *x, bo
         double bytes = s.bytes_lo + (zero_x ? 0.0 : s.bytes_up);
         if (!s.multi) {
             int ng = s.g1 - s.g0;
-            int grid = cdiv((long)ng * 32, 256);
+            int grid = cdiv((long)ng * GL, 256);
             if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_stage<true><<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, b, x, L.p1, done)));
             else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_stage<false><<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, b, x, L.p1, done)));
         } else {
@@ -258,7 +258,7 @@ static void sweep_bwd(Engine *h, Level &L, int l, double *x, const int *done)
         const Segment &s = L.segs[k];
         if (!s.multi) {
             int ng = s.g1 - s.g0;
-            int grid = cdiv((long)ng * 32, 256);
+            int grid = cdiv((long)ng * GL, 256);
             KL(h, DDPCA_K_SWEEP_BWD, l, s.bytes_up, (k_sweep_bwd_stage<<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, L.p1, x, done)));
         } else {
             KL(h, DDPCA_K_SWEEP_BWD, l, s.bytes_up, (k_sweep_bwd_multi<<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, L.p1, x, done)));
@@ -278,7 +278,7 @@ static void vcycle_dev(ddpca_mg *h, int l, const double *b, double *x, bool zero
     Level &C = h->lev[l - 1];
     sweep_fwd(h, L, l, b, x, zero_x, done);  // :65-72
     sweep_bwd(h, L, l, x, done);             // :73-76
-    KL(h, DDPCA_K_RESID, l, L.bytes_lower + 8.0 * L.n, (k_resid_lower<<<cdiv((long)L.ng * 32, 256), 256, 0, h->stream>>>(L.view(), b, L.p1, x, L.r, done)));
+    KL(h, DDPCA_K_RESID, l, L.bytes_lower + 8.0 * L.n, (k_resid_lower<<<cdiv((long)L.ng * GL, 256), 256, 0, h->stream>>>(L.view(), b, L.p1, x, L.r, done)));
     launch_spmv(h, DDPCA_K_RESTRICT, l, L.R, L.r, C.b, false, nullptr, nullptr, done);  // :96
     vcycle_dev(h, l - 1, C.b, C.x, true, done);                                          // :93-99
     launch_spmv(h, DDPCA_K_PROLONG, l, L.P, C.x, x, true, nullptr, nullptr, done);       // :100
@@ -970,3 +970,5 @@ int ddpca_mg_last_timing(ddpca_mg *h, double *solve_ms, double *h2d_ms, double *
 }
 
 }  // extern "C"
+
+#include "admm.inl"

@@ -123,6 +123,64 @@ int ddpca_ldlt_solve_dev(ddpca_ldlt *, const double *b_dev, double *x_dev);
 int ddpca_ldlt_info(const ddpca_ldlt *, int *n, long *nnzL, int *stages_fwd, int *stages_bwd);
 int ddpca_ldlt_destroy(ddpca_ldlt *);
 
+/* ---- MCONTACT: the ADMM loop ----------------------------------------------------
+ * ddpca_admm_* keeps the state of MCONTACT::CONTACT_ANALYSIS (resuDisp, inteAuxi,
+ * inteLagr, MCONTACT.h:25-27) and every operator the loop consumes (MCONTACT.h:29-46,
+ * built by MCONTACT::ESTABLISH on the host) in HBM.  ddpca_admm_step() is one pass of the
+ * loop body (MCONTACT.h:2505-2704) plus the norms MCONTACT::MONITOR needs (:2737-2833);
+ * the stopping logic (ring buffers, VECT_MEDI_OSCI, MULT_MAXI, :2838-2843) is scalar host
+ * code and stays with the caller.  Every body solve is MG-PCG on the device (the reference
+ * switches to a host LDLT below 50 000 rows, MCONTACT.h:2527; both are solves to 1e-14). */
+typedef struct ddpca_admm ddpca_admm;
+enum {
+    DDPCA_OP_SYSTTRAN = 0,      /* systTran[ts][tv]       3 n_nodes x d n_c   MCONTACT.h:2521 */
+    DDPCA_OP_SYSTTRAN_PENA = 1, /* systTran_pena[ts][tv]  3 n_nodes x d n_c   :2520,2673     */
+    DDPCA_OP_INTEMASS = 2,      /* inteMass[ts][tv]       d n_c x d n_c       :2674          */
+    DDPCA_OP_INTEMASS_PENA = 3, /* inteMass_pena[ts][tv]                      :2694          */
+    DDPCA_OP_INPOLAGR = 4,      /* inpoLagr[ts][tv]       d n_ip x d n_c      :2632          */
+    DDPCA_OP_INTEINPO = 5,      /* inteInpo[ts][tv]       d n_c x d n_ip      :2675          */
+    DDPCA_OP_PEMAINPO_R = 6,    /* pemaInpo_r[ts][tv]     d n_ip x 3 n_nodes  :2634          */
+    DDPCA_OP_GLOBTRAN = 7,      /* globTran[ts][tv]       n_glob x d n_c      :2545          */
+    DDPCA_OP_GLOBTRAN_PENA = 8, /* globTran_pena[ts][tv]                      :2546          */
+    DDPCA_OP_GLOBTRAN_D = 9,    /* globTran_D[ts][tv]     n_glob x 3 n_nodes  :2547          */
+    DDPCA_OP_COUNT = 10
+};
+enum { DDPCA_SOLVER_MASS = 0 /* inteDiso */, DDPCA_SOLVER_MASS_PENA = 1 /* inteDiso_pena */ };
+
+/* muscSett: bit 0 = macroscopic problem (MCONTACT.h:858-860); bit 1 is not supported */
+int ddpca_admm_create(int device, int nbody, int niface, int muscSett, ddpca_admm **out);
+/* Body v.  Takes ownership of `mg` (multGrid[v].mgpi).  forcOper (n_L x 3 n_nodes) is
+ * MULTIGRID::ADDITIONAL_FORCE as one operator, consOper[L] prolOper[L]^T earlTran^T
+ * (MULTIGRID.h:1257-1261); MULTIGRID::OUTP_SUB1 is forcOper^T u + dispCons
+ * (MULTIGRID.h:1263-1281, dispCons = OUTP_SUB1(0)); consForc is multGrid[v].consForc. */
+int ddpca_admm_set_body(ddpca_admm *, int v, ddpca_mg *mg, int nfull, const double *consForc,
+                        const int *F_rowptr, const int *F_colidx, const double *F_val, const double *dispCons);
+/* accuProl[v] (MCONTACT.h:864-872), needed when muscSett bit 0 is set */
+int ddpca_admm_set_body_accuprol(ddpca_admm *, int v, int rows, int cols, const int *rowptr, const int *colidx, const double *val);
+/* Interface ts between contBody[ts][0..1]; fricCoef < 0 tied, = 0 frictionless, > 0 Coulomb
+ * (MCONTACT.h:15-18); gapTerm = pemaInpo[ts] * inpoNgap[ts] (MCONTACT.h:2636), length d n_ip
+ * with d = 1 for fricCoef == 0 and 3 otherwise (MCONTACT.h:886-893). */
+int ddpca_admm_set_interface(ddpca_admm *, int ts, int body0, int body1, double fricCoef, int nip, const double *gapTerm);
+int ddpca_admm_set_side_op(ddpca_admm *, int ts, int tv, int op, int rows, int cols, const int *rowptr, const int *colidx, const double *val);
+/* takes ownership of the solver: inteDiso[ts][tv] / inteDiso_pena[ts][tv] (MCONTACT.h:837-847) */
+int ddpca_admm_set_side_solver(ddpca_admm *, int ts, int tv, int which, ddpca_ldlt *solver);
+/* macroscopic problem: coarSolv_D (factorised globCoup, MCONTACT.h:1229-1230) and baseReco[nbody+1] (:850-857) */
+int ddpca_admm_set_macro(ddpca_admm *, int nglob, const long *baseReco, ddpca_ldlt *coarSolv);
+/* checks completeness, allocates the zero initial state (MCONTACT.h:875-894) */
+int ddpca_admm_finalize(ddpca_admm *);
+/* One iteration.  apply_macro = ((muscSett>>0)%2 == 1 && tc <= MULT_MAXI) as evaluated by the
+ * caller (MCONTACT.h:2540).  monitor_row (host, ddpca_admm_row_length() doubles) is the line
+ * MONITOR appends to resuMoni.txt.  cg_iters / cg_dof_iters: CG iterations of this step summed
+ * over bodies, and sum of n_L * iterations. */
+int ddpca_admm_step(ddpca_admm *, int apply_macro, double *monitor_row, long *cg_iters, double *cg_dof_iters);
+int ddpca_admm_row_length(const ddpca_admm *);
+int ddpca_admm_get_disp(ddpca_admm *, int v, double *resuDisp);
+int ddpca_admm_get_side(ddpca_admm *, int ts, int tv, double *inteAuxi, double *inteLagr);
+/* inpoGamm[ts] and fricStat of the last iteration (what OUTPUT_PRTR writes, MCONTACT.h:97-123) */
+int ddpca_admm_get_gamma(ddpca_admm *, int ts, double *inpoGamm, int *fricStat);
+long ddpca_admm_launch_count(ddpca_admm *, int reset);
+int ddpca_admm_destroy(ddpca_admm *);
+
 /* ---- introspection / measurement -------------------------------------------*/
 /* rows, nnz, number of row groups and stages of a level's device layout */
 int ddpca_mg_level_info(const ddpca_mg *, int level, long *n, long *nnz, int *ngroups, int *nstages);

@@ -15,3 +15,4 @@ gzip -9 -n -c "$tmp/beam_2lev.ddpk" > "$here/beam_2lev.ddpk.gz"
 gzip -9 -n -c "$tmp/beam_3lev.ddpk" > "$here/beam_3lev.ddpk.gz"
 rm -rf "$tmp"
 ls -la "$here"
+python "$here/make_block_fixture.py"
