@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--smoother", default="mc", choices=["mc", "lex"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -232,7 +233,8 @@ def main():
     # ---- end-to-end through the public host-buffer API: `e2e` --------------------------------------
     b_pin = torch.from_numpy(b_host).pin_memory()
     x_pin = torch.empty(n, dtype=torch.float64).pin_memory()
-    for _ in range(min(args.warmup, 2)):
+    e2e_steps = 0 if args.no_e2e else args.steps
+    for _ in range(0 if args.no_e2e else min(args.warmup, 2)):
         mg.CG_SOLV(1, b_pin.numpy())
     barrier()
     import ctypes as C
@@ -244,7 +246,7 @@ def main():
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_iters = 0
     e2.record(stream)
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         check(lib.ddpca_mg_pcg(mg._h, C.c_int(1), C.c_void_p(b_pin.data_ptr()), C.c_void_p(x_pin.data_ptr()), C.c_double(1e-14), C.c_long(n),
                                C.byref(it_c), C.byref(res_c), C.byref(tol_c)))
         e2e_iters += it_c.value
@@ -260,7 +262,7 @@ def main():
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
     ms_max, ms_e2e_max = t.tolist()
     value = work[0].item() / (ms_max * 1e-3)
-    e2e_value = work[1].item() / (ms_e2e_max * 1e-3)
+    e2e_value = work[1].item() / (ms_e2e_max * 1e-3) if e2e_steps else None
 
     # ---- roofline of the dominant kernel class (CUDA events around every launch, same workload) ----
     roofline = None

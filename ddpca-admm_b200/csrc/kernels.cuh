@@ -134,6 +134,14 @@ __device__ __forceinline__ GroupMeta ld_meta(const GroupMeta *p)
 #define DDPCA_GROUP_LANES 8
 #endif
 constexpr int GL = DDPCA_GROUP_LANES;
+#ifndef DDPCA_MIN_BLOCKS
+#define DDPCA_MIN_BLOCKS 3
+#endif
+#ifndef DDPCA_UNROLL
+#define DDPCA_UNROLL 3
+#endif
+#define DDPCA_PRAGMA(x) _Pragma(#x)
+#define DDPCA_UNROLL_LOOP(n) DDPCA_PRAGMA(unroll n)
 
 __device__ __forceinline__ unsigned subwarp_mask()
 {
@@ -160,7 +168,7 @@ __device__ __forceinline__ void group_partial(const LvlView &A, const GroupMeta 
     const int len = m.len, kd = m.kd, ku = m.kd + m.gs, gs = m.gs;
     const int kbeg = LOWER ? 0 : (ku & ~1);
     const int kend = UPPER ? len : kd;   // exclusive; entries >= kend are never needed
-#pragma unroll 3
+    DDPCA_UNROLL_LOOP(DDPCA_UNROLL)
     for (int k = kbeg + 2 * sl; k < kend; k += 2 * GL) {
         const int2 c = ld_stream2(ci + k);
         double2 a[3];
@@ -270,7 +278,7 @@ __device__ __forceinline__ void group_bwd(const LvlView &A, int g, const double 
 
 // one stage = groups [g0,g1): mutually independent, one sub-warp per group
 template <bool ZERO_X>
-__global__ void __launch_bounds__(256) k_sweep_fwd_stage(LvlView A, int g0, int g1, const double *__restrict__ b,
+__global__ void __launch_bounds__(256, DDPCA_MIN_BLOCKS) k_sweep_fwd_stage(LvlView A, int g0, int g1, const double *__restrict__ b,
                                                          double *x, double *__restrict__ p1, const int *done)
 {
     if (done && *done) return;
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(256) k_sweep_fwd_stage(LvlView A, int g0, int 
     group_fwd<ZERO_X, true>(A, g, b, x, p1, threadIdx.x % GL, subwarp_mask());
 }
 
-__global__ void __launch_bounds__(256) k_sweep_bwd_stage(LvlView A, int g0, int g1, const double *__restrict__ p1,
+__global__ void __launch_bounds__(256, DDPCA_MIN_BLOCKS) k_sweep_bwd_stage(LvlView A, int g0, int g1, const double *__restrict__ p1,
                                                          double *x, const int *done)
 {
     if (done && *done) return;
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(512) k_sweep_bwd_multi(LvlView A, const int *_
 }
 
 // K2: r = b - (p1 + L x)   (MGPIS.h:92) -- strictly-lower half only, one sub-warp per group
-__global__ void __launch_bounds__(256) k_resid_lower(LvlView A, const double *__restrict__ b, const double *__restrict__ p1,
+__global__ void __launch_bounds__(256, DDPCA_MIN_BLOCKS) k_resid_lower(LvlView A, const double *__restrict__ b, const double *__restrict__ p1,
                                                      const double *__restrict__ x, double *__restrict__ r, const int *done)
 {
     if (done && *done) return;
@@ -343,7 +351,7 @@ __global__ void __launch_bounds__(256) k_resid_lower(LvlView A, const double *__
 // K1: y = A x on the group layout, one sub-warp per group, grid-stride; DOT: partial[blockIdx] = sum_i w_i y_i
 // (the p.q of MGPIS.h:201 fused into the product of :200).  Fixed grid => deterministic.
 template <bool DOT>
-__global__ void __launch_bounds__(256) k_spmv_group(LvlView A, const double *__restrict__ x, double *__restrict__ y,
+__global__ void __launch_bounds__(256, DDPCA_MIN_BLOCKS) k_spmv_group(LvlView A, const double *__restrict__ x, double *__restrict__ y,
                                                     const double *__restrict__ w, double *partial, const int *done)
 {
     if (done && *done) return;
@@ -356,7 +364,7 @@ __global__ void __launch_bounds__(256) k_spmv_group(LvlView A, const double *__r
         const int *ci = A.ci + m.cptr;
         const double *v = A.v + m.voff;
         double s[3] = {0.0, 0.0, 0.0};
-#pragma unroll 3
+        DDPCA_UNROLL_LOOP(DDPCA_UNROLL)
         for (int k = 2 * sl; k < m.len; k += 2 * GL) {
             const int2 c = ld_stream2(ci + k);
             double2 a[3];
@@ -612,6 +620,12 @@ __global__ void k_gamma_project(int nip, int d, double fric, const double *__res
     }
     gamma[3 * ip] = gn; gamma[3 * ip + 1] = g1; gamma[3 * ip + 2] = g2;
     stat[3 * ip] = 0; stat[3 * ip + 1] = st; stat[3 * ip + 2] = 0;
+}
+// y = a*x + b*y
+__global__ void k_axpby(int n, double a, const double *__restrict__ x, double b, double *__restrict__ y)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = a * x[i] + b * y[i];
 }
 // y += a*x
 __global__ void k_axpy(int n, double a, const double *__restrict__ x, double *__restrict__ y)

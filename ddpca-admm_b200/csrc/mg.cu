@@ -887,8 +887,130 @@ int ddpca_mg_coarse_solve(ddpca_mg *h, const double *b, double *x)
     return to_host(h, 0, h->cg_q, x);
 }
 
-int ddpca_mg_mult_solv(ddpca_mg *, const double *, double *, long *, double *) { return fail("ddpca_mg_mult_solv: not implemented yet"); }
-int ddpca_mg_bicgstab(ddpca_mg *, int, const double *, double *, double, long, long *, double *, double *) { return fail("ddpca_mg_bicgstab: not implemented yet"); }
+// ---- host-driven drivers on the same kernels: scalars come back to the host
+// after every reduction; these are not the throughput path.
+static int dev_dot(ddpca_mg *h, int n, const double *a, const double *b, double *out)
+{
+    int gv = vec_grid(h, n);
+    KL(h, DDPCA_K_VECTOR, h->nlev - 1, 16.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, a, b, h->partial[0], nullptr)));
+    std::vector<double> part(gv);
+    CU(cudaMemcpyAsync(part.data(), h->partial[0], sizeof(double) * gv, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    double s = 0.0;
+    for (int k = 0; k < gv; k++) s += part[k];
+    *out = s;
+    return 0;
+}
+static void dev_axpby(ddpca_mg *h, int n, double a, const double *x, double b, double *y)
+{
+    KL(h, DDPCA_K_VECTOR, h->nlev - 1, 24.0 * n, (k_axpby<<<cdiv(n, 256), 256, 0, h->stream>>>(n, a, x, b, y)));
+}
+
+// MGPIS::MULT_SOLV, MGPIS.h:130-160: V-cycle iteration until the residual norm stagnates
+int ddpca_mg_mult_solv(ddpca_mg *h, const double *b, double *x, long *iters, double *resid)
+{
+    if (!h || !b || !x) return fail("ddpca_mg_mult_solv: bad argument");
+    CU(cudaSetDevice(h->device));
+    int Lf = h->nlev - 1;
+    Level &L = h->lev[Lf];
+    int n = L.n;
+    double *bd = h->cg_r, *xd = h->cg_x, *rd = h->cg_q, *ax = h->cg_p;
+    if (to_dev(h, Lf, b, bd)) return 1;
+    CU(cudaMemsetAsync(xd, 0, sizeof(double) * n, h->stream));     // :133
+    const long maxiNumb = 10000;                                   // :134
+    double moni[5] = {0, 0, 0, 0, 0};
+    long it = 0;
+    while (it < maxiNumb) {
+        vcycle_dev(h, Lf, bd, xd, false, nullptr);                 // :143
+        launch_level_spmv(h, L, Lf, xd, ax, nullptr, nullptr, nullptr);
+        CU(cudaMemcpyAsync(rd, bd, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+        dev_axpby(h, n, -1.0, ax, 1.0, rd);                        // :144
+        double rr;
+        if (dev_dot(h, n, rd, rd, &rr)) return 1;
+        moni[it % 5] = std::sqrt(rr);                              // :146
+        if (it >= 4) {                                             // :147-153
+            double mx = *std::max_element(moni, moni + 5), mn = *std::min_element(moni, moni + 5);
+            if (mx - mn < 0.1 * ((mx + mn) / 2.0)) break;
+        }
+        it++;
+    }
+    if (h->profile) h->prof_collect();
+    if (iters) *iters = it;
+    if (resid) *resid = moni[it % 5];
+    return to_host(h, Lf, xd, x);
+}
+
+// MGPIS::BiCGSTAB_SOLV, MGPIS.h:350-432
+int ddpca_mg_bicgstab(ddpca_mg *h, int prec, const double *b, double *x, double rel_tol, long maxit, long *iters,
+                      double *resid, double *tol_abs)
+{
+    if (!h || !b || !x || (prec != 0 && prec != 1)) return fail("ddpca_mg_bicgstab: bad argument");
+    CU(cudaSetDevice(h->device));
+    int Lf = h->nlev - 1;
+    Level &L = h->lev[Lf];
+    int n = L.n;
+    if (prec == 0 && !L.dinv) {
+        CU(cudaMalloc(&L.dinv, sizeof(double) * n));
+        k_extract_diag_inv<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
+    }
+    // work vectors: r, rhat, p, v, s, t, phat, shat, x
+    std::vector<double *> w(6, nullptr);
+    for (auto &p : w) CU(cudaMalloc(&p, sizeof(double) * n));
+    double *r = h->cg_r, *rhat = w[0], *p = h->cg_p, *v = h->cg_q, *s = w[1], *t = w[2], *phat = h->cg_z, *shat = w[3], *xd = h->cg_x;
+    auto cleanup = [&]() { for (auto q : w) cudaFree(q); };
+    if (to_dev(h, Lf, b, r)) { cleanup(); return 1; }
+    CU(cudaMemsetAsync(xd, 0, sizeof(double) * n, h->stream));                                   // :361
+    CU(cudaMemcpyAsync(rhat, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));        // :378
+    double bb, rr;
+    if (dev_dot(h, n, r, r, &bb)) { cleanup(); return 1; }
+    const double tol = rel_tol * std::sqrt(bb);                                                  // :363
+    rr = bb;
+    double rho_old = 1.0, rho_new = 1.0, alph = 1.0, omeg = 1.0;
+    long it = 0;
+    while (it < maxit && std::sqrt(rr) > tol) {                                                  // :382
+        if (dev_dot(h, n, rhat, r, &rho_new)) { cleanup(); return 1; }                           // :383
+        if (std::fabs(rho_new) == 0.0) break;                                                    // :384-387
+        if (it == 0) {
+            CU(cudaMemcpyAsync(p, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));   // :389
+        } else {
+            double beta = (rho_new / rho_old) * (alph / omeg);                                   // :392-393
+            dev_axpby(h, n, -omeg, v, 1.0, p);                                                   // p - omeg v
+            dev_axpby(h, n, 1.0, r, beta, p);                                                    // :394
+        }
+        precondition(h, prec, p, phat, nullptr);                                                 // :396-402
+        launch_level_spmv(h, L, Lf, phat, v, nullptr, nullptr, nullptr);                         // :403
+        double rv;
+        if (dev_dot(h, n, rhat, v, &rv)) { cleanup(); return 1; }
+        alph = rho_new / rv;                                                                     // :404
+        CU(cudaMemcpyAsync(s, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+        dev_axpby(h, n, -alph, v, 1.0, s);                                                       // :405
+        double ss;
+        if (dev_dot(h, n, s, s, &ss)) { cleanup(); return 1; }
+        if (std::sqrt(ss) <= 0.0) {                                                              // :406-409
+            dev_axpby(h, n, alph, phat, 1.0, xd);
+            break;
+        }
+        precondition(h, prec, s, shat, nullptr);                                                 // :410-416
+        launch_level_spmv(h, L, Lf, shat, t, nullptr, nullptr, nullptr);                         // :417
+        double ts, tt;
+        if (dev_dot(h, n, t, s, &ts) || dev_dot(h, n, t, t, &tt)) { cleanup(); return 1; }
+        omeg = ts / tt;                                                                          // :418
+        dev_axpby(h, n, alph, phat, 1.0, xd);
+        dev_axpby(h, n, omeg, shat, 1.0, xd);                                                    // :419
+        CU(cudaMemcpyAsync(r, s, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+        dev_axpby(h, n, -omeg, t, 1.0, r);                                                       // :420
+        if (dev_dot(h, n, r, r, &rr)) { cleanup(); return 1; }
+        rho_old = rho_new;
+        it++;
+    }
+    if (h->profile) h->prof_collect();
+    if (iters) *iters = it;
+    if (resid) *resid = std::sqrt(rr);
+    if (tol_abs) *tol_abs = tol;
+    int rc = to_host(h, Lf, xd, x);
+    cleanup();
+    return rc;
+}
 
 int ddpca_ldlt_create(int device, int n, const int *perm, const int *L_rowptr, const int *L_colidx, const double *L_val,
                       const double *D, ddpca_ldlt **out)

@@ -13,7 +13,8 @@ class DdpcaError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(os.path.dirname(_HERE), "lib", "libddpca_b200.so")
+    # DDPCA_B200_LIB selects another build of the same library (kernel tuning variants)
+    return os.environ.get("DDPCA_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libddpca_b200.so")
 
 
 # every symbol include/ddpca_b200.h declares (checked by tests/test_abi.py)
@@ -25,6 +26,11 @@ EXPORTS = [
     "ddpca_mg_coarse_solve", "ddpca_mg_mult_solv", "ddpca_mg_bicgstab",
     "ddpca_mg_level_info", "ddpca_mg_launch_count", "ddpca_mg_set_stream",
     "ddpca_mg_profile", "ddpca_mg_profile_get", "ddpca_mg_last_timing",
+    "ddpca_ldlt_create", "ddpca_ldlt_solve", "ddpca_ldlt_solve_dev", "ddpca_ldlt_info", "ddpca_ldlt_destroy",
+    "ddpca_admm_create", "ddpca_admm_set_body", "ddpca_admm_set_body_accuprol", "ddpca_admm_set_interface",
+    "ddpca_admm_set_side_op", "ddpca_admm_set_side_solver", "ddpca_admm_set_macro", "ddpca_admm_finalize",
+    "ddpca_admm_step", "ddpca_admm_row_length", "ddpca_admm_get_disp", "ddpca_admm_get_side", "ddpca_admm_get_gamma",
+    "ddpca_admm_launch_count", "ddpca_admm_destroy",
 ]
 
 
@@ -42,6 +48,7 @@ def load_library() -> C.CDLL:
     lib = C.CDLL(path)
     lib.ddpca_last_error.restype = C.c_char_p
     lib.ddpca_mg_launch_count.restype = C.c_long
+    lib.ddpca_admm_launch_count.restype = C.c_long
     _LIB = lib
     return lib
 

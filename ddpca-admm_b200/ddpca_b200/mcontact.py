@@ -1,0 +1,270 @@
+"""Python mirror of the reference's `class MCONTACT` ADMM driver (MCONTACT.h:8-95, :2493-2845)
+on top of the C ABI (ddpca_admm_* / ddpca_ldlt_* in include/ddpca_b200.h).
+
+The per-iteration work runs on the device; this file keeps what the reference keeps on the
+host around it: the loop of CONTACT_ANALYSIS, MONITOR's ring buffers / VECT_MEDI_OSCI /
+MULT_MAXI logic, and resuMoni rows.  Operators come from the reference's own host setup
+(MCONTACT::ESTABLISH) -- here through a DDPK dump written by a reference-built driver."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import ddpk
+from .lib import DdpcaError, check, load_library
+from .mgpis import MGPIS, SMOOTH_MC, _pd, _pi
+
+OPS = ["systTran", "systTran_pena", "inteMass", "inteMass_pena", "inpoLagr", "inteInpo", "pemaInpo_r",
+       "globTran", "globTran_pena", "globTran_D"]
+SOLVER_MASS, SOLVER_MASS_PENA = 0, 1
+
+
+def VECT_MEDI_OSCI(v):
+    """PREP.h:147-153."""
+    mx, mn = max(v), min(v)
+    return (mx + mn) / 2.0, mx - mn
+
+
+class DIRE_SOLV:
+    """A factorised Eigen::SimplicialLDLT (typedef DIRE_SOLV, PREP.h:107) whose solve phase runs
+    on the device: perm = permutationP().indices(), L = strictly-lower unit factor (CSR), D = vectorD()."""
+
+    def __init__(self, perm, L: ddpk.Csr, D, device: int = 0):
+        lib = load_library()
+        self.n = int(L.shape[0])
+        perm = np.ascontiguousarray(perm, dtype=np.int32)
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        h = C.c_void_p()
+        check(lib.ddpca_ldlt_create(C.c_int(device), C.c_int(self.n), _pi(perm), _pi(L.rowptr), _pi(L.colidx), _pd(L.val), _pd(D), C.byref(h)))
+        self._h = h
+        self._owned = True
+
+    def solve(self, b):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        check(load_library().ddpca_ldlt_solve(self._h, _pd(b), _pd(x)))
+        return x
+
+    def info(self):
+        n, nnz, sf, sb = C.c_int(), C.c_long(), C.c_int(), C.c_int()
+        check(load_library().ddpca_ldlt_info(self._h, C.byref(n), C.byref(nnz), C.byref(sf), C.byref(sb)))
+        return {"n": n.value, "nnzL": nnz.value, "stages_fwd": sf.value, "stages_bwd": sb.value}
+
+    def release(self):
+        """Hand the device object over to an ADMM handle (which then owns it)."""
+        self._owned = False
+        return self._h
+
+    def close(self):
+        if self._owned and self._h is not None:
+            load_library().ddpca_ldlt_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _factor_from_dump(d, name, device, fallback_matrix=None, factorize=None):
+    if name + ".perm" in d:
+        return DIRE_SOLV(d[name + ".perm"], ddpk.get_csr(d, name + ".L"), d[name + ".D"], device)
+    if factorize is None:
+        raise DdpcaError(f"{name}: no factorisation in the dump and no host factoriser given")
+    perm, L, D = factorize(fallback_matrix)
+    return DIRE_SOLV(perm, L, D, device)
+
+
+class MCONTACT:
+    """Multibody contact / domain decomposition ADMM solver on a B200.
+
+    Public state follows the reference: `resuDisp[v]`, `inteAuxi[ts][tv]`, `inteLagr[ts][tv]`,
+    `iterNumbReco`, `muscSett`, `fricCoef`, `contBody` (MCONTACT.h:11-58)."""
+
+    def __init__(self, device: int = 0, smoother: int = SMOOTH_MC):
+        self.device = device
+        self.smoother = smoother
+        self._h = None
+        self.muscSett = 0
+        self.contBody = []
+        self.fricCoef = []
+        self.MULT_MAXI = 1000  # PREP.h:75
+        self.iterNumbReco = None
+        self.resuMoni = []
+        self.cg_iters = 0
+        self.cg_dof_iters = 0.0
+        self.body_dof = []
+        self.nfull = []
+
+    # ------------------------------------------------------------------------------------------
+    @classmethod
+    def from_ddpk(cls, d: dict, device: int = 0, smoother: int = SMOOTH_MC, muscSett=None, factorize=None):
+        """Upload everything MCONTACT::ESTABLISH built (dumped by oracle/ref_drivers/admm_hook.h)."""
+        lib = load_library()
+        self = cls(device, smoother)
+        nb, ni = int(d["nbody"][0]), int(d["niface"][0])
+        self.nb, self.ni = nb, ni
+        self.muscSett = int(d["muscSett"][0]) if muscSett is None else muscSett
+        h = C.c_void_p()
+        check(lib.ddpca_admm_create(C.c_int(device), C.c_int(nb), C.c_int(ni), C.c_int(self.muscSett), C.byref(h)))
+        self._h = h
+        for v in range(nb):
+            p = f"body{v}."
+            L = int(d[p + "maxiLeve"][0])
+            A = [ddpk.get_csr(d, p + f"consStif{l}") for l in range(L + 1)]
+            P = [ddpk.get_csr(d, p + f"realProl{l}") for l in range(L)]
+            mg = MGPIS.from_hierarchy(A, P, device=device, smoother=smoother)
+            F = ddpk.get_csr(d, p + "forcOper")
+            nfull = int(d[p + "nfull"][0])
+            consForc = np.ascontiguousarray(d[p + "consForc"])
+            dispCons = np.ascontiguousarray(d[p + "dispCons"])
+            check(lib.ddpca_admm_set_body(h, C.c_int(v), mg._h, C.c_int(nfull), _pd(consForc), _pi(F.rowptr), _pi(F.colidx), _pd(F.val), _pd(dispCons)))
+            mg._h = None  # ownership moved to the ADMM handle
+            self.body_dof.append(A[-1].shape[0])
+            self.nfull.append(nfull)
+            if self.muscSett & 1:
+                a = ddpk.get_csr(d, p + "accuProl")
+                check(lib.ddpca_admm_set_body_accuprol(h, C.c_int(v), C.c_int(a.shape[0]), C.c_int(a.shape[1]), _pi(a.rowptr), _pi(a.colidx), _pd(a.val)))
+        self.nc = []
+        self.ng = []
+        for ts in range(ni):
+            p = f"if{ts}."
+            cb = [int(x) for x in d[p + "contBody"]]
+            fric = float(d[p + "fricCoef"][0])
+            nip = int(d[p + "nip"][0])
+            gap = np.ascontiguousarray(d[p + "gapTerm"])
+            self.contBody.append(cb)
+            self.fricCoef.append(fric)
+            self.ng.append(gap.shape[0])
+            check(lib.ddpca_admm_set_interface(h, C.c_int(ts), C.c_int(cb[0]), C.c_int(cb[1]), C.c_double(fric), C.c_int(nip), _pd(gap)))
+            ncs = []
+            for tv in range(2):
+                q = p + f"s{tv}."
+                nops = 10 if (self.muscSett & 1) else 7
+                for k in range(nops):
+                    m = ddpk.get_csr(d, q + OPS[k])
+                    check(lib.ddpca_admm_set_side_op(h, C.c_int(ts), C.c_int(tv), C.c_int(k), C.c_int(m.shape[0]), C.c_int(m.shape[1]), _pi(m.rowptr), _pi(m.colidx), _pd(m.val)))
+                ncs.append(int(d[q + "inteMass.shape"][0]))
+                for which, nm, mat in ((SOLVER_MASS, "inteDiso", "inteMass"), (SOLVER_MASS_PENA, "inteDiso_pena", "inteMass_pena")):
+                    s = _factor_from_dump(d, q + nm, device, ddpk.get_csr(d, q + mat), factorize)
+                    check(lib.ddpca_admm_set_side_solver(h, C.c_int(ts), C.c_int(tv), C.c_int(which), s.release()))
+            self.nc.append(ncs)
+        if self.muscSett & 1:
+            s = _factor_from_dump(d, "coarSolv_D", device, ddpk.get_csr(d, "globCoup"), factorize)
+            base = np.ascontiguousarray(d["baseReco"], dtype=np.int64)
+            check(lib.ddpca_admm_set_macro(h, C.c_int(s.n), base.ctypes.data_as(C.POINTER(C.c_long)), s.release()))
+        check(lib.ddpca_admm_finalize(h))
+        self.row_len = int(lib.ddpca_admm_row_length(h))
+        self.moniReco = [[0.0] * 10 for _ in range(nb + 4 * ni)]  # MCONTACT.h:2494-2498
+        return self
+
+    def close(self):
+        if self._h is not None:
+            load_library().ddpca_admm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def step(self, tc: int):
+        """One pass of the loop body (MCONTACT.h:2505-2704) on the device; returns the monitor row."""
+        row = np.empty(self.row_len)
+        it, dofit = C.c_long(), C.c_double()
+        macro = 1 if ((self.muscSett >> 0) % 2 == 1 and tc <= self.MULT_MAXI) else 0  # :2540
+        check(load_library().ddpca_admm_step(self._h, C.c_int(macro), _pd(row), C.byref(it), C.byref(dofit)))
+        self.cg_iters += it.value
+        self.cg_dof_iters += dofit.value
+        return row
+
+    def MONITOR(self, tc: int, row):
+        """MCONTACT::MONITOR (MCONTACT.h:2725-2845) on the sums the device returned.  Returns 1 when
+        converged, -1 otherwise; lowers MULT_MAXI once the oscillation test passes (:2838-2840)."""
+        cyc = 10
+        flag0 = tc >= cyc
+        flag1 = True
+        c = 0
+        for v in range(self.nb):
+            dv, al = row[c], row[c + 1]
+            c += 2
+            self.moniReco[v][tc % cyc] = dv
+            if tc >= cyc:
+                medi, osci = VECT_MEDI_OSCI(self.moniReco[v])
+                if osci > 0.1 * medi:
+                    flag0 = False
+            if dv > 1.0e-12 * al:
+                flag1 = False
+        for ts in range(self.ni):
+            for tv in range(2):
+                k = self.nb + 4 * ts + 2 * tv
+                da, aa, dl, la = row[c], row[c + 1], row[c + 2], row[c + 3]
+                c += 4
+                self.moniReco[k][tc % cyc] = da
+                if tc >= cyc:
+                    medi, osci = VECT_MEDI_OSCI(self.moniReco[k])
+                    if osci > 0.1 * medi:
+                        flag0 = False
+                if da > 1.0e-12 * aa:
+                    flag1 = False
+                self.moniReco[k + 1][tc % cyc] = dl  # multiplier criteria are disabled in the reference (:2822,:2830)
+        if flag0:
+            self.MULT_MAXI = tc
+        return 1 if flag1 else -1
+
+    def CONTACT_ANALYSIS(self, maxiIter: int = 3000):
+        """MCONTACT::CONTACT_ANALYSIS (MCONTACT.h:2493-2723).  Returns 1; iterNumbReco as the reference."""
+        self.resuMoni = []
+        tc = 0
+        while tc < maxiIter:
+            row = self.step(tc)
+            self.resuMoni.append(row)
+            if self.MONITOR(tc, row) == 1:
+                break
+            tc += 1
+        self.iterNumbReco = tc
+        return 1
+
+    # ---- state read-back (the reference's public members) -----------------------------------------
+    @property
+    def resuDisp(self):
+        out = []
+        for v in range(self.nb):
+            a = np.empty(self.nfull[v])
+            check(load_library().ddpca_admm_get_disp(self._h, C.c_int(v), _pd(a)))
+            out.append(a)
+        return out
+
+    def _side(self, which):
+        out = []
+        for ts in range(self.ni):
+            row = []
+            for tv in range(2):
+                a = np.empty(self.nc[ts][tv])
+                args = (_pd(a), None) if which == 0 else (None, _pd(a))
+                check(load_library().ddpca_admm_get_side(self._h, C.c_int(ts), C.c_int(tv), *args))
+                row.append(a)
+            out.append(row)
+        return out
+
+    @property
+    def inteAuxi(self):
+        return self._side(0)
+
+    @property
+    def inteLagr(self):
+        return self._side(1)
+
+    def inpoGamm(self, ts: int):
+        """(inpoGamm[ts], fricStat) of the last iteration: the content of resuCont_<ts>.txt."""
+        g = np.empty(self.ng[ts])
+        st = np.empty(self.ng[ts], dtype=np.int32)
+        check(load_library().ddpca_admm_get_gamma(self._h, C.c_int(ts), _pd(g), st.ctypes.data_as(C.POINTER(C.c_int))))
+        return g, st
+
+    def launch_count(self, reset=False):
+        return int(load_library().ddpca_admm_launch_count(self._h, C.c_int(1 if reset else 0)))

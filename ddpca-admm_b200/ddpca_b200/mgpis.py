@@ -141,6 +141,26 @@ class MGPIS:
         self.last_iterNumb, self.last_resid, self.last_tol = it.value, res.value, tol.value
         return it.value
 
+    def BiCGSTAB_SOLV(self, precSwit: int, totaForc, rel_tol: float = 1.0e-14, maxit: int | None = None):
+        """MGPIS::BiCGSTAB_SOLV (MGPIS.h:350-432). Returns resuSolu; iterNumb in .last_iterNumb."""
+        b = _f64(totaForc)
+        n = self.n()
+        x = np.empty(n)
+        it, res, tol = C.c_long(), C.c_double(), C.c_double()
+        check(load_library().ddpca_mg_bicgstab(self._handle(), C.c_int(precSwit), _pd(b), _pd(x), C.c_double(rel_tol),
+                                               C.c_long(n if maxit is None else maxit), C.byref(it), C.byref(res), C.byref(tol)))
+        self.last_iterNumb, self.last_resid, self.last_tol = it.value, res.value, tol.value
+        return x
+
+    def MULT_SOLV(self, totaForc):
+        """MGPIS::MULT_SOLV (MGPIS.h:130-160): stand-alone V-cycle iteration."""
+        b = _f64(totaForc)
+        x = np.empty(self.n())
+        it, res = C.c_long(), C.c_double()
+        check(load_library().ddpca_mg_mult_solv(self._handle(), _pd(b), _pd(x), C.byref(it), C.byref(res)))
+        self.last_iterNumb, self.last_resid = it.value, res.value
+        return x
+
     def MULT_VCYC(self, tempLeve: int, righHand, resuSolu=None):
         """MGPIS::MULT_VCYC (MGPIS.h:55-128); resuSolu is the in/out iterate (zeros if None)."""
         b = _f64(righHand)

@@ -1,0 +1,221 @@
+// MGPIS.h -- B200 overlay of the reference's MGPIS.h (class MGPIS, /root/reference/MGPIS.h:8-38).
+//
+// Drop-in use: compile any reference example unchanged with
+//     g++ ... -include <repo>/ddpca-admm_b200/host/MGPIS.h -I<repo>/include -I<reference> \
+//         examples/BEAM.cpp -L<repo>/ddpca-admm_b200/lib -lddpca_b200
+// The include guard below is the reference's own (_MGPIS_H), so the `#include "MGPIS.h"` inside
+// the reference's MULTIGRID.h / MCONTACT.h becomes a no-op and every `MGPIS mgpi` member in the
+// reference is this class.  The public surface is kept verbatim (members maxiLeve, realProl,
+// consStif, consLowe, consDiag, consUppe are read and written by MULTIGRID.h:102,133-138,
+// 1214-1251 and MCONTACT.h:830,853,1539-1542; method signatures as MGPIS.h:16-37); the bodies
+// forward to the C ABI of include/ddpca_b200.h.  No CPU fallback: if the device call fails the
+// error is printed in the reference's style ("ERROR") and -1 is returned.
+#ifndef _MGPIS_H
+#define _MGPIS_H
+
+#include "PREP.h"
+#include "ddpca_b200.h"
+
+#include <cstdlib>
+#include <memory>
+
+class MGPIS{
+public:
+	/*********************************************************************************************/
+	long maxiLeve;                                                              // MGPIS.h:12
+	std::vector<Eigen::SparseMatrix<double,Eigen::RowMajor>> realProl;          // MGPIS.h:13
+	std::vector<Eigen::SparseMatrix<double,Eigen::RowMajor>> consStif;          // MGPIS.h:15
+	long ESTABLISH();                                                           // MGPIS.h:16
+	long MULT_SOLV(const Eigen::VectorXd &totaForc, Eigen::VectorXd &resuSolu); // MGPIS.h:18
+	long CG_SOLV(long precSwit, const Eigen::VectorXd &totaForc, Eigen::VectorXd &resuSolu);       // :22
+	long GMRES_SOLV(long precSwit, const Eigen::VectorXd &totaForc, Eigen::VectorXd &resuSolu);    // :24
+	long BiCGSTAB_SOLV(long precSwit, const Eigen::VectorXd &totaForc, Eigen::VectorXd &resuSolu); // :26
+	/*********************************************************************************************/
+	std::vector<Eigen::SparseMatrix<double,Eigen::RowMajor>> consLowe;          // MGPIS.h:29
+	std::vector<Eigen::SparseMatrix<double,Eigen::RowMajor>> consDiag;          // MGPIS.h:31
+	std::vector<Eigen::SparseMatrix<double,Eigen::RowMajor>> consUppe;          // MGPIS.h:33
+	long MULT_VCYC(long tempLeve, const Eigen::VectorXd &righHand,
+		Eigen::VectorXd &resuSolu, const DIRE_SOLV &direSolv
+	);                                                                          // MGPIS.h:35-37
+	/***************************** additions of the B200 build ***********************************/
+	MGPIS() : maxiLeve(-1) {}
+	// the device hierarchy is owned by one object; copies (MULTIGRID::COPY, vector growth)
+	// start without one and build their own on first use
+	MGPIS(const MGPIS &o) : maxiLeve(o.maxiLeve), realProl(o.realProl), consStif(o.consStif),
+		consLowe(o.consLowe), consDiag(o.consDiag), consUppe(o.consUppe) {}
+	MGPIS &operator=(const MGPIS &o){
+		if(this != &o){
+			maxiLeve = o.maxiLeve; realProl = o.realProl; consStif = o.consStif;
+			consLowe = o.consLowe; consDiag = o.consDiag; consUppe = o.consUppe;
+			devi.reset();
+		}
+		return *this;
+	}
+	// device hierarchy (built lazily from consStif / realProl); nullptr + message on failure
+	ddpca_mg *DEVICE_HANDLE();
+	// hand the hierarchy over to another owner (ddpca_admm_set_body takes ownership)
+	ddpca_mg *RELEASE_HANDLE(){ ddpca_mg *h = DEVICE_HANDLE(); if(devi) devi->h = nullptr; devi.reset(); return h; }
+	static int DEVICE(){ const char *e = std::getenv("DDPCA_DEVICE"); return e ? std::atoi(e) : 0; }
+	// DDPCA_SMOOTHER=lex reproduces the reference's lexicographic sweeps exactly (slow),
+	// default mc = multicolour ordering of the same symmetric Gauss-Seidel (include/ddpca_b200.h)
+	static int SMOOTHER(){
+		const char *e = std::getenv("DDPCA_SMOOTHER");
+		return (e && (e[0] == 'l' || e[0] == 'L')) ? DDPCA_SMOOTH_LEX : DDPCA_SMOOTH_MC;
+	}
+	long lastIterNumb = 0;      // iterNumb of the last CG_SOLV / BiCGSTAB_SOLV (the reference only prints it)
+private:
+	struct DEVI{
+		ddpca_mg *h = nullptr;
+		~DEVI(){ if(h) ddpca_mg_destroy(h); }
+	};
+	std::shared_ptr<DEVI> devi;
+};
+
+long MGPIS::ESTABLISH(){
+	// the L/D/U members stay available to the reference code that copies them by name
+	// (MULTIGRID.h:136-138); the device keeps its own single-copy layout
+	consLowe.resize(maxiLeve + 1);
+	consDiag.resize(maxiLeve + 1);
+	consUppe.resize(maxiLeve + 1);
+	for(long ti = 0; ti <= maxiLeve; ti ++){
+		consStif[ti].makeCompressed();
+		consLowe[ti] = consStif[ti].triangularView<Eigen::StrictlyLower>();
+		consUppe[ti] = consStif[ti].triangularView<Eigen::StrictlyUpper>();
+		std::vector<Eigen::Triplet<double>> diagList;
+		diagList.reserve(consStif[ti].rows());
+		for(long tj = 0; tj < consStif[ti].rows(); tj ++){
+			diagList.emplace_back(tj, tj, consStif[ti].coeff(tj,tj));
+		}
+		consDiag[ti].resize(consStif[ti].rows(), consStif[ti].cols());
+		consDiag[ti].setFromTriplets(diagList.begin(), diagList.end());
+	}
+	for(long ti = 0; ti < maxiLeve; ti ++){
+		realProl[ti].makeCompressed();
+	}
+	devi.reset();
+	return 1;
+}
+
+ddpca_mg *MGPIS::DEVICE_HANDLE(){
+	if(devi && devi->h){
+		return devi->h;
+	}
+	const long nlev = maxiLeve + 1;
+	std::vector<int> n(nlev);
+	std::vector<const int*> rp(nlev), ci(nlev), prp(nlev), pci(nlev);
+	std::vector<const double*> va(nlev), pva(nlev);
+	for(long ti = 0; ti < nlev; ti ++){
+		if(!consStif[ti].isCompressed()){
+			consStif[ti].makeCompressed();
+		}
+		n[ti] = consStif[ti].rows();
+		rp[ti] = consStif[ti].outerIndexPtr();
+		ci[ti] = consStif[ti].innerIndexPtr();
+		va[ti] = consStif[ti].valuePtr();
+	}
+	for(long ti = 0; ti + 1 < nlev; ti ++){
+		if(!realProl[ti].isCompressed()){
+			realProl[ti].makeCompressed();
+		}
+		prp[ti] = realProl[ti].outerIndexPtr();
+		pci[ti] = realProl[ti].innerIndexPtr();
+		pva[ti] = realProl[ti].valuePtr();
+	}
+	ddpca_mg *h = nullptr;
+	if(ddpca_mg_create(DEVICE(), nlev, n.data(), rp.data(), ci.data(), va.data(),
+		prp.data(), pci.data(), pva.data(), SMOOTHER(), &h) != 0){
+		std::cout << "MGPIS (B200): ERROR " << ddpca_last_error() << std::endl;
+		return nullptr;
+	}
+	devi = std::make_shared<DEVI>();
+	devi->h = h;
+	return h;
+}
+
+long MGPIS::MULT_VCYC(long tempLeve, const Eigen::VectorXd &righHand,
+	Eigen::VectorXd &resuSolu, const DIRE_SOLV &direSolv){
+	(void)direSolv;// level 0 is solved with the factorisation held on the device
+	ddpca_mg *h = DEVICE_HANDLE();
+	if(h == nullptr || ddpca_mg_vcycle(h, tempLeve, righHand.data(), resuSolu.data()) != 0){
+		std::cout << "MGPIS::MULT_VCYC (B200): ERROR " << ddpca_last_error() << std::endl;
+		return -1;
+	}
+	return 1;
+}
+
+long MGPIS::CG_SOLV(long precSwit, const Eigen::VectorXd &totaForc, Eigen::VectorXd &resuSolu){
+	std::cout << "MGPIS::CG_SOLV";
+	if(precSwit == 0){
+		std::cout << " (diagonal preconditioner)";
+	}
+	else if(precSwit == 1){
+		std::cout << " (multigrid preconditioner)";
+	}
+	OUTPUT_TIME("");
+	resuSolu = Eigen::VectorXd::Zero(consStif[maxiLeve].rows());
+	ddpca_mg *h = DEVICE_HANDLE();
+	long iterNumb = 0;
+	double resiNorm = 0.0, toleLimi = 0.0;
+	if(h == nullptr || ddpca_mg_pcg(h, precSwit, totaForc.data(), resuSolu.data(), 1.0E-14,
+		resuSolu.rows(), &iterNumb, &resiNorm, &toleLimi) != 0){
+		std::cout << "MGPIS::CG_SOLV (B200): ERROR " << ddpca_last_error() << std::endl;
+		return -1;
+	}
+	lastIterNumb = iterNumb;
+	std::cout << "#Iteration: " << iterNumb - 1
+		<< ", residual: " << resiNorm << "/" << toleLimi;
+	OUTPUT_TIME(":");
+	return 1;
+}
+
+long MGPIS::BiCGSTAB_SOLV(long precSwit,
+	const Eigen::VectorXd &totaForc, Eigen::VectorXd &resuSolu){
+	std::cout << "MGPIS::BiCGSTAB_SOLV";
+	if(precSwit == 0){
+		std::cout << " (diagonal preconditioner)";
+	}
+	else if(precSwit == 1){
+		std::cout << " (multigrid preconditioner)";
+	}
+	OUTPUT_TIME("");
+	resuSolu = Eigen::VectorXd::Zero(consStif[maxiLeve].rows());
+	ddpca_mg *h = DEVICE_HANDLE();
+	long iterNumb = 0;
+	double resiNorm = 0.0, toleLimi = 0.0;
+	if(h == nullptr || ddpca_mg_bicgstab(h, precSwit, totaForc.data(), resuSolu.data(), 1.0E-14,
+		resuSolu.rows(), &iterNumb, &resiNorm, &toleLimi) != 0){
+		std::cout << "MGPIS::BiCGSTAB_SOLV (B200): ERROR " << ddpca_last_error() << std::endl;
+		return -1;
+	}
+	lastIterNumb = iterNumb;
+	std::cout << "#Iteration: " << iterNumb - 1
+		<< ", residual: " << resiNorm << "/" << toleLimi;
+	OUTPUT_TIME(":");
+	return 1;
+}
+
+long MGPIS::MULT_SOLV(const Eigen::VectorXd &totaForc, Eigen::VectorXd &resuSolu){
+	OUTPUT_TIME("MGPIS::MULT_SOLV");
+	resuSolu = Eigen::VectorXd::Zero(consStif[maxiLeve].rows());
+	ddpca_mg *h = DEVICE_HANDLE();
+	long iterNumb = 0;
+	double resiNorm = 0.0;
+	if(h == nullptr || ddpca_mg_mult_solv(h, totaForc.data(), resuSolu.data(), &iterNumb, &resiNorm) != 0){
+		std::cout << "MGPIS::MULT_SOLV (B200): ERROR " << ddpca_last_error() << std::endl;
+		return -1;
+	}
+	std::cout << "#Iteration: " << iterNumb << ", residual: "
+		<< resiNorm << "/" << 1.0E-14 * totaForc.norm();
+	OUTPUT_TIME(":");
+	return 1;
+}
+
+long MGPIS::GMRES_SOLV(long precSwit, const Eigen::VectorXd &totaForc, Eigen::VectorXd &resuSolu){
+	// not referenced by any example of the reference (only in a comment, examples/BEAM.h:416);
+	// not yet offered by the B200 build
+	(void)precSwit; (void)totaForc; (void)resuSolu;
+	std::cout << "MGPIS::GMRES_SOLV (B200): ERROR not available, use CG_SOLV or BiCGSTAB_SOLV" << std::endl;
+	return -1;
+}
+
+#endif

@@ -266,3 +266,85 @@ long orc_cg_solv(orc_mg *h, long precSwit, const double *b, double *x, double *r
     free(r); free(p); free(q); free(z); free(dinv);
     return it;
 }
+
+/* MGPIS::MULT_SOLV, MGPIS.h:130-160.  Returns iterNumb; *resid_out = moniErro[iterNumb % 5]. */
+long orc_mult_solv(orc_mg *h, const double *b, double *x, double *resid_out)
+{
+    int L = h->nlev - 1;
+    const csr_t *A = &h->A[L];
+    int n = A->n;
+    memset(x, 0, sizeof(double) * n);                       /* :133 */
+    long maxiNumb = 10000;                                  /* :134 */
+    orc_mg_factor(h);                                       /* :137 */
+    double *r = (double *)malloc(sizeof(double) * n);
+    double moni[5] = {0, 0, 0, 0, 0};
+    long it = 0;
+    while (it < maxiNumb) {                                 /* :142 */
+        orc_vcycle(h, L, b, x);                             /* :143 */
+        orc_spmv(n, A->rp, A->ci, A->v, x, r);
+        for (int i = 0; i < n; i++) r[i] = b[i] - r[i];     /* :144 */
+        moni[it % 5] = sqrt(dot(n, r, r));                  /* :146 */
+        if (it >= 4) {                                      /* :147-153, VECT_MEDI_OSCI PREP.h:147-153 */
+            double mx = moni[0], mn = moni[0];
+            for (int k = 1; k < 5; k++) { if (moni[k] > mx) mx = moni[k]; if (moni[k] < mn) mn = moni[k]; }
+            if (mx - mn < 0.1 * ((mx + mn) / 2.0)) break;
+        }
+        it++;
+    }
+    if (resid_out) *resid_out = moni[it % 5];
+    free(r);
+    return it;
+}
+
+/* MGPIS::BiCGSTAB_SOLV, MGPIS.h:350-432.  Returns iterNumb. */
+long orc_bicgstab(orc_mg *h, long precSwit, const double *b, double *x, double *resid_out, double *tol_out)
+{
+    int L = h->nlev - 1;
+    const csr_t *A = &h->A[L];
+    int n = A->n;
+    memset(x, 0, sizeof(double) * n);                       /* :361 */
+    long maxiNumb = n;                                      /* :362 */
+    double toleLimi = 1.0E-14 * sqrt(dot(n, b, b));         /* :363 */
+    double *dinv = NULL;
+    if (precSwit == 0) {
+        dinv = (double *)malloc(sizeof(double) * n);
+        for (int i = 0; i < n; i++) dinv[i] = 1.0 / A->v[h->dpos[L][i]];
+    } else orc_mg_factor(h);                                /* :373 */
+    size_t nb = sizeof(double) * n;
+    double *r = (double *)malloc(nb), *rh = (double *)malloc(nb), *p = (double *)calloc(n, sizeof(double));
+    double *v = (double *)calloc(n, sizeof(double)), *s = (double *)malloc(nb), *t = (double *)malloc(nb);
+    double *ph = (double *)malloc(nb), *sh = (double *)malloc(nb);
+    memcpy(r, b, nb);                                       /* :377 */
+    memcpy(rh, r, nb);                                      /* :378 */
+    double rho[2] = {0, 0}, alph = 0, omeg = 0;
+    long it = 0;
+    while (it < maxiNumb && sqrt(dot(n, r, r)) > toleLimi) {            /* :382 */
+        rho[(it + 1) % 2] = dot(n, rh, r);                              /* :383 */
+        if (fabs(rho[(it + 1) % 2]) == 0.0) break;                      /* :384-387 */
+        if (it == 0) memcpy(p, r, nb);                                  /* :389 */
+        else {
+            double beta = (rho[(it + 1) % 2] / rho[it % 2]) * (alph / omeg);   /* :392-393 */
+            for (int i = 0; i < n; i++) p[i] = r[i] + beta * (p[i] - omeg * v[i]);   /* :394 */
+        }
+        if (precSwit == 0) for (int i = 0; i < n; i++) ph[i] = dinv[i] * p[i];
+        else { memset(ph, 0, nb); orc_vcycle(h, L, p, ph); }            /* :396-402 */
+        orc_spmv(n, A->rp, A->ci, A->v, ph, v);                         /* :403 */
+        alph = rho[(it + 1) % 2] / dot(n, rh, v);                       /* :404 */
+        for (int i = 0; i < n; i++) s[i] = r[i] - alph * v[i];          /* :405 */
+        if (sqrt(dot(n, s, s)) <= 0.0) {                                /* :406-409 */
+            for (int i = 0; i < n; i++) x[i] += alph * ph[i];
+            break;
+        }
+        if (precSwit == 0) for (int i = 0; i < n; i++) sh[i] = dinv[i] * s[i];
+        else { memset(sh, 0, nb); orc_vcycle(h, L, s, sh); }            /* :410-416 */
+        orc_spmv(n, A->rp, A->ci, A->v, sh, t);                         /* :417 */
+        omeg = dot(n, t, s) / dot(n, t, t);                             /* :418 */
+        for (int i = 0; i < n; i++) x[i] += alph * ph[i] + omeg * sh[i];/* :419 */
+        for (int i = 0; i < n; i++) r[i] = s[i] - omeg * t[i];          /* :420 */
+        it++;
+    }
+    if (resid_out) *resid_out = sqrt(dot(n, r, r));
+    if (tol_out) *tol_out = toleLimi;
+    free(r); free(rh); free(p); free(v); free(s); free(t); free(ph); free(sh); free(dinv);
+    return it;
+}

@@ -31,6 +31,8 @@ def lib() -> C.CDLL:
         _LIB = C.CDLL(path)
         _LIB.orc_mg_create.restype = C.c_void_p
         _LIB.orc_cg_solv.restype = C.c_long
+        _LIB.orc_bicgstab.restype = C.c_long
+        _LIB.orc_mult_solv.restype = C.c_long
     return _LIB
 
 
@@ -97,6 +99,28 @@ class OracleMG:
         tol = C.c_double()
         it = lib().orc_cg_solv(self.h, C.c_long(prec), _p(b, C.c_double), _p(x, C.c_double), C.byref(res), C.byref(tol))
         return x, int(it), res.value, tol.value
+
+
+def _bicgstab(self, prec, b):
+    """BiCGSTAB_SOLV(precSwit, b, x) -- MGPIS.h:350-432.  Returns (x, iterNumb, resid, tol)."""
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros_like(b)
+    res, tol = C.c_double(), C.c_double()
+    it = lib().orc_bicgstab(self.h, C.c_long(prec), _p(b, C.c_double), _p(x, C.c_double), C.byref(res), C.byref(tol))
+    return x, int(it), res.value, tol.value
+
+
+def _mult_solv(self, b):
+    """MULT_SOLV(b, x) -- MGPIS.h:130-160.  Returns (x, iterNumb, resid)."""
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros_like(b)
+    res = C.c_double()
+    it = lib().orc_mult_solv(self.h, _p(b, C.c_double), _p(x, C.c_double), C.byref(res))
+    return x, int(it), res.value
+
+
+OracleMG.bicgstab = _bicgstab
+OracleMG.mult_solv = _mult_solv
 
 
 def spmv(a, x):

@@ -11,7 +11,7 @@
 //     the results (golden vectors), with wall-clock timings.
 //
 // usage: beam_nodd --glob G [--divi a,b,c] [--out file.ddpk] [--nomat]
-//                  [--solve 0|1] [--jacobi 0|1] [--reps R]
+//                  [--solve 0|1] [--jacobi 0|1] [--extra 0|1] [--reps R]
 //                  [--bench-steps K --bench-warmup W]   (reference arm of bench.py: W untimed +
 //                   K timed MGPIS::CG_SOLV(1,...) calls, wall clock around the K calls)
 #include "examples/BEAM.h"
@@ -19,7 +19,7 @@
 #include "ref_capture.h"
 
 int main(int argc, char **argv) {
-	long glob = 2, doSolve = 1, doJacobi = 0, reps = 1, noMat = 0, benchSteps = 0, benchWarm = 0;
+	long glob = 2, doSolve = 1, doJacobi = 0, reps = 1, noMat = 0, benchSteps = 0, benchWarm = 0, doExtra = 0;
 	std::vector<long> divi;
 	std::string out;
 	for (int i = 1; i < argc; i++) {
@@ -35,6 +35,7 @@ int main(int argc, char **argv) {
 		else if (a == "--jacobi") doJacobi = std::stol(next());
 		else if (a == "--reps") reps = std::stol(next());
 		else if (a == "--nomat") noMat = 1;
+		else if (a == "--extra") doExtra = std::stol(next());
 		else if (a == "--bench-steps") benchSteps = std::stol(next());
 		else if (a == "--bench-warmup") benchWarm = std::stol(next());
 		else { std::cerr << "unknown arg " << a << std::endl; return 2; }
@@ -114,6 +115,19 @@ int main(int argc, char **argv) {
 		long iters = cap.last_iteration_plus1();
 		if (w) { w->vec("cg_jacobi_x", x); w->scalar_i64("cg_jacobi_iters", iters); }
 		js << ",\"cg_jacobi_iters\":" << iters << ",\"cg_jacobi_s\":" << dt;
+	}
+	if (doExtra) {
+		// the other MGPIS drivers: BiCGSTAB_SOLV (MGPIS.h:350-432) and MULT_SOLV (MGPIS.h:130-160)
+		Eigen::VectorXd x;
+		cap.buf.str("");
+		mgpi.BiCGSTAB_SOLV(1, mg.consForc, x);
+		long itb = cap.last_iteration_plus1();
+		if (w) { w->vec("bicgstab_mg_x", x); w->scalar_i64("bicgstab_mg_iters", itb); }
+		cap.buf.str("");
+		mgpi.MULT_SOLV(mg.consForc, x);
+		long itm = cap.last_iteration_plus1() - 1;   // MULT_SOLV prints iterNumb itself (:156)
+		if (w) { w->vec("mult_solv_x", x); w->scalar_i64("mult_solv_iters", itm); }
+		js << ",\"bicgstab_mg_iters\":" << itb << ",\"mult_solv_iters\":" << itm;
 	}
 	if (benchSteps > 0) {
 		Eigen::VectorXd x;

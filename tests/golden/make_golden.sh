@@ -9,8 +9,8 @@ tmp="$(mktemp -d)"
 cd "$tmp"   # the reference writes Beam/ Block/ result directories into the cwd
 # 2-level and 3-level BEAM (no domain decomposition) hierarchies + reference
 # MGPIS::MULT_VCYC / CG_SOLV / OUTP_SUB1 results (examples/BEAM.h:403-421)
-"$ref/beam_nodd" --glob 1 --divi 8,2,2 --jacobi 1 --out "$tmp/beam_2lev.ddpk" > "$here/beam_2lev.json"
-"$ref/beam_nodd" --glob 2 --divi 4,2,2 --jacobi 1 --out "$tmp/beam_3lev.ddpk" > "$here/beam_3lev.json"
+"$ref/beam_nodd" --glob 1 --divi 8,2,2 --jacobi 1 --extra 1 --out "$tmp/beam_2lev.ddpk" > "$here/beam_2lev.json"
+"$ref/beam_nodd" --glob 2 --divi 4,2,2 --jacobi 1 --extra 1 --out "$tmp/beam_3lev.ddpk" > "$here/beam_3lev.json"
 gzip -9 -n -c "$tmp/beam_2lev.ddpk" > "$here/beam_2lev.ddpk.gz"
 gzip -9 -n -c "$tmp/beam_3lev.ddpk" > "$here/beam_3lev.ddpk.gz"
 rm -rf "$tmp"

@@ -64,3 +64,36 @@ def permute_hierarchy(A, P, perms):
         m = pm.to_scipy()
         Ps.append(ddpk.Csr.from_scipy(m[perms[l + 1]][:, perms[l]]))
     return As, Ps
+
+
+def dense_ldlt_factor(m):
+    """(perm, L, D) of a small SPD Csr through a dense Cholesky: identity ordering,
+    unit-lower L (strict part, CSR) and D, in the layout ddpca_ldlt_create expects.
+    Test-side stand-in for Eigen::SimplicialLDLT when a fixture carries no factors."""
+    a = m.to_scipy().toarray()
+    c = np.linalg.cholesky(a)
+    dg = np.diag(c)
+    Lu = c / dg[None, :]
+    D = dg * dg
+    import scipy.sparse as sp
+
+    L = sp.csr_matrix(np.tril(Lu, -1))
+    return np.arange(a.shape[0], dtype=np.int32), ddpk.Csr.from_scipy(L), D
+
+
+def run_ref_block(glob, divi=None, musc=1, ref_iters=0):
+    """Run the prebuilt reference BLOCK driver (oracle/_ref/block_admm) and load its dump."""
+    key = ("block", glob, tuple(divi) if divi else None, musc, ref_iters)
+    if key in _cache:
+        return _cache[key]
+    tmp = tempfile.mkdtemp(prefix="ddpca_ref_")
+    out = os.path.join(tmp, "block.ddpk")
+    cmd = [os.path.join(REF_BIN, "block_admm"), "--glob", str(glob), "--musc", str(musc), "--out", out, "--ref-iters", str(ref_iters)]
+    if divi:
+        cmd += ["--divi", ",".join(str(v) for v in divi)]
+    txt = subprocess.check_output(cmd, cwd=tmp).decode()
+    meta = json.loads(txt.strip().splitlines()[-1])
+    d = ddpk.load(out)
+    os.remove(out)
+    _cache[key] = (d, meta)
+    return _cache[key]

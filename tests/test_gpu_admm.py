@@ -1,0 +1,137 @@
+"""GPU parity tests of the ADMM loop (MCONTACT::CONTACT_ANALYSIS) and the device LDLT solve,
+against the reference's golden vectors and the CPU oracle (oracle/admm_oracle.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import ddpca_b200 as dd
+from ddpca_b200 import ddpk
+from tests.helpers import GOLDEN, dense_ldlt_factor, have_ref_binary, rel, run_ref_block
+
+pytestmark = pytest.mark.gpu
+
+
+def _moni(d, key):
+    return d[key].reshape(tuple(int(v) for v in d[key + ".shape"]))
+
+
+def _rows_close(mine, ref, rtol):
+    mine, ref = np.asarray(mine), np.asarray(ref)
+    scale = np.abs(ref).max(axis=0, keepdims=True)
+    sig = np.abs(ref) > 1e-16 * scale
+    return float(np.max(np.abs(mine - ref)[sig] / np.abs(ref)[sig])) < rtol
+
+
+@pytest.fixture(scope="module")
+def block_small():
+    d = ddpk.load(os.path.join(GOLDEN, "block_small.ddpk.gz"))
+    meta = json.load(open(os.path.join(GOLDEN, "block_small.json")))
+    return d, meta
+
+
+def test_ldlt_solve_matches_direct_solve(block_small):
+    d, meta = block_small
+    rng = np.random.default_rng(0)
+    for name in ("if0.s0.inteMass", "if7.s1.inteMass_pena", "globCoup"):
+        m = ddpk.get_csr(d, name)
+        perm, L, D = dense_ldlt_factor(m)
+        s = dd.DIRE_SOLV(perm, L, D)
+        b = rng.standard_normal(m.shape[0])
+        x = s.solve(b)
+        assert rel(m.to_scipy() @ x, b) < 1e-10
+        info = s.info()
+        assert info["n"] == m.shape[0] and info["stages_fwd"] >= 1
+        s.close()
+
+
+@pytest.mark.skipif(not have_ref_binary("block_admm"), reason="oracle/_ref/block_admm not built")
+def test_ldlt_solve_with_eigen_amd_factor():
+    """The factor exactly as Eigen::SimplicialLDLT produced it (AMD ordering) in the reference run."""
+    d, meta = run_ref_block(1, divi=(2, 2, 2), musc=1, ref_iters=-1)
+    rng = np.random.default_rng(1)
+    for name, mat in (("coarSolv_D", "globCoup"), ("if6.s0.inteDiso", "if6.s0.inteMass"), ("if0.s1.inteDiso_pena", "if0.s1.inteMass_pena")):
+        s = dd.DIRE_SOLV(d[name + ".perm"], ddpk.get_csr(d, name + ".L"), d[name + ".D"])
+        m = ddpk.get_csr(d, mat).to_scipy()
+        b = rng.standard_normal(m.shape[0])
+        assert rel(m @ s.solve(b), b) < 1e-10
+        s.close()
+
+
+@pytest.mark.parametrize("smoother", [dd.SMOOTH_MC, dd.SMOOTH_LEX])
+def test_admm_macroscopic_run_matches_reference(block_small, smoother):
+    d, meta = block_small
+    mc = dd.MCONTACT.from_ddpk(d, smoother=smoother, factorize=dense_ldlt_factor)
+    mc.CONTACT_ANALYSIS()
+    assert mc.iterNumbReco == meta["musc1"]["ref_iterNumbReco"] == int(d["ref.iterNumbReco"][0])   # bit-exact count
+    disp = mc.resuDisp
+    for v in range(mc.nb):
+        assert rel(disp[v], d[f"ref.resuDisp{v}"]) < 1e-8
+    aux, lagr = mc.inteAuxi, mc.inteLagr
+    for ts in range(mc.ni):
+        for tv in range(2):
+            assert rel(aux[ts][tv], d[f"ref.if{ts}.s{tv}.inteAuxi"]) < 1e-8
+            assert rel(lagr[ts][tv], d[f"ref.if{ts}.s{tv}.inteLagr"]) < 1e-6
+    for ts in range(mc.ni):
+        if mc.fricCoef[ts] == 0.0:
+            g, st = mc.inpoGamm(ts)
+            p_ref = _moni(d, f"ref.resuCont{ts}")[:, 0]
+            assert rel(g, p_ref) < 1e-8                      # contact pressure
+            assert ((g > 0) == (p_ref > 0)).all()            # active contact set, bit-exact
+    assert mc.launch_count() > 0 and mc.cg_iters > 0
+    mc.close()
+
+
+def test_admm_trajectory_without_coarse_space_matches_reference(block_small):
+    d, meta = block_small
+    ref = _moni(d, "ref0.resuMoni")
+    mc = dd.MCONTACT.from_ddpk(d, muscSett=0, factorize=dense_ldlt_factor)
+    mc.CONTACT_ANALYSIS(maxiIter=ref.shape[0])
+    assert len(mc.resuMoni) == ref.shape[0]
+    assert _rows_close(mc.resuMoni, ref, 1e-6)
+    mc.close()
+
+
+def test_admm_matches_cpu_oracle_state_by_state(block_small):
+    from oracle.admm_oracle import AdmmOracle
+
+    d, meta = block_small
+    o = AdmmOracle(d)
+    o.muscSett = 0
+    mc = dd.MCONTACT.from_ddpk(d, muscSett=0, factorize=dense_ldlt_factor)
+    for tc in range(5):
+        o.step(tc)
+        mc.step(tc)
+    disp = mc.resuDisp
+    for v in range(mc.nb):
+        assert rel(disp[v], o.resuDisp[v]) < 1e-9
+    lagr = mc.inteLagr
+    for ts in range(mc.ni):
+        for tv in range(2):
+            assert rel(lagr[ts][tv], o.inteLagr[ts][tv]) < 1e-8
+        g, st = mc.inpoGamm(ts)
+        assert rel(g, o.inpoGamm[ts]) < 1e-8
+    mc.close()
+
+
+@pytest.mark.skipif(not have_ref_binary("block_admm"), reason="oracle/_ref/block_admm not built")
+def test_block_g2_small_25_iterations_against_reference_run_here():
+    """BLOCK, coarsest mesh 2x2x2, globLeve=2, macroscopic problem: the reference needs 25 ADMM
+    iterations; counts must match exactly, states to 1e-8 (uses Eigen's own LDLT factors)."""
+    d, meta = run_ref_block(2, divi=(2, 2, 2), musc=1, ref_iters=0)
+    mc = dd.MCONTACT.from_ddpk(d)
+    mc.CONTACT_ANALYSIS()
+    assert mc.iterNumbReco == meta["ref_iterNumbReco"]
+    disp = mc.resuDisp
+    for v in range(mc.nb):
+        assert rel(disp[v], d[f"ref.resuDisp{v}"]) < 1e-8
+    ref = _moni(d, "ref.resuMoni")
+    assert len(mc.resuMoni) == ref.shape[0]
+    assert _rows_close(np.array(mc.resuMoni)[:, -2:], ref[:, -2:], 1e-5)   # Cvalu, Ccrit per iteration
+    for ts in range(mc.ni):
+        if mc.fricCoef[ts] == 0.0:
+            g, st = mc.inpoGamm(ts)
+            p_ref = _moni(d, f"ref.resuCont{ts}")[:, 0]
+            assert rel(g, p_ref) < 1e-8 and ((g > 0) == (p_ref > 0)).all()
+    mc.close()
