@@ -186,3 +186,29 @@ def test_beam_g2_against_reference_run_here(mode):
     r = d["consForc"] - orc.spmv(A[-1], x)
     assert np.linalg.norm(r) <= 10 * meta["true_resid"]
     mg.close()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_bicgstab_matches_oracle_and_cg_solution(solvers, name):
+    """MGPIS::BiCGSTAB_SOLV (MGPIS.h:350-432) on the same kernels."""
+    mg, d, meta, A, P = solvers(name, dd.SMOOTH_LEX)
+    x = mg.BiCGSTAB_SOLV(1, d["consForc"])
+    xo, ito, reso, tolo = orc.OracleMG(A, P).bicgstab(1, d["consForc"])
+    assert mg.last_resid <= mg.last_tol
+    assert abs(mg.last_iterNumb - ito) <= max(2, ito // 10)
+    assert rel(x, xo) < 1e-8 and rel(x, d["cg_mg_x"]) < 1e-8
+    if "bicgstab_mg_x" in d:   # the reference's own run
+        assert rel(x, d["bicgstab_mg_x"]) < 1e-8
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_mult_solv_matches_oracle(solvers, name):
+    """MGPIS::MULT_SOLV (MGPIS.h:130-160): V-cycle iteration with the stagnation stop."""
+    mg, d, meta, A, P = solvers(name, dd.SMOOTH_LEX)
+    x = mg.MULT_SOLV(d["consForc"])
+    xo, ito, reso = orc.OracleMG(A, P).mult_solv(d["consForc"])
+    if ito < 100:   # beyond that the stop is decided by round-off noise on the residual floor
+        assert mg.last_iterNumb == ito
+    assert rel(x, xo) < 1e-8
+    if "mult_solv_x" in d:
+        assert rel(x, d["mult_solv_x"]) < 1e-8
