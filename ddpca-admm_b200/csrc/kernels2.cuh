@@ -1,0 +1,332 @@
+// kernels2.cuh -- "v2" level kernels: split lower/upper storage streamed through shared memory
+// by the TMA engine (cp.async.bulk + mbarrier), one cooperative launch per Gauss-Seidel sweep.
+//
+// Why (profiles/r1c): the v1 sweep kernels are latency-bound -- three dependent memory round
+// trips per row group (descriptor -> pattern/values -> x gather), short stage launches, and
+// 64-byte DRAM granularity over-fetch when only half of each row is needed.  Here
+//   * the strictly-lower and strictly-upper couplings of a level live in two separate arrays
+//     in stage order, so a half sweep streams ONE contiguous region;
+//   * a CTA processes CHUNKS of 16 row groups: descriptor, group metadata, diagonal blocks,
+//     patterns and values of a chunk arrive in shared memory by a handful of bulk copies
+//     (UBLKCP), double-buffered, so the only latency left on the critical path is the x gather,
+//     and all gathers of a group are issued back to back from a pattern that is already on chip;
+//   * the stages (colours) of one sweep run inside one cooperative kernel with grid.sync()
+//     between them; the next stage's first chunk is already in flight during the barrier.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace ddpca {
+
+namespace cg = cooperative_groups;
+
+constexpr int kChunkGroups = 16;   // row groups per chunk = sub-warps per CTA
+constexpr int kV2Threads = kChunkGroups * GL;
+static_assert(GL == 8, "v2 kernels assume 8-lane sub-warps");
+
+// 32-byte group descriptor of the split layout
+struct __align__(16) GroupMeta2 {
+    int row0, gs;
+    int nl, nu;      // lower / upper pattern lengths, padded to multiples of 4 (pads: value 0)
+    int cl, cu;      // offsets into CL / CU (ints)
+    int vl, vu;      // offsets into VL / VU in units of 16 bytes (2 doubles)
+};
+// 48-byte chunk descriptor
+struct __align__(16) ChunkDesc {
+    int g0, ng;
+    int cl0, ncl;    // pattern range (ints) of the chunk's lower parts
+    int cu0, ncu;
+    int vl0, nvl;    // value range in 16-byte units
+    int vu0, nvu;
+    int pad0, pad1;
+};
+constexpr int kBlkStride = 10;     // doubles per in-group block record (9 used; 80 B keeps 16-B alignment)
+
+struct Lvl2View {
+    int n, ng, nchunks, nstages;
+    const GroupMeta2 *__restrict__ meta;
+    const int *__restrict__ CL;
+    const double *__restrict__ VL;
+    const int *__restrict__ CU;
+    const double *__restrict__ VU;
+    const double *__restrict__ BD;          // [ng * kBlkStride]
+    const ChunkDesc *__restrict__ chunks;   // [nchunks], stage after stage
+    const int *__restrict__ stage_chunk;    // [nstages+1]
+};
+
+enum { V2_FWD_ZERO = 0, V2_FWD_FULL = 1, V2_BWD = 2, V2_RESID = 3, V2_SPMV = 4 };
+
+// fixed offsets inside a shared-memory buffer
+constexpr int kOffDesc = 0;                                   // 48 B (+16 pad)
+constexpr int kOffMeta = 64;                                  // 16 * 32 B
+constexpr int kOffBlk = kOffMeta + kChunkGroups * 32;         // 16 * 80 B
+constexpr int kOffData = kOffBlk + kChunkGroups * kBlkStride * 8;
+
+__host__ __device__ inline size_t v2_chunk_bytes(int mode, int ncl, int nvl, int ncu, int nvu)
+{
+    size_t b = kOffData;
+    const bool lo = (mode != V2_BWD), up = (mode == V2_FWD_FULL || mode == V2_BWD || mode == V2_SPMV);
+    if (lo) b += (size_t)ncl * 4 + (size_t)nvl * 16;
+    if (up) b += (size_t)ncu * 4 + (size_t)nvu * 16;
+    return b;
+}
+
+// ---- mbarrier / bulk-copy PTX ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// issue all bulk copies of one chunk (one thread)
+template <int MODE>
+__device__ __forceinline__ void v2_issue_chunk(const Lvl2View &A, int c, const ChunkDesc &d, unsigned char *buf, uint64_t *bar)
+{
+    constexpr bool LO = (MODE != V2_BWD);
+    constexpr bool UP = (MODE == V2_FWD_FULL || MODE == V2_BWD || MODE == V2_SPMV);
+    uint32_t bytes = 48 + (uint32_t)d.ng * 32 + (uint32_t)d.ng * kBlkStride * 8;
+    if (LO) bytes += (uint32_t)d.ncl * 4 + (uint32_t)d.nvl * 16;
+    if (UP) bytes += (uint32_t)d.ncu * 4 + (uint32_t)d.nvu * 16;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(buf + kOffDesc, A.chunks + c, 48, bar);
+    bulk_g2s(buf + kOffMeta, A.meta + d.g0, (uint32_t)d.ng * 32, bar);
+    bulk_g2s(buf + kOffBlk, A.BD + (size_t)d.g0 * kBlkStride, (uint32_t)d.ng * kBlkStride * 8, bar);
+    unsigned char *p = buf + kOffData;
+    if (LO) {
+        if (d.ncl) {
+            bulk_g2s(p, A.CL + d.cl0, (uint32_t)d.ncl * 4, bar);
+            bulk_g2s(p + (size_t)d.ncl * 4, A.VL + (size_t)d.vl0 * 2, (uint32_t)d.nvl * 16, bar);
+        }
+        p += (size_t)d.ncl * 4 + (size_t)d.nvl * 16;
+    }
+    if (UP) {
+        if (d.ncu) {
+            bulk_g2s(p, A.CU + d.cu0, (uint32_t)d.ncu * 4, bar);
+            bulk_g2s(p + (size_t)d.ncu * 4, A.VU + (size_t)d.vu0 * 2, (uint32_t)d.nvu * 16, bar);
+        }
+    }
+}
+
+// sum_k a_r[k] * x[c_k] for the gs rows of one group; pattern and values in shared memory
+__device__ __forceinline__ void v2_half(const int *__restrict__ pc, const double *__restrict__ pv, int n, int gs,
+                                        const double *x, int sl, double (&s)[3])
+{
+#pragma unroll 2
+    for (int k = 2 * sl; k < n; k += 2 * GL) {
+        const int2 c = *reinterpret_cast<const int2 *>(pc + k);
+        const double x0 = __ldcg(x + c.x), x1 = __ldcg(x + c.y);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            if (r < gs) {
+                const double2 a = *reinterpret_cast<const double2 *>(pv + (size_t)r * n + k);
+                s[r] += a.x * x0 + a.y * x1;
+            }
+    }
+}
+
+// One sweep (all stages s0..s1-1, descending for V2_BWD) or one stage-less pass (RESID, SPMV) over a level.
+//   FWD_*: b = right-hand side, x in/out, p1 out          (MGPIS.h:66-72)
+//   BWD  : p1 in, x in/out                                 (MGPIS.h:73-76)
+//   RESID: y = b - (p1 + L x)                              (MGPIS.h:92)
+//   SPMV : y = A x ; if w: partial[blockIdx] = sum w_i y_i (MGPIS.h:200-201)
+// Launched cooperatively when s1 - s0 > 1 (grid.sync between stages).
+template <int MODE>
+__global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, int s0, int s1, size_t buf_bytes, const double *__restrict__ b,
+                                                            double *x, double *p1, double *y, const double *__restrict__ w,
+                                                            double *partial, const int *done)
+{
+    if (done && *done) return;   // uniform across the grid: no CTA reaches a barrier
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[2];
+    constexpr bool LO = (MODE != V2_BWD);
+    constexpr bool UP = (MODE == V2_FWD_FULL || MODE == V2_BWD || MODE == V2_SPMV);
+    constexpr bool STAGED = (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD);
+    const int tid = threadIdx.x, sl = tid % GL, sw = tid / GL;
+    const unsigned mask = subwarp_mask();
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // this CTA's chunk sequence: stage after stage, chunks c = first(stage) + blockIdx.x + j * gridDim.x
+    const int nst = STAGED ? (s1 - s0) : 1;
+    auto stage_of = [&](int si) { return STAGED ? (MODE == V2_BWD ? (s1 - 1 - si) : (s0 + si)) : 0; };
+    auto c_begin = [&](int si) { return STAGED ? A.stage_chunk[stage_of(si)] : 0; };
+    auto c_end = [&](int si) { return STAGED ? A.stage_chunk[stage_of(si) + 1] : A.nchunks; };
+    // advance (si, c) to this CTA's next chunk at or after c; returns false when exhausted
+    auto settle = [&](int &si, int &c) {
+        while (si < nst) {
+            if (c < c_end(si)) return true;
+            si++;
+            if (si < nst) c = c_begin(si) + (int)blockIdx.x;
+        }
+        return false;
+    };
+
+    int si_cur = 0, c_cur = c_begin(0) + (int)blockIdx.x;
+    bool have_cur = settle(si_cur, c_cur);
+    int si_nxt = si_cur, c_nxt = c_cur + (int)gridDim.x;
+    bool have_nxt = have_cur && settle(si_nxt, c_nxt);
+    ChunkDesc d_nxt;   // descriptor of the next chunk, fetched one iteration early by thread 0
+    if (tid == 0) {
+        if (have_cur) {
+            const ChunkDesc d0 = A.chunks[c_cur];
+            v2_issue_chunk<MODE>(A, c_cur, d0, smem, &bars[0]);
+        }
+        if (have_nxt) d_nxt = A.chunks[c_nxt];
+    }
+    cg::grid_group grid = cg::this_grid();
+    double acc = 0.0;
+    int it = 0, si_done = 0;   // si_done: number of stage boundaries this CTA has passed
+    while (true) {
+        // stage barriers up to the stage of the current chunk (or all remaining ones at the end)
+        const int si_target = have_cur ? si_cur : nst - 1;
+        if (STAGED) {
+            while (si_done < si_target) { grid.sync(); si_done++; }
+        }
+        if (!have_cur) break;
+        const int bi = it & 1;
+        // start the next chunk's copies into the other buffer (freed by the __syncthreads below)
+        if (tid == 0 && have_nxt) {
+            fence_proxy_async();
+            v2_issue_chunk<MODE>(A, c_nxt, d_nxt, smem + (size_t)(bi ^ 1) * buf_bytes, &bars[bi ^ 1]);
+        }
+        // and fetch the descriptor of the one after
+        int si_n2 = si_nxt, c_n2 = c_nxt + (int)gridDim.x;
+        const bool have_n2 = have_nxt && settle(si_n2, c_n2);
+        if (tid == 0 && have_n2) d_nxt = A.chunks[c_n2];
+
+        mbar_wait(&bars[bi], (uint32_t)((it >> 1) & 1));
+        const unsigned char *buf = smem + (size_t)bi * buf_bytes;
+        const ChunkDesc &d = *reinterpret_cast<const ChunkDesc *>(buf + kOffDesc);
+        if (sw < d.ng) {
+            const GroupMeta2 m = *reinterpret_cast<const GroupMeta2 *>(buf + kOffMeta + sw * 32);
+            const double *blk = reinterpret_cast<const double *>(buf + kOffBlk) + sw * kBlkStride;
+            const unsigned char *pdat = buf + kOffData;
+            const int *cL = nullptr, *cU = nullptr;
+            const double *vL = nullptr, *vU = nullptr;
+            if (LO) {
+                cL = reinterpret_cast<const int *>(pdat) + (m.cl - d.cl0);
+                vL = reinterpret_cast<const double *>(pdat + (size_t)d.ncl * 4) + (size_t)(m.vl - d.vl0) * 2;
+                pdat += (size_t)d.ncl * 4 + (size_t)d.nvl * 16;
+            }
+            if (UP) {
+                cU = reinterpret_cast<const int *>(pdat) + (m.cu - d.cu0);
+                vU = reinterpret_cast<const double *>(pdat + (size_t)d.ncu * 4) + (size_t)(m.vu - d.vu0) * 2;
+            }
+            const int gs = m.gs, r0 = m.row0;
+            double sL[3] = {0.0, 0.0, 0.0}, sU[3] = {0.0, 0.0, 0.0};
+            // right-hand sides and old iterate of the own rows: issued before the gathers they overlap with
+            double rhs[3] = {0.0, 0.0, 0.0}, xo[3] = {0.0, 0.0, 0.0};
+            if (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD) {
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+                    if (r < gs) {
+                        rhs[r] = (MODE == V2_BWD) ? p1[r0 + r] : b[r0 + r];
+                        if (MODE == V2_FWD_FULL) xo[r] = __ldcg(x + r0 + r);
+                    }
+            }
+            if (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_RESID || MODE == V2_SPMV) v2_half(cL, vL, m.nl, gs, x, sl, sL);
+            if (MODE == V2_FWD_FULL || MODE == V2_BWD || MODE == V2_SPMV) v2_half(cU, vU, m.nu, gs, x, sl, sU);
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                if (LO) sL[r] = group_sum(sL[r], mask);
+                if (UP) sU[r] = group_sum(sU[r], mask);
+            }
+            if (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL) {
+                double xn[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    if (r < gs) {
+                        double inL = 0.0, inU = 0.0;
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            if (c < r) inL += blk[r * 3 + c] * xn[c];
+                            if (c > r) inU += blk[r * 3 + c] * xo[c];
+                        }
+                        const double up = sU[r] + inU, dg = blk[r * 3 + r];
+                        xn[r] = (rhs[r] - sL[r] - inL - up) / dg;
+                        if (sl == 0) {
+                            x[r0 + r] = xn[r];
+                            p1[r0 + r] = dg * xn[r] + up;
+                        }
+                    }
+                }
+            } else if (MODE == V2_BWD) {
+                double xn[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                for (int r = 2; r >= 0; r--) {
+                    if (r < gs) {
+                        double inU = 0.0;
+#pragma unroll
+                        for (int c = 0; c < 3; c++)
+                            if (c > r) inU += blk[r * 3 + c] * xn[c];
+                        xn[r] = (rhs[r] - sU[r] - inU) / blk[r * 3 + r];
+                        if (sl == 0) x[r0 + r] = xn[r];
+                    }
+                }
+            } else {
+                // RESID / SPMV: one lane per row finishes with the in-group block
+                if (sl < gs) {
+                    const int i = r0 + sl;
+                    double s = sl == 0 ? sL[0] : (sl == 1 ? sL[1] : sL[2]);
+                    if (MODE == V2_RESID) {
+                        for (int c = 0; c < sl; c++) s += blk[sl * 3 + c] * __ldcg(x + r0 + c);
+                        y[i] = b[i] - (p1[i] + s);
+                    } else {
+                        s += sl == 0 ? sU[0] : (sl == 1 ? sU[1] : sU[2]);
+                        for (int c = 0; c < gs; c++) s += blk[sl * 3 + c] * __ldcg(x + r0 + c);
+                        y[i] = s;
+                        if (w) acc += w[i] * s;
+                    }
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with bufs[bi]; it may be refilled in the next iteration
+        it++;
+        si_cur = si_nxt; c_cur = c_nxt; have_cur = have_nxt;
+        si_nxt = si_n2; c_nxt = c_n2; have_nxt = have_n2;
+    }
+    if (MODE == V2_SPMV && partial) block_sum_to_partial(acc, partial);
+}
+
+__global__ void k_extract_diag_inv2(Lvl2View A, double *__restrict__ dinv)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= A.ng) return;
+    const GroupMeta2 m = A.meta[g];
+    for (int r = 0; r < m.gs; r++) dinv[m.row0 + r] = 1.0 / A.BD[(size_t)g * kBlkStride + r * 3 + r];
+}
+
+}  // namespace ddpca

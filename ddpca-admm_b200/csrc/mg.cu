@@ -16,12 +16,14 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/ddpca_b200.h"
 #include "kernels.cuh"
+#include "kernels2.cuh"
 #include "plan.h"
 
 using namespace ddpca;
@@ -75,6 +77,15 @@ struct Level {
     double *x = nullptr, *b = nullptr, *p1 = nullptr, *r = nullptr, *dinv = nullptr;
     double bytes_lower = 0, bytes_upper = 0, bytes_full = 0;  // algorithmic bytes of one pass over a half / the whole level
     LvlView view() const { return LvlView{n, ng, meta, gci, gv}; }
+    // v2: split lower/upper storage + chunk table (kernels2.cuh); used when every stage is large
+    bool v2 = false;
+    GroupMeta2 *meta2 = nullptr;
+    int *CL = nullptr, *CU = nullptr, *stage_chunk = nullptr;
+    double *VL = nullptr, *VU = nullptr, *BD = nullptr;
+    ChunkDesc *chunks = nullptr;
+    int nchunks = 0, max_stage_chunks = 0;
+    size_t buf_lo = 0, buf_up = 0, buf_full = 0;   // shared-memory bytes of one chunk buffer per pass type
+    Lvl2View view2() const { return Lvl2View{n, ng, nchunks, plan.nstages(), meta2, CL, VL, CU, VU, BD, chunks, stage_chunk}; }
 };
 
 struct ProfRec {
@@ -226,9 +237,49 @@ static void launch_spmv(Engine *h, int kclass, int lvl, const DevCsr &A, const d
     else SPMV_CASE(4);
 #undef SPMV_CASE
 }
+// ---- v2 launches (kernels2.cuh) ------------------------------------------------------------------
+template <int MODE>
+static int v2_blocks_per_sm(size_t dyn)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_level_pass<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_level_pass<MODE>, kV2Threads, dyn);
+    return std::max(nb, 1);
+}
+// returns the grid used (number of partial sums for SPMV with a dot)
+template <int MODE>
+static int launch_v2(Engine *h, Level &L, int kclass, int l, double bytes, const double *b, double *x, double *p1, double *y,
+                     const double *w, double *partial, const int *done)
+{
+    const bool staged = (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD);
+    size_t buf = (MODE == V2_FWD_ZERO || MODE == V2_RESID) ? L.buf_lo : (MODE == V2_BWD ? L.buf_up : L.buf_full);
+    size_t dyn = 2 * buf;
+    int per_sm = v2_blocks_per_sm<MODE>(dyn);
+    int cap = per_sm * h->sms;
+    int grid = std::min(staged ? L.max_stage_chunks : L.nchunks, cap);
+    if (MODE == V2_SPMV && w) grid = std::min(grid, kNumPart);
+    grid = std::max(grid, 1);
+    Lvl2View A = L.view2();
+    int s0 = 0, s1 = L.plan.nstages();
+    h->pre(kclass, l, bytes);
+    if (staged && s1 - s0 > 1) {
+        void *args[] = {(void *)&A, (void *)&s0, (void *)&s1, (void *)&buf, (void *)&b, (void *)&x, (void *)&p1, (void *)&y, (void *)&w, (void *)&partial, (void *)&done};
+        cudaLaunchCooperativeKernel((const void *)k_level_pass<MODE>, dim3(grid), dim3(kV2Threads), args, dyn, h->stream);
+    } else {
+        k_level_pass<MODE><<<grid, kV2Threads, dyn, h->stream>>>(A, s0, s1, buf, b, x, p1, y, w, partial, done);
+    }
+    h->post();
+    return grid;
+}
+
 // y = consStif[l] x on the group layout; returns the grid (= number of partial sums when dotw)
 static int launch_level_spmv(Engine *h, Level &L, int l, const double *x, double *y, const double *dotw, double *partial, const int *done)
 {
+    if (L.v2) return launch_v2<V2_SPMV>(h, L, DDPCA_K_SPMV, l, L.bytes_full + (dotw ? 8.0 * L.n : 0.0), nullptr, const_cast<double *>(x), nullptr, y, dotw, partial, done);
     long need = cdiv((long)L.ng * GL, 256);
     int grid = (int)std::max<long>(1, std::min<long>(need, dotw ? kNumPart : (long)h->sms * 32));
     double bytes = L.bytes_full + (dotw ? 8.0 * L.n : 0.0);
@@ -239,6 +290,11 @@ static int launch_level_spmv(Engine *h, Level &L, int l, const double *x, double
 
 static void sweep_fwd(Engine *h, Level &L, int l, const double *b, double *x, bool zero_x, const int *done)
 {
+    if (L.v2) {
+        if (zero_x) launch_v2<V2_FWD_ZERO>(h, L, DDPCA_K_SWEEP_FWD, l, L.bytes_lower, b, x, L.p1, nullptr, nullptr, nullptr, done);
+        else launch_v2<V2_FWD_FULL>(h, L, DDPCA_K_SWEEP_FWD, l, L.bytes_lower + L.bytes_upper, b, x, L.p1, nullptr, nullptr, nullptr, done);
+        return;
+    }
     for (const Segment &s : L.segs) {
         double bytes = s.bytes_lo + (zero_x ? 0.0 : s.bytes_up);
         if (!s.multi) {
@@ -254,6 +310,10 @@ static void sweep_fwd(Engine *h, Level &L, int l, const double *b, double *x, bo
 }
 static void sweep_bwd(Engine *h, Level &L, int l, double *x, const int *done)
 {
+    if (L.v2) {
+        launch_v2<V2_BWD>(h, L, DDPCA_K_SWEEP_BWD, l, L.bytes_upper, nullptr, x, L.p1, nullptr, nullptr, nullptr, done);
+        return;
+    }
     for (int k = (int)L.segs.size() - 1; k >= 0; k--) {
         const Segment &s = L.segs[k];
         if (!s.multi) {
@@ -278,7 +338,8 @@ static void vcycle_dev(ddpca_mg *h, int l, const double *b, double *x, bool zero
     Level &C = h->lev[l - 1];
     sweep_fwd(h, L, l, b, x, zero_x, done);  // :65-72
     sweep_bwd(h, L, l, x, done);             // :73-76
-    KL(h, DDPCA_K_RESID, l, L.bytes_lower + 8.0 * L.n, (k_resid_lower<<<cdiv((long)L.ng * GL, 256), 256, 0, h->stream>>>(L.view(), b, L.p1, x, L.r, done)));
+    if (L.v2) launch_v2<V2_RESID>(h, L, DDPCA_K_RESID, l, L.bytes_lower + 8.0 * L.n, b, x, L.p1, L.r, nullptr, nullptr, done);
+    else KL(h, DDPCA_K_RESID, l, L.bytes_lower + 8.0 * L.n, (k_resid_lower<<<cdiv((long)L.ng * GL, 256), 256, 0, h->stream>>>(L.view(), b, L.p1, x, L.r, done)));
     launch_spmv(h, DDPCA_K_RESTRICT, l, L.R, L.r, C.b, false, nullptr, nullptr, done);  // :96
     vcycle_dev(h, l - 1, C.b, C.x, true, done);                                          // :93-99
     launch_spmv(h, DDPCA_K_PROLONG, l, L.P, C.x, x, true, nullptr, nullptr, done);       // :100
@@ -352,7 +413,8 @@ static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref,
     const int *done = &h->st->done;
     if (prec == 0 && !L.dinv) {
         CU(cudaMalloc(&L.dinv, sizeof(double) * n));
-        k_extract_diag_inv<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
+        if (L.v2) k_extract_diag_inv2<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view2(), L.dinv);
+        else k_extract_diag_inv<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
     }
     if (!h->profile) {
         if (build_iter_graph(h, prec)) return 1;
@@ -453,6 +515,86 @@ static bool build_group_layout(const CsrHost &Ap, const LevelPlan &pl, GroupLayo
     return true;
 }
 
+// ---- v2 layout (kernels2.cuh): split lower / upper arrays in stage order + chunk table -----------
+struct Layout2Host {
+    std::vector<GroupMeta2> meta;
+    std::vector<int> CL, CU, stage_chunk;
+    std::vector<double> VL, VU, BD;
+    std::vector<ChunkDesc> chunks;
+    size_t buf_lo = 0, buf_up = 0, buf_full = 0;
+    int max_stage_chunks = 0;
+};
+static inline int round4(int v) { return (v + 3) & ~3; }
+
+static bool build_layout2(const CsrHost &Ap, const LevelPlan &pl, Layout2Host &out, std::string &err)
+{
+    const int ng = pl.ngroups();
+    out.meta.resize(ng);
+    long cl = 0, cu = 0, vl = 0, vu = 0;   // ints / 16-byte units
+    for (int g = 0; g < ng; g++) {
+        int r0 = pl.group_start[g], gs = pl.group_start[g + 1] - r0;
+        int len = Ap.rp[r0 + 1] - Ap.rp[r0];
+        const int *c0 = Ap.ci.data() + Ap.rp[r0];
+        int kd = (int)(std::lower_bound(c0, c0 + len, r0) - c0);
+        if (kd + gs > len || c0[kd] != r0 || c0[kd + gs - 1] != r0 + gs - 1) { err = "group " + std::to_string(g) + ": in-group block incomplete"; return false; }
+        GroupMeta2 m;
+        m.row0 = r0; m.gs = gs;
+        m.nl = round4(kd); m.nu = round4(len - kd - gs);
+        m.cl = (int)cl; m.cu = (int)cu; m.vl = (int)vl; m.vu = (int)vu;
+        out.meta[g] = m;
+        cl += m.nl; cu += m.nu;
+        vl += (long)gs * m.nl / 2; vu += (long)gs * m.nu / 2;
+        if (cl > 0x7ffffff0L || cu > 0x7ffffff0L || vl > 0x7ffffff0L || vu > 0x7ffffff0L) { err = "level too large for 32-bit chunk offsets"; return false; }
+    }
+    out.CL.assign(cl, 0); out.CU.assign(cu, 0);
+    out.VL.assign(vl * 2, 0.0); out.VU.assign(vu * 2, 0.0);
+    out.BD.assign((size_t)ng * kBlkStride, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int g = 0; g < ng; g++) {
+        const GroupMeta2 &m = out.meta[g];
+        const int r0 = m.row0, gs = m.gs;
+        const int len = Ap.rp[r0 + 1] - Ap.rp[r0];
+        const int *c0 = Ap.ci.data() + Ap.rp[r0];
+        const int kd = (int)(std::lower_bound(c0, c0 + len, r0) - c0);
+        const int nlr = kd, nur = len - kd - gs;
+        for (int k = 0; k < m.nl; k++) out.CL[m.cl + k] = k < nlr ? c0[k] : r0;            // pads: value 0 on a valid column
+        for (int k = 0; k < m.nu; k++) out.CU[m.cu + k] = k < nur ? c0[kd + gs + k] : r0;
+        for (int r = 0; r < gs; r++) {
+            const double *vr = Ap.v.data() + Ap.rp[r0 + r];
+            double *dl = out.VL.data() + (size_t)m.vl * 2 + (size_t)r * m.nl;
+            double *du = out.VU.data() + (size_t)m.vu * 2 + (size_t)r * m.nu;
+            for (int k = 0; k < nlr; k++) dl[k] = vr[k];
+            for (int k = 0; k < nur; k++) du[k] = vr[kd + gs + k];
+            for (int c = 0; c < gs; c++) out.BD[(size_t)g * kBlkStride + r * 3 + c] = vr[kd + c];
+        }
+    }
+    // chunks: kChunkGroups consecutive groups, never across a stage boundary
+    const int ns = pl.nstages();
+    out.stage_chunk.assign(ns + 1, 0);
+    for (int s = 0; s < ns; s++) {
+        out.stage_chunk[s] = (int)out.chunks.size();
+        for (int g0 = pl.stage_group[s]; g0 < pl.stage_group[s + 1]; g0 += kChunkGroups) {
+            int g1 = std::min(g0 + kChunkGroups, pl.stage_group[s + 1]);
+            ChunkDesc d{};
+            d.g0 = g0; d.ng = g1 - g0;
+            const GroupMeta2 &a = out.meta[g0], &z = out.meta[g1 - 1];
+            d.cl0 = a.cl; d.ncl = z.cl + z.nl - a.cl;
+            d.cu0 = a.cu; d.ncu = z.cu + z.nu - a.cu;
+            d.vl0 = a.vl; d.nvl = z.vl + z.gs * z.nl / 2 - a.vl;
+            d.vu0 = a.vu; d.nvu = z.vu + z.gs * z.nu / 2 - a.vu;
+            out.chunks.push_back(d);
+            out.buf_lo = std::max(out.buf_lo, v2_chunk_bytes(V2_FWD_ZERO, d.ncl, d.nvl, d.ncu, d.nvu));
+            out.buf_up = std::max(out.buf_up, v2_chunk_bytes(V2_BWD, d.ncl, d.nvl, d.ncu, d.nvu));
+            out.buf_full = std::max(out.buf_full, v2_chunk_bytes(V2_FWD_FULL, d.ncl, d.nvl, d.ncu, d.nvu));
+        }
+        out.max_stage_chunks = std::max(out.max_stage_chunks, (int)out.chunks.size() - out.stage_chunk[s]);
+    }
+    out.stage_chunk[ns] = (int)out.chunks.size();
+    auto r128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
+    out.buf_lo = r128(out.buf_lo); out.buf_up = r128(out.buf_up); out.buf_full = r128(out.buf_full);
+    return true;
+}
+
 static int build_segments(Level &L, const GroupLayoutHost &G)
 {
     const LevelPlan &pl = L.plan;
@@ -504,6 +646,15 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
         GroupLayoutHost G;
         if (!build_group_layout(Ap, L.plan, G, err)) return fail(err);
         if (mode >= 0) build_segments(L, G);
+        // v2 (kernels2.cuh) when every stage is large enough to be worth a grid-wide pass
+        bool want_v2 = mode >= 0 && !L.segs.empty() && !std::getenv("DDPCA_NO_V2");
+        for (const Segment &sg : L.segs) if (sg.multi) want_v2 = false;
+        Layout2Host H2;
+        if (want_v2) {
+            if (!build_layout2(Ap, L.plan, H2, err)) return fail(err);
+            if (2 * H2.buf_full > 200 * 1024) want_v2 = false;   // two chunk buffers must fit in shared memory
+        }
+        L.v2 = want_v2;
         L.ng = (int)G.meta.size();
         L.pat_entries = (long)G.ci.size();
         L.val_entries = (long)G.v.size();
@@ -513,7 +664,15 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
             L.bytes_upper += (8.0 * m.gs + 4.0) * (m.pad - m.kd - m.gs) + common;
             L.bytes_full += (8.0 * m.gs + 4.0) * m.pad + 32.0 + 16.0 * m.gs;   // + x once, y once
         }
-        if (upload_vec(G.meta, &L.meta) || upload_vec(G.ci, &L.gci) || upload_vec(G.v, &L.gv)) return 1;
+        if (L.v2) {
+            L.nchunks = (int)H2.chunks.size();
+            L.max_stage_chunks = H2.max_stage_chunks;
+            L.buf_lo = H2.buf_lo; L.buf_up = H2.buf_up; L.buf_full = H2.buf_full;
+            if (upload_vec(H2.meta, &L.meta2) || upload_vec(H2.CL, &L.CL) || upload_vec(H2.CU, &L.CU) || upload_vec(H2.VL, &L.VL) ||
+                upload_vec(H2.VU, &L.VU) || upload_vec(H2.BD, &L.BD) || upload_vec(H2.chunks, &L.chunks) || upload_vec(H2.stage_chunk, &L.stage_chunk)) return 1;
+        } else {
+            if (upload_vec(G.meta, &L.meta) || upload_vec(G.ci, &L.gci) || upload_vec(G.v, &L.gv)) return 1;
+        }
     }
     if (upload_vec(L.plan.stage_group, &L.stage_group) || upload_vec(L.plan.perm, &L.perm)) return 1;
     CU(cudaMalloc(&L.x, sizeof(double) * std::max(1, n)));
@@ -527,6 +686,8 @@ static void free_level(Level &L)
     free_csr(L.A); free_csr(L.P); free_csr(L.R);
     cudaFree(L.meta); cudaFree(L.gci); cudaFree(L.gv); cudaFree(L.stage_group); cudaFree(L.perm);
     cudaFree(L.x); cudaFree(L.b); cudaFree(L.p1); cudaFree(L.r); cudaFree(L.dinv);
+    cudaFree(L.meta2); cudaFree(L.CL); cudaFree(L.CU); cudaFree(L.stage_chunk); cudaFree(L.VL); cudaFree(L.VU); cudaFree(L.BD); cudaFree(L.chunks);
+    L.meta2 = nullptr; L.CL = L.CU = L.stage_chunk = nullptr; L.VL = L.VU = L.BD = nullptr; L.chunks = nullptr;
     L.meta = nullptr; L.gci = nullptr; L.gv = nullptr; L.stage_group = nullptr; L.perm = nullptr;
     L.x = L.b = L.p1 = L.r = L.dinv = nullptr;
 }
@@ -951,7 +1112,8 @@ int ddpca_mg_bicgstab(ddpca_mg *h, int prec, const double *b, double *x, double 
     int n = L.n;
     if (prec == 0 && !L.dinv) {
         CU(cudaMalloc(&L.dinv, sizeof(double) * n));
-        k_extract_diag_inv<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
+        if (L.v2) k_extract_diag_inv2<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view2(), L.dinv);
+        else k_extract_diag_inv<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
     }
     // work vectors: r, rhat, p, v, s, t, phat, shat, x
     std::vector<double *> w(6, nullptr);
