@@ -1011,7 +1011,7 @@ int ddpca_mg_spmv(ddpca_mg *h, int level, const double *x, double *y)
     if (!h || level < 0 || level >= h->nlev || !x || !y) return fail("ddpca_mg_spmv: bad argument");
     CU(cudaSetDevice(h->device));
     if (to_dev(h, level, x, h->cg_p)) return 1;
-    if (h->lev[level].meta) launch_level_spmv(h, h->lev[level], level, h->cg_p, h->cg_q, nullptr, nullptr, nullptr);
+    if (h->lev[level].meta || h->lev[level].v2) launch_level_spmv(h, h->lev[level], level, h->cg_p, h->cg_q, nullptr, nullptr, nullptr);
     else launch_spmv(h, DDPCA_K_SPMV, level, h->lev[level].A, h->cg_p, h->cg_q, false, nullptr, nullptr, nullptr);
     if (h->profile) h->prof_collect();
     return to_host(h, level, h->cg_q, y);
