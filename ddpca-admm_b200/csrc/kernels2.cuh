@@ -23,8 +23,16 @@ namespace ddpca {
 
 namespace cg = cooperative_groups;
 
-constexpr int kChunkGroups = 16;   // row groups per chunk = sub-warps per CTA
-constexpr int kV2Threads = kChunkGroups * GL;
+#ifndef DDPCA_V2_GROUPS
+#define DDPCA_V2_GROUPS 8
+#endif
+#ifndef DDPCA_V2_BUFS
+#define DDPCA_V2_BUFS 3
+#endif
+constexpr int kChunkGroups = DDPCA_V2_GROUPS;        // row groups per chunk = consumer sub-warps per CTA
+constexpr int kV2Bufs = DDPCA_V2_BUFS;               // depth of the shared-memory ring
+constexpr int kV2Consumers = kChunkGroups * GL;      // consumer threads
+constexpr int kV2Threads = kV2Consumers + 32;        // + one producer warp (one lane issues the bulk copies)
 static_assert(GL == 8, "v2 kernels assume 8-lane sub-warps");
 
 // 32-byte group descriptor of the split layout
@@ -61,8 +69,8 @@ enum { V2_FWD_ZERO = 0, V2_FWD_FULL = 1, V2_BWD = 2, V2_RESID = 3, V2_SPMV = 4 }
 
 // fixed offsets inside a shared-memory buffer
 constexpr int kOffDesc = 0;                                   // 48 B (+16 pad)
-constexpr int kOffMeta = 64;                                  // 16 * 32 B
-constexpr int kOffBlk = kOffMeta + kChunkGroups * 32;         // 16 * 80 B
+constexpr int kOffMeta = 64;                                  // kChunkGroups * 32 B
+constexpr int kOffBlk = kOffMeta + kChunkGroups * 32;         // kChunkGroups * 80 B
 constexpr int kOffData = kOffBlk + kChunkGroups * kBlkStride * 8;
 
 __host__ __device__ inline size_t v2_chunk_bytes(int mode, int ncl, int nvl, int ncu, int nvu)
@@ -102,6 +110,35 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier among the consumer threads only (the producer warp never joins)
+__device__ __forceinline__ void consumer_bar_sync()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(kV2Consumers) : "memory");
+}
+// Grid-wide barrier among the consumer threads of all CTAs of a cooperative launch (all CTAs are
+// co-resident).  Self-resetting: gbar[0] = arrival count, gbar[1] = generation.
+__device__ __forceinline__ void consumer_grid_barrier(unsigned *gbar)
+{
+    consumer_bar_sync();
+    if (threadIdx.x == 0) {
+        volatile unsigned *vg = gbar;
+        const unsigned gen = vg[1];
+        __threadfence();
+        if (atomicAdd(&gbar[0], 1u) == gridDim.x - 1) {
+            vg[0] = 0;
+            __threadfence();
+            atomicAdd(&gbar[1], 1u);
+        } else {
+            while (vg[1] == gen) { __nanosleep(20); }
+        }
+        __threadfence();
+    }
+    consumer_bar_sync();
+}
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -136,12 +173,47 @@ __device__ __forceinline__ void v2_issue_chunk(const Lvl2View &A, int c, const C
     }
 }
 
-// sum_k a_r[k] * x[c_k] for the gs rows of one group; pattern and values in shared memory
-__device__ __forceinline__ void v2_half(const int *__restrict__ pc, const double *__restrict__ pv, int n, int gs,
+// Two-phase evaluation of one half of a row group from shared memory:
+//   phase 1 (v2_gather): every x gather of the half is issued back to back into registers
+//           (kV2Iters steps of 2*GL pattern positions cover 64 entries; hexahedral meshes have
+//           at most 40 lower / 40 upper couplings per node) -- ONE exposed L2 latency per group;
+//   phase 2 (v2_fma):    values stream from shared memory into the row sums.
+// Longer halves continue in a generic loop (v2_tail).
+constexpr int kV2Iters = 4;
+
+__device__ __forceinline__ void v2_gather(const int *__restrict__ pc, int n, const double *x, int sl, double (&xs)[2 * kV2Iters])
+{
+#pragma unroll
+    for (int it = 0; it < kV2Iters; it++) {
+        const int k = 2 * sl + it * 2 * GL;
+        xs[2 * it] = 0.0;
+        xs[2 * it + 1] = 0.0;
+        if (k < n) {
+            const int2 c = *reinterpret_cast<const int2 *>(pc + k);
+            xs[2 * it] = __ldcg(x + c.x);
+            xs[2 * it + 1] = __ldcg(x + c.y);
+        }
+    }
+}
+__device__ __forceinline__ void v2_fma(const double *__restrict__ pv, int n, int gs, int sl, const double (&xs)[2 * kV2Iters], double (&s)[3])
+{
+#pragma unroll
+    for (int it = 0; it < kV2Iters; it++) {
+        const int k = 2 * sl + it * 2 * GL;
+        if (k < n) {
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                if (r < gs) {
+                    const double2 a = *reinterpret_cast<const double2 *>(pv + (size_t)r * n + k);
+                    s[r] += a.x * xs[2 * it] + a.y * xs[2 * it + 1];
+                }
+        }
+    }
+}
+__device__ __forceinline__ void v2_tail(const int *__restrict__ pc, const double *__restrict__ pv, int n, int gs,
                                         const double *x, int sl, double (&s)[3])
 {
-#pragma unroll 2
-    for (int k = 2 * sl; k < n; k += 2 * GL) {
+    for (int k = 2 * sl + kV2Iters * 2 * GL; k < n; k += 2 * GL) {
         const int2 c = *reinterpret_cast<const int2 *>(pc + k);
         const double x0 = __ldcg(x + c.x), x1 = __ldcg(x + c.y);
 #pragma unroll
@@ -153,39 +225,42 @@ __device__ __forceinline__ void v2_half(const int *__restrict__ pc, const double
     }
 }
 
-// One sweep (all stages s0..s1-1, descending for V2_BWD) or one stage-less pass (RESID, SPMV) over a level.
+// One sweep (all stages, descending for V2_BWD) or one stage-less pass (RESID, SPMV) over a level.
 //   FWD_*: b = right-hand side, x in/out, p1 out          (MGPIS.h:66-72)
 //   BWD  : p1 in, x in/out                                 (MGPIS.h:73-76)
 //   RESID: y = b - (p1 + L x)                              (MGPIS.h:92)
 //   SPMV : y = A x ; if w: partial[blockIdx] = sum w_i y_i (MGPIS.h:200-201)
-// Launched cooperatively when s1 - s0 > 1 (grid.sync between stages).
+// Warp-specialised: one producer lane walks the CTA's chunk sequence kV2Bufs chunks ahead of the
+// consumers (full / empty mbarriers per ring slot) and keeps crossing stage boundaries -- operator
+// data does not depend on x --, the consumer warps meet the other CTAs at a grid barrier between
+// stages.  Staged modes must be launched cooperatively (co-residency of all CTAs).
 template <int MODE>
-__global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, int s0, int s1, size_t buf_bytes, const double *__restrict__ b,
+__global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, size_t buf_bytes, unsigned *gbar, const double *__restrict__ b,
                                                             double *x, double *p1, double *y, const double *__restrict__ w,
                                                             double *partial, const int *done)
 {
     if (done && *done) return;   // uniform across the grid: no CTA reaches a barrier
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bars[2];
+    __shared__ uint64_t full[kV2Bufs], empty[kV2Bufs];
     constexpr bool LO = (MODE != V2_BWD);
     constexpr bool UP = (MODE == V2_FWD_FULL || MODE == V2_BWD || MODE == V2_SPMV);
     constexpr bool STAGED = (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD);
-    const int tid = threadIdx.x, sl = tid % GL, sw = tid / GL;
-    const unsigned mask = subwarp_mask();
+    const int tid = threadIdx.x;
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int i = 0; i < kV2Bufs; i++) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kV2Consumers / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     // this CTA's chunk sequence: stage after stage, chunks c = first(stage) + blockIdx.x + j * gridDim.x
-    const int nst = STAGED ? (s1 - s0) : 1;
-    auto stage_of = [&](int si) { return STAGED ? (MODE == V2_BWD ? (s1 - 1 - si) : (s0 + si)) : 0; };
+    const int nst = STAGED ? A.nstages : 1;
+    auto stage_of = [&](int si) { return STAGED ? (MODE == V2_BWD ? (nst - 1 - si) : si) : 0; };
     auto c_begin = [&](int si) { return STAGED ? A.stage_chunk[stage_of(si)] : 0; };
     auto c_end = [&](int si) { return STAGED ? A.stage_chunk[stage_of(si) + 1] : A.nchunks; };
-    // advance (si, c) to this CTA's next chunk at or after c; returns false when exhausted
-    auto settle = [&](int &si, int &c) {
+    auto settle = [&](int &si, int &c) {   // advance (si, c) to this CTA's next chunk at or after c
         while (si < nst) {
             if (c < c_end(si)) return true;
             si++;
@@ -193,132 +268,131 @@ __global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, int s0, i
         }
         return false;
     };
-
-    int si_cur = 0, c_cur = c_begin(0) + (int)blockIdx.x;
-    bool have_cur = settle(si_cur, c_cur);
-    int si_nxt = si_cur, c_nxt = c_cur + (int)gridDim.x;
-    bool have_nxt = have_cur && settle(si_nxt, c_nxt);
-    ChunkDesc d_nxt;   // descriptor of the next chunk, fetched one iteration early by thread 0
-    if (tid == 0) {
-        if (have_cur) {
-            const ChunkDesc d0 = A.chunks[c_cur];
-            v2_issue_chunk<MODE>(A, c_cur, d0, smem, &bars[0]);
-        }
-        if (have_nxt) d_nxt = A.chunks[c_nxt];
-    }
-    cg::grid_group grid = cg::this_grid();
+    int si = 0, c = c_begin(0) + (int)blockIdx.x;
     double acc = 0.0;
-    int it = 0, si_done = 0;   // si_done: number of stage boundaries this CTA has passed
-    while (true) {
-        // stage barriers up to the stage of the current chunk (or all remaining ones at the end)
-        const int si_target = have_cur ? si_cur : nst - 1;
-        if (STAGED) {
-            while (si_done < si_target) { grid.sync(); si_done++; }
-        }
-        if (!have_cur) break;
-        const int bi = it & 1;
-        // start the next chunk's copies into the other buffer (freed by the __syncthreads below)
-        if (tid == 0 && have_nxt) {
-            fence_proxy_async();
-            v2_issue_chunk<MODE>(A, c_nxt, d_nxt, smem + (size_t)(bi ^ 1) * buf_bytes, &bars[bi ^ 1]);
-        }
-        // and fetch the descriptor of the one after
-        int si_n2 = si_nxt, c_n2 = c_nxt + (int)gridDim.x;
-        const bool have_n2 = have_nxt && settle(si_n2, c_n2);
-        if (tid == 0 && have_n2) d_nxt = A.chunks[c_n2];
 
-        mbar_wait(&bars[bi], (uint32_t)((it >> 1) & 1));
-        const unsigned char *buf = smem + (size_t)bi * buf_bytes;
-        const ChunkDesc &d = *reinterpret_cast<const ChunkDesc *>(buf + kOffDesc);
-        if (sw < d.ng) {
-            const GroupMeta2 m = *reinterpret_cast<const GroupMeta2 *>(buf + kOffMeta + sw * 32);
-            const double *blk = reinterpret_cast<const double *>(buf + kOffBlk) + sw * kBlkStride;
-            const unsigned char *pdat = buf + kOffData;
-            const int *cL = nullptr, *cU = nullptr;
-            const double *vL = nullptr, *vU = nullptr;
-            if (LO) {
-                cL = reinterpret_cast<const int *>(pdat) + (m.cl - d.cl0);
-                vL = reinterpret_cast<const double *>(pdat + (size_t)d.ncl * 4) + (size_t)(m.vl - d.vl0) * 2;
-                pdat += (size_t)d.ncl * 4 + (size_t)d.nvl * 16;
+    if (tid >= kV2Consumers) {
+        // ------------------------------- producer warp ---------------------------------------
+        if (tid == kV2Consumers) {
+            for (int j = 0; settle(si, c); j++, c += (int)gridDim.x) {
+                const int slot = j % kV2Bufs;
+                if (j >= kV2Bufs) mbar_wait(&empty[slot], (uint32_t)(((j / kV2Bufs) - 1) & 1));
+                const ChunkDesc d = A.chunks[c];
+                fence_proxy_async();
+                v2_issue_chunk<MODE>(A, c, d, smem + (size_t)slot * buf_bytes, &full[slot]);
             }
-            if (UP) {
-                cU = reinterpret_cast<const int *>(pdat) + (m.cu - d.cu0);
-                vU = reinterpret_cast<const double *>(pdat + (size_t)d.ncu * 4) + (size_t)(m.vu - d.vu0) * 2;
+        }
+    } else {
+        // ------------------------------- consumer warps --------------------------------------
+        const int sl = tid % GL, sw = tid / GL;
+        const unsigned mask = subwarp_mask();
+        int si_done = 0;   // stage boundaries passed so far
+        for (int j = 0;; j++, c += (int)gridDim.x) {
+            const bool have = settle(si, c);
+            if (STAGED) {
+                const int target = have ? si : nst - 1;
+                while (si_done < target) { consumer_grid_barrier(gbar); si_done++; }
             }
-            const int gs = m.gs, r0 = m.row0;
-            double sL[3] = {0.0, 0.0, 0.0}, sU[3] = {0.0, 0.0, 0.0};
-            // right-hand sides and old iterate of the own rows: issued before the gathers they overlap with
-            double rhs[3] = {0.0, 0.0, 0.0}, xo[3] = {0.0, 0.0, 0.0};
-            if (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD) {
+            if (!have) break;
+            const int slot = j % kV2Bufs;
+            mbar_wait(&full[slot], (uint32_t)((j / kV2Bufs) & 1));
+            const unsigned char *buf = smem + (size_t)slot * buf_bytes;
+            const ChunkDesc &d = *reinterpret_cast<const ChunkDesc *>(buf + kOffDesc);
+            if (sw < d.ng) {
+                const GroupMeta2 m = *reinterpret_cast<const GroupMeta2 *>(buf + kOffMeta + sw * 32);
+                const double *blk = reinterpret_cast<const double *>(buf + kOffBlk) + sw * kBlkStride;
+                const unsigned char *pdat = buf + kOffData;
+                const int *cL = nullptr, *cU = nullptr;
+                const double *vL = nullptr, *vU = nullptr;
+                if (LO) {
+                    cL = reinterpret_cast<const int *>(pdat) + (m.cl - d.cl0);
+                    vL = reinterpret_cast<const double *>(pdat + (size_t)d.ncl * 4) + (size_t)(m.vl - d.vl0) * 2;
+                    pdat += (size_t)d.ncl * 4 + (size_t)d.nvl * 16;
+                }
+                if (UP) {
+                    cU = reinterpret_cast<const int *>(pdat) + (m.cu - d.cu0);
+                    vU = reinterpret_cast<const double *>(pdat + (size_t)d.ncu * 4) + (size_t)(m.vu - d.vu0) * 2;
+                }
+                const int gs = m.gs, r0 = m.row0;
+                double sL[3] = {0.0, 0.0, 0.0}, sU[3] = {0.0, 0.0, 0.0};
+                // right-hand sides and old iterate of the own rows: issued before the gathers they overlap with
+                double rhs[3] = {0.0, 0.0, 0.0}, xo[3] = {0.0, 0.0, 0.0};
+                if (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD) {
 #pragma unroll
-                for (int r = 0; r < 3; r++)
-                    if (r < gs) {
-                        rhs[r] = (MODE == V2_BWD) ? p1[r0 + r] : b[r0 + r];
-                        if (MODE == V2_FWD_FULL) xo[r] = __ldcg(x + r0 + r);
-                    }
-            }
-            if (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_RESID || MODE == V2_SPMV) v2_half(cL, vL, m.nl, gs, x, sl, sL);
-            if (MODE == V2_FWD_FULL || MODE == V2_BWD || MODE == V2_SPMV) v2_half(cU, vU, m.nu, gs, x, sl, sU);
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-                if (LO) sL[r] = group_sum(sL[r], mask);
-                if (UP) sU[r] = group_sum(sU[r], mask);
-            }
-            if (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL) {
-                double xn[3] = {0.0, 0.0, 0.0};
+                    for (int r = 0; r < 3; r++)
+                        if (r < gs) {
+                            rhs[r] = (MODE == V2_BWD) ? p1[r0 + r] : b[r0 + r];
+                            if (MODE == V2_FWD_FULL) xo[r] = __ldcg(x + r0 + r);
+                        }
+                }
+                {
+                    double xl[2 * kV2Iters], xu[2 * kV2Iters];
+                    if (LO) v2_gather(cL, m.nl, x, sl, xl);
+                    if (UP) v2_gather(cU, m.nu, x, sl, xu);
+                    if (LO) v2_fma(vL, m.nl, gs, sl, xl, sL);
+                    if (UP) v2_fma(vU, m.nu, gs, sl, xu, sU);
+                    if (LO && m.nl > kV2Iters * 2 * GL) v2_tail(cL, vL, m.nl, gs, x, sl, sL);
+                    if (UP && m.nu > kV2Iters * 2 * GL) v2_tail(cU, vU, m.nu, gs, x, sl, sU);
+                }
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
-                    if (r < gs) {
-                        double inL = 0.0, inU = 0.0;
+                    if (LO) sL[r] = group_sum(sL[r], mask);
+                    if (UP) sU[r] = group_sum(sU[r], mask);
+                }
+                if (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL) {
+                    double xn[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            if (c < r) inL += blk[r * 3 + c] * xn[c];
-                            if (c > r) inU += blk[r * 3 + c] * xo[c];
-                        }
-                        const double up = sU[r] + inU, dg = blk[r * 3 + r];
-                        xn[r] = (rhs[r] - sL[r] - inL - up) / dg;
-                        if (sl == 0) {
-                            x[r0 + r] = xn[r];
-                            p1[r0 + r] = dg * xn[r] + up;
+                    for (int r = 0; r < 3; r++) {
+                        if (r < gs) {
+                            double inL = 0.0, inU = 0.0;
+#pragma unroll
+                            for (int cc = 0; cc < 3; cc++) {
+                                if (cc < r) inL += blk[r * 3 + cc] * xn[cc];
+                                if (cc > r) inU += blk[r * 3 + cc] * xo[cc];
+                            }
+                            const double up = sU[r] + inU, dg = blk[r * 3 + r];
+                            xn[r] = (rhs[r] - sL[r] - inL - up) / dg;
+                            if (sl == 0) {
+                                x[r0 + r] = xn[r];
+                                p1[r0 + r] = dg * xn[r] + up;
+                            }
                         }
                     }
-                }
-            } else if (MODE == V2_BWD) {
-                double xn[3] = {0.0, 0.0, 0.0};
+                } else if (MODE == V2_BWD) {
+                    double xn[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-                for (int r = 2; r >= 0; r--) {
-                    if (r < gs) {
-                        double inU = 0.0;
+                    for (int r = 2; r >= 0; r--) {
+                        if (r < gs) {
+                            double inU = 0.0;
 #pragma unroll
-                        for (int c = 0; c < 3; c++)
-                            if (c > r) inU += blk[r * 3 + c] * xn[c];
-                        xn[r] = (rhs[r] - sU[r] - inU) / blk[r * 3 + r];
-                        if (sl == 0) x[r0 + r] = xn[r];
+                            for (int cc = 0; cc < 3; cc++)
+                                if (cc > r) inU += blk[r * 3 + cc] * xn[cc];
+                            xn[r] = (rhs[r] - sU[r] - inU) / blk[r * 3 + r];
+                            if (sl == 0) x[r0 + r] = xn[r];
+                        }
                     }
-                }
-            } else {
-                // RESID / SPMV: one lane per row finishes with the in-group block
-                if (sl < gs) {
-                    const int i = r0 + sl;
-                    double s = sl == 0 ? sL[0] : (sl == 1 ? sL[1] : sL[2]);
-                    if (MODE == V2_RESID) {
-                        for (int c = 0; c < sl; c++) s += blk[sl * 3 + c] * __ldcg(x + r0 + c);
-                        y[i] = b[i] - (p1[i] + s);
-                    } else {
-                        s += sl == 0 ? sU[0] : (sl == 1 ? sU[1] : sU[2]);
-                        for (int c = 0; c < gs; c++) s += blk[sl * 3 + c] * __ldcg(x + r0 + c);
-                        y[i] = s;
-                        if (w) acc += w[i] * s;
+                } else {
+                    // RESID / SPMV: one lane per row finishes with the in-group block
+                    if (sl < gs) {
+                        const int i = r0 + sl;
+                        double sacc = sl == 0 ? sL[0] : (sl == 1 ? sL[1] : sL[2]);
+                        if (MODE == V2_RESID) {
+                            for (int cc = 0; cc < sl; cc++) sacc += blk[sl * 3 + cc] * __ldcg(x + r0 + cc);
+                            y[i] = b[i] - (p1[i] + sacc);
+                        } else {
+                            sacc += sl == 0 ? sU[0] : (sl == 1 ? sU[1] : sU[2]);
+                            for (int cc = 0; cc < gs; cc++) sacc += blk[sl * 3 + cc] * __ldcg(x + r0 + cc);
+                            y[i] = sacc;
+                            if (w) acc += w[i] * sacc;
+                        }
                     }
                 }
             }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[slot]);   // this warp is done reading the slot
         }
-        __syncthreads();   // everyone is done with bufs[bi]; it may be refilled in the next iteration
-        it++;
-        si_cur = si_nxt; c_cur = c_nxt; have_cur = have_nxt;
-        si_nxt = si_n2; c_nxt = c_n2; have_nxt = have_n2;
     }
-    if (MODE == V2_SPMV && partial) block_sum_to_partial(acc, partial);
+    if (MODE == V2_SPMV && partial) block_sum_to_partial(acc, partial);   // all warps, producer included
 }
 
 __global__ void k_extract_diag_inv2(Lvl2View A, double *__restrict__ dinv)

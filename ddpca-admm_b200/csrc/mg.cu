@@ -84,6 +84,7 @@ struct Level {
     double *VL = nullptr, *VU = nullptr, *BD = nullptr;
     ChunkDesc *chunks = nullptr;
     int nchunks = 0, max_stage_chunks = 0;
+    unsigned *gbar = nullptr;   // {arrival count, generation} of the consumer grid barrier
     size_t buf_lo = 0, buf_up = 0, buf_full = 0;   // shared-memory bytes of one chunk buffer per pass type
     Lvl2View view2() const { return Lvl2View{n, ng, nchunks, plan.nstages(), meta2, CL, VL, CU, VU, BD, chunks, stage_chunk}; }
 };
@@ -257,20 +258,20 @@ static int launch_v2(Engine *h, Level &L, int kclass, int l, double bytes, const
 {
     const bool staged = (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD);
     size_t buf = (MODE == V2_FWD_ZERO || MODE == V2_RESID) ? L.buf_lo : (MODE == V2_BWD ? L.buf_up : L.buf_full);
-    size_t dyn = 2 * buf;
+    size_t dyn = (size_t)kV2Bufs * buf;
     int per_sm = v2_blocks_per_sm<MODE>(dyn);
     int cap = per_sm * h->sms;
     int grid = std::min(staged ? L.max_stage_chunks : L.nchunks, cap);
     if (MODE == V2_SPMV && w) grid = std::min(grid, kNumPart);
     grid = std::max(grid, 1);
     Lvl2View A = L.view2();
-    int s0 = 0, s1 = L.plan.nstages();
+    unsigned *gbar = L.gbar;
     h->pre(kclass, l, bytes);
-    if (staged && s1 - s0 > 1) {
-        void *args[] = {(void *)&A, (void *)&s0, (void *)&s1, (void *)&buf, (void *)&b, (void *)&x, (void *)&p1, (void *)&y, (void *)&w, (void *)&partial, (void *)&done};
+    if (staged && L.plan.nstages() > 1) {
+        void *args[] = {(void *)&A, (void *)&buf, (void *)&gbar, (void *)&b, (void *)&x, (void *)&p1, (void *)&y, (void *)&w, (void *)&partial, (void *)&done};
         cudaLaunchCooperativeKernel((const void *)k_level_pass<MODE>, dim3(grid), dim3(kV2Threads), args, dyn, h->stream);
     } else {
-        k_level_pass<MODE><<<grid, kV2Threads, dyn, h->stream>>>(A, s0, s1, buf, b, x, p1, y, w, partial, done);
+        k_level_pass<MODE><<<grid, kV2Threads, dyn, h->stream>>>(A, buf, gbar, b, x, p1, y, w, partial, done);
     }
     h->post();
     return grid;
@@ -652,7 +653,7 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
         Layout2Host H2;
         if (want_v2) {
             if (!build_layout2(Ap, L.plan, H2, err)) return fail(err);
-            if (2 * H2.buf_full > 200 * 1024) want_v2 = false;   // two chunk buffers must fit in shared memory
+            if ((size_t)kV2Bufs * H2.buf_full > 200 * 1024) want_v2 = false;   // the chunk ring must fit in shared memory
         }
         L.v2 = want_v2;
         L.ng = (int)G.meta.size();
@@ -668,6 +669,8 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
             L.nchunks = (int)H2.chunks.size();
             L.max_stage_chunks = H2.max_stage_chunks;
             L.buf_lo = H2.buf_lo; L.buf_up = H2.buf_up; L.buf_full = H2.buf_full;
+            CU(cudaMalloc(&L.gbar, 2 * sizeof(unsigned)));
+            CU(cudaMemset(L.gbar, 0, 2 * sizeof(unsigned)));
             if (upload_vec(H2.meta, &L.meta2) || upload_vec(H2.CL, &L.CL) || upload_vec(H2.CU, &L.CU) || upload_vec(H2.VL, &L.VL) ||
                 upload_vec(H2.VU, &L.VU) || upload_vec(H2.BD, &L.BD) || upload_vec(H2.chunks, &L.chunks) || upload_vec(H2.stage_chunk, &L.stage_chunk)) return 1;
         } else {
@@ -686,7 +689,7 @@ static void free_level(Level &L)
     free_csr(L.A); free_csr(L.P); free_csr(L.R);
     cudaFree(L.meta); cudaFree(L.gci); cudaFree(L.gv); cudaFree(L.stage_group); cudaFree(L.perm);
     cudaFree(L.x); cudaFree(L.b); cudaFree(L.p1); cudaFree(L.r); cudaFree(L.dinv);
-    cudaFree(L.meta2); cudaFree(L.CL); cudaFree(L.CU); cudaFree(L.stage_chunk); cudaFree(L.VL); cudaFree(L.VU); cudaFree(L.BD); cudaFree(L.chunks);
+    cudaFree(L.meta2); cudaFree(L.CL); cudaFree(L.CU); cudaFree(L.stage_chunk); cudaFree(L.VL); cudaFree(L.VU); cudaFree(L.BD); cudaFree(L.chunks); cudaFree(L.gbar); L.gbar = nullptr;
     L.meta2 = nullptr; L.CL = L.CU = L.stage_chunk = nullptr; L.VL = L.VU = L.BD = nullptr; L.chunks = nullptr;
     L.meta = nullptr; L.gci = nullptr; L.gv = nullptr; L.stage_group = nullptr; L.perm = nullptr;
     L.x = L.b = L.p1 = L.r = L.dinv = nullptr;

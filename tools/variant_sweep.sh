@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-profile > /dev/null 2>&1   # generate + cache workload
 for lib in ddpca-admm_b200/lib/libddpca_b200.so ddpca-admm_b200/lib/var_*.so; do
-  v=$(DDPCA_B200_LIB=$PWD/$lib python bench.py --steps 5 --warmup 2 --no-cpu-baseline "$@" 2>&1 | tail -1 | python -c "
+  v=$(DDPCA_B200_LIB=$PWD/$lib python bench.py --steps 5 --warmup 2 --no-cpu-baseline --no-e2e "$@" 2>&1 | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())
 ks = d.get('kernel_shares') or {}
