@@ -27,7 +27,7 @@ namespace cg = cooperative_groups;
 #define DDPCA_V2_GROUPS 8
 #endif
 #ifndef DDPCA_V2_BUFS
-#define DDPCA_V2_BUFS 3
+#define DDPCA_V2_BUFS 2
 #endif
 constexpr int kChunkGroups = DDPCA_V2_GROUPS;        // row groups per chunk = consumer sub-warps per CTA
 constexpr int kV2Bufs = DDPCA_V2_BUFS;               // depth of the shared-memory ring

@@ -16,7 +16,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -s 280 -c 27
     --log-file gpurun_out/${tag}_launches.csv python bench.py $ARGS > gpurun_out/${tag}_ncu_list.log 2>&1
 echo "launch list rc=$?"
 cap() {  # name, kernel regex, skip, count
-  ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c $4 \
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c $4 \
       -o gpurun_out/${tag}_$1 python bench.py $ARGS > gpurun_out/${tag}_ncu_$1.log 2>&1
   echo "capture $1 rc=$?"
   ncu -i gpurun_out/${tag}_$1.ncu-rep --page raw --csv > gpurun_out/${tag}_$1_raw.csv 2>/dev/null
@@ -24,12 +24,10 @@ cap() {  # name, kernel regex, skip, count
   sz=$(stat -c %s gpurun_out/${tag}_$1.ncu-rep 2>/dev/null || echo 0)
   if [ "$sz" -gt 9000000 ]; then rm -f gpurun_out/${tag}_$1.ncu-rep; fi
 }
-# per V-cycle (4 levels, 8 colours): 48 fwd-stage launches [0-7] finest pre-smoothing (from zero,
-# lower half only) ... [40-47] finest post-smoothing (full rows); 48 bwd-stage launches likewise.
-cap spmv      'k_spmv_group'       1  1
-cap fwd_pre   'k_sweep_fwd_stage'  2  1
-cap fwd_post  'k_sweep_fwd_stage'  42 1
-cap bwd       'k_sweep_bwd_stage'  2  1
-cap resid     'k_resid_lower'      0  1
-cap transfer  '^k_spmv$'           0  6
+# v2 kernels: one k_level_pass<MODE> launch per sweep / residual / product
+cap spmv      'k_level_pass<4>|k_level_passILi4'  1  1
+cap fwd_zero  'k_level_pass<0>|k_level_passILi0'  0  1
+cap fwd_full  'k_level_pass<1>|k_level_passILi1'  2  1
+cap bwd       'k_level_pass<2>|k_level_passILi2'  0  1
+cap resid     'k_level_pass<3>|k_level_passILi3'  0  1
 du -sh gpurun_out; ls gpurun_out/ | head -50
