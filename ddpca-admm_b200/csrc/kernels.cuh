@@ -541,21 +541,31 @@ __global__ void __launch_bounds__(256) k_update_p(int n, const PcgState *st, con
 
 // ---- scalar kernels: one warp finishes a reduction and advances the PCG state ----------
 // after r = b: bb = b.b, tol = rel_tol*||b||, rr = bb ; loop condition of MGPIS.h:198 at it = 0
-__global__ void k_s_init(PcgState *st, const double *partial, int np, double rel_tol, long long maxit)
+// rel_tol / maxit of the coming solve (kept out of the captured graphs)
+__global__ void k_s_params(PcgState *st, double rel_tol, long long maxit)
+{
+    st->rel_tol = rel_tol;
+    st->maxit = maxit;
+}
+__global__ void k_s_init(PcgState *st, const double *partial, int np)
 {
     const double bb = warp_reduce_partials(partial, np);
     if (threadIdx.x == 0) {
-        st->bb = bb; st->rr = bb; st->rel_tol = rel_tol; st->tol = rel_tol * sqrt(bb);
-        st->it = 0; st->maxit = maxit; st->alpha = 0.0; st->beta = 0.0; st->delta_old = 0.0; st->delta_new = 0.0;
-        st->done = !(0 < maxit && sqrt(bb) > st->tol);
+        st->bb = bb; st->rr = bb; st->tol = st->rel_tol * sqrt(bb);
+        st->it = 0; st->alpha = 0.0; st->beta = 0.0; st->delta_old = 0.0; st->delta_new = 0.0;
+        st->done = !(0 < st->maxit && sqrt(bb) > st->tol);
     }
 }
 // delta_new = r.z after the first preconditioner application (MGPIS.h:197)
-__global__ void k_s_delta0(PcgState *st, const double *partial, int np)
+// `cond`: conditional handle of the WHILE node that repeats the CG iteration (device-side loop
+// control, one graph launch per solve); ignored when use_cond == 0.
+__global__ void k_s_delta0(PcgState *st, const double *partial, int np, cudaGraphConditionalHandle cond, int use_cond)
 {
-    if (st->done) return;
-    const double d = warp_reduce_partials(partial, np);
-    if (threadIdx.x == 0) st->delta_new = d;
+    if (!st->done) {
+        const double d = warp_reduce_partials(partial, np);
+        if (threadIdx.x == 0) st->delta_new = d;
+    }
+    if (use_cond && threadIdx.x == 0) cudaGraphSetConditional(cond, st->done ? 0u : 1u);
 }
 // alpha = delta_new / (p.q)   (MGPIS.h:201)
 __global__ void k_s_alpha(PcgState *st, const double *partial, int np)
@@ -579,11 +589,13 @@ __global__ void k_s_beta(PcgState *st, const double *partial, int np)
     if (threadIdx.x == 0) { st->delta_old = st->delta_new; st->delta_new = rz; st->beta = rz / st->delta_old; }
 }
 // end of an iteration: it++ and re-evaluate `it < maxit && ||r|| > tol` (MGPIS.h:219,198)
-__global__ void k_s_next(PcgState *st)
+__global__ void k_s_next(PcgState *st, cudaGraphConditionalHandle cond, int use_cond)
 {
-    if (st->done) return;
-    st->it += 1;
-    if (!(st->it < st->maxit && sqrt(st->rr) > st->tol)) st->done = 1;
+    if (!st->done) {
+        st->it += 1;
+        if (!(st->it < st->maxit && sqrt(st->rr) > st->tol)) st->done = 1;
+    }
+    if (use_cond) cudaGraphSetConditional(cond, st->done ? 0u : 1u);
 }
 
 // ---- ADMM interface kernels (MCONTACT.h:2632-2668, :2737-2833) ---------------------------------

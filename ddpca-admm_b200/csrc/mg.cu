@@ -165,6 +165,10 @@ struct ddpca_mg : Engine {
     double *partial[3] = {nullptr, nullptr, nullptr};
     cudaGraphExec_t iter_graph[2] = {nullptr, nullptr};  // per preconditioner
     long iter_graph_nodes[2] = {0, 0};
+    // whole solve as ONE graph: set-up nodes + a WHILE conditional node around the iteration body
+    cudaGraphExec_t solve_graph[2] = {nullptr, nullptr};
+    long solve_init_nodes[2] = {0, 0}, solve_iter_nodes[2] = {0, 0};
+    int while_state[2] = {0, 0};   // 0 untried, 1 available, -1 unavailable (host-polled loop is used)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double t_solve = 0, t_h2d = 0, t_d2h = 0;
 };
@@ -362,7 +366,7 @@ static void precondition(ddpca_mg *h, int prec, const double *r, double *z, cons
 static int vec_grid(const Engine *h, int n) { return std::max(1, std::min(cdiv(n, 256), std::min(kNumPart, h->sms * 8))); }
 
 // body of one CG iteration, MGPIS.h:199-219
-static void enqueue_iteration(ddpca_mg *h, int prec)
+static void enqueue_iteration(ddpca_mg *h, int prec, cudaGraphConditionalHandle cond = 0, int use_cond = 0)
 {
     int Lf = h->nlev - 1;
     Level &L = h->lev[Lf];
@@ -377,7 +381,78 @@ static void enqueue_iteration(ddpca_mg *h, int prec)
     KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, h->cg_r, h->cg_z, h->partial[2], done)));  // :212
     KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_beta<<<1, 32, 0, h->stream>>>(h->st, h->partial[2], gv)));                       // :211-213
     KL(h, DDPCA_K_VECTOR, Lf, 24.0 * n, (k_update_p<<<gv, 256, 0, h->stream>>>(n, h->st, h->cg_z, h->cg_p)));            // :214
-    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_next<<<1, 1, 0, h->stream>>>(h->st)));                                           // :219,198
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_next<<<1, 1, 0, h->stream>>>(h->st, cond, use_cond)));                                           // :219,198
+}
+
+// set-up of a solve after r = b, x = 0 (MGPIS.h:174-197): tolerance, first preconditioner application, delta_new
+static void enqueue_setup(ddpca_mg *h, int prec, cudaGraphConditionalHandle cond = 0, int use_cond = 0)
+{
+    int Lf = h->nlev - 1;
+    int n = h->lev[Lf].n;
+    const int *done = &h->st->done;
+    int gv = vec_grid(h, n);
+    KL(h, DDPCA_K_VECTOR, Lf, 8.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, h->cg_r, h->cg_r, h->partial[0], nullptr)));
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_init<<<1, 32, 0, h->stream>>>(h->st, h->partial[0], gv)));              // :174-175
+    precondition(h, prec, h->cg_r, h->cg_p, done);                                                              // :191-196
+    KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, h->cg_r, h->cg_p, h->partial[2], done)));
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_delta0<<<1, 32, 0, h->stream>>>(h->st, h->partial[2], gv, cond, use_cond)));  // :197
+}
+
+// One graph per solve: [set-up] -> WHILE(cond){ CG iteration }.  The loop condition of MGPIS.h:198
+// is evaluated on the device (k_s_delta0 / k_s_next call cudaGraphSetConditional): no host
+// polling, no iterations issued past convergence.  Returns 0 and sets while_state[prec] = -1 when
+// the driver refuses (then the host-polled per-iteration graph is used).
+static int build_solve_graph(ddpca_mg *h, int prec)
+{
+    if (h->while_state[prec] != 0) return 0;
+    h->while_state[prec] = -1;
+    if (std::getenv("DDPCA_NO_WHILE_GRAPH")) return 0;
+    cudaGraph_t g = nullptr;
+    cudaStream_t saved = h->stream;
+    h->stream = h->own_stream;
+    bool ok = false;
+    do {
+        if (cudaGraphCreate(&g, 0) != cudaSuccess) break;
+        cudaGraphConditionalHandle cond;
+        if (cudaGraphConditionalHandleCreate(&cond, g, 0, cudaGraphCondAssignDefault) != cudaSuccess) break;
+        // 1. set-up nodes
+        h->capturing = true; h->captured_nodes = 0;
+        if (cudaStreamBeginCaptureToGraph(h->stream, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { h->capturing = false; break; }
+        enqueue_setup(h, prec, cond, 1);
+        cudaStreamCaptureStatus cs; const cudaGraphNode_t *deps = nullptr; size_t ndeps = 0;
+        cudaError_t e1 = cudaStreamGetCaptureInfo(h->stream, &cs, nullptr, nullptr, &deps, &ndeps);
+        std::vector<cudaGraphNode_t> depv(deps, deps + (e1 == cudaSuccess ? ndeps : 0));
+        cudaGraph_t gout = nullptr;
+        cudaError_t e2 = cudaStreamEndCapture(h->stream, &gout);
+        h->capturing = false;
+        h->solve_init_nodes[prec] = h->captured_nodes;
+        if (e1 != cudaSuccess || e2 != cudaSuccess) break;
+        // 2. WHILE node after the set-up
+        cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+        np.conditional.handle = cond;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t wnode;
+        if (cudaGraphAddNode(&wnode, g, depv.data(), depv.size(), &np) != cudaSuccess) break;
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        // 3. iteration body
+        h->capturing = true; h->captured_nodes = 0;
+        if (cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { h->capturing = false; break; }
+        enqueue_iteration(h, prec, cond, 1);
+        cudaError_t e3 = cudaStreamEndCapture(h->stream, &gout);
+        h->capturing = false;
+        h->solve_iter_nodes[prec] = h->captured_nodes;
+        if (e3 != cudaSuccess) break;
+        if (cudaGraphInstantiate(&h->solve_graph[prec], g, 0) != cudaSuccess) break;
+        ok = true;
+    } while (0);
+    h->capturing = false;
+    h->stream = saved;
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();   // clear any sticky-free error of the attempt
+    if (ok) h->while_state[prec] = 1;
+    else if (std::getenv("DDPCA_VERBOSE")) std::fprintf(stderr, "ddpca: WHILE-graph unavailable, using the host-polled CG loop\n");
+    return 0;
 }
 
 static int build_iter_graph(ddpca_mg *h, int prec)
@@ -418,18 +493,20 @@ static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref,
         else k_extract_diag_inv<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
     }
     if (!h->profile) {
-        if (build_iter_graph(h, prec)) return 1;
+        build_solve_graph(h, prec);
+        if (h->while_state[prec] != 1 && build_iter_graph(h, prec)) return 1;
     }
-    int gv = vec_grid(h, n);
+    if (!h->profile) build_solve_graph(h, prec);
+    const bool use_while = !h->profile && h->while_state[prec] == 1;
     // r = b (device numbering), x = 0                                  MGPIS.h:173,189
     KL(h, DDPCA_K_VECTOR, Lf, 20.0 * n, (k_gather<<<cdiv(n, 256), 256, 0, h->stream>>>(n, L.perm, b_ref, h->cg_r)));
     CU(cudaMemsetAsync(h->cg_x, 0, sizeof(double) * n, h->stream));
     CU(cudaMemsetAsync(h->cg_p, 0, sizeof(double) * n, h->stream));
-    KL(h, DDPCA_K_VECTOR, Lf, 8.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, h->cg_r, h->cg_r, h->partial[0], nullptr)));
-    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_init<<<1, 32, 0, h->stream>>>(h->st, h->partial[0], gv, rel_tol, (long long)maxit)));  // :174-175
-    precondition(h, prec, h->cg_r, h->cg_p, done);                                                                              // :191-196
-    KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, h->cg_r, h->cg_p, h->partial[2], done)));
-    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_delta0<<<1, 32, 0, h->stream>>>(h->st, h->partial[2], gv)));                            // :197
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_params<<<1, 1, 0, h->stream>>>(h->st, rel_tol, (long long)maxit)));
+    if (use_while) {
+        CU(cudaGraphLaunch(h->solve_graph[prec], h->stream));
+    } else {
+    enqueue_setup(h, prec);
     // main loop: enqueue iterations ahead, poll `done` with a lag of kDepth iterations
     cudaEvent_t evs[kDepth + 1];
     for (int k = 0; k <= kDepth; k++) CU(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
@@ -458,12 +535,14 @@ static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref,
         }
         if (h->profile && (issued % 8) == 0) h->prof_collect();
     }
+    for (int k = 0; k <= kDepth; k++) cudaEventDestroy(evs[k]);
+    }
     // x (device numbering) -> reference numbering
     KL(h, DDPCA_K_VECTOR, Lf, 20.0 * n, (k_scatter<<<cdiv(n, 256), 256, 0, h->stream>>>(n, L.perm, h->cg_x, x_ref)));
     CU(cudaMemcpyAsync(&h->st_host[0], h->st, sizeof(PcgState), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    for (int k = 0; k <= kDepth; k++) cudaEventDestroy(evs[k]);
     if (h->profile) h->prof_collect();
+    if (use_while) h->launches += h->solve_init_nodes[prec] + (long)h->st_host[0].it * h->solve_iter_nodes[prec];
     if (iters) *iters = (long)h->st_host[0].it;
     if (resid) *resid = std::sqrt(h->st_host[0].rr);
     if (tol_abs) *tol_abs = h->st_host[0].tol;
@@ -868,6 +947,7 @@ int ddpca_mg_destroy(ddpca_mg *h)
     if (h->st_host) cudaFreeHost(h->st_host);
     for (int k = 0; k < 3; k++) cudaFree(h->partial[k]);
     for (int k = 0; k < 2; k++) if (h->iter_graph[k]) cudaGraphExecDestroy(h->iter_graph[k]);
+    for (int k = 0; k < 2; k++) if (h->solve_graph[k]) cudaGraphExecDestroy(h->solve_graph[k]);
     for (int k = 0; k < 4; k++) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;

@@ -8,11 +8,11 @@ tag="${1:-r1}"; shift || true
 mkdir -p gpurun_out
 # no warm-up solve: the first V-cycle's launches are at known positions (see cap calls below)
 ARGS="--steps 1 --warmup 0 --no-cpu-baseline --no-profile --no-e2e $*"
-KRE='regex:k_sweep|k_spmv|k_resid|k_dense|k_update|k_dot|k_s_|k_jacobi'
+KRE='regex:k_level_pass|k_sweep|k_spmv|k_resid|k_dense|k_update|k_dot|k_s_|k_jacobi'
 python bench.py $ARGS > gpurun_out/${tag}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${tag}_plain.log; exit 1; }
 tail -c 300 gpurun_out/${tag}_plain.log; echo
-# skip the set-up V-cycle and the first CG iteration (~280 launches); two iterations follow
-ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -s 280 -c 270 --csv \
+# skip the set-up V-cycle and the first CG iteration (~45 launches with v2 kernels); two iterations follow
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -s 45 -c 100 --csv \
     --log-file gpurun_out/${tag}_launches.csv python bench.py $ARGS > gpurun_out/${tag}_ncu_list.log 2>&1
 echo "launch list rc=$?"
 cap() {  # name, kernel regex, skip, count
@@ -25,9 +25,9 @@ cap() {  # name, kernel regex, skip, count
   if [ "$sz" -gt 9000000 ]; then rm -f gpurun_out/${tag}_$1.ncu-rep; fi
 }
 # v2 kernels: one k_level_pass<MODE> launch per sweep / residual / product
-cap spmv      'k_level_pass<4>|k_level_passILi4'  1  1
-cap fwd_zero  'k_level_pass<0>|k_level_passILi0'  0  1
-cap fwd_full  'k_level_pass<1>|k_level_passILi1'  2  1
-cap bwd       'k_level_pass<2>|k_level_passILi2'  0  1
-cap resid     'k_level_pass<3>|k_level_passILi3'  0  1
+cap spmv      'k_level_pass<\(int\)4>'  1  1
+cap fwd_zero  'k_level_pass<\(int\)0>'  0  1
+cap fwd_full  'k_level_pass<\(int\)1>'  2  1
+cap bwd       'k_level_pass<\(int\)2>'  0  1
+cap resid     'k_level_pass<\(int\)3>'  0  1
 du -sh gpurun_out; ls gpurun_out/ | head -50
