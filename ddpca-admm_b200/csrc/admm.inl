@@ -18,6 +18,7 @@ struct AdmmBody {
     DevCsr accuProl;       // macroscopic problem only
     double *disp = nullptr, *disp_prev = nullptr, *addi = nullptr, *rhs = nullptr, *u = nullptr;
     bool set = false;
+    bool local = true;     // owned by this rank (multi-GPU: one process per GPU)
 };
 struct AdmmSide {
     DevCsr op[10];
@@ -25,6 +26,8 @@ struct AdmmSide {
     ddpca_ldlt *mass = nullptr, *mass_pena = nullptr;
     double *aux = nullptr, *lagr = nullptr, *aux_prev = nullptr, *lagr_prev = nullptr, *force = nullptr, *tmp = nullptr;
     int nc = 0;   // d * n_c
+    bool local = true;     // side lives with its body
+    double *trace = nullptr;   // inpoLagr*lambda + pemaInpo_r*u of this side, d*n_ip (private or inside the exchange buffer)
 };
 struct AdmmIface {
     int body[2] = {-1, -1};
@@ -34,6 +37,8 @@ struct AdmmIface {
     int *stat = nullptr;
     AdmmSide side[2];
     bool set = false;
+    bool cross = false;    // the two sides live on different ranks: traces go through the exchange buffer
+    long trace_off[2] = {-1, -1};
 };
 
 }  // namespace
@@ -50,6 +55,12 @@ struct ddpca_admm : Engine {
     double *moni_host = nullptr;
     int nslots = 0;
     bool finalized = false;
+    // multi-rank: ownership + externally provided exchange buffers (device memory the caller all-reduces)
+    std::vector<int> body_rank;
+    int my_rank = 0;
+    long trace_total = 0;             // doubles in the packed trace buffer (cross-rank interfaces only)
+    double *x_glob = nullptr, *x_trace = nullptr, *x_moni = nullptr;   // external buffers (not owned) or null
+    double *own_trace = nullptr;      // internal packed trace buffer when none is provided
     long cg_iters = 0;        // CG iterations of the last step, all bodies
     double cg_dof_iters = 0;  // sum over bodies of n_L * iterations, last step
 };
@@ -70,10 +81,11 @@ static void admm_free(ddpca_admm *h)
             free_csr(s.systTran_penaT);
             ldlt_free(s.mass); ldlt_free(s.mass_pena);
             cudaFree(s.aux); cudaFree(s.lagr); cudaFree(s.aux_prev); cudaFree(s.lagr_prev); cudaFree(s.force); cudaFree(s.tmp);
+            if (!f.cross) cudaFree(s.trace);
         }
     }
     ldlt_free(h->coar);
-    cudaFree(h->globForc); cudaFree(h->globSolu); cudaFree(h->moni_part); cudaFree(h->moni_out);
+    cudaFree(h->globForc); cudaFree(h->globSolu); cudaFree(h->moni_part); cudaFree(h->moni_out); cudaFree(h->own_trace);
     if (h->moni_host) cudaFreeHost(h->moni_host);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -108,14 +120,21 @@ static void admm_moni(ddpca_admm *h, int slot, int n, const double *cur, const d
     KL(h, DDPCA_K_VECTOR, 15, 16.0 * n, (k_moni_partial<<<kMoniBlocks, 256, 0, h->stream>>>(n, cur, prev, h->moni_part + (size_t)slot * 2 * kMoniBlocks)));
 }
 
-static int admm_step(ddpca_admm *h, int apply_macro, double *monitor_row)
+// ---- the loop body in phases; between phases a multi-rank caller all-reduces one buffer ---------
+enum { PH_BODIES = 0, PH_MACRO_PARTIAL = 1, PH_MACRO_APPLY = 2, PH_TRACES = 3, PH_INTERFACE = 4, PH_MONITOR = 5 };
+
+static double *glob_buf(ddpca_admm *h) { return h->x_glob ? h->x_glob : h->globForc; }
+static double *moni_buf(ddpca_admm *h) { return h->x_moni ? h->x_moni : h->moni_out; }
+
+// body balance, MCONTACT.h:2511-2538 (local bodies)
+static int admm_bodies(ddpca_admm *h)
 {
     cudaStream_t st = h->stream;
     h->cg_iters = 0;
     h->cg_dof_iters = 0;
-    // ---- body balance, MCONTACT.h:2511-2538 --------------------------------------------------
     for (int v = 0; v < h->nb; v++) {
         AdmmBody &b = h->body[v];
+        if (!b.local) continue;
         CU(cudaMemcpyAsync(b.disp_prev, b.disp, sizeof(double) * b.nfull, cudaMemcpyDeviceToDevice, st));  // :2507
         CU(cudaMemsetAsync(b.addi, 0, sizeof(double) * b.nfull, st));                                       // :2514
         for (int ts = 0; ts < h->ni; ts++)
@@ -136,37 +155,75 @@ static int admm_step(ddpca_admm *h, int apply_macro, double *monitor_row)
         CU(cudaMemcpyAsync(b.disp, b.dispCons, sizeof(double) * b.nfull, cudaMemcpyDeviceToDevice, st));
         ADMM_SPMV(b.FT, b.u, b.disp, true, 1.0);    // OUTP_SUB1 :2533
     }
-    // ---- macroscopic problem, :2540-2573 -----------------------------------------------------------
-    if (apply_macro) {
-        if (!h->coar) return fail("ddpca_admm_step: macroscopic problem requested but not set");
-        CU(cudaMemsetAsync(h->globForc, 0, sizeof(double) * h->nglob, st));
-        for (int ts = 0; ts < h->ni; ts++)
-            for (int tv = 0; tv < 2; tv++) {
-                AdmmIface &f = h->iface[ts];
-                AdmmSide &s = f.side[tv];
-                ADMM_SPMV(s.op[DDPCA_OP_GLOBTRAN], s.lagr, h->globForc, true, 1.0);                       // :2545
-                ADMM_SPMV(s.op[DDPCA_OP_GLOBTRAN_PENA], s.aux, h->globForc, true, -1.0);                  // :2546
-                ADMM_SPMV(s.op[DDPCA_OP_GLOBTRAN_D], h->body[f.body[tv]].disp, h->globForc, true, 1.0);   // :2547
-            }
-        ldlt_solve_on(h, h->coar, h->globForc, h->globSolu, nullptr);   // :2553
-        for (int v = 0; v < h->nb; v++) {
-            AdmmBody &b = h->body[v];
-            ADMM_SPMV(b.accuProl, h->globSolu + h->baseReco[v], b.u, false, 1.0);   // :2564-2567
-            ADMM_SPMV(b.FT, b.u, b.disp, true, 1.0);                                 // :2569-2570 (OUTP_SUB1 ...
-            KL(h, DDPCA_K_VECTOR, 15, 24.0 * b.nfull, (k_axpy<<<cdiv(b.nfull, 256), 256, 0, st>>>(b.nfull, 1.0, b.dispCons, b.disp)));  // ... re-adds prescribed values)
+    return 0;
+}
+
+// macroscopic problem, :2541-2549: this rank's part of globForc (sum over its sides)
+static int admm_macro_partial(ddpca_admm *h)
+{
+    if (!h->coar) return fail("macroscopic problem requested but not set");
+    double *gf = glob_buf(h);
+    CU(cudaMemsetAsync(gf, 0, sizeof(double) * h->nglob, h->stream));
+    for (int ts = 0; ts < h->ni; ts++)
+        for (int tv = 0; tv < 2; tv++) {
+            AdmmIface &f = h->iface[ts];
+            AdmmSide &s = f.side[tv];
+            if (!s.local) continue;
+            ADMM_SPMV(s.op[DDPCA_OP_GLOBTRAN], s.lagr, gf, true, 1.0);                       // :2545
+            ADMM_SPMV(s.op[DDPCA_OP_GLOBTRAN_PENA], s.aux, gf, true, -1.0);                  // :2546
+            ADMM_SPMV(s.op[DDPCA_OP_GLOBTRAN_D], h->body[f.body[tv]].disp, gf, true, 1.0);   // :2547
         }
+    return 0;
+}
+// :2553-2572: replicated coarse solve, correction of the local bodies
+static int admm_macro_apply(ddpca_admm *h)
+{
+    cudaStream_t st = h->stream;
+    ldlt_solve_on(h, h->coar, glob_buf(h), h->globSolu, nullptr);   // :2553
+    for (int v = 0; v < h->nb; v++) {
+        AdmmBody &b = h->body[v];
+        if (!b.local) continue;
+        ADMM_SPMV(b.accuProl, h->globSolu + h->baseReco[v], b.u, false, 1.0);   // :2564-2567
+        ADMM_SPMV(b.FT, b.u, b.disp, true, 1.0);                                 // :2569-2570 (OUTP_SUB1 ...
+        KL(h, DDPCA_K_VECTOR, 15, 24.0 * b.nfull, (k_axpy<<<cdiv(b.nfull, 256), 256, 0, st>>>(b.nfull, 1.0, b.dispCons, b.disp)));  // ... re-adds prescribed values)
     }
-    // ---- interface balance, :2628-2685 ------------------------------------------------------------------
+    return 0;
+}
+// side traces inpoLagr*lambda + pemaInpo_r*u (:2632-2635); remote sides of cross-rank interfaces are zero-filled
+static int admm_traces(ddpca_admm *h)
+{
+    // slots of interfaces this rank does not touch must contribute zero to the all-reduce
+    if (h->trace_total) CU(cudaMemsetAsync(h->x_trace ? h->x_trace : h->own_trace, 0, sizeof(double) * h->trace_total, h->stream));
     for (int ts = 0; ts < h->ni; ts++) {
         AdmmIface &f = h->iface[ts];
+        if (!f.side[0].local && !f.side[1].local) continue;
         int ng = f.d * f.nip;
-        ADMM_SPMV(f.side[0].op[DDPCA_OP_INPOLAGR], f.side[0].lagr, f.t, false, 1.0);                // :2632
-        ADMM_SPMV(f.side[1].op[DDPCA_OP_INPOLAGR], f.side[1].lagr, f.t, true, -1.0);                // :2633
-        ADMM_SPMV(f.side[0].op[DDPCA_OP_PEMAINPO_R], h->body[f.body[0]].disp, f.t, true, 1.0);      // :2634
-        ADMM_SPMV(f.side[1].op[DDPCA_OP_PEMAINPO_R], h->body[f.body[1]].disp, f.t, true, -1.0);     // :2635
+        for (int tv = 0; tv < 2; tv++) {
+            AdmmSide &s = f.side[tv];
+            if (s.local) {
+                ADMM_SPMV(s.op[DDPCA_OP_INPOLAGR], s.lagr, s.trace, false, 1.0);
+                ADMM_SPMV(s.op[DDPCA_OP_PEMAINPO_R], h->body[f.body[tv]].disp, s.trace, true, 1.0);
+            } else {
+                CU(cudaMemsetAsync(s.trace, 0, sizeof(double) * ng, h->stream));
+            }
+        }
+    }
+    return 0;
+}
+// interface balance :2636-2685 and multiplier update :2689-2704 for the local sides
+static int admm_interface(ddpca_admm *h)
+{
+    cudaStream_t st = h->stream;
+    for (int ts = 0; ts < h->ni; ts++) {
+        AdmmIface &f = h->iface[ts];
+        if (!f.side[0].local && !f.side[1].local) continue;
+        int ng = f.d * f.nip;
+        CU(cudaMemcpyAsync(f.t, f.side[0].trace, sizeof(double) * ng, cudaMemcpyDeviceToDevice, st));
+        KL(h, DDPCA_K_VECTOR, 15, 24.0 * ng, (k_axpy<<<cdiv(ng, 256), 256, 0, st>>>(ng, -1.0, f.side[1].trace, f.t)));   // :2632-2635
         KL(h, DDPCA_K_VECTOR, 15, 28.0 * ng, (k_gamma_project<<<cdiv(f.nip, 256), 256, 0, st>>>(f.nip, f.d, f.fric, f.t, f.gap, f.gamma, f.stat)));  // :2636-2668
         for (int tv = 0; tv < 2; tv++) {
             AdmmSide &s = f.side[tv];
+            if (!s.local) continue;
             ADMM_SPMV(s.systTran_penaT, h->body[f.body[tv]].disp, s.force, false, 1.0);   // :2673
             ADMM_SPMV(s.op[DDPCA_OP_INTEMASS], s.lagr, s.force, true, 1.0);               // :2674
             ADMM_SPMV(s.op[DDPCA_OP_INTEINPO], f.gamma, s.force, true, 1.0);              // :2675
@@ -174,11 +231,11 @@ static int admm_step(ddpca_admm *h, int apply_macro, double *monitor_row)
             ldlt_solve_on(h, s.mass_pena, s.force, s.aux, nullptr);                       // :2677
         }
     }
-    // ---- Lagrange multiplier, :2689-2704 ------------------------------------------------------------------
     for (int ts = 0; ts < h->ni; ts++) {
         AdmmIface &f = h->iface[ts];
         for (int tv = 0; tv < 2; tv++) {
             AdmmSide &s = f.side[tv];
+            if (!s.local) continue;
             ADMM_SPMV(s.systTran_penaT, h->body[f.body[tv]].disp, s.force, false, 1.0);   // :2693
             ADMM_SPMV(s.op[DDPCA_OP_INTEMASS_PENA], s.aux, s.force, true, -1.0);          // :2694
             ldlt_solve_on(h, s.mass, s.force, s.tmp, nullptr);                            // :2696
@@ -186,44 +243,62 @@ static int admm_step(ddpca_admm *h, int apply_macro, double *monitor_row)
             KL(h, DDPCA_K_VECTOR, 15, 24.0 * s.nc, (k_axpy<<<cdiv(s.nc, 256), 256, 0, st>>>(s.nc, 1.0, s.tmp, s.lagr)));
         }
     }
-    // ---- MONITOR sums, :2737-2833 ------------------------------------------------------------------------------
-    for (int v = 0; v < h->nb; v++) admm_moni(h, v, h->body[v].nfull, h->body[v].disp, h->body[v].disp_prev);
+    return 0;
+}
+// MONITOR sums, :2737-2833: slots of remote bodies / sides stay zero (the caller all-reduces)
+static int admm_monitor(ddpca_admm *h)
+{
+    CU(cudaMemsetAsync(h->moni_part, 0, sizeof(double) * 2 * kMoniBlocks * h->nslots, h->stream));
+    for (int v = 0; v < h->nb; v++)
+        if (h->body[v].local) admm_moni(h, v, h->body[v].nfull, h->body[v].disp, h->body[v].disp_prev);
     for (int ts = 0; ts < h->ni; ts++)
         for (int tv = 0; tv < 2; tv++) {
             AdmmSide &s = h->iface[ts].side[tv];
+            if (!s.local) continue;
             int slot = h->nb + 4 * ts + 2 * tv;   // tempIndi of :2771
             admm_moni(h, slot, s.nc, s.aux, s.aux_prev);
             admm_moni(h, slot + 1, s.nc, s.lagr, s.lagr_prev);
         }
-    KL(h, DDPCA_K_VECTOR, 15, 0.0, (k_moni_final<<<h->nslots, 32, 0, st>>>(h->moni_part, h->moni_out)));
-    CU(cudaMemcpyAsync(h->moni_host, h->moni_out, sizeof(double) * 2 * h->nslots, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    KL(h, DDPCA_K_VECTOR, 15, 0.0, (k_moni_final<<<h->nslots, 32, 0, h->stream>>>(h->moni_part, moni_buf(h))));
+    return 0;
+}
+// row of resuMoni.txt (:2742-2743, :2777-2778, :2807-2808, :2835) from the (all-reduced) sums
+static int admm_row(ddpca_admm *h, double *monitor_row)
+{
+    CU(cudaMemcpyAsync(h->moni_host, moni_buf(h), sizeof(double) * 2 * h->nslots, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     if (h->profile) h->prof_collect();
-    if (monitor_row) {
-        // row layout of resuMoni.txt (:2742-2743, :2777-2778, :2807-2808, :2835)
-        double convValu = 0.0, convCrit = 0.0;
-        int c = 0;
-        for (int v = 0; v < h->nb; v++) {
-            monitor_row[c++] = h->moni_host[2 * v];
-            monitor_row[c++] = h->moni_host[2 * v + 1];
-            convValu += h->moni_host[2 * v];
-            convCrit += h->moni_host[2 * v + 1];
-        }
-        for (int ts = 0; ts < h->ni; ts++)
-            for (int tv = 0; tv < 2; tv++) {
-                int slot = h->nb + 4 * ts + 2 * tv;
-                monitor_row[c++] = h->moni_host[2 * slot];
-                monitor_row[c++] = h->moni_host[2 * slot + 1];
-                convValu += h->moni_host[2 * slot];
-                convCrit += h->moni_host[2 * slot + 1];
-                monitor_row[c++] = h->moni_host[2 * (slot + 1)];
-                monitor_row[c++] = h->moni_host[2 * (slot + 1) + 1];
-            }
-        monitor_row[c++] = convValu;
-        monitor_row[c++] = convCrit;
+    if (!monitor_row) return 0;
+    double convValu = 0.0, convCrit = 0.0;
+    int c = 0;
+    for (int v = 0; v < h->nb; v++) {
+        monitor_row[c++] = h->moni_host[2 * v];
+        monitor_row[c++] = h->moni_host[2 * v + 1];
+        convValu += h->moni_host[2 * v];
+        convCrit += h->moni_host[2 * v + 1];
     }
+    for (int ts = 0; ts < h->ni; ts++)
+        for (int tv = 0; tv < 2; tv++) {
+            int slot = h->nb + 4 * ts + 2 * tv;
+            monitor_row[c++] = h->moni_host[2 * slot];
+            monitor_row[c++] = h->moni_host[2 * slot + 1];
+            convValu += h->moni_host[2 * slot];
+            convCrit += h->moni_host[2 * slot + 1];
+            monitor_row[c++] = h->moni_host[2 * (slot + 1)];
+            monitor_row[c++] = h->moni_host[2 * (slot + 1) + 1];
+        }
+    monitor_row[c++] = convValu;
+    monitor_row[c++] = convCrit;
     return 0;
+}
+
+static int admm_step(ddpca_admm *h, int apply_macro, double *monitor_row)
+{
+    if (admm_bodies(h)) return 1;
+    if (apply_macro && (admm_macro_partial(h) || admm_macro_apply(h))) return 1;
+    if (admm_traces(h) || admm_interface(h) || admm_monitor(h)) return 1;
+    return admm_row(h, monitor_row);
 }
 
 extern "C" {
@@ -258,6 +333,7 @@ int ddpca_admm_set_body(ddpca_admm *h, int v, ddpca_mg *mg, int nfull, const dou
     CU(cudaSetDevice(h->device));
     AdmmBody &b = h->body[v];
     if (b.set) return fail("ddpca_admm_set_body: body already set");
+    if (!b.local) return fail("ddpca_admm_set_body: body " + std::to_string(v) + " belongs to another rank");
     b.mg = mg;
     b.nfull = nfull;
     b.nred = mg->lev[mg->nlev - 1].n;
@@ -290,6 +366,9 @@ int ddpca_admm_set_interface(ddpca_admm *h, int ts, int body0, int body1, double
     AdmmIface &f = h->iface[ts];
     if (f.set) return fail("interface already set");
     f.body[0] = body0; f.body[1] = body1;
+    f.side[0].local = h->body[body0].local;
+    f.side[1].local = h->body[body1].local;
+    f.cross = !h->body_rank.empty() && h->body_rank[body0] != h->body_rank[body1];
     f.fric = fricCoef;
     f.nip = nip;
     f.d = (fricCoef == 0.0) ? 1 : 3;   // MCONTACT.h:886-893
@@ -306,6 +385,7 @@ int ddpca_admm_set_side_op(ddpca_admm *h, int ts, int tv, int op, int rows, int 
     if (!h || ts < 0 || ts >= h->ni || tv < 0 || tv > 1 || op < 0 || op >= DDPCA_OP_COUNT || !h->iface[ts].set) return fail("ddpca_admm_set_side_op: bad argument");
     CU(cudaSetDevice(h->device));
     AdmmSide &s = h->iface[ts].side[tv];
+    if (!s.local) return fail("ddpca_admm_set_side_op: this side belongs to another rank");
     CsrHost A;
     if (host_csr(rows, cols, rowptr, colidx, val, A)) return 1;
     if (op == DDPCA_OP_INTEMASS) s.nc = rows;
@@ -346,6 +426,7 @@ int ddpca_admm_finalize(ddpca_admm *h)
     if (!h) return fail("null handle");
     CU(cudaSetDevice(h->device));
     for (int v = 0; v < h->nb; v++) {
+        if (!h->body[v].local) continue;
         if (!h->body[v].set) return fail("body " + std::to_string(v) + " not set");
         if ((h->muscSett & 1) && h->body[v].accuProl.rows == 0) return fail("body " + std::to_string(v) + ": accuProl missing");
         if ((h->muscSett & 1) && h->baseReco.size() == (size_t)h->nb + 1 && h->baseReco[v] + h->body[v].accuProl.cols > h->nglob) return fail("baseReco out of range");
@@ -356,6 +437,7 @@ int ddpca_admm_finalize(ddpca_admm *h)
         if (!f.set) return fail("interface " + std::to_string(ts) + " not set");
         for (int tv = 0; tv < 2; tv++) {
             AdmmSide &s = f.side[tv];
+            if (!s.local) continue;
             int need[] = {DDPCA_OP_SYSTTRAN, DDPCA_OP_SYSTTRAN_PENA, DDPCA_OP_INTEMASS, DDPCA_OP_INTEMASS_PENA, DDPCA_OP_INPOLAGR, DDPCA_OP_INTEINPO, DDPCA_OP_PEMAINPO_R};
             for (int o : need) if (s.op[o].rows == 0 && s.op[o].rp == nullptr) return fail("interface " + std::to_string(ts) + " side " + std::to_string(tv) + ": operator " + std::to_string(o) + " missing");
             if (h->muscSett & 1)
@@ -371,6 +453,23 @@ int ddpca_admm_finalize(ddpca_admm *h)
                 if (dev_vec(nullptr, s.nc, &s.aux) || dev_vec(nullptr, s.nc, &s.lagr) || dev_vec(nullptr, s.nc, &s.aux_prev) ||
                     dev_vec(nullptr, s.nc, &s.lagr_prev) || dev_vec(nullptr, s.nc, &s.force) || dev_vec(nullptr, s.nc, &s.tmp)) return 1;
             }
+        }
+    }
+    // trace buffers: cross-rank interfaces live in one packed buffer with the same layout on every rank
+    h->trace_total = 0;
+    for (int ts = 0; ts < h->ni; ts++) {
+        AdmmIface &f = h->iface[ts];
+        if (!f.cross) continue;
+        for (int tv = 0; tv < 2; tv++) { f.trace_off[tv] = h->trace_total; h->trace_total += (long)f.d * f.nip; }
+    }
+    if (h->trace_total && !h->x_trace && !h->own_trace) { if (dev_vec(nullptr, (int)h->trace_total, &h->own_trace)) return 1; }
+    for (int ts = 0; ts < h->ni; ts++) {
+        AdmmIface &f = h->iface[ts];
+        if (!f.side[0].local && !f.side[1].local) continue;
+        for (int tv = 0; tv < 2; tv++) {
+            AdmmSide &s = f.side[tv];
+            if (f.cross) s.trace = (h->x_trace ? h->x_trace : h->own_trace) + f.trace_off[tv];
+            else if (!s.trace) { if (dev_vec(nullptr, f.d * f.nip, &s.trace)) return 1; }
         }
     }
     h->nslots = h->nb + 4 * h->ni;
@@ -393,12 +492,69 @@ int ddpca_admm_step(ddpca_admm *h, int apply_macro, double *monitor_row, long *c
     return 0;
 }
 
+int ddpca_admm_set_partition(ddpca_admm *h, const int *body_rank, int my_rank)
+{
+    if (!h || !body_rank) return fail("ddpca_admm_set_partition: bad argument");
+    for (int v = 0; v < h->nb; v++) if (h->body[v].set) return fail("ddpca_admm_set_partition must precede ddpca_admm_set_body");
+    h->body_rank.assign(body_rank, body_rank + h->nb);
+    h->my_rank = my_rank;
+    for (int v = 0; v < h->nb; v++) h->body[v].local = (body_rank[v] == my_rank);
+    return 0;
+}
+int ddpca_admm_exchange_sizes(const ddpca_admm *h, long *nglob, long *ntrace, long *nmoni)
+{
+    if (!h) return fail("null handle");
+    long nt = 0;
+    for (int ts = 0; ts < h->ni; ts++) if (h->iface[ts].cross) nt += 2L * h->iface[ts].d * h->iface[ts].nip;
+    if (nglob) *nglob = h->nglob;
+    if (ntrace) *ntrace = nt;
+    if (nmoni) *nmoni = 2L * (h->nb + 4 * h->ni);
+    return 0;
+}
+int ddpca_admm_set_exchange(ddpca_admm *h, double *globForc_dev, double *traces_dev, double *moni_dev)
+{
+    if (!h) return fail("null handle");
+    if (h->finalized) return fail("ddpca_admm_set_exchange must precede ddpca_admm_finalize");
+    h->x_glob = globForc_dev; h->x_trace = traces_dev; h->x_moni = moni_dev;
+    return 0;
+}
+int ddpca_admm_phase(ddpca_admm *h, int phase)
+{
+    if (!h || !h->finalized) return fail("ddpca_admm_phase: handle not finalized");
+    CU(cudaSetDevice(h->device));
+    switch (phase) {
+    case PH_BODIES: return admm_bodies(h);
+    case PH_MACRO_PARTIAL: return admm_macro_partial(h);
+    case PH_MACRO_APPLY: return admm_macro_apply(h);
+    case PH_TRACES: return admm_traces(h);
+    case PH_INTERFACE: return admm_interface(h);
+    case PH_MONITOR: return admm_monitor(h);
+    }
+    return fail("ddpca_admm_phase: unknown phase");
+}
+int ddpca_admm_monitor_row(ddpca_admm *h, double *monitor_row, long *cg_iters, double *cg_dof_iters)
+{
+    if (!h || !h->finalized) return fail("ddpca_admm_monitor_row: handle not finalized");
+    CU(cudaSetDevice(h->device));
+    if (admm_row(h, monitor_row)) return 1;
+    if (cg_iters) *cg_iters = h->cg_iters;
+    if (cg_dof_iters) *cg_dof_iters = h->cg_dof_iters;
+    return 0;
+}
+int ddpca_admm_set_stream(ddpca_admm *h, void *stream)
+{
+    if (!h) return fail("null handle");
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return 0;
+}
+
 int ddpca_admm_row_length(const ddpca_admm *h) { return h ? 2 * h->nb + 8 * h->ni + 2 : -1; }
 
 int ddpca_admm_get_disp(ddpca_admm *h, int v, double *out)
 {
     if (!h || v < 0 || v >= h->nb || !out) return fail("ddpca_admm_get_disp: bad argument");
     CU(cudaSetDevice(h->device));
+    if (!h->body[v].local) return fail("ddpca_admm_get_disp: body belongs to another rank");
     CU(cudaMemcpy(out, h->body[v].disp, sizeof(double) * h->body[v].nfull, cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -407,6 +563,7 @@ int ddpca_admm_get_side(ddpca_admm *h, int ts, int tv, double *aux, double *lagr
     if (!h || ts < 0 || ts >= h->ni || tv < 0 || tv > 1) return fail("ddpca_admm_get_side: bad argument");
     CU(cudaSetDevice(h->device));
     AdmmSide &s = h->iface[ts].side[tv];
+    if (!s.local) return fail("ddpca_admm_get_side: side belongs to another rank");
     if (aux) CU(cudaMemcpy(aux, s.aux, sizeof(double) * s.nc, cudaMemcpyDeviceToHost));
     if (lagr) CU(cudaMemcpy(lagr, s.lagr, sizeof(double) * s.nc, cudaMemcpyDeviceToHost));
     return 0;

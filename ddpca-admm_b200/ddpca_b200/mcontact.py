@@ -100,18 +100,35 @@ class MCONTACT:
 
     # ------------------------------------------------------------------------------------------
     @classmethod
-    def from_ddpk(cls, d: dict, device: int = 0, smoother: int = SMOOTH_MC, muscSett=None, factorize=None):
-        """Upload everything MCONTACT::ESTABLISH built (dumped by oracle/ref_drivers/admm_hook.h)."""
+    def from_ddpk(cls, d: dict, device: int = 0, smoother: int = SMOOTH_MC, muscSett=None, factorize=None,
+                  body_rank=None, rank: int = 0, comm=None):
+        """Upload everything MCONTACT::ESTABLISH built (dumped by oracle/ref_drivers/admm_hook.h).
+
+        Multi-GPU (one process per GPU): `body_rank[v]` = owning rank (see partition.py), `rank` = this
+        process, `comm` = an object with `allreduce_sum(torch_tensor)` and `torch` device tensors for the
+        three exchange buffers (see comm.py); only the bodies / sides of this rank are uploaded."""
         lib = load_library()
         self = cls(device, smoother)
         nb, ni = int(d["nbody"][0]), int(d["niface"][0])
         self.nb, self.ni = nb, ni
         self.muscSett = int(d["muscSett"][0]) if muscSett is None else muscSett
+        self.rank = rank
+        self.comm = comm
+        self.body_rank = [0] * nb if body_rank is None else [int(r) for r in body_rank]
+        if body_rank is None:
+            self.rank = rank = 0
         h = C.c_void_p()
         check(lib.ddpca_admm_create(C.c_int(device), C.c_int(nb), C.c_int(ni), C.c_int(self.muscSett), C.byref(h)))
         self._h = h
+        if body_rank is not None:
+            br = (C.c_int * nb)(*self.body_rank)
+            check(lib.ddpca_admm_set_partition(h, br, C.c_int(rank)))
         for v in range(nb):
             p = f"body{v}."
+            self.body_dof.append(int(d[p + f"consStif{int(d[p + 'maxiLeve'][0])}.shape"][0]))
+            self.nfull.append(int(d[p + "nfull"][0]))
+            if self.body_rank[v] != rank:
+                continue
             L = int(d[p + "maxiLeve"][0])
             A = [ddpk.get_csr(d, p + f"consStif{l}") for l in range(L + 1)]
             P = [ddpk.get_csr(d, p + f"realProl{l}") for l in range(L)]
@@ -122,8 +139,6 @@ class MCONTACT:
             dispCons = np.ascontiguousarray(d[p + "dispCons"])
             check(lib.ddpca_admm_set_body(h, C.c_int(v), mg._h, C.c_int(nfull), _pd(consForc), _pi(F.rowptr), _pi(F.colidx), _pd(F.val), _pd(dispCons)))
             mg._h = None  # ownership moved to the ADMM handle
-            self.body_dof.append(A[-1].shape[0])
-            self.nfull.append(nfull)
             if self.muscSett & 1:
                 a = ddpk.get_csr(d, p + "accuProl")
                 check(lib.ddpca_admm_set_body_accuprol(h, C.c_int(v), C.c_int(a.shape[0]), C.c_int(a.shape[1]), _pi(a.rowptr), _pi(a.colidx), _pd(a.val)))
@@ -142,11 +157,13 @@ class MCONTACT:
             ncs = []
             for tv in range(2):
                 q = p + f"s{tv}."
+                ncs.append(int(d[q + "inteMass.shape"][0]))
+                if self.body_rank[cb[tv]] != rank:
+                    continue
                 nops = 10 if (self.muscSett & 1) else 7
                 for k in range(nops):
                     m = ddpk.get_csr(d, q + OPS[k])
                     check(lib.ddpca_admm_set_side_op(h, C.c_int(ts), C.c_int(tv), C.c_int(k), C.c_int(m.shape[0]), C.c_int(m.shape[1]), _pi(m.rowptr), _pi(m.colidx), _pd(m.val)))
-                ncs.append(int(d[q + "inteMass.shape"][0]))
                 for which, nm, mat in ((SOLVER_MASS, "inteDiso", "inteMass"), (SOLVER_MASS_PENA, "inteDiso_pena", "inteMass_pena")):
                     s = _factor_from_dump(d, q + nm, device, ddpk.get_csr(d, q + mat), factorize)
                     check(lib.ddpca_admm_set_side_solver(h, C.c_int(ts), C.c_int(tv), C.c_int(which), s.release()))
@@ -155,6 +172,13 @@ class MCONTACT:
             s = _factor_from_dump(d, "coarSolv_D", device, ddpk.get_csr(d, "globCoup"), factorize)
             base = np.ascontiguousarray(d["baseReco"], dtype=np.int64)
             check(lib.ddpca_admm_set_macro(h, C.c_int(s.n), base.ctypes.data_as(C.POINTER(C.c_long)), s.release()))
+        if comm is not None:
+            ng_, nt_, nm_ = C.c_long(), C.c_long(), C.c_long()
+            check(lib.ddpca_admm_exchange_sizes(h, C.byref(ng_), C.byref(nt_), C.byref(nm_)))
+            self._xbuf = comm.alloc(ng_.value, nt_.value, nm_.value)   # (globForc, traces, moni) device tensors
+            ptr = [C.c_void_p(t.data_ptr()) if t is not None and t.numel() else None for t in self._xbuf]
+            check(lib.ddpca_admm_set_exchange(h, ptr[0], ptr[1], ptr[2]))
+            check(lib.ddpca_admm_set_stream(h, C.c_void_p(comm.stream_ptr())))
         check(lib.ddpca_admm_finalize(h))
         self.row_len = int(lib.ddpca_admm_row_length(h))
         self.moniReco = [[0.0] * 10 for _ in range(nb + 4 * ni)]  # MCONTACT.h:2494-2498
@@ -177,7 +201,24 @@ class MCONTACT:
         row = np.empty(self.row_len)
         it, dofit = C.c_long(), C.c_double()
         macro = 1 if ((self.muscSett >> 0) % 2 == 1 and tc <= self.MULT_MAXI) else 0  # :2540
-        check(load_library().ddpca_admm_step(self._h, C.c_int(macro), _pd(row), C.byref(it), C.byref(dofit)))
+        lib = load_library()
+        if self.comm is None:
+            check(lib.ddpca_admm_step(self._h, C.c_int(macro), _pd(row), C.byref(it), C.byref(dofit)))
+        else:
+            # phases of the loop body with the three exchanges of SURVEY.md §8e in between
+            gl, tr, mo = self._xbuf
+            check(lib.ddpca_admm_phase(self._h, C.c_int(0)))            # body solves (local bodies)
+            if macro:
+                check(lib.ddpca_admm_phase(self._h, C.c_int(1)))        # partial coarse right-hand side
+                self.comm.allreduce_sum(gl)
+                check(lib.ddpca_admm_phase(self._h, C.c_int(2)))        # replicated coarse solve + correction
+            check(lib.ddpca_admm_phase(self._h, C.c_int(3)))            # interface side traces
+            if tr is not None and tr.numel():
+                self.comm.allreduce_sum(tr)
+            check(lib.ddpca_admm_phase(self._h, C.c_int(4)))            # projection, auxiliary and multiplier updates
+            check(lib.ddpca_admm_phase(self._h, C.c_int(5)))            # MONITOR sums
+            self.comm.allreduce_sum(mo)
+            check(lib.ddpca_admm_monitor_row(self._h, _pd(row), C.byref(it), C.byref(dofit)))
         self.cg_iters += it.value
         self.cg_dof_iters += dofit.value
         return row
@@ -234,6 +275,9 @@ class MCONTACT:
     def resuDisp(self):
         out = []
         for v in range(self.nb):
+            if self.body_rank[v] != self.rank:
+                out.append(None)   # lives on another rank
+                continue
             a = np.empty(self.nfull[v])
             check(load_library().ddpca_admm_get_disp(self._h, C.c_int(v), _pd(a)))
             out.append(a)
@@ -244,6 +288,9 @@ class MCONTACT:
         for ts in range(self.ni):
             row = []
             for tv in range(2):
+                if self.body_rank[self.contBody[ts][tv]] != self.rank:
+                    row.append(None)
+                    continue
                 a = np.empty(self.nc[ts][tv])
                 args = (_pd(a), None) if which == 0 else (None, _pd(a))
                 check(load_library().ddpca_admm_get_side(self._h, C.c_int(ts), C.c_int(tv), *args))

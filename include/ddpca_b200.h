@@ -166,6 +166,23 @@ int ddpca_admm_set_side_op(ddpca_admm *, int ts, int tv, int op, int rows, int c
 int ddpca_admm_set_side_solver(ddpca_admm *, int ts, int tv, int which, ddpca_ldlt *solver);
 /* macroscopic problem: coarSolv_D (factorised globCoup, MCONTACT.h:1229-1230) and baseReco[nbody+1] (:850-857) */
 int ddpca_admm_set_macro(ddpca_admm *, int nglob, const long *baseReco, ddpca_ldlt *coarSolv);
+/* Multi-GPU, one process per GPU: body_rank[v] = owning rank; a rank uploads only
+ * its own bodies and their interface sides (set_body / set_side_op / set_side_solver), but declares
+ * EVERY interface (set_interface) and the macroscopic solver.  Call before ddpca_admm_set_body. */
+int ddpca_admm_set_partition(ddpca_admm *, const int *body_rank, int my_rank);
+/* Device buffers the caller all-reduces (sum) between phases, e.g. torch tensors over NCCL:
+ *   globForc [nglob]   after DDPCA_PH_MACRO_PARTIAL   (MCONTACT.h:2541-2549, gather of the coarse RHS)
+ *   traces   [ntrace]  after DDPCA_PH_TRACES          (side traces of cross-rank interfaces, :2632-2635)
+ *   moni     [nmoni]   after DDPCA_PH_MONITOR         (MONITOR sums, :2737-2833)
+ * Optional on a single rank (internal buffers are used).  Call before ddpca_admm_finalize. */
+int ddpca_admm_exchange_sizes(const ddpca_admm *, long *nglob, long *ntrace, long *nmoni);
+int ddpca_admm_set_exchange(ddpca_admm *, double *globForc_dev, double *traces_dev, double *moni_dev);
+int ddpca_admm_set_stream(ddpca_admm *, void *stream);
+enum { DDPCA_PH_BODIES = 0, DDPCA_PH_MACRO_PARTIAL = 1, DDPCA_PH_MACRO_APPLY = 2, DDPCA_PH_TRACES = 3, DDPCA_PH_INTERFACE = 4, DDPCA_PH_MONITOR = 5 };
+/* enqueue one phase of the loop body on the handle's stream (ddpca_admm_step = all of them in order) */
+int ddpca_admm_phase(ddpca_admm *, int phase);
+/* after the moni buffer has been all-reduced: synchronise and assemble the resuMoni row */
+int ddpca_admm_monitor_row(ddpca_admm *, double *monitor_row, long *cg_iters, double *cg_dof_iters);
 /* checks completeness, allocates the zero initial state (MCONTACT.h:875-894) */
 int ddpca_admm_finalize(ddpca_admm *);
 /* One iteration.  apply_macro = ((muscSett>>0)%2 == 1 && tc <= MULT_MAXI) as evaluated by the

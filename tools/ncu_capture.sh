@@ -9,6 +9,9 @@ mkdir -p gpurun_out
 # no warm-up solve: the first V-cycle's launches are at known positions (see cap calls below)
 ARGS="--steps 1 --warmup 0 --no-cpu-baseline --no-profile --no-e2e $*"
 KRE='regex:k_level_pass|k_sweep|k_spmv|k_resid|k_dense|k_update|k_dot|k_s_|k_jacobi'
+# ncu cannot profile kernel nodes of graphs that contain conditional nodes: for the profiling runs the
+# CG loop falls back to one graph launch per iteration (same kernels, same launch parameters)
+export DDPCA_NO_WHILE_GRAPH=1
 python bench.py $ARGS > gpurun_out/${tag}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${tag}_plain.log; exit 1; }
 tail -c 300 gpurun_out/${tag}_plain.log; echo
 # skip the set-up V-cycle and the first CG iteration (~45 launches with v2 kernels); two iterations follow
