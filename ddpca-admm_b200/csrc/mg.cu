@@ -249,6 +249,9 @@ static int v2_blocks_per_sm(size_t dyn)
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_level_pass<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        // the chunk rings are the only consumers of the unified L1/shared array: take all of it,
+        // otherwise the driver sizes the carve-out for ~5 CTAs and the half passes lose occupancy
+        cudaFuncSetAttribute(k_level_pass<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     int nb = 0;

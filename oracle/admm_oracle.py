@@ -214,3 +214,157 @@ class AdmmOracle:
             tc += 1
         self.iterNumbReco = tc
         return tc
+
+
+class PartitionedAdmmOracle(AdmmOracle):
+    """The same loop split over ranks the way the multi-GPU product does it:
+    every rank owns some bodies and the interface sides attached to them; per iteration three
+    sum-all-reduces couple the ranks -- the coarse right-hand side, the side traces of cross-rank
+    interfaces, the MONITOR sums.  `allreduce(ndarray) -> ndarray` is supplied by the caller
+    (torch.distributed / gloo in tests).  TEST INFRASTRUCTURE: proves on CPU that the exchanged
+    data suffice and that the partitioned iteration is the reference iteration."""
+
+    def __init__(self, d, body_rank, rank, allreduce):
+        super().__init__(d)
+        self.body_rank = list(body_rank)
+        self.rank = rank
+        self.allreduce = allreduce
+        self.local_body = [r == rank for r in self.body_rank]
+
+    def _side_local(self, ts, tv):
+        return self.local_body[self.iface[ts]["contBody"][tv]]
+
+    def step(self, tc):
+        macro = (self.muscSett & 1) and tc <= self.MULT_MAXI
+        for v, b in enumerate(self.body):
+            if not self.local_body[v]:
+                continue
+            addiForc = np.zeros(b["nfull"])
+            for ts, it in enumerate(self.iface):
+                for ti in range(2):
+                    if it["contBody"][ti] == v:
+                        s = it["side"][ti]
+                        addiForc += s["systTran_pena"] @ self.inteAuxi[ts][ti] - s["systTran"] @ self.inteLagr[ts][ti]
+            u = b["solve"](b["consForc"] + b["forcOper"] @ addiForc)
+            self.resuDisp[v] = self.outp_sub1(v, u)
+        if macro:
+            globForc = np.zeros(self.globCoup.shape[0])
+            for ts, it in enumerate(self.iface):
+                for tv in range(2):
+                    if not self._side_local(ts, tv):
+                        continue
+                    s = it["side"][tv]
+                    globForc += s["globTran"] @ self.inteLagr[ts][tv] - s["globTran_pena"] @ self.inteAuxi[ts][tv] + s["globTran_D"] @ self.resuDisp[it["contBody"][tv]]
+            globForc = self.allreduce(globForc)            # exchange 1
+            globSolu = self.glob_solve(globForc)            # replicated
+            for v, b in enumerate(self.body):
+                if not self.local_body[v]:
+                    continue
+                seg = globSolu[self.baseReco[v] : self.baseReco[v] + b["accuProl"].shape[1]]
+                self.resuDisp[v] = self.resuDisp[v] + (b["forcOper"].T @ (b["accuProl"] @ seg) + b["dispCons"])
+        # side traces; cross-rank ones go through one packed all-reduce
+        traces = {}
+        packed, layout = [], []
+        for ts, it in enumerate(self.iface):
+            cross = self.body_rank[it["contBody"][0]] != self.body_rank[it["contBody"][1]]
+            for tv in range(2):
+                s = it["side"][tv]
+                if self._side_local(ts, tv):
+                    t = s["inpoLagr"] @ self.inteLagr[ts][tv] + s["pemaInpo_r"] @ self.resuDisp[it["contBody"][tv]]
+                else:
+                    t = np.zeros(it["gapTerm"].shape[0])
+                traces[(ts, tv)] = t
+                if cross:
+                    layout.append((ts, tv, len(t)))
+                    packed.append(t)
+        if packed:
+            flat = self.allreduce(np.concatenate(packed))   # exchange 2
+            off = 0
+            for ts, tv, n in layout:
+                traces[(ts, tv)] = flat[off : off + n]
+                off += n
+        for ts, it in enumerate(self.iface):
+            if not (self._side_local(ts, 0) or self._side_local(ts, 1)):
+                continue
+            g = 0.5 * (traces[(ts, 0)] - traces[(ts, 1)] - it["gapTerm"])
+            mu = it["fricCoef"]
+            stat = np.zeros(g.shape[0], dtype=np.int32)
+            if mu == 0.0:
+                g = np.maximum(0.0, g)
+            elif mu > 0.0:
+                g = g.copy()
+                g[0::3] = np.maximum(0.0, g[0::3])
+                gn, t1, t2 = g[0::3], g[1::3].copy(), g[2::3].copy()
+                nrm = np.sqrt(t1 * t1 + t2 * t2)
+                slid = mu * gn
+                open_ = ~(gn > 0.0)
+                slide = (gn > 0.0) & (nrm >= slid)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    fac = np.where(slide, slid / nrm, 1.0)
+                g[1::3], g[2::3] = np.where(open_, 0.0, t1 * fac), np.where(open_, 0.0, t2 * fac)
+                stat[1::3] = np.where(open_, 0, np.where(slide, 1, 2))
+            self.inpoGamm[ts], self.fricStat[ts] = g, stat
+            for tv, s in enumerate(it["side"]):
+                if not self._side_local(ts, tv):
+                    continue
+                u = self.resuDisp[it["contBody"][tv]]
+                inteForc = s["systTran_pena"].T @ u + s["inteMass"] @ self.inteLagr[ts][tv] + s["inteInpo"] @ g
+                self.inteAuxi[ts][tv] = s["solve_mass_pena"](inteForc)
+        for ts, it in enumerate(self.iface):
+            for tv, s in enumerate(it["side"]):
+                if not self._side_local(ts, tv):
+                    continue
+                u = self.resuDisp[it["contBody"][tv]]
+                inteForc = s["systTran_pena"].T @ u - s["inteMass_pena"] @ self.inteAuxi[ts][tv]
+                self.inteLagr[ts][tv] = self.inteLagr[ts][tv] + s["solve_mass"](inteForc)
+
+    def monitor(self, tc, disp0, auxi0, lagr0):
+        """MONITOR on all-reduced sums: every rank reaches the same decision."""
+        sums = np.zeros(2 * (self.nb + 4 * self.ni))
+        for v in range(self.nb):
+            if self.local_body[v]:
+                sums[2 * v] = float(np.sum((self.resuDisp[v] - disp0[v]) ** 2))
+                sums[2 * v + 1] = float(np.sum(self.resuDisp[v] ** 2))
+        for ts in range(self.ni):
+            for tv in range(2):
+                if not self._side_local(ts, tv):
+                    continue
+                k = self.nb + 4 * ts + 2 * tv
+                sums[2 * k] = float(np.sum((self.inteAuxi[ts][tv] - auxi0[ts][tv]) ** 2))
+                sums[2 * k + 1] = float(np.sum(self.inteAuxi[ts][tv] ** 2))
+                sums[2 * (k + 1)] = float(np.sum((self.inteLagr[ts][tv] - lagr0[ts][tv]) ** 2))
+                sums[2 * (k + 1) + 1] = float(np.sum(self.inteLagr[ts][tv] ** 2))
+        sums = self.allreduce(sums)                          # exchange 3
+        cyc = 10
+        flag0, flag1 = tc >= cyc, True
+        convValu = convCrit = 0.0
+        row = []
+        for v in range(self.nb):
+            dv, al = sums[2 * v], sums[2 * v + 1]
+            self.moniReco[v][tc % cyc] = dv
+            convValu += dv
+            convCrit += al
+            row += [dv, al]
+            if tc >= cyc:
+                medi, osci = vect_medi_osci(self.moniReco[v])
+                if osci > 0.1 * medi:
+                    flag0 = False
+            if dv > 1.0e-12 * al:
+                flag1 = False
+        for ts in range(self.ni):
+            for tv in range(2):
+                k = self.nb + 4 * ts + 2 * tv
+                da, aa, dl, la = sums[2 * k], sums[2 * k + 1], sums[2 * (k + 1)], sums[2 * (k + 1) + 1]
+                self.moniReco[k][tc % cyc] = da
+                convValu += da
+                convCrit += aa
+                row += [da, aa, dl, la]
+                if tc >= cyc:
+                    medi, osci = vect_medi_osci(self.moniReco[k])
+                    if osci > 0.1 * medi:
+                        flag0 = False
+                if da > 1.0e-12 * aa:
+                    flag1 = False
+                self.moniReco[k + 1][tc % cyc] = dl
+        row += [convValu, convCrit]
+        return row, flag0, flag1
