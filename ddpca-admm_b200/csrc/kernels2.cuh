@@ -32,6 +32,7 @@ namespace cg = cooperative_groups;
 constexpr int kChunkGroups = DDPCA_V2_GROUPS;        // row groups per chunk = consumer sub-warps per CTA
 constexpr int kV2Bufs = DDPCA_V2_BUFS;               // depth of the shared-memory ring
 constexpr int kV2Consumers = kChunkGroups * GL;      // consumer threads
+constexpr int kV2StagesSmem = 64;                     // stage tables up to this size are cached in shared memory
 constexpr int kV2Threads = kV2Consumers + 32;        // + one producer warp (one lane issues the bulk copies)
 static_assert(GL == 8, "v2 kernels assume 8-lane sub-warps");
 
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, size_t bu
     if (done && *done) return;   // uniform across the grid: no CTA reaches a barrier
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full[kV2Bufs], empty[kV2Bufs];
+    __shared__ int s_stage_chunk[kV2StagesSmem + 1];
     constexpr bool LO = (MODE != V2_BWD);
     constexpr bool UP = (MODE == V2_FWD_FULL || MODE == V2_BWD || MODE == V2_SPMV);
     constexpr bool STAGED = (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD);
@@ -253,13 +255,18 @@ __global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, size_t bu
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // the stage table is consulted for every chunk by producer and consumers: keep it on chip
+    const bool sc_smem = A.nstages <= kV2StagesSmem;
+    if (sc_smem)
+        for (int i = tid; i <= A.nstages; i += blockDim.x) s_stage_chunk[i] = A.stage_chunk[i];
     __syncthreads();
+    const int *sc = sc_smem ? s_stage_chunk : A.stage_chunk;
 
     // this CTA's chunk sequence: stage after stage, chunks c = first(stage) + blockIdx.x + j * gridDim.x
     const int nst = STAGED ? A.nstages : 1;
     auto stage_of = [&](int si) { return STAGED ? (MODE == V2_BWD ? (nst - 1 - si) : si) : 0; };
-    auto c_begin = [&](int si) { return STAGED ? A.stage_chunk[stage_of(si)] : 0; };
-    auto c_end = [&](int si) { return STAGED ? A.stage_chunk[stage_of(si) + 1] : A.nchunks; };
+    auto c_begin = [&](int si) { return STAGED ? sc[stage_of(si)] : 0; };
+    auto c_end = [&](int si) { return STAGED ? sc[stage_of(si) + 1] : A.nchunks; };
     auto settle = [&](int &si, int &c) {   // advance (si, c) to this CTA's next chunk at or after c
         while (si < nst) {
             if (c < c_end(si)) return true;
@@ -274,12 +281,21 @@ __global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, size_t bu
     if (tid >= kV2Consumers) {
         // ------------------------------- producer warp ---------------------------------------
         if (tid == kV2Consumers) {
-            for (int j = 0; settle(si, c); j++, c += (int)gridDim.x) {
+            // the descriptor of chunk j+1 is fetched before the wait for chunk j's ring slot, so
+            // that its global-memory latency never sits between a slot release and the next copy
+            bool have = settle(si, c);
+            ChunkDesc d_next;
+            if (have) d_next = A.chunks[c];
+            for (int j = 0; have; j++) {
+                const ChunkDesc d = d_next;
+                const int c_this = c;
+                c += (int)gridDim.x;
+                have = settle(si, c);
+                if (have) d_next = A.chunks[c];
                 const int slot = j % kV2Bufs;
                 if (j >= kV2Bufs) mbar_wait(&empty[slot], (uint32_t)(((j / kV2Bufs) - 1) & 1));
-                const ChunkDesc d = A.chunks[c];
                 fence_proxy_async();
-                v2_issue_chunk<MODE>(A, c, d, smem + (size_t)slot * buf_bytes, &full[slot]);
+                v2_issue_chunk<MODE>(A, c_this, d, smem + (size_t)slot * buf_bytes, &full[slot]);
             }
         }
     } else {

@@ -271,6 +271,10 @@ static int launch_v2(Engine *h, Level &L, int kclass, int l, double bytes, const
     int grid = std::min(staged ? L.max_stage_chunks : L.nchunks, cap);
     if (MODE == V2_SPMV && w) grid = std::min(grid, kNumPart);
     grid = std::max(grid, 1);
+    if (std::getenv("DDPCA_VERBOSE")) {
+        static int shown = 0;
+        if (shown++ < 40) std::fprintf(stderr, "ddpca v2: level n=%d mode=%d buf=%zu B x%d, %d CTA/SM, grid=%d, chunks=%d (max/stage %d)\n", L.n, MODE, buf, kV2Bufs, per_sm, grid, L.nchunks, L.max_stage_chunks);
+    }
     Lvl2View A = L.view2();
     unsigned *gbar = L.gbar;
     h->pre(kclass, l, bytes);
