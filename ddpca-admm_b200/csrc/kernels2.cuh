@@ -29,12 +29,28 @@ namespace cg = cooperative_groups;
 #ifndef DDPCA_V2_BUFS
 #define DDPCA_V2_BUFS 2
 #endif
+#ifndef DDPCA_V2_LANES
+#define DDPCA_V2_LANES 8
+#endif
+constexpr int GL2 = DDPCA_V2_LANES;                  // lanes per row group in the v2 kernels (8 or 16)
 constexpr int kChunkGroups = DDPCA_V2_GROUPS;        // row groups per chunk = consumer sub-warps per CTA
 constexpr int kV2Bufs = DDPCA_V2_BUFS;               // depth of the shared-memory ring
-constexpr int kV2Consumers = kChunkGroups * GL;      // consumer threads
+constexpr int kV2Consumers = kChunkGroups * GL2;     // consumer threads
 constexpr int kV2StagesSmem = 64;                     // stage tables up to this size are cached in shared memory
 constexpr int kV2Threads = kV2Consumers + 32;        // + one producer warp (one lane issues the bulk copies)
-static_assert(GL == 8, "v2 kernels assume 8-lane sub-warps");
+static_assert(GL2 == 8 || GL2 == 16 || GL2 == 32, "v2 kernels: 8, 16 or 32 lanes per row group");
+static_assert((kChunkGroups * GL2) % 32 == 0, "consumer threads must fill whole warps");
+__device__ __forceinline__ unsigned subwarp_mask2()
+{
+    const unsigned lane = threadIdx.x & 31u;
+    return (GL2 == 32) ? 0xffffffffu : (((1u << GL2) - 1u) << (lane & ~(unsigned)(GL2 - 1)));
+}
+__device__ __forceinline__ double group_sum2(double v, unsigned mask)
+{
+#pragma unroll
+    for (int o = GL2 / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
 
 // 32-byte group descriptor of the split layout
 struct __align__(16) GroupMeta2 {
@@ -180,13 +196,13 @@ __device__ __forceinline__ void v2_issue_chunk(const Lvl2View &A, int c, const C
 //           at most 40 lower / 40 upper couplings per node) -- ONE exposed L2 latency per group;
 //   phase 2 (v2_fma):    values stream from shared memory into the row sums.
 // Longer halves continue in a generic loop (v2_tail).
-constexpr int kV2Iters = 4;
+constexpr int kV2Iters = 64 / (2 * GL22) < 1 ? 1 : 64 / (2 * GL22);   // unrolled steps cover 64 pattern positions
 
 __device__ __forceinline__ void v2_gather(const int *__restrict__ pc, int n, const double *x, int sl, double (&xs)[2 * kV2Iters])
 {
 #pragma unroll
     for (int it = 0; it < kV2Iters; it++) {
-        const int k = 2 * sl + it * 2 * GL;
+        const int k = 2 * sl + it * 2 * GL2;
         xs[2 * it] = 0.0;
         xs[2 * it + 1] = 0.0;
         if (k < n) {
@@ -200,7 +216,7 @@ __device__ __forceinline__ void v2_fma(const double *__restrict__ pv, int n, int
 {
 #pragma unroll
     for (int it = 0; it < kV2Iters; it++) {
-        const int k = 2 * sl + it * 2 * GL;
+        const int k = 2 * sl + it * 2 * GL2;
         if (k < n) {
 #pragma unroll
             for (int r = 0; r < 3; r++)
@@ -214,7 +230,7 @@ __device__ __forceinline__ void v2_fma(const double *__restrict__ pv, int n, int
 __device__ __forceinline__ void v2_tail(const int *__restrict__ pc, const double *__restrict__ pv, int n, int gs,
                                         const double *x, int sl, double (&s)[3])
 {
-    for (int k = 2 * sl + kV2Iters * 2 * GL; k < n; k += 2 * GL) {
+    for (int k = 2 * sl + kV2Iters * 2 * GL2; k < n; k += 2 * GL2) {
         const int2 c = *reinterpret_cast<const int2 *>(pc + k);
         const double x0 = __ldcg(x + c.x), x1 = __ldcg(x + c.y);
 #pragma unroll
@@ -300,8 +316,8 @@ __global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, size_t bu
         }
     } else {
         // ------------------------------- consumer warps --------------------------------------
-        const int sl = tid % GL, sw = tid / GL;
-        const unsigned mask = subwarp_mask();
+        const int sl = tid % GL2, sw = tid / GL2;
+        const unsigned mask = subwarp_mask2();
         int si_done = 0;   // stage boundaries passed so far
         for (int j = 0;; j++, c += (int)gridDim.x) {
             const bool have = settle(si, c);
@@ -347,13 +363,13 @@ __global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, size_t bu
                     if (UP) v2_gather(cU, m.nu, x, sl, xu);
                     if (LO) v2_fma(vL, m.nl, gs, sl, xl, sL);
                     if (UP) v2_fma(vU, m.nu, gs, sl, xu, sU);
-                    if (LO && m.nl > kV2Iters * 2 * GL) v2_tail(cL, vL, m.nl, gs, x, sl, sL);
-                    if (UP && m.nu > kV2Iters * 2 * GL) v2_tail(cU, vU, m.nu, gs, x, sl, sU);
+                    if (LO && m.nl > kV2Iters * 2 * GL2) v2_tail(cL, vL, m.nl, gs, x, sl, sL);
+                    if (UP && m.nu > kV2Iters * 2 * GL2) v2_tail(cU, vU, m.nu, gs, x, sl, sU);
                 }
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
-                    if (LO) sL[r] = group_sum(sL[r], mask);
-                    if (UP) sU[r] = group_sum(sU[r], mask);
+                    if (LO) sL[r] = group_sum2(sL[r], mask);
+                    if (UP) sU[r] = group_sum2(sU[r], mask);
                 }
                 if (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL) {
                     double xn[3] = {0.0, 0.0, 0.0};
