@@ -196,7 +196,7 @@ __device__ __forceinline__ void v2_issue_chunk(const Lvl2View &A, int c, const C
 //           at most 40 lower / 40 upper couplings per node) -- ONE exposed L2 latency per group;
 //   phase 2 (v2_fma):    values stream from shared memory into the row sums.
 // Longer halves continue in a generic loop (v2_tail).
-constexpr int kV2Iters = 64 / (2 * GL22) < 1 ? 1 : 64 / (2 * GL22);   // unrolled steps cover 64 pattern positions
+constexpr int kV2Iters = 64 / (2 * GL2) < 1 ? 1 : 64 / (2 * GL2);   // unrolled steps cover 64 pattern positions
 
 __device__ __forceinline__ void v2_gather(const int *__restrict__ pc, int n, const double *x, int sl, double (&xs)[2 * kV2Iters])
 {
