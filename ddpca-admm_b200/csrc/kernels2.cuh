@@ -24,7 +24,7 @@ namespace ddpca {
 namespace cg = cooperative_groups;
 
 #ifndef DDPCA_V2_GROUPS
-#define DDPCA_V2_GROUPS 8
+#define DDPCA_V2_GROUPS 16
 #endif
 #ifndef DDPCA_V2_BUFS
 #define DDPCA_V2_BUFS 2
