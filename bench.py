@@ -73,6 +73,93 @@ def generate_workload(glob, ref_solve):
     return out, meta
 
 
+REF_BLOCK = os.path.join(ROOT, "oracle", "_ref", "block_admm")
+
+
+def generate_admm_workload(glob, divi):
+    """Reference host set-up of the BLOCK example (mesh, contact search, MCONTACT::ESTABLISH) plus the
+    untouched reference ADMM loop for the CPU baseline / golden results; cached in /tmp."""
+    cdir = workload_cache_dir()
+    tag = f"block_g{glob}" + (f"_d{divi.replace(',', 'x')}" if divi else "")
+    out = os.path.join(cdir, tag + ".ddpk")
+    if os.path.exists(out) and os.path.exists(out + ".json"):
+        return out, json.load(open(out + ".json"))
+    if not os.access(REF_BLOCK, os.X_OK):
+        raise SystemExit("oracle/_ref/block_admm is missing: run __graft_entry__.build() in the build container")
+    cmd = [REF_BLOCK, "--glob", str(glob), "--musc", "1", "--out", out + ".tmp", "--ref-iters", "0"]
+    if divi:
+        cmd += ["--divi", divi]
+    t0 = time.time()
+    txt = subprocess.check_output(cmd, cwd=cdir).decode()
+    meta = json.loads(txt.strip().splitlines()[-1])
+    meta["generate_wall_s"] = time.time() - t0
+    os.replace(out + ".tmp", out)
+    json.dump(meta, open(out + ".json", "w"))
+    return out, meta
+
+
+def admm_leg(args, rank, world, local, dist, torch):
+    """ADMM contact solve of the BLOCK example on `world` GPUs: bodies are partitioned over the ranks,
+    three all-reduces per iteration.  Strong scaling: the problem is fixed."""
+    import numpy as np
+
+    import ddpca_b200 as dd
+    from ddpca_b200 import ddpk
+    from ddpca_b200.comm import TorchComm
+    from ddpca_b200.partition import partition_bodies
+
+    if rank == 0:
+        path, meta = generate_admm_workload(args.admm_glob, args.admm_divi)
+    if dist is not None:
+        dist.barrier()
+    if rank != 0:
+        path, meta = generate_admm_workload(args.admm_glob, args.admm_divi)
+    d = ddpk.load(path)
+    nb, ni = int(d["nbody"][0]), int(d["niface"][0])
+    contBody = [[int(x) for x in d[f"if{ts}.contBody"]] for ts in range(ni)]
+    weights = [len(d[f"body{v}.consStif{int(d[f'body{v}.maxiLeve'][0])}.val"]) for v in range(nb)]
+    body_rank = partition_bodies(weights, contBody, world)
+    comm = TorchComm(torch.device("cuda", local)) if world > 1 else None
+    t0 = time.time()
+    mc = dd.MCONTACT.from_ddpk(d, device=local, body_rank=body_rank if world > 1 else None, rank=rank, comm=comm)
+    upload_s = time.time() - t0
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t1 = time.time()
+    mc.CONTACT_ANALYSIS()
+    torch.cuda.synchronize()
+    solve_s = time.time() - t1
+    tt = torch.tensor([solve_s], device=torch.device("cuda", local), dtype=torch.float64)
+    wk = torch.tensor([mc.cg_dof_iters, float(mc.cg_iters), float(mc.launch_count())], device=torch.device("cuda", local), dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(wk, op=dist.ReduceOp.SUM)
+    solve_s = tt.item()
+    iters = mc.iterNumbReco + 1
+    disp = mc.resuDisp
+    err = 0.0
+    for v in range(nb):
+        if disp[v] is not None and f"ref.resuDisp{v}" in d:
+            r = d[f"ref.resuDisp{v}"]
+            err = max(err, float(np.linalg.norm(disp[v] - r) / np.linalg.norm(r)))
+    et = torch.tensor([err], device=torch.device("cuda", local), dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    out = {
+        "workload": f"BLOCK domaNumb=1x1x1 globLeve={args.admm_glob}: {nb} bodies {meta['body_dof']}, {ni} interfaces (2 frictionless contact, 6 tied), macroscopic problem {meta.get('globCoup_rows')} rows",
+        "n_gpus": world, "body_rank": body_rank, "scaling": "strong",
+        "admm_iterations": iters, "reference_admm_iterations": meta.get("ref_iterNumbReco", -2) + 1,
+        "solve_wall_s": solve_s, "upload_s": upload_s, "admm_iter_per_s": iters / solve_s,
+        "mgpcg_dof_iter_per_s": wk[0].item() / solve_s, "cg_iterations_total": int(wk[1].item()), "gpu_launches": int(wk[2].item()),
+        "max_rel_err_resuDisp_vs_reference": et.item(),
+        "cpu_baseline": {"solve_wall_s": meta.get("ref_admm_s"), "kind": "reference", "cores": os.cpu_count(),
+                         "note": "untouched MCONTACT::CONTACT_ANALYSIS, OpenMP over bodies/interfaces (nested, dynamic); bodies < 50 000 DOF use host LDLT (MCONTACT.h:2527)"},
+    }
+    mc.close()
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -160,6 +247,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--admm", action="store_true", help="also run the ADMM contact solve (BLOCK example) and report it under \"admm\"")
+    ap.add_argument("--admm-glob", type=int, default=2, help="BLOCK globLeve of the ADMM leg (2: 3 x 45 725 DOF + 6 plates)")
+    ap.add_argument("--admm-divi", default="", help="BLOCK coarsest divisions a,b,c (default 6,6,6)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -285,6 +375,9 @@ def main():
                     "traffic": None, "peak_source": peak_src, "bytes_per_launch": kb / kn, "avg_launch_us": 1e3 * kms / kn,
                     "share_of_step": round(kms / tot, 4)}
 
+    admm = None
+    if args.admm:
+        admm = admm_leg(args, rank, world, local, dist, torch)
     if rank == 0:
         parity = None
         if "cg_mg_x" in d:
@@ -310,6 +403,8 @@ def main():
             "kernel_shares": shares,
             "parity_rel_err_vs_reference": parity,
         }
+        if admm is not None:
+            line["admm"] = admm
         print(json.dumps(line), flush=True)
     mg.close()
     if dist is not None:
