@@ -1015,6 +1015,9 @@ int ddpca_mg_create(int device, int nlevels, const int *n, const int *const *row
     CUC(cudaMallocHost(&h->st_host, sizeof(PcgState) * (kDepth + 2)));
     for (int k = 0; k < 3; k++) CUC(cudaMalloc(&h->partial[k], sizeof(double) * kNumPart));
     FAILC(invert_level0(h));
+    // capture + instantiate the V-cycle-preconditioned solve graph now (set-up time), not in the first solve
+    build_solve_graph(h, 1);
+    if (h->while_state[1] != 1) FAILC(build_iter_graph(h, 1));
 #undef FAILC
 #undef CUC
     *out = h;

@@ -212,3 +212,28 @@ def test_mult_solv_matches_oracle(solvers, name):
     assert rel(x, xo) < 1e-8
     if "mult_solv_x" in d:
         assert rel(x, d["mult_solv_x"]) < 1e-8
+
+
+def test_v1_v2_kernels_and_loop_drivers_agree(monkeypatch):
+    """The level kernels exist in two implementations (v1: direct loads per row group, v2: TMA-staged
+    chunks + cooperative sweep) and the CG loop in two drivers (device-side WHILE graph, host-polled
+    per-iteration graphs).  All four combinations must give the same iteration count and solution."""
+    d, meta, A, P = load_golden("beam_3lev")
+    ref = None
+    for no_v2 in ("", "1"):
+        for no_while in ("", "1"):
+            for k, v in (("DDPCA_NO_V2", no_v2), ("DDPCA_NO_WHILE_GRAPH", no_while)):
+                if v:
+                    monkeypatch.setenv(k, v)
+                else:
+                    monkeypatch.delenv(k, raising=False)
+            mg = dd.MGPIS.from_hierarchy(A, P, smoother=dd.SMOOTH_MC)
+            x = mg.CG_SOLV(1, d["consForc"])
+            it = mg.last_iterNumb
+            mg.close()
+            if ref is None:
+                ref = (x, it)
+            else:
+                assert it == ref[1]
+                assert rel(x, ref[0]) < 1e-11
+            assert rel(x, d["cg_mg_x"]) < 1e-8
