@@ -781,29 +781,35 @@ static void free_level(Level &L)
     L.x = L.b = L.p1 = L.r = L.dinv = nullptr;
 }
 
-static int invert_level0(ddpca_mg *h)
+// Dense inverse of an SPD operator given as device CSR: in-place Gauss-Jordan + symmetrisation
+// (set-up only).  *Binv is allocated here.
+static int dense_spd_inverse(cudaStream_t st, const DevCsr &A, double **Binv)
 {
-    Level &L0 = h->lev[0];
-    int n = L0.n;
-    h->n0 = n;
-    if (n > 32768) return fail("level 0 has " + std::to_string(n) + " rows; the dense direct solver supports <= 32768");
-    CU(cudaMalloc(&h->Binv, sizeof(double) * (size_t)n * n));
-    CU(cudaMemsetAsync(h->Binv, 0, sizeof(double) * (size_t)n * n, h->stream));
+    int n = A.rows;
+    CU(cudaMalloc(Binv, sizeof(double) * (size_t)n * n));
+    CU(cudaMemsetAsync(*Binv, 0, sizeof(double) * (size_t)n * n, st));
     double *rowk, *colk;
     CU(cudaMalloc(&rowk, sizeof(double) * n));
     CU(cudaMalloc(&colk, sizeof(double) * n));
-    k_csr_to_dense<<<cdiv(n, 128), 128, 0, h->stream>>>(L0.A.view(), n, h->Binv);
+    k_csr_to_dense<<<cdiv(n, 128), 128, 0, st>>>(A.view(), n, *Binv);
     dim3 g2(cdiv(n, 256), n);
     for (int k = 0; k < n; k++) {
-        k_gj_pivot<<<cdiv(n, 256), 256, 0, h->stream>>>(n, k, h->Binv, rowk, colk);
-        k_gj_update<<<g2, 256, 0, h->stream>>>(n, k, h->Binv, rowk, colk);
+        k_gj_pivot<<<cdiv(n, 256), 256, 0, st>>>(n, k, *Binv, rowk, colk);
+        k_gj_update<<<g2, 256, 0, st>>>(n, k, *Binv, rowk, colk);
     }
-    k_symmetrize<<<g2, 256, 0, h->stream>>>(n, h->Binv);
-    CU(cudaStreamSynchronize(h->stream));
+    k_symmetrize<<<g2, 256, 0, st>>>(n, *Binv);
+    CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     cudaFree(rowk);
     cudaFree(colk);
     return 0;
+}
+static int invert_level0(ddpca_mg *h)
+{
+    Level &L0 = h->lev[0];
+    h->n0 = L0.n;
+    if (L0.n > 32768) return fail("level 0 has " + std::to_string(L0.n) + " rows; the dense direct solver supports <= 32768");
+    return dense_spd_inverse(h->stream, L0.A, &h->Binv);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -819,11 +825,16 @@ struct ddpca_ldlt : Engine {
     Level lo, up;
     int *m_in = nullptr, *m_mid = nullptr, *m_out = nullptr;  // composed index maps
     double *dinv_lo = nullptr;                                 // 1/D in lo numbering
+    double *Binv = nullptr;                                    // small SPD operators: dense inverse, solve = one GEMV
 };
 
 static void ldlt_solve_on(Engine *e, ddpca_ldlt *s, const double *b_dev, double *x_dev, const int *done)
 {
     int n = s->n;
+    if (s->Binv) {
+        KL(e, DDPCA_K_COARSE, 0, 8.0 * n * (double)n + 16.0 * n, (k_dense_gemv<<<cdiv((long)n * 32, 256), 256, 0, e->stream>>>(n, s->Binv, b_dev, x_dev, done)));
+        return;
+    }
     double tri_bytes = 12.0 * s->nnzL + 44.0 * n;
     KL(e, DDPCA_K_VECTOR, 0, 20.0 * n, (k_scatter<<<cdiv(n, 256), 256, 0, e->stream>>>(n, s->m_in, b_dev, s->lo.b)));
     (void)tri_bytes;
@@ -838,7 +849,7 @@ static void ldlt_free(ddpca_ldlt *s)
     if (!s) return;
     cudaSetDevice(s->device);
     free_level(s->lo); free_level(s->up);
-    cudaFree(s->m_in); cudaFree(s->m_mid); cudaFree(s->m_out); cudaFree(s->dinv_lo);
+    cudaFree(s->m_in); cudaFree(s->m_mid); cudaFree(s->m_out); cudaFree(s->dinv_lo); cudaFree(s->Binv);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -1272,6 +1283,33 @@ int ddpca_ldlt_create(int device, int n, const int *perm, const int *L_rowptr, c
 {
     if (!out || n < 1 || !perm || !L_rowptr || !L_colidx || !L_val || !D) return fail("ddpca_ldlt_create: bad argument");
     return ldlt_build(device, n, perm, L_rowptr, L_colidx, L_val, D, out);
+}
+int ddpca_ldlt_create_dense(int device, int n, const int *rowptr, const int *colidx, const double *val, ddpca_ldlt **out)
+{
+    if (!out || n < 1 || n > 16384 || !rowptr || !colidx || !val) return fail("ddpca_ldlt_create_dense: bad argument (n must be <= 16384)");
+    int ndev = ddpca_device_count();
+    if (ndev == 0) return fail("no CUDA device: libddpca_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("device index out of range");
+    CU(cudaSetDevice(device));
+    CsrHost A;
+    A.rows = A.cols = n;
+    A.rp.assign(rowptr, rowptr + n + 1);
+    A.ci.assign(colidx, colidx + rowptr[n]);
+    A.v.assign(val, val + rowptr[n]);
+    ddpca_ldlt *s = new ddpca_ldlt();
+    s->device = device;
+    s->n = n;
+    s->nnzL = rowptr[n];
+    cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail("stream creation failed"); }
+    s->stream = s->own_stream;
+    DevCsr dA;
+    if (upload_csr(A, dA) || dense_spd_inverse(s->stream, dA, &s->Binv)) { free_csr(dA); ldlt_free(s); return 1; }
+    free_csr(dA);
+    // work vectors for the host-pointer entry point
+    if (cudaMalloc(&s->lo.r, sizeof(double) * n) != cudaSuccess || cudaMalloc(&s->up.r, sizeof(double) * n) != cudaSuccess) { ldlt_free(s); return fail("out of device memory"); }
+    *out = s;
+    return 0;
 }
 int ddpca_ldlt_destroy(ddpca_ldlt *s) { ldlt_free(s); return 0; }
 int ddpca_ldlt_solve_dev(ddpca_ldlt *s, const double *b_dev, double *x_dev)

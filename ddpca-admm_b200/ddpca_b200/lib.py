@@ -26,7 +26,7 @@ EXPORTS = [
     "ddpca_mg_coarse_solve", "ddpca_mg_mult_solv", "ddpca_mg_bicgstab",
     "ddpca_mg_level_info", "ddpca_mg_launch_count", "ddpca_mg_set_stream",
     "ddpca_mg_profile", "ddpca_mg_profile_get", "ddpca_mg_last_timing",
-    "ddpca_ldlt_create", "ddpca_ldlt_solve", "ddpca_ldlt_solve_dev", "ddpca_ldlt_info", "ddpca_ldlt_destroy",
+    "ddpca_ldlt_create", "ddpca_ldlt_create_dense", "ddpca_ldlt_solve", "ddpca_ldlt_solve_dev", "ddpca_ldlt_info", "ddpca_ldlt_destroy",
     "ddpca_admm_create", "ddpca_admm_set_body", "ddpca_admm_set_body_accuprol", "ddpca_admm_set_interface",
     "ddpca_admm_set_side_op", "ddpca_admm_set_side_solver", "ddpca_admm_set_macro", "ddpca_admm_finalize",
     "ddpca_admm_step", "ddpca_admm_row_length", "ddpca_admm_get_disp", "ddpca_admm_get_side", "ddpca_admm_get_gamma",

@@ -30,6 +30,19 @@ class DIRE_SOLV:
     """A factorised Eigen::SimplicialLDLT (typedef DIRE_SOLV, PREP.h:107) whose solve phase runs
     on the device: perm = permutationP().indices(), L = strictly-lower unit factor (CSR), D = vectorD()."""
 
+    DENSE_MAX = 4096   # below this size an SPD operator is inverted densely on the device (one GEMV per solve)
+
+    @classmethod
+    def dense(cls, A: ddpk.Csr, device: int = 0):
+        """Small SPD operator given as a matrix: dense inverse on the device, no host factor needed."""
+        self = cls.__new__(cls)
+        self.n = int(A.shape[0])
+        h = C.c_void_p()
+        check(load_library().ddpca_ldlt_create_dense(C.c_int(device), C.c_int(self.n), _pi(A.rowptr), _pi(A.colidx), _pd(A.val), C.byref(h)))
+        self._h = h
+        self._owned = True
+        return self
+
     def __init__(self, perm, L: ddpk.Csr, D, device: int = 0):
         lib = load_library()
         self.n = int(L.shape[0])
@@ -69,6 +82,8 @@ class DIRE_SOLV:
 
 
 def _factor_from_dump(d, name, device, fallback_matrix=None, factorize=None):
+    if fallback_matrix is not None and fallback_matrix.shape[0] <= DIRE_SOLV.DENSE_MAX:
+        return DIRE_SOLV.dense(fallback_matrix, device)
     if name + ".perm" in d:
         return DIRE_SOLV(d[name + ".perm"], ddpk.get_csr(d, name + ".L"), d[name + ".D"], device)
     if factorize is None:

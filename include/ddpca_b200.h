@@ -118,6 +118,9 @@ int ddpca_mg_bicgstab(ddpca_mg *, int prec, const double *b, double *x, double r
 typedef struct ddpca_ldlt ddpca_ldlt;
 int ddpca_ldlt_create(int device, int n, const int *perm, const int *L_rowptr, const int *L_colidx, const double *L_val,
                       const double *D, ddpca_ldlt **out);
+/* Small SPD operators (interface mass matrices, n <= 16384): no host factor needed -- the dense
+ * inverse is built on the device and every solve is one GEMV. */
+int ddpca_ldlt_create_dense(int device, int n, const int *rowptr, const int *colidx, const double *val, ddpca_ldlt **out);
 int ddpca_ldlt_solve(ddpca_ldlt *, const double *b, double *x);
 int ddpca_ldlt_solve_dev(ddpca_ldlt *, const double *b_dev, double *x_dev);
 int ddpca_ldlt_info(const ddpca_ldlt *, int *n, long *nnzL, int *stages_fwd, int *stages_bwd);
