@@ -143,23 +143,27 @@ constexpr int GL = DDPCA_GROUP_LANES;
 #define DDPCA_PRAGMA(x) _Pragma(#x)
 #define DDPCA_UNROLL_LOOP(n) DDPCA_PRAGMA(unroll n)
 
-__device__ __forceinline__ unsigned subwarp_mask()
+template <int LN>
+__device__ __forceinline__ unsigned subwarp_mask_t()
 {
     const unsigned lane = threadIdx.x & 31u;
-    return (GL == 32) ? 0xffffffffu : (((1u << GL) - 1u) << (lane & ~(unsigned)(GL - 1)));
+    return (LN == 32) ? 0xffffffffu : (((1u << (LN & 31)) - 1u) << (lane & ~(unsigned)(LN - 1)));
 }
-__device__ __forceinline__ double group_sum(double v, unsigned mask)
+template <int LN>
+__device__ __forceinline__ double group_sum_t(double v, unsigned mask)
 {
 #pragma unroll
-    for (int o = GL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    for (int o = LN / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
     return v;
 }
+__device__ __forceinline__ unsigned subwarp_mask() { return subwarp_mask_t<GL>(); }
+__device__ __forceinline__ double group_sum(double v, unsigned mask) { return group_sum_t<GL>(v, mask); }
 
 // Partial sums of one row group over the pattern range selected by LOWER / UPPER:
 //   sL[r] = sum_{k <  kd}      a_r[k] x[c_k]      sU[r] = sum_{k >= kd+gs} a_r[k] x[c_k]
 // Lane sl of the sub-warp owns pattern positions (2*sl, 2*sl+1) + 2*GL*it: one 8-byte index
 // load, gs 16-byte value loads and one x gather pair per step.
-template <bool LOWER, bool UPPER, bool NC_X>
+template <bool LOWER, bool UPPER, bool NC_X, int LN = GL>
 __device__ __forceinline__ void group_partial(const LvlView &A, const GroupMeta &m, const double *x, int sl,
                                               double (&sL)[3], double (&sU)[3])
 {
@@ -169,7 +173,7 @@ __device__ __forceinline__ void group_partial(const LvlView &A, const GroupMeta 
     const int kbeg = LOWER ? 0 : (ku & ~1);
     const int kend = UPPER ? len : kd;   // exclusive; entries >= kend are never needed
     DDPCA_UNROLL_LOOP(DDPCA_UNROLL)
-    for (int k = kbeg + 2 * sl; k < kend; k += 2 * GL) {
+    for (int k = kbeg + 2 * sl; k < kend; k += 2 * LN) {
         const int2 c = ld_stream2(ci + k);
         double2 a[3];
 #pragma unroll
@@ -197,7 +201,7 @@ __device__ __forceinline__ void group_partial(const LvlView &A, const GroupMeta 
 // ZERO_X: x is known to be zero on entry (first smoothing of a V-cycle, MGPIS.h:93,204):
 //         the strictly-upper half is not read at all.
 // ------------------------------------------------------------------------------------
-template <bool ZERO_X, bool NC_X>
+template <bool ZERO_X, bool NC_X, int LN = GL>
 __device__ __forceinline__ void group_fwd(const LvlView &A, int g, const double *__restrict__ b,
                                           double *x, double *__restrict__ p1, int sl, unsigned mask)
 {
@@ -216,11 +220,11 @@ __device__ __forceinline__ void group_fwd(const LvlView &A, int g, const double 
 #pragma unroll
         for (int c = 0; c < 3; c++) blk[r][c] = (r < gs && c < gs) ? __ldg(vb + (size_t)r * m.len + c) : 0.0;
     }
-    group_partial<true, !ZERO_X, NC_X>(A, m, x, sl, sL, sU);
+    group_partial<true, !ZERO_X, NC_X, LN>(A, m, x, sl, sL, sU);
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        sL[r] = group_sum(sL[r], mask);
-        if (!ZERO_X) sU[r] = group_sum(sU[r], mask);
+        sL[r] = group_sum_t<LN>(sL[r], mask);
+        if (!ZERO_X) sU[r] = group_sum_t<LN>(sU[r], mask);
     }
     // sequential in-group solve, done redundantly by every lane (no divergence); lane 0 stores
     double xn[3] = {0.0, 0.0, 0.0};
@@ -244,7 +248,7 @@ __device__ __forceinline__ void group_fwd(const LvlView &A, int g, const double 
 }
 
 // K4: backward relaxation of one row group (MGPIS.h:73-76):  x_i = (p1_i - sum_{j>i} a_ij x_j) / a_ii
-template <bool NC_X>
+template <bool NC_X, int LN = GL>
 __device__ __forceinline__ void group_bwd(const LvlView &A, int g, const double *__restrict__ p1,
                                           double *x, int sl, unsigned mask)
 {
@@ -259,9 +263,9 @@ __device__ __forceinline__ void group_bwd(const LvlView &A, int g, const double 
 #pragma unroll
         for (int c = 0; c < 3; c++) blk[r][c] = (r < gs && c < gs && c >= r) ? __ldg(vb + (size_t)r * m.len + c) : 0.0;
     }
-    group_partial<false, true, NC_X>(A, m, x, sl, sL, sU);
+    group_partial<false, true, NC_X, LN>(A, m, x, sl, sL, sU);
 #pragma unroll
-    for (int r = 0; r < 3; r++) sU[r] = group_sum(sU[r], mask);
+    for (int r = 0; r < 3; r++) sU[r] = group_sum_t<LN>(sU[r], mask);
     double xn[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int r = 2; r >= 0; r--) {
@@ -298,29 +302,32 @@ __global__ void __launch_bounds__(256, DDPCA_MIN_BLOCKS) k_sweep_bwd_stage(LvlVi
 
 // a run of small stages [s0,s1) relaxed by ONE CTA, __syncthreads() between stages
 // (latency-bound regime: LEX wavefronts, coarse levels, triangular solves)
-template <bool ZERO_X>
+// LN lanes per row group: 8 for multigrid levels (rows of <= 81 entries), 32 for the triangular
+// factors of the direct solves (fill-in rows of thousands of entries on a sequential dependency chain)
+template <bool ZERO_X, int LN>
 __global__ void __launch_bounds__(512) k_sweep_fwd_multi(LvlView A, const int *__restrict__ stage_group, int s0, int s1,
                                                           const double *__restrict__ b, double *x, double *p1, const int *done)
 {
     if (done && *done) return;
-    const int sl = threadIdx.x % GL, w = threadIdx.x / GL, nw = blockDim.x / GL;
-    const unsigned mask = subwarp_mask();
+    const int sl = threadIdx.x % LN, w = threadIdx.x / LN, nw = blockDim.x / LN;
+    const unsigned mask = subwarp_mask_t<LN>();
     for (int s = s0; s < s1; s++) {
         const int ga = stage_group[s], gb = stage_group[s + 1];
-        for (int g = ga + w; g < gb; g += nw) group_fwd<ZERO_X, false>(A, g, b, x, p1, sl, mask);
+        for (int g = ga + w; g < gb; g += nw) group_fwd<ZERO_X, false, LN>(A, g, b, x, p1, sl, mask);
         __syncthreads();
     }
 }
 
+template <int LN>
 __global__ void __launch_bounds__(512) k_sweep_bwd_multi(LvlView A, const int *__restrict__ stage_group, int s0, int s1,
                                                           const double *p1, double *x, const int *done)
 {
     if (done && *done) return;
-    const int sl = threadIdx.x % GL, w = threadIdx.x / GL, nw = blockDim.x / GL;
-    const unsigned mask = subwarp_mask();
+    const int sl = threadIdx.x % LN, w = threadIdx.x / LN, nw = blockDim.x / LN;
+    const unsigned mask = subwarp_mask_t<LN>();
     for (int s = s1 - 1; s >= s0; s--) {
         const int ga = stage_group[s], gb = stage_group[s + 1];
-        for (int g = ga + w; g < gb; g += nw) group_bwd<false>(A, g, p1, x, sl, mask);
+        for (int g = ga + w; g < gb; g += nw) group_bwd<false, LN>(A, g, p1, x, sl, mask);
         __syncthreads();
     }
 }

@@ -73,6 +73,7 @@ struct Level {
     long val_entries = 0;  // values stored (sum of gs * padded len)
     int *stage_group = nullptr, *perm = nullptr;
     std::vector<Segment> segs;
+    bool wide_rows = false;   // triangular factors: one full warp per row in the single-CTA stage runs
     DevCsr P, R;  // level l <-> l-1 (l >= 1)
     double *x = nullptr, *b = nullptr, *p1 = nullptr, *r = nullptr, *dinv = nullptr;
     double bytes_lower = 0, bytes_upper = 0, bytes_full = 0;  // algorithmic bytes of one pass over a half / the whole level
@@ -315,8 +316,13 @@ static void sweep_fwd(Engine *h, Level &L, int l, const double *b, double *x, bo
             if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_stage<true><<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, b, x, L.p1, done)));
             else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_stage<false><<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, b, x, L.p1, done)));
         } else {
-            if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<true><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
-            else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<false><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+            if (L.wide_rows) {
+                if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<true, 32><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+                else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<false, 32><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+            } else {
+                if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<true, GL><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+                else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<false, GL><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+            }
         }
     }
 }
@@ -333,7 +339,8 @@ static void sweep_bwd(Engine *h, Level &L, int l, double *x, const int *done)
             int grid = cdiv((long)ng * GL, 256);
             KL(h, DDPCA_K_SWEEP_BWD, l, s.bytes_up, (k_sweep_bwd_stage<<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, L.p1, x, done)));
         } else {
-            KL(h, DDPCA_K_SWEEP_BWD, l, s.bytes_up, (k_sweep_bwd_multi<<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, L.p1, x, done)));
+            if (L.wide_rows) KL(h, DDPCA_K_SWEEP_BWD, l, s.bytes_up, (k_sweep_bwd_multi<32><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, L.p1, x, done)));
+            else KL(h, DDPCA_K_SWEEP_BWD, l, s.bytes_up, (k_sweep_bwd_multi<GL><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, L.p1, x, done)));
         }
     }
 }
@@ -892,6 +899,7 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
     cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device);
     if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail("stream creation failed"); }
     s->stream = s->own_stream;
+    s->lo.wide_rows = s->up.wide_rows = ((double)Lrp[n] / n > 48.0);   // long fill-in rows
     if (setup_level(s->lo, n, Tlo.rp.data(), Tlo.ci.data(), Tlo.v.data(), DDPCA_SMOOTH_LEX, false, true) ||
         setup_level(s->up, n, Tup.rp.data(), Tup.ci.data(), Tup.v.data(), DDPCA_SMOOTH_LEX, false, true)) { ldlt_free(s); return 1; }
     std::vector<int> m_in(n), m_mid(n), m_out(n);
