@@ -332,6 +332,74 @@ __global__ void __launch_bounds__(512) k_sweep_bwd_multi(LvlView A, const int *_
     }
 }
 
+// Triangular solve with a unit-diagonal factor stored as a LEX-staged level of single-row groups
+// (I+L forward, I+L^T backward): one CTA of 32 warps walks the dependency wavefronts.  Stages with
+// many rows give each warp its own rows; stages with few rows -- the long fill-in rows at the end of
+// the elimination, which sit on ONE sequential dependency chain -- split every row over several
+// warps, so a 3000-entry row costs one load round trip instead of fifty.
+//   FWD: x_i = b_i - sum_{j<i} l_ij x_j          BWD: x_i = b_i - sum_{j>i} l_ji x_j
+template <bool FWD>
+__global__ void __launch_bounds__(1024) k_tri_multi(LvlView A, const int *__restrict__ stage_group, int s0, int s1,
+                                                     const double *__restrict__ b, double *x, const int *done)
+{
+    if (done && *done) return;
+    __shared__ double part[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int si = 0; si < s1 - s0; si++) {
+        const int s = FWD ? (s0 + si) : (s1 - 1 - si);
+        const int ga = stage_group[s], ng = stage_group[s + 1] - ga;
+        if (ng >= nw) {
+            for (int g = ga + w; g < ga + ng; g += nw) {
+                const GroupMeta m = ld_meta(A.meta + g);
+                const int kb = FWD ? 0 : ((m.kd + 1) & ~1), ke = FWD ? m.kd : m.len;
+                const int *ci = A.ci + m.cptr;
+                const double *v = A.v + m.voff;
+                double acc = 0.0;
+#pragma unroll 2
+                for (int k = kb + 2 * lane; k < ke; k += 64) {
+                    const int2 c = ld_stream2(ci + k);
+                    const double2 a = ld_stream2(v + k);
+                    if (FWD) { acc += a.x * x[c.x]; if (k + 1 < ke) acc += a.y * x[c.y]; }
+                    else { if (k > m.kd) acc += a.x * x[c.x]; acc += a.y * x[c.y]; }
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) x[m.row0] = b[m.row0] - acc;
+            }
+            __syncthreads();
+        } else {
+            // wpg warps per row
+            int wpg = 1;
+            while (wpg * 2 * ng <= nw) wpg *= 2;
+            const int gi = w / wpg, slice = w % wpg;
+            double acc = 0.0;
+            GroupMeta m;
+            m.row0 = 0;
+            if (gi < ng) {
+                m = ld_meta(A.meta + ga + gi);
+                const int kb = FWD ? 0 : ((m.kd + 1) & ~1), ke = FWD ? m.kd : m.len;
+                const int *ci = A.ci + m.cptr;
+                const double *v = A.v + m.voff;
+#pragma unroll 2
+                for (int k = kb + 2 * (slice * 32 + lane); k < ke; k += 64 * wpg) {
+                    const int2 c = ld_stream2(ci + k);
+                    const double2 a = ld_stream2(v + k);
+                    if (FWD) { acc += a.x * x[c.x]; if (k + 1 < ke) acc += a.y * x[c.y]; }
+                    else { if (k > m.kd) acc += a.x * x[c.x]; acc += a.y * x[c.y]; }
+                }
+                acc = warp_sum(acc);
+            }
+            if (lane == 0) part[w] = acc;
+            __syncthreads();
+            if (gi < ng && slice == 0 && lane == 0) {
+                double t = 0.0;
+                for (int q = 0; q < wpg; q++) t += part[gi * wpg + q];
+                x[m.row0] = b[m.row0] - t;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // K2: r = b - (p1 + L x)   (MGPIS.h:92) -- strictly-lower half only, one sub-warp per group
 __global__ void __launch_bounds__(256, DDPCA_MIN_BLOCKS) k_resid_lower(LvlView A, const double *__restrict__ b, const double *__restrict__ p1,
                                                      const double *__restrict__ x, double *__restrict__ r, const int *done)

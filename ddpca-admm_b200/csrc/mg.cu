@@ -833,6 +833,7 @@ struct ddpca_ldlt : Engine {
     int *m_in = nullptr, *m_mid = nullptr, *m_out = nullptr;  // composed index maps
     double *dinv_lo = nullptr;                                 // 1/D in lo numbering
     double *Binv = nullptr;                                    // small SPD operators: dense inverse, solve = one GEMV
+    bool single_rows = false;                                  // every group is one row: k_tri_multi applies
 };
 
 static void ldlt_solve_on(Engine *e, ddpca_ldlt *s, const double *b_dev, double *x_dev, const int *done)
@@ -845,9 +846,25 @@ static void ldlt_solve_on(Engine *e, ddpca_ldlt *s, const double *b_dev, double 
     double tri_bytes = 12.0 * s->nnzL + 44.0 * n;
     KL(e, DDPCA_K_VECTOR, 0, 20.0 * n, (k_scatter<<<cdiv(n, 256), 256, 0, e->stream>>>(n, s->m_in, b_dev, s->lo.b)));
     (void)tri_bytes;
-    sweep_fwd(e, s->lo, 0, s->lo.b, s->lo.x, true, done);
+    if (s->single_rows) {
+        // runs of small wavefronts: one CTA, rows split over warps (k_tri_multi); large wavefronts: one launch each
+        for (const Segment &sg : s->lo.segs) {
+            if (sg.multi) KL(e, DDPCA_K_SWEEP_FWD, 0, sg.bytes_lo, (k_tri_multi<true><<<1, 1024, 0, e->stream>>>(s->lo.view(), s->lo.stage_group, sg.s0, sg.s1, s->lo.b, s->lo.x, done)));
+            else KL(e, DDPCA_K_SWEEP_FWD, 0, sg.bytes_lo, (k_sweep_fwd_stage<true><<<cdiv((long)(sg.g1 - sg.g0) * GL, 256), 256, 0, e->stream>>>(s->lo.view(), sg.g0, sg.g1, s->lo.b, s->lo.x, s->lo.p1, done)));
+        }
+    } else {
+        sweep_fwd(e, s->lo, 0, s->lo.b, s->lo.x, true, done);
+    }
     KL(e, DDPCA_K_VECTOR, 0, 28.0 * n, (k_scatter_scaled<<<cdiv(n, 256), 256, 0, e->stream>>>(n, s->m_mid, s->dinv_lo, s->lo.x, s->up.p1)));
-    sweep_bwd(e, s->up, 0, s->up.x, done);
+    if (s->single_rows) {
+        for (int k = (int)s->up.segs.size() - 1; k >= 0; k--) {
+            const Segment &sg = s->up.segs[k];
+            if (sg.multi) KL(e, DDPCA_K_SWEEP_BWD, 0, sg.bytes_up, (k_tri_multi<false><<<1, 1024, 0, e->stream>>>(s->up.view(), s->up.stage_group, sg.s0, sg.s1, s->up.p1, s->up.x, done)));
+            else KL(e, DDPCA_K_SWEEP_BWD, 0, sg.bytes_up, (k_sweep_bwd_stage<<<cdiv((long)(sg.g1 - sg.g0) * GL, 256), 256, 0, e->stream>>>(s->up.view(), sg.g0, sg.g1, s->up.p1, s->up.x, done)));
+        }
+    } else {
+        sweep_bwd(e, s->up, 0, s->up.x, done);
+    }
     KL(e, DDPCA_K_VECTOR, 0, 20.0 * n, (k_gather<<<cdiv(n, 256), 256, 0, e->stream>>>(n, s->m_out, s->up.x, x_dev)));
 }
 
@@ -902,6 +919,7 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
     s->lo.wide_rows = s->up.wide_rows = ((double)Lrp[n] / n > 48.0);   // long fill-in rows
     if (setup_level(s->lo, n, Tlo.rp.data(), Tlo.ci.data(), Tlo.v.data(), DDPCA_SMOOTH_LEX, false, true) ||
         setup_level(s->up, n, Tup.rp.data(), Tup.ci.data(), Tup.v.data(), DDPCA_SMOOTH_LEX, false, true)) { ldlt_free(s); return 1; }
+    s->single_rows = (s->lo.plan.ngroups() == n && s->up.plan.ngroups() == n);
     std::vector<int> m_in(n), m_mid(n), m_out(n);
     std::vector<double> dinv(n);
     for (int i = 0; i < n; i++) {
