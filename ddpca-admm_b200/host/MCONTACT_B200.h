@@ -1,0 +1,271 @@
+// MCONTACT_B200.h -- B200 drop-in for MCONTACT::CONTACT_ANALYSIS (/root/reference/MCONTACT.h:2493-2723).
+//
+// Include AFTER the reference's MCONTACT.h (and with the MGPIS overlay force-included, see
+// INTEGRATION.md).  DDPCA_CONTACT_ANALYSIS(mc) does what mc.CONTACT_ANALYSIS() does -- same state
+// members on return (resuDisp, inteAuxi, inteLagr, iterNumbReco), same resuMoni.txt rows, same
+// console lines per iteration, same final resuCont_<ts>.txt -- with the loop body on the GPU:
+//   1. upload, once, everything MCONTACT::ESTABLISH built (MCONTACT.h:29-46, :864-872) through the
+//      C ABI of include/ddpca_b200.h; the host factorisations of ESTABLISH become device solvers;
+//   2. iterate ddpca_admm_step(); MONITOR (MCONTACT.h:2725-2845) is restated below on the sums the
+//      device returns (the reference's MONITOR needs the full state vectors on the host);
+//   3. read the state back.
+// Defining DDPCA_HOOK_CONTACT_ANALYSIS before including this file additionally redirects every later
+// call `CONTACT_ANALYSIS()` written inside a member function (e.g. examples/BLOCK.h:707) to the
+// drop-in, so that the reference's examples run unchanged.
+#ifndef _MCONTACT_B200_H
+#define _MCONTACT_B200_H
+
+#include "ddpca_b200.h"
+
+#ifndef _MCONTACT_H
+#error "include the reference's MCONTACT.h before MCONTACT_B200.h"
+#endif
+
+namespace ddpca_host {
+
+typedef Eigen::SparseMatrix<double,Eigen::RowMajor> SPM;
+
+inline bool FAIL(const char *what){
+	std::cout << "MCONTACT::CONTACT_ANALYSIS (B200): ERROR " << what << ": " << ddpca_last_error() << std::endl;
+	return false;
+}
+
+// a factorised DIRE_SOLV (Eigen::SimplicialLDLT) -> device solver; small SPD operators are
+// inverted densely on the device instead (no factor needed)
+inline ddpca_ldlt *UPLOAD_SOLVER(int devi, const DIRE_SOLV &solv, const SPM &matr){
+	ddpca_ldlt *resu = nullptr;
+	if(matr.rows() <= 4096){
+		SPM tempMatr = matr;
+		tempMatr.makeCompressed();
+		if(ddpca_ldlt_create_dense(devi, tempMatr.rows(), tempMatr.outerIndexPtr(),
+			tempMatr.innerIndexPtr(), tempMatr.valuePtr(), &resu) != 0){
+			return nullptr;
+		}
+		return resu;
+	}
+	SPM lowe = solv.matrixL().nestedExpression();// strictly lower, unit diagonal implied
+	lowe.makeCompressed();
+	Eigen::VectorXd diag = solv.vectorD();
+	std::vector<int> perm(solv.rows());
+	for(long ti = 0; ti < solv.rows(); ti ++){
+		perm[ti] = solv.permutationP().indices()(ti);
+	}
+	if(ddpca_ldlt_create(devi, lowe.rows(), perm.data(), lowe.outerIndexPtr(),
+		lowe.innerIndexPtr(), lowe.valuePtr(), diag.data(), &resu) != 0){
+		return nullptr;
+	}
+	return resu;
+}
+
+inline bool UPLOAD_OP(ddpca_admm *hand, long ts, long tv, int opid, const SPM &matr){
+	SPM tempMatr = matr;
+	tempMatr.makeCompressed();
+	return ddpca_admm_set_side_op(hand, ts, tv, opid, tempMatr.rows(), tempMatr.cols(),
+		tempMatr.outerIndexPtr(), tempMatr.innerIndexPtr(), tempMatr.valuePtr()) == 0;
+}
+
+}// namespace ddpca_host
+
+inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
+	using namespace ddpca_host;
+	const int devi = MGPIS::DEVICE();
+	const long bodyNumb = mc.multGrid.size(), inteNumb = mc.searCont.size();
+	if((mc.muscSett >> 1) % 2 == 1){
+		std::cout << "MCONTACT::CONTACT_ANALYSIS (B200): ERROR interface-eliminated problem "
+			<< "(muscSett bit 1) is not offered by the B200 build" << std::endl;
+		return -1;
+	}
+	const bool macrSwit = ((mc.muscSett >> 0) % 2 == 1);
+	if(macrSwit && mc.globCoup.rows() >= DIRE_MAXI){
+		std::cout << "MCONTACT::CONTACT_ANALYSIS (B200): ERROR macroscopic problem beyond DIRE_MAXI "
+			<< "is not offered by the B200 build" << std::endl;
+		return -1;
+	}
+	ddpca_admm *hand = nullptr;
+	if(ddpca_admm_create(devi, bodyNumb, inteNumb, macrSwit ? 1 : 0, &hand) != 0){
+		FAIL("create"); return -1;
+	}
+	bool allGood = true;
+	//******************************** upload (once) ********************************************
+	for(long tv = 0; tv < bodyNumb && allGood; tv ++){
+		MULTIGRID &mugr = mc.multGrid[tv];
+		const long maxiLeve = mugr.mgpi.maxiLeve;
+		// ADDITIONAL_FORCE as one operator (MULTIGRID.h:1257-1261); OUTP_SUB1 = its transpose + constant
+		SPM forcOper = mugr.consOper[maxiLeve] * SPM(mugr.prolOper[maxiLeve].transpose())
+			* SPM(mugr.earlTran.transpose());
+		forcOper.makeCompressed();
+		Eigen::VectorXd dispCons;
+		mugr.OUTP_SUB1(Eigen::VectorXd::Zero(forcOper.rows()), dispCons);
+		ddpca_mg *mgHand = mugr.mgpi.RELEASE_HANDLE();
+		if(mgHand == nullptr || ddpca_admm_set_body(hand, tv, mgHand, 3 * mugr.nodeCoor.size(),
+			mugr.consForc.data(), forcOper.outerIndexPtr(), forcOper.innerIndexPtr(),
+			forcOper.valuePtr(), dispCons.data()) != 0){
+			allGood = FAIL("set_body");
+			break;
+		}
+		if(macrSwit){
+			SPM accu = mc.accuProl[tv];
+			accu.makeCompressed();
+			if(ddpca_admm_set_body_accuprol(hand, tv, accu.rows(), accu.cols(),
+				accu.outerIndexPtr(), accu.innerIndexPtr(), accu.valuePtr()) != 0){
+				allGood = FAIL("set_body_accuprol");
+			}
+		}
+	}
+	for(long ts = 0; ts < inteNumb && allGood; ts ++){
+		Eigen::VectorXd gapTerm = mc.pemaInpo[ts] * mc.inpoNgap[ts];// MCONTACT.h:2636
+		if(ddpca_admm_set_interface(hand, ts, mc.contBody[ts][0], mc.contBody[ts][1], mc.fricCoef[ts],
+			mc.searCont[ts].intePoin.size(), gapTerm.data()) != 0){
+			allGood = FAIL("set_interface");
+			break;
+		}
+		for(long tv = 0; tv < 2 && allGood; tv ++){
+			allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_SYSTTRAN, mc.systTran[ts][tv]);
+			allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_SYSTTRAN_PENA, mc.systTran_pena[ts][tv]);
+			allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_INTEMASS, mc.inteMass[ts][tv]);
+			allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_INTEMASS_PENA, mc.inteMass_pena[ts][tv]);
+			allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_INPOLAGR, mc.inpoLagr[ts][tv]);
+			allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_INTEINPO, mc.inteInpo[ts][tv]);
+			allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_PEMAINPO_R, mc.pemaInpo_r[ts][tv]);
+			if(macrSwit){
+				allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_GLOBTRAN, mc.globTran[ts][tv]);
+				allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_GLOBTRAN_PENA, mc.globTran_pena[ts][tv]);
+				allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_GLOBTRAN_D, mc.globTran_D[ts][tv]);
+			}
+			if(!allGood){ FAIL("set_side_op"); break; }
+			if(mc.inteMass[ts][tv].rows() >= DIRE_MAXI){// MCONTACT.h:2676-2683: per-iteration Eigen CG
+				std::cout << "MCONTACT::CONTACT_ANALYSIS (B200): ERROR interface beyond DIRE_MAXI" << std::endl;
+				allGood = false; break;
+			}
+			ddpca_ldlt *soMa = UPLOAD_SOLVER(devi, mc.inteDiso[ts][tv], mc.inteMass[ts][tv]);
+			ddpca_ldlt *soPe = UPLOAD_SOLVER(devi, mc.inteDiso_pena[ts][tv], mc.inteMass_pena[ts][tv]);
+			if(soMa == nullptr || soPe == nullptr
+				|| ddpca_admm_set_side_solver(hand, ts, tv, DDPCA_SOLVER_MASS, soMa) != 0
+				|| ddpca_admm_set_side_solver(hand, ts, tv, DDPCA_SOLVER_MASS_PENA, soPe) != 0){
+				allGood = FAIL("set_side_solver");
+			}
+		}
+	}
+	if(allGood && macrSwit){
+		ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D, mc.globCoup);
+		if(soCo == nullptr || ddpca_admm_set_macro(hand, mc.globCoup.rows(), mc.baseReco.data(), soCo) != 0){
+			allGood = FAIL("set_macro");
+		}
+	}
+	if(allGood && ddpca_admm_finalize(hand) != 0){
+		allGood = FAIL("finalize");
+	}
+	if(!allGood){
+		ddpca_admm_destroy(hand);
+		return -1;
+	}
+	//******************************** the loop, MCONTACT.h:2494-2712 ***************************
+	const long moniCycl = 10;
+	VECTOR2D moniReco(bodyNumb + 4 * inteNumb);
+	for(long ti = 0; ti < moniReco.size(); ti ++){
+		moniReco[ti].assign(moniCycl, 0.0);
+	}
+	long tc;
+	const long maxiIter = 3000;
+	std::ofstream tempOfst(DIRECTORY("resuMoni.txt"), std::ios::out);
+	tempOfst << std::setiosflags(std::ios::scientific) << std::setprecision(20);
+	std::vector<double> moniRow(ddpca_admm_row_length(hand));
+	for(tc = 0; tc < maxiIter; tc ++){
+		std::cout << "The " << tc << "-th iteration";
+		OUTPUT_TIME("");
+		const int applMacr = (macrSwit && tc <= MULT_MAXI) ? 1 : 0;// :2540
+		long cgitNumb = 0;
+		if(ddpca_admm_step(hand, applMacr, moniRow.data(), &cgitNumb, nullptr) != 0){
+			FAIL("step");
+			ddpca_admm_destroy(hand);
+			return -1;
+		}
+		//stopping criterion: MONITOR (:2725-2845) on the sums computed by the device
+		bool tempFlag_0 = (tc >= moniCycl) ? true : false;
+		bool tempFlag_1 = true;
+		const double critRati_0 = 0.1, critRati_1 = 1.0E-12;
+		long tempColu = 0;
+		for(long tv = 0; tv < bodyNumb; tv ++){
+			const double dispVari = moniRow[tempColu], dispAllo = moniRow[tempColu + 1];
+			tempColu += 2;
+			moniReco[tv][tc % moniCycl] = dispVari;
+			tempOfst << std::setw(30) << dispVari << std::setw(30) << dispAllo;
+			if(tc >= moniCycl){
+				double dispMedi, dispOsci;
+				VECT_MEDI_OSCI(moniReco[tv], dispMedi, dispOsci);
+				if(dispOsci > critRati_0 * dispMedi){
+					tempFlag_0 = false;
+				}
+			}
+			if(dispVari > critRati_1 * dispAllo){
+				tempFlag_1 = false;
+			}
+		}
+		for(long ts = 0; ts < inteNumb; ts ++){
+			for(long tv = 0; tv < 2; tv ++){
+				const long tempIndi = bodyNumb + 4 * ts + 2 * tv;
+				const double auxiVari = moniRow[tempColu], auxiAllo = moniRow[tempColu + 1];
+				const double lagrVari = moniRow[tempColu + 2], lagrAllo = moniRow[tempColu + 3];
+				tempColu += 4;
+				moniReco[tempIndi][tc % moniCycl] = auxiVari;
+				moniReco[tempIndi + 1][tc % moniCycl] = lagrVari;
+				tempOfst << std::setw(30) << auxiVari << std::setw(30) << auxiAllo
+					<< std::setw(30) << lagrVari << std::setw(30) << lagrAllo;
+				if(tc >= moniCycl){
+					double auxiMedi, auxiOsci;
+					VECT_MEDI_OSCI(moniReco[tempIndi], auxiMedi, auxiOsci);
+					if(auxiOsci > critRati_0 * auxiMedi){
+						tempFlag_0 = false;
+					}
+				}
+				if(auxiVari > critRati_1 * auxiAllo){
+					tempFlag_1 = false;
+				}
+				//the multiplier criteria are evaluated but disabled in the reference (:2822,:2830)
+			}
+		}
+		const double convValu = moniRow[tempColu], convCrit = moniRow[tempColu + 1];
+		std::cout << "Cvalu = " << convValu << ", Ccrit = " << convCrit << std::endl;
+		tempOfst << std::setw(30) << convValu << std::setw(30) << convCrit;
+		tempOfst << std::endl;
+		if(tempFlag_0 == true){
+			MULT_MAXI = tc;// :2838-2840
+		}
+		if(tempFlag_1 == true){
+			break;// :2709-2711
+		}
+	}
+	tempOfst.close();
+	mc.iterNumbReco = tc;
+	//******************************** state back to the host members *****************************
+	for(long tv = 0; tv < bodyNumb; tv ++){
+		mc.resuDisp[tv].resize(3 * mc.multGrid[tv].nodeCoor.size());
+		ddpca_admm_get_disp(hand, tv, mc.resuDisp[tv].data());
+	}
+	for(long ts = 0; ts < inteNumb; ts ++){
+		for(long tv = 0; tv < 2; tv ++){
+			ddpca_admm_get_side(hand, ts, tv, mc.inteAuxi[ts][tv].data(), mc.inteLagr[ts][tv].data());
+		}
+		//final contact pressure/traction file, what OUTPUT_PRTR writes each iteration (:2669)
+		const long gammSize = ((mc.fricCoef[ts] == 0.0) ? 1 : 3) * mc.searCont[ts].intePoin.size();
+		Eigen::VectorXd inpoGamm(gammSize);
+		Eigen::VectorXi fricStat(gammSize);
+		ddpca_admm_get_gamma(hand, ts, inpoGamm.data(), fricStat.data());
+		mc.OUTPUT_PRTR(inpoGamm, fricStat, ts);
+	}
+	ddpca_admm_destroy(hand);
+	if(tc >= maxiIter){
+		std::cout << "Nonconvergence in MCONTACT::CONTACT_ANALYSIS";
+	}
+	else{
+		std::cout << "Converge after " << tc << "-th iterations";
+	}
+	OUTPUT_TIME("");
+	return 1;
+}
+
+#ifdef DDPCA_HOOK_CONTACT_ANALYSIS
+#define CONTACT_ANALYSIS() DDPCA_CONTACT_ANALYSIS(*this)
+#endif
+
+#endif
