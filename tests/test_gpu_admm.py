@@ -135,3 +135,34 @@ def test_block_g2_small_25_iterations_against_reference_run_here():
             p_ref = _moni(d, f"ref.resuCont{ts}")[:, 0]
             assert rel(g, p_ref) < 1e-8 and ((g > 0) == (p_ref > 0)).all()
     mc.close()
+
+
+def test_coulomb_friction_projection_matches_oracle(block_small):
+    """The reference's frictional branch (MCONTACT.h:2648-2668: normal clamp, Coulomb cone, status
+    0 open / 1 slide / 2 stick) is only reached by DEHW.  Here two vector-valued (d = 3) interfaces of
+    the BLOCK fixture are declared frictional in BOTH the oracle and the device loop: same operators,
+    same algebra, so states and status codes must agree."""
+    from oracle.admm_oracle import AdmmOracle
+
+    d, meta = block_small
+    d = dict(d)
+    for ts, mu in ((0, 0.3), (3, 0.05)):
+        assert float(d[f"if{ts}.fricCoef"][0]) < 0.0          # tied: three components per point
+        d[f"if{ts}.fricCoef"] = np.array([mu])
+    o = AdmmOracle(d)
+    o.muscSett = 0
+    mc = dd.MCONTACT.from_ddpk(d, muscSett=0, factorize=dense_ldlt_factor)
+    for tc in range(6):
+        o.step(tc)
+        mc.step(tc)
+    seen = set()
+    for ts in (0, 3):
+        g, st = mc.inpoGamm(ts)
+        assert rel(g, o.inpoGamm[ts]) < 1e-8
+        assert np.array_equal(st[1::3], o.fricStat[ts][1::3])  # friction status per integration point
+        seen |= set(st[1::3].tolist())
+    assert len(seen) >= 2                                      # more than one branch was exercised
+    disp = mc.resuDisp
+    for v in range(mc.nb):
+        assert rel(disp[v], o.resuDisp[v]) < 1e-8
+    mc.close()
