@@ -371,8 +371,16 @@ def main():
                                          "GBps": round(kb / (kms * 1e-3) / 1e9, 1) if kms > 0 else None}
         (kname, lvl), (kms, kn, kb) = best
         ach = kb / (kms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload, from the
+        # committed `ncu --set full` capture (profiles/NCU_TRAFFIC.json); null for kernels / workloads not captured
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "NCU_TRAFFIC.json")))
+            traffic = tr.get(f"beam_g{args.glob}", {}).get(f"{kname}@L{lvl}")
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": f"{kname}@L{lvl}", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                    "traffic": None, "peak_source": peak_src, "bytes_per_launch": kb / kn, "avg_launch_us": 1e3 * kms / kn,
+                    "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": kb / kn, "avg_launch_us": 1e3 * kms / kn,
                     "share_of_step": round(kms / tot, 4)}
 
     admm = None

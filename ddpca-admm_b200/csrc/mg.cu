@@ -304,24 +304,25 @@ static int launch_level_spmv(Engine *h, Level &L, int l, const double *x, double
 static void sweep_fwd(Engine *h, Level &L, int l, const double *b, double *x, bool zero_x, const int *done)
 {
     if (L.v2) {
-        if (zero_x) launch_v2<V2_FWD_ZERO>(h, L, DDPCA_K_SWEEP_FWD, l, L.bytes_lower, b, x, L.p1, nullptr, nullptr, nullptr, done);
+        if (zero_x) launch_v2<V2_FWD_ZERO>(h, L, DDPCA_K_SWEEP_FWD0, l, L.bytes_lower, b, x, L.p1, nullptr, nullptr, nullptr, done);
         else launch_v2<V2_FWD_FULL>(h, L, DDPCA_K_SWEEP_FWD, l, L.bytes_lower + L.bytes_upper, b, x, L.p1, nullptr, nullptr, nullptr, done);
         return;
     }
+    const int kc = zero_x ? DDPCA_K_SWEEP_FWD0 : DDPCA_K_SWEEP_FWD;
     for (const Segment &s : L.segs) {
         double bytes = s.bytes_lo + (zero_x ? 0.0 : s.bytes_up);
         if (!s.multi) {
             int ng = s.g1 - s.g0;
             int grid = cdiv((long)ng * GL, 256);
-            if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_stage<true><<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, b, x, L.p1, done)));
-            else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_stage<false><<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, b, x, L.p1, done)));
+            if (zero_x) KL(h, kc, l, bytes, (k_sweep_fwd_stage<true><<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, b, x, L.p1, done)));
+            else KL(h, kc, l, bytes, (k_sweep_fwd_stage<false><<<grid, 256, 0, h->stream>>>(L.view(), s.g0, s.g1, b, x, L.p1, done)));
         } else {
             if (L.wide_rows) {
-                if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<true, 32><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
-                else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<false, 32><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+                if (zero_x) KL(h, kc, l, bytes, (k_sweep_fwd_multi<true, 32><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+                else KL(h, kc, l, bytes, (k_sweep_fwd_multi<false, 32><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
             } else {
-                if (zero_x) KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<true, GL><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
-                else KL(h, DDPCA_K_SWEEP_FWD, l, bytes, (k_sweep_fwd_multi<false, GL><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+                if (zero_x) KL(h, kc, l, bytes, (k_sweep_fwd_multi<true, GL><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
+                else KL(h, kc, l, bytes, (k_sweep_fwd_multi<false, GL><<<1, 512, 0, h->stream>>>(L.view(), L.stage_group, s.s0, s.s1, b, x, L.p1, done)));
             }
         }
     }

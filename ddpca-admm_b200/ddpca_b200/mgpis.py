@@ -10,7 +10,7 @@ from .lib import check, load_library
 
 SMOOTH_LEX = 0
 SMOOTH_MC = 1
-KERNEL_CLASSES = ["spmv", "sweep_fwd", "sweep_bwd", "resid", "restrict", "prolong", "coarse", "vector"]
+KERNEL_CLASSES = ["spmv", "sweep_fwd", "sweep_bwd", "resid", "restrict", "prolong", "coarse", "vector", "sweep_fwd0"]
 
 
 def _pi(a):

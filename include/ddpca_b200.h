@@ -47,7 +47,8 @@ enum {
     DDPCA_K_PROLONG = 5,   /* K6  x += P e                      MGPIS.h:100        */
     DDPCA_K_COARSE = 6,    /* K7  x0 = A0^-1 b0                 MGPIS.h:58         */
     DDPCA_K_VECTOR = 7,    /* K8  axpy / dot / norm             MGPIS.h:197-214    */
-    DDPCA_K_COUNT = 8
+    DDPCA_K_SWEEP_FWD0 = 8,/* K3  forward sweep from x = 0 (lower half only)   MGPIS.h:93,204 + :66-72 */
+    DDPCA_K_COUNT = 9
 };
 
 typedef struct ddpca_mg ddpca_mg;
