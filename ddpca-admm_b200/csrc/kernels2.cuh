@@ -137,7 +137,13 @@ __device__ __forceinline__ void consumer_bar_sync()
     asm volatile("bar.sync 1, %0;" ::"n"(kV2Consumers) : "memory");
 }
 // Grid-wide barrier among the consumer threads of all CTAs of a cooperative launch (all CTAs are
-// co-resident).  Self-resetting: gbar[0] = arrival count, gbar[1] = generation.
+// co-resident).  Two-level and self-resetting: CTAs arrive on one of kGbarFan counters (separate
+// 128-byte lines, so the L2 atomic units work in parallel instead of serialising ~700 arrivals on
+// one address), the last arrival of each counter arrives on the root, the last root arrival bumps
+// the generation everybody polls.  Layout: gbar[0] root count, gbar[1] generation,
+// gbar[32 * (1 + k)] counter k.
+constexpr int kGbarFan = 32;
+constexpr int kGbarWords = 32 * (1 + kGbarFan);
 __device__ __forceinline__ void consumer_grid_barrier(unsigned *gbar)
 {
     consumer_bar_sync();
@@ -145,13 +151,20 @@ __device__ __forceinline__ void consumer_grid_barrier(unsigned *gbar)
         volatile unsigned *vg = gbar;
         const unsigned gen = vg[1];
         __threadfence();
-        if (atomicAdd(&gbar[0], 1u) == gridDim.x - 1) {
-            vg[0] = 0;
+        const unsigned nsub = gridDim.x < (unsigned)kGbarFan ? gridDim.x : (unsigned)kGbarFan;
+        const unsigned sub = blockIdx.x % nsub;
+        const unsigned sub_size = (gridDim.x - sub + nsub - 1) / nsub;
+        unsigned *cnt = gbar + 32 * (1 + sub);
+        if (atomicAdd(cnt, 1u) == sub_size - 1) {
+            *((volatile unsigned *)cnt) = 0;
             __threadfence();
-            atomicAdd(&gbar[1], 1u);
-        } else {
-            while (vg[1] == gen) { __nanosleep(20); }
+            if (atomicAdd(&gbar[0], 1u) == nsub - 1) {
+                vg[0] = 0;
+                __threadfence();
+                atomicAdd(&gbar[1], 1u);
+            }
         }
+        while (vg[1] == gen) { }
         __threadfence();
     }
     consumer_bar_sync();

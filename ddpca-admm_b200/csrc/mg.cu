@@ -763,8 +763,8 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
             L.nchunks = (int)H2.chunks.size();
             L.max_stage_chunks = H2.max_stage_chunks;
             L.buf_lo = H2.buf_lo; L.buf_up = H2.buf_up; L.buf_full = H2.buf_full;
-            CU(cudaMalloc(&L.gbar, 2 * sizeof(unsigned)));
-            CU(cudaMemset(L.gbar, 0, 2 * sizeof(unsigned)));
+            CU(cudaMalloc(&L.gbar, kGbarWords * sizeof(unsigned)));
+            CU(cudaMemset(L.gbar, 0, kGbarWords * sizeof(unsigned)));
             if (upload_vec(H2.meta, &L.meta2) || upload_vec(H2.CL, &L.CL) || upload_vec(H2.CU, &L.CU) || upload_vec(H2.VL, &L.VL) ||
                 upload_vec(H2.VU, &L.VU) || upload_vec(H2.BD, &L.BD) || upload_vec(H2.chunks, &L.chunks) || upload_vec(H2.stage_chunk, &L.stage_chunk)) return 1;
         } else {
