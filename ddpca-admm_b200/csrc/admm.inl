@@ -19,6 +19,7 @@ struct AdmmBody {
     double *disp = nullptr, *disp_prev = nullptr, *addi = nullptr, *rhs = nullptr, *u = nullptr;
     bool set = false;
     bool local = true;     // owned by this rank (multi-GPU: one process per GPU)
+    cudaEvent_t ev_done = nullptr;   // end of this body's solve on its own stream
 };
 struct AdmmSide {
     DevCsr op[10];
@@ -55,6 +56,7 @@ struct ddpca_admm : Engine {
     double *moni_host = nullptr;
     int nslots = 0;
     bool finalized = false;
+    cudaEvent_t ev_fork = nullptr;
     // multi-rank: ownership + externally provided exchange buffers (device memory the caller all-reduces)
     std::vector<int> body_rank;
     int my_rank = 0;
@@ -73,7 +75,9 @@ static void admm_free(ddpca_admm *h)
         if (b.mg) ddpca_mg_destroy(b.mg);
         cudaFree(b.consForc); cudaFree(b.dispCons); free_csr(b.F); free_csr(b.FT); free_csr(b.accuProl);
         cudaFree(b.disp); cudaFree(b.disp_prev); cudaFree(b.addi); cudaFree(b.rhs); cudaFree(b.u);
+        if (b.ev_done) cudaEventDestroy(b.ev_done);
     }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (auto &f : h->iface) {
         cudaFree(f.gap); cudaFree(f.t); cudaFree(f.gamma); cudaFree(f.stat);
         for (auto &s : f.side) {
@@ -126,34 +130,58 @@ enum { PH_BODIES = 0, PH_MACRO_PARTIAL = 1, PH_MACRO_APPLY = 2, PH_TRACES = 3, P
 static double *glob_buf(ddpca_admm *h) { return h->x_glob ? h->x_glob : h->globForc; }
 static double *moni_buf(ddpca_admm *h) { return h->x_moni ? h->x_moni : h->moni_out; }
 
-// body balance, MCONTACT.h:2511-2538 (local bodies)
+// body balance, MCONTACT.h:2511-2538 (local bodies).  The reference runs this loop under
+// `#pragma omp parallel for` (:2511); here every body is enqueued on its own stream (right-hand side,
+// the whole MG-PCG solve as one graph launch, expansion to nodal displacements) so that small
+// subdomains, which cannot fill the GPU alone, overlap; the ADMM stream joins them afterwards.
 static int admm_bodies(ddpca_admm *h)
 {
     cudaStream_t st = h->stream;
     h->cg_iters = 0;
     h->cg_dof_iters = 0;
+    if (!h->ev_fork) CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventRecord(h->ev_fork, st));
+    const bool overlap = !h->profile && !std::getenv("DDPCA_SERIAL_BODIES");
     for (int v = 0; v < h->nb; v++) {
         AdmmBody &b = h->body[v];
         if (!b.local) continue;
-        CU(cudaMemcpyAsync(b.disp_prev, b.disp, sizeof(double) * b.nfull, cudaMemcpyDeviceToDevice, st));  // :2507
-        CU(cudaMemsetAsync(b.addi, 0, sizeof(double) * b.nfull, st));                                       // :2514
-        for (int ts = 0; ts < h->ni; ts++)
-            for (int ti = 0; ti < 2; ti++) {
-                AdmmIface &f = h->iface[ts];
-                if (f.body[ti] != v) continue;
-                ADMM_SPMV(f.side[ti].op[DDPCA_OP_SYSTTRAN_PENA], f.side[ti].aux, b.addi, true, 1.0);   // :2520
-                ADMM_SPMV(f.side[ti].op[DDPCA_OP_SYSTTRAN], f.side[ti].lagr, b.addi, true, -1.0);      // :2521
-            }
-        CU(cudaMemcpyAsync(b.rhs, b.consForc, sizeof(double) * b.nred, cudaMemcpyDeviceToDevice, st));
-        ADMM_SPMV(b.F, b.addi, b.rhs, true, 1.0);   // ADDITIONAL_FORCE :2524 ; consForc + addiForc :2531
+        cudaStream_t bs = overlap ? b.mg->own_stream : st;
+        if (overlap) {
+            CU(cudaStreamWaitEvent(bs, h->ev_fork, 0));
+            if (!b.ev_done) CU(cudaEventCreateWithFlags(&b.ev_done, cudaEventDisableTiming));
+        }
+        h->stream = bs;   // the helper kernels of this body go to its stream
+        ddpca_mg_set_stream(b.mg, (void *)bs);
+        int rc = 0;
+        do {
+            if (cudaMemcpyAsync(b.disp_prev, b.disp, sizeof(double) * b.nfull, cudaMemcpyDeviceToDevice, bs) != cudaSuccess) { rc = 1; break; }  // :2507
+            if (cudaMemsetAsync(b.addi, 0, sizeof(double) * b.nfull, bs) != cudaSuccess) { rc = 1; break; }                                       // :2514
+            for (int ts = 0; ts < h->ni; ts++)
+                for (int ti = 0; ti < 2; ti++) {
+                    AdmmIface &f = h->iface[ts];
+                    if (f.body[ti] != v) continue;
+                    ADMM_SPMV(f.side[ti].op[DDPCA_OP_SYSTTRAN_PENA], f.side[ti].aux, b.addi, true, 1.0);   // :2520
+                    ADMM_SPMV(f.side[ti].op[DDPCA_OP_SYSTTRAN], f.side[ti].lagr, b.addi, true, -1.0);      // :2521
+                }
+            if (cudaMemcpyAsync(b.rhs, b.consForc, sizeof(double) * b.nred, cudaMemcpyDeviceToDevice, bs) != cudaSuccess) { rc = 1; break; }
+            ADMM_SPMV(b.F, b.addi, b.rhs, true, 1.0);   // ADDITIONAL_FORCE :2524 ; consForc + addiForc :2531
+            if (pcg_device(b.mg, 1, b.rhs, b.u, 1.0e-14, b.nred, nullptr, nullptr, nullptr, /*no_wait=*/true)) { rc = 1; break; }   // :2531 (MG-PCG for every body)
+            if (cudaMemcpyAsync(b.disp, b.dispCons, sizeof(double) * b.nfull, cudaMemcpyDeviceToDevice, bs) != cudaSuccess) { rc = 1; break; }
+            ADMM_SPMV(b.FT, b.u, b.disp, true, 1.0);    // OUTP_SUB1 :2533
+            if (overlap && cudaEventRecord(b.ev_done, bs) != cudaSuccess) { rc = 1; break; }
+        } while (0);
+        h->stream = st;
+        if (rc) return fail("ddpca_admm: enqueue of body " + std::to_string(v) + " failed: " + cudaGetErrorString(cudaGetLastError()) + " " + g_err);
+    }
+    for (int v = 0; v < h->nb; v++) {
+        AdmmBody &b = h->body[v];
+        if (!b.local) continue;
         long it = 0;
-        ddpca_mg_set_stream(b.mg, (void *)st);
-        if (pcg_device(b.mg, 1, b.rhs, b.u, 1.0e-14, b.nred, &it, nullptr, nullptr)) return 1;   // :2531 (MG-PCG for every body)
+        if (pcg_finish(b.mg, &it, nullptr, nullptr)) return 1;
+        if (overlap) CU(cudaStreamWaitEvent(st, b.ev_done, 0));
         h->launches += ddpca_mg_launch_count(b.mg, 1);
         h->cg_iters += it;
         h->cg_dof_iters += (double)it * b.nred;
-        CU(cudaMemcpyAsync(b.disp, b.dispCons, sizeof(double) * b.nfull, cudaMemcpyDeviceToDevice, st));
-        ADMM_SPMV(b.FT, b.u, b.disp, true, 1.0);    // OUTP_SUB1 :2533
     }
     return 0;
 }

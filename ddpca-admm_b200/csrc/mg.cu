@@ -170,6 +170,8 @@ struct ddpca_mg : Engine {
     cudaGraphExec_t solve_graph[2] = {nullptr, nullptr};
     long solve_init_nodes[2] = {0, 0}, solve_iter_nodes[2] = {0, 0};
     int while_state[2] = {0, 0};   // 0 untried, 1 available, -1 unavailable (host-polled loop is used)
+    bool pending_while = false;
+    int pending_prec = 1;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double t_solve = 0, t_h2d = 0, t_d2h = 0;
 };
@@ -493,9 +495,22 @@ static int build_iter_graph(ddpca_mg *h, int prec)
     return 0;
 }
 
+// wait for a solve enqueued by pcg_device and read its scalars back
+static int pcg_finish(ddpca_mg *h, long *iters, double *resid, double *tol_abs)
+{
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->profile) h->prof_collect();
+    if (h->pending_while) h->launches += h->solve_init_nodes[h->pending_prec] + (long)h->st_host[0].it * h->solve_iter_nodes[h->pending_prec];
+    if (iters) *iters = (long)h->st_host[0].it;
+    if (resid) *resid = std::sqrt(h->st_host[0].rr);
+    if (tol_abs) *tol_abs = h->st_host[0].tol;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // CG_SOLV on device vectors: b_ref/x_ref in REFERENCE numbering, resident on the device
 static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref, double rel_tol, long maxit,
-                      long *iters, double *resid, double *tol_abs)
+                      long *iters, double *resid, double *tol_abs, bool no_wait = false)
 {
     if (prec != 0 && prec != 1) return fail("prec must be 0 (Jacobi) or 1 (V-cycle)");
     int Lf = h->nlev - 1;
@@ -555,14 +570,10 @@ static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref,
     // x (device numbering) -> reference numbering
     KL(h, DDPCA_K_VECTOR, Lf, 20.0 * n, (k_scatter<<<cdiv(n, 256), 256, 0, h->stream>>>(n, L.perm, h->cg_x, x_ref)));
     CU(cudaMemcpyAsync(&h->st_host[0], h->st, sizeof(PcgState), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    if (h->profile) h->prof_collect();
-    if (use_while) h->launches += h->solve_init_nodes[prec] + (long)h->st_host[0].it * h->solve_iter_nodes[prec];
-    if (iters) *iters = (long)h->st_host[0].it;
-    if (resid) *resid = std::sqrt(h->st_host[0].rr);
-    if (tol_abs) *tol_abs = h->st_host[0].tol;
-    CU(cudaGetLastError());
-    return 0;
+    h->pending_while = use_while;
+    h->pending_prec = prec;
+    if (no_wait) return 0;   // the caller overlaps several solves and calls pcg_finish() later
+    return pcg_finish(h, iters, resid, tol_abs);
 }
 
 // ------------------------------------------------------------------------------------------
