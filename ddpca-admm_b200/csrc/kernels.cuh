@@ -508,6 +508,53 @@ __global__ void __launch_bounds__(256) k_dense_gemv(int n, const double *__restr
     if (lane == 0) y[i] = s;
 }
 
+// ---- dense tail of a sparse LDL^T factor (setup): M = L22 diag(D2) L22^T, 32x32 tiles ----------
+__global__ void __launch_bounds__(1024) k_ldl_tail_product(int T, const double *__restrict__ L22, const double *__restrict__ D2, double *__restrict__ M)
+{
+    __shared__ double sa[32][33], sb[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.y * 32 + ty, j = blockIdx.x * 32 + tx;
+    if (blockIdx.x > blockIdx.y) return;   // lower triangle of tiles; mirrored below
+    double acc = 0.0;
+    const int kmax = min(blockIdx.x * 32 + 32, T);   // L22 is lower triangular: k <= j
+    for (int k0 = 0; k0 < kmax; k0 += 32) {
+        const int ia = blockIdx.y * 32 + ty, ka = k0 + tx;
+        sa[ty][tx] = (ia < T && ka < T) ? L22[(size_t)ia * T + ka] * D2[ka] : 0.0;
+        const int jb = blockIdx.x * 32 + ty, kb = k0 + tx;
+        sb[ty][tx] = (jb < T && kb < T) ? L22[(size_t)jb * T + kb] : 0.0;
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; k++) acc += sa[ty][k] * sb[tx][k];
+        __syncthreads();
+    }
+    if (i < T && j < T) {
+        M[(size_t)i * T + j] = acc;
+        M[(size_t)j * T + i] = acc;
+    }
+}
+// tail right-hand side: out[i - n1] = b[i] - sum_{k < k1[i-n1]} l_ik y_k   (couplings to the sparse part)
+__global__ void __launch_bounds__(256) k_tail_rhs(LvlView A, int g0, int T, const int *__restrict__ k1, const double *__restrict__ b,
+                                                   const double *__restrict__ y, double *__restrict__ out, const int *done)
+{
+    if (done && *done) return;
+    const int lane = threadIdx.x & 31;
+    const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (t >= T) return;
+    const GroupMeta m = ld_meta(A.meta + g0 + t);
+    const int *ci = A.ci + m.cptr;
+    const double *v = A.v + m.voff;
+    const int ke = k1[t];
+    double acc = 0.0;
+    for (int k = 2 * lane; k < ke; k += 64) {
+        const int2 c = ld_stream2(ci + k);
+        const double2 a = ld_stream2(v + k);
+        acc += a.x * y[c.x];
+        if (k + 1 < ke) acc += a.y * y[c.y];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[t] = b[m.row0] - acc;
+}
+
 // ---- dense in-place Gauss-Jordan inversion of the SPD level-0 operator (setup only) ----
 __global__ void k_gj_pivot(int n, int k, const double *__restrict__ a, double *__restrict__ rowk, double *__restrict__ colk)
 {

@@ -802,6 +802,24 @@ static void free_level(Level &L)
 
 // Dense inverse of an SPD operator given as device CSR: in-place Gauss-Jordan + symmetrisation
 // (set-up only).  *Binv is allocated here.
+// in-place Gauss-Jordan inversion + symmetrisation of a dense SPD matrix already on the device
+static int dense_invert_inplace(cudaStream_t st, int n, double *B)
+{
+    double *rowk, *colk;
+    CU(cudaMalloc(&rowk, sizeof(double) * n));
+    CU(cudaMalloc(&colk, sizeof(double) * n));
+    dim3 g2(cdiv(n, 256), n);
+    for (int k = 0; k < n; k++) {
+        k_gj_pivot<<<cdiv(n, 256), 256, 0, st>>>(n, k, B, rowk, colk);
+        k_gj_update<<<g2, 256, 0, st>>>(n, k, B, rowk, colk);
+    }
+    k_symmetrize<<<g2, 256, 0, st>>>(n, B);
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    cudaFree(rowk);
+    cudaFree(colk);
+    return 0;
+}
 static int dense_spd_inverse(cudaStream_t st, const DevCsr &A, double **Binv)
 {
     int n = A.rows;
@@ -846,6 +864,11 @@ struct ddpca_ldlt : Engine {
     double *dinv_lo = nullptr;                                 // 1/D in lo numbering
     double *Binv = nullptr;                                    // small SPD operators: dense inverse, solve = one GEMV
     bool single_rows = false;                                  // every group is one row: k_tri_multi applies
+    // dense tail: the last T rows of the elimination (one row per wavefront: a purely sequential chain)
+    // are replaced by the dense inverse of their Schur complement M = L22 D2 L22^T -> one GEMV
+    int tail_T = 0, tail_stage = 0, tail_g0 = 0, tail_n1 = 0;
+    double *tail_Minv = nullptr, *tail_rhs = nullptr;
+    int *tail_k1 = nullptr;
 };
 
 static void ldlt_solve_on(Engine *e, ddpca_ldlt *s, const double *b_dev, double *x_dev, const int *done)
@@ -860,7 +883,11 @@ static void ldlt_solve_on(Engine *e, ddpca_ldlt *s, const double *b_dev, double 
     (void)tri_bytes;
     if (s->single_rows) {
         // runs of small wavefronts: one CTA, rows split over warps (k_tri_multi); large wavefronts: one launch each
-        for (const Segment &sg : s->lo.segs) {
+        const int slim = s->tail_T ? s->tail_stage : s->lo.plan.nstages();   // stages >= slim belong to the dense tail
+        for (const Segment &sg0 : s->lo.segs) {
+            Segment sg = sg0;
+            if (sg.s0 >= slim) break;
+            if (sg.s1 > slim) sg.s1 = slim;   // only multi segments can straddle the tail boundary (tail stages hold one row)
             if (sg.multi) KL(e, DDPCA_K_SWEEP_FWD, 0, sg.bytes_lo, (k_tri_multi<true><<<1, 1024, 0, e->stream>>>(s->lo.view(), s->lo.stage_group, sg.s0, sg.s1, s->lo.b, s->lo.x, done)));
             else KL(e, DDPCA_K_SWEEP_FWD, 0, sg.bytes_lo, (k_sweep_fwd_stage<true><<<cdiv((long)(sg.g1 - sg.g0) * GL, 256), 256, 0, e->stream>>>(s->lo.view(), sg.g0, sg.g1, s->lo.b, s->lo.x, s->lo.p1, done)));
         }
@@ -868,9 +895,18 @@ static void ldlt_solve_on(Engine *e, ddpca_ldlt *s, const double *b_dev, double 
         sweep_fwd(e, s->lo, 0, s->lo.b, s->lo.x, true, done);
     }
     KL(e, DDPCA_K_VECTOR, 0, 28.0 * n, (k_scatter_scaled<<<cdiv(n, 256), 256, 0, e->stream>>>(n, s->m_mid, s->dinv_lo, s->lo.x, s->up.p1)));
+    if (s->tail_T) {
+        // x2 = (L22 D2 L22^T)^-1 (b2 - L21 y1): replaces the T sequential forward / backward steps of the tail
+        const int T = s->tail_T;
+        KL(e, DDPCA_K_SWEEP_FWD, 0, 0.0, (k_tail_rhs<<<cdiv((long)T * 32, 256), 256, 0, e->stream>>>(s->lo.view(), s->tail_g0, T, s->tail_k1, s->lo.b, s->lo.x, s->tail_rhs, done)));
+        KL(e, DDPCA_K_COARSE, 0, 8.0 * T * (double)T, (k_dense_gemv<<<cdiv((long)T * 32, 256), 256, 0, e->stream>>>(T, s->tail_Minv, s->tail_rhs, s->up.x + s->tail_n1, done)));
+    }
     if (s->single_rows) {
+        const int slim = s->tail_T ? s->tail_stage : s->up.plan.nstages();
         for (int k = (int)s->up.segs.size() - 1; k >= 0; k--) {
-            const Segment &sg = s->up.segs[k];
+            Segment sg = s->up.segs[k];
+            if (sg.s0 >= slim) continue;
+            if (sg.s1 > slim) sg.s1 = slim;
             if (sg.multi) KL(e, DDPCA_K_SWEEP_BWD, 0, sg.bytes_up, (k_tri_multi<false><<<1, 1024, 0, e->stream>>>(s->up.view(), s->up.stage_group, sg.s0, sg.s1, s->up.p1, s->up.x, done)));
             else KL(e, DDPCA_K_SWEEP_BWD, 0, sg.bytes_up, (k_sweep_bwd_stage<<<cdiv((long)(sg.g1 - sg.g0) * GL, 256), 256, 0, e->stream>>>(s->up.view(), sg.g0, sg.g1, s->up.p1, s->up.x, done)));
         }
@@ -885,7 +921,7 @@ static void ldlt_free(ddpca_ldlt *s)
     if (!s) return;
     cudaSetDevice(s->device);
     free_level(s->lo); free_level(s->up);
-    cudaFree(s->m_in); cudaFree(s->m_mid); cudaFree(s->m_out); cudaFree(s->dinv_lo); cudaFree(s->Binv);
+    cudaFree(s->m_in); cudaFree(s->m_mid); cudaFree(s->m_out); cudaFree(s->dinv_lo); cudaFree(s->Binv); cudaFree(s->tail_Minv); cudaFree(s->tail_rhs); cudaFree(s->tail_k1);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -945,6 +981,46 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
         dinv[j] = 1.0 / D[o];
     }
     if (upload_vec(m_in, &s->m_in) || upload_vec(m_mid, &s->m_mid) || upload_vec(m_out, &s->m_out) || upload_vec(dinv, &s->dinv_lo)) { ldlt_free(s); return 1; }
+    if (s->single_rows && s->lo.plan.perm == s->up.plan.perm && !std::getenv("DDPCA_NO_DENSE_TAIL")) {
+        // trailing run of one-row wavefronts
+        const LevelPlan &pl = s->lo.plan;
+        int ns = pl.nstages(), st = ns;
+        while (st > 0 && pl.stage_group[st] - pl.stage_group[st - 1] == 1 && ns - (st - 1) <= 8192) st--;
+        int T = ns - st;
+        if (T >= 512) {
+            int g0 = pl.stage_group[st], n1 = pl.group_start[g0];
+            // dense unit-lower L22 and the split position k1 of every tail row, from the permuted I+L
+            CsrHost Tp;
+            permute_csr(n, n, Tlo.rp.data(), Tlo.ci.data(), Tlo.v.data(), pl.perm, pl.iperm, Tp);
+            std::vector<double> L22((size_t)T * T, 0.0), D2(T);
+            std::vector<int> k1(T);
+            for (int t = 0; t < T; t++) {
+                int i = n1 + t;
+                int kk = 0;
+                for (int p = Tp.rp[i]; p < Tp.rp[i + 1]; p++) {
+                    int c = Tp.ci[p];
+                    if (c < n1) kk++;
+                    else L22[(size_t)t * T + (c - n1)] = Tp.v[p];   // includes the unit diagonal
+                }
+                k1[t] = kk;
+                D2[t] = D[pl.perm[i]];
+            }
+            double *dL = nullptr, *dD = nullptr;
+            bool ok = cudaMalloc(&dL, sizeof(double) * (size_t)T * T) == cudaSuccess && cudaMalloc(&dD, sizeof(double) * T) == cudaSuccess &&
+                      cudaMalloc(&s->tail_Minv, sizeof(double) * (size_t)T * T) == cudaSuccess && cudaMalloc(&s->tail_rhs, sizeof(double) * T) == cudaSuccess;
+            if (ok) {
+                cudaMemcpy(dL, L22.data(), sizeof(double) * (size_t)T * T, cudaMemcpyHostToDevice);
+                cudaMemcpy(dD, D2.data(), sizeof(double) * T, cudaMemcpyHostToDevice);
+                dim3 gt(cdiv(T, 32), cdiv(T, 32));
+                k_ldl_tail_product<<<gt, 1024, 0, s->stream>>>(T, dL, dD, s->tail_Minv);
+                ok = dense_invert_inplace(s->stream, T, s->tail_Minv) == 0 && upload_vec(k1, &s->tail_k1) == 0;
+            }
+            cudaFree(dL);
+            cudaFree(dD);
+            if (ok) { s->tail_T = T; s->tail_stage = st; s->tail_g0 = g0; s->tail_n1 = n1; }
+            else { cudaFree(s->tail_Minv); cudaFree(s->tail_rhs); s->tail_Minv = s->tail_rhs = nullptr; cudaGetLastError(); }
+        }
+    }
     *out = s;
     return 0;
 }
