@@ -144,28 +144,42 @@ __device__ __forceinline__ void consumer_bar_sync()
 // gbar[32 * (1 + k)] counter k.
 constexpr int kGbarFan = 32;
 constexpr int kGbarWords = 32 * (1 + kGbarFan);
+__device__ __forceinline__ unsigned atom_add_acqrel(unsigned *p, unsigned v)
+{
+    unsigned old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned *p, unsigned v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Release/acquire chain instead of membar.gl: a CTA's stores (ordered before thread 0's arrival by the
+// CTA barrier) are released by its acq_rel arrival, carried through the acq_rel arrivals of the last
+// CTA of each counter and of the root to the generation bump, and acquired by every poller.
 __device__ __forceinline__ void consumer_grid_barrier(unsigned *gbar)
 {
     consumer_bar_sync();
     if (threadIdx.x == 0) {
-        volatile unsigned *vg = gbar;
-        const unsigned gen = vg[1];
-        __threadfence();
+        const unsigned gen = ld_acquire(gbar + 1);
         const unsigned nsub = gridDim.x < (unsigned)kGbarFan ? gridDim.x : (unsigned)kGbarFan;
         const unsigned sub = blockIdx.x % nsub;
         const unsigned sub_size = (gridDim.x - sub + nsub - 1) / nsub;
         unsigned *cnt = gbar + 32 * (1 + sub);
-        if (atomicAdd(cnt, 1u) == sub_size - 1) {
-            *((volatile unsigned *)cnt) = 0;
-            __threadfence();
-            if (atomicAdd(&gbar[0], 1u) == nsub - 1) {
-                vg[0] = 0;
-                __threadfence();
-                atomicAdd(&gbar[1], 1u);
+        if (atom_add_acqrel(cnt, 1u) == sub_size - 1) {
+            st_relaxed(cnt, 0u);
+            if (atom_add_acqrel(gbar, 1u) == nsub - 1) {
+                st_relaxed(gbar, 0u);
+                atom_add_acqrel(gbar + 1, 1u);
             }
         }
-        while (vg[1] == gen) { }
-        __threadfence();
+        while (ld_acquire(gbar + 1) == gen) { }
     }
     consumer_bar_sync();
 }
