@@ -97,3 +97,23 @@ def run_ref_block(glob, divi=None, musc=1, ref_iters=0):
     os.remove(out)
     _cache[key] = (d, meta)
     return _cache[key]
+
+
+def run_ref_beam_dd(glob, doma=(8, 1, 1), musc=1, ref_iters=0, keep_file=False):
+    """Run the prebuilt reference BEAM-with-domain-decomposition driver (oracle/_ref/beam_admm)."""
+    key = ("beam_dd", glob, tuple(doma), musc, ref_iters, keep_file)
+    if key in _cache:
+        return _cache[key]
+    tmp = tempfile.mkdtemp(prefix="ddpca_ref_")
+    out = os.path.join(tmp, "beam_dd.ddpk")
+    cmd = [os.path.join(REF_BIN, "beam_admm"), "--glob", str(glob), "--musc", str(musc), "--out", out, "--ref-iters", str(ref_iters),
+           "--doma", ",".join(str(v) for v in doma)]
+    txt = subprocess.check_output(cmd, cwd=tmp).decode()
+    meta = json.loads(txt.strip().splitlines()[-1])
+    d = ddpk.load(out)
+    if keep_file:
+        meta["path"] = out
+    else:
+        os.remove(out)
+    _cache[key] = (d, meta)
+    return _cache[key]

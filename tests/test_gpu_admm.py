@@ -8,7 +8,7 @@ import pytest
 
 import ddpca_b200 as dd
 from ddpca_b200 import ddpk
-from tests.helpers import GOLDEN, dense_ldlt_factor, have_ref_binary, rel, run_ref_block
+from tests.helpers import GOLDEN, dense_ldlt_factor, have_ref_binary, rel, run_ref_beam_dd, run_ref_block
 
 pytestmark = pytest.mark.gpu
 
@@ -165,4 +165,21 @@ def test_coulomb_friction_projection_matches_oracle(block_small):
     disp = mc.resuDisp
     for v in range(mc.nb):
         assert rel(disp[v], o.resuDisp[v]) < 1e-8
+    mc.close()
+
+
+@pytest.mark.skipif(not have_ref_binary("beam_admm"), reason="oracle/_ref/beam_admm not built")
+def test_beam_dd_8_subdomains_against_reference_run_here():
+    """BASELINE.json config "BEAM ... 8 subdomains": examples/BEAM.h with domaNumb = 8x1x1, tied
+    (vector-valued, d = 3) interfaces only, macroscopic problem; the reference runs on this box's CPU."""
+    d, meta = run_ref_beam_dd(1, doma=(8, 1, 1), musc=1)
+    assert meta["bodies"] == 8 and meta["interfaces"] == 7
+    mc = dd.MCONTACT.from_ddpk(d)
+    mc.CONTACT_ANALYSIS()
+    assert mc.iterNumbReco == meta["ref_iterNumbReco"]
+    disp = mc.resuDisp
+    for v in range(mc.nb):
+        assert rel(disp[v], d[f"ref.resuDisp{v}"]) < 1e-8
+    ref = _moni(d, "ref.resuMoni")
+    assert _rows_close(np.array(mc.resuMoni)[:, -2:], ref[:, -2:], 1e-5)
     mc.close()

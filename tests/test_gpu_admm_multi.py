@@ -11,7 +11,7 @@ import pytest
 
 import ddpca_b200 as dd
 from ddpca_b200 import ddpk
-from tests.helpers import GOLDEN
+from tests.helpers import GOLDEN, have_ref_binary, run_ref_beam_dd
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -51,3 +51,19 @@ def test_two_gpu_admm_matches_reference(musc, iters):
             if musc:
                 assert abs(nrm - np.linalg.norm(d[f"ref.resuDisp{v}"])) <= 1e-8 * nrm
         assert r["launches"] > 0
+
+
+@pytest.mark.skipif(_ngpu() < 2 or not have_ref_binary("beam_admm"), reason="needs 2 GPUs and oracle/_ref/beam_admm")
+def test_two_gpu_beam_dd_8_subdomains():
+    """8 BEAM subdomains split 4 + 4 over two GPUs: same iteration count and displacements as the reference."""
+    d, meta = run_ref_beam_dd(1, doma=(8, 1, 1), musc=1, keep_file=True)
+    out = tempfile.mkdtemp(prefix="ddpca_gpu_dist_")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29619", os.path.join(ROOT, "tests", "gpu_dist_worker.py"), meta["path"], out, "1", "3000"]
+    subprocess.check_call(cmd, timeout=900)
+    res = [json.load(open(os.path.join(out, f"rank{r}.json"))) for r in range(2)]
+    assert res[0]["iterNumbReco"] == res[1]["iterNumbReco"] == meta["ref_iterNumbReco"]
+    assert sorted(res[0]["body_rank"].count(r) for r in (0, 1)) == [4, 4]
+    for r in res:
+        for v, nrm in r["disp_norm"].items():
+            assert abs(nrm - np.linalg.norm(d[f"ref.resuDisp{v}"])) <= 1e-8 * nrm

@@ -45,3 +45,16 @@ def test_block_example_through_the_contact_analysis_overlay():
     assert gpu["iterNumbReco"] == ref["ref_iterNumbReco"]        # ADMM iteration count: bit-exact
     for a, b in zip(gpu["disp_norm"], ref["ref_disp_norm"]):
         assert abs(a - b) <= 1e-8 * b
+
+
+@pytest.mark.skipif(not (os.access(os.path.join(BIN, "beam_dd_b200"), os.X_OK) and os.access(os.path.join(REF, "beam_admm"), os.X_OK)),
+                    reason="overlay / reference binaries not built")
+def test_beam_dd_example_through_the_overlay():
+    """examples/BEAM.h:424-609 (SOLVE_DD, 8 subdomains) unchanged, ADMM loop and MG-PCG on the GPU."""
+    args = ["--glob", "1", "--doma", "8,1,1", "--musc", "1"]
+    ref = _run(os.path.join(REF, "beam_admm"), args)
+    gpu = _run(os.path.join(BIN, "beam_dd_b200"), args)
+    assert gpu["error"] is False
+    assert gpu["iterNumbReco"] == ref["ref_iterNumbReco"]
+    for a, b in zip(gpu["disp_norm"], ref["ref_disp_norm"]):
+        assert abs(a - b) <= 1e-8 * b
