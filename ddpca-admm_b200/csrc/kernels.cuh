@@ -759,7 +759,7 @@ __global__ void k_gamma_project(int nip, int d, double fric, const double *__res
 __global__ void k_axpby(int n, double a, const double *__restrict__ x, double b, double *__restrict__ y)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = a * x[i] + b * y[i];
+    if (i < n) y[i] = (b == 0.0) ? a * x[i] : a * x[i] + b * y[i];   // b == 0: y may be uninitialised
 }
 // y += a*x
 __global__ void k_axpy(int n, double a, const double *__restrict__ x, double *__restrict__ y)

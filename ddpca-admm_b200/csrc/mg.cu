@@ -1319,6 +1319,107 @@ int ddpca_mg_mult_solv(ddpca_mg *h, const double *b, double *x, long *iters, dou
     return to_host(h, Lf, xd, x);
 }
 
+// MGPIS::GMRES_SOLV, MGPIS.h:227-348: left-preconditioned restarted GMRES(10); Arnoldi vectors and
+// all matrix / preconditioner work on the device, the 11x10 Hessenberg algebra on the host.
+int ddpca_mg_gmres(ddpca_mg *h, int prec, const double *b, double *x, long *iters, double *resid, double *tol_abs)
+{
+    if (!h || !b || !x || (prec != 0 && prec != 1)) return fail("ddpca_mg_gmres: bad argument");
+    CU(cudaSetDevice(h->device));
+    enum { STAG = 10 };
+    int Lf = h->nlev - 1;
+    Level &L = h->lev[Lf];
+    int n = L.n;
+    if (prec == 0 && !L.dinv) {
+        CU(cudaMalloc(&L.dinv, sizeof(double) * n));
+        if (L.v2) k_extract_diag_inv2<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view2(), L.dinv);
+        else k_extract_diag_inv<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
+    }
+    double *V = nullptr, *x0 = nullptr, *bd = nullptr;
+    CU(cudaMalloc(&V, sizeof(double) * (size_t)n * (STAG + 1)));
+    CU(cudaMalloc(&x0, sizeof(double) * n));
+    CU(cudaMalloc(&bd, sizeof(double) * n));
+    auto cleanup = [&]() { cudaFree(V); cudaFree(x0); cudaFree(bd); };
+    double *r = h->cg_r, *w0 = h->cg_q, *w = h->cg_z, *xd = h->cg_x;
+    if (to_dev(h, Lf, b, bd)) { cleanup(); return 1; }
+    CU(cudaMemsetAsync(xd, 0, sizeof(double) * n, h->stream));                       // :248
+    double bb;
+    if (dev_dot(h, n, bd, bd, &bb)) { cleanup(); return 1; }
+    const double tol = 1.0E-12 * std::sqrt(bb);                                      // :250
+    const long maxiNumb = n;                                                         // :249
+    double H[STAG + 1][STAG], Q[STAG + 1][STAG], R[STAG][STAG], moni[STAG];
+    std::memset(moni, 0, sizeof(moni));
+    double normR0 = 0.0;
+    long it = 0;
+    int rc = 0;
+    while (it < maxiNumb) {                                                          // :261
+        int k = (int)(it % STAG);
+        if (k == 0) {                                                                // restart, :263-276
+            CU(cudaMemcpyAsync(x0, xd, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+            launch_level_spmv(h, L, Lf, x0, w0, nullptr, nullptr, nullptr);
+            CU(cudaMemcpyAsync(r, bd, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+            dev_axpby(h, n, -1.0, w0, 1.0, r);
+            precondition(h, prec, r, w, nullptr);
+            double ww;
+            if ((rc = dev_dot(h, n, w, w, &ww))) break;
+            normR0 = std::sqrt(ww);
+            dev_axpby(h, n, 1.0 / normR0, w, 0.0, V);
+            std::memset(H, 0, sizeof(H)); std::memset(Q, 0, sizeof(Q)); std::memset(R, 0, sizeof(R));
+        }
+        launch_level_spmv(h, L, Lf, V + (size_t)k * n, w0, nullptr, nullptr, nullptr);   // :278
+        precondition(h, prec, w0, w, nullptr);                                           // :279-285
+        for (int j = 0; j <= k && !rc; j++) rc = dev_dot(h, n, V + (size_t)j * n, w, &H[j][k]);   // :286
+        if (rc) break;
+        for (int j = 0; j <= k; j++) dev_axpby(h, n, -H[j][k], V + (size_t)j * n, 1.0, w);        // :287
+        double qq;
+        if ((rc = dev_dot(h, n, w, w, &qq))) break;
+        const double nq = std::sqrt(qq);                                                 // :288
+        H[k + 1][k] = nq;
+        dev_axpby(h, n, 1.0 / nq, w, 0.0, V + (size_t)(k + 1) * n);                      // :294-296
+        {   // QR of the Hessenberg matrix by Gram-Schmidt, one column per step, :297-316
+            double col[STAG + 1];
+            for (int i = 0; i <= k + 1; i++) col[i] = H[i][k];
+            for (int j = 0; j < k; j++) {
+                double s = 0.0;
+                for (int i = 0; i <= k + 1; i++) s += Q[i][j] * H[i][k];
+                R[j][k] = s;
+            }
+            for (int j = 0; j < k; j++) for (int i = 0; i <= k + 1; i++) col[i] -= Q[i][j] * R[j][k];
+            double nc = 0.0;
+            for (int i = 0; i <= k + 1; i++) nc += col[i] * col[i];
+            nc = std::sqrt(nc);
+            R[k][k] = nc;
+            for (int i = 0; i <= k + 1; i++) Q[i][k] = col[i] / nc;
+        }
+        double y[STAG];                                                                  // :317-324
+        for (int j = k; j >= 0; j--) {
+            double s = normR0 * Q[0][j];
+            for (int c = j + 1; c <= k; c++) s -= R[j][c] * y[c];
+            y[j] = s / R[j][j];
+        }
+        CU(cudaMemcpyAsync(xd, x0, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));   // :325
+        for (int j = 0; j <= k; j++) dev_axpby(h, n, y[j], V + (size_t)j * n, 1.0, xd);
+        launch_level_spmv(h, L, Lf, xd, w0, nullptr, nullptr, nullptr);                  // :326
+        CU(cudaMemcpyAsync(r, bd, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+        dev_axpby(h, n, -1.0, w0, 1.0, r);
+        double rr;
+        if ((rc = dev_dot(h, n, r, r, &rr))) break;
+        moni[k] = std::sqrt(rr);                                                         // :328
+        if (it >= STAG - 1) {                                                            // :333-341
+            double mx = *std::max_element(moni, moni + STAG), mn = *std::min_element(moni, moni + STAG);
+            if (moni[k] <= tol || (moni[k] <= 1.0E2 * tol && (mx - mn) < 0.1 * ((mx + mn) / 2.0))) break;
+        }
+        it++;
+    }
+    if (h->profile) h->prof_collect();
+    if (rc) { cleanup(); return 1; }
+    if (iters) *iters = it;
+    if (resid) *resid = moni[it % STAG];
+    if (tol_abs) *tol_abs = tol;
+    rc = to_host(h, Lf, xd, x);
+    cleanup();
+    return rc;
+}
+
 // MGPIS::BiCGSTAB_SOLV, MGPIS.h:350-432
 int ddpca_mg_bicgstab(ddpca_mg *h, int prec, const double *b, double *x, double rel_tol, long maxit, long *iters,
                       double *resid, double *tol_abs)

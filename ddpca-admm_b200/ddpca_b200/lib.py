@@ -23,7 +23,7 @@ EXPORTS = [
     "ddpca_plan_create", "ddpca_plan_sizes", "ddpca_plan_get", "ddpca_plan_destroy",
     "ddpca_mg_create", "ddpca_mg_destroy", "ddpca_mg_pcg", "ddpca_mg_pcg_dev",
     "ddpca_mg_vcycle", "ddpca_mg_spmv", "ddpca_mg_restrict", "ddpca_mg_prolong_add",
-    "ddpca_mg_coarse_solve", "ddpca_mg_mult_solv", "ddpca_mg_bicgstab",
+    "ddpca_mg_coarse_solve", "ddpca_mg_mult_solv", "ddpca_mg_bicgstab", "ddpca_mg_gmres",
     "ddpca_mg_level_info", "ddpca_mg_launch_count", "ddpca_mg_set_stream",
     "ddpca_mg_profile", "ddpca_mg_profile_get", "ddpca_mg_last_timing",
     "ddpca_ldlt_create", "ddpca_ldlt_create_dense", "ddpca_ldlt_solve", "ddpca_ldlt_solve_dev", "ddpca_ldlt_info", "ddpca_ldlt_destroy",

@@ -152,6 +152,15 @@ class MGPIS:
         self.last_iterNumb, self.last_resid, self.last_tol = it.value, res.value, tol.value
         return x
 
+    def GMRES_SOLV(self, precSwit: int, totaForc):
+        """MGPIS::GMRES_SOLV (MGPIS.h:227-348): restarted GMRES(10). iterNumb in .last_iterNumb."""
+        b = _f64(totaForc)
+        x = np.empty(self.n())
+        it, res, tol = C.c_long(), C.c_double(), C.c_double()
+        check(load_library().ddpca_mg_gmres(self._handle(), C.c_int(precSwit), _pd(b), _pd(x), C.byref(it), C.byref(res), C.byref(tol)))
+        self.last_iterNumb, self.last_resid, self.last_tol = it.value, res.value, tol.value
+        return x
+
     def MULT_SOLV(self, totaForc):
         """MGPIS::MULT_SOLV (MGPIS.h:130-160): stand-alone V-cycle iteration."""
         b = _f64(totaForc)

@@ -211,11 +211,27 @@ long MGPIS::MULT_SOLV(const Eigen::VectorXd &totaForc, Eigen::VectorXd &resuSolu
 }
 
 long MGPIS::GMRES_SOLV(long precSwit, const Eigen::VectorXd &totaForc, Eigen::VectorXd &resuSolu){
-	// not referenced by any example of the reference (only in a comment, examples/BEAM.h:416);
-	// not yet offered by the B200 build
-	(void)precSwit; (void)totaForc; (void)resuSolu;
-	std::cout << "MGPIS::GMRES_SOLV (B200): ERROR not available, use CG_SOLV or BiCGSTAB_SOLV" << std::endl;
-	return -1;
+	std::cout << "MGPIS::GMRES_SOLV";
+	if(precSwit == 0){
+		std::cout << " (diagonal preconditioner)";
+	}
+	else if(precSwit == 1){
+		std::cout << " (multigrid preconditioner)";
+	}
+	OUTPUT_TIME("");
+	resuSolu = Eigen::VectorXd::Zero(consStif[maxiLeve].rows());
+	ddpca_mg *h = DEVICE_HANDLE();
+	long iterNumb = 0;
+	double resiNorm = 0.0, toleLimi = 0.0;
+	if(h == nullptr || ddpca_mg_gmres(h, precSwit, totaForc.data(), resuSolu.data(),
+		&iterNumb, &resiNorm, &toleLimi) != 0){
+		std::cout << "MGPIS::GMRES_SOLV (B200): ERROR " << ddpca_last_error() << std::endl;
+		return -1;
+	}
+	lastIterNumb = iterNumb;
+	std::cout << "#Iteration: " << iterNumb << ", residual: " << resiNorm << "/" << toleLimi;
+	OUTPUT_TIME(":");
+	return 1;
 }
 
 #endif

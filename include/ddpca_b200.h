@@ -102,10 +102,14 @@ int ddpca_mg_prolong_add(ddpca_mg *, int level, const double *e_coarse, double *
 /* direSolv.solve(b) on consStif[0], MGPIS.h:58 */
 int ddpca_mg_coarse_solve(ddpca_mg *, const double *b, double *x);
 
-/* MGPIS::MULT_SOLV (MGPIS.h:130-160), BiCGSTAB_SOLV (:350-432): same kernels, other drivers */
+/* MGPIS::MULT_SOLV (MGPIS.h:130-160), BiCGSTAB_SOLV (:350-432), GMRES_SOLV (:227-348): the same
+ * kernels under host-driven drivers (scalars return to the host after each reduction) */
 int ddpca_mg_mult_solv(ddpca_mg *, const double *b, double *x, long *iters, double *resid);
 int ddpca_mg_bicgstab(ddpca_mg *, int prec, const double *b, double *x, double rel_tol, long maxit,
                       long *iters, double *resid, double *tol_abs);
+/* MGPIS::GMRES_SOLV (MGPIS.h:227-348): restarted GMRES(10), tolerance 1e-12 ||b|| and the
+ * reference's stagnation stop; iters = iterNumb as the reference prints it */
+int ddpca_mg_gmres(ddpca_mg *, int prec, const double *b, double *x, long *iters, double *resid, double *tol_abs);
 
 /* ---- DIRE_SOLV: sparse direct solves with a host-computed factorisation --------
  * The reference factorises the interface mass matrices and the macroscopic problem

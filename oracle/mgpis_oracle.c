@@ -348,3 +348,89 @@ long orc_bicgstab(orc_mg *h, long precSwit, const double *b, double *x, double *
     free(r); free(rh); free(p); free(v); free(s); free(t); free(ph); free(sh); free(dinv);
     return it;
 }
+
+/* MGPIS::GMRES_SOLV, MGPIS.h:227-348: left-preconditioned GMRES, restart 10, classical Gram-Schmidt
+ * Arnoldi, QR of the Hessenberg matrix by Gram-Schmidt, true residual every step, stop when
+ * ||r|| <= tol or (||r|| <= 100 tol and the last 10 residuals stagnate).  Returns iterNumb. */
+long orc_gmres(orc_mg *h, long precSwit, const double *b, double *x, double *resid_out, double *tol_out)
+{
+    enum { STAG = 10 };
+    int L = h->nlev - 1;
+    const csr_t *A = &h->A[L];
+    int n = A->n;
+    double *dinv = NULL;
+    if (precSwit == 0) {
+        dinv = (double *)malloc(sizeof(double) * n);
+        for (int i = 0; i < n; i++) dinv[i] = 1.0 / A->v[h->dpos[L][i]];
+    } else orc_mg_factor(h);                                 /* :245 */
+    memset(x, 0, sizeof(double) * n);                        /* :248 */
+    long maxiNumb = n;                                       /* :249 */
+    double toleLimi = 1.0E-12 * sqrt(dot(n, b, b));          /* :250 */
+    size_t nb = sizeof(double) * n;
+    double *V = (double *)malloc(nb * (STAG + 1));           /* orthBasi */
+    double *x0 = (double *)malloc(nb), *r = (double *)malloc(nb), *w0 = (double *)malloc(nb), *w = (double *)malloc(nb);
+    double H[STAG + 1][STAG], Q[STAG + 1][STAG], R[STAG][STAG], moni[STAG];
+    double normR0 = 0.0;
+    memset(moni, 0, sizeof(moni));
+    long it = 0;
+    while (it < maxiNumb) {                                  /* :261 */
+        int k = (int)(it % STAG);
+        if (k == 0) {                                        /* restart :263-276 */
+            memcpy(x0, x, nb);
+            orc_spmv(n, A->rp, A->ci, A->v, x0, r);
+            for (int i = 0; i < n; i++) r[i] = b[i] - r[i];
+            if (precSwit == 0) for (int i = 0; i < n; i++) w[i] = dinv[i] * r[i];
+            else { memset(w, 0, nb); orc_vcycle(h, L, r, w); }
+            normR0 = sqrt(dot(n, w, w));
+            for (int i = 0; i < n; i++) V[i] = w[i] / normR0;
+            memset(H, 0, sizeof(H)); memset(Q, 0, sizeof(Q)); memset(R, 0, sizeof(R));
+        }
+        orc_spmv(n, A->rp, A->ci, A->v, V + (size_t)k * n, w0);           /* :278 */
+        if (precSwit == 0) for (int i = 0; i < n; i++) w[i] = dinv[i] * w0[i];
+        else { memset(w, 0, nb); orc_vcycle(h, L, w0, w); }               /* :279-285 */
+        for (int j = 0; j <= k; j++) H[j][k] = dot(n, V + (size_t)j * n, w);   /* b_i :286 */
+        for (int j = 0; j <= k; j++) for (int i = 0; i < n; i++) w[i] -= H[j][k] * V[(size_t)j * n + i];   /* :287 */
+        double nq = sqrt(dot(n, w, w));                                   /* :288 */
+        H[k + 1][k] = nq;                                                 /* :289-293 */
+        for (int i = 0; i < n; i++) V[(size_t)(k + 1) * n + i] = w[i] / nq;   /* :294-296 */
+        /* QR of H by Gram-Schmidt, one column per step  :297-316 */
+        {
+            double col[STAG + 1];
+            for (int i = 0; i <= k + 1; i++) col[i] = H[i][k];
+            for (int j = 0; j < k; j++) {
+                double s = 0.0;
+                for (int i = 0; i <= k + 1; i++) s += Q[i][j] * H[i][k];
+                R[j][k] = s;
+            }
+            for (int j = 0; j < k; j++) for (int i = 0; i <= k + 1; i++) col[i] -= Q[i][j] * R[j][k];
+            double nc = 0.0;
+            for (int i = 0; i <= k + 1; i++) nc += col[i] * col[i];
+            nc = sqrt(nc);
+            R[k][k] = nc;
+            for (int i = 0; i <= k + 1; i++) Q[i][k] = col[i] / nc;
+        }
+        /* y = R^-1 (normR0 * Q.row(0)^T)  :317-324 */
+        double y[STAG];
+        for (int j = k; j >= 0; j--) {
+            double s = normR0 * Q[0][j];
+            for (int c = j + 1; c <= k; c++) s -= R[j][c] * y[c];
+            y[j] = s / R[j][j];
+        }
+        memcpy(x, x0, nb);                                                /* :325 */
+        for (int j = 0; j <= k; j++) for (int i = 0; i < n; i++) x[i] += y[j] * V[(size_t)j * n + i];
+        orc_spmv(n, A->rp, A->ci, A->v, x, r);                            /* :326 */
+        for (int i = 0; i < n; i++) r[i] = b[i] - r[i];
+        moni[k] = sqrt(dot(n, r, r));                                     /* :328 */
+        if (it >= STAG - 1) {                                             /* :333-341 */
+            double mx = moni[0], mn = moni[0];
+            for (int j = 1; j < STAG; j++) { if (moni[j] > mx) mx = moni[j]; if (moni[j] < mn) mn = moni[j]; }
+            double medi = (mx + mn) / 2.0, osci = mx - mn;
+            if (moni[k] <= toleLimi || (moni[k] <= 1.0E2 * toleLimi && osci < 0.1 * medi)) break;
+        }
+        it++;
+    }
+    if (resid_out) *resid_out = moni[it % STAG];
+    if (tol_out) *tol_out = toleLimi;
+    free(V); free(x0); free(r); free(w0); free(w); free(dinv);
+    return it;
+}

@@ -33,6 +33,7 @@ def lib() -> C.CDLL:
         _LIB.orc_cg_solv.restype = C.c_long
         _LIB.orc_bicgstab.restype = C.c_long
         _LIB.orc_mult_solv.restype = C.c_long
+        _LIB.orc_gmres.restype = C.c_long
     return _LIB
 
 
@@ -119,6 +120,16 @@ def _mult_solv(self, b):
     return x, int(it), res.value
 
 
+def _gmres(self, prec, b):
+    """GMRES_SOLV(precSwit, b, x) -- MGPIS.h:227-348.  Returns (x, iterNumb, resid, tol)."""
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros_like(b)
+    res, tol = C.c_double(), C.c_double()
+    it = lib().orc_gmres(self.h, C.c_long(prec), _p(b, C.c_double), _p(x, C.c_double), C.byref(res), C.byref(tol))
+    return x, int(it), res.value, tol.value
+
+
+OracleMG.gmres = _gmres
 OracleMG.bicgstab = _bicgstab
 OracleMG.mult_solv = _mult_solv
 

@@ -127,7 +127,11 @@ int main(int argc, char **argv) {
 		mgpi.MULT_SOLV(mg.consForc, x);
 		long itm = cap.last_iteration_plus1() - 1;   // MULT_SOLV prints iterNumb itself (:156)
 		if (w) { w->vec("mult_solv_x", x); w->scalar_i64("mult_solv_iters", itm); }
-		js << ",\"bicgstab_mg_iters\":" << itb << ",\"mult_solv_iters\":" << itm;
+		cap.buf.str("");
+		mgpi.GMRES_SOLV(1, mg.consForc, x);   // MGPIS.h:227-348 (prints iterNumb itself, :344)
+		long itg = cap.last_iteration_plus1() - 1;
+		if (w) { w->vec("gmres_mg_x", x); w->scalar_i64("gmres_mg_iters", itg); }
+		js << ",\"bicgstab_mg_iters\":" << itb << ",\"mult_solv_iters\":" << itm << ",\"gmres_mg_iters\":" << itg;
 	}
 	if (benchSteps > 0) {
 		Eigen::VectorXd x;

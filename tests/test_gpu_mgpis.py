@@ -239,3 +239,15 @@ def test_v1_v2_kernels_and_loop_drivers_agree(monkeypatch):
             # v1 and v2 kernels sum in different orders: counts of this 141-iteration solve may move a little
             assert abs(it - 141) <= 6
             assert rel(x, d["cg_mg_x"]) < 1e-8
+
+
+def test_gmres_matches_oracle(solvers):
+    """MGPIS::GMRES_SOLV (MGPIS.h:227-348), restarted GMRES(10) with the V-cycle preconditioner."""
+    mg, d, meta, A, P = solvers("beam_2lev", dd.SMOOTH_LEX)
+    x = mg.GMRES_SOLV(1, d["consForc"])
+    xo, ito, reso, tolo = orc.OracleMG(A, P).gmres(1, d["consForc"])
+    assert rel(x, xo) < 1e-8 and rel(x, d["cg_mg_x"]) < 1e-8
+    # the residual floor of this system lies above 1e-12 ||b||: reference, oracle and device all run to maxiNumb
+    assert mg.last_iterNumb == ito or abs(mg.last_iterNumb - ito) <= ito // 10
+    if "gmres_mg_x" in d:
+        assert rel(x, d["gmres_mg_x"]) < 1e-8
