@@ -6,7 +6,7 @@
 // 64-byte DRAM granularity over-fetch when only half of each row is needed.  Here
 //   * the strictly-lower and strictly-upper couplings of a level live in two separate arrays
 //     in stage order, so a half sweep streams ONE contiguous region;
-//   * a CTA processes CHUNKS of 16 row groups: descriptor, group metadata, diagonal blocks,
+//   * a CTA processes CHUNKS of 16 row groups (up to 32 where a pass reads only one half): descriptor, group metadata, diagonal blocks,
 //     patterns and values of a chunk arrive in shared memory by a handful of bulk copies
 //     (UBLKCP), double-buffered, so the only latency left on the critical path is the x gather,
 //     and all gathers of a group are issued back to back from a pattern that is already on chip;
@@ -33,13 +33,24 @@ namespace cg = cooperative_groups;
 #define DDPCA_V2_LANES 8
 #endif
 constexpr int GL2 = DDPCA_V2_LANES;                  // lanes per row group in the v2 kernels (8 or 16)
-constexpr int kChunkGroups = DDPCA_V2_GROUPS;        // row groups per chunk = consumer sub-warps per CTA
+#ifndef DDPCA_V2_HALF_GROUPS
+#define DDPCA_V2_HALF_GROUPS DDPCA_V2_GROUPS
+#endif
+constexpr int kChunkGroups = DDPCA_V2_GROUPS;        // row groups per chunk of a pass over whole rows (FWD_FULL, SPMV)
+// Passes over one half of the rows (FWD_ZERO, BWD, RESID) have their own chunk tables, cut by BYTES:
+// at most kHalfGroups groups and at most 1/kHalfBudgetDiv of the streamed bytes of the largest
+// whole-row chunk.  With the default (16 groups, 1/2) a half-pass ring is half as large, 5 CTAs fit
+// on a SM instead of 3, and colours whose couplings all lie in one half get chunks of ~8 groups.
+constexpr int kHalfGroups = DDPCA_V2_HALF_GROUPS;
+#ifndef DDPCA_V2_HALF_BUDGET_DIV
+#define DDPCA_V2_HALF_BUDGET_DIV 2
+#endif
+constexpr int kHalfBudgetDiv = DDPCA_V2_HALF_BUDGET_DIV;   // half-pass chunk budget = largest whole-row chunk / this
 constexpr int kV2Bufs = DDPCA_V2_BUFS;               // depth of the shared-memory ring
-constexpr int kV2Consumers = kChunkGroups * GL2;     // consumer threads
 constexpr int kV2StagesSmem = 64;                     // stage tables up to this size are cached in shared memory
-constexpr int kV2Threads = kV2Consumers + 32;        // + one producer warp (one lane issues the bulk copies)
 static_assert(GL2 == 8 || GL2 == 16 || GL2 == 32, "v2 kernels: 8, 16 or 32 lanes per row group");
-static_assert((kChunkGroups * GL2) % 32 == 0, "consumer threads must fill whole warps");
+static_assert((kChunkGroups * GL2) % 32 == 0 && (kHalfGroups * GL2) % 32 == 0, "consumer threads must fill whole warps");
+static_assert(kHalfGroups >= kChunkGroups, "half-pass chunks hold at least as many groups as whole-row chunks");
 __device__ __forceinline__ unsigned subwarp_mask2()
 {
     const unsigned lane = threadIdx.x & 31u;
@@ -78,21 +89,27 @@ struct Lvl2View {
     const int *__restrict__ CU;
     const double *__restrict__ VU;
     const double *__restrict__ BD;          // [ng * kBlkStride]
-    const ChunkDesc *__restrict__ chunks;   // [nchunks], stage after stage
+    const ChunkDesc *__restrict__ chunks;   // [nchunks], stage after stage -- the table of the pass type (V2_TAB_*)
     const int *__restrict__ stage_chunk;    // [nstages+1]
 };
 
 enum { V2_FWD_ZERO = 0, V2_FWD_FULL = 1, V2_BWD = 2, V2_RESID = 3, V2_SPMV = 4 };
+// chunk tables of a level: whole rows / lower halves / upper halves
+enum { V2_TAB_FULL = 0, V2_TAB_LO = 1, V2_TAB_UP = 2 };
+__host__ __device__ constexpr int v2_table(int mode) { return (mode == V2_FWD_FULL || mode == V2_SPMV) ? V2_TAB_FULL : (mode == V2_BWD ? V2_TAB_UP : V2_TAB_LO); }
+__host__ __device__ constexpr int v2_groups(int mode) { return v2_table(mode) == V2_TAB_FULL ? kChunkGroups : kHalfGroups; }   // consumer sub-warps per CTA
+__host__ __device__ constexpr int v2_consumers(int mode) { return v2_groups(mode) * GL2; }
+__host__ __device__ constexpr int v2_threads(int mode) { return v2_consumers(mode) + 32; }   // + one producer warp (one lane issues the bulk copies)
 
-// fixed offsets inside a shared-memory buffer
+// fixed offsets inside a shared-memory buffer (G = group capacity of the chunk table)
 constexpr int kOffDesc = 0;                                   // 48 B (+16 pad)
-constexpr int kOffMeta = 64;                                  // kChunkGroups * 32 B
-constexpr int kOffBlk = kOffMeta + kChunkGroups * 32;         // kChunkGroups * 80 B
-constexpr int kOffData = kOffBlk + kChunkGroups * kBlkStride * 8;
+constexpr int kOffMeta = 64;                                  // G * 32 B
+__host__ __device__ constexpr int v2_off_blk(int G) { return kOffMeta + G * 32; }              // G * 80 B
+__host__ __device__ constexpr int v2_off_data(int G) { return v2_off_blk(G) + G * kBlkStride * 8; }
 
 __host__ __device__ inline size_t v2_chunk_bytes(int mode, int ncl, int nvl, int ncu, int nvu)
 {
-    size_t b = kOffData;
+    size_t b = v2_off_data(v2_groups(mode));
     const bool lo = (mode != V2_BWD), up = (mode == V2_FWD_FULL || mode == V2_BWD || mode == V2_SPMV);
     if (lo) b += (size_t)ncl * 4 + (size_t)nvl * 16;
     if (up) b += (size_t)ncu * 4 + (size_t)nvu * 16;
@@ -132,17 +149,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // barrier among the consumer threads only (the producer warp never joins)
+template <int NCONS>
 __device__ __forceinline__ void consumer_bar_sync()
 {
-    asm volatile("bar.sync 1, %0;" ::"n"(kV2Consumers) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
 }
 // Grid-wide barrier among the consumer threads of all CTAs of a cooperative launch (all CTAs are
-// co-resident).  Two-level and self-resetting: CTAs arrive on one of kGbarFan counters (separate
-// 128-byte lines, so the L2 atomic units work in parallel instead of serialising ~700 arrivals on
-// one address), the last arrival of each counter arrives on the root, the last root arrival bumps
-// the generation everybody polls.  Layout: gbar[0] root count, gbar[1] generation,
-// gbar[32 * (1 + k)] counter k.
-constexpr int kGbarFan = 32;
+// co-resident).  Flat and monotonic: a CTA arrives with ONE fire-and-forget red.release on one of
+// kGbarFan counters (separate 128-byte lines, so arrivals spread over L2 atomic units), and the first
+// lanes of its warp 0 poll all counters with ld.acquire until each holds epoch * (its share of the
+// grid) -- one L2 one-way trip for the arrival plus the poll instead of a chain of dependent atomic
+// round trips.  The counters are never reset inside the sweep; the last CTA to leave the kernel zeroes
+// them (consumer_grid_barrier_exit).  Layout: gbar[32 * k] counter k, gbar[32 * kGbarFan] exit count.
+#ifndef DDPCA_GBAR_FAN
+#define DDPCA_GBAR_FAN 8
+#endif
+#ifndef DDPCA_GBAR_POLL
+#define DDPCA_GBAR_POLL 0
+#endif
+constexpr int kGbarFan = DDPCA_GBAR_FAN;
+static_assert(kGbarFan >= 1 && kGbarFan <= 32, "one polling lane per counter");
 constexpr int kGbarWords = 32 * (1 + kGbarFan);
 __device__ __forceinline__ unsigned atom_add_acqrel(unsigned *p, unsigned v)
 {
@@ -150,38 +176,64 @@ __device__ __forceinline__ unsigned atom_add_acqrel(unsigned *p, unsigned v)
     asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
     return old;
 }
+__device__ __forceinline__ void red_add_release(unsigned *p, unsigned v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
 {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_relaxed(unsigned *p, unsigned v)
 {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// Release/acquire chain instead of membar.gl: a CTA's stores (ordered before thread 0's arrival by the
-// CTA barrier) are released by its acq_rel arrival, carried through the acq_rel arrivals of the last
-// CTA of each counter and of the root to the generation bump, and acquired by every poller.
-__device__ __forceinline__ void consumer_grid_barrier(unsigned *gbar)
+// epoch = 1 for the first barrier of the launch, 2 for the second, ...  A CTA's stores are ordered
+// before thread 0's release by the CTA barrier; the polling lanes' acquires are ordered before the
+// other consumers' loads by the second CTA barrier.
+template <int NCONS>
+__device__ __forceinline__ void consumer_grid_barrier(unsigned *gbar, unsigned epoch)
 {
-    consumer_bar_sync();
-    if (threadIdx.x == 0) {
-        const unsigned gen = ld_acquire(gbar + 1);
+    consumer_bar_sync<NCONS>();
+    if (threadIdx.x < 32) {
         const unsigned nsub = gridDim.x < (unsigned)kGbarFan ? gridDim.x : (unsigned)kGbarFan;
-        const unsigned sub = blockIdx.x % nsub;
-        const unsigned sub_size = (gridDim.x - sub + nsub - 1) / nsub;
-        unsigned *cnt = gbar + 32 * (1 + sub);
-        if (atom_add_acqrel(cnt, 1u) == sub_size - 1) {
-            st_relaxed(cnt, 0u);
-            if (atom_add_acqrel(gbar, 1u) == nsub - 1) {
-                st_relaxed(gbar, 0u);
-                atom_add_acqrel(gbar + 1, 1u);
-            }
+        if (threadIdx.x == 0) red_add_release(gbar + 32 * (blockIdx.x % nsub), 1u);
+        if (threadIdx.x < nsub) {
+            const unsigned sub_size = (gridDim.x - threadIdx.x + nsub - 1) / nsub;
+            const unsigned target = epoch * sub_size;
+            const unsigned *cnt = gbar + 32 * threadIdx.x;
+#if DDPCA_GBAR_POLL == 0
+            while (ld_acquire(cnt) < target) { }
+#else
+            // relaxed polling + one acquire fence: an acquire load drops the SM's L1 lines on every
+            // poll, which the CTAs still working on the stage would pay for with gather misses
+            while (ld_relaxed(cnt) < target) { }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
         }
-        while (ld_acquire(gbar + 1) == gen) { }
+        __syncwarp();
     }
-    consumer_bar_sync();
+    consumer_bar_sync<NCONS>();
+}
+// after the last barrier of the launch: the last CTA out zeroes the counters for the next launch
+__device__ __forceinline__ void consumer_grid_barrier_exit(unsigned *gbar)
+{
+    if (threadIdx.x == 0) {
+        unsigned *ex = gbar + 32 * kGbarFan;
+        if (atom_add_acqrel(ex, 1u) == gridDim.x - 1) {
+            const unsigned nsub = gridDim.x < (unsigned)kGbarFan ? gridDim.x : (unsigned)kGbarFan;
+            for (unsigned k = 0; k < nsub; k++) st_relaxed(gbar + 32 * k, 0u);
+            st_relaxed(ex, 0u);
+        }
+    }
 }
 __device__ __forceinline__ void fence_proxy_async()
 {
@@ -194,6 +246,7 @@ __device__ __forceinline__ void v2_issue_chunk(const Lvl2View &A, int c, const C
 {
     constexpr bool LO = (MODE != V2_BWD);
     constexpr bool UP = (MODE == V2_FWD_FULL || MODE == V2_BWD || MODE == V2_SPMV);
+    constexpr int kOffBlk = v2_off_blk(v2_groups(MODE)), kOffData = v2_off_data(v2_groups(MODE));
     uint32_t bytes = 48 + (uint32_t)d.ng * 32 + (uint32_t)d.ng * kBlkStride * 8;
     if (LO) bytes += (uint32_t)d.ncl * 4 + (uint32_t)d.nvl * 16;
     if (UP) bytes += (uint32_t)d.ncu * 4 + (uint32_t)d.nvu * 16;
@@ -225,6 +278,27 @@ __device__ __forceinline__ void v2_issue_chunk(const Lvl2View &A, int c, const C
 // Longer halves continue in a generic loop (v2_tail).
 constexpr int kV2Iters = 64 / (2 * GL2) < 1 ? 1 : 64 / (2 * GL2);   // unrolled steps cover 64 pattern positions
 
+// x gathers go through L1: neighbouring row groups share most of their columns, and an L1 hit
+// takes the gather off the L2 round trip that bounds these kernels.
+//   RESID, SPMV: x is constant for the whole launch -> read-only path (ld.global.nc);
+//   staged sweeps: other CTAs write x between stages -> ordinary (weak, L1-allocating) loads.  They
+//   are ordered after those writes by the grid barrier (release on arrival, acquire by the polling
+//   lanes -- which drops the SM's L1 lines --, CTA barrier), and nothing a stage reads is written
+//   during that stage (rows of one colour are contiguous after the permutation and mutually
+//   uncoupled; a sector shared with the colour being written is only read for its stable part and
+//   is dropped again at the next barrier).
+// DDPCA_V2_GATHER_L1: 0 = L2 only everywhere, 1 = L1 for RESID/SPMV only, 2 = everywhere.
+#ifndef DDPCA_V2_GATHER_L1
+#define DDPCA_V2_GATHER_L1 2
+#endif
+template <bool RO>
+__device__ __forceinline__ double v2_ldx(const double *p)
+{
+    if (RO && DDPCA_V2_GATHER_L1 >= 1) return __ldg(p);
+    if (!RO && DDPCA_V2_GATHER_L1 >= 2) return *p;
+    return __ldcg(p);
+}
+template <bool RO>
 __device__ __forceinline__ void v2_gather(const int *__restrict__ pc, int n, const double *x, int sl, double (&xs)[2 * kV2Iters])
 {
 #pragma unroll
@@ -234,8 +308,8 @@ __device__ __forceinline__ void v2_gather(const int *__restrict__ pc, int n, con
         xs[2 * it + 1] = 0.0;
         if (k < n) {
             const int2 c = *reinterpret_cast<const int2 *>(pc + k);
-            xs[2 * it] = __ldcg(x + c.x);
-            xs[2 * it + 1] = __ldcg(x + c.y);
+            xs[2 * it] = v2_ldx<RO>(x + c.x);
+            xs[2 * it + 1] = v2_ldx<RO>(x + c.y);
         }
     }
 }
@@ -254,12 +328,13 @@ __device__ __forceinline__ void v2_fma(const double *__restrict__ pv, int n, int
         }
     }
 }
+template <bool RO>
 __device__ __forceinline__ void v2_tail(const int *__restrict__ pc, const double *__restrict__ pv, int n, int gs,
                                         const double *x, int sl, double (&s)[3])
 {
     for (int k = 2 * sl + kV2Iters * 2 * GL2; k < n; k += 2 * GL2) {
         const int2 c = *reinterpret_cast<const int2 *>(pc + k);
-        const double x0 = __ldcg(x + c.x), x1 = __ldcg(x + c.y);
+        const double x0 = v2_ldx<RO>(x + c.x), x1 = v2_ldx<RO>(x + c.y);
 #pragma unroll
         for (int r = 0; r < 3; r++)
             if (r < gs) {
@@ -279,7 +354,7 @@ __device__ __forceinline__ void v2_tail(const int *__restrict__ pc, const double
 // data does not depend on x --, the consumer warps meet the other CTAs at a grid barrier between
 // stages.  Staged modes must be launched cooperatively (co-residency of all CTAs).
 template <int MODE>
-__global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, size_t buf_bytes, unsigned *gbar, const double *__restrict__ b,
+__global__ void __launch_bounds__(v2_threads(MODE)) k_level_pass(Lvl2View A, size_t buf_bytes, unsigned *gbar, const double *__restrict__ b,
                                                             double *x, double *p1, double *y, const double *__restrict__ w,
                                                             double *partial, const int *done)
 {
@@ -290,6 +365,8 @@ __global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, size_t bu
     constexpr bool LO = (MODE != V2_BWD);
     constexpr bool UP = (MODE == V2_FWD_FULL || MODE == V2_BWD || MODE == V2_SPMV);
     constexpr bool STAGED = (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD);
+    constexpr int kV2Consumers = v2_consumers(MODE);
+    constexpr int kOffBlk = v2_off_blk(v2_groups(MODE)), kOffData = v2_off_data(v2_groups(MODE));
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < kV2Bufs; i++) {
@@ -350,7 +427,7 @@ __global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, size_t bu
             const bool have = settle(si, c);
             if (STAGED) {
                 const int target = have ? si : nst - 1;
-                while (si_done < target) { consumer_grid_barrier(gbar); si_done++; }
+                while (si_done < target) { si_done++; consumer_grid_barrier<kV2Consumers>(gbar, (unsigned)si_done); }
             }
             if (!have) break;
             const int slot = j % kV2Bufs;
@@ -386,12 +463,12 @@ __global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, size_t bu
                 }
                 {
                     double xl[2 * kV2Iters], xu[2 * kV2Iters];
-                    if (LO) v2_gather(cL, m.nl, x, sl, xl);
-                    if (UP) v2_gather(cU, m.nu, x, sl, xu);
+                    if (LO) v2_gather<!STAGED>(cL, m.nl, x, sl, xl);
+                    if (UP) v2_gather<!STAGED>(cU, m.nu, x, sl, xu);
                     if (LO) v2_fma(vL, m.nl, gs, sl, xl, sL);
                     if (UP) v2_fma(vU, m.nu, gs, sl, xu, sU);
-                    if (LO && m.nl > kV2Iters * 2 * GL2) v2_tail(cL, vL, m.nl, gs, x, sl, sL);
-                    if (UP && m.nu > kV2Iters * 2 * GL2) v2_tail(cU, vU, m.nu, gs, x, sl, sU);
+                    if (LO && m.nl > kV2Iters * 2 * GL2) v2_tail<!STAGED>(cL, vL, m.nl, gs, x, sl, sL);
+                    if (UP && m.nu > kV2Iters * 2 * GL2) v2_tail<!STAGED>(cU, vU, m.nu, gs, x, sl, sU);
                 }
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
@@ -450,6 +527,7 @@ __global__ void __launch_bounds__(kV2Threads) k_level_pass(Lvl2View A, size_t bu
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty[slot]);   // this warp is done reading the slot
         }
+        if (STAGED && nst > 1) consumer_grid_barrier_exit(gbar);
     }
     if (MODE == V2_SPMV && partial) block_sum_to_partial(acc, partial);   // all warps, producer included
 }

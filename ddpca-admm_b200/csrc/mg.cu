@@ -81,13 +81,15 @@ struct Level {
     // v2: split lower/upper storage + chunk table (kernels2.cuh); used when every stage is large
     bool v2 = false;
     GroupMeta2 *meta2 = nullptr;
-    int *CL = nullptr, *CU = nullptr, *stage_chunk = nullptr;
+    int *CL = nullptr, *CU = nullptr;
     double *VL = nullptr, *VU = nullptr, *BD = nullptr;
-    ChunkDesc *chunks = nullptr;
-    int nchunks = 0, max_stage_chunks = 0;
-    unsigned *gbar = nullptr;   // {arrival count, generation} of the consumer grid barrier
-    size_t buf_lo = 0, buf_up = 0, buf_full = 0;   // shared-memory bytes of one chunk buffer per pass type
-    Lvl2View view2() const { return Lvl2View{n, ng, nchunks, plan.nstages(), meta2, CL, VL, CU, VU, BD, chunks, stage_chunk}; }
+    // one chunk table per pass type (V2_TAB_FULL / _LO / _UP): the half passes cut their chunks by bytes
+    ChunkDesc *chunks[3] = {nullptr, nullptr, nullptr};
+    int *stage_chunk[3] = {nullptr, nullptr, nullptr};
+    int nchunks[3] = {0, 0, 0}, max_stage_chunks[3] = {0, 0, 0};
+    size_t buf[3] = {0, 0, 0};   // shared-memory bytes of one chunk buffer
+    unsigned *gbar = nullptr;   // counters of the consumer grid barrier
+    Lvl2View view2(int tab = V2_TAB_FULL) const { return Lvl2View{n, ng, nchunks[tab], plan.nstages(), meta2, CL, VL, CU, VU, BD, chunks[tab], stage_chunk[tab]}; }
 };
 
 struct ProfRec {
@@ -258,7 +260,7 @@ static int v2_blocks_per_sm(size_t dyn)
         attr_set = true;
     }
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_level_pass<MODE>, kV2Threads, dyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_level_pass<MODE>, v2_threads(MODE), dyn);
     return std::max(nb, 1);
 }
 // returns the grid used (number of partial sums for SPMV with a dot)
@@ -267,25 +269,26 @@ static int launch_v2(Engine *h, Level &L, int kclass, int l, double bytes, const
                      const double *w, double *partial, const int *done)
 {
     const bool staged = (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD);
-    size_t buf = (MODE == V2_FWD_ZERO || MODE == V2_RESID) ? L.buf_lo : (MODE == V2_BWD ? L.buf_up : L.buf_full);
+    constexpr int tab = v2_table(MODE);
+    size_t buf = L.buf[tab];
     size_t dyn = (size_t)kV2Bufs * buf;
     int per_sm = v2_blocks_per_sm<MODE>(dyn);
     int cap = per_sm * h->sms;
-    int grid = std::min(staged ? L.max_stage_chunks : L.nchunks, cap);
+    int grid = std::min(staged ? L.max_stage_chunks[tab] : L.nchunks[tab], cap);
     if (MODE == V2_SPMV && w) grid = std::min(grid, kNumPart);
     grid = std::max(grid, 1);
     if (std::getenv("DDPCA_VERBOSE")) {
         static int shown = 0;
-        if (shown++ < 40) std::fprintf(stderr, "ddpca v2: level n=%d mode=%d buf=%zu B x%d, %d CTA/SM, grid=%d, chunks=%d (max/stage %d)\n", L.n, MODE, buf, kV2Bufs, per_sm, grid, L.nchunks, L.max_stage_chunks);
+        if (shown++ < 40) std::fprintf(stderr, "ddpca v2: level n=%d mode=%d buf=%zu B x%d, %d CTA/SM, grid=%d, chunks=%d (max/stage %d)\n", L.n, MODE, buf, kV2Bufs, per_sm, grid, L.nchunks[tab], L.max_stage_chunks[tab]);
     }
-    Lvl2View A = L.view2();
+    Lvl2View A = L.view2(tab);
     unsigned *gbar = L.gbar;
     h->pre(kclass, l, bytes);
     if (staged && L.plan.nstages() > 1) {
         void *args[] = {(void *)&A, (void *)&buf, (void *)&gbar, (void *)&b, (void *)&x, (void *)&p1, (void *)&y, (void *)&w, (void *)&partial, (void *)&done};
-        cudaLaunchCooperativeKernel((const void *)k_level_pass<MODE>, dim3(grid), dim3(kV2Threads), args, dyn, h->stream);
+        cudaLaunchCooperativeKernel((const void *)k_level_pass<MODE>, dim3(grid), dim3(v2_threads(MODE)), args, dyn, h->stream);
     } else {
-        k_level_pass<MODE><<<grid, kV2Threads, dyn, h->stream>>>(A, buf, gbar, b, x, p1, y, w, partial, done);
+        k_level_pass<MODE><<<grid, v2_threads(MODE), dyn, h->stream>>>(A, buf, gbar, b, x, p1, y, w, partial, done);
     }
     h->post();
     return grid;
@@ -624,11 +627,13 @@ static bool build_group_layout(const CsrHost &Ap, const LevelPlan &pl, GroupLayo
 // ---- v2 layout (kernels2.cuh): split lower / upper arrays in stage order + chunk table -----------
 struct Layout2Host {
     std::vector<GroupMeta2> meta;
-    std::vector<int> CL, CU, stage_chunk;
+    std::vector<int> CL, CU;
     std::vector<double> VL, VU, BD;
-    std::vector<ChunkDesc> chunks;
-    size_t buf_lo = 0, buf_up = 0, buf_full = 0;
-    int max_stage_chunks = 0;
+    // per chunk table (V2_TAB_*)
+    std::vector<ChunkDesc> chunks[3];
+    std::vector<int> stage_chunk[3];
+    size_t buf[3] = {0, 0, 0};
+    int max_stage_chunks[3] = {0, 0, 0};
 };
 static inline int round4(int v) { return (v + 3) & ~3; }
 
@@ -674,30 +679,53 @@ static bool build_layout2(const CsrHost &Ap, const LevelPlan &pl, Layout2Host &o
             for (int c = 0; c < gs; c++) out.BD[(size_t)g * kBlkStride + r * 3 + c] = vr[kd + c];
         }
     }
-    // chunks: kChunkGroups consecutive groups, never across a stage boundary
+    // Chunks: consecutive groups, never across a stage boundary.  Whole-row passes take kChunkGroups
+    // groups per chunk; the half-pass tables take groups while the streamed bytes stay within the
+    // largest whole-row chunk (up to kHalfGroups), so a chunk carries the same traffic in every pass.
     const int ns = pl.nstages();
-    out.stage_chunk.assign(ns + 1, 0);
-    for (int s = 0; s < ns; s++) {
-        out.stage_chunk[s] = (int)out.chunks.size();
-        for (int g0 = pl.stage_group[s]; g0 < pl.stage_group[s + 1]; g0 += kChunkGroups) {
-            int g1 = std::min(g0 + kChunkGroups, pl.stage_group[s + 1]);
-            ChunkDesc d{};
-            d.g0 = g0; d.ng = g1 - g0;
-            const GroupMeta2 &a = out.meta[g0], &z = out.meta[g1 - 1];
-            d.cl0 = a.cl; d.ncl = z.cl + z.nl - a.cl;
-            d.cu0 = a.cu; d.ncu = z.cu + z.nu - a.cu;
-            d.vl0 = a.vl; d.nvl = z.vl + z.gs * z.nl / 2 - a.vl;
-            d.vu0 = a.vu; d.nvu = z.vu + z.gs * z.nu / 2 - a.vu;
-            out.chunks.push_back(d);
-            out.buf_lo = std::max(out.buf_lo, v2_chunk_bytes(V2_FWD_ZERO, d.ncl, d.nvl, d.ncu, d.nvu));
-            out.buf_up = std::max(out.buf_up, v2_chunk_bytes(V2_BWD, d.ncl, d.nvl, d.ncu, d.nvu));
-            out.buf_full = std::max(out.buf_full, v2_chunk_bytes(V2_FWD_FULL, d.ncl, d.nvl, d.ncu, d.nvu));
+    auto make_desc = [&](int g0, int g1) {
+        ChunkDesc d{};
+        d.g0 = g0; d.ng = g1 - g0;
+        const GroupMeta2 &a = out.meta[g0], &z = out.meta[g1 - 1];
+        d.cl0 = a.cl; d.ncl = z.cl + z.nl - a.cl;
+        d.cu0 = a.cu; d.ncu = z.cu + z.nu - a.cu;
+        d.vl0 = a.vl; d.nvl = z.vl + z.gs * z.nl / 2 - a.vl;
+        d.vu0 = a.vu; d.nvu = z.vu + z.gs * z.nu / 2 - a.vu;
+        return d;
+    };
+    size_t budget = 0;   // streamed bytes (patterns + values) of the largest whole-row chunk
+    for (int tab = 0; tab < 3; tab++) {
+        const int mode = tab == V2_TAB_FULL ? V2_FWD_FULL : (tab == V2_TAB_LO ? V2_FWD_ZERO : V2_BWD);
+        const int cap = v2_groups(mode);
+        const size_t fixed = v2_chunk_bytes(mode, 0, 0, 0, 0);
+        std::vector<ChunkDesc> &ch = out.chunks[tab];
+        std::vector<int> &sc = out.stage_chunk[tab];
+        sc.assign(ns + 1, 0);
+        for (int s = 0; s < ns; s++) {
+            sc[s] = (int)ch.size();
+            int g0 = pl.stage_group[s];
+            const int gend = pl.stage_group[s + 1];
+            while (g0 < gend) {
+                int g1 = g0 + 1;
+                if (tab == V2_TAB_FULL) g1 = std::min(g0 + cap, gend);
+                else
+                    while (g1 < gend && g1 - g0 < cap) {
+                        ChunkDesc t = make_desc(g0, g1 + 1);
+                        if (v2_chunk_bytes(mode, t.ncl, t.nvl, t.ncu, t.nvu) - fixed > budget / kHalfBudgetDiv) break;
+                        g1++;
+                    }
+                ChunkDesc d = make_desc(g0, g1);
+                ch.push_back(d);
+                size_t b = v2_chunk_bytes(mode, d.ncl, d.nvl, d.ncu, d.nvu);
+                out.buf[tab] = std::max(out.buf[tab], b);
+                if (tab == V2_TAB_FULL) budget = std::max(budget, b - fixed);
+                g0 = g1;
+            }
+            out.max_stage_chunks[tab] = std::max(out.max_stage_chunks[tab], (int)ch.size() - sc[s]);
         }
-        out.max_stage_chunks = std::max(out.max_stage_chunks, (int)out.chunks.size() - out.stage_chunk[s]);
+        sc[ns] = (int)ch.size();
+        out.buf[tab] = (out.buf[tab] + 127) & ~(size_t)127;
     }
-    out.stage_chunk[ns] = (int)out.chunks.size();
-    auto r128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
-    out.buf_lo = r128(out.buf_lo); out.buf_up = r128(out.buf_up); out.buf_full = r128(out.buf_full);
     return true;
 }
 
@@ -758,7 +786,8 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
         Layout2Host H2;
         if (want_v2) {
             if (!build_layout2(Ap, L.plan, H2, err)) return fail(err);
-            if ((size_t)kV2Bufs * H2.buf_full > 200 * 1024) want_v2 = false;   // the chunk ring must fit in shared memory
+            for (int tab = 0; tab < 3; tab++)
+                if ((size_t)kV2Bufs * H2.buf[tab] > 200 * 1024) want_v2 = false;   // the chunk ring must fit in shared memory
         }
         L.v2 = want_v2;
         L.ng = (int)G.meta.size();
@@ -771,13 +800,16 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
             L.bytes_full += (8.0 * m.gs + 4.0) * m.pad + 32.0 + 16.0 * m.gs;   // + x once, y once
         }
         if (L.v2) {
-            L.nchunks = (int)H2.chunks.size();
-            L.max_stage_chunks = H2.max_stage_chunks;
-            L.buf_lo = H2.buf_lo; L.buf_up = H2.buf_up; L.buf_full = H2.buf_full;
+            for (int tab = 0; tab < 3; tab++) {
+                L.nchunks[tab] = (int)H2.chunks[tab].size();
+                L.max_stage_chunks[tab] = H2.max_stage_chunks[tab];
+                L.buf[tab] = H2.buf[tab];
+                if (upload_vec(H2.chunks[tab], &L.chunks[tab]) || upload_vec(H2.stage_chunk[tab], &L.stage_chunk[tab])) return 1;
+            }
             CU(cudaMalloc(&L.gbar, kGbarWords * sizeof(unsigned)));
             CU(cudaMemset(L.gbar, 0, kGbarWords * sizeof(unsigned)));
             if (upload_vec(H2.meta, &L.meta2) || upload_vec(H2.CL, &L.CL) || upload_vec(H2.CU, &L.CU) || upload_vec(H2.VL, &L.VL) ||
-                upload_vec(H2.VU, &L.VU) || upload_vec(H2.BD, &L.BD) || upload_vec(H2.chunks, &L.chunks) || upload_vec(H2.stage_chunk, &L.stage_chunk)) return 1;
+                upload_vec(H2.VU, &L.VU) || upload_vec(H2.BD, &L.BD)) return 1;
         } else {
             if (upload_vec(G.meta, &L.meta) || upload_vec(G.ci, &L.gci) || upload_vec(G.v, &L.gv)) return 1;
         }
@@ -794,8 +826,9 @@ static void free_level(Level &L)
     free_csr(L.A); free_csr(L.P); free_csr(L.R);
     cudaFree(L.meta); cudaFree(L.gci); cudaFree(L.gv); cudaFree(L.stage_group); cudaFree(L.perm);
     cudaFree(L.x); cudaFree(L.b); cudaFree(L.p1); cudaFree(L.r); cudaFree(L.dinv);
-    cudaFree(L.meta2); cudaFree(L.CL); cudaFree(L.CU); cudaFree(L.stage_chunk); cudaFree(L.VL); cudaFree(L.VU); cudaFree(L.BD); cudaFree(L.chunks); cudaFree(L.gbar); L.gbar = nullptr;
-    L.meta2 = nullptr; L.CL = L.CU = L.stage_chunk = nullptr; L.VL = L.VU = L.BD = nullptr; L.chunks = nullptr;
+    cudaFree(L.meta2); cudaFree(L.CL); cudaFree(L.CU); cudaFree(L.VL); cudaFree(L.VU); cudaFree(L.BD); cudaFree(L.gbar); L.gbar = nullptr;
+    for (int tab = 0; tab < 3; tab++) { cudaFree(L.chunks[tab]); cudaFree(L.stage_chunk[tab]); L.chunks[tab] = nullptr; L.stage_chunk[tab] = nullptr; }
+    L.meta2 = nullptr; L.CL = L.CU = nullptr; L.VL = L.VU = L.BD = nullptr;
     L.meta = nullptr; L.gci = nullptr; L.gv = nullptr; L.stage_group = nullptr; L.perm = nullptr;
     L.x = L.b = L.p1 = L.r = L.dinv = nullptr;
 }
