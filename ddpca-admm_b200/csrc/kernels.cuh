@@ -493,7 +493,9 @@ __global__ void __launch_bounds__(256) k_spmv(CsrView A, double alpha, const dou
     if (DOT) block_sum_to_partial(acc, partial);
 }
 
-// K7: level-0 direct solve as a dense symmetric GEMV with the precomputed inverse
+// K7: level-0 direct solve as a dense symmetric GEMV with the precomputed inverse.  One warp per row;
+// 16-byte streaming loads, four independent partial sums per lane (eight loads in flight) -- the rows
+// are short (a few thousand entries), so memory-level parallelism per warp is what sets the rate.
 __global__ void __launch_bounds__(256) k_dense_gemv(int n, const double *__restrict__ B, const double *__restrict__ x,
                                                     double *__restrict__ y, const int *done)
 {
@@ -503,7 +505,29 @@ __global__ void __launch_bounds__(256) k_dense_gemv(int n, const double *__restr
     if (i >= n) return;
     const double *row = B + (size_t)i * n;
     double s = 0.0;
-    for (int j = lane; j < n; j += 32) s += ld_stream(row + j) * __ldg(x + j);
+    if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0) {
+        const int n2 = n >> 1;
+        const double2 *x2 = reinterpret_cast<const double2 *>(x);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int j = lane;
+        for (; j + 96 < n2; j += 128) {
+            const double2 a0 = ld_stream2(row + 2 * j), a1 = ld_stream2(row + 2 * (j + 32));
+            const double2 a2 = ld_stream2(row + 2 * (j + 64)), a3 = ld_stream2(row + 2 * (j + 96));
+            const double2 b0 = __ldg(x2 + j), b1 = __ldg(x2 + j + 32), b2 = __ldg(x2 + j + 64), b3 = __ldg(x2 + j + 96);
+            s0 += a0.x * b0.x + a0.y * b0.y;
+            s1 += a1.x * b1.x + a1.y * b1.y;
+            s2 += a2.x * b2.x + a2.y * b2.y;
+            s3 += a3.x * b3.x + a3.y * b3.y;
+        }
+        for (; j < n2; j += 32) {
+            const double2 a0 = ld_stream2(row + 2 * j);
+            const double2 b0 = __ldg(x2 + j);
+            s0 += a0.x * b0.x + a0.y * b0.y;
+        }
+        s = (s0 + s1) + (s2 + s3);
+    } else {
+        for (int j = lane; j < n; j += 32) s += ld_stream(row + j) * __ldg(x + j);
+    }
     s = warp_sum(s);
     if (lane == 0) y[i] = s;
 }
@@ -638,12 +662,23 @@ __global__ void __launch_bounds__(256) k_dot(int n, const double *__restrict__ a
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += a[i] * b[i];
     block_sum_to_partial(acc, partial);
 }
-// x += alpha p ; r -= alpha q ; partial = r.r   (MGPIS.h:202-203 and the norm of :198)
-__global__ void __launch_bounds__(256) k_update_xr(int n, const PcgState *st, const double *__restrict__ p, const double *__restrict__ q,
+// alpha = delta_new / (p.q) ; x += alpha p ; r -= alpha q ; partial = r.r   (MGPIS.h:201-203 and the norm of :198)
+// Every CTA finishes the p.q reduction itself (same fixed order => same alpha everywhere); CTA 0 records it.
+__global__ void __launch_bounds__(256) k_update_xr(int n, PcgState *st, const double *__restrict__ pq_partial, int npq,
+                                                   const double *__restrict__ p, const double *__restrict__ q,
                                                    double *__restrict__ x, double *__restrict__ r, double *partial)
 {
     if (st->done) return;
-    const double alpha = st->alpha;
+    __shared__ double s_alpha;
+    if (threadIdx.x < 32) {
+        const double pq = warp_reduce_partials(pq_partial, npq);
+        if (threadIdx.x == 0) {
+            s_alpha = st->delta_new / pq;
+            if (blockIdx.x == 0) { st->pq = pq; st->alpha = s_alpha; }
+        }
+    }
+    __syncthreads();
+    const double alpha = s_alpha;
     double acc = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         x[i] += alpha * p[i];
@@ -689,37 +724,28 @@ __global__ void k_s_delta0(PcgState *st, const double *partial, int np, cudaGrap
     }
     if (use_cond && threadIdx.x == 0) cudaGraphSetConditional(cond, st->done ? 0u : 1u);
 }
-// alpha = delta_new / (p.q)   (MGPIS.h:201)
-__global__ void k_s_alpha(PcgState *st, const double *partial, int np)
+// rr = r.r ; delta_old = delta_new ; delta_new = r.z ; beta = delta_new/delta_old ; it++ and the loop
+// condition `it < maxit && ||r|| > tol` (MGPIS.h:211-213,219,198) -- one launch, two warps reduce.
+// p = z + beta p (k_update_p) runs after it and is skipped once done is set: p is dead by then.
+__global__ void k_s_beta_next(PcgState *st, const double *rr_partial, const double *rz_partial, int np,
+                              cudaGraphConditionalHandle cond, int use_cond)
 {
-    if (st->done) return;
-    const double pq = warp_reduce_partials(partial, np);
-    if (threadIdx.x == 0) { st->pq = pq; st->alpha = st->delta_new / pq; }
-}
-// rr = r.r
-__global__ void k_s_rr(PcgState *st, const double *partial, int np)
-{
-    if (st->done) return;
-    const double rr = warp_reduce_partials(partial, np);
-    if (threadIdx.x == 0) st->rr = rr;
-}
-// delta_old = delta_new; delta_new = r.z; beta = delta_new/delta_old   (MGPIS.h:211-213)
-__global__ void k_s_beta(PcgState *st, const double *partial, int np)
-{
-    if (st->done) return;
-    const double rz = warp_reduce_partials(partial, np);
-    if (threadIdx.x == 0) { st->delta_old = st->delta_new; st->delta_new = rz; st->beta = rz / st->delta_old; }
-}
-// end of an iteration: it++ and re-evaluate `it < maxit && ||r|| > tol` (MGPIS.h:219,198)
-__global__ void k_s_next(PcgState *st, cudaGraphConditionalHandle cond, int use_cond)
-{
-    if (!st->done) {
-        st->it += 1;
-        if (!(st->it < st->maxit && sqrt(st->rr) > st->tol)) st->done = 1;
+    __shared__ double s_rr;
+    if (!st->done) {   // uniform
+        const double t = warp_reduce_partials(threadIdx.x < 32 ? rr_partial : rz_partial, np);
+        if (threadIdx.x == 0) s_rr = t;
+        __syncthreads();
+        if (threadIdx.x == 32) {
+            const double rr = s_rr;
+            st->rr = rr;
+            st->delta_old = st->delta_new; st->delta_new = t; st->beta = t / st->delta_old;
+            st->it += 1;
+            if (!(st->it < st->maxit && sqrt(rr) > st->tol)) st->done = 1;
+        }
+        __syncthreads();
     }
-    if (use_cond) cudaGraphSetConditional(cond, st->done ? 0u : 1u);
+    if (use_cond && threadIdx.x == 0) cudaGraphSetConditional(cond, st->done ? 0u : 1u);
 }
-
 // ---- ADMM interface kernels (MCONTACT.h:2632-2668, :2737-2833) ---------------------------------
 // gamma = 0.5*(t - gapTerm) followed by the contact projection; t already holds
 // inpoLagr0 l0 - inpoLagr1 l1 + pemaInpo_r0 u0 - pemaInpo_r1 u1.

@@ -83,6 +83,8 @@ constexpr int kBlkStride = 10;     // doubles per in-group block record (9 used;
 
 struct Lvl2View {
     int n, ng, nchunks, nstages;
+    int fuse_bwd_last;   // 1: no group of the last stage has couplings above it -- the forward sweeps finish that
+                         // stage with its backward substitution and the backward sweep starts one stage earlier
     const GroupMeta2 *__restrict__ meta;
     const int *__restrict__ CL;
     const double *__restrict__ VL;
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(v2_threads(MODE)) k_level_pass(Lvl2View A, siz
     const int *sc = sc_smem ? s_stage_chunk : A.stage_chunk;
 
     // this CTA's chunk sequence: stage after stage, chunks c = first(stage) + blockIdx.x + j * gridDim.x
-    const int nst = STAGED ? A.nstages : 1;
+    const int nst = STAGED ? (MODE == V2_BWD ? A.nstages - A.fuse_bwd_last : A.nstages) : 1;
     auto stage_of = [&](int si) { return STAGED ? (MODE == V2_BWD ? (nst - 1 - si) : si) : 0; };
     auto c_begin = [&](int si) { return STAGED ? sc[stage_of(si)] : 0; };
     auto c_end = [&](int si) { return STAGED ? sc[stage_of(si) + 1] : A.nchunks; };
@@ -488,11 +490,31 @@ __global__ void __launch_bounds__(v2_threads(MODE)) k_level_pass(Lvl2View A, siz
                             }
                             const double up = sU[r] + inU, dg = blk[r * 3 + r];
                             xn[r] = (rhs[r] - sL[r] - inL - up) / dg;
-                            if (sl == 0) {
-                                x[r0 + r] = xn[r];
-                                p1[r0 + r] = dg * xn[r] + up;
+                            rhs[r] = dg * xn[r] + up;   // p1 (MGPIS.h:71)
+                            if (sl == 0) p1[r0 + r] = rhs[r];
+                        }
+                    }
+                    if (A.fuse_bwd_last && si == nst - 1) {
+                        // last colour: the backward sweep's step for these rows (MGPIS.h:73-76) only involves
+                        // the group itself -- do it now, the backward launch starts at the previous colour
+                        double xb[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                        for (int r = 2; r >= 0; r--) {
+                            if (r < gs) {
+                                double inU = 0.0;
+#pragma unroll
+                                for (int cc = 0; cc < 3; cc++)
+                                    if (cc > r) inU += blk[r * 3 + cc] * xb[cc];
+                                xb[r] = (rhs[r] - sU[r] - inU) / blk[r * 3 + r];
                             }
                         }
+#pragma unroll
+                        for (int r = 0; r < 3; r++) xn[r] = xb[r];
+                    }
+                    if (sl == 0) {
+#pragma unroll
+                        for (int r = 0; r < 3; r++)
+                            if (r < gs) x[r0 + r] = xn[r];
                     }
                 } else if (MODE == V2_BWD) {
                     double xn[3] = {0.0, 0.0, 0.0};

@@ -89,7 +89,9 @@ struct Level {
     int nchunks[3] = {0, 0, 0}, max_stage_chunks[3] = {0, 0, 0};
     size_t buf[3] = {0, 0, 0};   // shared-memory bytes of one chunk buffer
     unsigned *gbar = nullptr;   // counters of the consumer grid barrier
-    Lvl2View view2(int tab = V2_TAB_FULL) const { return Lvl2View{n, ng, nchunks[tab], plan.nstages(), meta2, CL, VL, CU, VU, BD, chunks[tab], stage_chunk[tab]}; }
+    int fuse_bwd_last = 0;       // the forward sweeps also do the backward step of the last colour (see Lvl2View)
+    double bytes_bwd_skip = 0;   // algorithmic bytes the backward sweep no longer touches then
+    Lvl2View view2(int tab = V2_TAB_FULL) const { return Lvl2View{n, ng, nchunks[tab], plan.nstages(), fuse_bwd_last, meta2, CL, VL, CU, VU, BD, chunks[tab], stage_chunk[tab]}; }
 };
 
 struct ProfRec {
@@ -269,6 +271,8 @@ static int launch_v2(Engine *h, Level &L, int kclass, int l, double bytes, const
                      const double *w, double *partial, const int *done)
 {
     const bool staged = (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD);
+    const int nst = L.plan.nstages() - (MODE == V2_BWD ? L.fuse_bwd_last : 0);   // stages this launch walks
+    if (nst <= 0) return 0;
     constexpr int tab = v2_table(MODE);
     size_t buf = L.buf[tab];
     size_t dyn = (size_t)kV2Bufs * buf;
@@ -284,7 +288,7 @@ static int launch_v2(Engine *h, Level &L, int kclass, int l, double bytes, const
     Lvl2View A = L.view2(tab);
     unsigned *gbar = L.gbar;
     h->pre(kclass, l, bytes);
-    if (staged && L.plan.nstages() > 1) {
+    if (staged && nst > 1) {
         void *args[] = {(void *)&A, (void *)&buf, (void *)&gbar, (void *)&b, (void *)&x, (void *)&p1, (void *)&y, (void *)&w, (void *)&partial, (void *)&done};
         cudaLaunchCooperativeKernel((const void *)k_level_pass<MODE>, dim3(grid), dim3(v2_threads(MODE)), args, dyn, h->stream);
     } else {
@@ -335,7 +339,7 @@ static void sweep_fwd(Engine *h, Level &L, int l, const double *b, double *x, bo
 static void sweep_bwd(Engine *h, Level &L, int l, double *x, const int *done)
 {
     if (L.v2) {
-        launch_v2<V2_BWD>(h, L, DDPCA_K_SWEEP_BWD, l, L.bytes_upper, nullptr, x, L.p1, nullptr, nullptr, nullptr, done);
+        launch_v2<V2_BWD>(h, L, DDPCA_K_SWEEP_BWD, l, L.bytes_upper - L.bytes_bwd_skip, nullptr, x, L.p1, nullptr, nullptr, nullptr, done);
         return;
     }
     for (int k = (int)L.segs.size() - 1; k >= 0; k--) {
@@ -393,15 +397,12 @@ static void enqueue_iteration(ddpca_mg *h, int prec, cudaGraphConditionalHandle 
     const int *done = &h->st->done;
     int n = L.n;
     int gq = launch_level_spmv(h, L, Lf, h->cg_p, h->cg_q, h->cg_p, h->partial[0], done);  // :200 + p.q
-    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_alpha<<<1, 32, 0, h->stream>>>(h->st, h->partial[0], gq)));  // :201
     int gv = vec_grid(h, n);
-    KL(h, DDPCA_K_VECTOR, Lf, 48.0 * n, (k_update_xr<<<gv, 256, 0, h->stream>>>(n, h->st, h->cg_p, h->cg_q, h->cg_x, h->cg_r, h->partial[1])));  // :202-203
-    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_rr<<<1, 32, 0, h->stream>>>(h->st, h->partial[1], gv)));
+    KL(h, DDPCA_K_VECTOR, Lf, 48.0 * n, (k_update_xr<<<gv, 256, 0, h->stream>>>(n, h->st, h->partial[0], gq, h->cg_p, h->cg_q, h->cg_x, h->cg_r, h->partial[1])));  // :201-203
     precondition(h, prec, h->cg_r, h->cg_z, done);  // :204-210
     KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, h->cg_r, h->cg_z, h->partial[2], done)));  // :212
-    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_beta<<<1, 32, 0, h->stream>>>(h->st, h->partial[2], gv)));                       // :211-213
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_beta_next<<<1, 64, 0, h->stream>>>(h->st, h->partial[1], h->partial[2], gv, cond, use_cond)));  // :211-213,219,198
     KL(h, DDPCA_K_VECTOR, Lf, 24.0 * n, (k_update_p<<<gv, 256, 0, h->stream>>>(n, h->st, h->cg_z, h->cg_p)));            // :214
-    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_next<<<1, 1, 0, h->stream>>>(h->st, cond, use_cond)));                                           // :219,198
 }
 
 // set-up of a solve after r = b, x = 0 (MGPIS.h:174-197): tolerance, first preconditioner application, delta_new
@@ -637,6 +638,60 @@ struct Layout2Host {
 };
 static inline int round4(int v) { return (v + 3) & ~3; }
 
+// Chunk tables of the v2 layout: consecutive groups, never across a stage boundary.  Whole-row passes
+// take kChunkGroups groups per chunk; the half-pass tables take groups while the streamed bytes stay
+// within 1/kHalfBudgetDiv of the largest whole-row chunk (at most kHalfGroups groups).
+// (Re-cutting a colour into a multiple of the grid of equal chunks, so that no CTA waits for a last,
+// nearly empty round, was measured and is slower: more, smaller chunks cost more than the tails.)
+static void build_chunks2(const LevelPlan &pl, Layout2Host &out)
+{
+    const int ns = pl.nstages();
+    auto make_desc = [&](int g0, int g1) {
+        ChunkDesc d{};
+        d.g0 = g0; d.ng = g1 - g0;
+        const GroupMeta2 &a = out.meta[g0], &z = out.meta[g1 - 1];
+        d.cl0 = a.cl; d.ncl = z.cl + z.nl - a.cl;
+        d.cu0 = a.cu; d.ncu = z.cu + z.nu - a.cu;
+        d.vl0 = a.vl; d.nvl = z.vl + z.gs * z.nl / 2 - a.vl;
+        d.vu0 = a.vu; d.nvu = z.vu + z.gs * z.nu / 2 - a.vu;
+        return d;
+    };
+    size_t budget = 0;   // streamed bytes (patterns + values) of the largest whole-row chunk
+    for (int tab = 0; tab < 3; tab++) {
+        const int mode = tab == V2_TAB_FULL ? V2_FWD_FULL : (tab == V2_TAB_LO ? V2_FWD_ZERO : V2_BWD);
+        const int cap = v2_groups(mode);
+        const size_t fixed = v2_chunk_bytes(mode, 0, 0, 0, 0);
+        auto data_bytes = [&](const ChunkDesc &d) { return v2_chunk_bytes(mode, d.ncl, d.nvl, d.ncu, d.nvu) - fixed; };
+        std::vector<ChunkDesc> &ch = out.chunks[tab];
+        std::vector<int> &sc = out.stage_chunk[tab];
+        ch.clear();
+        out.buf[tab] = 0; out.max_stage_chunks[tab] = 0;
+        sc.assign(ns + 1, 0);
+        const size_t lim = tab == V2_TAB_FULL ? (size_t)-1 : budget / kHalfBudgetDiv;
+        std::vector<ChunkDesc> st;
+        for (int s = 0; s < ns; s++) {
+            sc[s] = (int)ch.size();
+            const int gbeg = pl.stage_group[s], gend = pl.stage_group[s + 1];
+            st.clear();
+            for (int g0 = gbeg; g0 < gend;) {
+                int g1 = g0 + 1;
+                while (g1 < gend && g1 - g0 < cap && data_bytes(make_desc(g0, g1 + 1)) <= lim) g1++;
+                st.push_back(make_desc(g0, g1));
+                g0 = g1;
+            }
+            for (const ChunkDesc &d : st) {
+                ch.push_back(d);
+                const size_t b = fixed + data_bytes(d);
+                out.buf[tab] = std::max(out.buf[tab], b);
+                if (tab == V2_TAB_FULL) budget = std::max(budget, b - fixed);
+            }
+            out.max_stage_chunks[tab] = std::max(out.max_stage_chunks[tab], (int)ch.size() - sc[s]);
+        }
+        sc[ns] = (int)ch.size();
+        out.buf[tab] = (out.buf[tab] + 127) & ~(size_t)127;
+    }
+}
+
 static bool build_layout2(const CsrHost &Ap, const LevelPlan &pl, Layout2Host &out, std::string &err)
 {
     const int ng = pl.ngroups();
@@ -679,53 +734,7 @@ static bool build_layout2(const CsrHost &Ap, const LevelPlan &pl, Layout2Host &o
             for (int c = 0; c < gs; c++) out.BD[(size_t)g * kBlkStride + r * 3 + c] = vr[kd + c];
         }
     }
-    // Chunks: consecutive groups, never across a stage boundary.  Whole-row passes take kChunkGroups
-    // groups per chunk; the half-pass tables take groups while the streamed bytes stay within the
-    // largest whole-row chunk (up to kHalfGroups), so a chunk carries the same traffic in every pass.
-    const int ns = pl.nstages();
-    auto make_desc = [&](int g0, int g1) {
-        ChunkDesc d{};
-        d.g0 = g0; d.ng = g1 - g0;
-        const GroupMeta2 &a = out.meta[g0], &z = out.meta[g1 - 1];
-        d.cl0 = a.cl; d.ncl = z.cl + z.nl - a.cl;
-        d.cu0 = a.cu; d.ncu = z.cu + z.nu - a.cu;
-        d.vl0 = a.vl; d.nvl = z.vl + z.gs * z.nl / 2 - a.vl;
-        d.vu0 = a.vu; d.nvu = z.vu + z.gs * z.nu / 2 - a.vu;
-        return d;
-    };
-    size_t budget = 0;   // streamed bytes (patterns + values) of the largest whole-row chunk
-    for (int tab = 0; tab < 3; tab++) {
-        const int mode = tab == V2_TAB_FULL ? V2_FWD_FULL : (tab == V2_TAB_LO ? V2_FWD_ZERO : V2_BWD);
-        const int cap = v2_groups(mode);
-        const size_t fixed = v2_chunk_bytes(mode, 0, 0, 0, 0);
-        std::vector<ChunkDesc> &ch = out.chunks[tab];
-        std::vector<int> &sc = out.stage_chunk[tab];
-        sc.assign(ns + 1, 0);
-        for (int s = 0; s < ns; s++) {
-            sc[s] = (int)ch.size();
-            int g0 = pl.stage_group[s];
-            const int gend = pl.stage_group[s + 1];
-            while (g0 < gend) {
-                int g1 = g0 + 1;
-                if (tab == V2_TAB_FULL) g1 = std::min(g0 + cap, gend);
-                else
-                    while (g1 < gend && g1 - g0 < cap) {
-                        ChunkDesc t = make_desc(g0, g1 + 1);
-                        if (v2_chunk_bytes(mode, t.ncl, t.nvl, t.ncu, t.nvu) - fixed > budget / kHalfBudgetDiv) break;
-                        g1++;
-                    }
-                ChunkDesc d = make_desc(g0, g1);
-                ch.push_back(d);
-                size_t b = v2_chunk_bytes(mode, d.ncl, d.nvl, d.ncu, d.nvu);
-                out.buf[tab] = std::max(out.buf[tab], b);
-                if (tab == V2_TAB_FULL) budget = std::max(budget, b - fixed);
-                g0 = g1;
-            }
-            out.max_stage_chunks[tab] = std::max(out.max_stage_chunks[tab], (int)ch.size() - sc[s]);
-        }
-        sc[ns] = (int)ch.size();
-        out.buf[tab] = (out.buf[tab] + 127) & ~(size_t)127;
-    }
+    build_chunks2(pl, out);
     return true;
 }
 
@@ -800,6 +809,18 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
             L.bytes_full += (8.0 * m.gs + 4.0) * m.pad + 32.0 + 16.0 * m.gs;   // + x once, y once
         }
         if (L.v2) {
+            // fwd -> bwd junction: the last colour has nothing above its groups (it is ordered last)
+            {
+                const int ns = L.plan.nstages();
+                bool none_above = ns >= 1 && !std::getenv("DDPCA_NO_FUSE_BWD");
+                for (int g = L.plan.stage_group[ns - 1]; none_above && g < L.plan.stage_group[ns]; g++) none_above = (H2.meta[g].nu == 0);
+                L.fuse_bwd_last = none_above ? 1 : 0;
+                if (none_above)
+                    for (int g = L.plan.stage_group[ns - 1]; g < L.plan.stage_group[ns]; g++) {
+                        const int gs = H2.meta[g].gs;
+                        L.bytes_bwd_skip += 32.0 + 8.0 * gs * gs + 32.0 * gs;
+                    }
+            }
             for (int tab = 0; tab < 3; tab++) {
                 L.nchunks[tab] = (int)H2.chunks[tab].size();
                 L.max_stage_chunks[tab] = H2.max_stage_chunks[tab];
@@ -1156,6 +1177,9 @@ int ddpca_mg_create(int device, int nlevels, const int *n, const int *const *row
             CsrHost Pp, Rp;
             // realProl[l-1]: n_l x n_{l-1}; rows follow level l's permutation, columns level l-1's
             permute_csr(n[l], n[l - 1], P_rowptr[l - 1], P_colidx[l - 1], P_val[l - 1], L.plan.perm, h->lev[l - 1].plan.iperm, Pp);
+            // the reference stores realProl with explicit zeros (a 3x3 block per node pair, diagonal only
+            // non-zero): x + 0 * y == x, so they are dropped -- two thirds of the transfer operators' bytes
+            drop_zeros_csr(Pp);
             transpose_csr(Pp, Rp);
             FAILC(upload_csr(Pp, L.P));
             FAILC(upload_csr(Rp, L.R));

@@ -195,4 +195,20 @@ void transpose_csr(const CsrHost &A, CsrHost &out)
         }
 }
 
+long drop_zeros_csr(CsrHost &A)
+{
+    long w = 0, nnz = A.nnz();
+    int start = 0;
+    for (int i = 0; i < A.rows; i++) {
+        const int end = A.rp[i + 1];
+        for (int p = start; p < end; p++)
+            if (A.v[p] != 0.0) { A.ci[w] = A.ci[p]; A.v[w] = A.v[p]; w++; }
+        start = end;
+        A.rp[i + 1] = (int)w;
+    }
+    A.ci.resize(w);
+    A.v.resize(w);
+    return nnz - w;
+}
+
 }  // namespace ddpca

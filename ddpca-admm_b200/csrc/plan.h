@@ -52,5 +52,7 @@ void permute_csr(int rows, int cols, const int *rp, const int *ci, const double 
 
 // out = A^T (sorted columns)
 void transpose_csr(const CsrHost &A, CsrHost &out);
+// Removes stored entries whose value is exactly 0.0 (in place); returns how many were dropped.
+long drop_zeros_csr(CsrHost &A);
 
 }  // namespace ddpca
