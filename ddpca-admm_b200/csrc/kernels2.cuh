@@ -77,7 +77,7 @@ struct __align__(16) ChunkDesc {
     int cu0, ncu;
     int vl0, nvl;    // value range in 16-byte units
     int vu0, nvu;
-    int dep0, ndep;  // range in dep_idx: the chunks (same table) this one waits for in a dataflow sweep
+    int pad0, pad1;
 };
 constexpr int kBlkStride = 10;     // doubles per in-group block record (9 used; 80 B keeps 16-B alignment)
 
@@ -93,19 +93,15 @@ struct Lvl2View {
     const double *__restrict__ BD;          // [ng * kBlkStride]
     const ChunkDesc *__restrict__ chunks;   // [nchunks], stage after stage -- the table of the pass type (V2_TAB_*)
     const int *__restrict__ stage_chunk;    // [nstages+1]
-    const int *__restrict__ dep_idx;        // dependency lists of the table's chunks (ChunkDesc::dep0/ndep)
-    unsigned *flags;                        // [nchunks] sweep number in which the chunk was last completed
 };
 
 enum { V2_FWD_ZERO = 0, V2_FWD_FULL = 1, V2_BWD = 2, V2_RESID = 3, V2_SPMV = 4 };
-__host__ __device__ constexpr bool v2_staged(int mode) { return mode == V2_FWD_ZERO || mode == V2_FWD_FULL || mode == V2_BWD; }
 // chunk tables of a level: whole rows / lower halves / upper halves
 enum { V2_TAB_FULL = 0, V2_TAB_LO = 1, V2_TAB_UP = 2 };
 __host__ __device__ constexpr int v2_table(int mode) { return (mode == V2_FWD_FULL || mode == V2_SPMV) ? V2_TAB_FULL : (mode == V2_BWD ? V2_TAB_UP : V2_TAB_LO); }
 __host__ __device__ constexpr int v2_groups(int mode) { return v2_table(mode) == V2_TAB_FULL ? kChunkGroups : kHalfGroups; }   // consumer sub-warps per CTA
 __host__ __device__ constexpr int v2_consumers(int mode) { return v2_groups(mode) * GL2; }
-// + one producer warp (one lane issues the bulk copies) + in dataflow sweeps one warp that polls / publishes completion flags
-__host__ __device__ constexpr int v2_threads(int mode, bool dataflow) { return v2_consumers(mode) + 32 + (dataflow ? 32 : 0); }
+__host__ __device__ constexpr int v2_threads(int mode) { return v2_consumers(mode) + 32; }   // + one producer warp (one lane issues the bulk copies)
 
 // fixed offsets inside a shared-memory buffer (G = group capacity of the chunk table)
 constexpr int kOffDesc = 0;                                   // 48 B (+16 pad)
@@ -144,18 +140,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// non-blocking: has the phase with this parity completed?
-__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -187,7 +171,7 @@ __device__ __forceinline__ void consumer_bar_sync()
 #endif
 constexpr int kGbarFan = DDPCA_GBAR_FAN;
 static_assert(kGbarFan >= 1 && kGbarFan <= 32, "one polling lane per counter");
-constexpr int kGbarWords = 32 * (2 + kGbarFan);   // + exit count + number of dataflow sweeps completed on the level
+constexpr int kGbarWords = 32 * (1 + kGbarFan);
 __device__ __forceinline__ unsigned atom_add_acqrel(unsigned *p, unsigned v)
 {
     unsigned old;
@@ -290,11 +274,15 @@ __device__ __forceinline__ void v2_issue_chunk(const Lvl2View &A, int c, const C
 
 // Two-phase evaluation of one half of a row group from shared memory:
 //   phase 1 (v2_gather): every x gather of the half is issued back to back into registers
-//           (kV2Iters steps of 2*GL pattern positions cover 64 entries; hexahedral meshes have
+//           (v2_iters(MODE) steps of 2*GL pattern positions cover 64 or 80 entries; hexahedral meshes have
 //           at most 40 lower / 40 upper couplings per node) -- ONE exposed L2 latency per group;
 //   phase 2 (v2_fma):    values stream from shared memory into the row sums.
 // Longer halves continue in a generic loop (v2_tail).
-constexpr int kV2Iters = 64 / (2 * GL2) < 1 ? 1 : 64 / (2 * GL2);   // unrolled steps cover 64 pattern positions
+// Entries of one half covered by the unrolled steps.  A node of a hexahedral mesh couples to 26 others:
+// at most 78 entries in one half.  The sweeps and the residual cover 80 (measured +2 % on the half
+// passes: no second dependent gather for the colours whose couplings all lie on one side); the plain
+// product keeps 64, where the extra registers cost more than the rare tail (measured 6.0 vs 5.3 TB/s).
+__host__ __device__ constexpr int v2_iters(int mode) { return ((mode == V2_SPMV ? 64 : 80) + 2 * GL2 - 1) / (2 * GL2); }
 
 // x gathers go through L1: neighbouring row groups share most of their columns, and an L1 hit
 // takes the gather off the L2 round trip that bounds these kernels.
@@ -316,11 +304,11 @@ __device__ __forceinline__ double v2_ldx(const double *p)
     if (!RO && DDPCA_V2_GATHER_L1 >= 2) return *p;
     return __ldcg(p);
 }
-template <bool RO>
-__device__ __forceinline__ void v2_gather(const int *__restrict__ pc, int n, const double *x, int sl, double (&xs)[2 * kV2Iters])
+template <bool RO, int ITERS>
+__device__ __forceinline__ void v2_gather(const int *__restrict__ pc, int n, const double *x, int sl, double (&xs)[2 * ITERS])
 {
 #pragma unroll
-    for (int it = 0; it < kV2Iters; it++) {
+    for (int it = 0; it < ITERS; it++) {
         const int k = 2 * sl + it * 2 * GL2;
         xs[2 * it] = 0.0;
         xs[2 * it + 1] = 0.0;
@@ -331,10 +319,11 @@ __device__ __forceinline__ void v2_gather(const int *__restrict__ pc, int n, con
         }
     }
 }
-__device__ __forceinline__ void v2_fma(const double *__restrict__ pv, int n, int gs, int sl, const double (&xs)[2 * kV2Iters], double (&s)[3])
+template <int ITERS>
+__device__ __forceinline__ void v2_fma(const double *__restrict__ pv, int n, int gs, int sl, const double (&xs)[2 * ITERS], double (&s)[3])
 {
 #pragma unroll
-    for (int it = 0; it < kV2Iters; it++) {
+    for (int it = 0; it < ITERS; it++) {
         const int k = 2 * sl + it * 2 * GL2;
         if (k < n) {
 #pragma unroll
@@ -346,11 +335,11 @@ __device__ __forceinline__ void v2_fma(const double *__restrict__ pv, int n, int
         }
     }
 }
-template <bool RO>
+template <bool RO, int ITERS>
 __device__ __forceinline__ void v2_tail(const int *__restrict__ pc, const double *__restrict__ pv, int n, int gs,
                                         const double *x, int sl, double (&s)[3])
 {
-    for (int k = 2 * sl + kV2Iters * 2 * GL2; k < n; k += 2 * GL2) {
+    for (int k = 2 * sl + ITERS * 2 * GL2; k < n; k += 2 * GL2) {
         const int2 c = *reinterpret_cast<const int2 *>(pc + k);
         const double x0 = v2_ldx<RO>(x + c.x), x1 = v2_ldx<RO>(x + c.y);
 #pragma unroll
@@ -369,14 +358,10 @@ __device__ __forceinline__ void v2_tail(const int *__restrict__ pc, const double
 //   SPMV : y = A x ; if w: partial[blockIdx] = sum w_i y_i (MGPIS.h:200-201)
 // Warp-specialised: one producer lane walks the CTA's chunk sequence kV2Bufs chunks ahead of the
 // consumers (full / empty mbarriers per ring slot) and keeps crossing stage boundaries -- operator
-// data does not depend on x.  Ordering between the colours (stages) of a sweep, two variants:
-//   DFLOW = false: a grid barrier of the consumer warps between stages;
-//   DFLOW = true : per-chunk completion flags -- a chunk starts when the chunks holding its coupled
-//                  rows of the earlier colours are done.  CTAs drift apart by up to a colour and the
-//                  operator stream never drains; pays off when a colour is several rounds of chunks.
-// Either way staged modes must be launched cooperatively (co-residency of all CTAs).
-template <int MODE, bool DFLOW>
-__global__ void __launch_bounds__(v2_threads(MODE, DFLOW)) k_level_pass(Lvl2View A, size_t buf_bytes, unsigned *gbar, const double *__restrict__ b,
+// data does not depend on x --, the consumer warps meet the other CTAs at a grid barrier between
+// stages.  Staged modes must be launched cooperatively (co-residency of all CTAs).
+template <int MODE>
+__global__ void __launch_bounds__(v2_threads(MODE)) k_level_pass(Lvl2View A, size_t buf_bytes, unsigned *gbar, const double *__restrict__ b,
                                                             double *x, double *p1, double *y, const double *__restrict__ w,
                                                             double *partial, const int *done)
 {
@@ -386,14 +371,13 @@ __global__ void __launch_bounds__(v2_threads(MODE, DFLOW)) k_level_pass(Lvl2View
     __shared__ int s_stage_chunk[kV2StagesSmem + 1];
     constexpr bool LO = (MODE != V2_BWD);
     constexpr bool UP = (MODE == V2_FWD_FULL || MODE == V2_BWD || MODE == V2_SPMV);
-    constexpr bool STAGED = v2_staged(MODE);
-    constexpr bool DF = DFLOW && STAGED;
+    constexpr bool STAGED = (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD);
     constexpr int kV2Consumers = v2_consumers(MODE);
     constexpr int kOffBlk = v2_off_blk(v2_groups(MODE)), kOffData = v2_off_data(v2_groups(MODE));
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < kV2Bufs; i++) {
-            mbar_init(&full[i], DF ? 2 : 1);   // dataflow: + the arrival of the dependency warp
+            mbar_init(&full[i], 1);
             mbar_init(&empty[i], kV2Consumers / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -421,84 +405,7 @@ __global__ void __launch_bounds__(v2_threads(MODE, DFLOW)) k_level_pass(Lvl2View
     int si = 0, c = c_begin(0) + (int)blockIdx.x;
     double acc = 0.0;
 
-    if (tid >= kV2Consumers + 32) {
-        // ------------------ dependency / completion warp (dataflow sweeps only) ---------------
-        // Walks the CTA's chunk sequence.  For chunk j it (1) polls the flags of the chunks j depends on
-        // (acquire loads: they order the consumers' x gathers, which wait behind the slot's `full`
-        // mbarrier, after the other CTAs' stores, and drop the SM's L1 lines that may predate them),
-        // (2) makes sure chunk j - kV2Bufs has been PUBLISHED, (3) arrives on full[slot].  Publishing a
-        // chunk = its `empty` phase is complete (every consumer warp arrived after its x stores) ->
-        // fence -> store the sweep number into the chunk's flag.  Consumed chunks are published from
-        // inside the polling loop (non-blocking test of `empty`), never behind a wait for somebody
-        // else's flag: a chain  my chunk -> their chunk -> my next chunk  cannot lock up.  Step (2)
-        // also keeps `empty` at most one phase ahead of the parity tested here.
-        if (DF) {
-            const int lane = tid & 31;
-            const unsigned ep = ld_relaxed(gbar + 32 * (kGbarFan + 1)) + 1u;
-            int c_hist[kV2Bufs];
-#pragma unroll
-            for (int i = 0; i < kV2Bufs; i++) c_hist[i] = -1;
-            int npub = 0;   // chunks published so far (in sequence order)
-            auto publish = [&](int slot) {   // warp-uniform
-                if (lane == 0) {
-                    int cp = -1;
-#pragma unroll
-                    for (int i = 0; i < kV2Bufs; i++)
-                        if (i == slot) cp = c_hist[i];
-                    asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                    st_relaxed(A.flags + cp, ep);
-                }
-                __syncwarp();
-            };
-            bool have = settle(si, c);
-            int dep0 = 0, ndep = 0;
-            if (have) { dep0 = A.chunks[c].dep0; ndep = A.chunks[c].ndep; }
-            int j = 0;
-            for (; have; j++) {
-                const int d0 = dep0, nd = ndep, c_this = c;
-                c += (int)gridDim.x;
-                have = settle(si, c);
-                if (have) { dep0 = A.chunks[c].dep0; ndep = A.chunks[c].ndep; }
-                // (1) dependencies of chunk j, publishing whatever got consumed meanwhile
-                for (int k0 = 0; k0 < nd; k0 += 32) {
-                    const unsigned *f = (k0 + lane < nd) ? A.flags + A.dep_idx[d0 + k0 + lane] : nullptr;
-                    for (;;) {
-                        // (lane 0's test result for the whole warp: npub must stay uniform)
-                        while (npub < j && __shfl_sync(0xffffffffu, (int)mbar_test(&empty[npub % kV2Bufs], (uint32_t)((npub / kV2Bufs) & 1)), 0)) {
-                            publish(npub % kV2Bufs);
-                            npub++;
-                        }
-                        const bool ok = (f == nullptr) || (ld_acquire(f) == ep);
-                        if (__all_sync(0xffffffffu, ok)) break;
-                    }
-                }
-                // (2) chunk j - kV2Bufs published (hence its slot is free)
-                while (npub < j - kV2Bufs + 1) {
-                    mbar_wait(&empty[npub % kV2Bufs], (uint32_t)((npub / kV2Bufs) & 1));
-                    publish(npub % kV2Bufs);
-                    npub++;
-                }
-                // (3) release chunk j to the consumers
-                const int slot = j % kV2Bufs;
-#pragma unroll
-                for (int i = 0; i < kV2Bufs; i++)
-                    if (i == slot) c_hist[i] = c_this;
-                if (lane == 0) mbar_arrive(&full[slot]);
-            }
-            for (; npub < j; npub++) {   // drain
-                mbar_wait(&empty[npub % kV2Bufs], (uint32_t)((npub / kV2Bufs) & 1));
-                publish(npub % kV2Bufs);
-            }
-            // the last CTA out closes the sweep: its number becomes the level's count
-            if (lane == 0) {
-                unsigned *ex = gbar + 32 * kGbarFan;
-                if (atom_add_acqrel(ex, 1u) == gridDim.x - 1) {
-                    st_relaxed(gbar + 32 * (kGbarFan + 1), ep);
-                    st_relaxed(ex, 0u);
-                }
-            }
-        }
-    } else if (tid >= kV2Consumers) {
+    if (tid >= kV2Consumers) {
         // ------------------------------- producer warp ---------------------------------------
         if (tid == kV2Consumers) {
             // the descriptor of chunk j+1 is fetched before the wait for chunk j's ring slot, so
@@ -525,7 +432,7 @@ __global__ void __launch_bounds__(v2_threads(MODE, DFLOW)) k_level_pass(Lvl2View
         int si_done = 0;   // stage boundaries passed so far
         for (int j = 0;; j++, c += (int)gridDim.x) {
             const bool have = settle(si, c);
-            if (STAGED && !DF) {
+            if (STAGED) {
                 const int target = have ? si : nst - 1;
                 while (si_done < target) { si_done++; consumer_grid_barrier<kV2Consumers>(gbar, (unsigned)si_done); }
             }
@@ -560,15 +467,25 @@ __global__ void __launch_bounds__(v2_threads(MODE, DFLOW)) k_level_pass(Lvl2View
                             rhs[r] = (MODE == V2_BWD) ? p1[r0 + r] : b[r0 + r];
                             if (MODE == V2_FWD_FULL) xo[r] = __ldcg(x + r0 + r);
                         }
+                } else {
+                    // RESID / SPMV: the operands of the finishing lanes, too
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+                        if (r < gs) xo[r] = v2_ldx<true>(x + r0 + r);
+                    if (sl < gs) {
+                        if (MODE == V2_RESID) { rhs[0] = b[r0 + sl]; rhs[1] = p1[r0 + sl]; }
+                        else if (w) rhs[0] = w[r0 + sl];
+                    }
                 }
                 {
-                    double xl[2 * kV2Iters], xu[2 * kV2Iters];
-                    if (LO) v2_gather<!STAGED>(cL, m.nl, x, sl, xl);
-                    if (UP) v2_gather<!STAGED>(cU, m.nu, x, sl, xu);
-                    if (LO) v2_fma(vL, m.nl, gs, sl, xl, sL);
-                    if (UP) v2_fma(vU, m.nu, gs, sl, xu, sU);
-                    if (LO && m.nl > kV2Iters * 2 * GL2) v2_tail<!STAGED>(cL, vL, m.nl, gs, x, sl, sL);
-                    if (UP && m.nu > kV2Iters * 2 * GL2) v2_tail<!STAGED>(cU, vU, m.nu, gs, x, sl, sU);
+                    constexpr int IT = v2_iters(MODE);
+                    double xl[2 * IT], xu[2 * IT];
+                    if (LO) v2_gather<!STAGED, IT>(cL, m.nl, x, sl, xl);
+                    if (UP) v2_gather<!STAGED, IT>(cU, m.nu, x, sl, xu);
+                    if (LO) v2_fma<IT>(vL, m.nl, gs, sl, xl, sL);
+                    if (UP) v2_fma<IT>(vU, m.nu, gs, sl, xu, sU);
+                    if (LO && m.nl > IT * 2 * GL2) v2_tail<!STAGED, IT>(cL, vL, m.nl, gs, x, sl, sL);
+                    if (UP && m.nu > IT * 2 * GL2) v2_tail<!STAGED, IT>(cU, vU, m.nu, gs, x, sl, sU);
                 }
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
@@ -633,13 +550,17 @@ __global__ void __launch_bounds__(v2_threads(MODE, DFLOW)) k_level_pass(Lvl2View
                         const int i = r0 + sl;
                         double sacc = sl == 0 ? sL[0] : (sl == 1 ? sL[1] : sL[2]);
                         if (MODE == V2_RESID) {
-                            for (int cc = 0; cc < sl; cc++) sacc += blk[sl * 3 + cc] * __ldcg(x + r0 + cc);
-                            y[i] = b[i] - (p1[i] + sacc);
+#pragma unroll
+                            for (int cc = 0; cc < 3; cc++)
+                                if (cc < sl) sacc += blk[sl * 3 + cc] * xo[cc];
+                            y[i] = rhs[0] - (rhs[1] + sacc);
                         } else {
                             sacc += sl == 0 ? sU[0] : (sl == 1 ? sU[1] : sU[2]);
-                            for (int cc = 0; cc < gs; cc++) sacc += blk[sl * 3 + cc] * __ldcg(x + r0 + cc);
+#pragma unroll
+                            for (int cc = 0; cc < 3; cc++)
+                                if (cc < gs) sacc += blk[sl * 3 + cc] * xo[cc];
                             y[i] = sacc;
-                            if (w) acc += w[i] * sacc;
+                            if (w) acc += rhs[0] * sacc;
                         }
                     }
                 }
@@ -647,9 +568,8 @@ __global__ void __launch_bounds__(v2_threads(MODE, DFLOW)) k_level_pass(Lvl2View
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty[slot]);   // this warp is done reading the slot
         }
-        if (STAGED && !DF && nst > 1) consumer_grid_barrier_exit(gbar);
+        if (STAGED && nst > 1) consumer_grid_barrier_exit(gbar);
     }
-    static_assert(!DFLOW || v2_staged(MODE), "dataflow ordering only exists for the staged sweeps");
     if (MODE == V2_SPMV && partial) block_sum_to_partial(acc, partial);   // all warps, producer included
 }
 

@@ -86,15 +86,12 @@ struct Level {
     // one chunk table per pass type (V2_TAB_FULL / _LO / _UP): the half passes cut their chunks by bytes
     ChunkDesc *chunks[3] = {nullptr, nullptr, nullptr};
     int *stage_chunk[3] = {nullptr, nullptr, nullptr};
-    int *dep_idx[3] = {nullptr, nullptr, nullptr};        // dataflow sweeps: dependency lists of the chunks
-    unsigned *flags[3] = {nullptr, nullptr, nullptr};     // ... and their completion flags
     int nchunks[3] = {0, 0, 0}, max_stage_chunks[3] = {0, 0, 0};
     size_t buf[3] = {0, 0, 0};   // shared-memory bytes of one chunk buffer
     unsigned *gbar = nullptr;   // counters of the consumer grid barrier
-    bool dataflow = false;       // sweeps ordered by chunk completion flags instead of a grid barrier per colour (kernels2.cuh)
     int fuse_bwd_last = 0;       // the forward sweeps also do the backward step of the last colour (see Lvl2View)
     double bytes_bwd_skip = 0;   // algorithmic bytes the backward sweep no longer touches then
-    Lvl2View view2(int tab = V2_TAB_FULL) const { return Lvl2View{n, ng, nchunks[tab], plan.nstages(), fuse_bwd_last, meta2, CL, VL, CU, VU, BD, chunks[tab], stage_chunk[tab], dep_idx[tab], flags[tab]}; }
+    Lvl2View view2(int tab = V2_TAB_FULL) const { return Lvl2View{n, ng, nchunks[tab], plan.nstages(), fuse_bwd_last, meta2, CL, VL, CU, VU, BD, chunks[tab], stage_chunk[tab]}; }
 };
 
 struct ProfRec {
@@ -253,61 +250,52 @@ static void launch_spmv(Engine *h, int kclass, int lvl, const DevCsr &A, const d
 #undef SPMV_CASE
 }
 // ---- v2 launches (kernels2.cuh) ------------------------------------------------------------------
-template <int MODE, bool DF>
+template <int MODE>
 static int v2_blocks_per_sm(size_t dyn)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_level_pass<MODE, DF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_level_pass<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         // the chunk rings are the only consumers of the unified L1/shared array: take all of it,
         // otherwise the driver sizes the carve-out for ~5 CTAs and the half passes lose occupancy
-        cudaFuncSetAttribute(k_level_pass<MODE, DF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_level_pass<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_level_pass<MODE, DF>, v2_threads(MODE, DF), dyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_level_pass<MODE>, v2_threads(MODE), dyn);
     return std::max(nb, 1);
 }
 // returns the grid used (number of partial sums for SPMV with a dot)
-template <int MODE, bool DF>
-static int launch_v2_impl(Engine *h, Level &L, int kclass, int l, double bytes, const double *b, double *x, double *p1, double *y,
-                          const double *w, double *partial, const int *done)
+template <int MODE>
+static int launch_v2(Engine *h, Level &L, int kclass, int l, double bytes, const double *b, double *x, double *p1, double *y,
+                     const double *w, double *partial, const int *done)
 {
-    const bool staged = v2_staged(MODE);
+    const bool staged = (MODE == V2_FWD_ZERO || MODE == V2_FWD_FULL || MODE == V2_BWD);
     const int nst = L.plan.nstages() - (MODE == V2_BWD ? L.fuse_bwd_last : 0);   // stages this launch walks
     if (nst <= 0) return 0;
     constexpr int tab = v2_table(MODE);
     size_t buf = L.buf[tab];
     size_t dyn = (size_t)kV2Bufs * buf;
-    int per_sm = v2_blocks_per_sm<MODE, DF>(dyn);
+    int per_sm = v2_blocks_per_sm<MODE>(dyn);
     int cap = per_sm * h->sms;
     int grid = std::min(staged ? L.max_stage_chunks[tab] : L.nchunks[tab], cap);
     if (MODE == V2_SPMV && w) grid = std::min(grid, kNumPart);
     grid = std::max(grid, 1);
     if (std::getenv("DDPCA_VERBOSE")) {
         static int shown = 0;
-        if (shown++ < 40) std::fprintf(stderr, "ddpca v2: level n=%d mode=%d%s buf=%zu B x%d, %d CTA/SM, grid=%d, chunks=%d (max/stage %d)\n", L.n, MODE, DF ? " dataflow" : "", buf, kV2Bufs, per_sm, grid, L.nchunks[tab], L.max_stage_chunks[tab]);
+        if (shown++ < 40) std::fprintf(stderr, "ddpca v2: level n=%d mode=%d buf=%zu B x%d, %d CTA/SM, grid=%d, chunks=%d (max/stage %d)\n", L.n, MODE, buf, kV2Bufs, per_sm, grid, L.nchunks[tab], L.max_stage_chunks[tab]);
     }
     Lvl2View A = L.view2(tab);
     unsigned *gbar = L.gbar;
     h->pre(kclass, l, bytes);
     if (staged && nst > 1) {
         void *args[] = {(void *)&A, (void *)&buf, (void *)&gbar, (void *)&b, (void *)&x, (void *)&p1, (void *)&y, (void *)&w, (void *)&partial, (void *)&done};
-        cudaLaunchCooperativeKernel((const void *)k_level_pass<MODE, DF>, dim3(grid), dim3(v2_threads(MODE, DF)), args, dyn, h->stream);
+        cudaLaunchCooperativeKernel((const void *)k_level_pass<MODE>, dim3(grid), dim3(v2_threads(MODE)), args, dyn, h->stream);
     } else {
-        k_level_pass<MODE, DF><<<grid, v2_threads(MODE, DF), dyn, h->stream>>>(A, buf, gbar, b, x, p1, y, w, partial, done);
+        k_level_pass<MODE><<<grid, v2_threads(MODE), dyn, h->stream>>>(A, buf, gbar, b, x, p1, y, w, partial, done);
     }
     h->post();
     return grid;
-}
-template <int MODE>
-static int launch_v2(Engine *h, Level &L, int kclass, int l, double bytes, const double *b, double *x, double *p1, double *y,
-                     const double *w, double *partial, const int *done)
-{
-    if constexpr (v2_staged(MODE)) {
-        if (L.dataflow) return launch_v2_impl<MODE, true>(h, L, kclass, l, bytes, b, x, p1, y, w, partial, done);
-    }
-    return launch_v2_impl<MODE, false>(h, L, kclass, l, bytes, b, x, p1, y, w, partial, done);
 }
 
 // y = consStif[l] x on the group layout; returns the grid (= number of partial sums when dotw)
@@ -645,7 +633,6 @@ struct Layout2Host {
     // per chunk table (V2_TAB_*)
     std::vector<ChunkDesc> chunks[3];
     std::vector<int> stage_chunk[3];
-    std::vector<int> dep_idx[3];
     size_t buf[3] = {0, 0, 0};
     int max_stage_chunks[3] = {0, 0, 0};
 };
@@ -703,69 +690,6 @@ static void build_chunks2(const LevelPlan &pl, Layout2Host &out)
         sc[ns] = (int)ch.size();
         out.buf[tab] = (out.buf[tab] + 127) & ~(size_t)127;
     }
-}
-
-// Dependency lists for the dataflow sweeps (kernels2.cuh).  A chunk of the forward tables waits for
-// the chunks that hold the row groups its rows couple to BELOW them (earlier colours), a chunk of the
-// backward table for those ABOVE (later colours; not the last colour when the forward sweeps already
-// finish it).  The forward sweep over whole rows also reads the OLD iterate of the rows above: those
-// must not be overwritten before -- guaranteed by the same lists when the group graph is symmetric
-// (g above h  <=>  h below g), which is verified here; returns false otherwise (the level then keeps
-// the barrier-free single-stage launches or falls back to the v1 kernels).
-static bool build_deps2(const LevelPlan &pl, Layout2Host &out, bool fuse_bwd_last)
-{
-    const int ng = pl.ngroups(), ns = pl.nstages();
-    const int n = pl.n;
-    std::vector<int> grp_of_row(n);
-    for (int g = 0; g < ng; g++)
-        for (int r = pl.group_start[g]; r < pl.group_start[g + 1]; r++) grp_of_row[r] = g;
-    // sorted unique neighbour groups below / above every group
-    std::vector<std::vector<int>> lowN(ng), upN(ng);
-#pragma omp parallel for schedule(dynamic, 256)
-    for (int g = 0; g < ng; g++) {
-        const GroupMeta2 &m = out.meta[g];
-        std::vector<int> &lo = lowN[g], &up = upN[g];
-        for (int k = 0; k < m.nl; k++) { int h = grp_of_row[out.CL[m.cl + k]]; if (h != g) lo.push_back(h); }
-        for (int k = 0; k < m.nu; k++) { int h = grp_of_row[out.CU[m.cu + k]]; if (h != g) up.push_back(h); }
-        std::sort(lo.begin(), lo.end()); lo.erase(std::unique(lo.begin(), lo.end()), lo.end());
-        std::sort(up.begin(), up.end()); up.erase(std::unique(up.begin(), up.end()), up.end());
-    }
-    int asym = 0;
-#pragma omp parallel for schedule(dynamic, 256) reduction(+ : asym)
-    for (int g = 0; g < ng; g++) {
-        for (int h : lowN[g]) if (!std::binary_search(upN[h].begin(), upN[h].end(), g)) asym++;
-        for (int h : upN[g]) if (!std::binary_search(lowN[h].begin(), lowN[h].end(), g)) asym++;
-    }
-    if (asym) return false;
-    const int last_stage_g0 = pl.stage_group[ns - 1];
-    for (int tab = 0; tab < 3; tab++) {
-        std::vector<ChunkDesc> &ch = out.chunks[tab];
-        const int nc = (int)ch.size();
-        std::vector<int> chunk_of_group(ng, -1);
-        for (int c = 0; c < nc; c++)
-            for (int g = ch[c].g0; g < ch[c].g0 + ch[c].ng; g++) chunk_of_group[g] = c;
-        std::vector<std::vector<int>> deps(nc);
-#pragma omp parallel for schedule(dynamic, 64)
-        for (int c = 0; c < nc; c++) {
-            std::vector<int> &d = deps[c];
-            for (int g = ch[c].g0; g < ch[c].g0 + ch[c].ng; g++) {
-                const std::vector<int> &nb = (tab == V2_TAB_UP) ? upN[g] : lowN[g];
-                for (int h : nb) {
-                    if (tab == V2_TAB_UP && fuse_bwd_last && h >= last_stage_g0) continue;   // finished by the forward sweep
-                    d.push_back(chunk_of_group[h]);
-                }
-            }
-            std::sort(d.begin(), d.end()); d.erase(std::unique(d.begin(), d.end()), d.end());
-        }
-        out.dep_idx[tab].clear();
-        for (int c = 0; c < nc; c++) {
-            ch[c].dep0 = (int)out.dep_idx[tab].size();
-            ch[c].ndep = (int)deps[c].size();
-            out.dep_idx[tab].insert(out.dep_idx[tab].end(), deps[c].begin(), deps[c].end());
-        }
-        if (out.dep_idx[tab].empty()) out.dep_idx[tab].push_back(0);   // never an empty upload
-    }
-    return true;
 }
 
 static bool build_layout2(const CsrHost &Ap, const LevelPlan &pl, Layout2Host &out, std::string &err)
@@ -874,28 +798,6 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
             for (int tab = 0; tab < 3; tab++)
                 if ((size_t)kV2Bufs * H2.buf[tab] > 200 * 1024) want_v2 = false;   // the chunk ring must fit in shared memory
         }
-        if (want_v2) {
-            // fwd -> bwd junction: the last colour has nothing above its groups (it is ordered last)
-            const int ns = L.plan.nstages();
-            bool none_above = ns >= 1 && !std::getenv("DDPCA_NO_FUSE_BWD");
-            for (int g = L.plan.stage_group[ns - 1]; none_above && g < L.plan.stage_group[ns]; g++) none_above = (H2.meta[g].nu == 0);
-            L.fuse_bwd_last = none_above ? 1 : 0;
-            if (none_above)
-                for (int g = L.plan.stage_group[ns - 1]; g < L.plan.stage_group[ns]; g++) {
-                    const int gs = H2.meta[g].gs;
-                    L.bytes_bwd_skip += 32.0 + 8.0 * gs * gs + 32.0 * gs;
-                }
-            // Dataflow sweeps where a colour is several rounds of chunks for the whole GPU (the finest levels):
-            // they need the chunk dependency lists and a symmetric coupling graph.  Smaller levels keep the
-            // grid barrier per colour: every CTA has one chunk per colour there and nothing to pipeline.
-            int dev = 0, sms = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            const char *env_df = std::getenv("DDPCA_DATAFLOW_ROUNDS");   // 0 = never
-            const double min_rounds = env_df ? std::atof(env_df) : 2.0;
-            const int resident = sms * v2_blocks_per_sm<V2_FWD_FULL, false>((size_t)kV2Bufs * H2.buf[V2_TAB_FULL]);
-            L.dataflow = min_rounds > 0 && H2.max_stage_chunks[V2_TAB_FULL] >= min_rounds * resident && build_deps2(L.plan, H2, none_above);
-        }
         L.v2 = want_v2;
         L.ng = (int)G.meta.size();
         L.pat_entries = (long)G.ci.size();
@@ -907,16 +809,23 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
             L.bytes_full += (8.0 * m.gs + 4.0) * m.pad + 32.0 + 16.0 * m.gs;   // + x once, y once
         }
         if (L.v2) {
+            // fwd -> bwd junction: the last colour has nothing above its groups (it is ordered last)
+            {
+                const int ns = L.plan.nstages();
+                bool none_above = ns >= 1 && !std::getenv("DDPCA_NO_FUSE_BWD");
+                for (int g = L.plan.stage_group[ns - 1]; none_above && g < L.plan.stage_group[ns]; g++) none_above = (H2.meta[g].nu == 0);
+                L.fuse_bwd_last = none_above ? 1 : 0;
+                if (none_above)
+                    for (int g = L.plan.stage_group[ns - 1]; g < L.plan.stage_group[ns]; g++) {
+                        const int gs = H2.meta[g].gs;
+                        L.bytes_bwd_skip += 32.0 + 8.0 * gs * gs + 32.0 * gs;
+                    }
+            }
             for (int tab = 0; tab < 3; tab++) {
                 L.nchunks[tab] = (int)H2.chunks[tab].size();
                 L.max_stage_chunks[tab] = H2.max_stage_chunks[tab];
                 L.buf[tab] = H2.buf[tab];
                 if (upload_vec(H2.chunks[tab], &L.chunks[tab]) || upload_vec(H2.stage_chunk[tab], &L.stage_chunk[tab])) return 1;
-                if (L.dataflow) {
-                    if (upload_vec(H2.dep_idx[tab], &L.dep_idx[tab])) return 1;
-                    CU(cudaMalloc(&L.flags[tab], sizeof(unsigned) * std::max(1, L.nchunks[tab])));
-                    CU(cudaMemset(L.flags[tab], 0, sizeof(unsigned) * std::max(1, L.nchunks[tab])));
-                }
             }
             CU(cudaMalloc(&L.gbar, kGbarWords * sizeof(unsigned)));
             CU(cudaMemset(L.gbar, 0, kGbarWords * sizeof(unsigned)));
@@ -939,10 +848,7 @@ static void free_level(Level &L)
     cudaFree(L.meta); cudaFree(L.gci); cudaFree(L.gv); cudaFree(L.stage_group); cudaFree(L.perm);
     cudaFree(L.x); cudaFree(L.b); cudaFree(L.p1); cudaFree(L.r); cudaFree(L.dinv);
     cudaFree(L.meta2); cudaFree(L.CL); cudaFree(L.CU); cudaFree(L.VL); cudaFree(L.VU); cudaFree(L.BD); cudaFree(L.gbar); L.gbar = nullptr;
-    for (int tab = 0; tab < 3; tab++) {
-        cudaFree(L.chunks[tab]); cudaFree(L.stage_chunk[tab]); cudaFree(L.dep_idx[tab]); cudaFree(L.flags[tab]);
-        L.chunks[tab] = nullptr; L.stage_chunk[tab] = nullptr; L.dep_idx[tab] = nullptr; L.flags[tab] = nullptr;
-    }
+    for (int tab = 0; tab < 3; tab++) { cudaFree(L.chunks[tab]); cudaFree(L.stage_chunk[tab]); L.chunks[tab] = nullptr; L.stage_chunk[tab] = nullptr; }
     L.meta2 = nullptr; L.CL = L.CU = nullptr; L.VL = L.VU = L.BD = nullptr;
     L.meta = nullptr; L.gci = nullptr; L.gv = nullptr; L.stage_group = nullptr; L.perm = nullptr;
     L.x = L.b = L.p1 = L.r = L.dinv = nullptr;

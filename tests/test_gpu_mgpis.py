@@ -241,27 +241,6 @@ def test_v1_v2_kernels_and_loop_drivers_agree(monkeypatch):
             assert rel(x, d["cg_mg_x"]) < 1e-8
 
 
-def test_dataflow_and_barrier_sweeps_are_bit_identical(monkeypatch):
-    """The coloured sweeps order their colours either by a grid barrier or by per-chunk completion flags
-    (kernels2.cuh, DFLOW); the arithmetic per row is the same, so V-cycle and CG results must be
-    bit-identical.  DDPCA_DATAFLOW_ROUNDS forces one or the other on every level of the fixtures."""
-    cases = [load_golden("beam_3lev")]
-    if have_ref_binary():
-        cases.append(run_ref_beam(2))
-    for d, meta, A, P in cases:
-        out = []
-        for rounds in ("0", "0.0001"):
-            monkeypatch.setenv("DDPCA_DATAFLOW_ROUNDS", rounds)
-            mg = dd.MGPIS.from_hierarchy(A, P, smoother=dd.SMOOTH_MC)
-            z = mg.MULT_VCYC(len(A) - 1, d["consForc"])
-            x = mg.CG_SOLV(1, d["consForc"])
-            out.append((z, x, mg.last_iterNumb))
-            mg.close()
-        assert np.array_equal(out[0][0], out[1][0])
-        assert out[0][2] == out[1][2] and np.array_equal(out[0][1], out[1][1])
-        assert rel(out[1][1], d["cg_mg_x"]) < 1e-8
-
-
 def test_gmres_matches_oracle(solvers):
     """MGPIS::GMRES_SOLV (MGPIS.h:227-348), restarted GMRES(10) with the V-cycle preconditioner."""
     mg, d, meta, A, P = solvers("beam_2lev", dd.SMOOTH_LEX)

@@ -28,10 +28,9 @@ cap() {  # name, kernel regex, skip, count
   if [ "$sz" -gt 9000000 ]; then rm -f gpurun_out/${tag}_$1.ncu-rep; fi
 }
 # v2 kernels: one k_level_pass<MODE> launch per sweep / residual / product
-# (the finest level runs the dataflow variant <MODE, true> of the sweeps; first instance = finest level)
-cap spmv      'k_level_pass<\(int\)4'  1  1
-cap fwd_zero  'k_level_pass<\(int\)0, \(bool\)1'  0  1
-cap fwd_full  'k_level_pass<\(int\)1, \(bool\)1'  0  1
-cap bwd       'k_level_pass<\(int\)2, \(bool\)1'  0  1
-cap resid     'k_level_pass<\(int\)3'  0  1
+cap spmv      'k_level_pass<\(int\)4>'  1  1
+cap fwd_zero  'k_level_pass<\(int\)0>'  0  1
+cap fwd_full  'k_level_pass<\(int\)1>'  2  1
+cap bwd       'k_level_pass<\(int\)2>'  0  1
+cap resid     'k_level_pass<\(int\)3>'  0  1
 du -sh gpurun_out; ls gpurun_out/ | head -50
