@@ -79,7 +79,14 @@ struct __align__(16) ChunkDesc {
     int vu0, nvu;
     int pad0, pad1;
 };
-constexpr int kBlkStride = 10;     // doubles per in-group block record (9 used; 80 B keeps 16-B alignment)
+constexpr int kBlkStride = 12;     // doubles per in-group block record: the gs x gs block row-major (9) + 1/diagonal (3)
+// The v2 sweeps multiply by the stored reciprocal of the diagonal instead of dividing (three dependent
+// FP64 divisions per row group sit on the critical path of every chunk otherwise) and take
+// p1 = b - L x_new directly instead of D x_new + U x_old (equal in exact arithmetic, MGPIS.h:70-72).
+// Results move by <= 1 ulp per operation; DDPCA_V2_RECIP_DIAG=0 restores the divisions.
+#ifndef DDPCA_V2_RECIP_DIAG
+#define DDPCA_V2_RECIP_DIAG 1
+#endif
 
 struct Lvl2View {
     int n, ng, nchunks, nstages;
@@ -106,7 +113,7 @@ __host__ __device__ constexpr int v2_threads(int mode) { return v2_consumers(mod
 // fixed offsets inside a shared-memory buffer (G = group capacity of the chunk table)
 constexpr int kOffDesc = 0;                                   // 48 B (+16 pad)
 constexpr int kOffMeta = 64;                                  // G * 32 B
-__host__ __device__ constexpr int v2_off_blk(int G) { return kOffMeta + G * 32; }              // G * 80 B
+__host__ __device__ constexpr int v2_off_blk(int G) { return kOffMeta + G * 32; }              // G * kBlkStride * 8 B
 __host__ __device__ constexpr int v2_off_data(int G) { return v2_off_blk(G) + G * kBlkStride * 8; }
 
 __host__ __device__ inline size_t v2_chunk_bytes(int mode, int ncl, int nvl, int ncu, int nvu)
@@ -503,9 +510,16 @@ __global__ void __launch_bounds__(v2_threads(MODE)) k_level_pass(Lvl2View A, siz
                                 if (cc < r) inL += blk[r * 3 + cc] * xn[cc];
                                 if (cc > r) inU += blk[r * 3 + cc] * xo[cc];
                             }
-                            const double up = sU[r] + inU, dg = blk[r * 3 + r];
+                            const double up = sU[r] + inU;
+#if DDPCA_V2_RECIP_DIAG
+                            const double t = rhs[r] - sL[r] - inL;
+                            xn[r] = (t - up) * blk[9 + r];
+                            rhs[r] = t;                 // p1 (MGPIS.h:72)
+#else
+                            const double dg = blk[r * 3 + r];
                             xn[r] = (rhs[r] - sL[r] - inL - up) / dg;
-                            rhs[r] = dg * xn[r] + up;   // p1 (MGPIS.h:71)
+                            rhs[r] = dg * xn[r] + up;   // p1 (MGPIS.h:72)
+#endif
                             if (sl == 0) p1[r0 + r] = rhs[r];
                         }
                     }
@@ -520,7 +534,11 @@ __global__ void __launch_bounds__(v2_threads(MODE)) k_level_pass(Lvl2View A, siz
 #pragma unroll
                                 for (int cc = 0; cc < 3; cc++)
                                     if (cc > r) inU += blk[r * 3 + cc] * xb[cc];
+#if DDPCA_V2_RECIP_DIAG
+                                xb[r] = (rhs[r] - sU[r] - inU) * blk[9 + r];
+#else
                                 xb[r] = (rhs[r] - sU[r] - inU) / blk[r * 3 + r];
+#endif
                             }
                         }
 #pragma unroll
@@ -540,7 +558,11 @@ __global__ void __launch_bounds__(v2_threads(MODE)) k_level_pass(Lvl2View A, siz
 #pragma unroll
                             for (int cc = 0; cc < 3; cc++)
                                 if (cc > r) inU += blk[r * 3 + cc] * xn[cc];
+#if DDPCA_V2_RECIP_DIAG
+                            xn[r] = (rhs[r] - sU[r] - inU) * blk[9 + r];
+#else
                             xn[r] = (rhs[r] - sU[r] - inU) / blk[r * 3 + r];
+#endif
                             if (sl == 0) x[r0 + r] = xn[r];
                         }
                     }

@@ -732,6 +732,7 @@ static bool build_layout2(const CsrHost &Ap, const LevelPlan &pl, Layout2Host &o
             for (int k = 0; k < nlr; k++) dl[k] = vr[k];
             for (int k = 0; k < nur; k++) du[k] = vr[kd + gs + k];
             for (int c = 0; c < gs; c++) out.BD[(size_t)g * kBlkStride + r * 3 + c] = vr[kd + c];
+            out.BD[(size_t)g * kBlkStride + 9 + r] = 1.0 / vr[kd + r];
         }
     }
     build_chunks2(pl, out);
