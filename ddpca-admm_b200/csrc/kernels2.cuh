@@ -6,12 +6,14 @@
 // 64-byte DRAM granularity over-fetch when only half of each row is needed.  Here
 //   * the strictly-lower and strictly-upper couplings of a level live in two separate arrays
 //     in stage order, so a half sweep streams ONE contiguous region;
-//   * a CTA processes CHUNKS of 16 row groups (up to 32 where a pass reads only one half): descriptor, group metadata, diagonal blocks,
-//     patterns and values of a chunk arrive in shared memory by a handful of bulk copies
+//   * a CTA processes CHUNKS of up to 16 row groups (passes over one half cut theirs by bytes):
+//     descriptor, group metadata, diagonal blocks, patterns and values of a chunk arrive in shared
+//     memory by a handful of bulk copies
 //     (UBLKCP), double-buffered, so the only latency left on the critical path is the x gather,
 //     and all gathers of a group are issued back to back from a pattern that is already on chip;
-//   * the stages (colours) of one sweep run inside one cooperative kernel with grid.sync()
-//     between them; the next stage's first chunk is already in flight during the barrier.
+//   * the stages (colours) of one sweep run inside one cooperative kernel with a grid barrier of the
+//     consumer warps between them; the next stage's first chunks are already in flight during the
+//     barrier.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>

@@ -420,7 +420,7 @@ static void enqueue_setup(ddpca_mg *h, int prec, cudaGraphConditionalHandle cond
 }
 
 // One graph per solve: [set-up] -> WHILE(cond){ CG iteration }.  The loop condition of MGPIS.h:198
-// is evaluated on the device (k_s_delta0 / k_s_next call cudaGraphSetConditional): no host
+// is evaluated on the device (k_s_delta0 / k_s_beta_next call cudaGraphSetConditional): no host
 // polling, no iterations issued past convergence.  Returns 0 and sets while_state[prec] = -1 when
 // the driver refuses (then the host-polled per-iteration graph is used).
 static int build_solve_graph(ddpca_mg *h, int prec)
