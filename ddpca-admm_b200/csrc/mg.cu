@@ -1037,11 +1037,20 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
     }
     if (upload_vec(m_in, &s->m_in) || upload_vec(m_mid, &s->m_mid) || upload_vec(m_out, &s->m_out) || upload_vec(dinv, &s->dinv_lo)) { ldlt_free(s); return 1; }
     if (s->single_rows && s->lo.plan.perm == s->up.plan.perm && !std::getenv("DDPCA_NO_DENSE_TAIL")) {
-        // trailing run of one-row wavefronts
+        // Trailing run of narrow wavefronts (the separators eliminated last: a nearly sequential chain of
+        // thousands of stages of a few rows).  BLOCK's macroscopic factor (27 802 rows, 6 198 wavefronts):
+        // the last 8 901 rows sit in 5 929 of them; as one dense block they cost one 0.63 GB GEMV per solve
+        // (~0.1 ms) instead of 2 x 5 929 dependent steps, and 269 wide wavefronts remain.  The bounds keep
+        // the set-up (an unblocked Gauss-Jordan inversion of the block, ~T^3 * 16 bytes of traffic) at seconds.
         const LevelPlan &pl = s->lo.plan;
-        int ns = pl.nstages(), st = ns;
-        while (st > 0 && pl.stage_group[st] - pl.stage_group[st - 1] == 1 && ns - (st - 1) <= 8192) st--;
-        int T = ns - st;
+        const int kTailWidth = 16, kTailMaxRows = 9216;
+        int ns = pl.nstages(), st = ns, T = 0;
+        while (st > 0) {
+            const int wdt = pl.stage_group[st] - pl.stage_group[st - 1];   // single_rows: groups are rows
+            if (wdt > kTailWidth || T + wdt > kTailMaxRows) break;
+            T += wdt;
+            st--;
+        }
         if (T >= 512) {
             int g0 = pl.stage_group[st], n1 = pl.group_start[g0];
             // dense unit-lower L22 and the split position k1 of every tail row, from the permuted I+L
