@@ -281,23 +281,25 @@ __device__ __forceinline__ void group_bwd(const LvlView &A, int g, const double 
 }
 
 // one stage = groups [g0,g1): mutually independent, one sub-warp per group
-template <bool ZERO_X>
+// (LN lanes per group: GL for multigrid levels, 32 for the long fill-in rows of triangular factors)
+template <bool ZERO_X, int LN = GL>
 __global__ void __launch_bounds__(256, DDPCA_MIN_BLOCKS) k_sweep_fwd_stage(LvlView A, int g0, int g1, const double *__restrict__ b,
                                                          double *x, double *__restrict__ p1, const int *done)
 {
     if (done && *done) return;
-    const int g = g0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / GL);
+    const int g = g0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / LN);
     if (g >= g1) return;
-    group_fwd<ZERO_X, true>(A, g, b, x, p1, threadIdx.x % GL, subwarp_mask());
+    group_fwd<ZERO_X, true, LN>(A, g, b, x, p1, threadIdx.x % LN, subwarp_mask_t<LN>());
 }
 
+template <int LN = GL>
 __global__ void __launch_bounds__(256, DDPCA_MIN_BLOCKS) k_sweep_bwd_stage(LvlView A, int g0, int g1, const double *__restrict__ p1,
                                                          double *x, const int *done)
 {
     if (done && *done) return;
-    const int g = g0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / GL);
+    const int g = g0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / LN);
     if (g >= g1) return;
-    group_bwd<true>(A, g, p1, x, threadIdx.x % GL, subwarp_mask());
+    group_bwd<true, LN>(A, g, p1, x, threadIdx.x % LN, subwarp_mask_t<LN>());
 }
 
 // a run of small stages [s0,s1) relaxed by ONE CTA, __syncthreads() between stages

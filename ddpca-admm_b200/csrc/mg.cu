@@ -944,6 +944,7 @@ static void ldlt_solve_on(Engine *e, ddpca_ldlt *s, const double *b_dev, double 
             if (sg.s0 >= slim) break;
             if (sg.s1 > slim) sg.s1 = slim;   // only multi segments can straddle the tail boundary (tail stages hold one row)
             if (sg.multi) KL(e, DDPCA_K_SWEEP_FWD, 0, sg.bytes_lo, (k_tri_multi<true><<<1, 1024, 0, e->stream>>>(s->lo.view(), s->lo.stage_group, sg.s0, sg.s1, s->lo.b, s->lo.x, done)));
+            else if (s->lo.wide_rows) KL(e, DDPCA_K_SWEEP_FWD, 0, sg.bytes_lo, (k_sweep_fwd_stage<true, 32><<<cdiv((long)(sg.g1 - sg.g0) * 32, 256), 256, 0, e->stream>>>(s->lo.view(), sg.g0, sg.g1, s->lo.b, s->lo.x, s->lo.p1, done)));
             else KL(e, DDPCA_K_SWEEP_FWD, 0, sg.bytes_lo, (k_sweep_fwd_stage<true><<<cdiv((long)(sg.g1 - sg.g0) * GL, 256), 256, 0, e->stream>>>(s->lo.view(), sg.g0, sg.g1, s->lo.b, s->lo.x, s->lo.p1, done)));
         }
     } else {
@@ -963,6 +964,7 @@ static void ldlt_solve_on(Engine *e, ddpca_ldlt *s, const double *b_dev, double 
             if (sg.s0 >= slim) continue;
             if (sg.s1 > slim) sg.s1 = slim;
             if (sg.multi) KL(e, DDPCA_K_SWEEP_BWD, 0, sg.bytes_up, (k_tri_multi<false><<<1, 1024, 0, e->stream>>>(s->up.view(), s->up.stage_group, sg.s0, sg.s1, s->up.p1, s->up.x, done)));
+            else if (s->up.wide_rows) KL(e, DDPCA_K_SWEEP_BWD, 0, sg.bytes_up, (k_sweep_bwd_stage<32><<<cdiv((long)(sg.g1 - sg.g0) * 32, 256), 256, 0, e->stream>>>(s->up.view(), sg.g0, sg.g1, s->up.p1, s->up.x, done)));
             else KL(e, DDPCA_K_SWEEP_BWD, 0, sg.bytes_up, (k_sweep_bwd_stage<<<cdiv((long)(sg.g1 - sg.g0) * GL, 256), 256, 0, e->stream>>>(s->up.view(), sg.g0, sg.g1, s->up.p1, s->up.x, done)));
         }
     } else {
