@@ -32,6 +32,19 @@ def have_ref_binary(name="beam_nodd"):
 _cache = {}
 
 
+def _run_ref(cmd, cwd, attempts=4):
+    """Run a reference driver.  The ADMM drivers stop the reference's loop from a watcher thread with
+    _exit(); on rare occasions that races with the OpenMP runtime's teardown (SIGABRT after the dump is
+    complete or before it is written) -- retry instead of failing the parity test on it."""
+    last = None
+    for _ in range(attempts):
+        try:
+            return subprocess.check_output(cmd, cwd=cwd).decode()
+        except subprocess.CalledProcessError as e:
+            last = e
+    raise last
+
+
 def run_ref_beam(glob, divi=None, solve=1):
     """Run the prebuilt reference driver (oracle/_ref/beam_nodd) and load what it dumps.
     The binary was compiled from the untouched reference; it does not need /root/reference."""
@@ -43,7 +56,7 @@ def run_ref_beam(glob, divi=None, solve=1):
     cmd = [os.path.join(REF_BIN, "beam_nodd"), "--glob", str(glob), "--out", out, "--solve", str(solve)]
     if divi:
         cmd += ["--divi", ",".join(str(v) for v in divi)]
-    txt = subprocess.check_output(cmd, cwd=tmp).decode()
+    txt = _run_ref(cmd, tmp)
     meta = json.loads(txt.strip().splitlines()[-1])
     d = ddpk.load(out)
     os.remove(out)
@@ -91,7 +104,7 @@ def run_ref_block(glob, divi=None, musc=1, ref_iters=0):
     cmd = [os.path.join(REF_BIN, "block_admm"), "--glob", str(glob), "--musc", str(musc), "--out", out, "--ref-iters", str(ref_iters)]
     if divi:
         cmd += ["--divi", ",".join(str(v) for v in divi)]
-    txt = subprocess.check_output(cmd, cwd=tmp).decode()
+    txt = _run_ref(cmd, tmp)
     meta = json.loads(txt.strip().splitlines()[-1])
     d = ddpk.load(out)
     os.remove(out)
@@ -108,7 +121,7 @@ def run_ref_beam_dd(glob, doma=(8, 1, 1), musc=1, ref_iters=0, keep_file=False):
     out = os.path.join(tmp, "beam_dd.ddpk")
     cmd = [os.path.join(REF_BIN, "beam_admm"), "--glob", str(glob), "--musc", str(musc), "--out", out, "--ref-iters", str(ref_iters),
            "--doma", ",".join(str(v) for v in doma)]
-    txt = subprocess.check_output(cmd, cwd=tmp).decode()
+    txt = _run_ref(cmd, tmp)
     meta = json.loads(txt.strip().splitlines()[-1])
     d = ddpk.load(out)
     if keep_file:
