@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -253,13 +254,17 @@ static void launch_spmv(Engine *h, int kclass, int lvl, const DevCsr &A, const d
 template <int MODE>
 static int v2_blocks_per_sm(size_t dyn)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    // function attributes are per device: a process may hold handles on several devices (and threads)
+    static std::atomic<unsigned long long> attr_set{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_set.load() & bit)) {
         cudaFuncSetAttribute(k_level_pass<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         // the chunk rings are the only consumers of the unified L1/shared array: take all of it,
         // otherwise the driver sizes the carve-out for ~5 CTAs and the half passes lose occupancy
         cudaFuncSetAttribute(k_level_pass<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
+        attr_set.fetch_or(bit);
     }
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_level_pass<MODE>, v2_threads(MODE), dyn);
