@@ -51,6 +51,8 @@ struct ddpca_admm : Engine {
     int nglob = 0;
     std::vector<long> baseReco;
     ddpca_ldlt *coar = nullptr;
+    ddpca_mg *coar_mg = nullptr;   // macroscopic problem solved by MG-PCG instead (globCoup beyond DIRE_MAXI rows)
+    long macro_cg_iters = 0;
     double *globForc = nullptr, *globSolu = nullptr;
     double *moni_part = nullptr, *moni_out = nullptr;
     double *moni_host = nullptr;
@@ -89,6 +91,7 @@ static void admm_free(ddpca_admm *h)
         }
     }
     ldlt_free(h->coar);
+    if (h->coar_mg) ddpca_mg_destroy(h->coar_mg);
     cudaFree(h->globForc); cudaFree(h->globSolu); cudaFree(h->moni_part); cudaFree(h->moni_out); cudaFree(h->own_trace);
     if (h->moni_host) cudaFreeHost(h->moni_host);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -189,7 +192,7 @@ static int admm_bodies(ddpca_admm *h)
 // macroscopic problem, :2541-2549: this rank's part of globForc (sum over its sides)
 static int admm_macro_partial(ddpca_admm *h)
 {
-    if (!h->coar) return fail("macroscopic problem requested but not set");
+    if (!h->coar && !h->coar_mg) return fail("macroscopic problem requested but not set");
     double *gf = glob_buf(h);
     CU(cudaMemsetAsync(gf, 0, sizeof(double) * h->nglob, h->stream));
     for (int ts = 0; ts < h->ni; ts++)
@@ -207,7 +210,16 @@ static int admm_macro_partial(ddpca_admm *h)
 static int admm_macro_apply(ddpca_admm *h)
 {
     cudaStream_t st = h->stream;
-    ldlt_solve_on(h, h->coar, glob_buf(h), h->globSolu, nullptr);   // :2553
+    if (h->coar_mg) {
+        // :2560-2562  mgpi.CG_SOLV(1, globForc, globSolu)
+        long it = 0;
+        ddpca_mg_set_stream(h->coar_mg, (void *)st);
+        if (pcg_device(h->coar_mg, 1, glob_buf(h), h->globSolu, 1.0e-14, h->nglob, &it, nullptr, nullptr)) return 1;
+        h->launches += ddpca_mg_launch_count(h->coar_mg, 1);
+        h->macro_cg_iters += it;
+    } else {
+        ldlt_solve_on(h, h->coar, glob_buf(h), h->globSolu, nullptr);   // :2553
+    }
     for (int v = 0; v < h->nb; v++) {
         AdmmBody &b = h->body[v];
         if (!b.local) continue;
@@ -449,6 +461,22 @@ int ddpca_admm_set_macro(ddpca_admm *h, int nglob, const long *baseReco, ddpca_l
     return 0;
 }
 
+int ddpca_admm_set_macro_mg(ddpca_admm *h, int nglob, const long *baseReco, ddpca_mg *mgpi)
+{
+    if (!h || nglob < 1 || !baseReco || !mgpi) return fail("ddpca_admm_set_macro_mg: bad argument");
+    if (mgpi->lev[mgpi->nlev - 1].n != nglob) return fail("finest level of the macroscopic hierarchy does not match globCoup");
+    if (mgpi->device != h->device) return fail("macroscopic hierarchy lives on another device");
+    CU(cudaSetDevice(h->device));
+    h->nglob = nglob;
+    h->baseReco.assign(baseReco, baseReco + h->nb + 1);
+    ldlt_free(h->coar);
+    h->coar = nullptr;
+    if (h->coar_mg && h->coar_mg != mgpi) ddpca_mg_destroy(h->coar_mg);
+    h->coar_mg = mgpi;
+    if (dev_vec(nullptr, nglob, &h->globForc) || dev_vec(nullptr, nglob, &h->globSolu)) return 1;
+    return 0;
+}
+
 int ddpca_admm_finalize(ddpca_admm *h)
 {
     if (!h) return fail("null handle");
@@ -459,7 +487,7 @@ int ddpca_admm_finalize(ddpca_admm *h)
         if ((h->muscSett & 1) && h->body[v].accuProl.rows == 0) return fail("body " + std::to_string(v) + ": accuProl missing");
         if ((h->muscSett & 1) && h->baseReco.size() == (size_t)h->nb + 1 && h->baseReco[v] + h->body[v].accuProl.cols > h->nglob) return fail("baseReco out of range");
     }
-    if ((h->muscSett & 1) && !h->coar) return fail("macroscopic problem not set");
+    if ((h->muscSett & 1) && !h->coar && !h->coar_mg) return fail("macroscopic problem not set");
     for (int ts = 0; ts < h->ni; ts++) {
         AdmmIface &f = h->iface[ts];
         if (!f.set) return fail("interface " + std::to_string(ts) + " not set");

@@ -116,12 +116,16 @@ class MCONTACT:
     # ------------------------------------------------------------------------------------------
     @classmethod
     def from_ddpk(cls, d: dict, device: int = 0, smoother: int = SMOOTH_MC, muscSett=None, factorize=None,
-                  body_rank=None, rank: int = 0, comm=None):
+                  body_rank=None, rank: int = 0, comm=None, macro_mgpis=None):
         """Upload everything MCONTACT::ESTABLISH built (dumped by oracle/ref_drivers/admm_hook.h).
 
         Multi-GPU (one process per GPU): `body_rank[v]` = owning rank (see partition.py), `rank` = this
         process, `comm` = an object with `allreduce_sum(torch_tensor)` and `torch` device tensors for the
-        three exchange buffers (see comm.py); only the bodies / sides of this rank are uploaded."""
+        three exchange buffers (see comm.py); only the bodies / sides of this rank are uploaded.
+
+        `macro_mgpis`: an established MGPIS whose finest level is globCoup -- the macroscopic problem is then
+        solved by mgpi.CG_SOLV(1, .) like the reference does beyond DIRE_MAXI rows (MCONTACT.h:2560-2562)
+        instead of the factor coarSolv_D; ownership of its device hierarchy moves to this object."""
         lib = load_library()
         self = cls(device, smoother)
         nb, ni = int(d["nbody"][0]), int(d["niface"][0])
@@ -184,9 +188,14 @@ class MCONTACT:
                     check(lib.ddpca_admm_set_side_solver(h, C.c_int(ts), C.c_int(tv), C.c_int(which), s.release()))
             self.nc.append(ncs)
         if self.muscSett & 1:
-            s = _factor_from_dump(d, "coarSolv_D", device, ddpk.get_csr(d, "globCoup"), factorize)
             base = np.ascontiguousarray(d["baseReco"], dtype=np.int64)
-            check(lib.ddpca_admm_set_macro(h, C.c_int(s.n), base.ctypes.data_as(C.POINTER(C.c_long)), s.release()))
+            if macro_mgpis is not None:
+                nglob = int(ddpk.get_csr(d, "globCoup").shape[0])
+                check(lib.ddpca_admm_set_macro_mg(h, C.c_int(nglob), base.ctypes.data_as(C.POINTER(C.c_long)), macro_mgpis._h))
+                macro_mgpis._h = None  # ownership moved to the ADMM handle
+            else:
+                s = _factor_from_dump(d, "coarSolv_D", device, ddpk.get_csr(d, "globCoup"), factorize)
+                check(lib.ddpca_admm_set_macro(h, C.c_int(s.n), base.ctypes.data_as(C.POINTER(C.c_long)), s.release()))
         if comm is not None:
             ng_, nt_, nm_ = C.c_long(), C.c_long(), C.c_long()
             check(lib.ddpca_admm_exchange_sizes(h, C.byref(ng_), C.byref(nt_), C.byref(nm_)))

@@ -76,11 +76,6 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 		return -1;
 	}
 	const bool macrSwit = ((mc.muscSett >> 0) % 2 == 1);
-	if(macrSwit && mc.globCoup.rows() >= DIRE_MAXI){
-		std::cout << "MCONTACT::CONTACT_ANALYSIS (B200): ERROR macroscopic problem beyond DIRE_MAXI "
-			<< "is not offered by the B200 build" << std::endl;
-		return -1;
-	}
 	ddpca_admm *hand = nullptr;
 	if(ddpca_admm_create(devi, bodyNumb, inteNumb, macrSwit ? 1 : 0, &hand) != 0){
 		FAIL("create"); return -1;
@@ -147,9 +142,18 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 		}
 	}
 	if(allGood && macrSwit){
-		ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D, mc.globCoup);
-		if(soCo == nullptr || ddpca_admm_set_macro(hand, mc.globCoup.rows(), mc.baseReco.data(), soCo) != 0){
-			allGood = FAIL("set_macro");
+		if(mc.globCoup.rows() < DIRE_MAXI){// MCONTACT.h:2553-2555
+			ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D, mc.globCoup);
+			if(soCo == nullptr || ddpca_admm_set_macro(hand, mc.globCoup.rows(), mc.baseReco.data(), soCo) != 0){
+				allGood = FAIL("set_macro");
+			}
+		}
+		else{// MCONTACT.h:2560-2562: mgpi.CG_SOLV(1, globForc, globSolu), hierarchy of DOUBLE_M (:1538-1670)
+			//(COGR_MAXI < DIRE_MAXI, PREP.h:69,73: the Eigen-CG branch :2556-2558 is unreachable)
+			ddpca_mg *mgHand = mc.mgpi.RELEASE_HANDLE();
+			if(mgHand == nullptr || ddpca_admm_set_macro_mg(hand, mc.globCoup.rows(), mc.baseReco.data(), mgHand) != 0){
+				allGood = FAIL("set_macro_mg");
+			}
 		}
 	}
 	if(allGood && ddpca_admm_finalize(hand) != 0){

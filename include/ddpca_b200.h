@@ -174,6 +174,10 @@ int ddpca_admm_set_side_op(ddpca_admm *, int ts, int tv, int op, int rows, int c
 int ddpca_admm_set_side_solver(ddpca_admm *, int ts, int tv, int which, ddpca_ldlt *solver);
 /* macroscopic problem: coarSolv_D (factorised globCoup, MCONTACT.h:1229-1230) and baseReco[nbody+1] (:850-857) */
 int ddpca_admm_set_macro(ddpca_admm *, int nglob, const long *baseReco, ddpca_ldlt *coarSolv);
+/* the same for a macroscopic problem beyond DIRE_MAXI rows (PREP.h:69): the reference then solves it with
+ * MCONTACT's own multigrid hierarchy, mgpi.CG_SOLV(1, globForc, globSolu) (MCONTACT.h:2560-2562, hierarchy
+ * built by DOUBLE_M, :1538-1670).  Takes ownership of the hierarchy (finest level = globCoup). */
+int ddpca_admm_set_macro_mg(ddpca_admm *, int nglob, const long *baseReco, ddpca_mg *mgpi);
 /* Multi-GPU, one process per GPU: body_rank[v] = owning rank; a rank uploads only
  * its own bodies and their interface sides (set_body / set_side_op / set_side_solver), but declares
  * EVERY interface (set_interface) and the macroscopic solver.  Call before ddpca_admm_set_body. */

@@ -137,6 +137,28 @@ def test_block_g2_small_25_iterations_against_reference_run_here():
     mc.close()
 
 
+def test_macroscopic_problem_through_its_own_mgpis_hierarchy(block_small):
+    """MCONTACT.h:2553-2562: beyond DIRE_MAXI rows the reference solves the macroscopic problem with
+    MCONTACT's own hierarchy, mgpi.CG_SOLV(1, globForc, globSolu), instead of the factor coarSolv_D.
+    Here the fixture's globCoup is wrapped in a one-level MGPIS (its level-0 direct solve makes the
+    preconditioner exact), so the ADMM iterates must agree with those of the factor path."""
+    d, meta = block_small
+    mg = dd.MGPIS.from_hierarchy([ddpk.get_csr(d, "globCoup")], [])
+    a = dd.MCONTACT.from_ddpk(d, factorize=dense_ldlt_factor)
+    b = dd.MCONTACT.from_ddpk(d, factorize=dense_ldlt_factor, macro_mgpis=mg)
+    for tc in range(5):
+        ra, rb = a.step(tc), b.step(tc)
+    da, db = a.resuDisp, b.resuDisp
+    for v in range(a.nb):
+        assert rel(db[v], da[v]) < 1e-8
+    la, lb = a.inteLagr, b.inteLagr
+    for ts in range(a.ni):
+        for tv in range(2):
+            assert rel(lb[ts][tv], la[ts][tv]) < 1e-8
+    a.close()
+    b.close()
+
+
 def test_coulomb_friction_projection_matches_oracle(block_small):
     """The reference's frictional branch (MCONTACT.h:2648-2668: normal clamp, Coulomb cone, status
     0 open / 1 slide / 2 stick) is only reached by DEHW.  Here two vector-valued (d = 3) interfaces of
