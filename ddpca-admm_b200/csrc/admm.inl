@@ -15,14 +15,15 @@ struct AdmmBody {
     int nfull = 0, nred = 0;
     double *consForc = nullptr, *dispCons = nullptr;
     DevCsr F, FT;          // forcOper (nred x nfull) and its transpose (OUTP_SUB1 = FT u + dispCons)
-    DevCsr accuProl;       // macroscopic problem only
+    DevCsr accuProl;       // coarse-space corrections only (muscSett bits 0 / 1)
+    DevCsr globTran_D_1;   // muscSett bit 1 only (MCONTACT.h:2583)
     double *disp = nullptr, *disp_prev = nullptr, *addi = nullptr, *rhs = nullptr, *u = nullptr;
     bool set = false;
     bool local = true;     // owned by this rank (multi-GPU: one process per GPU)
     cudaEvent_t ev_done = nullptr;   // end of this body's solve on its own stream
 };
 struct AdmmSide {
-    DevCsr op[10];
+    DevCsr op[DDPCA_OP_COUNT];
     DevCsr systTran_penaT;
     ddpca_ldlt *mass = nullptr, *mass_pena = nullptr;
     double *aux = nullptr, *lagr = nullptr, *aux_prev = nullptr, *lagr_prev = nullptr, *force = nullptr, *tmp = nullptr;
@@ -54,6 +55,10 @@ struct ddpca_admm : Engine {
     ddpca_mg *coar_mg = nullptr;   // macroscopic problem solved by MG-PCG instead (globCoup beyond DIRE_MAXI rows)
     long macro_cg_iters = 0;
     double *globForc = nullptr, *globSolu = nullptr;
+    // interface-eliminated coarse problem (muscSett bit 1, MCONTACT.h:2575-2607)
+    int nglob1 = 0;
+    ddpca_ldlt *coar1 = nullptr;
+    double *globForc1_const = nullptr, *globForc1 = nullptr, *globSolu1 = nullptr;
     double *moni_part = nullptr, *moni_out = nullptr;
     double *moni_host = nullptr;
     int nslots = 0;
@@ -75,7 +80,7 @@ static void admm_free(ddpca_admm *h)
     cudaSetDevice(h->device);
     for (auto &b : h->body) {
         if (b.mg) ddpca_mg_destroy(b.mg);
-        cudaFree(b.consForc); cudaFree(b.dispCons); free_csr(b.F); free_csr(b.FT); free_csr(b.accuProl);
+        cudaFree(b.consForc); cudaFree(b.dispCons); free_csr(b.F); free_csr(b.FT); free_csr(b.accuProl); free_csr(b.globTran_D_1);
         cudaFree(b.disp); cudaFree(b.disp_prev); cudaFree(b.addi); cudaFree(b.rhs); cudaFree(b.u);
         if (b.ev_done) cudaEventDestroy(b.ev_done);
     }
@@ -92,6 +97,8 @@ static void admm_free(ddpca_admm *h)
     }
     ldlt_free(h->coar);
     if (h->coar_mg) ddpca_mg_destroy(h->coar_mg);
+    ldlt_free(h->coar1);
+    cudaFree(h->globForc1_const); cudaFree(h->globForc1); cudaFree(h->globSolu1);
     cudaFree(h->globForc); cudaFree(h->globSolu); cudaFree(h->moni_part); cudaFree(h->moni_out); cudaFree(h->own_trace);
     if (h->moni_host) cudaFreeHost(h->moni_host);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -128,9 +135,10 @@ static void admm_moni(ddpca_admm *h, int slot, int n, const double *cur, const d
 }
 
 // ---- the loop body in phases; between phases a multi-rank caller all-reduces one buffer ---------
-enum { PH_BODIES = 0, PH_MACRO_PARTIAL = 1, PH_MACRO_APPLY = 2, PH_TRACES = 3, PH_INTERFACE = 4, PH_MONITOR = 5 };
+enum { PH_BODIES = 0, PH_MACRO_PARTIAL = 1, PH_MACRO_APPLY = 2, PH_TRACES = 3, PH_INTERFACE = 4, PH_MONITOR = 5, PH_MACRO1_PARTIAL = 6, PH_MACRO1_APPLY = 7 };
 
 static double *glob_buf(ddpca_admm *h) { return h->x_glob ? h->x_glob : h->globForc; }
+static double *glob_buf1(ddpca_admm *h) { return h->x_glob ? h->x_glob : h->globForc1; }   // the exchange buffer holds max(nglob, nglob1)
 static double *moni_buf(ddpca_admm *h) { return h->x_moni ? h->x_moni : h->moni_out; }
 
 // body balance, MCONTACT.h:2511-2538 (local bodies).  The reference runs this loop under
@@ -206,6 +214,19 @@ static int admm_macro_partial(ddpca_admm *h)
         }
     return 0;
 }
+// resuDisp[v] += OUTP_SUB1(accuProl[v] * globSolu[baseReco[v] ...]) for the local bodies (:2564-2570, :2599-2604)
+static int admm_coarse_correction(ddpca_admm *h, const double *globSolu)
+{
+    cudaStream_t st = h->stream;
+    for (int v = 0; v < h->nb; v++) {
+        AdmmBody &b = h->body[v];
+        if (!b.local) continue;
+        ADMM_SPMV(b.accuProl, globSolu + h->baseReco[v], b.u, false, 1.0);      // :2564-2567
+        ADMM_SPMV(b.FT, b.u, b.disp, true, 1.0);                                 // :2569-2570 (OUTP_SUB1 ...
+        KL(h, DDPCA_K_VECTOR, 15, 24.0 * b.nfull, (k_axpy<<<cdiv(b.nfull, 256), 256, 0, st>>>(b.nfull, 1.0, b.dispCons, b.disp)));  // ... re-adds prescribed values)
+    }
+    return 0;
+}
 // :2553-2572: replicated coarse solve, correction of the local bodies
 static int admm_macro_apply(ddpca_admm *h)
 {
@@ -220,14 +241,35 @@ static int admm_macro_apply(ddpca_admm *h)
     } else {
         ldlt_solve_on(h, h->coar, glob_buf(h), h->globSolu, nullptr);   // :2553
     }
+    return admm_coarse_correction(h, h->globSolu);
+}
+// muscSett bit 1, :2576-2584: this rank's part of globForc - globForc_1
+static int admm_macro1_partial(ddpca_admm *h)
+{
+    if (!h->coar1) return fail("interface-eliminated coarse problem requested but not set");
+    double *gf = glob_buf1(h);
+    CU(cudaMemsetAsync(gf, 0, sizeof(double) * h->nglob1, h->stream));
+    for (int ts = 0; ts < h->ni; ts++)
+        for (int tv = 0; tv < 2; tv++) {
+            AdmmSide &s = h->iface[ts].side[tv];
+            if (!s.local) continue;
+            ADMM_SPMV(s.op[DDPCA_OP_GLOBTRAN_1], s.lagr, gf, true, 1.0);   // :2579
+        }
     for (int v = 0; v < h->nb; v++) {
         AdmmBody &b = h->body[v];
         if (!b.local) continue;
-        ADMM_SPMV(b.accuProl, h->globSolu + h->baseReco[v], b.u, false, 1.0);   // :2564-2567
-        ADMM_SPMV(b.FT, b.u, b.disp, true, 1.0);                                 // :2569-2570 (OUTP_SUB1 ...
-        KL(h, DDPCA_K_VECTOR, 15, 24.0 * b.nfull, (k_axpy<<<cdiv(b.nfull, 256), 256, 0, st>>>(b.nfull, 1.0, b.dispCons, b.disp)));  // ... re-adds prescribed values)
+        ADMM_SPMV(b.globTran_D_1, b.disp, gf, true, -1.0);                 // :2583
     }
     return 0;
+}
+// :2576 (constant part, added once after the sum over ranks), :2585-2606
+static int admm_macro1_apply(ddpca_admm *h)
+{
+    cudaStream_t st = h->stream;
+    double *gf = glob_buf1(h);
+    KL(h, DDPCA_K_VECTOR, 15, 24.0 * h->nglob1, (k_axpy<<<cdiv(h->nglob1, 256), 256, 0, st>>>(h->nglob1, 1.0, h->globForc1_const, gf)));
+    ldlt_solve_on(h, h->coar1, gf, h->globSolu1, nullptr);   // :2588
+    return admm_coarse_correction(h, h->globSolu1);
 }
 // side traces inpoLagr*lambda + pemaInpo_r*u (:2632-2635); remote sides of cross-rank interfaces are zero-filled
 static int admm_traces(ddpca_admm *h)
@@ -336,7 +378,8 @@ static int admm_row(ddpca_admm *h, double *monitor_row)
 static int admm_step(ddpca_admm *h, int apply_macro, double *monitor_row)
 {
     if (admm_bodies(h)) return 1;
-    if (apply_macro && (admm_macro_partial(h) || admm_macro_apply(h))) return 1;
+    if (apply_macro && (h->muscSett & 1) && (admm_macro_partial(h) || admm_macro_apply(h))) return 1;
+    if (apply_macro && (h->muscSett & 2) && (admm_macro1_partial(h) || admm_macro1_apply(h))) return 1;
     if (admm_traces(h) || admm_interface(h) || admm_monitor(h)) return 1;
     return admm_row(h, monitor_row);
 }
@@ -346,7 +389,7 @@ extern "C" {
 int ddpca_admm_create(int device, int nbody, int niface, int muscSett, ddpca_admm **out)
 {
     if (!out || nbody < 1 || niface < 0) return fail("ddpca_admm_create: bad argument");
-    if (muscSett & ~1) return fail("ddpca_admm_create: only muscSett bit 0 (macroscopic problem) is supported");
+    if (muscSett & ~3) return fail("ddpca_admm_create: muscSett has bits 0 (macroscopic problem) and 1 (interface-eliminated problem) only");
     int ndev = ddpca_device_count();
     if (ndev == 0) return fail("no CUDA device: libddpca_b200 has no CPU fallback");
     if (device < 0 || device >= ndev) return fail("device index out of range");
@@ -477,6 +520,29 @@ int ddpca_admm_set_macro_mg(ddpca_admm *h, int nglob, const long *baseReco, ddpc
     return 0;
 }
 
+int ddpca_admm_set_body_globtran_d1(ddpca_admm *h, int v, int rows, int cols, const int *rowptr, const int *colidx, const double *val)
+{
+    if (!h || v < 0 || v >= h->nb || !h->body[v].set) return fail("ddpca_admm_set_body_globtran_d1: bad argument");
+    if (cols != h->body[v].nfull) return fail("globTran_D_1 must have 3 n_nodes columns");
+    CU(cudaSetDevice(h->device));
+    CsrHost A;
+    if (host_csr(rows, cols, rowptr, colidx, val, A)) return 1;
+    return upload_csr(A, h->body[v].globTran_D_1);
+}
+
+int ddpca_admm_set_macro1(ddpca_admm *h, int nglob1, const long *baseReco, const double *globForc_1, ddpca_ldlt *coarSolv_D_1)
+{
+    if (!h || nglob1 < 1 || !baseReco || !globForc_1 || !coarSolv_D_1) return fail("ddpca_admm_set_macro1: bad argument");
+    if (coarSolv_D_1->n != nglob1) return fail("coarse solver size does not match globCoup_1");
+    CU(cudaSetDevice(h->device));
+    h->nglob1 = nglob1;
+    h->baseReco.assign(baseReco, baseReco + h->nb + 1);
+    ldlt_free(h->coar1);
+    h->coar1 = coarSolv_D_1;
+    if (dev_vec(globForc_1, nglob1, &h->globForc1_const) || dev_vec(nullptr, nglob1, &h->globForc1) || dev_vec(nullptr, nglob1, &h->globSolu1)) return 1;
+    return 0;
+}
+
 int ddpca_admm_finalize(ddpca_admm *h)
 {
     if (!h) return fail("null handle");
@@ -484,10 +550,13 @@ int ddpca_admm_finalize(ddpca_admm *h)
     for (int v = 0; v < h->nb; v++) {
         if (!h->body[v].local) continue;
         if (!h->body[v].set) return fail("body " + std::to_string(v) + " not set");
-        if ((h->muscSett & 1) && h->body[v].accuProl.rows == 0) return fail("body " + std::to_string(v) + ": accuProl missing");
+        if ((h->muscSett & 3) && h->body[v].accuProl.rows == 0) return fail("body " + std::to_string(v) + ": accuProl missing");
         if ((h->muscSett & 1) && h->baseReco.size() == (size_t)h->nb + 1 && h->baseReco[v] + h->body[v].accuProl.cols > h->nglob) return fail("baseReco out of range");
+        if ((h->muscSett & 2) && h->baseReco.size() == (size_t)h->nb + 1 && h->baseReco[v] + h->body[v].accuProl.cols > h->nglob1) return fail("baseReco out of range (globCoup_1)");
+        if ((h->muscSett & 2) && (h->body[v].globTran_D_1.rp == nullptr || h->body[v].globTran_D_1.rows != h->nglob1)) return fail("body " + std::to_string(v) + ": globTran_D_1 missing");
     }
     if ((h->muscSett & 1) && !h->coar && !h->coar_mg) return fail("macroscopic problem not set");
+    if ((h->muscSett & 2) && !h->coar1) return fail("interface-eliminated coarse problem not set");
     for (int ts = 0; ts < h->ni; ts++) {
         AdmmIface &f = h->iface[ts];
         if (!f.set) return fail("interface " + std::to_string(ts) + " not set");
@@ -498,6 +567,7 @@ int ddpca_admm_finalize(ddpca_admm *h)
             for (int o : need) if (s.op[o].rows == 0 && s.op[o].rp == nullptr) return fail("interface " + std::to_string(ts) + " side " + std::to_string(tv) + ": operator " + std::to_string(o) + " missing");
             if (h->muscSett & 1)
                 for (int o : {DDPCA_OP_GLOBTRAN, DDPCA_OP_GLOBTRAN_PENA, DDPCA_OP_GLOBTRAN_D}) if (s.op[o].rp == nullptr) return fail("macroscopic transfer operator missing");
+            if ((h->muscSett & 2) && s.op[DDPCA_OP_GLOBTRAN_1].rp == nullptr) return fail("globTran_1 missing");
             if (!s.mass || !s.mass_pena) return fail("interface " + std::to_string(ts) + " side " + std::to_string(tv) + ": mass solvers missing");
             int ng = f.d * f.nip, nfull = h->body[f.body[tv]].nfull;
             if (s.op[DDPCA_OP_SYSTTRAN].rows != nfull || s.op[DDPCA_OP_SYSTTRAN].cols != s.nc || s.op[DDPCA_OP_INPOLAGR].rows != ng ||
@@ -562,7 +632,7 @@ int ddpca_admm_exchange_sizes(const ddpca_admm *h, long *nglob, long *ntrace, lo
     if (!h) return fail("null handle");
     long nt = 0;
     for (int ts = 0; ts < h->ni; ts++) if (h->iface[ts].cross) nt += 2L * h->iface[ts].d * h->iface[ts].nip;
-    if (nglob) *nglob = h->nglob;
+    if (nglob) *nglob = std::max(h->nglob, h->nglob1);
     if (ntrace) *ntrace = nt;
     if (nmoni) *nmoni = 2L * (h->nb + 4 * h->ni);
     return 0;
@@ -585,6 +655,8 @@ int ddpca_admm_phase(ddpca_admm *h, int phase)
     case PH_TRACES: return admm_traces(h);
     case PH_INTERFACE: return admm_interface(h);
     case PH_MONITOR: return admm_monitor(h);
+    case PH_MACRO1_PARTIAL: return admm_macro1_partial(h);
+    case PH_MACRO1_APPLY: return admm_macro1_apply(h);
     }
     return fail("ddpca_admm_phase: unknown phase");
 }

@@ -28,7 +28,7 @@ EXPORTS = [
     "ddpca_mg_profile", "ddpca_mg_profile_get", "ddpca_mg_last_timing",
     "ddpca_ldlt_create", "ddpca_ldlt_create_dense", "ddpca_ldlt_solve", "ddpca_ldlt_solve_dev", "ddpca_ldlt_info", "ddpca_ldlt_destroy",
     "ddpca_admm_create", "ddpca_admm_set_body", "ddpca_admm_set_body_accuprol", "ddpca_admm_set_interface",
-    "ddpca_admm_set_side_op", "ddpca_admm_set_side_solver", "ddpca_admm_set_macro", "ddpca_admm_set_macro_mg", "ddpca_admm_finalize",
+    "ddpca_admm_set_side_op", "ddpca_admm_set_side_solver", "ddpca_admm_set_macro", "ddpca_admm_set_macro_mg", "ddpca_admm_set_body_globtran_d1", "ddpca_admm_set_macro1", "ddpca_admm_finalize",
     "ddpca_admm_step", "ddpca_admm_row_length", "ddpca_admm_get_disp", "ddpca_admm_get_side", "ddpca_admm_get_gamma",
     "ddpca_admm_launch_count", "ddpca_admm_destroy", "ddpca_admm_set_partition", "ddpca_admm_exchange_sizes",
     "ddpca_admm_set_exchange", "ddpca_admm_set_stream", "ddpca_admm_phase", "ddpca_admm_monitor_row",

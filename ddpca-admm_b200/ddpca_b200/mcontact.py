@@ -16,7 +16,7 @@ from .lib import DdpcaError, check, load_library
 from .mgpis import MGPIS, SMOOTH_MC, _pd, _pi
 
 OPS = ["systTran", "systTran_pena", "inteMass", "inteMass_pena", "inpoLagr", "inteInpo", "pemaInpo_r",
-       "globTran", "globTran_pena", "globTran_D"]
+       "globTran", "globTran_pena", "globTran_D", "globTran_1"]
 SOLVER_MASS, SOLVER_MASS_PENA = 0, 1
 
 
@@ -158,9 +158,12 @@ class MCONTACT:
             dispCons = np.ascontiguousarray(d[p + "dispCons"])
             check(lib.ddpca_admm_set_body(h, C.c_int(v), mg._h, C.c_int(nfull), _pd(consForc), _pi(F.rowptr), _pi(F.colidx), _pd(F.val), _pd(dispCons)))
             mg._h = None  # ownership moved to the ADMM handle
-            if self.muscSett & 1:
+            if self.muscSett & 3:
                 a = ddpk.get_csr(d, p + "accuProl")
                 check(lib.ddpca_admm_set_body_accuprol(h, C.c_int(v), C.c_int(a.shape[0]), C.c_int(a.shape[1]), _pi(a.rowptr), _pi(a.colidx), _pd(a.val)))
+            if self.muscSett & 2:   # interface-eliminated coarse problem, MCONTACT.h:2583
+                a = ddpk.get_csr(d, p + "globTran_D_1")
+                check(lib.ddpca_admm_set_body_globtran_d1(h, C.c_int(v), C.c_int(a.shape[0]), C.c_int(a.shape[1]), _pi(a.rowptr), _pi(a.colidx), _pd(a.val)))
         self.nc = []
         self.ng = []
         for ts in range(ni):
@@ -179,8 +182,8 @@ class MCONTACT:
                 ncs.append(int(d[q + "inteMass.shape"][0]))
                 if self.body_rank[cb[tv]] != rank:
                     continue
-                nops = 10 if (self.muscSett & 1) else 7
-                for k in range(nops):
+                ops = list(range(7)) + ([7, 8, 9] if (self.muscSett & 1) else []) + ([10] if (self.muscSett & 2) else [])
+                for k in ops:
                     m = ddpk.get_csr(d, q + OPS[k])
                     check(lib.ddpca_admm_set_side_op(h, C.c_int(ts), C.c_int(tv), C.c_int(k), C.c_int(m.shape[0]), C.c_int(m.shape[1]), _pi(m.rowptr), _pi(m.colidx), _pd(m.val)))
                 for which, nm, mat in ((SOLVER_MASS, "inteDiso", "inteMass"), (SOLVER_MASS_PENA, "inteDiso_pena", "inteMass_pena")):
@@ -196,6 +199,11 @@ class MCONTACT:
             else:
                 s = _factor_from_dump(d, "coarSolv_D", device, ddpk.get_csr(d, "globCoup"), factorize)
                 check(lib.ddpca_admm_set_macro(h, C.c_int(s.n), base.ctypes.data_as(C.POINTER(C.c_long)), s.release()))
+        if self.muscSett & 2:   # MCONTACT::MULTISCALE_1 (MCONTACT.h:1672-2343), applied at :2575-2607
+            base = np.ascontiguousarray(d["baseReco"], dtype=np.int64)
+            s1 = _factor_from_dump(d, "coarSolv_D_1", device, ddpk.get_csr(d, "globCoup_1"), factorize)
+            gf1 = np.ascontiguousarray(d["globForc_1"], dtype=np.float64)
+            check(lib.ddpca_admm_set_macro1(h, C.c_int(s1.n), base.ctypes.data_as(C.POINTER(C.c_long)), _pd(gf1), s1.release()))
         if comm is not None:
             ng_, nt_, nm_ = C.c_long(), C.c_long(), C.c_long()
             check(lib.ddpca_admm_exchange_sizes(h, C.byref(ng_), C.byref(nt_), C.byref(nm_)))
@@ -224,7 +232,7 @@ class MCONTACT:
         """One pass of the loop body (MCONTACT.h:2505-2704) on the device; returns the monitor row."""
         row = np.empty(self.row_len)
         it, dofit = C.c_long(), C.c_double()
-        macro = 1 if ((self.muscSett >> 0) % 2 == 1 and tc <= self.MULT_MAXI) else 0  # :2540
+        macro = 1 if ((self.muscSett & 3) and tc <= self.MULT_MAXI) else 0  # :2540, :2575
         lib = load_library()
         if self.comm is None:
             check(lib.ddpca_admm_step(self._h, C.c_int(macro), _pd(row), C.byref(it), C.byref(dofit)))
@@ -232,10 +240,14 @@ class MCONTACT:
             # phases of the loop body with the three exchanges of SURVEY.md §8e in between
             gl, tr, mo = self._xbuf
             check(lib.ddpca_admm_phase(self._h, C.c_int(0)))            # body solves (local bodies)
-            if macro:
+            if macro and (self.muscSett & 1):
                 check(lib.ddpca_admm_phase(self._h, C.c_int(1)))        # partial coarse right-hand side
                 self.comm.allreduce_sum(gl)
                 check(lib.ddpca_admm_phase(self._h, C.c_int(2)))        # replicated coarse solve + correction
+            if macro and (self.muscSett & 2):
+                check(lib.ddpca_admm_phase(self._h, C.c_int(6)))        # the same for the interface-eliminated problem (:2575-2607)
+                self.comm.allreduce_sum(gl)
+                check(lib.ddpca_admm_phase(self._h, C.c_int(7)))
             check(lib.ddpca_admm_phase(self._h, C.c_int(3)))            # interface side traces
             if tr is not None and tr.numel():
                 self.comm.allreduce_sum(tr)

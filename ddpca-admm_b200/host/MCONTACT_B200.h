@@ -70,14 +70,15 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 	using namespace ddpca_host;
 	const int devi = MGPIS::DEVICE();
 	const long bodyNumb = mc.multGrid.size(), inteNumb = mc.searCont.size();
-	if((mc.muscSett >> 1) % 2 == 1){
-		std::cout << "MCONTACT::CONTACT_ANALYSIS (B200): ERROR interface-eliminated problem "
-			<< "(muscSett bit 1) is not offered by the B200 build" << std::endl;
+	const bool macrSwit = ((mc.muscSett >> 0) % 2 == 1);
+	const bool elimSwit = ((mc.muscSett >> 1) % 2 == 1);// interface-eliminated coarse problem, MCONTACT.h:2575-2607
+	if(elimSwit && mc.globCoup_1.rows() >= DIRE_MAXI){// :2590-2595 (coarSolv_C_1 / mgpi_1)
+		std::cout << "MCONTACT::CONTACT_ANALYSIS (B200): ERROR interface-eliminated problem beyond DIRE_MAXI "
+			<< "is not offered by the B200 build" << std::endl;
 		return -1;
 	}
-	const bool macrSwit = ((mc.muscSett >> 0) % 2 == 1);
 	ddpca_admm *hand = nullptr;
-	if(ddpca_admm_create(devi, bodyNumb, inteNumb, macrSwit ? 1 : 0, &hand) != 0){
+	if(ddpca_admm_create(devi, bodyNumb, inteNumb, (macrSwit ? 1 : 0) | (elimSwit ? 2 : 0), &hand) != 0){
 		FAIL("create"); return -1;
 	}
 	bool allGood = true;
@@ -98,12 +99,20 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 			allGood = FAIL("set_body");
 			break;
 		}
-		if(macrSwit){
+		if(macrSwit || elimSwit){
 			SPM accu = mc.accuProl[tv];
 			accu.makeCompressed();
 			if(ddpca_admm_set_body_accuprol(hand, tv, accu.rows(), accu.cols(),
 				accu.outerIndexPtr(), accu.innerIndexPtr(), accu.valuePtr()) != 0){
 				allGood = FAIL("set_body_accuprol");
+			}
+		}
+		if(allGood && elimSwit){
+			SPM tran = mc.globTran_D_1[tv];// MCONTACT.h:2583
+			tran.makeCompressed();
+			if(ddpca_admm_set_body_globtran_d1(hand, tv, tran.rows(), tran.cols(),
+				tran.outerIndexPtr(), tran.innerIndexPtr(), tran.valuePtr()) != 0){
+				allGood = FAIL("set_body_globtran_d1");
 			}
 		}
 	}
@@ -126,6 +135,9 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 				allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_GLOBTRAN, mc.globTran[ts][tv]);
 				allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_GLOBTRAN_PENA, mc.globTran_pena[ts][tv]);
 				allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_GLOBTRAN_D, mc.globTran_D[ts][tv]);
+			}
+			if(elimSwit){
+				allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_GLOBTRAN_1, mc.globTran_1[ts][tv]);// :2579
 			}
 			if(!allGood){ FAIL("set_side_op"); break; }
 			if(mc.inteMass[ts][tv].rows() >= DIRE_MAXI){// MCONTACT.h:2676-2683: per-iteration Eigen CG
@@ -156,6 +168,13 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 			}
 		}
 	}
+	if(allGood && elimSwit){// MCONTACT.h:2576,2588
+		ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D_1, mc.globCoup_1);
+		if(soCo == nullptr || ddpca_admm_set_macro1(hand, mc.globCoup_1.rows(), mc.baseReco.data(),
+			mc.globForc_1.data(), soCo) != 0){
+			allGood = FAIL("set_macro1");
+		}
+	}
 	if(allGood && ddpca_admm_finalize(hand) != 0){
 		allGood = FAIL("finalize");
 	}
@@ -177,7 +196,7 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 	for(tc = 0; tc < maxiIter; tc ++){
 		std::cout << "The " << tc << "-th iteration";
 		OUTPUT_TIME("");
-		const int applMacr = (macrSwit && tc <= MULT_MAXI) ? 1 : 0;// :2540
+		const int applMacr = ((macrSwit || elimSwit) && tc <= MULT_MAXI) ? 1 : 0;// :2540, :2575
 		long cgitNumb = 0;
 		if(ddpca_admm_step(hand, applMacr, moniRow.data(), &cgitNumb, nullptr) != 0){
 			FAIL("step");

@@ -151,7 +151,8 @@ enum {
     DDPCA_OP_GLOBTRAN = 7,      /* globTran[ts][tv]       n_glob x d n_c      :2545          */
     DDPCA_OP_GLOBTRAN_PENA = 8, /* globTran_pena[ts][tv]                      :2546          */
     DDPCA_OP_GLOBTRAN_D = 9,    /* globTran_D[ts][tv]     n_glob x 3 n_nodes  :2547          */
-    DDPCA_OP_COUNT = 10
+    DDPCA_OP_GLOBTRAN_1 = 10,   /* globTran_1[ts][tv]     n_glob1 x d n_c     :2579 (muscSett bit 1) */
+    DDPCA_OP_COUNT = 11
 };
 enum { DDPCA_SOLVER_MASS = 0 /* inteDiso */, DDPCA_SOLVER_MASS_PENA = 1 /* inteDiso_pena */ };
 
@@ -178,6 +179,12 @@ int ddpca_admm_set_macro(ddpca_admm *, int nglob, const long *baseReco, ddpca_ld
  * MCONTACT's own multigrid hierarchy, mgpi.CG_SOLV(1, globForc, globSolu) (MCONTACT.h:2560-2562, hierarchy
  * built by DOUBLE_M, :1538-1670).  Takes ownership of the hierarchy (finest level = globCoup). */
 int ddpca_admm_set_macro_mg(ddpca_admm *, int nglob, const long *baseReco, ddpca_mg *mgpi);
+/* Interface-eliminated coarse problem (muscSett bit 1; built by MCONTACT::MULTISCALE_1, MCONTACT.h:1672-2343,
+ * applied at :2575-2607):  globForc = globForc_1 + sum globTran_1[ts][tv] inteLagr[ts][tv] - sum globTran_D_1[v] resuDisp[v],
+ * globSolu = coarSolv_D_1.solve(globForc), then the same correction of the bodies through accuProl / baseReco as bit 0.
+ * globTran_1 is side operator DDPCA_OP_GLOBTRAN_1; accuProl is needed as for bit 0.  Takes ownership of the solver. */
+int ddpca_admm_set_body_globtran_d1(ddpca_admm *, int v, int rows, int cols, const int *rowptr, const int *colidx, const double *val);
+int ddpca_admm_set_macro1(ddpca_admm *, int nglob1, const long *baseReco, const double *globForc_1, ddpca_ldlt *coarSolv_D_1);
 /* Multi-GPU, one process per GPU: body_rank[v] = owning rank; a rank uploads only
  * its own bodies and their interface sides (set_body / set_side_op / set_side_solver), but declares
  * EVERY interface (set_interface) and the macroscopic solver.  Call before ddpca_admm_set_body. */
@@ -190,7 +197,8 @@ int ddpca_admm_set_partition(ddpca_admm *, const int *body_rank, int my_rank);
 int ddpca_admm_exchange_sizes(const ddpca_admm *, long *nglob, long *ntrace, long *nmoni);
 int ddpca_admm_set_exchange(ddpca_admm *, double *globForc_dev, double *traces_dev, double *moni_dev);
 int ddpca_admm_set_stream(ddpca_admm *, void *stream);
-enum { DDPCA_PH_BODIES = 0, DDPCA_PH_MACRO_PARTIAL = 1, DDPCA_PH_MACRO_APPLY = 2, DDPCA_PH_TRACES = 3, DDPCA_PH_INTERFACE = 4, DDPCA_PH_MONITOR = 5 };
+enum { DDPCA_PH_BODIES = 0, DDPCA_PH_MACRO_PARTIAL = 1, DDPCA_PH_MACRO_APPLY = 2, DDPCA_PH_TRACES = 3, DDPCA_PH_INTERFACE = 4, DDPCA_PH_MONITOR = 5,
+       DDPCA_PH_MACRO1_PARTIAL = 6, DDPCA_PH_MACRO1_APPLY = 7 /* muscSett bit 1: between MACRO_APPLY and TRACES, same globForc exchange buffer */ };
 /* enqueue one phase of the loop body on the handle's stream (ddpca_admm_step = all of them in order) */
 int ddpca_admm_phase(ddpca_admm *, int phase);
 /* after the moni buffer has been all-reduced: synchronise and assemble the resuMoni row */

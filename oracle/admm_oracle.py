@@ -47,8 +47,10 @@ class AdmmOracle:
                 "dispCons": d[p + "dispCons"],  # OUTP_SUB1 constant part, MULTIGRID.h:1272-1279
                 "nfull": int(d[p + "nfull"][0]),
             }
-            if self.muscSett & 1:
+            if self.muscSett & 3:
                 b["accuProl"] = _csr(d, p + "accuProl")
+            if self.muscSett & 2:
+                b["globTran_D_1"] = _csr(d, p + "globTran_D_1")  # MCONTACT.h:1868-2055
             self.body.append(b)
         self.iface = []
         for ts in range(self.ni):
@@ -68,12 +70,19 @@ class AdmmOracle:
                 if self.muscSett & 1:
                     for k in ("globTran", "globTran_pena", "globTran_D"):
                         s[k] = _csr(d, q + k)
+                if self.muscSett & 2:
+                    s["globTran_1"] = _csr(d, q + "globTran_1")  # :2124-2298
                 it["side"].append(s)
             self.iface.append(it)
+        if self.muscSett & 3:
+            self.baseReco = [int(x) for x in d["baseReco"]]
         if self.muscSett & 1:
             self.globCoup = _csr(d, "globCoup")
             self.glob_solve = spla.splu(self.globCoup.tocsc()).solve  # coarSolv_D, :2553
-            self.baseReco = [int(x) for x in d["baseReco"]]
+        if self.muscSett & 2:  # interface-eliminated coarse problem, MULTISCALE_1 (:1672-2343)
+            self.globCoup_1 = _csr(d, "globCoup_1")
+            self.glob_solve_1 = spla.splu(self.globCoup_1.tocsc()).solve  # coarSolv_D_1, :2588
+            self.globForc_1 = d["globForc_1"]
         # state, zero-initialised (:875-894)
         self.resuDisp = [np.zeros(b["nfull"]) for b in self.body]
         self.inteAuxi = [[np.zeros(s["inteMass"].shape[0]) for s in it["side"]] for it in self.iface]
@@ -117,6 +126,20 @@ class AdmmOracle:
                 seg = globSolu[self.baseReco[v] : self.baseReco[v] + nrow]  # :2564-2566
                 u = b["accuProl"] @ seg  # :2567
                 self.resuDisp[v] = self.resuDisp[v] + (b["forcOper"].T @ u + b["dispCons"])  # :2569-2570 (OUTP_SUB1 re-adds prescribed values)
+        # ---- interface-eliminated coarse problem :2575-2607
+        if (self.muscSett & 2) and tc <= self.MULT_MAXI:
+            globForc = self.globForc_1.copy()  # :2576
+            for ts, it in enumerate(self.iface):
+                for tv in range(2):
+                    globForc += it["side"][tv]["globTran_1"] @ self.inteLagr[ts][tv]  # :2579
+            for v, b in enumerate(self.body):
+                globForc -= b["globTran_D_1"] @ self.resuDisp[v]  # :2583
+            globSolu = self.glob_solve_1(globForc)  # :2588
+            for v, b in enumerate(self.body):
+                nrow = b["accuProl"].shape[1]
+                seg = globSolu[self.baseReco[v] : self.baseReco[v] + nrow]  # :2599-2601
+                u = b["accuProl"] @ seg  # :2602
+                self.resuDisp[v] = self.resuDisp[v] + (b["forcOper"].T @ u + b["dispCons"])  # :2603-2604
         # ---- interface balance :2628-2685
         for ts, it in enumerate(self.iface):
             s0, s1 = it["side"]
@@ -257,6 +280,22 @@ class PartitionedAdmmOracle(AdmmOracle):
                     globForc += s["globTran"] @ self.inteLagr[ts][tv] - s["globTran_pena"] @ self.inteAuxi[ts][tv] + s["globTran_D"] @ self.resuDisp[it["contBody"][tv]]
             globForc = self.allreduce(globForc)            # exchange 1
             globSolu = self.glob_solve(globForc)            # replicated
+            for v, b in enumerate(self.body):
+                if not self.local_body[v]:
+                    continue
+                seg = globSolu[self.baseReco[v] : self.baseReco[v] + b["accuProl"].shape[1]]
+                self.resuDisp[v] = self.resuDisp[v] + (b["forcOper"].T @ (b["accuProl"] @ seg) + b["dispCons"])
+        if (self.muscSett & 2) and tc <= self.MULT_MAXI:   # interface-eliminated coarse problem, :2575-2607
+            part = np.zeros(self.globCoup_1.shape[0])
+            for ts, it in enumerate(self.iface):
+                for tv in range(2):
+                    if self._side_local(ts, tv):
+                        part += it["side"][tv]["globTran_1"] @ self.inteLagr[ts][tv]
+            for v, b in enumerate(self.body):
+                if self.local_body[v]:
+                    part -= b["globTran_D_1"] @ self.resuDisp[v]
+            globForc = self.allreduce(part) + self.globForc_1   # same exchange buffer; constant part added once
+            globSolu = self.glob_solve_1(globForc)               # replicated
             for v, b in enumerate(self.body):
                 if not self.local_body[v]:
                     continue

@@ -101,7 +101,8 @@ inline long ADMM_HOOK(MCONTACT &mc) {
 				double e2 = (g - forcOper * f).norm() / g.norm();
 				if (e1 > 1e-13 || e2 > 1e-13) { std::cerr << "forcOper self-check failed " << e1 << " " << e2 << std::endl; std::exit(3); }
 			}
-			if ((mc.muscSett & 1) && (long)mc.accuProl.size() > v) w->csr(p + "accuProl", mc.accuProl[v]);
+			if ((mc.muscSett & 3) && (long)mc.accuProl.size() > v) w->csr(p + "accuProl", mc.accuProl[v]);
+			if ((mc.muscSett & 2) && (long)mc.globTran_D_1.size() > v) w->csr(p + "globTran_D_1", mc.globTran_D_1[v]);   // MCONTACT.h:1868-2055
 		}
 		for (long ts = 0; ts < ni; ts++) {
 			std::string p = "if" + std::to_string(ts) + ".";
@@ -129,12 +130,18 @@ inline long ADMM_HOOK(MCONTACT &mc) {
 					w->csr(q + "globTran_pena", mc.globTran_pena[ts][tv]);
 					w->csr(q + "globTran_D", mc.globTran_D[ts][tv]);
 				}
+				if (mc.muscSett & 2) w->csr(q + "globTran_1", mc.globTran_1[ts][tv]);   // MCONTACT.h:2124-2298
 			}
 		}
+		if (mc.muscSett & 3) w->i64("baseReco", mc.baseReco.data(), mc.baseReco.size());
 		if (mc.muscSett & 1) {
 			w->csr("globCoup", mc.globCoup);
 			if (mc.globCoup.rows() < DIRE_MAXI) DUMP_LDLT(*w, "coarSolv_D", mc.coarSolv_D);   // MCONTACT.h:1229-1230
-			w->i64("baseReco", mc.baseReco.data(), mc.baseReco.size());
+		}
+		if (mc.muscSett & 2) {   // interface-eliminated coarse problem, MCONTACT::MULTISCALE_1 (MCONTACT.h:1672-2343)
+			w->csr("globCoup_1", mc.globCoup_1);
+			if (mc.globCoup_1.rows() < DIRE_MAXI) DUMP_LDLT(*w, "coarSolv_D_1", mc.coarSolv_D_1);   // :1857-1858
+			w->vec("globForc_1", mc.globForc_1);
 		}
 	}
 	if (mc.muscSett & 1) js << ",\"globCoup_rows\":" << mc.globCoup.rows();

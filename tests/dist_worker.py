@@ -19,10 +19,11 @@ from oracle.admm_oracle import PartitionedAdmmOracle  # noqa: E402
 
 def main():
     out_dir, musc, iters = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    dump = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "tests", "golden", "block_small.ddpk.gz")
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    d = ddpk.load(os.path.join(ROOT, "tests", "golden", "block_small.ddpk.gz"))
+    d = ddpk.load(dump)
     nb, ni = int(d["nbody"][0]), int(d["niface"][0])
     contBody = [[int(x) for x in d[f"if{ts}.contBody"]] for ts in range(ni)]
     weights = [len(d[f"body{v}.consStif{int(d[f'body{v}.maxiLeve'][0])}.val"]) for v in range(nb)]

@@ -11,14 +11,15 @@ import pytest
 
 from ddpca_b200 import ddpk
 from ddpca_b200.partition import cross_interfaces, partition_bodies
+from tests.helpers import have_ref_binary, run_ref_beam_dd
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(world, musc, iters):
+def _run(world, musc, iters, dump=None):
     out = tempfile.mkdtemp(prefix="ddpca_dist_")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29613", os.path.join(ROOT, "tests", "dist_worker.py"), out, str(musc), str(iters)]
+           "--master-port", "29613", os.path.join(ROOT, "tests", "dist_worker.py"), out, str(musc), str(iters)] + ([dump] if dump else [])
     subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
     return [json.load(open(os.path.join(out, f"rank{r}.json"))) for r in range(world)]
 
@@ -58,3 +59,23 @@ def test_two_rank_admm_equals_single_process_oracle(golden_dir, musc, iters):
     # three all-reduces per iteration with the macroscopic problem, two without
     n_it = len(o.rows)
     assert res[0]["allreduces"] == (3 if musc else 2) * n_it
+
+
+@pytest.mark.skipif(not have_ref_binary("beam_admm"), reason="oracle/_ref/beam_admm not built")
+@pytest.mark.parametrize("musc", [2, 3])
+def test_two_rank_admm_with_the_interface_eliminated_coarse_problem(musc):
+    """muscSett bit 1 (MCONTACT.h:2575-2607) on the reference's BEAM with 8 subdomains: one more
+    all-reduce of a coarse right-hand side per iteration; two ranks == one process == the reference."""
+    from oracle.admm_oracle import AdmmOracle
+
+    d, meta = run_ref_beam_dd(1, doma=(8, 1, 1), musc=musc, keep_file=True)
+    res = _run(2, musc, 3000, dump=meta["path"])
+    o = AdmmOracle(d)
+    it = o.run()
+    assert it == meta["ref_iterNumbReco"] == res[0]["iterNumbReco"] == res[1]["iterNumbReco"]
+    for r in res:
+        for v, nrm in r["disp_norm"].items():
+            assert abs(nrm - np.linalg.norm(d[f"ref.resuDisp{v}"])) <= 1e-8 * nrm
+    n_it = len(o.rows)
+    assert res[0]["allreduces"] == (2 + bin(musc).count("1")) * n_it
+

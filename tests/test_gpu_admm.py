@@ -137,6 +137,23 @@ def test_block_g2_small_25_iterations_against_reference_run_here():
     mc.close()
 
 
+@pytest.mark.skipif(not have_ref_binary("beam_admm"), reason="oracle/_ref/beam_admm not built")
+@pytest.mark.parametrize("musc", [2, 3])
+def test_beam_dd_with_the_interface_eliminated_coarse_problem(musc):
+    """muscSett bit 1 (operators of MCONTACT::MULTISCALE_1, loop block MCONTACT.h:2575-2607), alone and with
+    the macroscopic problem, on the reference's BEAM with 8 subdomains: the reference runs on this box's
+    CPU, the device loop must stop at the same iteration with the same state."""
+    d, meta = run_ref_beam_dd(1, doma=(8, 1, 1), musc=musc)
+    mc = dd.MCONTACT.from_ddpk(d)
+    assert mc.muscSett == musc
+    mc.CONTACT_ANALYSIS()
+    assert mc.iterNumbReco == meta["ref_iterNumbReco"]
+    disp = mc.resuDisp
+    for v in range(mc.nb):
+        assert rel(disp[v], d[f"ref.resuDisp{v}"]) < 1e-8
+    mc.close()
+
+
 def test_macroscopic_problem_through_its_own_mgpis_hierarchy(block_small):
     """MCONTACT.h:2553-2562: beyond DIRE_MAXI rows the reference solves the macroscopic problem with
     MCONTACT's own hierarchy, mgpi.CG_SOLV(1, globForc, globSolu), instead of the factor coarSolv_D.

@@ -49,9 +49,11 @@ def test_block_example_through_the_contact_analysis_overlay():
 
 @pytest.mark.skipif(not (os.access(os.path.join(BIN, "beam_dd_b200"), os.X_OK) and os.access(os.path.join(REF, "beam_admm"), os.X_OK)),
                     reason="overlay / reference binaries not built")
-def test_beam_dd_example_through_the_overlay():
-    """examples/BEAM.h:424-609 (SOLVE_DD, 8 subdomains) unchanged, ADMM loop and MG-PCG on the GPU."""
-    args = ["--glob", "1", "--doma", "8,1,1", "--musc", "1"]
+@pytest.mark.parametrize("musc", ["1", "2", "3"])
+def test_beam_dd_example_through_the_overlay(musc):
+    """examples/BEAM.h:424-609 (SOLVE_DD, 8 subdomains) unchanged, ADMM loop and MG-PCG on the GPU; with the
+    macroscopic problem (muscSett 1), the interface-eliminated coarse problem (2, MCONTACT.h:2575-2607) and both."""
+    args = ["--glob", "1", "--doma", "8,1,1", "--musc", musc]
     ref = _run(os.path.join(REF, "beam_admm"), args)
     gpu = _run(os.path.join(BIN, "beam_dd_b200"), args)
     assert gpu["error"] is False
