@@ -156,7 +156,7 @@ enum {
 };
 enum { DDPCA_SOLVER_MASS = 0 /* inteDiso */, DDPCA_SOLVER_MASS_PENA = 1 /* inteDiso_pena */ };
 
-/* muscSett: bit 0 = macroscopic problem (MCONTACT.h:858-860); bit 1 is not supported */
+/* muscSett: bit 0 = macroscopic problem (MCONTACT.h:858-860), bit 1 = interface-eliminated coarse problem (:861-863) */
 int ddpca_admm_create(int device, int nbody, int niface, int muscSett, ddpca_admm **out);
 /* Body v.  Takes ownership of `mg` (multGrid[v].mgpi).  forcOper (n_L x 3 n_nodes) is
  * MULTIGRID::ADDITIONAL_FORCE as one operator, consOper[L] prolOper[L]^T earlTran^T
@@ -164,7 +164,7 @@ int ddpca_admm_create(int device, int nbody, int niface, int muscSett, ddpca_adm
  * (MULTIGRID.h:1263-1281, dispCons = OUTP_SUB1(0)); consForc is multGrid[v].consForc. */
 int ddpca_admm_set_body(ddpca_admm *, int v, ddpca_mg *mg, int nfull, const double *consForc,
                         const int *F_rowptr, const int *F_colidx, const double *F_val, const double *dispCons);
-/* accuProl[v] (MCONTACT.h:864-872), needed when muscSett bit 0 is set */
+/* accuProl[v] (MCONTACT.h:864-872), needed when muscSett bit 0 or bit 1 is set */
 int ddpca_admm_set_body_accuprol(ddpca_admm *, int v, int rows, int cols, const int *rowptr, const int *colidx, const double *val);
 /* Interface ts between contBody[ts][0..1]; fricCoef < 0 tied, = 0 frictionless, > 0 Coulomb
  * (MCONTACT.h:15-18); gapTerm = pemaInpo[ts] * inpoNgap[ts] (MCONTACT.h:2636), length d n_ip
@@ -205,7 +205,7 @@ int ddpca_admm_phase(ddpca_admm *, int phase);
 int ddpca_admm_monitor_row(ddpca_admm *, double *monitor_row, long *cg_iters, double *cg_dof_iters);
 /* checks completeness, allocates the zero initial state (MCONTACT.h:875-894) */
 int ddpca_admm_finalize(ddpca_admm *);
-/* One iteration.  apply_macro = ((muscSett>>0)%2 == 1 && tc <= MULT_MAXI) as evaluated by the
+/* One iteration.  apply_macro = ((muscSett & 3) != 0 && tc <= MULT_MAXI) (MCONTACT.h:2540,2575) as evaluated by the
  * caller (MCONTACT.h:2540).  monitor_row (host, ddpca_admm_row_length() doubles) is the line
  * MONITOR appends to resuMoni.txt.  cg_iters / cg_dof_iters: CG iterations of this step summed
  * over bodies, and sum of n_L * iterations. */
