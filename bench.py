@@ -90,7 +90,13 @@ def generate_admm_workload(glob, divi):
     if divi:
         cmd += ["--divi", divi]
     t0 = time.time()
-    txt = subprocess.check_output(cmd, cwd=cdir).decode()
+    for attempt in range(3):   # the driver ends through a watcher thread (_exit); a rare teardown race aborts it
+        try:
+            txt = subprocess.check_output(cmd, cwd=cdir).decode()
+            break
+        except subprocess.CalledProcessError:
+            if attempt == 2:
+                raise
     meta = json.loads(txt.strip().splitlines()[-1])
     meta["generate_wall_s"] = time.time() - t0
     os.replace(out + ".tmp", out)
