@@ -154,6 +154,20 @@ def test_beam_dd_with_the_interface_eliminated_coarse_problem(musc):
     mc.close()
 
 
+def test_admm_loop_is_bit_reproducible(block_small):
+    """Fixed-order reductions everywhere, body solves on their own streams, the macroscopic solve with its dense
+    tail: three fresh handles must produce identical monitor rows and displacements, bit for bit."""
+    d, meta = block_small
+    outs = []
+    for rep in range(3):
+        mc = dd.MCONTACT.from_ddpk(d, factorize=dense_ldlt_factor)
+        rows = [mc.step(tc).copy() for tc in range(4)]
+        outs.append((np.concatenate(mc.resuDisp), np.array(rows)))
+        mc.close()
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1])
+
+
 def test_macroscopic_problem_through_its_own_mgpis_hierarchy(block_small):
     """MCONTACT.h:2553-2562: beyond DIRE_MAXI rows the reference solves the macroscopic problem with
     MCONTACT's own hierarchy, mgpi.CG_SOLV(1, globForc, globSolu), instead of the factor coarSolv_D.
