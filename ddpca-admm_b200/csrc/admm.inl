@@ -485,7 +485,9 @@ int ddpca_admm_set_side_solver(ddpca_admm *h, int ts, int tv, int which, ddpca_l
 {
     if (!h || ts < 0 || ts >= h->ni || tv < 0 || tv > 1 || !sol || (which != DDPCA_SOLVER_MASS && which != DDPCA_SOLVER_MASS_PENA)) return fail("ddpca_admm_set_side_solver: bad argument");
     if (sol->device != h->device) return fail("solver lives on another device");
+    if (!h->iface[ts].set) return fail("ddpca_admm_set_side_solver: interface not set");
     AdmmSide &s = h->iface[ts].side[tv];
+    if (!s.local) return fail("ddpca_admm_set_side_solver: this side belongs to another rank");
     if (which == DDPCA_SOLVER_MASS) { ldlt_free(s.mass); s.mass = sol; }
     else { ldlt_free(s.mass_pena); s.mass_pena = sol; }
     return 0;
@@ -622,6 +624,7 @@ int ddpca_admm_set_partition(ddpca_admm *h, const int *body_rank, int my_rank)
 {
     if (!h || !body_rank) return fail("ddpca_admm_set_partition: bad argument");
     for (int v = 0; v < h->nb; v++) if (h->body[v].set) return fail("ddpca_admm_set_partition must precede ddpca_admm_set_body");
+    for (int ts = 0; ts < h->ni; ts++) if (h->iface[ts].set) return fail("ddpca_admm_set_partition must precede ddpca_admm_set_interface");
     h->body_rank.assign(body_rank, body_rank + h->nb);
     h->my_rank = my_rank;
     for (int v = 0; v < h->nb; v++) h->body[v].local = (body_rank[v] == my_rank);
@@ -683,7 +686,9 @@ int ddpca_admm_get_disp(ddpca_admm *h, int v, double *out)
     if (!h || v < 0 || v >= h->nb || !out) return fail("ddpca_admm_get_disp: bad argument");
     CU(cudaSetDevice(h->device));
     if (!h->body[v].local) return fail("ddpca_admm_get_disp: body belongs to another rank");
-    CU(cudaMemcpy(out, h->body[v].disp, sizeof(double) * h->body[v].nfull, cudaMemcpyDeviceToHost));
+    // ordered after everything enqueued on the handle's stream (which is non-blocking w.r.t. the legacy stream)
+    CU(cudaMemcpyAsync(out, h->body[v].disp, sizeof(double) * h->body[v].nfull, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 int ddpca_admm_get_side(ddpca_admm *h, int ts, int tv, double *aux, double *lagr)
@@ -692,8 +697,9 @@ int ddpca_admm_get_side(ddpca_admm *h, int ts, int tv, double *aux, double *lagr
     CU(cudaSetDevice(h->device));
     AdmmSide &s = h->iface[ts].side[tv];
     if (!s.local) return fail("ddpca_admm_get_side: side belongs to another rank");
-    if (aux) CU(cudaMemcpy(aux, s.aux, sizeof(double) * s.nc, cudaMemcpyDeviceToHost));
-    if (lagr) CU(cudaMemcpy(lagr, s.lagr, sizeof(double) * s.nc, cudaMemcpyDeviceToHost));
+    if (aux) CU(cudaMemcpyAsync(aux, s.aux, sizeof(double) * s.nc, cudaMemcpyDeviceToHost, h->stream));
+    if (lagr) CU(cudaMemcpyAsync(lagr, s.lagr, sizeof(double) * s.nc, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 int ddpca_admm_get_gamma(ddpca_admm *h, int ts, double *gamma, int *fricStat)
@@ -701,8 +707,9 @@ int ddpca_admm_get_gamma(ddpca_admm *h, int ts, double *gamma, int *fricStat)
     if (!h || ts < 0 || ts >= h->ni) return fail("ddpca_admm_get_gamma: bad argument");
     CU(cudaSetDevice(h->device));
     AdmmIface &f = h->iface[ts];
-    if (gamma) CU(cudaMemcpy(gamma, f.gamma, sizeof(double) * f.d * f.nip, cudaMemcpyDeviceToHost));
-    if (fricStat) CU(cudaMemcpy(fricStat, f.stat, sizeof(int) * f.d * f.nip, cudaMemcpyDeviceToHost));
+    if (gamma) CU(cudaMemcpyAsync(gamma, f.gamma, sizeof(double) * f.d * f.nip, cudaMemcpyDeviceToHost, h->stream));
+    if (fricStat) CU(cudaMemcpyAsync(fricStat, f.stat, sizeof(int) * f.d * f.nip, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 long ddpca_admm_launch_count(ddpca_admm *h, int reset)

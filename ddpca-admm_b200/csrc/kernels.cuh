@@ -748,6 +748,187 @@ __global__ void k_s_beta_next(PcgState *st, const double *rr_partial, const doub
     }
     if (use_cond && threadIdx.x == 0) cudaGraphSetConditional(cond, st->done ? 0u : 1u);
 }
+// ---- batched PCG: several independent hierarchies ("subs") advance in lock-step ---------------------
+// One ddpca_mg may hold nsub >= 1 subdomain hierarchies as ONE block-diagonal hierarchy: every level
+// kernel (sweeps, residual, transfers, product) then works on all subdomains at once -- small subdomains,
+// which cannot fill 148 SMs alone, share launches instead of queueing behind each other.  The CG recurrence
+// stays per subdomain (MGPIS.h:163-225 is called once per subdomain, MCONTACT.h:2531): each sub has its own
+// PcgState, reductions are segmented, a converged sub freezes (x, r, p are no longer touched, its iteration
+// count stops), the loop ends when every sub is done.
+// Rows of one sub are contiguous inside every stage (colour) of the permuted finest level; these ranges are
+// cut into CHUNKS of at most kSegRows rows, numbered sub-major, so the partial sums of sub s are the
+// contiguous range [sub_chunk[s], sub_chunk[s+1]) -- fixed order, bit-reproducible.
+constexpr int kSegRows = 2048;
+struct __align__(16) SegChunk { int row0, nrows, sub, pad; };
+struct BatchFlags { int done_all; int pad; long long it_max; };
+
+// partial[chunk] = sum_{i in chunk} a_i b_i
+__global__ void __launch_bounds__(256) k_seg_dot(const SegChunk *__restrict__ ch, const double *__restrict__ a, const double *__restrict__ b,
+                                                 double *partial, const int *done)
+{
+    if (done && *done) return;
+    const SegChunk c = ch[blockIdx.x];
+    const double *pa = a + c.row0, *pb = b + c.row0;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < c.nrows; i += 256) acc += pa[i] * pb[i];
+    block_sum_to_partial(acc, partial);
+}
+// rel_tol / maxit of the coming solve (kept out of the captured graphs); maxit <= 0: rows of the sub (MGPIS.h:178)
+__global__ void k_seg_params(int nsub, PcgState *st, const int *__restrict__ sub_n, double rel_tol, long long maxit)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsub) return;
+    st[s].rel_tol = rel_tol;
+    st[s].maxit = maxit > 0 ? maxit : (long long)sub_n[s];
+}
+// after r = b: bb = b.b, tol = rel_tol ||b||, loop condition of MGPIS.h:198 at it = 0 -- one warp per sub
+__global__ void __launch_bounds__(1024) k_seg_init(int nsub, PcgState *st, const int *__restrict__ sub_chunk, const double *__restrict__ bb_partial,
+                                                    BatchFlags *fl)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int all = 1;
+    for (int s = w; s < nsub; s += 32) {
+        const double bb = warp_reduce_partials(bb_partial + sub_chunk[s], sub_chunk[s + 1] - sub_chunk[s]);
+        int dn = 0;
+        if (lane == 0) {
+            PcgState *p = st + s;
+            p->bb = bb; p->rr = bb; p->tol = p->rel_tol * sqrt(bb);
+            p->it = 0; p->alpha = 0.0; p->beta = 0.0; p->delta_old = 0.0; p->delta_new = 0.0;
+            dn = !(0 < p->maxit && sqrt(bb) > p->tol);
+            p->done = dn;
+        }
+        dn = __shfl_sync(0xffffffffu, dn, 0);
+        all &= dn;
+    }
+    all = __syncthreads_and(all);
+    if (threadIdx.x == 0) { fl->done_all = all; fl->it_max = 0; }
+}
+// delta_new = r.z after the first preconditioner application (MGPIS.h:197); `cond`: WHILE node of the solve graph
+__global__ void __launch_bounds__(1024) k_seg_delta0(int nsub, PcgState *st, const int *__restrict__ sub_chunk, const double *__restrict__ rz_partial,
+                                                      const BatchFlags *fl, cudaGraphConditionalHandle cond, int use_cond)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int s = w; s < nsub; s += 32) {
+        if (st[s].done) continue;   // warp-uniform
+        const double d = warp_reduce_partials(rz_partial + sub_chunk[s], sub_chunk[s + 1] - sub_chunk[s]);
+        if (lane == 0) st[s].delta_new = d;
+    }
+    if (use_cond && threadIdx.x == 0) cudaGraphSetConditional(cond, fl->done_all ? 0u : 1u);
+}
+// alpha = delta_new / (p.q) ; x += alpha p ; r -= alpha q ; partial = r.r   (MGPIS.h:201-203 and the norm of :198)
+// per chunk; every CTA finishes the p.q reduction of ITS sub itself (same fixed order => same alpha in all of them)
+__global__ void __launch_bounds__(256) k_seg_update_xr(const SegChunk *__restrict__ ch, const int *__restrict__ sub_chunk, PcgState *st,
+                                                       const double *__restrict__ pq_partial, const double *__restrict__ p,
+                                                       const double *__restrict__ q, double *__restrict__ x, double *__restrict__ r,
+                                                       double *rr_partial, const int *done)
+{
+    if (*done) return;
+    const SegChunk c = ch[blockIdx.x];
+    PcgState *ps = st + c.sub;
+    if (ps->done) return;   // frozen sub: its partial sums are not consulted any more
+    __shared__ double s_alpha;
+    if (threadIdx.x < 32) {
+        const int c0 = sub_chunk[c.sub];
+        const double pq = warp_reduce_partials(pq_partial + c0, sub_chunk[c.sub + 1] - c0);
+        if (threadIdx.x == 0) {
+            s_alpha = ps->delta_new / pq;
+            if ((int)blockIdx.x == c0) { ps->pq = pq; ps->alpha = s_alpha; }
+        }
+    }
+    __syncthreads();
+    const double alpha = s_alpha;
+    double acc = 0.0;
+    for (int i = c.row0 + threadIdx.x; i < c.row0 + c.nrows; i += 256) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        acc += ri * ri;
+    }
+    block_sum_to_partial(acc, rr_partial);
+}
+// per sub: rr = r.r ; delta_old = delta_new ; delta_new = r.z ; beta ; it++ ; loop condition (MGPIS.h:211-213,219,198);
+// the batch is done when every sub is
+__global__ void __launch_bounds__(1024) k_seg_beta_next(int nsub, PcgState *st, const int *__restrict__ sub_chunk, const double *__restrict__ rr_partial,
+                                                         const double *__restrict__ rz_partial, BatchFlags *fl, cudaGraphConditionalHandle cond, int use_cond)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int all = 1;
+    if (!fl->done_all) {
+        for (int s = w; s < nsub; s += 32) {
+            PcgState *p = st + s;
+            int dn = p->done;   // warp-uniform
+            if (!dn) {
+                const int c0 = sub_chunk[s], nc = sub_chunk[s + 1] - c0;
+                const double rr = warp_reduce_partials(rr_partial + c0, nc);
+                const double rz = warp_reduce_partials(rz_partial + c0, nc);
+                if (lane == 0) {
+                    p->rr = rr;
+                    p->delta_old = p->delta_new; p->delta_new = rz; p->beta = rz / p->delta_old;
+                    p->it += 1;
+                    if (!(p->it < p->maxit && sqrt(rr) > p->tol)) { p->done = 1; dn = 1; }
+                }
+                dn = __shfl_sync(0xffffffffu, dn, 0);
+            }
+            all &= dn;
+        }
+        all = __syncthreads_and(all);
+        if (threadIdx.x == 0) { fl->it_max += 1; if (all) fl->done_all = 1; }
+    }
+    if (use_cond && threadIdx.x == 0) cudaGraphSetConditional(cond, all ? 0u : 1u);
+}
+// p = z + beta p   (MGPIS.h:214); skipped for frozen subs (p is dead by then)
+__global__ void __launch_bounds__(256) k_seg_update_p(const SegChunk *__restrict__ ch, const PcgState *__restrict__ st, const double *__restrict__ z,
+                                                      double *__restrict__ p, const int *done)
+{
+    if (*done) return;
+    const SegChunk c = ch[blockIdx.x];
+    if (st[c.sub].done) return;
+    const double beta = st[c.sub].beta;
+    for (int i = c.row0 + threadIdx.x; i < c.row0 + c.nrows; i += 256) p[i] = z[i] + beta * p[i];
+}
+// level-0 direct solves of all subs: y_s = Binv_s b_s.  One warp per row; off[s] = first row of sub s,
+// boff[s] = first element of its dense inverse.
+__global__ void __launch_bounds__(256) k_dense_gemv_batch(int nsub, const int *__restrict__ off, const long long *__restrict__ boff,
+                                                          const double *__restrict__ B, const double *__restrict__ x, double *__restrict__ y,
+                                                          const int *done)
+{
+    if (done && *done) return;
+    const int lane = threadIdx.x & 31;
+    const int i = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (i >= off[nsub]) return;
+    int lo = 0, hi = nsub;   // largest s with off[s] <= i
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
+    const int n = off[lo + 1] - off[lo];
+    const double *row = B + boff[lo] + (size_t)(i - off[lo]) * n;
+    const double *xs = x + off[lo];
+    double s = 0.0;
+    if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(xs) & 15) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+        const int n2 = n >> 1;
+        const double2 *x2 = reinterpret_cast<const double2 *>(xs);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int j = lane;
+        for (; j + 96 < n2; j += 128) {
+            const double2 a0 = ld_stream2(row + 2 * j), a1 = ld_stream2(row + 2 * (j + 32));
+            const double2 a2 = ld_stream2(row + 2 * (j + 64)), a3 = ld_stream2(row + 2 * (j + 96));
+            const double2 b0 = __ldg(x2 + j), b1 = __ldg(x2 + j + 32), b2 = __ldg(x2 + j + 64), b3 = __ldg(x2 + j + 96);
+            s0 += a0.x * b0.x + a0.y * b0.y;
+            s1 += a1.x * b1.x + a1.y * b1.y;
+            s2 += a2.x * b2.x + a2.y * b2.y;
+            s3 += a3.x * b3.x + a3.y * b3.y;
+        }
+        for (; j < n2; j += 32) {
+            const double2 a0 = ld_stream2(row + 2 * j);
+            const double2 b0 = __ldg(x2 + j);
+            s0 += a0.x * b0.x + a0.y * b0.y;
+        }
+        s = (s0 + s1) + (s2 + s3);
+    } else {
+        for (int j = lane; j < n; j += 32) s += ld_stream(row + j) * __ldg(xs + j);
+    }
+    s = warp_sum(s);
+    if (lane == 0) y[i] = s;
+}
+
 // ---- ADMM interface kernels (MCONTACT.h:2632-2668, :2737-2833) ---------------------------------
 // gamma = 0.5*(t - gapTerm) followed by the contact projection; t already holds
 // inpoLagr0 l0 - inpoLagr1 l1 + pemaInpo_r0 u0 - pemaInpo_r1 u1.

@@ -42,6 +42,18 @@ static int fail(const std::string &m) { g_err = m; return 1; }
         }                                                                                         \
     } while (0)
 
+// inside the host-driven solvers: error exit through the function's cleanup() lambda
+#define CUX(call)                                                                                 \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" +  \
+                    std::to_string(__LINE__) + ")";                                               \
+            cleanup();                                                                            \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+
 namespace {
 
 struct DevCsr {
@@ -112,6 +124,7 @@ struct Engine {
     bool capturing = false;
     long captured_nodes = 0;
     bool profile = false;
+    std::string launch_err;   // first failed launch since the last check (cooperative launches report through their return code)
     std::vector<ProfRec> prof;
     double prof_ms[DDPCA_K_COUNT][16];
     long prof_n[DDPCA_K_COUNT][16];
@@ -217,6 +230,16 @@ static int upload_vec(const std::vector<T> &h, T **d)
     return 0;
 }
 
+// Work vector of n entries + ONE always-zero slot at [n], all zero-initialised.  The padding entries of
+// the group layouts (value 0) point at column n, so a gather never multiplies 0 by stale or non-finite
+// memory; nothing ever writes slot n.  The reference starts every solve from fresh zero vectors.
+static int alloc_vec(double **d, long n)
+{
+    CU(cudaMalloc(d, sizeof(double) * (size_t)(n + 1)));
+    CU(cudaMemset(*d, 0, sizeof(double) * (size_t)(n + 1)));
+    return 0;
+}
+
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 // ---- kernel launch helpers (all on h->stream) ----------------------------------------------
@@ -260,15 +283,20 @@ static int v2_blocks_per_sm(size_t dyn)
     cudaGetDevice(&dev);
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(attr_set.load() & bit)) {
-        cudaFuncSetAttribute(k_level_pass<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e1 = cudaFuncSetAttribute(k_level_pass<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         // the chunk rings are the only consumers of the unified L1/shared array: take all of it,
         // otherwise the driver sizes the carve-out for ~5 CTAs and the half passes lose occupancy
-        cudaFuncSetAttribute(k_level_pass<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaError_t e2 = cudaFuncSetAttribute(k_level_pass<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            std::fprintf(stderr, "ddpca: cudaFuncSetAttribute(k_level_pass<%d>) failed: %s\n", MODE, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+            cudaGetLastError();
+            return 0;   // the caller reports the launch as impossible
+        }
         attr_set.fetch_or(bit);
     }
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_level_pass<MODE>, v2_threads(MODE), dyn);
-    return std::max(nb, 1);
+    return std::max(nb, 1);   // 0 is reserved for "attributes could not be set" above
 }
 // returns the grid used (number of partial sums for SPMV with a dot)
 template <int MODE>
@@ -282,6 +310,7 @@ static int launch_v2(Engine *h, Level &L, int kclass, int l, double bytes, const
     size_t buf = L.buf[tab];
     size_t dyn = (size_t)kV2Bufs * buf;
     int per_sm = v2_blocks_per_sm<MODE>(dyn);
+    if (per_sm <= 0) { if (h->launch_err.empty()) h->launch_err = "k_level_pass: shared-memory attributes could not be set"; return 0; }
     int cap = per_sm * h->sms;
     int grid = std::min(staged ? L.max_stage_chunks[tab] : L.nchunks[tab], cap);
     if (MODE == V2_SPMV && w) grid = std::min(grid, kNumPart);
@@ -295,7 +324,9 @@ static int launch_v2(Engine *h, Level &L, int kclass, int l, double bytes, const
     h->pre(kclass, l, bytes);
     if (staged && nst > 1) {
         void *args[] = {(void *)&A, (void *)&buf, (void *)&gbar, (void *)&b, (void *)&x, (void *)&p1, (void *)&y, (void *)&w, (void *)&partial, (void *)&done};
-        cudaLaunchCooperativeKernel((const void *)k_level_pass<MODE>, dim3(grid), dim3(v2_threads(MODE)), args, dyn, h->stream);
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_level_pass<MODE>, dim3(grid), dim3(v2_threads(MODE)), args, dyn, h->stream);
+        if (e != cudaSuccess && h->launch_err.empty())
+            h->launch_err = std::string("cooperative launch of k_level_pass failed (grid ") + std::to_string(grid) + " too large for co-residency?): " + cudaGetErrorString(e);
     } else {
         k_level_pass<MODE><<<grid, v2_threads(MODE), dyn, h->stream>>>(A, buf, gbar, b, x, p1, y, w, partial, done);
     }
@@ -508,6 +539,7 @@ static int build_iter_graph(ddpca_mg *h, int prec)
 static int pcg_finish(ddpca_mg *h, long *iters, double *resid, double *tol_abs)
 {
     CU(cudaStreamSynchronize(h->stream));
+    if (!h->launch_err.empty()) { std::string m = h->launch_err; h->launch_err.clear(); cudaGetLastError(); return fail(m); }
     if (h->profile) h->prof_collect();
     if (h->pending_while) h->launches += h->solve_init_nodes[h->pending_prec] + (long)h->st_host[0].it * h->solve_iter_nodes[h->pending_prec];
     if (iters) *iters = (long)h->st_host[0].it;
@@ -535,7 +567,6 @@ static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref,
         build_solve_graph(h, prec);
         if (h->while_state[prec] != 1 && build_iter_graph(h, prec)) return 1;
     }
-    if (!h->profile) build_solve_graph(h, prec);
     const bool use_while = !h->profile && h->while_state[prec] == 1;
     // r = b (device numbering), x = 0                                  MGPIS.h:173,189
     KL(h, DDPCA_K_VECTOR, Lf, 20.0 * n, (k_gather<<<cdiv(n, 256), 256, 0, h->stream>>>(n, L.perm, b_ref, h->cg_r)));
@@ -620,7 +651,7 @@ static bool build_group_layout(const CsrHost &Ap, const LevelPlan &pl, GroupLayo
         int len = m.pad;
         const int *c0 = Ap.ci.data() + Ap.rp[m.row0];
         for (int k = 0; k < len; k++) out.ci[m.cptr + k] = c0[k];
-        if (m.len > len) out.ci[m.cptr + len] = c0[len - 1];   // padding: value 0 on a valid column
+        if (m.len > len) out.ci[m.cptr + len] = Ap.rows;      // padding: value 0 times the always-zero slot x[n] (alloc_vec)
         for (int r = 0; r < m.gs; r++) {
             const double *vr = Ap.v.data() + Ap.rp[m.row0 + r];
             double *dst = out.v.data() + m.voff + (long)r * m.len;
@@ -728,8 +759,10 @@ static bool build_layout2(const CsrHost &Ap, const LevelPlan &pl, Layout2Host &o
         const int *c0 = Ap.ci.data() + Ap.rp[r0];
         const int kd = (int)(std::lower_bound(c0, c0 + len, r0) - c0);
         const int nlr = kd, nur = len - kd - gs;
-        for (int k = 0; k < m.nl; k++) out.CL[m.cl + k] = k < nlr ? c0[k] : r0;            // pads: value 0 on a valid column
-        for (int k = 0; k < m.nu; k++) out.CU[m.cu + k] = k < nur ? c0[kd + gs + k] : r0;
+        // pads: value 0 times the always-zero slot x[n] of every gathered vector (alloc_vec) -- never a row
+        // of the level, whose entry may be stale or, after a failed solve, not finite (0 * NaN = NaN)
+        for (int k = 0; k < m.nl; k++) out.CL[m.cl + k] = k < nlr ? c0[k] : Ap.rows;
+        for (int k = 0; k < m.nu; k++) out.CU[m.cu + k] = k < nur ? c0[kd + gs + k] : Ap.rows;
         for (int r = 0; r < gs; r++) {
             const double *vr = Ap.v.data() + Ap.rp[r0 + r];
             double *dl = out.VL.data() + (size_t)m.vl * 2 + (size_t)r * m.nl;
@@ -842,10 +875,7 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
         }
     }
     if (upload_vec(L.plan.stage_group, &L.stage_group) || upload_vec(L.plan.perm, &L.perm)) return 1;
-    CU(cudaMalloc(&L.x, sizeof(double) * std::max(1, n)));
-    CU(cudaMalloc(&L.b, sizeof(double) * std::max(1, n)));
-    CU(cudaMalloc(&L.p1, sizeof(double) * std::max(1, n)));
-    CU(cudaMalloc(&L.r, sizeof(double) * std::max(1, n)));
+    if (alloc_vec(&L.x, n) || alloc_vec(&L.b, n) || alloc_vec(&L.p1, n) || alloc_vec(&L.r, n)) return 1;
     return 0;
 }
 static void free_level(Level &L)
@@ -1202,13 +1232,8 @@ int ddpca_mg_create(int device, int nlevels, const int *n, const int *const *row
             FAILC(upload_csr(Rp, L.R));
         }
     }
-    CUC(cudaMalloc(&h->cg_r, sizeof(double) * nmax));
-    CUC(cudaMalloc(&h->cg_p, sizeof(double) * nmax));
-    CUC(cudaMalloc(&h->cg_q, sizeof(double) * nmax));
-    CUC(cudaMalloc(&h->cg_z, sizeof(double) * nmax));
-    CUC(cudaMalloc(&h->cg_x, sizeof(double) * nmax));
-    CUC(cudaMalloc(&h->stage_a, sizeof(double) * nmax));
-    CUC(cudaMalloc(&h->stage_b, sizeof(double) * nmax));
+    FAILC(alloc_vec(&h->cg_r, nmax) || alloc_vec(&h->cg_p, nmax) || alloc_vec(&h->cg_q, nmax) || alloc_vec(&h->cg_z, nmax) ||
+          alloc_vec(&h->cg_x, nmax) || alloc_vec(&h->stage_a, nmax) || alloc_vec(&h->stage_b, nmax));
     CUC(cudaMalloc(&h->st, sizeof(PcgState)));
     CUC(cudaMemset(h->st, 0, sizeof(PcgState)));
     CUC(cudaMallocHost(&h->st_host, sizeof(PcgState) * (kDepth + 2)));
@@ -1274,6 +1299,7 @@ static int to_dev(ddpca_mg *h, int l, const double *host, double *dev_perm)
     Level &L = h->lev[l];
     CU(cudaMemcpyAsync(h->stage_a, host, sizeof(double) * L.n, cudaMemcpyHostToDevice, h->stream));
     k_gather<<<cdiv(L.n, 256), 256, 0, h->stream>>>(L.n, L.perm, h->stage_a, dev_perm);
+    CU(cudaMemsetAsync(dev_perm + L.n, 0, sizeof(double), h->stream));   // the always-zero slot of THIS level (the vectors are sized for the largest)
     return 0;
 }
 static int to_host(ddpca_mg *h, int l, const double *dev_perm, double *host)
@@ -1408,14 +1434,14 @@ int ddpca_mg_gmres(ddpca_mg *h, int prec, const double *b, double *x, long *iter
         if (L.v2) k_extract_diag_inv2<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view2(), L.dinv);
         else k_extract_diag_inv<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
     }
+    // Arnoldi vectors with stride n+1: each keeps the always-zero slot the padded gathers rely on (alloc_vec)
+    const size_t ldv = (size_t)n + 1;
     double *V = nullptr, *x0 = nullptr, *bd = nullptr;
-    CU(cudaMalloc(&V, sizeof(double) * (size_t)n * (STAG + 1)));
-    CU(cudaMalloc(&x0, sizeof(double) * n));
-    CU(cudaMalloc(&bd, sizeof(double) * n));
     auto cleanup = [&]() { cudaFree(V); cudaFree(x0); cudaFree(bd); };
+    if (alloc_vec(&V, (long)(ldv * (STAG + 1)) - 1) || alloc_vec(&x0, n) || alloc_vec(&bd, n)) { cleanup(); return 1; }
     double *r = h->cg_r, *w0 = h->cg_q, *w = h->cg_z, *xd = h->cg_x;
     if (to_dev(h, Lf, b, bd)) { cleanup(); return 1; }
-    CU(cudaMemsetAsync(xd, 0, sizeof(double) * n, h->stream));                       // :248
+    CUX(cudaMemsetAsync(xd, 0, sizeof(double) * n, h->stream));                       // :248
     double bb;
     if (dev_dot(h, n, bd, bd, &bb)) { cleanup(); return 1; }
     const double tol = 1.0E-12 * std::sqrt(bb);                                      // :250
@@ -1428,9 +1454,9 @@ int ddpca_mg_gmres(ddpca_mg *h, int prec, const double *b, double *x, long *iter
     while (it < maxiNumb) {                                                          // :261
         int k = (int)(it % STAG);
         if (k == 0) {                                                                // restart, :263-276
-            CU(cudaMemcpyAsync(x0, xd, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+            CUX(cudaMemcpyAsync(x0, xd, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
             launch_level_spmv(h, L, Lf, x0, w0, nullptr, nullptr, nullptr);
-            CU(cudaMemcpyAsync(r, bd, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+            CUX(cudaMemcpyAsync(r, bd, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
             dev_axpby(h, n, -1.0, w0, 1.0, r);
             precondition(h, prec, r, w, nullptr);
             double ww;
@@ -1439,16 +1465,16 @@ int ddpca_mg_gmres(ddpca_mg *h, int prec, const double *b, double *x, long *iter
             dev_axpby(h, n, 1.0 / normR0, w, 0.0, V);
             std::memset(H, 0, sizeof(H)); std::memset(Q, 0, sizeof(Q)); std::memset(R, 0, sizeof(R));
         }
-        launch_level_spmv(h, L, Lf, V + (size_t)k * n, w0, nullptr, nullptr, nullptr);   // :278
+        launch_level_spmv(h, L, Lf, V + (size_t)k * ldv, w0, nullptr, nullptr, nullptr);   // :278
         precondition(h, prec, w0, w, nullptr);                                           // :279-285
-        for (int j = 0; j <= k && !rc; j++) rc = dev_dot(h, n, V + (size_t)j * n, w, &H[j][k]);   // :286
+        for (int j = 0; j <= k && !rc; j++) rc = dev_dot(h, n, V + (size_t)j * ldv, w, &H[j][k]);   // :286
         if (rc) break;
-        for (int j = 0; j <= k; j++) dev_axpby(h, n, -H[j][k], V + (size_t)j * n, 1.0, w);        // :287
+        for (int j = 0; j <= k; j++) dev_axpby(h, n, -H[j][k], V + (size_t)j * ldv, 1.0, w);        // :287
         double qq;
         if ((rc = dev_dot(h, n, w, w, &qq))) break;
         const double nq = std::sqrt(qq);                                                 // :288
         H[k + 1][k] = nq;
-        dev_axpby(h, n, 1.0 / nq, w, 0.0, V + (size_t)(k + 1) * n);                      // :294-296
+        dev_axpby(h, n, 1.0 / nq, w, 0.0, V + (size_t)(k + 1) * ldv);                      // :294-296
         {   // QR of the Hessenberg matrix by Gram-Schmidt, one column per step, :297-316
             double col[STAG + 1];
             for (int i = 0; i <= k + 1; i++) col[i] = H[i][k];
@@ -1470,10 +1496,10 @@ int ddpca_mg_gmres(ddpca_mg *h, int prec, const double *b, double *x, long *iter
             for (int c = j + 1; c <= k; c++) s -= R[j][c] * y[c];
             y[j] = s / R[j][j];
         }
-        CU(cudaMemcpyAsync(xd, x0, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));   // :325
-        for (int j = 0; j <= k; j++) dev_axpby(h, n, y[j], V + (size_t)j * n, 1.0, xd);
+        CUX(cudaMemcpyAsync(xd, x0, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));   // :325
+        for (int j = 0; j <= k; j++) dev_axpby(h, n, y[j], V + (size_t)j * ldv, 1.0, xd);
         launch_level_spmv(h, L, Lf, xd, w0, nullptr, nullptr, nullptr);                  // :326
-        CU(cudaMemcpyAsync(r, bd, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+        CUX(cudaMemcpyAsync(r, bd, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
         dev_axpby(h, n, -1.0, w0, 1.0, r);
         double rr;
         if ((rc = dev_dot(h, n, r, r, &rr))) break;
@@ -1509,13 +1535,13 @@ int ddpca_mg_bicgstab(ddpca_mg *h, int prec, const double *b, double *x, double 
         else k_extract_diag_inv<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
     }
     // work vectors: r, rhat, p, v, s, t, phat, shat, x
-    std::vector<double *> w(6, nullptr);
-    for (auto &p : w) CU(cudaMalloc(&p, sizeof(double) * n));
-    double *r = h->cg_r, *rhat = w[0], *p = h->cg_p, *v = h->cg_q, *s = w[1], *t = w[2], *phat = h->cg_z, *shat = w[3], *xd = h->cg_x;
+    std::vector<double *> w(4, nullptr);
     auto cleanup = [&]() { for (auto q : w) cudaFree(q); };
+    for (auto &p : w) if (alloc_vec(&p, n)) { cleanup(); return 1; }
+    double *r = h->cg_r, *rhat = w[0], *p = h->cg_p, *v = h->cg_q, *s = w[1], *t = w[2], *phat = h->cg_z, *shat = w[3], *xd = h->cg_x;
     if (to_dev(h, Lf, b, r)) { cleanup(); return 1; }
-    CU(cudaMemsetAsync(xd, 0, sizeof(double) * n, h->stream));                                   // :361
-    CU(cudaMemcpyAsync(rhat, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));        // :378
+    CUX(cudaMemsetAsync(xd, 0, sizeof(double) * n, h->stream));                                   // :361
+    CUX(cudaMemcpyAsync(rhat, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));        // :378
     double bb, rr;
     if (dev_dot(h, n, r, r, &bb)) { cleanup(); return 1; }
     const double tol = rel_tol * std::sqrt(bb);                                                  // :363
@@ -1526,7 +1552,7 @@ int ddpca_mg_bicgstab(ddpca_mg *h, int prec, const double *b, double *x, double 
         if (dev_dot(h, n, rhat, r, &rho_new)) { cleanup(); return 1; }                           // :383
         if (std::fabs(rho_new) == 0.0) break;                                                    // :384-387
         if (it == 0) {
-            CU(cudaMemcpyAsync(p, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));   // :389
+            CUX(cudaMemcpyAsync(p, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));   // :389
         } else {
             double beta = (rho_new / rho_old) * (alph / omeg);                                   // :392-393
             dev_axpby(h, n, -omeg, v, 1.0, p);                                                   // p - omeg v
@@ -1537,7 +1563,7 @@ int ddpca_mg_bicgstab(ddpca_mg *h, int prec, const double *b, double *x, double 
         double rv;
         if (dev_dot(h, n, rhat, v, &rv)) { cleanup(); return 1; }
         alph = rho_new / rv;                                                                     // :404
-        CU(cudaMemcpyAsync(s, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+        CUX(cudaMemcpyAsync(s, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
         dev_axpby(h, n, -alph, v, 1.0, s);                                                       // :405
         double ss;
         if (dev_dot(h, n, s, s, &ss)) { cleanup(); return 1; }
@@ -1552,7 +1578,7 @@ int ddpca_mg_bicgstab(ddpca_mg *h, int prec, const double *b, double *x, double 
         omeg = ts / tt;                                                                          // :418
         dev_axpby(h, n, alph, phat, 1.0, xd);
         dev_axpby(h, n, omeg, shat, 1.0, xd);                                                    // :419
-        CU(cudaMemcpyAsync(r, s, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+        CUX(cudaMemcpyAsync(r, s, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
         dev_axpby(h, n, -omeg, t, 1.0, r);                                                       // :420
         if (dev_dot(h, n, r, r, &rr)) { cleanup(); return 1; }
         rho_old = rho_new;

@@ -6,14 +6,17 @@
 //   1. dumps every operator the ADMM loop consumes (SURVEY.md §8a rows a6-a13 and the
 //      macroscopic-problem operators of MCONTACT.h:2540-2573) into a DDPK file,
 //   2. optionally runs the UNTOUCHED reference loop MCONTACT::CONTACT_ANALYSIS
-//      (MCONTACT.h:2493-2723), either to convergence or -- in a forked child that is
-//      stopped after K monitor rows -- for the first K iterations, and dumps its results
-//      (resuMoni.txt rows, resuDisp, inteAuxi, inteLagr, resuCont_*.txt) as golden vectors.
+//      (MCONTACT.h:2493-2723), either to convergence or for exactly the first K iterations
+//      (the loop announces every iteration on std::cout, MCONTACT.h:2505; a stream buffer
+//      installed by the hook counts the announcements and, on the one that opens iteration K,
+//      i.e. after K complete passes of the loop body incl. MONITOR, dumps the state and leaves
+//      the process from the main thread -- a deterministic stop, no second thread),
+//      and dumps its results (resuMoni.txt rows, resuDisp, inteAuxi, inteLagr,
+//      resuCont_*.txt) as golden vectors.
 #ifndef ADMM_HOOK_H
 #define ADMM_HOOK_H
 #include <unistd.h>
-#include <atomic>
-#include <thread>
+#include <functional>
 #include "ddpk_io.h"
 #include "ref_capture.h"
 
@@ -62,6 +65,27 @@ static void DUMP_LDLT(DDPK_WRITER &w, const std::string &name, const DIRE_SOLV &
 	w.i32(name + ".perm", p.data(), p.size());
 }
 
+// Counts the loop's "The <tc>-th iteration" announcements (MCONTACT.h:2505) passing through std::cout and
+// calls `onStop` when announcement number `stopAt` (0-based: the one that opens iteration stopAt) arrives.
+class ITER_STOP_BUF : public std::streambuf {
+public:
+	ITER_STOP_BUF(std::streambuf *next, long stopAt, std::function<void()> onStop) : next_(next), stopAt_(stopAt), onStop_(onStop) {}
+protected:
+	std::streamsize xsputn(const char *s, std::streamsize n) override {
+		if (std::string(s, (size_t)n).find("-th iteration") != std::string::npos) {
+			if (seen_ == stopAt_) onStop_();
+			seen_++;
+		}
+		return next_ ? next_->sputn(s, n) : n;
+	}
+	int overflow(int c) override { return (next_ && c != EOF) ? next_->sputc((char)c) : c; }
+	int sync() override { return next_ ? next_->pubsync() : 0; }
+private:
+	std::streambuf *next_;
+	long stopAt_, seen_ = 0;
+	std::function<void()> onStop_;
+};
+
 inline long ADMM_HOOK(MCONTACT &mc) {
 	typedef Eigen::SparseMatrix<double, Eigen::RowMajor> SPM;
 	const long nb = mc.multGrid.size(), ni = mc.searCont.size();
@@ -85,6 +109,12 @@ inline long ADMM_HOOK(MCONTACT &mc) {
 				for (long l = 0; l < L; l++) w->csr(p + "realProl" + std::to_string(l), mg.mgpi.realProl[l]);
 			}
 			w->vec(p + "consForc", mg.consForc);
+			{   // node coordinates by node id (analytic checks, e.g. examples/TORSION.h:49)
+				std::vector<double> xyz(3 * mg.nodeCoor.size(), 0.0);
+				for (const auto &it : mg.nodeCoor)
+					if (it.first >= 0 && 3 * (size_t)it.first + 2 < xyz.size()) for (int k = 0; k < 3; k++) xyz[3 * it.first + k] = it.second[k];
+				w->f64(p + "nodeCoor", xyz.data(), xyz.size());
+			}
 			// ADDITIONAL_FORCE (MULTIGRID.h:1257-1261) as ONE operator: n_L x 3 n_nodes
 			SPM forcOper = mg.consOper[L] * SPM(mg.prolOper[L].transpose()) * SPM(mg.earlTran.transpose());
 			w->csr(p + "forcOper", forcOper);
@@ -146,6 +176,18 @@ inline long ADMM_HOOK(MCONTACT &mc) {
 	}
 	if (mc.muscSett & 1) js << ",\"globCoup_rows\":" << mc.globCoup.rows();
 	// ---- the untouched reference loop ------------------------------------------------------
+	auto dump_state = [&]() {
+		if (!w) return;
+		for (long v = 0; v < nb; v++) w->vec("ref.resuDisp" + std::to_string(v), mc.resuDisp[v]);
+		for (long ts = 0; ts < ni; ts++) for (long tv = 0; tv < 2; tv++) {
+			std::string q = "ref.if" + std::to_string(ts) + ".s" + std::to_string(tv) + ".";
+			w->vec(q + "inteAuxi", mc.inteAuxi[ts][tv]);
+			w->vec(q + "inteLagr", mc.inteLagr[ts][tv]);
+		}
+		DUMP_TABLE(*w, "ref.resuMoni", READ_TABLE(DIRECTORY("resuMoni.txt")));
+		for (long ts = 0; ts < ni; ts++)   // written by OUTPUT_PRTR in every iteration (MCONTACT.h:2669): the LAST iteration's content
+			if (mc.fricCoef[ts] >= 0.0) DUMP_TABLE(*w, "ref.resuCont" + std::to_string(ts), READ_TABLE(DIRECTORY("resuCont_" + std::to_string(ts) + ".txt")));
+	};
 	if (g_admmOpts.refIters == 0) {
 		double t0 = now_s();
 		(mc.CONTACT_ANALYSIS)();     // parenthesised: not the function-like macro below
@@ -154,50 +196,30 @@ inline long ADMM_HOOK(MCONTACT &mc) {
 		js << ",\"ref_disp_norm\":[";
 		for (long v = 0; v < nb; v++) js << (v ? "," : "") << mc.resuDisp[v].norm();
 		js << "]";
-		if (w) {
-			w->scalar_i64("ref.iterNumbReco", mc.iterNumbReco);
-			for (long v = 0; v < nb; v++) w->vec("ref.resuDisp" + std::to_string(v), mc.resuDisp[v]);
-			for (long ts = 0; ts < ni; ts++) for (long tv = 0; tv < 2; tv++) {
-				std::string q = "ref.if" + std::to_string(ts) + ".s" + std::to_string(tv) + ".";
-				w->vec(q + "inteAuxi", mc.inteAuxi[ts][tv]);
-				w->vec(q + "inteLagr", mc.inteLagr[ts][tv]);
-			}
-			DUMP_TABLE(*w, "ref.resuMoni", READ_TABLE(DIRECTORY("resuMoni.txt")));
-			for (long ts = 0; ts < ni; ts++)
-				if (mc.fricCoef[ts] >= 0.0) DUMP_TABLE(*w, "ref.resuCont" + std::to_string(ts), READ_TABLE(DIRECTORY("resuCont_" + std::to_string(ts) + ".txt")));
-		}
+		if (w) w->scalar_i64("ref.iterNumbReco", mc.iterNumbReco);
+		dump_state();
 	} else if (g_admmOpts.refIters > 0) {
-		// first K iterations only: a watcher thread waits until resuMoni.txt (flushed once per
-		// iteration, MCONTACT.h:2836) holds K rows, dumps them, prints the JSON line and ends the
-		// process; the main thread runs the untouched loop meanwhile.
+		// exactly the first K iterations: state after K passes of the loop body, K resuMoni rows, and the
+		// resuCont_*.txt of iteration K-1.  If the loop converges earlier it simply returns.
 		std::remove(DIRECTORY("resuMoni.txt").c_str());
 		double t0 = now_s();
-		std::atomic<bool> stop(false);
 		std::string head = js.str();
-		std::thread watcher([&]() {
-			const long ncol = nb * 2 + ni * 8 + 2;
-			while (!stop.load()) {
-				usleep(20000);
-				std::vector<std::vector<double>> rows = READ_TABLE(DIRECTORY("resuMoni.txt"));
-				long full = 0;
-				for (auto &r : rows) if ((long)r.size() == ncol) full++;
-				if (full >= g_admmOpts.refIters) {
-					rows.resize(g_admmOpts.refIters);
-					if (w) { DUMP_TABLE(*w, "ref.resuMoni", rows); delete w; }
-					std::ostringstream o;
-					o << std::setprecision(17) << head << ",\"ref_first_iters\":" << rows.size() << ",\"ref_first_iters_s\":" << now_s() - t0
-					  << g_admmOpts.jsonTail << "}";
-					std::printf("%s\n", o.str().c_str());
-					std::fflush(stdout);
-					_exit(0);
-				}
-			}
+		std::streambuf *prev = std::cout.rdbuf();
+		ITER_STOP_BUF stopper(prev, g_admmOpts.refIters, [&]() {
+			if (w) { w->scalar_i64("ref.first_iters", g_admmOpts.refIters); dump_state(); delete w; }
+			std::ostringstream o;
+			o << std::setprecision(17) << head << ",\"ref_first_iters\":" << g_admmOpts.refIters << ",\"ref_first_iters_s\":" << now_s() - t0
+			  << ",\"ref_MULT_MAXI\":" << MULT_MAXI << g_admmOpts.jsonTail << "}";
+			std::printf("%s\n", o.str().c_str());
+			std::fflush(stdout);
+			_exit(0);
 		});
+		std::cout.rdbuf(&stopper);
 		(mc.CONTACT_ANALYSIS)();
-		stop.store(true);
-		watcher.join();
-		js << ",\"ref_iterNumbReco\":" << mc.iterNumbReco;   // converged before K rows
-		if (w) DUMP_TABLE(*w, "ref.resuMoni", READ_TABLE(DIRECTORY("resuMoni.txt")));
+		std::cout.rdbuf(prev);
+		js << ",\"ref_iterNumbReco\":" << mc.iterNumbReco << ",\"ref_admm_s\":" << now_s() - t0;   // converged before K iterations
+		if (w) w->scalar_i64("ref.iterNumbReco", mc.iterNumbReco);
+		dump_state();
 	}
 	js << "}";
 	g_admmOpts.json = js.str();

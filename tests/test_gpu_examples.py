@@ -1,0 +1,113 @@
+"""GPU parity tests on the reference's other three examples (BASELINE.json configs TORSION, CYLINDER, DEHW).
+
+The untouched reference (oracle/_ref/<example>_admm, built from /root/reference by oracle/Makefile) runs on
+this box's host cores at a reduced refinement, dumps every operator MCONTACT::ESTABLISH built plus its own
+results; the device loop (through the C ABI) must reproduce them:
+  * ADMM iteration count exact, displacements / contact pressure within 1e-8 relative,
+  * active contact set and Coulomb status codes (0 open / 1 slide / 2 stick, MCONTACT.h:118,2656-2665) bit-exact.
+What these examples add over BEAM / BLOCK: nodal rotations (full 3x3 prolongation blocks), local refinement
+with hanging nodes (ragged row groups, non-geometric level sizes), frictional interfaces (d = 3 with the cone
+projection), the interface-eliminated coarse problem on a closed ring of subdomains."""
+import numpy as np
+import pytest
+
+import ddpca_b200 as dd
+from tests.helpers import (have_ref_binary, rel, run_ref_cylinder, run_ref_dehw, run_ref_torsion,
+                           torsion_tangential_displacement)
+
+pytestmark = pytest.mark.gpu
+
+
+def _table(d, key):
+    return d[key].reshape(tuple(int(v) for v in d[key + ".shape"]))
+
+
+def _check_state(mc, d, tol_disp=1e-8, tol_aux=1e-8, tol_lagr=1e-6):
+    disp = mc.resuDisp
+    for v in range(mc.nb):
+        assert rel(disp[v], d[f"ref.resuDisp{v}"]) < tol_disp, f"resuDisp[{v}]"
+    aux, lagr = mc.inteAuxi, mc.inteLagr
+    for ts in range(mc.ni):
+        for tv in range(2):
+            assert rel(aux[ts][tv], d[f"ref.if{ts}.s{tv}.inteAuxi"]) < tol_aux, f"inteAuxi[{ts}][{tv}]"
+            assert rel(lagr[ts][tv], d[f"ref.if{ts}.s{tv}.inteLagr"]) < tol_lagr, f"inteLagr[{ts}][{tv}]"
+
+
+@pytest.mark.skipif(not have_ref_binary("torsion_admm"), reason="oracle/_ref/torsion_admm not built")
+def test_torsion_dd_32_subdomains_against_reference_and_analytic_value():
+    """examples/TORSION.h, menu 0 layout (domaNumb 1x8x4: a closed ring of 8 x 4 subdomains, 56 tied
+    interfaces), interface-eliminated coarse problem (the example's default muscSett), globHomo lowered
+    to 2.  The analytic tangential displacement of the loaded end is 1.159111630361142e-06 (TORSION.h:49)."""
+    d, meta = run_ref_torsion(homo=2, musc=2)
+    assert meta["bodies"] == 32 and meta["interfaces"] == 56
+    mc = dd.MCONTACT.from_ddpk(d)
+    mc.CONTACT_ANALYSIS()
+    assert mc.iterNumbReco == meta["ref_iterNumbReco"] == int(d["ref.iterNumbReco"][0])
+    _check_state(mc, d)
+    ut = torsion_tangential_displacement(d, mc.resuDisp)
+    ut_ref = torsion_tangential_displacement(d, [d[f"ref.resuDisp{v}"] for v in range(mc.nb)])
+    assert len(ut) > 0 and np.allclose(ut, ut_ref, rtol=1e-8, atol=0)
+    assert abs(ut.mean() - 1.159111630361142e-06) < 2e-6 * 1.159111630361142e-06   # the FE answer of this mesh, as the reference's
+    mc.close()
+
+
+@pytest.mark.skipif(not have_ref_binary("cylinder_admm"), reason="oracle/_ref/cylinder_admm not built")
+def test_cylinder_hertz_contact_against_reference_run_here():
+    """examples/CYLINDER.h (copyNumb = 1: 8 subdomains, 6 frictionless contact + 4 tied interfaces), local
+    refinement towards the contact bands lowered to 4 levels: hanging nodes, 7 multigrid levels of
+    non-geometric sizes."""
+    d, meta = run_ref_cylinder(copy=1, loca=4, musc=1)
+    mc = dd.MCONTACT.from_ddpk(d)
+    mc.CONTACT_ANALYSIS()
+    assert mc.iterNumbReco == meta["ref_iterNumbReco"]
+    _check_state(mc, d)
+    ncont = 0
+    for ts in range(mc.ni):
+        if mc.fricCoef[ts] == 0.0:
+            g, st = mc.inpoGamm(ts)
+            p_ref = _table(d, f"ref.resuCont{ts}")[:, 0]
+            assert rel(g, p_ref) < 1e-8                      # Hertzian contact pressure
+            assert ((g > 0) == (p_ref > 0)).all()            # active contact set, bit-exact
+            ncont += int((g > 0).sum())
+    assert ncont > 0
+    mc.close()
+
+
+@pytest.mark.skipif(not have_ref_binary("dehw_admm"), reason="oracle/_ref/dehw_admm not built")
+def test_dehw_frictional_contact_first_iterations_against_reference_run_here():
+    """examples/DEHW.h, menu 0 (one worm + one wheel body, four FRICTIONAL tooth-pair interfaces, mu = 0.08,
+    macroscopic problem) at the smallest refinement.  The full run needs hundreds of 12-second reference
+    iterations; the reference is stopped deterministically after K passes of the loop body and the device
+    loop must be in the same state: same monitor rows, same normal pressure / tangential traction, and the
+    same Coulomb status code at every integration point (resuCont_<ts>.txt column 5)."""
+    K = 6
+    d, meta = run_ref_dehw(K)
+    assert meta.get("ref_first_iters") == K
+    mc = dd.MCONTACT.from_ddpk(d)
+    assert any(f > 0.0 for f in mc.fricCoef)
+    rows = []
+    for tc in range(K):
+        row = mc.step(tc)
+        rows.append(row)
+        assert mc.MONITOR(tc, row) == -1
+    ref = _table(d, "ref.resuMoni")
+    assert ref.shape[0] == K
+    rows = np.array(rows)
+    assert np.allclose(rows[:, -1], ref[:, -1], rtol=1e-8, atol=0)          # Ccrit: squared norms of the state
+    assert np.allclose(rows[:, -2], ref[:, -2], rtol=1e-6, atol=0)          # Cvalu: squared increments
+    _check_state(mc, d)
+    seen = set()
+    for ts in range(mc.ni):
+        if mc.fricCoef[ts] <= 0.0:
+            continue
+        g, st = mc.inpoGamm(ts)
+        t = _table(d, f"ref.resuCont{ts}")                                  # gamma_n, traction xyz, status (MCONTACT.h:106-118)
+        assert t.shape[1] == 5
+        assert rel(g[0::3], t[:, 0]) < 1e-8                                 # normal pressure
+        assert ((g[0::3] > 0) == (t[:, 0] > 0)).all()                       # active set, bit-exact
+        assert np.array_equal(st[1::3], t[:, 4].astype(np.int32))           # open / slide / stick, bit-exact
+        tang = np.hypot(g[1::3], g[2::3])                                   # basis vectors are orthonormal
+        assert rel(tang, np.linalg.norm(t[:, 1:4], axis=1)) < 1e-8
+        seen |= set(st[1::3].tolist())
+    assert len(seen) >= 2                                                   # more than one branch of the cone projection occurred
+    mc.close()
