@@ -174,13 +174,27 @@ struct ddpca_mg : Engine {
     int mode = DDPCA_SMOOTH_MC;
     int nlev = 0;
     std::vector<Level> lev;
-    double *Binv = nullptr;  // dense inverse of level 0
-    int n0 = 0;
+    // nsub >= 1 independent subdomain hierarchies held as ONE block-diagonal hierarchy (kernels.cuh, "batched PCG"):
+    // level kernels work on all of them at once, the CG recurrence is per sub
+    int nsub = 1;
+    std::vector<std::vector<int>> sub_off;   // [nlev][nsub+1] first row of each sub on each level (reference numbering)
+    std::vector<int> sub_n;                  // finest-level rows of each sub
+    double *Binv = nullptr;       // dense inverses of the level-0 blocks, sub after sub
+    int n0 = 0;                   // rows of level 0 (all subs)
+    double coarse_bytes = 0;      // algorithmic bytes of one level-0 solve
+    int *sub0_off_d = nullptr;    // [nsub+1] rows of level 0
+    double **binv_ptr_d = nullptr;   // [nsub] dense inverse of each sub's level 0
+    // segmented reductions on the finest level (device numbering)
+    int nseg = 0;
+    SegChunk *seg_d = nullptr;
+    int *sub_chunk_d = nullptr, *sub_n_d = nullptr;
     // finest-level CG vectors (device numbering) + staging in reference numbering
     double *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr, *cg_z = nullptr, *cg_x = nullptr;
     double *stage_a = nullptr, *stage_b = nullptr;  // max-n staging buffers
-    PcgState *st = nullptr;
-    PcgState *st_host = nullptr;  // pinned, ring of kDepth+1
+    PcgState *st = nullptr;       // [nsub]
+    PcgState *st_host = nullptr;  // pinned [nsub]
+    BatchFlags *fl = nullptr;
+    BatchFlags *fl_host = nullptr;   // pinned, ring of kDepth+2
     double *partial[3] = {nullptr, nullptr, nullptr};
     cudaGraphExec_t iter_graph[2] = {nullptr, nullptr};  // per preconditioner
     long iter_graph_nodes[2] = {0, 0};
@@ -192,6 +206,7 @@ struct ddpca_mg : Engine {
     int pending_prec = 1;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double t_solve = 0, t_h2d = 0, t_d2h = 0;
+    const int *done_flag() const { return &fl->done_all; }
 };
 
 #define KL(h, kc, lvl, bytes, ...) \
@@ -395,8 +410,7 @@ static void sweep_bwd(Engine *h, Level &L, int l, double *x, const int *done)
 static void vcycle_dev(ddpca_mg *h, int l, const double *b, double *x, bool zero_x, const int *done)
 {
     if (l == 0) {
-        double bytes = 8.0 * h->n0 * (double)h->n0 + 16.0 * h->n0;
-        KL(h, DDPCA_K_COARSE, 0, bytes, (k_dense_gemv<<<cdiv((long)h->n0 * 32, 256), 256, 0, h->stream>>>(h->n0, h->Binv, b, x, done)));
+        KL(h, DDPCA_K_COARSE, 0, h->coarse_bytes, (k_dense_gemv_batch<<<cdiv((long)h->n0 * 32, 256), 256, 0, h->stream>>>(h->nsub, h->sub0_off_d, h->binv_ptr_d, b, x, done)));
         return;
     }
     Level &L = h->lev[l];
@@ -425,20 +439,20 @@ static void precondition(ddpca_mg *h, int prec, const double *r, double *z, cons
 
 static int vec_grid(const Engine *h, int n) { return std::max(1, std::min(cdiv(n, 256), std::min(kNumPart, h->sms * 8))); }
 
-// body of one CG iteration, MGPIS.h:199-219
+// body of one CG iteration, MGPIS.h:199-219, for every sub of the batch (segmented reductions, kernels.cuh)
 static void enqueue_iteration(ddpca_mg *h, int prec, cudaGraphConditionalHandle cond = 0, int use_cond = 0)
 {
     int Lf = h->nlev - 1;
     Level &L = h->lev[Lf];
-    const int *done = &h->st->done;
-    int n = L.n;
-    int gq = launch_level_spmv(h, L, Lf, h->cg_p, h->cg_q, h->cg_p, h->partial[0], done);  // :200 + p.q
-    int gv = vec_grid(h, n);
-    KL(h, DDPCA_K_VECTOR, Lf, 48.0 * n, (k_update_xr<<<gv, 256, 0, h->stream>>>(n, h->st, h->partial[0], gq, h->cg_p, h->cg_q, h->cg_x, h->cg_r, h->partial[1])));  // :201-203
+    const int *done = h->done_flag();
+    const int n = L.n, ns = h->nseg;
+    launch_level_spmv(h, L, Lf, h->cg_p, h->cg_q, nullptr, nullptr, done);  // :200
+    KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_seg_dot<<<ns, 256, 0, h->stream>>>(h->seg_d, h->cg_p, h->cg_q, h->partial[0], done)));  // p.q of :201
+    KL(h, DDPCA_K_VECTOR, Lf, 48.0 * n, (k_seg_update_xr<<<ns, 256, 0, h->stream>>>(h->seg_d, h->sub_chunk_d, h->st, h->partial[0], h->cg_p, h->cg_q, h->cg_x, h->cg_r, h->partial[1], done)));  // :201-203
     precondition(h, prec, h->cg_r, h->cg_z, done);  // :204-210
-    KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, h->cg_r, h->cg_z, h->partial[2], done)));  // :212
-    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_beta_next<<<1, 64, 0, h->stream>>>(h->st, h->partial[1], h->partial[2], gv, cond, use_cond)));  // :211-213,219,198
-    KL(h, DDPCA_K_VECTOR, Lf, 24.0 * n, (k_update_p<<<gv, 256, 0, h->stream>>>(n, h->st, h->cg_z, h->cg_p)));            // :214
+    KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_seg_dot<<<ns, 256, 0, h->stream>>>(h->seg_d, h->cg_r, h->cg_z, h->partial[2], done)));  // :212
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_seg_beta_next<<<1, 1024, 0, h->stream>>>(h->nsub, h->st, h->sub_chunk_d, h->partial[1], h->partial[2], h->fl, cond, use_cond)));  // :211-213,219,198
+    KL(h, DDPCA_K_VECTOR, Lf, 24.0 * n, (k_seg_update_p<<<ns, 256, 0, h->stream>>>(h->seg_d, h->st, h->cg_z, h->cg_p, done)));   // :214
 }
 
 // set-up of a solve after r = b, x = 0 (MGPIS.h:174-197): tolerance, first preconditioner application, delta_new
@@ -446,13 +460,13 @@ static void enqueue_setup(ddpca_mg *h, int prec, cudaGraphConditionalHandle cond
 {
     int Lf = h->nlev - 1;
     int n = h->lev[Lf].n;
-    const int *done = &h->st->done;
-    int gv = vec_grid(h, n);
-    KL(h, DDPCA_K_VECTOR, Lf, 8.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, h->cg_r, h->cg_r, h->partial[0], nullptr)));
-    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_init<<<1, 32, 0, h->stream>>>(h->st, h->partial[0], gv)));              // :174-175
-    precondition(h, prec, h->cg_r, h->cg_p, done);                                                              // :191-196
-    KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_dot<<<gv, 256, 0, h->stream>>>(n, h->cg_r, h->cg_p, h->partial[2], done)));
-    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_delta0<<<1, 32, 0, h->stream>>>(h->st, h->partial[2], gv, cond, use_cond)));  // :197
+    const int *done = h->done_flag();
+    const int ns = h->nseg;
+    KL(h, DDPCA_K_VECTOR, Lf, 8.0 * n, (k_seg_dot<<<ns, 256, 0, h->stream>>>(h->seg_d, h->cg_r, h->cg_r, h->partial[0], nullptr)));
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_seg_init<<<1, 1024, 0, h->stream>>>(h->nsub, h->st, h->sub_chunk_d, h->partial[0], h->fl)));   // :174-175
+    precondition(h, prec, h->cg_r, h->cg_p, done);                                                                                    // :191-196
+    KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_seg_dot<<<ns, 256, 0, h->stream>>>(h->seg_d, h->cg_r, h->cg_p, h->partial[2], done)));
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_seg_delta0<<<1, 1024, 0, h->stream>>>(h->nsub, h->st, h->sub_chunk_d, h->partial[2], h->fl, cond, use_cond)));  // :197
 }
 
 // One graph per solve: [set-up] -> WHILE(cond){ CG iteration }.  The loop condition of MGPIS.h:198
@@ -535,21 +549,26 @@ static int build_iter_graph(ddpca_mg *h, int prec)
     return 0;
 }
 
-// wait for a solve enqueued by pcg_device and read its scalars back
+// wait for a solve enqueued by pcg_device and read its scalars back (iters / resid / tol_abs: sub 0, or the
+// largest iteration count / residual of a batch; per-sub values through ddpca_mg_batch_result)
 static int pcg_finish(ddpca_mg *h, long *iters, double *resid, double *tol_abs)
 {
     CU(cudaStreamSynchronize(h->stream));
     if (!h->launch_err.empty()) { std::string m = h->launch_err; h->launch_err.clear(); cudaGetLastError(); return fail(m); }
     if (h->profile) h->prof_collect();
-    if (h->pending_while) h->launches += h->solve_init_nodes[h->pending_prec] + (long)h->st_host[0].it * h->solve_iter_nodes[h->pending_prec];
-    if (iters) *iters = (long)h->st_host[0].it;
-    if (resid) *resid = std::sqrt(h->st_host[0].rr);
+    if (h->pending_while) h->launches += h->solve_init_nodes[h->pending_prec] + (long)h->fl_host[0].it_max * h->solve_iter_nodes[h->pending_prec];
+    long it = 0;
+    double rr = 0.0;
+    for (int s = 0; s < h->nsub; s++) { it = std::max(it, (long)h->st_host[s].it); rr = std::max(rr, h->st_host[s].rr); }
+    if (iters) *iters = it;
+    if (resid) *resid = std::sqrt(rr);
     if (tol_abs) *tol_abs = h->st_host[0].tol;
     CU(cudaGetLastError());
     return 0;
 }
 
-// CG_SOLV on device vectors: b_ref/x_ref in REFERENCE numbering, resident on the device
+// CG_SOLV on device vectors: b_ref/x_ref in REFERENCE numbering (the subs' vectors one after the other),
+// resident on the device.  maxit <= 0: the rows of each sub (MGPIS.h:178).
 static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref, double rel_tol, long maxit,
                       long *iters, double *resid, double *tol_abs, bool no_wait = false)
 {
@@ -557,7 +576,6 @@ static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref,
     int Lf = h->nlev - 1;
     Level &L = h->lev[Lf];
     int n = L.n;
-    const int *done = &h->st->done;
     if (prec == 0 && !L.dinv) {
         CU(cudaMalloc(&L.dinv, sizeof(double) * n));
         if (L.v2) k_extract_diag_inv2<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view2(), L.dinv);
@@ -572,44 +590,47 @@ static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref,
     KL(h, DDPCA_K_VECTOR, Lf, 20.0 * n, (k_gather<<<cdiv(n, 256), 256, 0, h->stream>>>(n, L.perm, b_ref, h->cg_r)));
     CU(cudaMemsetAsync(h->cg_x, 0, sizeof(double) * n, h->stream));
     CU(cudaMemsetAsync(h->cg_p, 0, sizeof(double) * n, h->stream));
-    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_s_params<<<1, 1, 0, h->stream>>>(h->st, rel_tol, (long long)maxit)));
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_seg_params<<<cdiv(h->nsub, 128), 128, 0, h->stream>>>(h->nsub, h->st, h->sub_n_d, rel_tol, (long long)maxit)));
     if (use_while) {
         CU(cudaGraphLaunch(h->solve_graph[prec], h->stream));
     } else {
-    enqueue_setup(h, prec);
-    // main loop: enqueue iterations ahead, poll `done` with a lag of kDepth iterations
-    cudaEvent_t evs[kDepth + 1];
-    for (int k = 0; k <= kDepth; k++) CU(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
-    long issued = 0;
-    bool finished = false;
-    // state after setup (covers zero RHS: done already set, MGPIS.h:198 never entered)
-    CU(cudaMemcpyAsync(&h->st_host[0], h->st, sizeof(PcgState), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaEventRecord(evs[0], h->stream));
-    CU(cudaEventSynchronize(evs[0]));
-    finished = h->st_host[0].done != 0;
-    while (!finished) {
-        int slot = (int)(issued % (kDepth + 1));
-        if (h->profile) {
-            enqueue_iteration(h, prec);
-        } else {
-            CU(cudaGraphLaunch(h->iter_graph[prec], h->stream));
-            h->launches += h->iter_graph_nodes[prec];
+        enqueue_setup(h, prec);
+        // main loop: enqueue iterations ahead, poll the batch's done flag with a lag of `depth` iterations.  Under the
+        // per-launch profiler the lag is zero, so that no early-exiting launch is timed (and booked with full bytes).
+        const int depth = h->profile ? 0 : kDepth;
+        cudaEvent_t evs[kDepth + 1];
+        for (int k = 0; k <= kDepth; k++) CU(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+        long issued = 0;
+        bool finished = false;
+        // state after setup (covers zero RHS: done already set, MGPIS.h:198 never entered)
+        CU(cudaMemcpyAsync(&h->fl_host[0], h->fl, sizeof(BatchFlags), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventRecord(evs[0], h->stream));
+        CU(cudaEventSynchronize(evs[0]));
+        finished = h->fl_host[0].done_all != 0;
+        while (!finished) {
+            int slot = (int)(issued % (kDepth + 1));
+            if (h->profile) {
+                enqueue_iteration(h, prec);
+            } else {
+                CU(cudaGraphLaunch(h->iter_graph[prec], h->stream));
+                h->launches += h->iter_graph_nodes[prec];
+            }
+            CU(cudaMemcpyAsync(&h->fl_host[slot], h->fl, sizeof(BatchFlags), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaEventRecord(evs[slot], h->stream));
+            issued++;
+            if (issued >= depth) {
+                int old = (int)((issued - std::max(depth, 1)) % (kDepth + 1));
+                CU(cudaEventSynchronize(evs[old]));
+                if (h->fl_host[old].done_all) finished = true;
+            }
+            if (h->profile && (issued % 8) == 0) h->prof_collect();
         }
-        CU(cudaMemcpyAsync(&h->st_host[slot], h->st, sizeof(PcgState), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaEventRecord(evs[slot], h->stream));
-        issued++;
-        if (issued >= kDepth) {
-            int old = (int)((issued - kDepth) % (kDepth + 1));
-            CU(cudaEventSynchronize(evs[old]));
-            if (h->st_host[old].done) finished = true;
-        }
-        if (h->profile && (issued % 8) == 0) h->prof_collect();
-    }
-    for (int k = 0; k <= kDepth; k++) cudaEventDestroy(evs[k]);
+        for (int k = 0; k <= kDepth; k++) cudaEventDestroy(evs[k]);
     }
     // x (device numbering) -> reference numbering
     KL(h, DDPCA_K_VECTOR, Lf, 20.0 * n, (k_scatter<<<cdiv(n, 256), 256, 0, h->stream>>>(n, L.perm, h->cg_x, x_ref)));
-    CU(cudaMemcpyAsync(&h->st_host[0], h->st, sizeof(PcgState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->st_host, h->st, sizeof(PcgState) * h->nsub, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&h->fl_host[0], h->fl, sizeof(BatchFlags), cudaMemcpyDeviceToHost, h->stream));
     h->pending_while = use_while;
     h->pending_prec = prec;
     if (no_wait) return 0;   // the caller overlaps several solves and calls pcg_finish() later
@@ -890,53 +911,51 @@ static void free_level(Level &L)
     L.x = L.b = L.p1 = L.r = L.dinv = nullptr;
 }
 
-// Dense inverse of an SPD operator given as device CSR: in-place Gauss-Jordan + symmetrisation
-// (set-up only).  *Binv is allocated here.
-// in-place Gauss-Jordan inversion + symmetrisation of a dense SPD matrix already on the device
+// In-place inversion + symmetrisation of a dense SPD matrix already on the device (set-up only):
+// blocked Gauss-Jordan, three launches per 64-wide panel (kernels.cuh).
 static int dense_invert_inplace(cudaStream_t st, int n, double *B)
 {
-    double *rowk, *colk;
-    CU(cudaMalloc(&rowk, sizeof(double) * n));
-    CU(cudaMalloc(&colk, sizeof(double) * n));
-    dim3 g2(cdiv(n, 256), n);
-    for (int k = 0; k < n; k++) {
-        k_gj_pivot<<<cdiv(n, 256), 256, 0, st>>>(n, k, B, rowk, colk);
-        k_gj_update<<<g2, 256, 0, st>>>(n, k, B, rowk, colk);
+    static std::atomic<unsigned long long> attr_set{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    const size_t smem = sizeof(double) * 2 * kGjB * (kGjB + 1);
+    if (!(attr_set.load() & bit)) {
+        CU(cudaFuncSetAttribute(k_bgj_panels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(k_bgj_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set.fetch_or(bit);
     }
+    double *Dinv = nullptr, *C = nullptr, *R = nullptr;
+    auto cleanup = [&]() { cudaFree(Dinv); cudaFree(C); cudaFree(R); };
+    CUX(cudaMalloc(&Dinv, sizeof(double) * kGjB * kGjB));
+    CUX(cudaMalloc(&C, sizeof(double) * (size_t)n * kGjB));
+    CUX(cudaMalloc(&R, sizeof(double) * (size_t)n * kGjB));
+    const int nt = cdiv(n, kGjB);
+    for (int k0 = 0; k0 < n; k0 += kGjB) {
+        const int nb = std::min(kGjB, n - k0);
+        k_bgj_diag<<<1, 1024, 0, st>>>(n, k0, nb, B, Dinv);
+        k_bgj_panels<<<nt, 256, smem, st>>>(n, k0, nb, B, Dinv, C, R);
+        k_bgj_update<<<dim3(nt, nt), 256, smem, st>>>(n, k0, nb, B, Dinv, C, R);
+    }
+    dim3 g2(cdiv(n, 256), n);
     k_symmetrize<<<g2, 256, 0, st>>>(n, B);
-    CU(cudaStreamSynchronize(st));
-    CU(cudaGetLastError());
-    cudaFree(rowk);
-    cudaFree(colk);
+    CUX(cudaStreamSynchronize(st));
+    CUX(cudaGetLastError());
+    cleanup();
     return 0;
+}
+// Dense inverse of the diagonal block [r0, r0+n) of an SPD operator given as device CSR, written to Bblk (n x n)
+static int dense_spd_inverse_block(cudaStream_t st, const DevCsr &A, int r0, int n, double *Bblk)
+{
+    CU(cudaMemsetAsync(Bblk, 0, sizeof(double) * (size_t)n * n, st));
+    k_csr_to_dense<<<cdiv(n, 128), 128, 0, st>>>(A.view(), r0, n, Bblk);
+    return dense_invert_inplace(st, n, Bblk);
 }
 static int dense_spd_inverse(cudaStream_t st, const DevCsr &A, double **Binv)
 {
     int n = A.rows;
     CU(cudaMalloc(Binv, sizeof(double) * (size_t)n * n));
-    CU(cudaMemsetAsync(*Binv, 0, sizeof(double) * (size_t)n * n, st));
-    double *rowk, *colk;
-    CU(cudaMalloc(&rowk, sizeof(double) * n));
-    CU(cudaMalloc(&colk, sizeof(double) * n));
-    k_csr_to_dense<<<cdiv(n, 128), 128, 0, st>>>(A.view(), n, *Binv);
-    dim3 g2(cdiv(n, 256), n);
-    for (int k = 0; k < n; k++) {
-        k_gj_pivot<<<cdiv(n, 256), 256, 0, st>>>(n, k, *Binv, rowk, colk);
-        k_gj_update<<<g2, 256, 0, st>>>(n, k, *Binv, rowk, colk);
-    }
-    k_symmetrize<<<g2, 256, 0, st>>>(n, *Binv);
-    CU(cudaStreamSynchronize(st));
-    CU(cudaGetLastError());
-    cudaFree(rowk);
-    cudaFree(colk);
-    return 0;
-}
-static int invert_level0(ddpca_mg *h)
-{
-    Level &L0 = h->lev[0];
-    h->n0 = L0.n;
-    if (L0.n > 32768) return fail("level 0 has " + std::to_string(L0.n) + " rows; the dense direct solver supports <= 32768");
-    return dense_spd_inverse(h->stream, L0.A, &h->Binv);
+    return dense_spd_inverse_block(st, A, 0, n, *Binv);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1176,8 +1195,10 @@ int ddpca_mg_destroy(ddpca_mg *h)
     cudaFree(h->Binv);
     cudaFree(h->cg_r); cudaFree(h->cg_p); cudaFree(h->cg_q); cudaFree(h->cg_z); cudaFree(h->cg_x);
     cudaFree(h->stage_a); cudaFree(h->stage_b);
-    cudaFree(h->st);
+    cudaFree(h->st); cudaFree(h->fl);
+    cudaFree(h->sub0_off_d); cudaFree(h->binv_ptr_d); cudaFree(h->seg_d); cudaFree(h->sub_chunk_d); cudaFree(h->sub_n_d);
     if (h->st_host) cudaFreeHost(h->st_host);
+    if (h->fl_host) cudaFreeHost(h->fl_host);
     for (int k = 0; k < 3; k++) cudaFree(h->partial[k]);
     for (int k = 0; k < 2; k++) if (h->iter_graph[k]) cudaGraphExecDestroy(h->iter_graph[k]);
     for (int k = 0; k < 2; k++) if (h->solve_graph[k]) cudaGraphExecDestroy(h->solve_graph[k]);
@@ -1187,12 +1208,41 @@ int ddpca_mg_destroy(ddpca_mg *h)
     return 0;
 }
 
-int ddpca_mg_create(int device, int nlevels, const int *n, const int *const *rowptr, const int *const *colidx,
-                    const double *const *val, const int *const *P_rowptr, const int *const *P_colidx,
-                    const double *const *P_val, int smoother_mode, ddpca_mg **out)
+// block-diagonal concatenation of the subs' operators of one level (rows r[s], columns c[s])
+static int concat_block_diag(int nsub, const int *r, const int *c, const int *const *rp, const int *const *ci, const double *const *v,
+                             CsrHost &out)
 {
-    if (!out || nlevels < 1 || nlevels > 16 || !n || !rowptr || !colidx || !val) return fail("ddpca_mg_create: bad argument");
+    long rows = 0, cols = 0, nnz = 0;
+    for (int s = 0; s < nsub; s++) { rows += r[s]; cols += c[s]; nnz += rp[s][r[s]]; }
+    if (rows > 0x7ffffff0L || cols > 0x7ffffff0L || nnz > 0x7ffffff0L) return fail("batch too large for 32-bit indices: split it into several batches");
+    out.rows = (int)rows; out.cols = (int)cols;
+    out.rp.resize(rows + 1);
+    out.ci.resize(nnz);
+    out.v.resize(nnz);
+    long r0 = 0, c0 = 0, p0 = 0;
+    out.rp[0] = 0;
+    for (int s = 0; s < nsub; s++) {
+        const int nr = r[s];
+        const long nz = rp[s][nr];
+        for (int i = 0; i < nr; i++) out.rp[r0 + i + 1] = (int)(p0 + rp[s][i + 1]);
+        const int *cs = ci[s];
+        const double *vs = v[s];
+        const int coff = (int)c0;
+#pragma omp parallel for schedule(static)
+        for (long p = 0; p < nz; p++) { out.ci[p0 + p] = cs[p] + coff; out.v[p0 + p] = vs[p]; }
+        r0 += nr; c0 += c[s]; p0 += nz;
+    }
+    return 0;
+}
+
+// nsub hierarchies of `nlevels` levels each; every array is indexed [s * nlevels + l] (prolongations [s * (nlevels-1) + l])
+static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const int *const *rowptr, const int *const *colidx,
+                          const double *const *val, const int *const *P_rowptr, const int *const *P_colidx,
+                          const double *const *P_val, int smoother_mode, ddpca_mg **out)
+{
+    if (!out || nsub < 1 || nlevels < 1 || nlevels > 16 || !n || !rowptr || !colidx || !val) return fail("ddpca_mg_create: bad argument");
     if (smoother_mode != DDPCA_SMOOTH_LEX && smoother_mode != DDPCA_SMOOTH_MC) return fail("unknown smoother mode");
+    if (nlevels > 1 && (!P_rowptr || !P_colidx || !P_val)) return fail("prolongation operators missing");
     int ndev = ddpca_device_count();
     if (ndev == 0) return fail("no CUDA device: libddpca_b200 has no CPU fallback");
     if (device < 0 || device >= ndev) return fail("device index out of range");
@@ -1201,31 +1251,60 @@ int ddpca_mg_create(int device, int nlevels, const int *n, const int *const *row
     h->device = device;
     h->mode = smoother_mode;
     h->nlev = nlevels;
+    h->nsub = nsub;
     h->lev.resize(nlevels);
+    h->sub_off.assign(nlevels, std::vector<int>(nsub + 1, 0));
     cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
 #define FAILC(expr) do { if (expr) { ddpca_mg_destroy(h); return 1; } } while (0)
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); ddpca_mg_destroy(h); return 1; } } while (0)
     CUC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     for (int k = 0; k < 4; k++) CUC(cudaEventCreate(&h->ev[k]));
+    for (int l = 0; l < nlevels; l++) {
+        long acc = 0;
+        for (int s = 0; s < nsub; s++) { h->sub_off[l][s] = (int)acc; acc += n[s * nlevels + l]; }
+        if (acc > 0x7ffffff0L) { ddpca_mg_destroy(h); return fail("batch too large for 32-bit indices: split it into several batches"); }
+        h->sub_off[l][nsub] = (int)acc;
+    }
     int nmax = 0;
+    std::vector<int> rs(nsub), cs(nsub);
+    std::vector<const int *> prp(nsub), pci(nsub);
+    std::vector<const double *> pv(nsub);
     for (int l = 0; l < nlevels; l++) {
         Level &L = h->lev[l];
-        nmax = std::max(nmax, n[l]);
+        const int ntot = h->sub_off[l][nsub];
+        nmax = std::max(nmax, ntot);
         int mode = (l == 0) ? -1 : smoother_mode;   // level 0 is only ever solved directly
         bool coarse_only = (l == 0 && nlevels > 1);
-        if (setup_level(L, n[l], rowptr[l], colidx[l], val[l], mode, /*keep_csr=*/l == 0, /*group_layout=*/!coarse_only)) {
+        CsrHost cat;
+        const int *rp = rowptr[l], *ci = colidx[l];
+        const double *vv = val[l];
+        if (nsub > 1) {
+            for (int s = 0; s < nsub; s++) { rs[s] = n[s * nlevels + l]; prp[s] = rowptr[s * nlevels + l]; pci[s] = colidx[s * nlevels + l]; pv[s] = val[s * nlevels + l]; }
+            FAILC(concat_block_diag(nsub, rs.data(), rs.data(), prp.data(), pci.data(), pv.data(), cat));
+            rp = cat.rp.data(); ci = cat.ci.data(); vv = cat.v.data();
+        }
+        if (setup_level(L, ntot, rp, ci, vv, mode, /*keep_csr=*/l == 0, /*group_layout=*/!coarse_only)) {
             g_err = "level " + std::to_string(l) + ": " + g_err;
             ddpca_mg_destroy(h);
             return 1;
         }
         if (l >= 1) {
-            if (!P_rowptr || !P_colidx || !P_val) { g_err = "prolongation operators missing"; ddpca_mg_destroy(h); return 1; }
-            CsrHost Pp, Rp;
+            CsrHost Pcat, Pp, Rp;
+            const int *prp0 = P_rowptr[l - 1], *pci0 = P_colidx[l - 1];
+            const double *pv0 = P_val[l - 1];
+            if (nsub > 1) {
+                for (int s = 0; s < nsub; s++) {
+                    rs[s] = n[s * nlevels + l]; cs[s] = n[s * nlevels + l - 1];
+                    prp[s] = P_rowptr[s * (nlevels - 1) + l - 1]; pci[s] = P_colidx[s * (nlevels - 1) + l - 1]; pv[s] = P_val[s * (nlevels - 1) + l - 1];
+                }
+                FAILC(concat_block_diag(nsub, rs.data(), cs.data(), prp.data(), pci.data(), pv.data(), Pcat));
+                prp0 = Pcat.rp.data(); pci0 = Pcat.ci.data(); pv0 = Pcat.v.data();
+            }
             // realProl[l-1]: n_l x n_{l-1}; rows follow level l's permutation, columns level l-1's
-            permute_csr(n[l], n[l - 1], P_rowptr[l - 1], P_colidx[l - 1], P_val[l - 1], L.plan.perm, h->lev[l - 1].plan.iperm, Pp);
+            permute_csr(ntot, h->sub_off[l - 1][nsub], prp0, pci0, pv0, L.plan.perm, h->lev[l - 1].plan.iperm, Pp);
             // the reference stores realProl with explicit zeros (a 3x3 block per node pair, diagonal only
-            // non-zero): x + 0 * y == x, so they are dropped -- two thirds of the transfer operators' bytes
+            // non-zero unless the nodes carry rotations): x + 0 * y == x, so they are dropped
             drop_zeros_csr(Pp);
             transpose_csr(Pp, Rp);
             FAILC(upload_csr(Pp, L.P));
@@ -1234,17 +1313,94 @@ int ddpca_mg_create(int device, int nlevels, const int *n, const int *const *row
     }
     FAILC(alloc_vec(&h->cg_r, nmax) || alloc_vec(&h->cg_p, nmax) || alloc_vec(&h->cg_q, nmax) || alloc_vec(&h->cg_z, nmax) ||
           alloc_vec(&h->cg_x, nmax) || alloc_vec(&h->stage_a, nmax) || alloc_vec(&h->stage_b, nmax));
-    CUC(cudaMalloc(&h->st, sizeof(PcgState)));
-    CUC(cudaMemset(h->st, 0, sizeof(PcgState)));
-    CUC(cudaMallocHost(&h->st_host, sizeof(PcgState) * (kDepth + 2)));
-    for (int k = 0; k < 3; k++) CUC(cudaMalloc(&h->partial[k], sizeof(double) * kNumPart));
-    FAILC(invert_level0(h));
+    CUC(cudaMalloc(&h->st, sizeof(PcgState) * nsub));
+    CUC(cudaMemset(h->st, 0, sizeof(PcgState) * nsub));
+    CUC(cudaMalloc(&h->fl, sizeof(BatchFlags)));
+    CUC(cudaMemset(h->fl, 0, sizeof(BatchFlags)));
+    CUC(cudaMallocHost(&h->st_host, sizeof(PcgState) * nsub));
+    CUC(cudaMallocHost(&h->fl_host, sizeof(BatchFlags) * (kDepth + 2)));
+    std::memset(h->st_host, 0, sizeof(PcgState) * nsub);
+    std::memset(h->fl_host, 0, sizeof(BatchFlags) * (kDepth + 2));
+    {   // ---- segmented-reduction tables of the finest level: rows of one sub are contiguous inside a stage ----
+        const int Lf = nlevels - 1;
+        const Level &L = h->lev[Lf];
+        const std::vector<int> &off = h->sub_off[Lf];
+        h->sub_n.resize(nsub);
+        for (int s = 0; s < nsub; s++) h->sub_n[s] = off[s + 1] - off[s];
+        std::vector<std::vector<SegChunk>> per_sub(nsub);
+        int cur = -1, start = 0, sub = 0;
+        auto flush = [&](int end) {
+            for (int r0 = start; r0 < end; r0 += kSegRows) per_sub[cur].push_back(SegChunk{r0, std::min(kSegRows, end - r0), cur, 0});
+        };
+        for (int i = 0; i < L.n; i++) {
+            const int old = L.plan.perm[i];
+            if (nsub > 1) { while (old >= off[sub + 1]) sub++; while (old < off[sub]) sub--; } else sub = 0;
+            if (sub != cur) { if (cur >= 0) flush(i); cur = sub; start = i; }
+        }
+        if (cur >= 0) flush(L.n);
+        std::vector<SegChunk> seg;
+        std::vector<int> sub_chunk(nsub + 1, 0);
+        for (int s = 0; s < nsub; s++) { sub_chunk[s] = (int)seg.size(); seg.insert(seg.end(), per_sub[s].begin(), per_sub[s].end()); }
+        sub_chunk[nsub] = (int)seg.size();
+        h->nseg = (int)seg.size();
+        if (h->nseg == 0) { seg.push_back(SegChunk{0, 0, 0, 0}); }
+        FAILC(upload_vec(seg, &h->seg_d) || upload_vec(sub_chunk, &h->sub_chunk_d) || upload_vec(h->sub_n, &h->sub_n_d));
+        for (int k = 0; k < 3; k++) {
+            CUC(cudaMalloc(&h->partial[k], sizeof(double) * std::max(h->nseg, kNumPart)));
+            CUC(cudaMemset(h->partial[k], 0, sizeof(double) * std::max(h->nseg, kNumPart)));
+        }
+    }
+    {   // ---- level 0: dense inverse of every sub's block (the reference re-factorises in every CG_SOLV call, MGPIS.h:185) ----
+        Level &L0 = h->lev[0];
+        h->n0 = L0.n;
+        std::vector<long long> boff(nsub);
+        long long tot = 0;
+        for (int s = 0; s < nsub; s++) {
+            const long long ns = h->sub_off[0][s + 1] - h->sub_off[0][s];
+            if (ns > 32768) { ddpca_mg_destroy(h); return fail("level 0 has " + std::to_string(ns) + " rows; the dense direct solver supports <= 32768"); }
+            boff[s] = tot;
+            tot += ns * ns + (ns & 1);   // keep every block 16-byte aligned
+            h->coarse_bytes += 8.0 * ns * (double)ns + 16.0 * ns;
+        }
+        CUC(cudaMalloc(&h->Binv, sizeof(double) * (size_t)std::max<long long>(tot, 1)));
+        for (int s = 0; s < nsub; s++)
+            FAILC(dense_spd_inverse_block(h->stream, L0.A, h->sub_off[0][s], h->sub_off[0][s + 1] - h->sub_off[0][s], h->Binv + boff[s]));
+        std::vector<double *> bptr(nsub);
+        for (int s = 0; s < nsub; s++) bptr[s] = h->Binv + boff[s];
+        FAILC(upload_vec(h->sub_off[0], &h->sub0_off_d) || upload_vec(bptr, &h->binv_ptr_d));
+    }
     // capture + instantiate the V-cycle-preconditioned solve graph now (set-up time), not in the first solve
     build_solve_graph(h, 1);
     if (h->while_state[1] != 1) FAILC(build_iter_graph(h, 1));
 #undef FAILC
 #undef CUC
     *out = h;
+    return 0;
+}
+
+int ddpca_mg_create(int device, int nlevels, const int *n, const int *const *rowptr, const int *const *colidx,
+                    const double *const *val, const int *const *P_rowptr, const int *const *P_colidx,
+                    const double *const *P_val, int smoother_mode, ddpca_mg **out)
+{
+    return mg_create_impl(device, 1, nlevels, n, rowptr, colidx, val, P_rowptr, P_colidx, P_val, smoother_mode, out);
+}
+
+int ddpca_mg_create_batch(int device, int nsub, int nlevels, const int *n, const int *const *rowptr, const int *const *colidx,
+                          const double *const *val, const int *const *P_rowptr, const int *const *P_colidx,
+                          const double *const *P_val, int smoother_mode, ddpca_mg **out)
+{
+    return mg_create_impl(device, nsub, nlevels, n, rowptr, colidx, val, P_rowptr, P_colidx, P_val, smoother_mode, out);
+}
+
+int ddpca_mg_batch_result(const ddpca_mg *h, int *nsub, long *iters, double *resid, double *tol_abs)
+{
+    if (!h) return fail("null handle");
+    if (nsub) *nsub = h->nsub;
+    for (int s = 0; s < h->nsub; s++) {
+        if (iters) iters[s] = (long)h->st_host[s].it;
+        if (resid) resid[s] = std::sqrt(h->st_host[s].rr);
+        if (tol_abs) tol_abs[s] = h->st_host[s].tol;
+    }
     return 0;
 }
 

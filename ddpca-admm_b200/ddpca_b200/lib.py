@@ -21,7 +21,7 @@ def library_path() -> str:
 EXPORTS = [
     "ddpca_last_error", "ddpca_abi_version", "ddpca_device_count",
     "ddpca_plan_create", "ddpca_plan_sizes", "ddpca_plan_get", "ddpca_plan_destroy",
-    "ddpca_mg_create", "ddpca_mg_destroy", "ddpca_mg_pcg", "ddpca_mg_pcg_dev",
+    "ddpca_mg_create", "ddpca_mg_create_batch", "ddpca_mg_batch_result", "ddpca_mg_destroy", "ddpca_mg_pcg", "ddpca_mg_pcg_dev",
     "ddpca_mg_vcycle", "ddpca_mg_spmv", "ddpca_mg_restrict", "ddpca_mg_prolong_add",
     "ddpca_mg_coarse_solve", "ddpca_mg_mult_solv", "ddpca_mg_bicgstab", "ddpca_mg_gmres",
     "ddpca_mg_level_info", "ddpca_mg_launch_count", "ddpca_mg_set_stream",
@@ -31,7 +31,8 @@ EXPORTS = [
     "ddpca_admm_set_side_op", "ddpca_admm_set_side_solver", "ddpca_admm_set_macro", "ddpca_admm_set_macro_mg", "ddpca_admm_set_body_globtran_d1", "ddpca_admm_set_macro1", "ddpca_admm_finalize",
     "ddpca_admm_step", "ddpca_admm_row_length", "ddpca_admm_get_disp", "ddpca_admm_get_side", "ddpca_admm_get_gamma",
     "ddpca_admm_launch_count", "ddpca_admm_destroy", "ddpca_admm_set_partition", "ddpca_admm_exchange_sizes",
-    "ddpca_admm_set_exchange", "ddpca_admm_set_stream", "ddpca_admm_phase", "ddpca_admm_monitor_row",
+    "ddpca_admm_set_exchange", "ddpca_admm_exchange_peers", "ddpca_admm_set_stream", "ddpca_admm_phase", "ddpca_admm_monitor_row",
+    "ddpca_admm_set_smoother", "ddpca_admm_reset", "ddpca_admm_set_consforc", "ddpca_admm_body_iters",
 ]
 
 

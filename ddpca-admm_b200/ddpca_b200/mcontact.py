@@ -13,7 +13,7 @@ import numpy as np
 
 from . import ddpk
 from .lib import DdpcaError, check, load_library
-from .mgpis import MGPIS, SMOOTH_MC, _pd, _pi
+from .mgpis import MGPIS, SMOOTH_MC, _pd, _pi, hierarchy_pointers
 
 OPS = ["systTran", "systTran_pena", "inteMass", "inteMass_pena", "inpoLagr", "inteInpo", "pemaInpo_r",
        "globTran", "globTran_pena", "globTran_D", "globTran_1"]
@@ -139,6 +139,8 @@ class MCONTACT:
         h = C.c_void_p()
         check(lib.ddpca_admm_create(C.c_int(device), C.c_int(nb), C.c_int(ni), C.c_int(self.muscSett), C.byref(h)))
         self._h = h
+        check(lib.ddpca_admm_set_smoother(h, C.c_int(smoother)))
+        keep = []   # hierarchy arrays must stay alive until ddpca_admm_finalize
         if body_rank is not None:
             br = (C.c_int * nb)(*self.body_rank)
             check(lib.ddpca_admm_set_partition(h, br, C.c_int(rank)))
@@ -151,13 +153,13 @@ class MCONTACT:
             L = int(d[p + "maxiLeve"][0])
             A = [ddpk.get_csr(d, p + f"consStif{l}") for l in range(L + 1)]
             P = [ddpk.get_csr(d, p + f"realProl{l}") for l in range(L)]
-            mg = MGPIS.from_hierarchy(A, P, device=device, smoother=smoother)
+            args = hierarchy_pointers([(A, P)])
+            keep.append((A, P, args))
             F = ddpk.get_csr(d, p + "forcOper")
             nfull = int(d[p + "nfull"][0])
             consForc = np.ascontiguousarray(d[p + "consForc"])
             dispCons = np.ascontiguousarray(d[p + "dispCons"])
-            check(lib.ddpca_admm_set_body(h, C.c_int(v), mg._h, C.c_int(nfull), _pd(consForc), _pi(F.rowptr), _pi(F.colidx), _pd(F.val), _pd(dispCons)))
-            mg._h = None  # ownership moved to the ADMM handle
+            check(lib.ddpca_admm_set_body(h, C.c_int(v), C.c_int(L + 1), *args, C.c_int(nfull), _pd(consForc), _pi(F.rowptr), _pi(F.colidx), _pd(F.val), _pd(dispCons)))
             if self.muscSett & 3:
                 a = ddpk.get_csr(d, p + "accuProl")
                 check(lib.ddpca_admm_set_body_accuprol(h, C.c_int(v), C.c_int(a.shape[0]), C.c_int(a.shape[1]), _pi(a.rowptr), _pi(a.colidx), _pd(a.val)))
@@ -207,11 +209,20 @@ class MCONTACT:
         if comm is not None:
             ng_, nt_, nm_ = C.c_long(), C.c_long(), C.c_long()
             check(lib.ddpca_admm_exchange_sizes(h, C.byref(ng_), C.byref(nt_), C.byref(nm_)))
-            self._xbuf = comm.alloc(ng_.value, nt_.value, nm_.value)   # (globForc, traces, moni) device tensors
+            self._xbuf = comm.alloc(ng_.value, nt_.value, nm_.value)   # (globForc, trace_send, trace_recv, moni) device tensors
             ptr = [C.c_void_p(t.data_ptr()) if t is not None and t.numel() else None for t in self._xbuf]
-            check(lib.ddpca_admm_set_exchange(h, ptr[0], ptr[1], ptr[2]))
+            check(lib.ddpca_admm_set_exchange(h, ptr[0], ptr[1], ptr[2], ptr[3]))
             check(lib.ddpca_admm_set_stream(h, C.c_void_p(comm.stream_ptr())))
         check(lib.ddpca_admm_finalize(h))
+        del keep
+        self._peers = []
+        if comm is not None:
+            np_ = C.c_int()
+            check(lib.ddpca_admm_exchange_peers(h, C.byref(np_), None, None, None))
+            k = np_.value
+            pr, off, cnt = (C.c_int * max(1, k))(), (C.c_long * max(1, k))(), (C.c_long * max(1, k))()
+            check(lib.ddpca_admm_exchange_peers(h, C.byref(np_), pr, off, cnt))
+            self._peers = [(int(pr[i]), int(off[i]), int(cnt[i])) for i in range(k)]
         self.row_len = int(lib.ddpca_admm_row_length(h))
         self.moniReco = [[0.0] * 10 for _ in range(nb + 4 * ni)]  # MCONTACT.h:2494-2498
         return self
@@ -238,7 +249,7 @@ class MCONTACT:
             check(lib.ddpca_admm_step(self._h, C.c_int(macro), _pd(row), C.byref(it), C.byref(dofit)))
         else:
             # phases of the loop body with the three exchanges of SURVEY.md §8e in between
-            gl, tr, mo = self._xbuf
+            gl, tx, rx, mo = self._xbuf
             check(lib.ddpca_admm_phase(self._h, C.c_int(0)))            # body solves (local bodies)
             if macro and (self.muscSett & 1):
                 check(lib.ddpca_admm_phase(self._h, C.c_int(1)))        # partial coarse right-hand side
@@ -249,8 +260,8 @@ class MCONTACT:
                 self.comm.allreduce_sum(gl)
                 check(lib.ddpca_admm_phase(self._h, C.c_int(7)))
             check(lib.ddpca_admm_phase(self._h, C.c_int(3)))            # interface side traces
-            if tr is not None and tr.numel():
-                self.comm.allreduce_sum(tr)
+            if self._peers:
+                self.comm.swap(tx, rx, self._peers)                     # pairwise with the owners of the other sides
             check(lib.ddpca_admm_phase(self._h, C.c_int(4)))            # projection, auxiliary and multiplier updates
             check(lib.ddpca_admm_phase(self._h, C.c_int(5)))            # MONITOR sums
             self.comm.allreduce_sum(mo)
@@ -351,3 +362,21 @@ class MCONTACT:
 
     def launch_count(self, reset=False):
         return int(load_library().ddpca_admm_launch_count(self._h, C.c_int(1 if reset else 0)))
+
+    def body_iters(self):
+        """(number of batched hierarchies, CG iteration count of every body in the last step)."""
+        nbt = C.c_int()
+        it = (C.c_long * self.nb)()
+        check(load_library().ddpca_admm_body_iters(self._h, C.byref(nbt), it))
+        return nbt.value, list(it)
+
+    def reset(self, consForc=None):
+        """Zero initial state again (MCONTACT.h:875-894); consForc: {v: host vector} new load vectors."""
+        lib = load_library()
+        for v, f in (consForc or {}).items():
+            check(lib.ddpca_admm_set_consforc(self._h, C.c_int(v), C.c_void_p(f) if isinstance(f, int) else _pd(np.ascontiguousarray(f, dtype=np.float64))))
+        check(lib.ddpca_admm_reset(self._h))
+        self.MULT_MAXI = 1000
+        self.moniReco = [[0.0] * 10 for _ in range(self.nb + 4 * self.ni)]
+        self.cg_iters = 0
+        self.cg_dof_iters = 0.0

@@ -42,6 +42,26 @@ class Plan:
         lib.ddpca_plan_destroy(h)
 
 
+def hierarchy_pointers(hiers):
+    """ctypes argument tuple (n, rowptr, colidx, val, P_rowptr, P_colidx, P_val) for a list of hierarchies
+    [(A, P), ...] of equal level count, indexed [s * nlevels + l] as ddpca_mg_create_batch expects.
+    The Csr objects must outlive the call that consumes the pointers."""
+    nlev = len(hiers[0][0])
+    ns = len(hiers)
+    if any(len(A) != nlev or len(P) != nlev - 1 for A, P in hiers):
+        raise ValueError("hierarchies of one batch must have the same number of levels")
+    n = (C.c_int * (ns * nlev))(*[a.shape[0] for A, _ in hiers for a in A])
+    ipp = C.POINTER(C.c_int) * (ns * nlev)
+    dpp = C.POINTER(C.c_double) * (ns * nlev)
+    npr = max(1, ns * (nlev - 1))
+    ipp2 = C.POINTER(C.c_int) * npr
+    dpp2 = C.POINTER(C.c_double) * npr
+    As = [a for A, _ in hiers for a in A]
+    Ps = [p for _, P in hiers for p in P]
+    return (n, ipp(*[_pi(a.rowptr) for a in As]), ipp(*[_pi(a.colidx) for a in As]), dpp(*[_pd(a.val) for a in As]),
+            ipp2(*[_pi(p.rowptr) for p in Ps]), ipp2(*[_pi(p.colidx) for p in Ps]), dpp2(*[_pd(p.val) for p in Ps]))
+
+
 class MGPIS:
     """Multigrid-preconditioned iterative solver on a B200.
 
@@ -63,6 +83,36 @@ class MGPIS:
         self.last_iterNumb = None
         self.last_resid = None
         self.last_tol = None
+        self.nsub = 1
+        self._batch = None   # [(A, P), ...] of a batched handle
+        self._ntot = None
+
+    @classmethod
+    def from_batch(cls, hiers, device=0, smoother=SMOOTH_MC):
+        """Several subdomain hierarchies [(A, P), ...] (equal level count) as ONE device hierarchy advanced in
+        lock-step (ddpca_mg_create_batch).  CG_SOLV then takes / returns the subdomains' vectors one after the
+        other; per-subdomain iteration counts in .last_iters."""
+        m = cls(device=device, smoother=smoother)
+        m._batch = [(list(A), list(P)) for A, P in hiers]
+        m.nsub = len(m._batch)
+        m.maxiLeve = len(m._batch[0][0]) - 1
+        m.consStif = list(m._batch[0][0])
+        m.realProl = list(m._batch[0][1])
+        args = hierarchy_pointers(m._batch)
+        h = C.c_void_p()
+        check(load_library().ddpca_mg_create_batch(C.c_int(device), C.c_int(m.nsub), C.c_int(m.maxiLeve + 1), *args, C.c_int(smoother), C.byref(h)))
+        m._h = h
+        m._ntot = [sum(A[l].shape[0] for A, _ in m._batch) for l in range(m.maxiLeve + 1)]
+        return m
+
+    def batch_result(self):
+        """(iters[nsub], resid[nsub], tol_abs[nsub]) of the last CG_SOLV."""
+        ns = self.nsub
+        it = (C.c_long * ns)()
+        rs = (C.c_double * ns)()
+        tl = (C.c_double * ns)()
+        check(load_library().ddpca_mg_batch_result(self._handle(), None, it, rs, tl))
+        return list(it), list(rs), list(tl)
 
     # -- lifetime ---------------------------------------------------------------------
     def ESTABLISH(self) -> int:
@@ -108,6 +158,8 @@ class MGPIS:
 
     def n(self, level=None) -> int:
         level = self.maxiLeve if level is None else level
+        if self._ntot is not None:
+            return self._ntot[level]
         return self.consStif[level].shape[0]
 
     # -- solvers (host buffers) ----------------------------------------------------------
@@ -122,10 +174,12 @@ class MGPIS:
         check(
             load_library().ddpca_mg_pcg(
                 self._handle(), C.c_int(precSwit), _pd(b), _pd(x), C.c_double(rel_tol),
-                C.c_long(n if maxit is None else maxit), C.byref(it), C.byref(res), C.byref(tol),
+                C.c_long((n if self.nsub == 1 else 0) if maxit is None else maxit), C.byref(it), C.byref(res), C.byref(tol),
             )
         )
         self.last_iterNumb, self.last_resid, self.last_tol = it.value, res.value, tol.value
+        if self.nsub > 1:
+            self.last_iters = self.batch_result()[0]
         return x
 
     def CG_SOLV_dev(self, precSwit: int, b_ptr: int, x_ptr: int, rel_tol: float = 1.0e-14, maxit: int | None = None):
@@ -135,7 +189,7 @@ class MGPIS:
         check(
             load_library().ddpca_mg_pcg_dev(
                 self._handle(), C.c_int(precSwit), C.c_void_p(b_ptr), C.c_void_p(x_ptr), C.c_double(rel_tol),
-                C.c_long(n if maxit is None else maxit), C.byref(it), C.byref(res), C.byref(tol),
+                C.c_long((n if self.nsub == 1 else 0) if maxit is None else maxit), C.byref(it), C.byref(res), C.byref(tol),
             )
         )
         self.last_iterNumb, self.last_resid, self.last_tol = it.value, res.value, tol.value

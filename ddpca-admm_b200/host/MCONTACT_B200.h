@@ -78,7 +78,8 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 		return -1;
 	}
 	ddpca_admm *hand = nullptr;
-	if(ddpca_admm_create(devi, bodyNumb, inteNumb, (macrSwit ? 1 : 0) | (elimSwit ? 2 : 0), &hand) != 0){
+	if(ddpca_admm_create(devi, bodyNumb, inteNumb, (macrSwit ? 1 : 0) | (elimSwit ? 2 : 0), &hand) != 0
+		|| ddpca_admm_set_smoother(hand, MGPIS::SMOOTHER()) != 0){
 		FAIL("create"); return -1;
 	}
 	bool allGood = true;
@@ -92,8 +93,12 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 		forcOper.makeCompressed();
 		Eigen::VectorXd dispCons;
 		mugr.OUTP_SUB1(Eigen::VectorXd::Zero(forcOper.rows()), dispCons);
-		ddpca_mg *mgHand = mugr.mgpi.RELEASE_HANDLE();
-		if(mgHand == nullptr || ddpca_admm_set_body(hand, tv, mgHand, 3 * mugr.nodeCoor.size(),
+		// the hierarchy goes over as plain arrays: ddpca_admm_finalize builds ONE batched device hierarchy for
+		// all bodies with the same level count (the members of mgpi stay untouched until then)
+		MGPIS::POINTERS poin;
+		mugr.mgpi.HIERARCHY_POINTERS(poin);
+		if(ddpca_admm_set_body(hand, tv, maxiLeve + 1, poin.n.data(), poin.rp.data(), poin.ci.data(),
+			poin.va.data(), poin.prp.data(), poin.pci.data(), poin.pva.data(), 3 * mugr.nodeCoor.size(),
 			mugr.consForc.data(), forcOper.outerIndexPtr(), forcOper.innerIndexPtr(),
 			forcOper.valuePtr(), dispCons.data()) != 0){
 			allGood = FAIL("set_body");

@@ -53,8 +53,16 @@ public:
 	}
 	// device hierarchy (built lazily from consStif / realProl); nullptr + message on failure
 	ddpca_mg *DEVICE_HANDLE();
-	// hand the hierarchy over to another owner (ddpca_admm_set_body takes ownership)
+	// hand the hierarchy over to another owner (ddpca_admm_set_macro_mg takes ownership)
 	ddpca_mg *RELEASE_HANDLE(){ ddpca_mg *h = DEVICE_HANDLE(); if(devi) devi->h = nullptr; devi.reset(); return h; }
+	// the hierarchy as the plain arrays of the C ABI (Eigen's compressed RowMajor storage of the members);
+	// they stay valid as long as consStif / realProl are not modified
+	struct POINTERS{
+		std::vector<int> n;
+		std::vector<const int*> rp, ci, prp, pci;
+		std::vector<const double*> va, pva;
+	};
+	void HIERARCHY_POINTERS(POINTERS &poin);
 	static int DEVICE(){ const char *e = std::getenv("DDPCA_DEVICE"); return e ? std::atoi(e) : 0; }
 	// DDPCA_SMOOTHER=lex reproduces the reference's lexicographic sweeps exactly (slow),
 	// default mc = multicolour ordering of the same symmetric Gauss-Seidel (include/ddpca_b200.h)
@@ -96,34 +104,40 @@ long MGPIS::ESTABLISH(){
 	return 1;
 }
 
-ddpca_mg *MGPIS::DEVICE_HANDLE(){
-	if(devi && devi->h){
-		return devi->h;
-	}
+void MGPIS::HIERARCHY_POINTERS(POINTERS &poin){
 	const long nlev = maxiLeve + 1;
-	std::vector<int> n(nlev);
-	std::vector<const int*> rp(nlev), ci(nlev), prp(nlev), pci(nlev);
-	std::vector<const double*> va(nlev), pva(nlev);
+	poin.n.resize(nlev);
+	poin.rp.resize(nlev); poin.ci.resize(nlev); poin.va.resize(nlev);
+	poin.prp.resize(nlev); poin.pci.resize(nlev); poin.pva.resize(nlev);
 	for(long ti = 0; ti < nlev; ti ++){
 		if(!consStif[ti].isCompressed()){
 			consStif[ti].makeCompressed();
 		}
-		n[ti] = consStif[ti].rows();
-		rp[ti] = consStif[ti].outerIndexPtr();
-		ci[ti] = consStif[ti].innerIndexPtr();
-		va[ti] = consStif[ti].valuePtr();
+		poin.n[ti] = consStif[ti].rows();
+		poin.rp[ti] = consStif[ti].outerIndexPtr();
+		poin.ci[ti] = consStif[ti].innerIndexPtr();
+		poin.va[ti] = consStif[ti].valuePtr();
 	}
 	for(long ti = 0; ti + 1 < nlev; ti ++){
 		if(!realProl[ti].isCompressed()){
 			realProl[ti].makeCompressed();
 		}
-		prp[ti] = realProl[ti].outerIndexPtr();
-		pci[ti] = realProl[ti].innerIndexPtr();
-		pva[ti] = realProl[ti].valuePtr();
+		poin.prp[ti] = realProl[ti].outerIndexPtr();
+		poin.pci[ti] = realProl[ti].innerIndexPtr();
+		poin.pva[ti] = realProl[ti].valuePtr();
 	}
+}
+
+ddpca_mg *MGPIS::DEVICE_HANDLE(){
+	if(devi && devi->h){
+		return devi->h;
+	}
+	const long nlev = maxiLeve + 1;
+	POINTERS poin;
+	HIERARCHY_POINTERS(poin);
 	ddpca_mg *h = nullptr;
-	if(ddpca_mg_create(DEVICE(), nlev, n.data(), rp.data(), ci.data(), va.data(),
-		prp.data(), pci.data(), pva.data(), SMOOTHER(), &h) != 0){
+	if(ddpca_mg_create(DEVICE(), nlev, poin.n.data(), poin.rp.data(), poin.ci.data(), poin.va.data(),
+		poin.prp.data(), poin.pci.data(), poin.pva.data(), SMOOTHER(), &h) != 0){
 		std::cout << "MGPIS (B200): ERROR " << ddpca_last_error() << std::endl;
 		return nullptr;
 	}

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DDPCA_ABI_VERSION 1
+#define DDPCA_ABI_VERSION 2
 
 /* Smoother ordering of the multigrid V-cycle.
  * LEX: the reference's lexicographic symmetric Gauss-Seidel (MGPIS.h:65-77),
@@ -79,12 +79,26 @@ int ddpca_mg_create(int device, int nlevels, const int *n,
                     const int *const *rowptr, const int *const *colidx, const double *const *val,
                     const int *const *P_rowptr, const int *const *P_colidx, const double *const *P_val,
                     int smoother_mode, ddpca_mg **out);
+/* The same for nsub independent subdomain hierarchies of `nlevels` levels each, held as ONE block-diagonal
+ * hierarchy: every level kernel (smoother sweeps, residual, transfers, product, level-0 solve) works on all
+ * subdomains at once, the CG recurrence of MGPIS::CG_SOLV stays per subdomain (own alpha, beta, tolerance,
+ * iteration count; a converged subdomain freezes).  This is how the body loop of MCONTACT::CONTACT_ANALYSIS
+ * (`#pragma omp parallel for` over multGrid[tv].mgpi.CG_SOLV, MCONTACT.h:2511-2532) maps onto one GPU: small
+ * subdomains share launches instead of queueing.  Arrays are indexed [s * nlevels + l] (prolongations
+ * [s * (nlevels-1) + l]); vectors of ddpca_mg_pcg* are the subdomains' vectors one after the other. */
+int ddpca_mg_create_batch(int device, int nsub, int nlevels, const int *n,
+                          const int *const *rowptr, const int *const *colidx, const double *const *val,
+                          const int *const *P_rowptr, const int *const *P_colidx, const double *const *P_val,
+                          int smoother_mode, ddpca_mg **out);
+/* per-subdomain results of the last ddpca_mg_pcg* call: iters[nsub], resid[nsub], tol_abs[nsub] (any may be null) */
+int ddpca_mg_batch_result(const ddpca_mg *, int *nsub, long *iters, double *resid, double *tol_abs);
 int ddpca_mg_destroy(ddpca_mg *);
 
 /* MGPIS::CG_SOLV(precSwit, totaForc, resuSolu), MGPIS.h:163-225.
  * prec 0 = Jacobi (DIAG_PREC, PREP.h:393-401), 1 = one V-cycle.  x0 = 0,
- * stop when it >= maxit or ||r||_2 <= rel_tol*||b||_2 (reference: 1e-14, n).
- * iters = the reference's iterNumb (it prints iterNumb-1).  b, x: host, length n_L. */
+ * stop when it >= maxit or ||r||_2 <= rel_tol*||b||_2 (reference: 1e-14, n; maxit <= 0 means n, per subdomain).
+ * iters = the reference's iterNumb (it prints iterNumb-1); for a batch the largest count and residual, see
+ * ddpca_mg_batch_result.  b, x: host, length n_L (sum over the subdomains of a batch). */
 int ddpca_mg_pcg(ddpca_mg *, int prec, const double *b, double *x, double rel_tol, long maxit,
                  long *iters, double *resid, double *tol_abs);
 /* same, operands resident in HBM on the handle's device (reference numbering) */
@@ -158,12 +172,19 @@ enum { DDPCA_SOLVER_MASS = 0 /* inteDiso */, DDPCA_SOLVER_MASS_PENA = 1 /* inteD
 
 /* muscSett: bit 0 = macroscopic problem (MCONTACT.h:858-860), bit 1 = interface-eliminated coarse problem (:861-863) */
 int ddpca_admm_create(int device, int nbody, int niface, int muscSett, ddpca_admm **out);
-/* Body v.  Takes ownership of `mg` (multGrid[v].mgpi).  forcOper (n_L x 3 n_nodes) is
+/* Body v: the hierarchy of multGrid[v].mgpi (consStif[0..nlevels-1], realProl[0..nlevels-2], as for
+ * ddpca_mg_create -- the arrays must stay valid until ddpca_admm_finalize, which builds ONE batched hierarchy
+ * per group of bodies with equal level count) and the body's loop operators: forcOper (n_L x 3 n_nodes) is
  * MULTIGRID::ADDITIONAL_FORCE as one operator, consOper[L] prolOper[L]^T earlTran^T
  * (MULTIGRID.h:1257-1261); MULTIGRID::OUTP_SUB1 is forcOper^T u + dispCons
  * (MULTIGRID.h:1263-1281, dispCons = OUTP_SUB1(0)); consForc is multGrid[v].consForc. */
-int ddpca_admm_set_body(ddpca_admm *, int v, ddpca_mg *mg, int nfull, const double *consForc,
+int ddpca_admm_set_body(ddpca_admm *, int v, int nlevels, const int *n,
+                        const int *const *rowptr, const int *const *colidx, const double *const *val,
+                        const int *const *P_rowptr, const int *const *P_colidx, const double *const *P_val,
+                        int nfull, const double *consForc,
                         const int *F_rowptr, const int *F_colidx, const double *F_val, const double *dispCons);
+/* smoother ordering of the bodies' hierarchies (default DDPCA_SMOOTH_MC; environment DDPCA_SMOOTHER=lex); before finalize */
+int ddpca_admm_set_smoother(ddpca_admm *, int smoother_mode);
 /* accuProl[v] (MCONTACT.h:864-872), needed when muscSett bit 0 or bit 1 is set */
 int ddpca_admm_set_body_accuprol(ddpca_admm *, int v, int rows, int cols, const int *rowptr, const int *colidx, const double *val);
 /* Interface ts between contBody[ts][0..1]; fricCoef < 0 tied, = 0 frictionless, > 0 Coulomb
@@ -189,13 +210,18 @@ int ddpca_admm_set_macro1(ddpca_admm *, int nglob1, const long *baseReco, const 
  * its own bodies and their interface sides (set_body / set_side_op / set_side_solver), but declares
  * EVERY interface (set_interface) and the macroscopic solver.  Call before ddpca_admm_set_body. */
 int ddpca_admm_set_partition(ddpca_admm *, const int *body_rank, int my_rank);
-/* Device buffers the caller all-reduces (sum) between phases, e.g. torch tensors over NCCL:
- *   globForc [nglob]   after DDPCA_PH_MACRO_PARTIAL   (MCONTACT.h:2541-2549, gather of the coarse RHS)
- *   traces   [ntrace]  after DDPCA_PH_TRACES          (side traces of cross-rank interfaces, :2632-2635)
- *   moni     [nmoni]   after DDPCA_PH_MONITOR         (MONITOR sums, :2737-2833)
- * Optional on a single rank (internal buffers are used).  Call before ddpca_admm_finalize. */
+/* Device buffers of the per-iteration exchange between ranks (e.g. torch tensors over NCCL):
+ *   globForc   [nglob]   all-reduced (sum) after DDPCA_PH_MACRO_PARTIAL / _MACRO1_PARTIAL (MCONTACT.h:2541-2549: coarse RHS)
+ *   trace_send [ntrace]  after DDPCA_PH_TRACES: this rank's signed side traces of its cross-rank interfaces
+ *   trace_recv [ntrace]  (:2632-2635), grouped by peer (ddpca_admm_exchange_peers): range k is SENT to peer k and the
+ *                        same range of trace_recv RECEIVED from it -- a pairwise swap, half the bytes of a reduction;
+ *                        both owners then add the two parts (a + b == b + a bit for bit) and project the same gamma
+ *   moni       [nmoni]   all-reduced (sum) after DDPCA_PH_MONITOR (MONITOR sums, :2737-2833)
+ * Not needed on a single rank.  Sizes are known once every interface is declared; call set_exchange before the
+ * first iteration, exchange_peers after ddpca_admm_finalize. */
 int ddpca_admm_exchange_sizes(const ddpca_admm *, long *nglob, long *ntrace, long *nmoni);
-int ddpca_admm_set_exchange(ddpca_admm *, double *globForc_dev, double *traces_dev, double *moni_dev);
+int ddpca_admm_set_exchange(ddpca_admm *, double *globForc_dev, double *trace_send_dev, double *trace_recv_dev, double *moni_dev);
+int ddpca_admm_exchange_peers(const ddpca_admm *, int *npeers, int *peer_rank, long *offset, long *count);
 int ddpca_admm_set_stream(ddpca_admm *, void *stream);
 enum { DDPCA_PH_BODIES = 0, DDPCA_PH_MACRO_PARTIAL = 1, DDPCA_PH_MACRO_APPLY = 2, DDPCA_PH_TRACES = 3, DDPCA_PH_INTERFACE = 4, DDPCA_PH_MONITOR = 5,
        DDPCA_PH_MACRO1_PARTIAL = 6, DDPCA_PH_MACRO1_APPLY = 7 /* muscSett bit 1: between MACRO_APPLY and TRACES, same globForc exchange buffer */ };
@@ -211,6 +237,12 @@ int ddpca_admm_finalize(ddpca_admm *);
  * over bodies, and sum of n_L * iterations. */
 int ddpca_admm_step(ddpca_admm *, int apply_macro, double *monitor_row, long *cg_iters, double *cg_dof_iters);
 int ddpca_admm_row_length(const ddpca_admm *);
+/* Repeat the analysis on the same handle: zero initial state again (MCONTACT.h:875-894), optionally new load
+ * vectors multGrid[v].consForc (host, n_L doubles; copied on the handle's stream). */
+int ddpca_admm_reset(ddpca_admm *);
+int ddpca_admm_set_consforc(ddpca_admm *, int v, const double *consForc);
+/* number of batched hierarchies and the CG iteration count of every body in the last step (0 for remote bodies) */
+int ddpca_admm_body_iters(const ddpca_admm *, int *nbatches, long *iters);
 int ddpca_admm_get_disp(ddpca_admm *, int v, double *resuDisp);
 int ddpca_admm_get_side(ddpca_admm *, int ts, int tv, double *inteAuxi, double *inteLagr);
 /* inpoGamm[ts] and fricStat of the last iteration (what OUTPUT_PRTR writes, MCONTACT.h:97-123) */

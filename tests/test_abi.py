@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
 
 def test_abi_version_and_device_count():
     lib = dd.load_library()
-    assert lib.ddpca_abi_version() == 1
+    assert lib.ddpca_abi_version() == 2
     assert dd.device_count() >= 0
 
 

@@ -251,3 +251,52 @@ def test_gmres_matches_oracle(solvers):
     assert mg.last_iterNumb == ito or abs(mg.last_iterNumb - ito) <= ito // 10
     if "gmres_mg_x" in d:
         assert rel(x, d["gmres_mg_x"]) < 1e-8
+
+
+def test_batched_hierarchies_advance_per_subdomain():
+    """ddpca_mg_create_batch: three subdomain hierarchies as one block-diagonal device hierarchy.  Every
+    subdomain keeps its own CG recurrence (MGPIS.h:163-225 is called once per subdomain by the body loop,
+    MCONTACT.h:2511-2532): same iteration count and solution as a stand-alone handle, a zero right-hand side
+    never enters the loop (iterNumb 0, MGPIS.h:175,198), the batch stops when the slowest subdomain does."""
+    d, meta, A, P = load_golden("beam_3lev")
+    n = A[-1].shape[0]
+    rng = np.random.default_rng(3)
+    rhs = [d["consForc"], np.zeros(n), 1e3 * rng.standard_normal(n)]
+    solo = dd.MGPIS.from_hierarchy(A, P)
+    ref = []
+    for b in rhs:
+        x = solo.CG_SOLV(1, b)
+        ref.append((x, solo.last_iterNumb))
+    solo.close()
+    mg = dd.MGPIS.from_batch([(A, P)] * 3)
+    x = mg.CG_SOLV(1, np.concatenate(rhs))
+    its = mg.last_iters
+    assert mg.last_iterNumb == max(its)
+    for s in range(3):
+        xs = x[s * n:(s + 1) * n]
+        assert its[s] == ref[s][1]
+        if np.linalg.norm(ref[s][0]) == 0.0:
+            assert its[s] == 0 and not xs.any()
+        else:
+            assert rel(xs, ref[s][0]) < 1e-9
+    assert rel(x[:n], d["cg_mg_x"]) < 1e-8
+    # the same handle again: results are bit-reproducible
+    assert np.array_equal(mg.CG_SOLV(1, np.concatenate(rhs)), x)
+    mg.close()
+
+
+def test_solve_after_a_non_finite_right_hand_side_is_clean():
+    """Work vectors are zero-initialised and the padding entries of the group layouts point at an always-zero
+    slot, so a solve that produced NaN does not poison later solves on the same handle (round-1 advice)."""
+    d, meta, A, P = load_golden("beam_3lev")
+    b = d["consForc"]
+    for mode in (dd.SMOOTH_MC, dd.SMOOTH_LEX):
+        mg = dd.MGPIS.from_hierarchy(A, P, smoother=mode)
+        x0 = mg.CG_SOLV(1, b)
+        it0 = mg.last_iterNumb
+        bad = b.copy()
+        bad[::7] = np.nan
+        mg.CG_SOLV(1, bad, maxit=3)
+        x1 = mg.CG_SOLV(1, b)
+        assert mg.last_iterNumb == it0 and np.array_equal(x0, x1)
+        mg.close()
