@@ -1,20 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- MG-PCG DOF*iter/s of the DDPCA-ADMM hot path on B200 (BASELINE.json metric).
+"""bench.py -- the DDPCA-ADMM hot path on B200: MG-PCG DOF*iter/s inside the ADMM contact / domain-decomposition
+solve, ADMM solve wall time, strong scaling over 1/2/4/8 GPUs (BASELINE.json metric).
 
-A "step" is one complete MGPIS::CG_SOLV(1, consForc) (MGPIS.h:163-225) on one subdomain
-hierarchy: x0 = 0, V-cycle-preconditioned CG down to ||r|| <= 1e-14 ||b||.  The hierarchy is
-produced by the reference's own host C++ (mesh, TRANSFER, STIF_MATR, CONSTRAINT -- setup, out
-of scope of the GPU path) through the prebuilt driver oracle/_ref/beam_nodd, outside the timed
-region.  With N ranks every rank owns one such subdomain (subdomains are independent in the
-solve phase of an ADMM iteration, MCONTACT.h:2511-2538): weak scaling, no data-path collective.
+Workload (fixed, whatever --gpus says: STRONG scaling): the reference's BEAM example with domain decomposition
+(examples/BEAM.h:390-609), domaNumb 8x2x1 = 16 subdomains of ~58 k DOF joined by 22 tied interfaces, globLeve 3
+(0.93 M DOF, 4 multigrid levels per subdomain), macroscopic coarse problem.  The reference's own host C++ does
+mesh, contact search, MULTIGRID::STIF_MATR/CONSTRAINT and MCONTACT::ESTABLISH (set-up, out of scope of the GPU
+path) through the prebuilt driver oracle/_ref/beam_admm, outside the timed region; the same process then runs
+the untouched reference loop for a few iterations on this box's host cores (the CPU baseline).
 
-  value : sum over ranks of (DOF * CG iterations * steps) / max-over-ranks device time, operands in HBM
-  e2e   : the same through MGPIS.CG_SOLV with HOST (pinned) buffers, H2D + D2H inside the timing
-  roofline     : dominant kernel class, algorithmic bytes / CUDA-event time
-  cpu_baseline : the untouched reference (oracle/_ref) timed on this box's host cores
+A "step" is one complete MCONTACT::CONTACT_ANALYSIS (MCONTACT.h:2493-2723): zero initial state, ADMM iterations
+until MONITOR reports convergence; every iteration solves all subdomains with MG-PCG to 1e-14 (one batched solve
+per rank), exchanges interface traces and updates auxiliary variables and multipliers.  With N ranks the 16
+subdomains are partitioned over the ranks (ddpca_b200/partition.py); per iteration the ranks all-reduce the coarse
+right-hand side and the MONITOR sums and swap interface traces pairwise (NCCL).
 
-`--impl reference` times the reference's own CPU implementation (oracle/_ref/beam_nodd
---bench-steps) and prints the same line with "impl": "reference".
+  value : sum over subdomains and ADMM iterations of (n_L * CG iterations) / max-over-ranks device time, state in HBM
+  e2e   : the same with, per step, the load vectors copied from pinned host memory and the displacements read back
+  admm  : solve wall time, ADMM iterations/s, upload time, launches per iteration, parity against the reference
+  roofline     : dominant kernel of the batched MG-PCG, algorithmic bytes / CUDA-event time per launch
+  cpu_baseline : the untouched reference (oracle/_ref/beam_admm) on the host cores, first iterations of the same solve
+
+`--impl reference` times the reference's own loop on the same configuration (all host cores) and prints the same
+line with "impl": "reference"; a step there is one ADMM iteration (a bounded sample of the solve).
 """
 import argparse
 import json
@@ -32,8 +40,8 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-REF_BEAM = os.path.join(ROOT, "oracle", "_ref", "beam_nodd")
-METRIC = "MG-PCG DOF*iter/s"
+REF_BEAM_DD = os.path.join(ROOT, "oracle", "_ref", "beam_admm")
+METRIC = "MG-PCG DOF*iter/s inside the ADMM solve"
 UNIT = "DOF*iter/s"
 
 
@@ -53,117 +61,49 @@ def workload_cache_dir():
     return d
 
 
-def generate_workload(glob, ref_solve):
-    """Run the reference's host setup (and, optionally, its CPU solve) once; cache in /tmp."""
-    cdir = workload_cache_dir()
-    out = os.path.join(cdir, f"beam_nodd_g{glob}.ddpk")
-    meta_p = out + ".json"
-    if os.path.exists(out) and os.path.exists(meta_p):
-        meta = json.load(open(meta_p))
-        if (not ref_solve) or "cg_mg_s" in meta:
-            return out, meta
-    if not os.access(REF_BEAM, os.X_OK):
-        raise SystemExit("oracle/_ref/beam_nodd is missing: run __graft_entry__.build() in the build container")
+def workload_name(args):
+    return f"BEAM DD domaNumb={args.doma.replace(',', 'x')} globLeve={args.glob}" + (f" diviNumb={args.divi.replace(',', 'x')}" if args.divi else "") + f" muscSett={args.musc}"
+
+
+def run_reference_driver(args, ref_iters, out):
+    """oracle/_ref/beam_admm: reference host set-up (+ dump) and `ref_iters` iterations of the untouched loop."""
+    if not os.access(REF_BEAM_DD, os.X_OK):
+        raise SystemExit("oracle/_ref/beam_admm is missing: run __graft_entry__.build() in the build container")
+    cmd = [REF_BEAM_DD, "--glob", str(args.glob), "--doma", args.doma, "--musc", str(args.musc), "--ref-iters", str(ref_iters)]
+    if args.divi:
+        cmd += ["--divi", args.divi]
+    cmd += ["--out", out] if out else ["--nomat"]
     t0 = time.time()
-    txt = subprocess.check_output([REF_BEAM, "--glob", str(glob), "--out", out + ".tmp", "--solve", "1" if ref_solve else "0"], cwd=cdir).decode()
+    txt = subprocess.check_output(cmd, cwd=workload_cache_dir()).decode()
     meta = json.loads(txt.strip().splitlines()[-1])
-    meta["generate_wall_s"] = time.time() - t0
-    os.replace(out + ".tmp", out)
-    json.dump(meta, open(meta_p, "w"))
-    return out, meta
+    meta["driver_wall_s"] = time.time() - t0
+    return meta
 
 
-REF_BLOCK = os.path.join(ROOT, "oracle", "_ref", "block_admm")
-
-
-def generate_admm_workload(glob, divi):
-    """Reference host set-up of the BLOCK example (mesh, contact search, MCONTACT::ESTABLISH) plus the
-    untouched reference ADMM loop for the CPU baseline / golden results; cached in /tmp."""
-    cdir = workload_cache_dir()
-    tag = f"block_g{glob}" + (f"_d{divi.replace(',', 'x')}" if divi else "")
-    out = os.path.join(cdir, tag + ".ddpk")
+def generate_workload(args):
+    """Reference host set-up once per box (cached in /tmp), with the first `--cpu-iters` reference iterations."""
+    tag = f"beam_dd_g{args.glob}_{args.doma.replace(',', 'x')}" + (f"_d{args.divi.replace(',', 'x')}" if args.divi else "") + f"_m{args.musc}_r{args.cpu_iters}"
+    out = os.path.join(workload_cache_dir(), tag + ".ddpk")
     if os.path.exists(out) and os.path.exists(out + ".json"):
         return out, json.load(open(out + ".json"))
-    if not os.access(REF_BLOCK, os.X_OK):
-        raise SystemExit("oracle/_ref/block_admm is missing: run __graft_entry__.build() in the build container")
-    cmd = [REF_BLOCK, "--glob", str(glob), "--musc", "1", "--out", out + ".tmp", "--ref-iters", "0"]
-    if divi:
-        cmd += ["--divi", divi]
-    t0 = time.time()
-    for attempt in range(3):   # the driver ends through a watcher thread (_exit); a rare teardown race aborts it
-        try:
-            txt = subprocess.check_output(cmd, cwd=cdir).decode()
-            break
-        except subprocess.CalledProcessError:
-            if attempt == 2:
-                raise
-    meta = json.loads(txt.strip().splitlines()[-1])
-    meta["generate_wall_s"] = time.time() - t0
+    meta = run_reference_driver(args, args.cpu_iters, out + ".tmp")
     os.replace(out + ".tmp", out)
     json.dump(meta, open(out + ".json", "w"))
     return out, meta
 
 
-def admm_leg(args, rank, world, local, dist, torch):
-    """ADMM contact solve of the BLOCK example on `world` GPUs: bodies are partitioned over the ranks,
-    three all-reduces per iteration.  Strong scaling: the problem is fixed."""
-    import numpy as np
-
-    import ddpca_b200 as dd
-    from ddpca_b200 import ddpk
-    from ddpca_b200.comm import TorchComm
-    from ddpca_b200.partition import partition_bodies
-
-    if rank == 0:
-        path, meta = generate_admm_workload(args.admm_glob, args.admm_divi)
-    if dist is not None:
-        dist.barrier()
-    if rank != 0:
-        path, meta = generate_admm_workload(args.admm_glob, args.admm_divi)
-    d = ddpk.load(path)
-    nb, ni = int(d["nbody"][0]), int(d["niface"][0])
-    contBody = [[int(x) for x in d[f"if{ts}.contBody"]] for ts in range(ni)]
-    weights = [len(d[f"body{v}.consStif{int(d[f'body{v}.maxiLeve'][0])}.val"]) for v in range(nb)]
-    body_rank = partition_bodies(weights, contBody, world)
-    comm = TorchComm(torch.device("cuda", local)) if world > 1 else None
-    t0 = time.time()
-    mc = dd.MCONTACT.from_ddpk(d, device=local, body_rank=body_rank if world > 1 else None, rank=rank, comm=comm)
-    upload_s = time.time() - t0
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    t1 = time.time()
-    mc.CONTACT_ANALYSIS()
-    torch.cuda.synchronize()
-    solve_s = time.time() - t1
-    tt = torch.tensor([solve_s], device=torch.device("cuda", local), dtype=torch.float64)
-    wk = torch.tensor([mc.cg_dof_iters, float(mc.cg_iters), float(mc.launch_count())], device=torch.device("cuda", local), dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(wk, op=dist.ReduceOp.SUM)
-    solve_s = tt.item()
-    iters = mc.iterNumbReco + 1
-    disp = mc.resuDisp
-    err = 0.0
-    for v in range(nb):
-        if disp[v] is not None and f"ref.resuDisp{v}" in d:
-            r = d[f"ref.resuDisp{v}"]
-            err = max(err, float(np.linalg.norm(disp[v] - r) / np.linalg.norm(r)))
-    et = torch.tensor([err], device=torch.device("cuda", local), dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(et, op=dist.ReduceOp.MAX)
-    out = {
-        "workload": f"BLOCK domaNumb=1x1x1 globLeve={args.admm_glob}: {nb} bodies {meta['body_dof']}, {ni} interfaces (2 frictionless contact, 6 tied), macroscopic problem {meta.get('globCoup_rows')} rows",
-        "n_gpus": world, "body_rank": body_rank, "scaling": "strong",
-        "admm_iterations": iters, "reference_admm_iterations": meta.get("ref_iterNumbReco", -2) + 1,
-        "solve_wall_s": solve_s, "upload_s": upload_s, "admm_iter_per_s": iters / solve_s,
-        "mgpcg_dof_iter_per_s": wk[0].item() / solve_s, "cg_iterations_total": int(wk[1].item()), "gpu_launches": int(wk[2].item()),
-        "max_rel_err_resuDisp_vs_reference": et.item(),
-        "cpu_baseline": {"solve_wall_s": meta.get("ref_admm_s"), "kind": "reference", "cores": os.cpu_count(),
-                         "note": "untouched MCONTACT::CONTACT_ANALYSIS, OpenMP over bodies/interfaces (nested, dynamic); bodies < 50 000 DOF use host LDLT (MCONTACT.h:2527)"},
-    }
-    mc.close()
-    return out
+def ref_rate(meta, w, k):
+    """DOF*iter/s of the reference over its ADMM iterations [w, w+k): per-iteration wall times and CG iteration sums
+    come from the driver (admm_hook.h); CG counts are summed over the CG_SOLV calls, DOF = mean subdomain size (the
+    reference does not say which call belongs to which subdomain; sizes differ by < 5 %)."""
+    ts, cg, calls = meta["ref_iter_s"], meta["ref_cg_iters"], meta["ref_cg_calls"]
+    n = len(ts)
+    w = min(w, max(0, n - 1))
+    k = max(1, min(k, n - w))
+    dof = sum(meta["body_dof"]) / len(meta["body_dof"])
+    t = sum(ts[w:w + k])
+    return {"value": dof * sum(cg[w:w + k]) / t, "seconds": t, "first": w, "count": k, "cg_iters": sum(cg[w:w + k]), "cg_calls": sum(calls[w:w + k]),
+            "admm_iter_per_s": k / t}
 
 
 class ClockSampler:
@@ -210,32 +150,34 @@ class ClockSampler:
             for k, nme in enumerate(names):
                 if f[3 + k].lower().startswith("active"):
                     reasons.add(nme)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] if pw else sm
+        return {"sm_mhz": statistics.median(busy or sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def run_reference(args):
-    """Reference arm: the untouched reference's MGPIS::CG_SOLV on this box's host cores."""
+    """Reference arm: the untouched MCONTACT::CONTACT_ANALYSIS on this box's host cores, same configuration."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    glob = args.ref_glob
-    cdir = workload_cache_dir()
     t0 = time.time()
-    txt = subprocess.check_output([REF_BEAM, "--glob", str(glob), "--solve", "0", "--bench-steps", str(args.steps), "--bench-warmup", str(args.warmup)], cwd=cdir).decode()
-    meta = json.loads(txt.strip().splitlines()[-1])
-    n = meta["levels"][-1][0]
-    v = meta["bench_dof_iter_per_s"]
-    sample = f"BEAM no-DD globLeve={glob} ({n} DOF, {len(meta['levels'])} levels): {args.steps} MGPIS::CG_SOLV(1,.) calls, {meta['bench_iters'] // max(1, args.steps)} CG iterations each"
+    need = args.warmup + args.steps
+    meta = run_reference_driver(args, need, None)
+    r = ref_rate(meta, args.warmup, args.steps)
+    cores = meta.get("omp_max_threads", os.cpu_count())
+    sample = (f"{workload_name(args)}: ADMM iterations {r['first']}..{r['first'] + r['count'] - 1} of the untouched reference loop "
+              f"({r['cg_calls']} MGPIS::CG_SOLV calls, {r['cg_iters']} CG iterations, {r['seconds']:.2f} s), OpenMP over subdomains, {cores} threads"
+              + ("" if r["count"] == args.steps else f"; the reference converged after {len(meta['ref_iter_s'])} iterations, fewer than warmup+steps"))
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * meta["bench_s"] / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["seconds"] / r["count"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BEAM no-DD single-subdomain MG-PCG (bounded sample: globLeve={glob}, {n} DOF; per-thread throughput of the reference is size-independent)",
-                   "levels": meta["levels"], "rel_tol": 1e-14},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample,
-                         "note": "the reference's MG-PCG is single-threaded per subdomain (Eigen nbThreads()==-1); one subdomain => one core"},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload_name(args), "bodies": meta["bodies"], "interfaces": meta["interfaces"], "body_dof": meta["body_dof"],
+                   "step": "one ADMM iteration of the reference loop (bounded sample of the solve)", "rel_tol": 1e-14},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "admm": {"admm_iter_per_s": r["admm_iter_per_s"], "iterations_timed": r["count"], "cores": cores,
+                 "solve_wall_s_extrapolated": None if meta.get("ref_iterNumbReco") is None else sum(meta["ref_iter_s"])},
         "wall_s": time.time() - t0,
     }
     print(json.dumps(line), flush=True)
@@ -247,15 +189,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--glob", type=int, default=3, help="BEAM globLeve of the GPU workload (3: 861 696 DOF, 4 levels)")
-    ap.add_argument("--ref-glob", type=int, default=2, help="BEAM globLeve of the bounded CPU sample for --impl reference")
+    ap.add_argument("--glob", type=int, default=3, help="BEAM globLeve (3: 0.93 M DOF in all)")
+    ap.add_argument("--doma", default="8,2,1", help="BEAM domaNumb (subdomains per direction)")
+    ap.add_argument("--divi", default="", help="BEAM diviNumb of the coarsest mesh (default 64,4,2)")
+    ap.add_argument("--musc", type=int, default=1, help="coarse-space correction: 1 macroscopic problem, 2 interface-eliminated, 3 both, 0 none")
+    ap.add_argument("--cpu-iters", type=int, default=4, help="reference iterations run on the host cores for the CPU baseline")
     ap.add_argument("--smoother", default="mc", choices=["mc", "lex"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
-    ap.add_argument("--admm", action="store_true", help="also run the ADMM contact solve (BLOCK example) and report it under \"admm\"")
-    ap.add_argument("--admm-glob", type=int, default=2, help="BLOCK globLeve of the ADMM leg (2: 3 x 45 725 DOF + 6 plates)")
-    ap.add_argument("--admm-divi", default="", help="BLOCK coarsest divisions a,b,c (default 6,6,6)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -268,6 +209,8 @@ def main():
 
     import ddpca_b200 as dd
     from ddpca_b200 import ddpk
+    from ddpca_b200.comm import TorchComm
+    from ddpca_b200.partition import partition_bodies
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -286,73 +229,94 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- setup (untimed): reference host C++ builds the hierarchy; upload to HBM ----------------
-    want_ref = (rank == 0) and not args.no_cpu_baseline
+    # ---- set-up (untimed): the reference's host C++ builds every operator; upload to HBM ------------------
     if rank == 0:
-        path, meta = generate_workload(args.glob, want_ref)
+        path, meta = generate_workload(args)
     barrier()
     if rank != 0:
-        path, meta = generate_workload(args.glob, False)
-    d = ddpk.load(path)
-    A, P = ddpk.get_hierarchy(d)
-    b_host = np.ascontiguousarray(d["consForc"])
-    n = A[-1].shape[0]
-    t0 = time.time()
-    mg = dd.MGPIS.from_hierarchy(A, P, device=local, smoother=dd.SMOOTH_MC if args.smoother == "mc" else dd.SMOOTH_LEX)
-    establish_s = time.time() - t0
-    # a real (non-null) torch stream: the library launches on it, torch events bracket it
-    stream = torch.cuda.Stream(device=dev)
+        path, meta = generate_workload(args)
+    d = ddpk.load(path, copy=False)
+    nb, ni = int(d["nbody"][0]), int(d["niface"][0])
+    contBody = [[int(x) for x in d[f"if{ts}.contBody"]] for ts in range(ni)]
+    nlev = [int(d[f"body{v}.maxiLeve"][0]) + 1 for v in range(nb)]
+    weights = [len(d[f"body{v}.consStif{nlev[v] - 1}.val"]) for v in range(nb)]
+    body_rank = partition_bodies(weights, contBody, world)
+    comm = TorchComm(dev) if world > 1 else None
+    stream = comm.stream if comm is not None else torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    mg.set_stream(stream.cuda_stream)
-    b_dev = torch.from_numpy(b_host).to(dev)
-    x_dev = torch.empty_like(b_dev)
+    t0 = time.time()
+    mc = dd.MCONTACT.from_ddpk(d, device=local, smoother=dd.SMOOTH_MC if args.smoother == "mc" else dd.SMOOTH_LEX,
+                               body_rank=body_rank if world > 1 else None, rank=rank, comm=comm)
+    if comm is None:
+        from ddpca_b200.lib import check, load_library
+        import ctypes as C
+
+        check(load_library().ddpca_admm_set_stream(mc._h, C.c_void_p(stream.cuda_stream)))
+    torch.cuda.synchronize()
+    upload_s = time.time() - t0
+    mine = [v for v in range(nb) if body_rank[v] == rank]
+    dof_local = sum(mc.body_dof[v] for v in mine)
+
+    def solve(consForc=None):
+        mc.reset(consForc)
+        mc.CONTACT_ANALYSIS()
+        return mc.iterNumbReco + 1
 
     # ---- device-resident timing: `value` -----------------------------------------------------
     for _ in range(args.warmup):
-        mg.CG_SOLV_dev(1, b_dev.data_ptr(), x_dev.data_ptr())
+        solve()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    mg.launch_count(reset=True)
+    mc.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters_total = 0
+    dof_iters, cg_total, admm_iters = 0.0, 0, 0
     e0.record(stream)
     for _ in range(args.steps):
-        iters_total += mg.CG_SOLV_dev(1, b_dev.data_ptr(), x_dev.data_ptr())
+        admm_iters += solve()
+        dof_iters += mc.cg_dof_iters
+        cg_total += mc.cg_iters
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = mg.launch_count()
+    launches = mc.launch_count()
     clocks = sampler.stop()
-    x_gpu = x_dev.cpu().numpy()
+    disp_final = mc.resuDisp
 
-    # ---- end-to-end through the public host-buffer API: `e2e` --------------------------------------
-    b_pin = torch.from_numpy(b_host).pin_memory()
-    x_pin = torch.empty(n, dtype=torch.float64).pin_memory()
-    e2e_steps = 0 if args.no_e2e else args.steps
-    for _ in range(0 if args.no_e2e else min(args.warmup, 2)):
-        mg.CG_SOLV(1, b_pin.numpy())
-    barrier()
+    # ---- end-to-end: per step the load vectors come from pinned host memory and the displacements go back ---------
+    pin_in = {v: torch.from_numpy(np.ascontiguousarray(d[f"body{v}.consForc"])).pin_memory() for v in mine}
+    pin_out = {v: torch.empty(mc.nfull[v], dtype=torch.float64).pin_memory() for v in mine}
+    h2d = sum(8 * t.numel() for t in pin_in.values())
+    d2h = sum(8 * t.numel() for t in pin_out.values())
     import ctypes as C
 
     from ddpca_b200.lib import check, load_library
 
     lib = load_library()
-    it_c, res_c, tol_c = C.c_long(), C.c_double(), C.c_double()
+
+    def solve_e2e():
+        it = solve({v: pin_in[v].data_ptr() for v in mine})
+        for v in mine:
+            check(lib.ddpca_admm_get_disp(mc._h, C.c_int(v), C.c_void_p(pin_out[v].data_ptr())))
+        return it
+
+    e2e_steps = 0 if args.no_e2e else args.steps
+    for _ in range(0 if args.no_e2e else min(args.warmup, 1)):
+        solve_e2e()
+    barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_iters = 0
+    e2e_dof_iters = 0.0
     e2.record(stream)
     for _ in range(e2e_steps):
-        check(lib.ddpca_mg_pcg(mg._h, C.c_int(1), C.c_void_p(b_pin.data_ptr()), C.c_void_p(x_pin.data_ptr()), C.c_double(1e-14), C.c_long(n),
-                               C.byref(it_c), C.byref(res_c), C.byref(tol_c)))
-        e2e_iters += it_c.value
+        solve_e2e()
+        e2e_dof_iters += mc.cg_dof_iters
     e3.record(stream)
     barrier()
     ms_e2e = e2.elapsed_time(e3)
 
     # ---- max over ranks, whole-job aggregate --------------------------------------------------------
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    work = torch.tensor([float(n) * iters_total, float(n) * e2e_iters, float(launches)], device=dev, dtype=torch.float64)
+    work = torch.tensor([dof_iters, e2e_dof_iters, float(launches), float(cg_total), float(h2d), float(d2h)], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
@@ -360,67 +324,89 @@ def main():
     value = work[0].item() / (ms_max * 1e-3)
     e2e_value = work[1].item() / (ms_e2e_max * 1e-3) if e2e_steps else None
 
-    # ---- roofline of the dominant kernel class (CUDA events around every launch, same workload) ----
+    # ---- parity: the state after the reference's own first iterations (dumped by the driver) ------------------
+    k_ref = int(d["ref.first_iters"][0]) if "ref.first_iters" in d else 0
+    err = 0.0
+    if k_ref:
+        mc.reset()
+        for tc in range(k_ref):
+            mc.MONITOR(tc, mc.step(tc))
+        disp = mc.resuDisp
+        for v in mine:
+            r = d[f"ref.resuDisp{v}"]
+            err = max(err, float(np.linalg.norm(disp[v] - r) / np.linalg.norm(r)))
+    et = torch.tensor([err], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+
+    # ---- roofline of the dominant kernel class (CUDA events around every launch of the batched solves) ----
     roofline = None
     shares = {}
-    if rank == 0 and not args.no_profile:
-        mg.profile(True)
-        for _ in range(max(1, min(3, args.steps))):
-            mg.CG_SOLV_dev(1, b_dev.data_ptr(), x_dev.data_ptr())
-        prof = mg.profile_get()
-        mg.profile(False)
-        tot = sum(v[0] for v in prof.values())
-        peak, peak_src = hbm_peak()
-        best = max(prof.items(), key=lambda kv: kv[1][0])
-        for (kname, lvl), (kms, kn, kb) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-            shares[f"{kname}@L{lvl}"] = {"share": round(kms / tot, 4), "launches": kn, "avg_us": round(1e3 * kms / kn, 2),
-                                         "GBps": round(kb / (kms * 1e-3) / 1e9, 1) if kms > 0 else None}
-        (kname, lvl), (kms, kn, kb) = best
-        ach = kb / (kms * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload, from the
-        # committed `ncu --set full` capture (profiles/NCU_TRAFFIC.json); null for kernels / workloads not captured
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "NCU_TRAFFIC.json")))
-            traffic = tr.get(f"beam_g{args.glob}", {}).get(f"{kname}@L{lvl}")
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": f"{kname}@L{lvl}", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                    "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": kb / kn, "avg_launch_us": 1e3 * kms / kn,
-                    "share_of_step": round(kms / tot, 4)}
+    if not args.no_profile:
+        if rank == 0:
+            mc.profile(True)
+        mc.reset()
+        for tc in range(2):   # two ADMM iterations = two batched solves of ~20 CG iterations each; all ranks take part
+            mc.MONITOR(tc, mc.step(tc))
+        if rank == 0:
+            prof = mc.profile_get(max(nlev))
+            mc.profile(False)
+            tot = sum(v[0] for v in prof.values())
+            peak, peak_src = hbm_peak()
+            for (kname, lvl), (kms, kn, kb) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+                shares[f"{kname}@L{lvl}"] = {"share": round(kms / tot, 4), "launches": kn, "avg_us": round(1e3 * kms / kn, 2),
+                                             "GBps": round(kb / (kms * 1e-3) / 1e9, 1) if kms > 0 else None}
+            (kname, lvl), (kms, kn, kb) = max(prof.items(), key=lambda kv: kv[1][0])
+            ach = kb / (kms * 1e-3) / 1e9
+            traffic = None
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "NCU_TRAFFIC.json")))
+                traffic = tr.get(f"beam_dd_g{args.glob}_{args.doma.replace(',', 'x')}_n{world}", {}).get(f"{kname}@L{lvl}")
+            except Exception:
+                pass
+            roofline = {"bound": "hbm", "kernel": f"{kname}@L{lvl}", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                        "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": kb / kn, "avg_launch_us": 1e3 * kms / kn,
+                        "share_of_solve_kernels": round(kms / tot, 4),
+                        "note": "per-launch CUDA events on rank 0's batched MG-PCG (all its subdomains in one launch), host-polled loop without look-ahead"}
 
-    admm = None
-    if args.admm:
-        admm = admm_leg(args, rank, world, local, dist, torch)
     if rank == 0:
-        parity = None
-        if "cg_mg_x" in d:
-            parity = float(np.linalg.norm(x_gpu - d["cg_mg_x"]) / np.linalg.norm(d["cg_mg_x"]))
+        steps = max(1, args.steps)
+        solve_s = ms_max * 1e-3 / steps
+        cpu = ref_rate(meta, 1, args.cpu_iters) if meta.get("ref_cg_iters") else None
         cpu_baseline = None
-        if "cg_mg_s" in meta:
-            cpu_baseline = {"value": meta["dof_iter_per_s"], "unit": UNIT, "cores": 1, "kind": "reference",
-                            "sample": f"the same workload once: untouched reference MGPIS::CG_SOLV(1,.) on {n} DOF, {meta['cg_mg_iters']} iterations, {meta['cg_mg_s']:.2f} s on one host core (its MG-PCG is single-threaded per subdomain)"}
+        if cpu:
+            cores = meta.get("omp_max_threads", os.cpu_count())
+            cpu_baseline = {"value": cpu["value"], "unit": UNIT, "cores": cores, "kind": "reference",
+                            "sample": f"the same workload: ADMM iterations {cpu['first']}..{cpu['first'] + cpu['count'] - 1} of the untouched reference loop right after its set-up "
+                                      f"({cpu['cg_calls']} MGPIS::CG_SOLV calls, {cpu['cg_iters']} CG iterations, {cpu['seconds']:.2f} s), OpenMP over subdomains, {cores} threads",
+                            "admm_iter_per_s": cpu["admm_iter_per_s"]}
+        its = admm_iters // steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BEAM no-DD single-subdomain MG-PCG per GPU: globLeve={args.glob}, {n} DOF, {len(A)} levels, V(1,1) SGS ({args.smoother}), rel_tol 1e-14",
-                       "levels": [[a.shape[0], a.nnz] for a in A], "subdomains_per_gpu": 1,
-                       "l2_policy": f"inputs larger than L2: finest operator {12 * A[-1].nnz / 1e6:.0f} MB streamed several times per iteration vs 126 MB L2",
-                       "cg_iterations_per_solve": iters_total // max(1, args.steps), "reference_cg_iterations": meta.get("cg_mg_iters"),
-                       "establish_s": round(establish_s, 2)},
+            "config": {"workload": workload_name(args), "bodies": nb, "interfaces": ni, "body_dof": mc.body_dof, "levels_per_body": nlev,
+                       "total_dof": int(sum(mc.body_dof)), "step": "one MCONTACT::CONTACT_ANALYSIS to convergence (MG-PCG of every subdomain to 1e-14 in every ADMM iteration)",
+                       "smoother": args.smoother, "body_rank": body_rank, "exchange": "per iteration: all-reduce coarse RHS + MONITOR sums, pairwise swap of interface traces (NCCL)" if world > 1 else "none (one rank)",
+                       "l2_policy": f"inputs larger than L2: the rank's finest operators ({sum(weights[v] for v in mine) * 9.33 / 1e6:.0f} MB) are streamed ~5 times per CG iteration vs 126 MB L2"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n, "ms_per_step": ms_e2e_max / args.steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(work[4].item()), "d2h_bytes_per_step": int(work[5].item()),
+                    "ms_per_step": ms_e2e_max / steps if e2e_steps else None},
             "gpu_launches": int(work[2].item()),
+            "admm": {"solve_wall_s": solve_s, "admm_iterations": its, "admm_iter_per_s": its / solve_s, "upload_s": round(upload_s, 2),
+                     "mgpcg_dof_iter_per_s": value, "cg_iterations_per_solve": int(work[3].item()) // steps,
+                     "gpu_launches_per_admm_iteration": round(work[2].item() / max(1, admm_iters) / 1.0, 1),
+                     "reference_set_up_s": round(meta.get("driver_wall_s", 0.0) - sum(meta.get("ref_iter_s", [])), 1),
+                     "parity_rel_err_resuDisp_vs_reference_after_first_iterations": et.item(), "parity_iterations_compared": k_ref,
+                     "reference_admm_iter_per_s": cpu["admm_iter_per_s"] if cpu else None,
+                     "reference_solve_wall_s_at_same_iteration_count": (its / cpu["admm_iter_per_s"]) if cpu else None,
+                     "reference_cores": meta.get("omp_max_threads")},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "kernel_shares": shares,
-            "parity_rel_err_vs_reference": parity,
         }
-        if admm is not None:
-            line["admm"] = admm
         print(json.dumps(line), flush=True)
-    mg.close()
+    mc.close()
     if dist is not None:
         dist.destroy_process_group()
 

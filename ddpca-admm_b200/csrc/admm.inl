@@ -987,6 +987,29 @@ long ddpca_admm_launch_count(ddpca_admm *h, int reset)
     if (reset) h->launches = 0;
     return v;
 }
+// per-kernel-class timing of the batched body solves (ddpca_mg_profile on every batch): enable, run steps, read
+int ddpca_admm_profile(ddpca_admm *h, int enable)
+{
+    if (!h || !h->finalized) return fail("ddpca_admm_profile: handle not finalized");
+    for (Batch &b : h->batch) if (ddpca_mg_profile(b.mg, enable)) return 1;
+    return 0;
+}
+int ddpca_admm_profile_get(ddpca_admm *h, int kclass, int level, double *ms, long *launches, double *bytes)
+{
+    if (!h || !h->finalized) return fail("ddpca_admm_profile_get: handle not finalized");
+    double m = 0.0, by = 0.0;
+    long n = 0;
+    for (Batch &b : h->batch) {
+        double m1 = 0.0, b1 = 0.0;
+        long n1 = 0;
+        if (level < b.mg->nlev && ddpca_mg_profile_get(b.mg, kclass, level, &m1, &n1, &b1)) return 1;
+        m += m1; n += n1; by += b1;
+    }
+    if (ms) *ms = m;
+    if (launches) *launches = n;
+    if (bytes) *bytes = by;
+    return 0;
+}
 // number of batches and, for every body, its CG iteration count in the last step (0 for remote bodies)
 int ddpca_admm_body_iters(const ddpca_admm *h, int *nbatches, long *iters)
 {

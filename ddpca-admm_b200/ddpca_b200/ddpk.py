@@ -50,8 +50,28 @@ class Csr:
         )
 
 
-def load(path: str) -> dict:
-    """Return {name: ndarray}; arrays are copies (aligned, writable)."""
+def load(path: str, copy: bool = True) -> dict:
+    """Return {name: ndarray}; arrays are copies (aligned, writable) or, with copy=False, read-only views of a
+    memory map of the file (large dumps: no second copy in memory, pages shared between processes)."""
+    if not copy and not str(path).endswith(".gz"):
+        blob = np.memmap(path, dtype=np.uint8, mode="r")
+        if bytes(blob[:8]) != _MAGIC:
+            raise ValueError(f"{path}: not a DDPK file")
+        out = {}
+        off = 8
+        n = blob.shape[0]
+        while off < n:
+            (nl,) = struct.unpack_from("<I", blob, off)
+            off += 4
+            name = bytes(blob[off : off + nl]).decode()
+            off += nl
+            dt, cnt = struct.unpack_from("<IQ", blob, off)
+            off += 12
+            off += (8 - off % 8) % 8
+            dtype = _DTYPES[dt]
+            out[name] = np.frombuffer(blob, dtype=dtype, count=cnt, offset=off)
+            off += cnt * dtype.itemsize
+        return out
     if str(path).endswith(".gz"):
         import gzip
 

@@ -363,6 +363,22 @@ class MCONTACT:
     def launch_count(self, reset=False):
         return int(load_library().ddpca_admm_launch_count(self._h, C.c_int(1 if reset else 0)))
 
+    def profile(self, enable: bool):
+        check(load_library().ddpca_admm_profile(self._h, C.c_int(1 if enable else 0)))
+
+    def profile_get(self, nlevels=16):
+        """{(kernel_class, level): (ms, launches, algorithmic_bytes)} of the batched body solves since profile(True)."""
+        from .mgpis import KERNEL_CLASSES
+
+        out = {}
+        for k, name in enumerate(KERNEL_CLASSES):
+            for l in range(nlevels):
+                ms, nl, by = C.c_double(), C.c_long(), C.c_double()
+                check(load_library().ddpca_admm_profile_get(self._h, C.c_int(k), C.c_int(l), C.byref(ms), C.byref(nl), C.byref(by)))
+                if nl.value:
+                    out[(name, l)] = (ms.value, nl.value, by.value)
+        return out
+
     def body_iters(self):
         """(number of batched hierarchies, CG iteration count of every body in the last step)."""
         nbt = C.c_int()

@@ -241,6 +241,9 @@ int ddpca_admm_row_length(const ddpca_admm *);
  * vectors multGrid[v].consForc (host, n_L doubles; copied on the handle's stream). */
 int ddpca_admm_reset(ddpca_admm *);
 int ddpca_admm_set_consforc(ddpca_admm *, int v, const double *consForc);
+/* per-kernel-class timing of the batched body solves, as ddpca_mg_profile / ddpca_mg_profile_get (summed over batches) */
+int ddpca_admm_profile(ddpca_admm *, int enable);
+int ddpca_admm_profile_get(ddpca_admm *, int kclass, int level, double *ms, long *launches, double *bytes);
 /* number of batched hierarchies and the CG iteration count of every body in the last step (0 for remote bodies) */
 int ddpca_admm_body_iters(const ddpca_admm *, int *nbatches, long *iters);
 int ddpca_admm_get_disp(ddpca_admm *, int v, double *resuDisp);

@@ -17,6 +17,8 @@
 #define ADMM_HOOK_H
 #include <unistd.h>
 #include <functional>
+#include <mutex>
+#include <omp.h>
 #include "ddpk_io.h"
 #include "ref_capture.h"
 
@@ -65,24 +67,44 @@ static void DUMP_LDLT(DDPK_WRITER &w, const std::string &name, const DIRE_SOLV &
 	w.i32(name + ".perm", p.data(), p.size());
 }
 
-// Counts the loop's "The <tc>-th iteration" announcements (MCONTACT.h:2505) passing through std::cout and
-// calls `onStop` when announcement number `stopAt` (0-based: the one that opens iteration stopAt) arrives.
-class ITER_STOP_BUF : public std::streambuf {
+// Watches the reference's std::cout traffic during the loop (every write takes a mutex: the reference prints from
+// its OpenMP threads):
+//   * "The <tc>-th iteration" (MCONTACT.h:2505, main thread) -> time stamp; announcement number `stopAt` (the one
+//     that opens iteration stopAt, i.e. after stopAt complete passes incl. MONITOR) triggers `onStop`;
+//   * "#Iteration: <k>" (MGPIS.h:221, one per MGPIS::CG_SOLV call, printed by the thread that ran the solve):
+//     iterNumb = k + 1 is added to the CG iteration total of the current ADMM iteration.  The two tokens arrive
+//     as consecutive writes of ONE thread, so a thread-local flag pairs them even when threads interleave.
+class LOOP_WATCH_BUF : public std::streambuf {
 public:
-	ITER_STOP_BUF(std::streambuf *next, long stopAt, std::function<void()> onStop) : next_(next), stopAt_(stopAt), onStop_(onStop) {}
+	LOOP_WATCH_BUF(std::streambuf *next, long stopAt, std::function<void()> onStop) : next_(next), stopAt_(stopAt), onStop_(onStop) {}
+	std::vector<double> iterStart;      // time stamp of every announcement
+	std::vector<long> cgIters, cgCalls; // per ADMM iteration: sum of iterNumb over the CG_SOLV calls, number of calls
 protected:
 	std::streamsize xsputn(const char *s, std::streamsize n) override {
-		if (std::string(s, (size_t)n).find("-th iteration") != std::string::npos) {
-			if (seen_ == stopAt_) onStop_();
-			seen_++;
+		static thread_local bool expectCount = false;
+		std::string chunk(s, (size_t)n);
+		std::lock_guard<std::mutex> g(mtx_);
+		if (expectCount) {
+			expectCount = false;
+			char *end = nullptr;
+			long k = std::strtol(chunk.c_str(), &end, 10);
+			if (end != chunk.c_str() && !cgIters.empty()) { cgIters.back() += k + 1; cgCalls.back() += 1; }
+		}
+		if (chunk.find("#Iteration: ") != std::string::npos) expectCount = true;
+		if (chunk.find("-th iteration") != std::string::npos) {
+			if (stopAt_ >= 0 && (long)iterStart.size() == stopAt_) { iterStart.push_back(now_s()); onStop_(); }
+			iterStart.push_back(now_s());
+			cgIters.push_back(0);
+			cgCalls.push_back(0);
 		}
 		return next_ ? next_->sputn(s, n) : n;
 	}
 	int overflow(int c) override { return (next_ && c != EOF) ? next_->sputc((char)c) : c; }
 	int sync() override { return next_ ? next_->pubsync() : 0; }
 private:
+	std::mutex mtx_;
 	std::streambuf *next_;
-	long stopAt_, seen_ = 0;
+	long stopAt_;
 	std::function<void()> onStop_;
 };
 
@@ -188,10 +210,27 @@ inline long ADMM_HOOK(MCONTACT &mc) {
 		for (long ts = 0; ts < ni; ts++)   // written by OUTPUT_PRTR in every iteration (MCONTACT.h:2669): the LAST iteration's content
 			if (mc.fricCoef[ts] >= 0.0) DUMP_TABLE(*w, "ref.resuCont" + std::to_string(ts), READ_TABLE(DIRECTORY("resuCont_" + std::to_string(ts) + ".txt")));
 	};
+	auto timing_json = [&](LOOP_WATCH_BUF &wb, double tEnd) {
+		// per ADMM iteration: wall time, CG_SOLV calls and the sum of their iteration counts (iterNumb)
+		std::ostringstream o;
+		o << std::setprecision(9) << ",\"ref_iter_s\":[";
+		for (size_t k = 0; k < wb.cgIters.size(); k++) o << (k ? "," : "") << ((k + 1 < wb.iterStart.size() ? wb.iterStart[k + 1] : tEnd) - wb.iterStart[k]);
+		o << "],\"ref_cg_iters\":[";
+		for (size_t k = 0; k < wb.cgIters.size(); k++) o << (k ? "," : "") << wb.cgIters[k];
+		o << "],\"ref_cg_calls\":[";
+		for (size_t k = 0; k < wb.cgCalls.size(); k++) o << (k ? "," : "") << wb.cgCalls[k];
+		o << "],\"omp_max_threads\":" << omp_get_max_threads();
+		return o.str();
+	};
 	if (g_admmOpts.refIters == 0) {
 		double t0 = now_s();
+		std::streambuf *prev0 = std::cout.rdbuf();
+		LOOP_WATCH_BUF watch0(prev0, -1, []() {});
+		std::cout.rdbuf(&watch0);
 		(mc.CONTACT_ANALYSIS)();     // parenthesised: not the function-like macro below
+		std::cout.rdbuf(prev0);
 		double dt = now_s() - t0;
+		js << timing_json(watch0, now_s());
 		js << ",\"ref_iterNumbReco\":" << mc.iterNumbReco << ",\"ref_admm_s\":" << dt << ",\"ref_MULT_MAXI\":" << MULT_MAXI;
 		js << ",\"ref_disp_norm\":[";
 		for (long v = 0; v < nb; v++) js << (v ? "," : "") << mc.resuDisp[v].norm();
@@ -205,19 +244,21 @@ inline long ADMM_HOOK(MCONTACT &mc) {
 		double t0 = now_s();
 		std::string head = js.str();
 		std::streambuf *prev = std::cout.rdbuf();
-		ITER_STOP_BUF stopper(prev, g_admmOpts.refIters, [&]() {
+		LOOP_WATCH_BUF *self = nullptr;
+		LOOP_WATCH_BUF stopper(prev, g_admmOpts.refIters, [&]() {
 			if (w) { w->scalar_i64("ref.first_iters", g_admmOpts.refIters); dump_state(); delete w; }
 			std::ostringstream o;
 			o << std::setprecision(17) << head << ",\"ref_first_iters\":" << g_admmOpts.refIters << ",\"ref_first_iters_s\":" << now_s() - t0
-			  << ",\"ref_MULT_MAXI\":" << MULT_MAXI << g_admmOpts.jsonTail << "}";
+			  << ",\"ref_MULT_MAXI\":" << MULT_MAXI << timing_json(*self, now_s()) << g_admmOpts.jsonTail << "}";
 			std::printf("%s\n", o.str().c_str());
 			std::fflush(stdout);
 			_exit(0);
 		});
+		self = &stopper;
 		std::cout.rdbuf(&stopper);
 		(mc.CONTACT_ANALYSIS)();
 		std::cout.rdbuf(prev);
-		js << ",\"ref_iterNumbReco\":" << mc.iterNumbReco << ",\"ref_admm_s\":" << now_s() - t0;   // converged before K iterations
+		js << ",\"ref_iterNumbReco\":" << mc.iterNumbReco << ",\"ref_admm_s\":" << now_s() - t0 << timing_json(stopper, now_s());   // converged before K iterations
 		if (w) w->scalar_i64("ref.iterNumbReco", mc.iterNumbReco);
 		dump_state();
 	}

