@@ -428,16 +428,10 @@ static int admm_monitor(ddpca_admm *h)
     KL(h, DDPCA_K_VECTOR, 15, 0.0, (k_moni_slots<<<cdiv(h->nslots, 128), 128, 0, h->stream>>>(h->nslots, h->slot_chunk_d, h->moni_part, moni_buf(h))));
     return 0;
 }
-// row of resuMoni.txt (:2742-2743, :2777-2778, :2807-2808, :2835) from the (all-reduced) sums
-static int admm_row(ddpca_admm *h, double *monitor_row)
+// row of resuMoni.txt (:2742-2743, :2777-2778, :2807-2808, :2835) from the sums in h->moni_host
+static void admm_format_row(ddpca_admm *h, double *monitor_row)
 {
-    CU(cudaMemcpyAsync(h->moni_host, moni_buf(h), sizeof(double) * 2 * h->nslots, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    CU(cudaGetLastError());
-    if (admm_bodies_finish(h)) return 1;
-    if (!h->launch_err.empty()) { std::string m = h->launch_err; h->launch_err.clear(); return fail(m); }
-    if (h->profile) h->prof_collect();
-    if (!monitor_row) return 0;
+    if (!monitor_row) return;
     double convValu = 0.0, convCrit = 0.0;
     int c = 0;
     for (int v = 0; v < h->nb; v++) {
@@ -458,6 +452,17 @@ static int admm_row(ddpca_admm *h, double *monitor_row)
         }
     monitor_row[c++] = convValu;
     monitor_row[c++] = convCrit;
+}
+// wait for the iteration, fetch the (all-reduced) MONITOR sums, assemble the row
+static int admm_row(ddpca_admm *h, double *monitor_row)
+{
+    CU(cudaMemcpyAsync(h->moni_host, moni_buf(h), sizeof(double) * 2 * h->nslots, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    if (admm_bodies_finish(h)) return 1;
+    if (!h->launch_err.empty()) { std::string m = h->launch_err; h->launch_err.clear(); return fail(m); }
+    if (h->profile) h->prof_collect();
+    admm_format_row(h, monitor_row);
     return 0;
 }
 

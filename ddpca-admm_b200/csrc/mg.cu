@@ -1858,3 +1858,4 @@ int ddpca_mg_last_timing(ddpca_mg *h, double *solve_ms, double *h2d_ms, double *
 }  // extern "C"
 
 #include "admm.inl"
+#include "group.inl"

@@ -253,6 +253,28 @@ int ddpca_admm_get_gamma(ddpca_admm *, int ts, double *inpoGamm, int *fricStat);
 long ddpca_admm_launch_count(ddpca_admm *, int reset);
 int ddpca_admm_destroy(ddpca_admm *);
 
+/* ---- one process, several GPUs -----------------------------------------------------
+ * The reference spreads the bodies of the loop over host threads (`#pragma omp parallel for`, MCONTACT.h:2511,2629,2689).
+ * A group is that idea with devices: member k is an ordinary ddpca_admm handle on devices[k] that owns the bodies with
+ * body_rank[v] == k (and their interface sides).  Fill the members with the setters above -- set_body / set_side_op /
+ * set_side_solver on the owner (solvers created on the owner's device), set_interface and the coarse solvers on EVERY
+ * member -- then ddpca_admm_group_finalize.  ddpca_admm_group_step issues one iteration on all members and moves the
+ * exchanges itself over NVLink peer copies ordered by events: coarse right-hand side to member 0, fixed-order sum, back;
+ * signed side traces of shared interfaces straight into the partner's receive buffer (pairwise); MONITOR sums to the host.
+ * State is read from the owner: ddpca_admm_get_disp(ddpca_admm_group_member(g, ddpca_admm_group_owner(g, v)), v, out). */
+typedef struct ddpca_admm_group ddpca_admm_group;
+/* greedy bin packing of bodies onto ranks by weight (e.g. nnz of the finest operator); contBody[2 ts + 0..1] */
+int ddpca_partition_bodies(int nbody, const double *weight, int niface, const int *contBody, int nranks, int *body_rank);
+int ddpca_admm_group_create(int ndev, const int *devices, int nbody, int niface, int muscSett, const int *body_rank, ddpca_admm_group **out);
+int ddpca_admm_group_size(const ddpca_admm_group *);
+ddpca_admm *ddpca_admm_group_member(ddpca_admm_group *, int k);
+int ddpca_admm_group_owner(const ddpca_admm_group *, int v);      /* member index of body v */
+int ddpca_admm_group_device(const ddpca_admm_group *, int k);     /* CUDA device of member k */
+int ddpca_admm_group_finalize(ddpca_admm_group *);
+int ddpca_admm_group_step(ddpca_admm_group *, int apply_macro, double *monitor_row, long *cg_iters, double *cg_dof_iters);
+long ddpca_admm_group_launch_count(ddpca_admm_group *, int reset);
+int ddpca_admm_group_destroy(ddpca_admm_group *);                 /* destroys the members, too */
+
 /* ---- introspection / measurement -------------------------------------------*/
 /* rows, nnz, number of row groups and stages of a level's device layout */
 int ddpca_mg_level_info(const ddpca_mg *, int level, long *n, long *nnz, int *ngroups, int *nstages);
