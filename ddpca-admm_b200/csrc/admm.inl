@@ -627,6 +627,7 @@ int ddpca_admm_finalize(ddpca_admm *h)
     if (h->finalized) return 0;
     CU(cudaSetDevice(h->device));
     const int nb = h->nb, ni = h->ni;
+    StageTimer tm("admm finalize");
     // ---- completeness --------------------------------------------------------------------------
     for (int v = 0; v < nb; v++) {
         HostBody &b = h->body[v];
@@ -728,6 +729,7 @@ int ddpca_admm_finalize(ddpca_admm *h)
             return 1;
         }
     }
+    tm.lap("batched hierarchies");
     // ---- vectors -------------------------------------------------------------------------------------
     if (dev_vec(nullptr, ncols, &h->state) || dev_vec(nullptr, 2 * h->NC + h->NF, &h->state_prev) || dev_vec(nullptr, h->NF, &h->addi) ||
         dev_vec(nullptr, h->NR, &h->rhs) || dev_vec(nullptr, h->NR, &h->u) || dev_vec(nullptr, h->NC, &h->force) || dev_vec(nullptr, h->NC, &h->tmp) ||
@@ -784,6 +786,7 @@ int ddpca_admm_finalize(ddpca_admm *h)
         if ((h->muscSett & 2) && stack_upload(h->nglob1, ncols, G1, h->OPG1)) return 1;
         if ((h->muscSett & 3) && stack_upload(h->NR, std::max(h->nglob, h->nglob1), AC, h->ACCU)) return 1;
     }
+    tm.lap("stacked operators");
     if (h->muscSett & 3) { if (dev_vec(nullptr, std::max(h->nglob, h->nglob1), &h->globForc)) return 1; }
     if (h->muscSett & 1) { if (dev_vec(nullptr, h->nglob, &h->globSolu)) return 1; }
     if (h->muscSett & 2) { if (dev_vec(nullptr, h->nglob1, &h->globSolu1)) return 1; }
@@ -992,6 +995,36 @@ long ddpca_admm_launch_count(ddpca_admm *h, int reset)
     if (reset) h->launches = 0;
     return v;
 }
+// kernel-level entry (parity tests): the projection kernel of the loop on host arrays
+int ddpca_gamma_project(int device, int nip, int d, double fricCoef, const double *t, const double *gapTerm, double *inpoGamm, int *fricStat)
+{
+    if (nip < 0 || (d != 1 && d != 3) || !t || !gapTerm || !inpoGamm || !fricStat) return fail("ddpca_gamma_project: bad argument");
+    int ndev = ddpca_device_count();
+    if (ndev == 0) return fail("no CUDA device: libddpca_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("device index out of range");
+    CU(cudaSetDevice(device));
+    const size_t n = (size_t)d * nip;
+    double *dt = nullptr, *dg = nullptr, *dgam = nullptr;
+    int *dst = nullptr;
+    IfaceMeta *dm = nullptr;
+    auto cleanup = [&]() { cudaFree(dt); cudaFree(dg); cudaFree(dgam); cudaFree(dst); cudaFree(dm); };
+    IfaceMeta m{0, nip, d, 0, fricCoef};
+    CUX(cudaMalloc(&dt, sizeof(double) * std::max<size_t>(1, n)));
+    CUX(cudaMalloc(&dg, sizeof(double) * std::max<size_t>(1, n)));
+    CUX(cudaMalloc(&dgam, sizeof(double) * std::max<size_t>(1, n)));
+    CUX(cudaMalloc(&dst, sizeof(int) * std::max<size_t>(1, n)));
+    CUX(cudaMalloc(&dm, sizeof(IfaceMeta)));
+    CUX(cudaMemcpy(dt, t, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CUX(cudaMemcpy(dg, gapTerm, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CUX(cudaMemcpy(dm, &m, sizeof(IfaceMeta), cudaMemcpyHostToDevice));
+    k_gamma_project_all<<<cdiv(std::max(nip, 1), 256), 256>>>(1, dm, dt, dg, dgam, dst);
+    CUX(cudaMemcpy(inpoGamm, dgam, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CUX(cudaMemcpy(fricStat, dst, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    CUX(cudaGetLastError());
+    cleanup();
+    return 0;
+}
+
 // per-kernel-class timing of the batched body solves (ddpca_mg_profile on every batch): enable, run steps, read
 int ddpca_admm_profile(ddpca_admm *h, int enable)
 {

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -256,6 +257,17 @@ static int alloc_vec(double **d, long n)
 }
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// DDPCA_VERBOSE: wall-clock stages of the set-up on stderr
+struct StageTimer {
+    bool on;
+    double t0, last;
+    const char *what;
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    explicit StageTimer(const char *w) : on(std::getenv("DDPCA_VERBOSE") != nullptr), t0(now()), last(t0), what(w) {}
+    void lap(const char *stage) { if (!on) return; double t = now(); std::fprintf(stderr, "ddpca set-up [%s] %-28s %8.3f s\n", what, stage, t - last); last = t; }
+    ~StageTimer() { if (on) std::fprintf(stderr, "ddpca set-up [%s] total %8.3f s\n", what, now() - t0); }
+};
 
 // ---- kernel launch helpers (all on h->stream) ----------------------------------------------
 static void launch_spmv(Engine *h, int kclass, int lvl, const DevCsr &A, const double *x, double *y, bool add,
@@ -1266,6 +1278,8 @@ static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const
         if (acc > 0x7ffffff0L) { ddpca_mg_destroy(h); return fail("batch too large for 32-bit indices: split it into several batches"); }
         h->sub_off[l][nsub] = (int)acc;
     }
+    StageTimer tm("hierarchy");
+    double t_cat = 0, t_lvl = 0, t_p = 0;
     int nmax = 0;
     std::vector<int> rs(nsub), cs(nsub);
     std::vector<const int *> prp(nsub), pci(nsub);
@@ -1279,16 +1293,21 @@ static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const
         CsrHost cat;
         const int *rp = rowptr[l], *ci = colidx[l];
         const double *vv = val[l];
+        double ta = StageTimer::now();
         if (nsub > 1) {
             for (int s = 0; s < nsub; s++) { rs[s] = n[s * nlevels + l]; prp[s] = rowptr[s * nlevels + l]; pci[s] = colidx[s * nlevels + l]; pv[s] = val[s * nlevels + l]; }
             FAILC(concat_block_diag(nsub, rs.data(), rs.data(), prp.data(), pci.data(), pv.data(), cat));
             rp = cat.rp.data(); ci = cat.ci.data(); vv = cat.v.data();
         }
+        double tb = StageTimer::now();
+        t_cat += tb - ta;
         if (setup_level(L, ntot, rp, ci, vv, mode, /*keep_csr=*/l == 0, /*group_layout=*/!coarse_only)) {
             g_err = "level " + std::to_string(l) + ": " + g_err;
             ddpca_mg_destroy(h);
             return 1;
         }
+        double tc = StageTimer::now();
+        t_lvl += tc - tb;
         if (l >= 1) {
             CsrHost Pcat, Pp, Rp;
             const int *prp0 = P_rowptr[l - 1], *pci0 = P_colidx[l - 1];
@@ -1309,8 +1328,11 @@ static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const
             transpose_csr(Pp, Rp);
             FAILC(upload_csr(Pp, L.P));
             FAILC(upload_csr(Rp, L.R));
+            t_p += StageTimer::now() - tc;
         }
     }
+    if (tm.on) std::fprintf(stderr, "ddpca set-up [hierarchy] %d subs, %d levels, %d rows: concatenate %.3f s, plan+layout+upload %.3f s, transfers %.3f s\n", nsub, nlevels, nmax, t_cat, t_lvl, t_p);
+    tm.lap("levels");
     FAILC(alloc_vec(&h->cg_r, nmax) || alloc_vec(&h->cg_p, nmax) || alloc_vec(&h->cg_q, nmax) || alloc_vec(&h->cg_z, nmax) ||
           alloc_vec(&h->cg_x, nmax) || alloc_vec(&h->stage_a, nmax) || alloc_vec(&h->stage_b, nmax));
     CUC(cudaMalloc(&h->st, sizeof(PcgState) * nsub));
@@ -1369,6 +1391,7 @@ static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const
         for (int s = 0; s < nsub; s++) bptr[s] = h->Binv + boff[s];
         FAILC(upload_vec(h->sub_off[0], &h->sub0_off_d) || upload_vec(bptr, &h->binv_ptr_d));
     }
+    tm.lap("level-0 dense inverses");
     // capture + instantiate the V-cycle-preconditioned solve graph now (set-up time), not in the first solve
     build_solve_graph(h, 1);
     if (h->while_state[1] != 1) FAILC(build_iter_graph(h, 1));

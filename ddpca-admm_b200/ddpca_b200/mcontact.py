@@ -92,6 +92,20 @@ def _factor_from_dump(d, name, device, fallback_matrix=None, factorize=None):
     return DIRE_SOLV(perm, L, D, device)
 
 
+def gamma_project(t, gapTerm, fricCoef: float, device: int = 0):
+    """The loop's projection kernel on host arrays (kernel-level parity entry, ddpca_gamma_project):
+    inpoGamm = proj(0.5 (t - gapTerm)) and fricStat, MCONTACT.h:2636-2668."""
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    gap = np.ascontiguousarray(gapTerm, dtype=np.float64)
+    d = 1 if fricCoef == 0.0 else 3
+    nip = t.shape[0] // d
+    g = np.empty_like(t)
+    st = np.empty(t.shape[0], dtype=np.int32)
+    check(load_library().ddpca_gamma_project(C.c_int(device), C.c_int(nip), C.c_int(d), C.c_double(fricCoef), _pd(t), _pd(gap), _pd(g),
+                                             st.ctypes.data_as(C.POINTER(C.c_int))))
+    return g, st
+
+
 class MCONTACT:
     """Multibody contact / domain decomposition ADMM solver on a B200.
 

@@ -66,9 +66,29 @@ inline bool UPLOAD_OP(ddpca_admm *hand, long ts, long tv, int opid, const SPM &m
 
 }// namespace ddpca_host
 
+// devices of the run: DDPCA_DEVICES="0,1,2,3" (one process, several GPUs: the bodies are bin-packed over them by the
+// size of their finest operator, include/ddpca_b200.h "one process, several GPUs"), else the single DDPCA_DEVICE
+inline std::vector<int> DDPCA_DEVICE_LIST(){
+	std::vector<int> resu;
+	const char *envi = std::getenv("DDPCA_DEVICES");
+	if(envi != nullptr && envi[0] != 0){
+		std::stringstream tempStre(envi);
+		std::string item;
+		while(std::getline(tempStre, item, ',')){
+			if(!item.empty()){
+				resu.push_back(std::atoi(item.c_str()));
+			}
+		}
+	}
+	if(resu.empty()){
+		resu.push_back(MGPIS::DEVICE());
+	}
+	return resu;
+}
+
 inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 	using namespace ddpca_host;
-	const int devi = MGPIS::DEVICE();
+	const std::vector<int> deviList = DDPCA_DEVICE_LIST();
 	const long bodyNumb = mc.multGrid.size(), inteNumb = mc.searCont.size();
 	const bool macrSwit = ((mc.muscSett >> 0) % 2 == 1);
 	const bool elimSwit = ((mc.muscSett >> 1) % 2 == 1);// interface-eliminated coarse problem, MCONTACT.h:2575-2607
@@ -77,14 +97,30 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 			<< "is not offered by the B200 build" << std::endl;
 		return -1;
 	}
-	ddpca_admm *hand = nullptr;
-	if(ddpca_admm_create(devi, bodyNumb, inteNumb, (macrSwit ? 1 : 0) | (elimSwit ? 2 : 0), &hand) != 0
-		|| ddpca_admm_set_smoother(hand, MGPIS::SMOOTHER()) != 0){
+	//bodies -> devices (balanced groups; the reference's omp loop over bodies, MCONTACT.h:2511)
+	std::vector<double> bodyWeig(bodyNumb);
+	std::vector<int> contPair(2 * inteNumb), bodyRank(bodyNumb, 0);
+	for(long tv = 0; tv < bodyNumb; tv ++){
+		bodyWeig[tv] = mc.multGrid[tv].mgpi.consStif[mc.multGrid[tv].mgpi.maxiLeve].nonZeros();
+	}
+	for(long ts = 0; ts < inteNumb; ts ++){
+		contPair[2 * ts + 0] = mc.contBody[ts][0];
+		contPair[2 * ts + 1] = mc.contBody[ts][1];
+	}
+	ddpca_admm_group *grou = nullptr;
+	if(ddpca_partition_bodies(bodyNumb, bodyWeig.data(), inteNumb, contPair.data(), deviList.size(), bodyRank.data()) != 0
+		|| ddpca_admm_group_create(deviList.size(), deviList.data(), bodyNumb, inteNumb,
+			(macrSwit ? 1 : 0) | (elimSwit ? 2 : 0), bodyRank.data(), &grou) != 0){
 		FAIL("create"); return -1;
 	}
+	const long membNumb = ddpca_admm_group_size(grou);
 	bool allGood = true;
+	for(long tk = 0; tk < membNumb; tk ++){
+		allGood = allGood && ddpca_admm_set_smoother(ddpca_admm_group_member(grou, tk), MGPIS::SMOOTHER()) == 0;
+	}
 	//******************************** upload (once) ********************************************
 	for(long tv = 0; tv < bodyNumb && allGood; tv ++){
+		ddpca_admm *hand = ddpca_admm_group_member(grou, bodyRank[tv]);
 		MULTIGRID &mugr = mc.multGrid[tv];
 		const long maxiLeve = mugr.mgpi.maxiLeve;
 		// ADDITIONAL_FORCE as one operator (MULTIGRID.h:1257-1261); OUTP_SUB1 = its transpose + constant
@@ -94,7 +130,7 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 		Eigen::VectorXd dispCons;
 		mugr.OUTP_SUB1(Eigen::VectorXd::Zero(forcOper.rows()), dispCons);
 		// the hierarchy goes over as plain arrays: ddpca_admm_finalize builds ONE batched device hierarchy for
-		// all bodies with the same level count (the members of mgpi stay untouched until then)
+		// all bodies of a device with the same level count (the members of mgpi stay untouched until then)
 		MGPIS::POINTERS poin;
 		mugr.mgpi.HIERARCHY_POINTERS(poin);
 		if(ddpca_admm_set_body(hand, tv, maxiLeve + 1, poin.n.data(), poin.rp.data(), poin.ci.data(),
@@ -123,12 +159,16 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 	}
 	for(long ts = 0; ts < inteNumb && allGood; ts ++){
 		Eigen::VectorXd gapTerm = mc.pemaInpo[ts] * mc.inpoNgap[ts];// MCONTACT.h:2636
-		if(ddpca_admm_set_interface(hand, ts, mc.contBody[ts][0], mc.contBody[ts][1], mc.fricCoef[ts],
-			mc.searCont[ts].intePoin.size(), gapTerm.data()) != 0){
-			allGood = FAIL("set_interface");
-			break;
+		for(long tk = 0; tk < membNumb && allGood; tk ++){// every member knows every interface
+			if(ddpca_admm_set_interface(ddpca_admm_group_member(grou, tk), ts, mc.contBody[ts][0], mc.contBody[ts][1],
+				mc.fricCoef[ts], mc.searCont[ts].intePoin.size(), gapTerm.data()) != 0){
+				allGood = FAIL("set_interface");
+			}
 		}
 		for(long tv = 0; tv < 2 && allGood; tv ++){
+			const long ownr = bodyRank[mc.contBody[ts][tv]];// the side lives with its body
+			ddpca_admm *hand = ddpca_admm_group_member(grou, ownr);
+			const int devi = ddpca_admm_group_device(grou, ownr);
 			allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_SYSTTRAN, mc.systTran[ts][tv]);
 			allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_SYSTTRAN_PENA, mc.systTran_pena[ts][tv]);
 			allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_INTEMASS, mc.inteMass[ts][tv]);
@@ -158,33 +198,41 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 			}
 		}
 	}
-	if(allGood && macrSwit){
-		if(mc.globCoup.rows() < DIRE_MAXI){// MCONTACT.h:2553-2555
-			ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D, mc.globCoup);
-			if(soCo == nullptr || ddpca_admm_set_macro(hand, mc.globCoup.rows(), mc.baseReco.data(), soCo) != 0){
-				allGood = FAIL("set_macro");
+	for(long tk = 0; tk < membNumb && allGood; tk ++){// the coarse problems are solved redundantly on every device
+		ddpca_admm *hand = ddpca_admm_group_member(grou, tk);
+		const int devi = ddpca_admm_group_device(grou, tk);
+		if(macrSwit){
+			if(mc.globCoup.rows() < DIRE_MAXI){// MCONTACT.h:2553-2555
+				ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D, mc.globCoup);
+				if(soCo == nullptr || ddpca_admm_set_macro(hand, mc.globCoup.rows(), mc.baseReco.data(), soCo) != 0){
+					allGood = FAIL("set_macro");
+				}
+			}
+			else{// MCONTACT.h:2560-2562: mgpi.CG_SOLV(1, globForc, globSolu), hierarchy of DOUBLE_M (:1538-1670)
+				//(COGR_MAXI < DIRE_MAXI, PREP.h:69,73: the Eigen-CG branch :2556-2558 is unreachable)
+				MGPIS::POINTERS poin;
+				mc.mgpi.HIERARCHY_POINTERS(poin);
+				ddpca_mg *mgHand = nullptr;
+				if(ddpca_mg_create(devi, mc.mgpi.maxiLeve + 1, poin.n.data(), poin.rp.data(), poin.ci.data(),
+					poin.va.data(), poin.prp.data(), poin.pci.data(), poin.pva.data(), MGPIS::SMOOTHER(), &mgHand) != 0
+					|| ddpca_admm_set_macro_mg(hand, mc.globCoup.rows(), mc.baseReco.data(), mgHand) != 0){
+					allGood = FAIL("set_macro_mg");
+				}
 			}
 		}
-		else{// MCONTACT.h:2560-2562: mgpi.CG_SOLV(1, globForc, globSolu), hierarchy of DOUBLE_M (:1538-1670)
-			//(COGR_MAXI < DIRE_MAXI, PREP.h:69,73: the Eigen-CG branch :2556-2558 is unreachable)
-			ddpca_mg *mgHand = mc.mgpi.RELEASE_HANDLE();
-			if(mgHand == nullptr || ddpca_admm_set_macro_mg(hand, mc.globCoup.rows(), mc.baseReco.data(), mgHand) != 0){
-				allGood = FAIL("set_macro_mg");
+		if(allGood && elimSwit){// MCONTACT.h:2576,2588
+			ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D_1, mc.globCoup_1);
+			if(soCo == nullptr || ddpca_admm_set_macro1(hand, mc.globCoup_1.rows(), mc.baseReco.data(),
+				mc.globForc_1.data(), soCo) != 0){
+				allGood = FAIL("set_macro1");
 			}
 		}
 	}
-	if(allGood && elimSwit){// MCONTACT.h:2576,2588
-		ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D_1, mc.globCoup_1);
-		if(soCo == nullptr || ddpca_admm_set_macro1(hand, mc.globCoup_1.rows(), mc.baseReco.data(),
-			mc.globForc_1.data(), soCo) != 0){
-			allGood = FAIL("set_macro1");
-		}
-	}
-	if(allGood && ddpca_admm_finalize(hand) != 0){
+	if(allGood && ddpca_admm_group_finalize(grou) != 0){
 		allGood = FAIL("finalize");
 	}
 	if(!allGood){
-		ddpca_admm_destroy(hand);
+		ddpca_admm_group_destroy(grou);
 		return -1;
 	}
 	//******************************** the loop, MCONTACT.h:2494-2712 ***************************
@@ -197,15 +245,15 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 	const long maxiIter = 3000;
 	std::ofstream tempOfst(DIRECTORY("resuMoni.txt"), std::ios::out);
 	tempOfst << std::setiosflags(std::ios::scientific) << std::setprecision(20);
-	std::vector<double> moniRow(ddpca_admm_row_length(hand));
+	std::vector<double> moniRow(ddpca_admm_row_length(ddpca_admm_group_member(grou, 0)));
 	for(tc = 0; tc < maxiIter; tc ++){
 		std::cout << "The " << tc << "-th iteration";
 		OUTPUT_TIME("");
 		const int applMacr = ((macrSwit || elimSwit) && tc <= MULT_MAXI) ? 1 : 0;// :2540, :2575
 		long cgitNumb = 0;
-		if(ddpca_admm_step(hand, applMacr, moniRow.data(), &cgitNumb, nullptr) != 0){
+		if(ddpca_admm_group_step(grou, applMacr, moniRow.data(), &cgitNumb, nullptr) != 0){
 			FAIL("step");
-			ddpca_admm_destroy(hand);
+			ddpca_admm_group_destroy(grou);
 			return -1;
 		}
 		//stopping criterion: MONITOR (:2725-2845) on the sums computed by the device
@@ -268,20 +316,21 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 	//******************************** state back to the host members *****************************
 	for(long tv = 0; tv < bodyNumb; tv ++){
 		mc.resuDisp[tv].resize(3 * mc.multGrid[tv].nodeCoor.size());
-		ddpca_admm_get_disp(hand, tv, mc.resuDisp[tv].data());
+		ddpca_admm_get_disp(ddpca_admm_group_member(grou, bodyRank[tv]), tv, mc.resuDisp[tv].data());
 	}
 	for(long ts = 0; ts < inteNumb; ts ++){
 		for(long tv = 0; tv < 2; tv ++){
-			ddpca_admm_get_side(hand, ts, tv, mc.inteAuxi[ts][tv].data(), mc.inteLagr[ts][tv].data());
+			ddpca_admm_get_side(ddpca_admm_group_member(grou, bodyRank[mc.contBody[ts][tv]]), ts, tv,
+				mc.inteAuxi[ts][tv].data(), mc.inteLagr[ts][tv].data());
 		}
 		//final contact pressure/traction file, what OUTPUT_PRTR writes each iteration (:2669)
 		const long gammSize = ((mc.fricCoef[ts] == 0.0) ? 1 : 3) * mc.searCont[ts].intePoin.size();
 		Eigen::VectorXd inpoGamm(gammSize);
 		Eigen::VectorXi fricStat(gammSize);
-		ddpca_admm_get_gamma(hand, ts, inpoGamm.data(), fricStat.data());
+		ddpca_admm_get_gamma(ddpca_admm_group_member(grou, bodyRank[mc.contBody[ts][0]]), ts, inpoGamm.data(), fricStat.data());
 		mc.OUTPUT_PRTR(inpoGamm, fricStat, ts);
 	}
-	ddpca_admm_destroy(hand);
+	ddpca_admm_group_destroy(grou);
 	if(tc >= maxiIter){
 		std::cout << "Nonconvergence in MCONTACT::CONTACT_ANALYSIS";
 	}

@@ -241,6 +241,10 @@ int ddpca_admm_row_length(const ddpca_admm *);
  * vectors multGrid[v].consForc (host, n_L doubles; copied on the handle's stream). */
 int ddpca_admm_reset(ddpca_admm *);
 int ddpca_admm_set_consforc(ddpca_admm *, int v, const double *consForc);
+/* kernel-level entry for parity tests: the contact projection of the interface block (MCONTACT.h:2636-2668) on host
+ * arrays: inpoGamm = proj(0.5 (t - gapTerm)), d = 1 (fricCoef == 0) or 3 components per integration point, fricStat as
+ * OUTPUT_PRTR writes it (0 open / 1 slide / 2 stick in the second component's slot, MCONTACT.h:118,2656-2665) */
+int ddpca_gamma_project(int device, int nip, int d, double fricCoef, const double *t, const double *gapTerm, double *inpoGamm, int *fricStat);
 /* per-kernel-class timing of the batched body solves, as ddpca_mg_profile / ddpca_mg_profile_get (summed over batches) */
 int ddpca_admm_profile(ddpca_admm *, int enable);
 int ddpca_admm_profile_get(ddpca_admm *, int kclass, int level, double *ms, long *launches, double *bytes);

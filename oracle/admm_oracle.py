@@ -28,6 +28,33 @@ def vect_medi_osci(v):
     return (mx + mn) / 2.0, mx - mn
 
 
+def contact_projection(g, mu):
+    """The contact projection of the interface block, MCONTACT.h:2637-2668, on gamma = 0.5 (trace - gapTerm):
+    mu < 0 tied (nothing), mu == 0 frictionless (one component per point, clamp), mu > 0 Coulomb (three components
+    per point: normal clamp, tangential pair scaled back onto the cone; status 0 open / 1 slide / 2 stick in the
+    second component's slot, as OUTPUT_PRTR writes it, :118).  Returns (gamma, fricStat).
+    Pinned to the reference's DEHW run by tests/test_oracle_golden.py (tests/golden/dehw_friction.ddpk.gz)."""
+    stat = np.zeros(g.shape[0], dtype=np.int32)
+    if mu == 0.0:
+        g = np.maximum(0.0, g)  # :2640
+    elif mu > 0.0:
+        g = g.copy()
+        g[0::3] = np.maximum(0.0, g[0::3])  # :2643
+        gn = g[0::3]
+        t1, t2 = g[1::3].copy(), g[2::3].copy()
+        nrm = np.sqrt(t1 * t1 + t2 * t2)
+        slid = mu * gn
+        open_ = ~(gn > 0.0)
+        slide = (gn > 0.0) & (nrm >= slid)  # :2653
+        with np.errstate(divide="ignore", invalid="ignore"):
+            fac = np.where(slide, slid / nrm, 1.0)
+        t1 = np.where(open_, 0.0, t1 * fac)  # :2654-2655, :2663-2664
+        t2 = np.where(open_, 0.0, t2 * fac)
+        g[1::3], g[2::3] = t1, t2
+        stat[1::3] = np.where(open_, 0, np.where(slide, 1, 2))  # :2656-2665
+    return g, stat
+
+
 class AdmmOracle:
     def __init__(self, d: dict):
         self.nb = int(d["nbody"][0])
@@ -147,24 +174,7 @@ class AdmmOracle:
             g = 0.5 * (s0["inpoLagr"] @ self.inteLagr[ts][0] - s1["inpoLagr"] @ self.inteLagr[ts][1] + s0["pemaInpo_r"] @ u0 - s1["pemaInpo_r"] @ u1 - it["gapTerm"])  # :2632-2636
             mu = it["fricCoef"]
             nip = it["nip"]
-            stat = np.zeros(g.shape[0], dtype=np.int32)
-            if mu == 0.0:
-                g = np.maximum(0.0, g)  # :2640
-            elif mu > 0.0:
-                g = g.copy()
-                g[0::3] = np.maximum(0.0, g[0::3])  # :2643
-                gn = g[0::3]
-                t1, t2 = g[1::3].copy(), g[2::3].copy()
-                nrm = np.sqrt(t1 * t1 + t2 * t2)
-                slid = mu * gn
-                open_ = ~(gn > 0.0)
-                slide = (gn > 0.0) & (nrm >= slid)  # :2653
-                with np.errstate(divide="ignore", invalid="ignore"):
-                    fac = np.where(slide, slid / nrm, 1.0)
-                t1 = np.where(open_, 0.0, t1 * fac)  # :2654-2655, :2663-2664
-                t2 = np.where(open_, 0.0, t2 * fac)
-                g[1::3], g[2::3] = t1, t2
-                stat[1::3] = np.where(open_, 0, np.where(slide, 1, 2))  # :2656-2665
+            g, stat = contact_projection(g, mu)  # :2637-2668
             assert g.shape[0] == (nip if mu == 0.0 else 3 * nip)
             self.inpoGamm[ts], self.fricStat[ts] = g, stat
             for tv, s in enumerate(it["side"]):

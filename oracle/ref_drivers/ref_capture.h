@@ -19,6 +19,7 @@
 class LOCKED_TEXT_BUF : public std::streambuf {
 public:
 	std::string text() { std::lock_guard<std::mutex> g(mtx_); return text_; }
+	std::string str() { return text(); }   // like std::stringstream::str()
 	void str(const std::string &t) { std::lock_guard<std::mutex> g(mtx_); text_ = t; }   // reset, like std::stringstream::str("")
 protected:
 	std::streamsize xsputn(const char *s, std::streamsize n) override {

@@ -175,3 +175,45 @@ def torsion_tangential_displacement(d, disp):
             th = np.arctan2(xyz[m, 1], xyz[m, 0])
             vals += list(-u[m, 0] * np.sin(th) + u[m, 1] * np.cos(th))
     return np.array(vals)
+
+
+def dehw_friction_cases():
+    """Replays the trace of the reference's DEHW interface block from tests/golden/dehw_friction.ddpk.gz (built by
+    tests/golden/make_dehw_friction_fixture.py from a 260-iteration run of the untouched reference).  Yields, per
+    frictional interface, (fricCoef, t, gapTerm, resuCont rows) for the sampled integration points, where
+    t = inpoLagr0 l0 - inpoLagr1 l1 + pemaInpo_r0 u0 - pemaInpo_r1 u1 (MCONTACT.h:2632-2635) is evaluated with the
+    multipliers of BEFORE the last update, l_{K-1} = l_K - M^-1 (S_p^T u_K - M_p aux_K) (MCONTACT.h:2691-2697)."""
+    import scipy.sparse.linalg as spla
+
+    d = ddpk.load(os.path.join(GOLDEN, "dehw_friction.ddpk.gz"))
+    for k in range(int(d["niface"][0])):
+        q = f"f{k}."
+        t = 0.0
+        for tv in range(2):
+            s = q + f"s{tv}."
+            M = ddpk.get_csr(d, s + "inteMass").to_scipy().tocsc()
+            Mp = ddpk.get_csr(d, s + "inteMass_pena").to_scipy()
+            Sp = ddpk.get_csr(d, s + "systTran_pena").to_scipy()
+            Pr = ddpk.get_csr(d, s + "pemaInpo_r").to_scipy()
+            IL = ddpk.get_csr(d, s + "inpoLagr").to_scipy()
+            u, lam, aux = d[s + "resuDisp_used"], d[s + "inteLagr"], d[s + "inteAuxi"]
+            lam_prev = lam - spla.spsolve(M, Sp.T @ u - Mp @ aux)
+            t = t + (1.0 if tv == 0 else -1.0) * (IL @ lam_prev + Pr @ u)
+        yield float(d[q + "fricCoef"][0]), t, d[q + "gapTerm"], d[q + "resuCont"].reshape(-1, 5)
+
+
+def check_projection_against_resucont(g, st, cont, mu):
+    """gamma / fricStat of the sampled points against the reference's resuCont rows (MCONTACT.h:106-118):
+    normal pressure and tangential traction magnitude to 1e-8, Coulomb status bit-exact.  Points that sit on a
+    branch boundary to within the accuracy of the replayed trace (|gamma_n| or the distance to the cone below 1e-9
+    of the largest pressure) are left out of the exact comparison and counted."""
+    gn, g1, g2 = g[0::3], g[1::3], g[2::3]
+    scale = max(np.abs(cont[:, 0]).max(), 1e-300)
+    tang = np.hypot(g1, g2)
+    tang_ref = np.linalg.norm(cont[:, 1:4], axis=1)
+    assert np.linalg.norm(gn - cont[:, 0]) <= 1e-8 * np.linalg.norm(cont[:, 0])
+    assert np.linalg.norm(tang - tang_ref) <= 1e-8 * max(np.linalg.norm(tang_ref), 1e-300)
+    edge = (np.abs(cont[:, 0]) < 1e-9 * scale) | (np.abs(tang_ref - mu * cont[:, 0]) < 1e-9 * scale) & (cont[:, 0] > 0) & (cont[:, 4] == 2)
+    ok = st[1::3] == cont[:, 4].astype(np.int32)
+    assert ok[~edge].all()
+    return int(edge.sum())

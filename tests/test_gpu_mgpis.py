@@ -62,7 +62,8 @@ def test_coarse_solve_matches_reference_ldlt(solvers, name):
     x = mg.coarse_solve(d["coarse_rhs"])
     assert rel(x, d["coarse_sol"]) < 1e-9
     # residual of the direct solve
-    assert rel(orc.spmv(A[0], x), d["coarse_rhs"]) < 1e-10
+    # level 0 is applied as a dense inverse built by a blocked Gauss-Jordan sweep without pivoting (SPD): kappa * eps
+    assert rel(orc.spmv(A[0], x), d["coarse_rhs"]) < 1e-9
 
 
 @pytest.mark.parametrize("name", CASES)

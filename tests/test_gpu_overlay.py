@@ -14,18 +14,25 @@ BIN = os.path.join(ROOT, "ddpca-admm_b200", "host", "_bin")
 REF = os.path.join(ROOT, "oracle", "_ref")
 
 
-def _run(exe, args, attempts=3):
-    # the pure-reference ADMM drivers end through a watcher thread (_exit) that on rare occasions races with
-    # the OpenMP runtime's teardown: retry instead of failing the comparison on it
-    last = None
-    for _ in range(attempts):
-        tmp = tempfile.mkdtemp(prefix="ddpca_overlay_")
-        try:
-            txt = subprocess.check_output([exe] + args, cwd=tmp, timeout=900).decode()
-            return json.loads(txt.strip().splitlines()[-1])
-        except subprocess.CalledProcessError as e:
-            last = e
-    raise last
+def _run(exe, args, env=None):
+    tmp = tempfile.mkdtemp(prefix="ddpca_overlay_")
+    e = dict(os.environ)
+    e.update(env or {})
+    txt = subprocess.check_output([exe] + args, cwd=tmp, timeout=900, env=e).decode()
+    out = json.loads(txt.strip().splitlines()[-1])
+    moni = os.path.join(tmp, "Beam", "resuMoni.txt")
+    if os.path.exists(moni):
+        out["resuMoni"] = open(moni).read()
+    return out
+
+
+def _ngpu():
+    try:
+        import ddpca_b200 as dd
+
+        return dd.device_count()
+    except Exception:
+        return 0
 
 
 @pytest.mark.skipif(not (os.access(os.path.join(BIN, "beam_nodd_b200"), os.X_OK) and os.access(os.path.join(REF, "beam_nodd"), os.X_OK)),
@@ -68,3 +75,21 @@ def test_beam_dd_example_through_the_overlay(musc):
     assert gpu["iterNumbReco"] == ref["ref_iterNumbReco"]
     for a, b in zip(gpu["disp_norm"], ref["ref_disp_norm"]):
         assert abs(a - b) <= 1e-8 * b
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.skipif(not os.access(os.path.join(BIN, "beam_dd_b200"), os.X_OK), reason="overlay binaries not built")
+@pytest.mark.parametrize("musc", ["1", "3"])
+def test_beam_dd_example_on_several_gpus_in_one_process(musc):
+    """DDPCA_DEVICES=0,1[,2,3]: the same unchanged example, its 8 subdomains bin-packed over the devices of ONE
+    process (ddpca_admm_group_*: peer-copy exchanges ordered by events).  Same iteration count as on one device;
+    per-body arithmetic does not depend on the batch a body runs in, so the displacements agree to round-off of the
+    coarse right-hand side's partial sums."""
+    args = ["--glob", "1", "--doma", "8,1,1", "--musc", musc]
+    one = _run(os.path.join(BIN, "beam_dd_b200"), args, {"DDPCA_DEVICES": "0"})
+    n = min(_ngpu(), 4)
+    many = _run(os.path.join(BIN, "beam_dd_b200"), args, {"DDPCA_DEVICES": ",".join(str(k) for k in range(n))})
+    assert one["error"] is False and many["error"] is False
+    assert many["iterNumbReco"] == one["iterNumbReco"]
+    for a, b in zip(many["disp_norm"], one["disp_norm"]):
+        assert abs(a - b) <= 1e-10 * b

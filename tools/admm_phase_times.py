@@ -1,6 +1,7 @@
-"""Diagnostic: wall time of each phase of one ADMM iteration (BLOCK example) on one GPU."""
+"""Diagnostic: device time of each phase of one ADMM iteration (bench.py's BEAM DD workload, or --block G) on one GPU,
+plus the CG iteration counts of the bodies of the last batched solve (how much lock-step waiting the batch costs)."""
+import argparse
 import ctypes as C
-import json
 import os
 import sys
 import time
@@ -16,26 +17,32 @@ import ddpca_b200 as dd
 from ddpca_b200 import ddpk
 from ddpca_b200.lib import check, load_library
 
-glob = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-path, meta = bench.generate_admm_workload(glob, "")
-d = ddpk.load(path)
+ap = argparse.ArgumentParser()
+ap.add_argument("--glob", type=int, default=3)
+ap.add_argument("--doma", default="8,2,1")
+ap.add_argument("--divi", default="")
+ap.add_argument("--musc", type=int, default=1)
+ap.add_argument("--cpu-iters", type=int, default=4)
+ap.add_argument("--iters", type=int, default=4)
+args = ap.parse_args()
+path, meta = bench.generate_workload(args)
+d = ddpk.load(path, copy=False)
+t0 = time.time()
 mc = dd.MCONTACT.from_ddpk(d)
+print("upload s", round(time.time() - t0, 2), flush=True)
 lib = load_library()
-names = ["bodies", "macro_partial", "macro_apply", "traces", "interface", "monitor"]
-for tc in range(3):
+names = {0: "bodies", 1: "macro_partial", 2: "macro_apply", 6: "macro1_partial", 7: "macro1_apply", 3: "traces", 4: "interface", 5: "monitor"}
+order = [0] + ([1, 2] if mc.muscSett & 1 else []) + ([6, 7] if mc.muscSett & 2 else []) + [3, 4, 5]
+row = np.empty(mc.row_len)
+for tc in range(args.iters):
     out = {}
-    for ph in range(6):
+    for ph in order:
         torch.cuda.synchronize()
         t0 = time.time()
         check(lib.ddpca_admm_phase(mc._h, C.c_int(ph)))
         torch.cuda.synchronize()
         out[names[ph]] = round(1e3 * (time.time() - t0), 3)
-    print("iteration", tc, "phase ms", out, flush=True)
-for nm in ("coarSolv_D",):
-    s = dd.DIRE_SOLV(d[nm + ".perm"], ddpk.get_csr(d, nm + ".L"), d[nm + ".D"])
-    b = np.random.default_rng(0).standard_normal(s.n)
-    s.solve(b)
-    t0 = time.time()
-    for _ in range(3):
-        x = s.solve(b)
-    print(nm, s.info(), "solve ms", round(1e3 * (time.time() - t0) / 3, 3), "resid", float(np.linalg.norm(ddpk.get_csr(d, "globCoup").to_scipy() @ x - b) / np.linalg.norm(b)))
+    it, dofit = C.c_long(), C.c_double()
+    check(lib.ddpca_admm_monitor_row(mc._h, row.ctypes.data_as(C.POINTER(C.c_double)), C.byref(it), C.byref(dofit)))
+    nbt, its = mc.body_iters()
+    print("iteration", tc, "phase ms", out, "| batches", nbt, "CG iterations per body", its, "lock-step efficiency %.3f" % (sum(its) / (len(its) * max(its)) if max(its) else 1.0), flush=True)
