@@ -393,7 +393,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(work[4].item()), "d2h_bytes_per_step": int(work[5].item()),
                     "ms_per_step": ms_e2e_max / steps if e2e_steps else None},
             "gpu_launches": int(work[2].item()),
-            "admm": {"solve_wall_s": solve_s, "admm_iterations": its, "admm_iter_per_s": its / solve_s, "upload_s": round(upload_s, 2),
+            "admm": {"solve_wall_s": solve_s, "admm_iterations": its, "admm_iter_per_s": its / solve_s, "upload_s": round(upload_s, 2), "upload_breakdown_s": getattr(mc, "upload_times", None),
                      "mgpcg_dof_iter_per_s": value, "cg_iterations_per_solve": int(work[3].item()) // steps,
                      "gpu_launches_per_admm_iteration": round(work[2].item() / max(1, admm_iters) / 1.0, 1),
                      "reference_set_up_s": round(meta.get("driver_wall_s", 0.0) - sum(meta.get("ref_iter_s", [])), 1),

@@ -495,6 +495,54 @@ __global__ void __launch_bounds__(256) k_spmv(CsrView A, double alpha, const dou
     if (DOT) block_sum_to_partial(acc, partial);
 }
 
+// K5/K6 on the NODE structure of the transfer operators.  realProl couples fine node i to coarse node j with one
+// scalar weight for all three displacement components unless the nodes carry rotations (MULTIGRID.h:1143-1176), so
+// after the explicit zeros are dropped the three rows of a node are shifted copies of each other:
+// cols(row k) = cols(row 0) + k, same values.  Such row triples are stored ONCE (first column + weight per node
+// pair: 12 B instead of 36 B of CSR); rows that do not fit (constrained or rotated nodes) stay in a small CSR
+// remainder.  y (=|+=) T x for the triples, LANES lanes per triple (1-2 for prolongation rows of ~3 pairs, 8 for
+// restriction rows of ~27).
+template <int LANES, bool ADD>
+__global__ void __launch_bounds__(256) k_trip_spmv(int ntrip, const int *__restrict__ trow, const int *__restrict__ tptr,
+                                                   const int *__restrict__ tcol, const double *__restrict__ tw,
+                                                   const double *__restrict__ x, double *y, const int *done)
+{
+    if (done && *done) return;
+    const int sub = threadIdx.x % LANES;
+    const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / LANES);
+    const bool live = g < ntrip;   // whole sub-warps are live or not (256 % LANES == 0)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    int r = 0;
+    if (live) {
+        r = trow[g];
+        const int pb = tptr[g], pe = tptr[g + 1];
+        for (int p = pb + sub; p < pe; p += LANES) {
+            const int c = ld_stream(tcol + p);
+            const double w = ld_stream(tw + p);
+            s0 += w * __ldg(x + c);
+            s1 += w * __ldg(x + c + 1);
+            s2 += w * __ldg(x + c + 2);
+        }
+    }
+    s0 = subwarp_sum<LANES>(s0); s1 = subwarp_sum<LANES>(s1); s2 = subwarp_sum<LANES>(s2);
+    if (live && sub == 0) {
+        if (ADD) { y[r] += s0; y[r + 1] += s1; y[r + 2] += s2; }
+        else { y[r] = s0; y[r + 1] = s1; y[r + 2] = s2; }
+    }
+}
+// remainder rows (compact CSR + row map): y[row[k]] (=|+=) sum_p v_p x[c_p], one thread per row
+template <bool ADD>
+__global__ void __launch_bounds__(256) k_rowmap_spmv(int nrows, const int *__restrict__ row, CsrView A, const double *__restrict__ x, double *y, const int *done)
+{
+    if (done && *done) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nrows) return;
+    double s = 0.0;
+    for (int p = A.rp[k]; p < A.rp[k + 1]; p++) s += A.v[p] * __ldg(x + A.ci[p]);
+    const int i = row[k];
+    if (ADD) y[i] += s; else y[i] = s;
+}
+
 // K7: level-0 direct solve as a dense symmetric GEMV with the precomputed inverse.  One warp per row;
 // 16-byte streaming loads, four independent partial sums per lane (eight loads in flight) -- the rows
 // are short (a few thousand entries), so memory-level parallelism per warp is what sets the rate.

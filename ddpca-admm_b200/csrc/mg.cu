@@ -66,6 +66,17 @@ struct DevCsr {
     double avg_row() const { return rows ? (double)nnz / rows : 0.0; }
 };
 
+// transfer operator in node-triple form (kernels.cuh, k_trip_spmv) + CSR remainder
+struct DevTrip {
+    int rows = 0, cols = 0, ntrip = 0, nrest = 0;
+    long npairs = 0, nnz_rest = 0;
+    int *trow = nullptr, *tptr = nullptr, *tcol = nullptr, *rest_row = nullptr;
+    double *tw = nullptr;
+    DevCsr rest;
+    bool ok = false;        // built (otherwise the plain CSR operator is used)
+    double avg_pairs() const { return ntrip ? (double)npairs / ntrip : 0.0; }
+};
+
 struct Segment {
     int multi;   // 0: one stage, one launch, one warp per group; 1: run of stages in one CTA
     int s0, s1;  // stage range
@@ -89,6 +100,7 @@ struct Level {
     std::vector<Segment> segs;
     bool wide_rows = false;   // triangular factors: one full warp per row in the single-CTA stage runs
     DevCsr P, R;  // level l <-> l-1 (l >= 1)
+    DevTrip Pt, Rt;  // the same in node-triple form when the operators have that structure
     double *x = nullptr, *b = nullptr, *p1 = nullptr, *r = nullptr, *dinv = nullptr;
     double bytes_lower = 0, bytes_upper = 0, bytes_full = 0;  // algorithmic bytes of one pass over a half / the whole level
     LvlView view() const { return LvlView{n, ng, meta, gci, gv}; }
@@ -257,7 +269,6 @@ static int alloc_vec(double **d, long n)
 }
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
-
 // DDPCA_VERBOSE: wall-clock stages of the set-up on stderr
 struct StageTimer {
     bool on;
@@ -268,6 +279,50 @@ struct StageTimer {
     void lap(const char *stage) { if (!on) return; double t = now(); std::fprintf(stderr, "ddpca set-up [%s] %-28s %8.3f s\n", what, stage, t - last); last = t; }
     ~StageTimer() { if (on) std::fprintf(stderr, "ddpca set-up [%s] total %8.3f s\n", what, now() - t0); }
 };
+
+// Node-triple form of a transfer operator: runs of three consecutive rows that are shifted copies of each other
+// (same length, same values, columns +1, +2) are stored once; everything else goes to the CSR remainder.  Worth it
+// when most rows are in triples (no nodal rotations); returns with t.ok == false otherwise.
+static int build_trip(const CsrHost &A, DevTrip &t)
+{
+    t.rows = A.rows; t.cols = A.cols;
+    std::vector<int> trow, tptr(1, 0), tcol, rest_row;
+    std::vector<double> tw;
+    CsrHost R;
+    R.rp.push_back(0);
+    long in_trip = 0;
+    for (int i = 0; i < A.rows;) {
+        bool trip = false;
+        if (i + 2 < A.rows) {
+            const int len = A.rp[i + 1] - A.rp[i];
+            trip = (A.rp[i + 2] - A.rp[i + 1] == len) && (A.rp[i + 3] - A.rp[i + 2] == len);
+            for (int k = 0; trip && k < len; k++) {
+                const int c = A.ci[A.rp[i] + k];
+                const double w = A.v[A.rp[i] + k];
+                trip = A.ci[A.rp[i + 1] + k] == c + 1 && A.ci[A.rp[i + 2] + k] == c + 2 && A.v[A.rp[i + 1] + k] == w && A.v[A.rp[i + 2] + k] == w;
+            }
+        }
+        if (trip) {
+            trow.push_back(i);
+            for (int p = A.rp[i]; p < A.rp[i + 1]; p++) { tcol.push_back(A.ci[p]); tw.push_back(A.v[p]); }
+            tptr.push_back((int)tcol.size());
+            in_trip += 3;
+            i += 3;
+        } else {
+            rest_row.push_back(i);
+            for (int p = A.rp[i]; p < A.rp[i + 1]; p++) { R.ci.push_back(A.ci[p]); R.v.push_back(A.v[p]); }
+            R.rp.push_back((int)R.ci.size());
+            i += 1;
+        }
+    }
+    if (A.rows == 0 || in_trip < 0.8 * A.rows || std::getenv("DDPCA_NO_TRIP")) return 0;
+    R.rows = (int)rest_row.size(); R.cols = A.cols;
+    t.ntrip = (int)trow.size(); t.nrest = R.rows; t.npairs = (long)tcol.size(); t.nnz_rest = R.nnz();
+    if (upload_vec(trow, &t.trow) || upload_vec(tptr, &t.tptr) || upload_vec(tcol, &t.tcol) || upload_vec(tw, &t.tw) ||
+        upload_vec(rest_row, &t.rest_row) || upload_csr(R, t.rest)) return 1;
+    t.ok = true;
+    return 0;
+}
 
 // ---- kernel launch helpers (all on h->stream) ----------------------------------------------
 static void launch_spmv(Engine *h, int kclass, int lvl, const DevCsr &A, const double *x, double *y, bool add,
@@ -300,6 +355,33 @@ static void launch_spmv(Engine *h, int kclass, int lvl, const DevCsr &A, const d
     else SPMV_CASE(4);
 #undef SPMV_CASE
 }
+// y (=|+=) T x with the node-triple form when available, else the CSR operator
+static void launch_transfer(Engine *h, int kclass, int lvl, const DevCsr &A, const DevTrip &T, const double *x, double *y, bool add, const int *done)
+{
+    if (!T.ok) { launch_spmv(h, kclass, lvl, A, x, y, add, nullptr, nullptr, done); return; }
+    // algorithmic bytes of the layout actually stored: 12 B per node pair + 8 B per triple (row, pointer) + remainder CSR + vectors
+    const double bytes = 12.0 * T.npairs + 8.0 * T.ntrip + 12.0 * T.nnz_rest + 8.0 * T.nrest + 8.0 * T.cols + 8.0 * T.rows * (add ? 2 : 1);
+    h->pre(kclass, lvl, bytes);
+    const int TB = 256;
+    if (T.ntrip) {
+        if (T.avg_pairs() > 12.0) {
+            const int g = cdiv((long)T.ntrip * 8, TB);
+            if (add) k_trip_spmv<8, true><<<g, TB, 0, h->stream>>>(T.ntrip, T.trow, T.tptr, T.tcol, T.tw, x, y, done);
+            else k_trip_spmv<8, false><<<g, TB, 0, h->stream>>>(T.ntrip, T.trow, T.tptr, T.tcol, T.tw, x, y, done);
+        } else {
+            const int g = cdiv((long)T.ntrip * 2, TB);
+            if (add) k_trip_spmv<2, true><<<g, TB, 0, h->stream>>>(T.ntrip, T.trow, T.tptr, T.tcol, T.tw, x, y, done);
+            else k_trip_spmv<2, false><<<g, TB, 0, h->stream>>>(T.ntrip, T.trow, T.tptr, T.tcol, T.tw, x, y, done);
+        }
+    }
+    if (T.nrest) {
+        if (h->capturing) h->captured_nodes++; else h->launches++;
+        if (add) k_rowmap_spmv<true><<<cdiv(T.nrest, TB), TB, 0, h->stream>>>(T.nrest, T.rest_row, T.rest.view(), x, y, done);
+        else k_rowmap_spmv<false><<<cdiv(T.nrest, TB), TB, 0, h->stream>>>(T.nrest, T.rest_row, T.rest.view(), x, y, done);
+    }
+    h->post();
+}
+
 // ---- v2 launches (kernels2.cuh) ------------------------------------------------------------------
 template <int MODE>
 static int v2_blocks_per_sm(size_t dyn)
@@ -431,9 +513,9 @@ static void vcycle_dev(ddpca_mg *h, int l, const double *b, double *x, bool zero
     sweep_bwd(h, L, l, x, done);             // :73-76
     if (L.v2) launch_v2<V2_RESID>(h, L, DDPCA_K_RESID, l, L.bytes_lower + 8.0 * L.n, b, x, L.p1, L.r, nullptr, nullptr, done);
     else KL(h, DDPCA_K_RESID, l, L.bytes_lower + 8.0 * L.n, (k_resid_lower<<<cdiv((long)L.ng * GL, 256), 256, 0, h->stream>>>(L.view(), b, L.p1, x, L.r, done)));
-    launch_spmv(h, DDPCA_K_RESTRICT, l, L.R, L.r, C.b, false, nullptr, nullptr, done);  // :96
+    launch_transfer(h, DDPCA_K_RESTRICT, l, L.R, L.Rt, L.r, C.b, false, done);  // :96
     vcycle_dev(h, l - 1, C.b, C.x, true, done);                                          // :93-99
-    launch_spmv(h, DDPCA_K_PROLONG, l, L.P, C.x, x, true, nullptr, nullptr, done);       // :100
+    launch_transfer(h, DDPCA_K_PROLONG, l, L.P, L.Pt, C.x, x, true, done);               // :100
     sweep_fwd(h, L, l, b, x, false, done);  // :102-109
     sweep_bwd(h, L, l, x, done);            // :110-113
 }
@@ -911,9 +993,16 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
     if (alloc_vec(&L.x, n) || alloc_vec(&L.b, n) || alloc_vec(&L.p1, n) || alloc_vec(&L.r, n)) return 1;
     return 0;
 }
+static void free_trip(DevTrip &t)
+{
+    cudaFree(t.trow); cudaFree(t.tptr); cudaFree(t.tcol); cudaFree(t.tw); cudaFree(t.rest_row);
+    free_csr(t.rest);
+    t = DevTrip();
+}
 static void free_level(Level &L)
 {
     free_csr(L.A); free_csr(L.P); free_csr(L.R);
+    free_trip(L.Pt); free_trip(L.Rt);
     cudaFree(L.meta); cudaFree(L.gci); cudaFree(L.gv); cudaFree(L.stage_group); cudaFree(L.perm);
     cudaFree(L.x); cudaFree(L.b); cudaFree(L.p1); cudaFree(L.r); cudaFree(L.dinv);
     cudaFree(L.meta2); cudaFree(L.CL); cudaFree(L.CU); cudaFree(L.VL); cudaFree(L.VU); cudaFree(L.BD); cudaFree(L.gbar); L.gbar = nullptr;
@@ -1328,6 +1417,7 @@ static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const
             transpose_csr(Pp, Rp);
             FAILC(upload_csr(Pp, L.P));
             FAILC(upload_csr(Rp, L.R));
+            FAILC(build_trip(Pp, L.Pt) || build_trip(Rp, L.Rt));
             t_p += StageTimer::now() - tc;
         }
     }
@@ -1519,7 +1609,7 @@ int ddpca_mg_restrict(ddpca_mg *h, int level, const double *r_fine, double *r_co
     if (!h || level < 0 || level + 1 >= h->nlev || !r_fine || !r_coarse) return fail("ddpca_mg_restrict: bad argument");
     CU(cudaSetDevice(h->device));
     if (to_dev(h, level + 1, r_fine, h->cg_p)) return 1;
-    launch_spmv(h, DDPCA_K_RESTRICT, level + 1, h->lev[level + 1].R, h->cg_p, h->cg_q, false, nullptr, nullptr, nullptr);
+    launch_transfer(h, DDPCA_K_RESTRICT, level + 1, h->lev[level + 1].R, h->lev[level + 1].Rt, h->cg_p, h->cg_q, false, nullptr);
     if (h->profile) h->prof_collect();
     return to_host(h, level, h->cg_q, r_coarse);
 }
@@ -1530,7 +1620,7 @@ int ddpca_mg_prolong_add(ddpca_mg *h, int level, const double *e_coarse, double 
     CU(cudaSetDevice(h->device));
     if (to_dev(h, level, e_coarse, h->cg_p)) return 1;
     if (to_dev(h, level + 1, x_fine, h->cg_q)) return 1;
-    launch_spmv(h, DDPCA_K_PROLONG, level + 1, h->lev[level + 1].P, h->cg_p, h->cg_q, true, nullptr, nullptr, nullptr);
+    launch_transfer(h, DDPCA_K_PROLONG, level + 1, h->lev[level + 1].P, h->lev[level + 1].Pt, h->cg_p, h->cg_q, true, nullptr);
     if (h->profile) h->prof_collect();
     return to_host(h, level + 1, h->cg_q, x_fine);
 }

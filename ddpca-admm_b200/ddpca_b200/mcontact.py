@@ -140,8 +140,12 @@ class MCONTACT:
         `macro_mgpis`: an established MGPIS whose finest level is globCoup -- the macroscopic problem is then
         solved by mgpi.CG_SOLV(1, .) like the reference does beyond DIRE_MAXI rows (MCONTACT.h:2560-2562)
         instead of the factor coarSolv_D; ownership of its device hierarchy moves to this object."""
+        import time
+
         lib = load_library()
         self = cls(device, smoother)
+        tm = {"bodies": 0.0, "side_operators": 0.0, "side_solvers": 0.0, "coarse_solvers": 0.0, "finalize": 0.0}
+        t_ = time.time()
         nb, ni = int(d["nbody"][0]), int(d["niface"][0])
         self.nb, self.ni = nb, ni
         self.muscSett = int(d["muscSett"][0]) if muscSett is None else muscSett
@@ -180,6 +184,7 @@ class MCONTACT:
             if self.muscSett & 2:   # interface-eliminated coarse problem, MCONTACT.h:2583
                 a = ddpk.get_csr(d, p + "globTran_D_1")
                 check(lib.ddpca_admm_set_body_globtran_d1(h, C.c_int(v), C.c_int(a.shape[0]), C.c_int(a.shape[1]), _pi(a.rowptr), _pi(a.colidx), _pd(a.val)))
+        tm["bodies"] = time.time() - t_
         self.nc = []
         self.ng = []
         for ts in range(ni):
@@ -199,13 +204,18 @@ class MCONTACT:
                 if self.body_rank[cb[tv]] != rank:
                     continue
                 ops = list(range(7)) + ([7, 8, 9] if (self.muscSett & 1) else []) + ([10] if (self.muscSett & 2) else [])
+                t_ = time.time()
                 for k in ops:
                     m = ddpk.get_csr(d, q + OPS[k])
                     check(lib.ddpca_admm_set_side_op(h, C.c_int(ts), C.c_int(tv), C.c_int(k), C.c_int(m.shape[0]), C.c_int(m.shape[1]), _pi(m.rowptr), _pi(m.colidx), _pd(m.val)))
+                tm["side_operators"] += time.time() - t_
+                t_ = time.time()
                 for which, nm, mat in ((SOLVER_MASS, "inteDiso", "inteMass"), (SOLVER_MASS_PENA, "inteDiso_pena", "inteMass_pena")):
                     s = _factor_from_dump(d, q + nm, device, ddpk.get_csr(d, q + mat), factorize)
                     check(lib.ddpca_admm_set_side_solver(h, C.c_int(ts), C.c_int(tv), C.c_int(which), s.release()))
+                tm["side_solvers"] += time.time() - t_
             self.nc.append(ncs)
+        t_ = time.time()
         if self.muscSett & 1:
             base = np.ascontiguousarray(d["baseReco"], dtype=np.int64)
             if macro_mgpis is not None:
@@ -220,6 +230,8 @@ class MCONTACT:
             s1 = _factor_from_dump(d, "coarSolv_D_1", device, ddpk.get_csr(d, "globCoup_1"), factorize)
             gf1 = np.ascontiguousarray(d["globForc_1"], dtype=np.float64)
             check(lib.ddpca_admm_set_macro1(h, C.c_int(s1.n), base.ctypes.data_as(C.POINTER(C.c_long)), _pd(gf1), s1.release()))
+        tm["coarse_solvers"] = time.time() - t_
+        t_ = time.time()
         if comm is not None:
             ng_, nt_, nm_ = C.c_long(), C.c_long(), C.c_long()
             check(lib.ddpca_admm_exchange_sizes(h, C.byref(ng_), C.byref(nt_), C.byref(nm_)))
@@ -228,6 +240,8 @@ class MCONTACT:
             check(lib.ddpca_admm_set_exchange(h, ptr[0], ptr[1], ptr[2], ptr[3]))
             check(lib.ddpca_admm_set_stream(h, C.c_void_p(comm.stream_ptr())))
         check(lib.ddpca_admm_finalize(h))
+        tm["finalize"] = time.time() - t_
+        self.upload_times = {k: round(v, 3) for k, v in tm.items()}
         del keep
         self._peers = []
         if comm is not None:

@@ -204,15 +204,20 @@ def dehw_friction_cases():
 
 def check_projection_against_resucont(g, st, cont, mu):
     """gamma / fricStat of the sampled points against the reference's resuCont rows (MCONTACT.h:106-118):
-    normal pressure and tangential traction magnitude to 1e-8, Coulomb status bit-exact.  Points that sit on a
-    branch boundary to within the accuracy of the replayed trace (|gamma_n| or the distance to the cone below 1e-9
-    of the largest pressure) are left out of the exact comparison and counted."""
+    normal pressure to 1e-8, Coulomb status bit-exact, tangential traction magnitude to 1e-3 -- OUTPUT_PRTR writes
+    the traction as gamma_1 b_1 + gamma_2 b_2 in the integration point's own tangent basis (MCONTACT.h:110-113),
+    which on the curved tooth flanks is orthonormal to ~1e-4 only, so |traction| and hypot(gamma_1, gamma_2) differ
+    by that much in the reference's own data.  Points that sit on a branch boundary to within the accuracy of the
+    replayed trace (|gamma_n| or the distance to the cone below 1e-9 of the largest pressure) are left out of the
+    exact comparison and counted."""
     gn, g1, g2 = g[0::3], g[1::3], g[2::3]
     scale = max(np.abs(cont[:, 0]).max(), 1e-300)
     tang = np.hypot(g1, g2)
     tang_ref = np.linalg.norm(cont[:, 1:4], axis=1)
     assert np.linalg.norm(gn - cont[:, 0]) <= 1e-8 * np.linalg.norm(cont[:, 0])
-    assert np.linalg.norm(tang - tang_ref) <= 1e-8 * max(np.linalg.norm(tang_ref), 1e-300)
+    assert np.linalg.norm(tang - tang_ref) <= 1e-3 * max(np.linalg.norm(tang_ref), 1e-300)
+    slide = cont[:, 4] == 1
+    assert np.allclose(tang[slide], mu * gn[slide], rtol=1e-12, atol=0)      # sliding points sit ON the cone (MCONTACT.h:2654)
     edge = (np.abs(cont[:, 0]) < 1e-9 * scale) | (np.abs(tang_ref - mu * cont[:, 0]) < 1e-9 * scale) & (cont[:, 0] > 0) & (cont[:, 4] == 2)
     ok = st[1::3] == cont[:, 4].astype(np.int32)
     assert ok[~edge].all()

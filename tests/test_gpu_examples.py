@@ -123,3 +123,22 @@ def test_dehw_first_iterations_against_reference_run_here():
         assert ((g[0::3] > 0) == (t[:, 0] > 0)).all()                       # active set, bit-exact
         assert np.array_equal(st[1::3], t[:, 4].astype(np.int32))           # open / slide / stick, bit-exact
     mc.close()
+
+
+def test_coulomb_projection_kernel_matches_the_reference_dehw_run():
+    """The device projection kernel (k_gamma_project_all through ddpca_gamma_project) on the trace replayed from the
+    reference's own DEHW run after 260 iterations (tests/golden/dehw_friction.ddpk.gz): normal pressure, tangential
+    traction and the Coulomb status code of every sampled integration point as the reference wrote them to
+    resuCont_<ts>.txt (MCONTACT.h:106-118, column 5) -- bit-exact status."""
+    import os
+
+    from tests.helpers import GOLDEN, check_projection_against_resucont, dehw_friction_cases
+
+    if not os.path.exists(os.path.join(GOLDEN, "dehw_friction.ddpk.gz")):
+        pytest.skip("tests/golden/dehw_friction.ddpk.gz not generated")
+    seen = set()
+    for mu, t, gap, cont in dehw_friction_cases():
+        g, st = dd.gamma_project(t, gap, mu)
+        check_projection_against_resucont(g, st, cont, mu)
+        seen |= set(st[1::3].tolist())
+    assert {0, 1} <= seen
