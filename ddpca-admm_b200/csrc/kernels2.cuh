@@ -79,7 +79,7 @@ struct __align__(16) ChunkDesc {
     int cu0, ncu;
     int vl0, nvl;    // value range in 16-byte units
     int vu0, nvu;
-    int pad0, pad1;
+    int sub, pad1;   // sub: subdomain of a batched hierarchy the chunk belongs to (chunks never straddle subdomains)
 };
 constexpr int kBlkStride = 12;     // doubles per in-group block record: the gs x gs block row-major (9) + 1/diagonal (3)
 // The v2 sweeps multiply by the stored reciprocal of the diagonal instead of dividing (three dependent
@@ -102,6 +102,10 @@ struct Lvl2View {
     const double *__restrict__ BD;          // [ng * kBlkStride]
     const ChunkDesc *__restrict__ chunks;   // [nchunks], stage after stage -- the table of the pass type (V2_TAB_*)
     const int *__restrict__ stage_chunk;    // [nstages+1]
+    // batched PCG: subdomains whose CG has converged are frozen -- the producer replaces their chunks by an empty
+    // descriptor (ng = 0: 48 bytes instead of ~20 KB, nothing to compute), the ring protocol stays as it is
+    const ChunkDesc *__restrict__ empty_desc;   // one descriptor with ng = 0
+    const PcgState *__restrict__ sub_state;     // [nsub] or null: nothing is skipped
 };
 
 enum { V2_FWD_ZERO = 0, V2_FWD_FULL = 1, V2_BWD = 2, V2_RESID = 3, V2_SPMV = 4 };
@@ -253,8 +257,13 @@ __device__ __forceinline__ void fence_proxy_async()
 
 // issue all bulk copies of one chunk (one thread)
 template <int MODE>
-__device__ __forceinline__ void v2_issue_chunk(const Lvl2View &A, int c, const ChunkDesc &d, unsigned char *buf, uint64_t *bar)
+__device__ __forceinline__ void v2_issue_chunk(const Lvl2View &A, int c, const ChunkDesc &d, unsigned char *buf, uint64_t *bar, const PcgState *sub_state)
 {
+    if (sub_state != nullptr && sub_state[d.sub].done) {   // frozen subdomain: an empty chunk keeps the ring in step
+        mbar_expect_tx(bar, 48);
+        bulk_g2s(buf + kOffDesc, A.empty_desc, 48, bar);
+        return;
+    }
     constexpr bool LO = (MODE != V2_BWD);
     constexpr bool UP = (MODE == V2_FWD_FULL || MODE == V2_BWD || MODE == V2_SPMV);
     constexpr int kOffBlk = v2_off_blk(v2_groups(MODE)), kOffData = v2_off_data(v2_groups(MODE));
@@ -417,6 +426,9 @@ __global__ void __launch_bounds__(v2_threads(MODE)) k_level_pass(Lvl2View A, siz
     if (tid >= kV2Consumers) {
         // ------------------------------- producer warp ---------------------------------------
         if (tid == kV2Consumers) {
+            // inside a PCG loop (done != null) the states of the batch's subdomains are current: skip the frozen ones;
+            // stand-alone passes (ddpca_mg_vcycle, the host-driven solvers) never skip
+            const PcgState *sub_state = done ? A.sub_state : nullptr;
             // the descriptor of chunk j+1 is fetched before the wait for chunk j's ring slot, so
             // that its global-memory latency never sits between a slot release and the next copy
             bool have = settle(si, c);
@@ -431,7 +443,7 @@ __global__ void __launch_bounds__(v2_threads(MODE)) k_level_pass(Lvl2View A, siz
                 const int slot = j % kV2Bufs;
                 if (j >= kV2Bufs) mbar_wait(&empty[slot], (uint32_t)(((j / kV2Bufs) - 1) & 1));
                 fence_proxy_async();
-                v2_issue_chunk<MODE>(A, c_this, d, smem + (size_t)slot * buf_bytes, &full[slot]);
+                v2_issue_chunk<MODE>(A, c_this, d, smem + (size_t)slot * buf_bytes, &full[slot], sub_state);
             }
         }
     } else {

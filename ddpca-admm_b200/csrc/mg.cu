@@ -114,10 +114,12 @@ struct Level {
     int *stage_chunk[3] = {nullptr, nullptr, nullptr};
     int nchunks[3] = {0, 0, 0}, max_stage_chunks[3] = {0, 0, 0};
     size_t buf[3] = {0, 0, 0};   // shared-memory bytes of one chunk buffer
+    ChunkDesc *empty_desc = nullptr;   // one zero descriptor (ng = 0) standing in for chunks of frozen subdomains
+    const PcgState *sub_state = nullptr;   // per-sub CG states of the owning batch when skipping is on (not owned)
     unsigned *gbar = nullptr;   // counters of the consumer grid barrier
     int fuse_bwd_last = 0;       // the forward sweeps also do the backward step of the last colour (see Lvl2View)
     double bytes_bwd_skip = 0;   // algorithmic bytes the backward sweep no longer touches then
-    Lvl2View view2(int tab = V2_TAB_FULL) const { return Lvl2View{n, ng, nchunks[tab], plan.nstages(), fuse_bwd_last, meta2, CL, VL, CU, VU, BD, chunks[tab], stage_chunk[tab]}; }
+    Lvl2View view2(int tab = V2_TAB_FULL) const { return Lvl2View{n, ng, nchunks[tab], plan.nstages(), fuse_bwd_last, meta2, CL, VL, CU, VU, BD, chunks[tab], stage_chunk[tab], empty_desc, sub_state}; }
 };
 
 struct ProfRec {
@@ -794,12 +796,13 @@ static inline int round4(int v) { return (v + 3) & ~3; }
 // within 1/kHalfBudgetDiv of the largest whole-row chunk (at most kHalfGroups groups).
 // (Re-cutting a colour into a multiple of the grid of equal chunks, so that no CTA waits for a last,
 // nearly empty round, was measured and is slower: more, smaller chunks cost more than the tails.)
-static void build_chunks2(const LevelPlan &pl, Layout2Host &out)
+static void build_chunks2(const LevelPlan &pl, Layout2Host &out, const std::vector<int> *group_sub)
 {
     const int ns = pl.nstages();
     auto make_desc = [&](int g0, int g1) {
         ChunkDesc d{};
         d.g0 = g0; d.ng = g1 - g0;
+        d.sub = group_sub ? (*group_sub)[g0] : 0;
         const GroupMeta2 &a = out.meta[g0], &z = out.meta[g1 - 1];
         d.cl0 = a.cl; d.ncl = z.cl + z.nl - a.cl;
         d.cu0 = a.cu; d.ncu = z.cu + z.nu - a.cu;
@@ -826,7 +829,7 @@ static void build_chunks2(const LevelPlan &pl, Layout2Host &out)
             st.clear();
             for (int g0 = gbeg; g0 < gend;) {
                 int g1 = g0 + 1;
-                while (g1 < gend && g1 - g0 < cap && data_bytes(make_desc(g0, g1 + 1)) <= lim) g1++;
+                while (g1 < gend && g1 - g0 < cap && (!group_sub || (*group_sub)[g1] == (*group_sub)[g0]) && data_bytes(make_desc(g0, g1 + 1)) <= lim) g1++;
                 st.push_back(make_desc(g0, g1));
                 g0 = g1;
             }
@@ -843,7 +846,7 @@ static void build_chunks2(const LevelPlan &pl, Layout2Host &out)
     }
 }
 
-static bool build_layout2(const CsrHost &Ap, const LevelPlan &pl, Layout2Host &out, std::string &err)
+static bool build_layout2(const CsrHost &Ap, const LevelPlan &pl, Layout2Host &out, std::string &err, const std::vector<int> *group_sub)
 {
     const int ng = pl.ngroups();
     out.meta.resize(ng);
@@ -888,7 +891,7 @@ static bool build_layout2(const CsrHost &Ap, const LevelPlan &pl, Layout2Host &o
             out.BD[(size_t)g * kBlkStride + 9 + r] = 1.0 / vr[kd + r];
         }
     }
-    build_chunks2(pl, out);
+    build_chunks2(pl, out, group_sub);
     return true;
 }
 
@@ -930,7 +933,8 @@ static int build_segments(Level &L, const GroupLayoutHost &G)
 }
 
 // Plan + permute + group layout + upload of one operator level (device must be current).
-static int setup_level(Level &L, int n, const int *rp, const int *ci, const double *v, int mode, bool keep_csr, bool group_layout)
+static int setup_level(Level &L, int n, const int *rp, const int *ci, const double *v, int mode, bool keep_csr, bool group_layout,
+                       const std::vector<int> *sub_off = nullptr)
 {
     L.n = n;
     std::string err;
@@ -948,7 +952,17 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
         for (const Segment &sg : L.segs) if (sg.multi) want_v2 = false;
         Layout2Host H2;
         if (want_v2) {
-            if (!build_layout2(Ap, L.plan, H2, err)) return fail(err);
+            // subdomain of every row group (batched hierarchies: chunks are cut at subdomain boundaries)
+            std::vector<int> group_sub;
+            if (sub_off && sub_off->size() > 2) {
+                const int ngp = L.plan.ngroups();
+                group_sub.resize(ngp);
+                for (int g = 0; g < ngp; g++) {
+                    const int old = L.plan.perm[L.plan.group_start[g]];
+                    group_sub[g] = (int)(std::upper_bound(sub_off->begin(), sub_off->end(), old) - sub_off->begin()) - 1;
+                }
+            }
+            if (!build_layout2(Ap, L.plan, H2, err, group_sub.empty() ? nullptr : &group_sub)) return fail(err);
             for (int tab = 0; tab < 3; tab++)
                 if ((size_t)kV2Bufs * H2.buf[tab] > 200 * 1024) want_v2 = false;   // the chunk ring must fit in shared memory
         }
@@ -981,6 +995,8 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
                 L.buf[tab] = H2.buf[tab];
                 if (upload_vec(H2.chunks[tab], &L.chunks[tab]) || upload_vec(H2.stage_chunk[tab], &L.stage_chunk[tab])) return 1;
             }
+            CU(cudaMalloc(&L.empty_desc, sizeof(ChunkDesc)));
+            CU(cudaMemset(L.empty_desc, 0, sizeof(ChunkDesc)));
             CU(cudaMalloc(&L.gbar, kGbarWords * sizeof(unsigned)));
             CU(cudaMemset(L.gbar, 0, kGbarWords * sizeof(unsigned)));
             if (upload_vec(H2.meta, &L.meta2) || upload_vec(H2.CL, &L.CL) || upload_vec(H2.CU, &L.CU) || upload_vec(H2.VL, &L.VL) ||
@@ -1005,7 +1021,7 @@ static void free_level(Level &L)
     free_trip(L.Pt); free_trip(L.Rt);
     cudaFree(L.meta); cudaFree(L.gci); cudaFree(L.gv); cudaFree(L.stage_group); cudaFree(L.perm);
     cudaFree(L.x); cudaFree(L.b); cudaFree(L.p1); cudaFree(L.r); cudaFree(L.dinv);
-    cudaFree(L.meta2); cudaFree(L.CL); cudaFree(L.CU); cudaFree(L.VL); cudaFree(L.VU); cudaFree(L.BD); cudaFree(L.gbar); L.gbar = nullptr;
+    cudaFree(L.meta2); cudaFree(L.CL); cudaFree(L.CU); cudaFree(L.VL); cudaFree(L.VU); cudaFree(L.BD); cudaFree(L.gbar); L.gbar = nullptr; cudaFree(L.empty_desc); L.empty_desc = nullptr;
     for (int tab = 0; tab < 3; tab++) { cudaFree(L.chunks[tab]); cudaFree(L.stage_chunk[tab]); L.chunks[tab] = nullptr; L.stage_chunk[tab] = nullptr; }
     L.meta2 = nullptr; L.CL = L.CU = nullptr; L.VL = L.VU = L.BD = nullptr;
     L.meta = nullptr; L.gci = nullptr; L.gv = nullptr; L.stage_group = nullptr; L.perm = nullptr;
@@ -1390,7 +1406,7 @@ static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const
         }
         double tb = StageTimer::now();
         t_cat += tb - ta;
-        if (setup_level(L, ntot, rp, ci, vv, mode, /*keep_csr=*/l == 0, /*group_layout=*/!coarse_only)) {
+        if (setup_level(L, ntot, rp, ci, vv, mode, /*keep_csr=*/l == 0, /*group_layout=*/!coarse_only, &h->sub_off[l])) {
             g_err = "level " + std::to_string(l) + ": " + g_err;
             ddpca_mg_destroy(h);
             return 1;
@@ -1427,6 +1443,8 @@ static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const
           alloc_vec(&h->cg_x, nmax) || alloc_vec(&h->stage_a, nmax) || alloc_vec(&h->stage_b, nmax));
     CUC(cudaMalloc(&h->st, sizeof(PcgState) * nsub));
     CUC(cudaMemset(h->st, 0, sizeof(PcgState) * nsub));
+    if (nsub > 1 && !std::getenv("DDPCA_NO_SKIP_FROZEN"))
+        for (Level &L : h->lev) L.sub_state = h->st;   // v2 passes skip the chunks of converged subdomains
     CUC(cudaMalloc(&h->fl, sizeof(BatchFlags)));
     CUC(cudaMemset(h->fl, 0, sizeof(BatchFlags)));
     CUC(cudaMallocHost(&h->st_host, sizeof(PcgState) * nsub));

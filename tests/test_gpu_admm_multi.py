@@ -54,12 +54,15 @@ def test_two_gpu_admm_matches_reference(musc, iters):
 
 
 @pytest.mark.skipif(_ngpu() < 2 or not have_ref_binary("beam_admm"), reason="needs 2 GPUs and oracle/_ref/beam_admm")
-def test_two_gpu_beam_dd_8_subdomains():
-    """8 BEAM subdomains split 4 + 4 over two GPUs: same iteration count and displacements as the reference."""
-    d, meta = run_ref_beam_dd(1, doma=(8, 1, 1), musc=1, keep_file=True)
+@pytest.mark.parametrize("musc", [1, 2, 3])
+def test_two_gpu_beam_dd_8_subdomains(musc):
+    """8 BEAM subdomains split 4 + 4 over two GPUs (NCCL: all-reduce of the coarse right-hand sides and MONITOR sums,
+    pairwise swap of the interface traces), with the macroscopic problem, the interface-eliminated coarse problem and
+    both: same iteration count and displacements as the reference."""
+    d, meta = run_ref_beam_dd(1, doma=(8, 1, 1), musc=musc, keep_file=True)
     out = tempfile.mkdtemp(prefix="ddpca_gpu_dist_")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29619", os.path.join(ROOT, "tests", "gpu_dist_worker.py"), meta["path"], out, "1", "3000"]
+           "--master-port", "29619", os.path.join(ROOT, "tests", "gpu_dist_worker.py"), meta["path"], out, str(musc), "3000"]
     subprocess.check_call(cmd, timeout=900)
     res = [json.load(open(os.path.join(out, f"rank{r}.json"))) for r in range(2)]
     assert res[0]["iterNumbReco"] == res[1]["iterNumbReco"] == meta["ref_iterNumbReco"]
