@@ -20,7 +20,7 @@ struct ddpca_admm_group {
     std::vector<int> body_rank;
     std::vector<double *> glob, send, recv, moni;        // per member, on its device
     std::vector<cudaEvent_t> ev_a, ev_b;                  // per member: "my part is ready" / "the sum is ready" etc.
-    double *stage0 = nullptr;                             // member 0: [n members x nglob] staging of the reduction
+    double *stage0 = nullptr;                             // member 0: [(n members + 1) x nglob] parts of the reduction + its result
     std::vector<double *> moni_host;                      // pinned, per member
     long nglob = 0, nmoni = 0;
     bool finalized = false;
@@ -66,15 +66,20 @@ static int group_allreduce_glob(ddpca_admm_group *g, long n)
         CU(cudaMemcpyPeerAsync(g->stage0 + (size_t)k * n, g->dev[0], g->glob[k], g->dev[k], sizeof(double) * n, g->m[k]->stream));
         CU(cudaEventRecord(g->ev_a[k], g->m[k]->stream));
     }
+    // The sum goes to its own slot behind the members' parts: the members (0 included) copy it from there, so nobody
+    // reads a buffer another member is already modifying (the interface-eliminated problem adds its constant part to the
+    // right-hand side in place).  The slot is rewritten by the next sum only, which waits for every member's next part,
+    // i.e. for their copies of this one (stream order).
+    double *res = g->stage0 + (size_t)nm * g->nglob;
     CU(cudaSetDevice(g->dev[0]));
     for (int k = 1; k < nm; k++) CU(cudaStreamWaitEvent(g->m[0]->stream, g->ev_a[k], 0));
-    k_sum_members<<<cdiv(n, 256), 256, 0, g->m[0]->stream>>>(nm, n, g->stage0, g->glob[0]);
+    k_sum_members<<<cdiv(n, 256), 256, 0, g->m[0]->stream>>>(nm, n, g->stage0, res);
     g->m[0]->launches++;
     CU(cudaEventRecord(g->ev_b[0], g->m[0]->stream));
-    for (int k = 1; k < nm; k++) {
+    for (int k = 0; k < nm; k++) {
         CU(cudaSetDevice(g->dev[k]));
-        CU(cudaStreamWaitEvent(g->m[k]->stream, g->ev_b[0], 0));
-        CU(cudaMemcpyPeerAsync(g->glob[k], g->dev[k], g->glob[0], g->dev[0], sizeof(double) * n, g->m[k]->stream));
+        if (k) CU(cudaStreamWaitEvent(g->m[k]->stream, g->ev_b[0], 0));
+        CU(cudaMemcpyPeerAsync(g->glob[k], g->dev[k], res, g->dev[0], sizeof(double) * n, g->m[k]->stream));
     }
     return 0;
 }
@@ -163,7 +168,7 @@ int ddpca_admm_group_finalize(ddpca_admm_group *g)
         if (nm > 1 && ddpca_admm_set_exchange(g->m[k], g->glob[k], g->send[k], g->recv[k], g->moni[k])) return 1;
         if (ddpca_admm_finalize(g->m[k])) { g_err = "member " + std::to_string(k) + ": " + g_err; return 1; }
     }
-    if (nm > 1) { CU(cudaSetDevice(g->dev[0])); if (dev_vec(nullptr, (long)nm * g->nglob, &g->stage0)) return 1; }
+    if (nm > 1) { CU(cudaSetDevice(g->dev[0])); if (dev_vec(nullptr, (long)(nm + 1) * g->nglob, &g->stage0)) return 1; }
     g->finalized = true;
     return 0;
 }

@@ -1888,7 +1888,7 @@ int ddpca_ldlt_create(int device, int n, const int *perm, const int *L_rowptr, c
 }
 int ddpca_ldlt_create_dense(int device, int n, const int *rowptr, const int *colidx, const double *val, ddpca_ldlt **out)
 {
-    if (!out || n < 1 || n > 16384 || !rowptr || !colidx || !val) return fail("ddpca_ldlt_create_dense: bad argument (n must be <= 16384)");
+    if (!out || n < 1 || n > 32768 || !rowptr || !colidx || !val) return fail("ddpca_ldlt_create_dense: bad argument (n must be <= 32768)");
     int ndev = ddpca_device_count();
     if (ndev == 0) return fail("no CUDA device: libddpca_b200 has no CPU fallback");
     if (device < 0 || device >= ndev) return fail("device index out of range");

@@ -31,6 +31,10 @@ class DIRE_SOLV:
     on the device: perm = permutationP().indices(), L = strictly-lower unit factor (CSR), D = vectorD()."""
 
     DENSE_MAX = 4096   # below this size an SPD operator is inverted densely on the device (one GEMV per solve)
+    # The coarse problems (macroscopic / interface-eliminated) are solved once per ADMM iteration on EVERY rank: the staged
+    # sparse triangular solves cost ~2 ms of launch latency at 23 k rows, one 4.4 GB product 0.7 ms -- and it is the part
+    # of an iteration that does not shrink with more GPUs.  HBM is 180 GB; the dense form is used up to this size.
+    DENSE_MAX_COARSE = 32768
 
     @classmethod
     def dense(cls, A: ddpk.Csr, device: int = 0):
@@ -81,8 +85,9 @@ class DIRE_SOLV:
             pass
 
 
-def _factor_from_dump(d, name, device, fallback_matrix=None, factorize=None):
-    if fallback_matrix is not None and fallback_matrix.shape[0] <= DIRE_SOLV.DENSE_MAX:
+def _factor_from_dump(d, name, device, fallback_matrix=None, factorize=None, dense_max=None):
+    dense_max = DIRE_SOLV.DENSE_MAX if dense_max is None else dense_max
+    if fallback_matrix is not None and fallback_matrix.shape[0] <= dense_max:
         return DIRE_SOLV.dense(fallback_matrix, device)
     if name + ".perm" in d:
         return DIRE_SOLV(d[name + ".perm"], ddpk.get_csr(d, name + ".L"), d[name + ".D"], device)
@@ -223,11 +228,11 @@ class MCONTACT:
                 check(lib.ddpca_admm_set_macro_mg(h, C.c_int(nglob), base.ctypes.data_as(C.POINTER(C.c_long)), macro_mgpis._h))
                 macro_mgpis._h = None  # ownership moved to the ADMM handle
             else:
-                s = _factor_from_dump(d, "coarSolv_D", device, ddpk.get_csr(d, "globCoup"), factorize)
+                s = _factor_from_dump(d, "coarSolv_D", device, ddpk.get_csr(d, "globCoup"), factorize, DIRE_SOLV.DENSE_MAX_COARSE)
                 check(lib.ddpca_admm_set_macro(h, C.c_int(s.n), base.ctypes.data_as(C.POINTER(C.c_long)), s.release()))
         if self.muscSett & 2:   # MCONTACT::MULTISCALE_1 (MCONTACT.h:1672-2343), applied at :2575-2607
             base = np.ascontiguousarray(d["baseReco"], dtype=np.int64)
-            s1 = _factor_from_dump(d, "coarSolv_D_1", device, ddpk.get_csr(d, "globCoup_1"), factorize)
+            s1 = _factor_from_dump(d, "coarSolv_D_1", device, ddpk.get_csr(d, "globCoup_1"), factorize, DIRE_SOLV.DENSE_MAX_COARSE)
             gf1 = np.ascontiguousarray(d["globForc_1"], dtype=np.float64)
             check(lib.ddpca_admm_set_macro1(h, C.c_int(s1.n), base.ctypes.data_as(C.POINTER(C.c_long)), _pd(gf1), s1.release()))
         tm["coarse_solvers"] = time.time() - t_

@@ -32,9 +32,11 @@ inline bool FAIL(const char *what){
 
 // a factorised DIRE_SOLV (Eigen::SimplicialLDLT) -> device solver; small SPD operators are
 // inverted densely on the device instead (no factor needed)
-inline ddpca_ldlt *UPLOAD_SOLVER(int devi, const DIRE_SOLV &solv, const SPM &matr){
+// denseMaxi: interface mass matrices 4096; the coarse problems, solved on every device in every iteration and the
+// part of an iteration that does not shrink with more devices, 32768 (one product instead of staged sparse sweeps)
+inline ddpca_ldlt *UPLOAD_SOLVER(int devi, const DIRE_SOLV &solv, const SPM &matr, long denseMaxi = 4096){
 	ddpca_ldlt *resu = nullptr;
-	if(matr.rows() <= 4096){
+	if(matr.rows() <= denseMaxi){
 		SPM tempMatr = matr;
 		tempMatr.makeCompressed();
 		if(ddpca_ldlt_create_dense(devi, tempMatr.rows(), tempMatr.outerIndexPtr(),
@@ -203,7 +205,7 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 		const int devi = ddpca_admm_group_device(grou, tk);
 		if(macrSwit){
 			if(mc.globCoup.rows() < DIRE_MAXI){// MCONTACT.h:2553-2555
-				ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D, mc.globCoup);
+				ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D, mc.globCoup, 32768);
 				if(soCo == nullptr || ddpca_admm_set_macro(hand, mc.globCoup.rows(), mc.baseReco.data(), soCo) != 0){
 					allGood = FAIL("set_macro");
 				}
@@ -221,7 +223,7 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 			}
 		}
 		if(allGood && elimSwit){// MCONTACT.h:2576,2588
-			ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D_1, mc.globCoup_1);
+			ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D_1, mc.globCoup_1, 32768);
 			if(soCo == nullptr || ddpca_admm_set_macro1(hand, mc.globCoup_1.rows(), mc.baseReco.data(),
 				mc.globForc_1.data(), soCo) != 0){
 				allGood = FAIL("set_macro1");

@@ -137,8 +137,9 @@ int ddpca_mg_gmres(ddpca_mg *, int prec, const double *b, double *x, long *iters
 typedef struct ddpca_ldlt ddpca_ldlt;
 int ddpca_ldlt_create(int device, int n, const int *perm, const int *L_rowptr, const int *L_colidx, const double *L_val,
                       const double *D, ddpca_ldlt **out);
-/* Small SPD operators (interface mass matrices, n <= 16384): no host factor needed -- the dense
- * inverse is built on the device and every solve is one GEMV. */
+/* SPD operators up to 32768 rows (interface mass matrices; the coarse problems, which every rank solves once per
+ * iteration): no host factor needed -- the dense inverse is built on the device (blocked Gauss-Jordan, 8 n^2 bytes)
+ * and every solve is one product. */
 int ddpca_ldlt_create_dense(int device, int n, const int *rowptr, const int *colidx, const double *val, ddpca_ldlt **out);
 int ddpca_ldlt_solve(ddpca_ldlt *, const double *b, double *x);
 int ddpca_ldlt_solve_dev(ddpca_ldlt *, const double *b_dev, double *x_dev);
