@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -938,7 +939,8 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
 {
     L.n = n;
     std::string err;
-    if (!build_level_plan(n, rp, ci, mode, L.plan, err)) return fail(err);
+    if (sub_off && sub_off->size() > 2) { if (!build_level_plan_blocks(n, rp, ci, mode, *sub_off, L.plan, err)) return fail(err); }
+    else if (!build_level_plan(n, rp, ci, mode, L.plan, err)) return fail(err);
     CsrHost Ap;
     permute_csr(n, n, rp, ci, v, L.plan.perm, L.plan.iperm, Ap);
     L.nnz = Ap.nnz();
@@ -1042,11 +1044,23 @@ static int dense_invert_inplace(cudaStream_t st, int n, double *B)
         CU(cudaFuncSetAttribute(k_bgj_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set.fetch_or(bit);
     }
-    double *Dinv = nullptr, *C = nullptr, *R = nullptr;
-    auto cleanup = [&]() { cudaFree(Dinv); cudaFree(C); cudaFree(R); };
-    CUX(cudaMalloc(&Dinv, sizeof(double) * kGjB * kGjB));
-    CUX(cudaMalloc(&C, sizeof(double) * (size_t)n * kGjB));
-    CUX(cudaMalloc(&R, sizeof(double) * (size_t)n * kGjB));
+    // panel workspace (Dinv 64 x 64, C and R n x 64): one per device, grown on demand and kept -- an ADMM set-up
+    // inverts hundreds of small interface mass matrices, and cudaMalloc / cudaFree (which synchronises) per call
+    // cost more than the arithmetic
+    static std::mutex ws_mtx;
+    static double *ws_buf[64] = {nullptr};
+    static size_t ws_len[64] = {0};
+    std::lock_guard<std::mutex> ws_lock(ws_mtx);
+    auto cleanup = [&]() {};
+    const size_t need = (size_t)kGjB * kGjB + 2 * (size_t)n * kGjB;
+    if (ws_len[dev & 63] < need) {
+        CUX(cudaStreamSynchronize(st));
+        cudaFree(ws_buf[dev & 63]);
+        ws_buf[dev & 63] = nullptr; ws_len[dev & 63] = 0;
+        CUX(cudaMalloc(&ws_buf[dev & 63], sizeof(double) * need));
+        ws_len[dev & 63] = need;
+    }
+    double *Dinv = ws_buf[dev & 63], *C = Dinv + kGjB * kGjB, *R = C + (size_t)n * kGjB;
     const int nt = cdiv(n, kGjB);
     for (int k0 = 0; k0 < n; k0 += kGjB) {
         const int nb = std::min(kGjB, n - k0);
@@ -1056,9 +1070,8 @@ static int dense_invert_inplace(cudaStream_t st, int n, double *B)
     }
     dim3 g2(cdiv(n, 256), n);
     k_symmetrize<<<g2, 256, 0, st>>>(n, B);
-    CUX(cudaStreamSynchronize(st));
+    CUX(cudaStreamSynchronize(st));   // the workspace is free again when the lock is released
     CUX(cudaGetLastError());
-    cleanup();
     return 0;
 }
 // Dense inverse of the diagonal block [r0, r0+n) of an SPD operator given as device CSR, written to Bblk (n x n)
@@ -1282,6 +1295,16 @@ int ddpca_plan_create(int n, const int *rowptr, const int *colidx, int smoother_
     ddpca_plan *pl = new ddpca_plan();
     std::string err;
     if (!build_level_plan(n, rowptr, colidx, smoother_mode, pl->p, err)) { delete pl; return fail(err); }
+    *out = pl;
+    return 0;
+}
+int ddpca_plan_create_blocks(int n, const int *rowptr, const int *colidx, int smoother_mode, int nsub, const int *sub_off, ddpca_plan **out)
+{
+    if (!out || !rowptr || !colidx || n < 0 || nsub < 1 || !sub_off || sub_off[0] != 0 || sub_off[nsub] != n) return fail("ddpca_plan_create_blocks: bad argument");
+    ddpca_plan *pl = new ddpca_plan();
+    std::string err;
+    std::vector<int> off(sub_off, sub_off + nsub + 1);
+    if (!build_level_plan_blocks(n, rowptr, colidx, smoother_mode, off, pl->p, err)) { delete pl; return fail(err); }
     *out = pl;
     return 0;
 }

@@ -45,6 +45,10 @@ struct LevelPlan {
 // Returns false and fills err on malformed input (unsorted columns, missing diagonal).
 bool build_level_plan(int n, const int *rp, const int *ci, int mode, LevelPlan &out, std::string &err);
 
+// The same for a block-diagonal level whose blocks are the row ranges [sub_off[s], sub_off[s+1]): blocks are planned
+// in parallel and merged; identical to build_level_plan on the whole level.
+bool build_level_plan_blocks(int n, const int *rp, const int *ci, int mode, const std::vector<int> &sub_off, LevelPlan &out, std::string &err);
+
 // B = Pr * A * Pc^T with sorted columns: row `i` of B is row prow[i] of A, column j of A
 // becomes icol[j].  prow has B.rows entries, icol has A.cols entries.
 void permute_csr(int rows, int cols, const int *rp, const int *ci, const double *v,

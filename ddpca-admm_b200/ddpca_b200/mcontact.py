@@ -30,7 +30,9 @@ class DIRE_SOLV:
     """A factorised Eigen::SimplicialLDLT (typedef DIRE_SOLV, PREP.h:107) whose solve phase runs
     on the device: perm = permutationP().indices(), L = strictly-lower unit factor (CSR), D = vectorD()."""
 
-    DENSE_MAX = 4096   # below this size an SPD operator is inverted densely on the device (one GEMV per solve)
+    # up to this size an SPD operator is inverted densely on the device (8 n^2 bytes; all interface mass solves of a rank
+    # are then ONE block-diagonal product per update); beyond: staged sparse triangular solves with the host factor
+    DENSE_MAX = 8192
     # The coarse problems (macroscopic / interface-eliminated) are solved once per ADMM iteration on EVERY rank: the staged
     # sparse triangular solves cost ~2 ms of launch latency at 23 k rows, one 4.4 GB product 0.7 ms -- and it is the part
     # of an iteration that does not shrink with more GPUs.  HBM is 180 GB; the dense form is used up to this size.

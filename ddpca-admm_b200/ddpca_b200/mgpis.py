@@ -28,10 +28,14 @@ def _f64(a):
 class Plan:
     """Host-side stage plan of one level (ddpca_plan_*): no GPU needed."""
 
-    def __init__(self, A: Csr, mode: int = SMOOTH_MC):
+    def __init__(self, A: Csr, mode: int = SMOOTH_MC, sub_off=None):
         lib = load_library()
         h = C.c_void_p()
-        check(lib.ddpca_plan_create(C.c_int(A.shape[0]), _pi(A.rowptr), _pi(A.colidx), C.c_int(mode), C.byref(h)))
+        if sub_off is None:
+            check(lib.ddpca_plan_create(C.c_int(A.shape[0]), _pi(A.rowptr), _pi(A.colidx), C.c_int(mode), C.byref(h)))
+        else:   # block-diagonal level: blocks planned in parallel and merged
+            so = np.ascontiguousarray(sub_off, dtype=np.int32)
+            check(lib.ddpca_plan_create_blocks(C.c_int(A.shape[0]), _pi(A.rowptr), _pi(A.colidx), C.c_int(mode), C.c_int(len(so) - 1), _pi(so), C.byref(h)))
         n, ng, ns = C.c_int(), C.c_int(), C.c_int()
         check(lib.ddpca_plan_sizes(h, C.byref(n), C.byref(ng), C.byref(ns)))
         self.n, self.ngroups, self.nstages = n.value, ng.value, ns.value

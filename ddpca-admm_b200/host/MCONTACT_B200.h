@@ -32,9 +32,9 @@ inline bool FAIL(const char *what){
 
 // a factorised DIRE_SOLV (Eigen::SimplicialLDLT) -> device solver; small SPD operators are
 // inverted densely on the device instead (no factor needed)
-// denseMaxi: interface mass matrices 4096; the coarse problems, solved on every device in every iteration and the
+// denseMaxi: interface mass matrices 8192; the coarse problems, solved on every device in every iteration and the
 // part of an iteration that does not shrink with more devices, 32768 (one product instead of staged sparse sweeps)
-inline ddpca_ldlt *UPLOAD_SOLVER(int devi, const DIRE_SOLV &solv, const SPM &matr, long denseMaxi = 4096){
+inline ddpca_ldlt *UPLOAD_SOLVER(int devi, const DIRE_SOLV &solv, const SPM &matr, long denseMaxi = 8192){
 	ddpca_ldlt *resu = nullptr;
 	if(matr.rows() <= denseMaxi){
 		SPM tempMatr = matr;

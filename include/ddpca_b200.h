@@ -65,6 +65,9 @@ int ddpca_device_count(void);
  * symmetric permutation that makes every stage a contiguous row range.
  * Exposed so that the ordering can be inspected and tested on a CPU-only box. */
 int ddpca_plan_create(int n, const int *rowptr, const int *colidx, int smoother_mode, ddpca_plan **out);
+/* the same for a block-diagonal level (a batch of subdomains, blocks = row ranges [sub_off[s], sub_off[s+1])): the
+ * blocks are planned in parallel and merged; the result is identical to ddpca_plan_create on the whole level */
+int ddpca_plan_create_blocks(int n, const int *rowptr, const int *colidx, int smoother_mode, int nsub, const int *sub_off, ddpca_plan **out);
 int ddpca_plan_sizes(const ddpca_plan *, int *n, int *ngroups, int *nstages);
 /* perm[new] = old ; group_start[ngroups+1] and stage_start[nstages+1] are in NEW row numbering */
 int ddpca_plan_get(const ddpca_plan *, int *perm, int *group_start, int *stage_start);

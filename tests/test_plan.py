@@ -79,3 +79,23 @@ def test_plan_handles_ragged_groups():
         pl = dd.Plan(a, mode)
         sizes = np.diff(pl.group_start)
         assert set(sizes.tolist()) <= {1, 2, 3} and 1 in sizes and 3 in sizes
+
+
+@pytest.mark.parametrize("mode", [dd.SMOOTH_MC, dd.SMOOTH_LEX])
+def test_block_diagonal_level_planned_by_blocks_equals_whole_level_plan(mode):
+    """A batch of subdomains is one block-diagonal level; its blocks are planned in parallel and merged
+    (build_level_plan_blocks).  The merged plan must be the plan of the whole level: same permutation, groups, stages."""
+    import scipy.sparse as sp
+
+    from tests.helpers import load_golden
+
+    d, meta, A, P = load_golden("beam_3lev")
+    a, b = A[1].to_scipy(), A[2].to_scipy()
+    cat = ddpk.Csr.from_scipy(sp.block_diag([b, a, b], format="csr"))
+    off = np.cumsum([0, b.shape[0], a.shape[0], b.shape[0]])
+    whole = dd.Plan(cat, mode)
+    blocks = dd.Plan(cat, mode, sub_off=off)
+    assert whole.nstages == blocks.nstages and whole.ngroups == blocks.ngroups
+    assert np.array_equal(whole.perm, blocks.perm)
+    assert np.array_equal(whole.group_start, blocks.group_start)
+    assert np.array_equal(whole.stage_start, blocks.stage_start)

@@ -29,7 +29,7 @@ path, meta = bench.generate_workload(args)
 d = ddpk.load(path, copy=False)
 t0 = time.time()
 mc = dd.MCONTACT.from_ddpk(d)
-print("upload s", round(time.time() - t0, 2), flush=True)
+print("upload s", round(time.time() - t0, 2), mc.upload_times, "bodies DOF", sum(mc.body_dof), flush=True)
 lib = load_library()
 names = {0: "bodies", 1: "macro_partial", 2: "macro_apply", 6: "macro1_partial", 7: "macro1_apply", 3: "traces", 4: "interface", 5: "monitor"}
 order = [0] + ([1, 2] if mc.muscSett & 1 else []) + ([6, 7] if mc.muscSett & 2 else []) + [3, 4, 5]
