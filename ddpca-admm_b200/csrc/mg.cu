@@ -1108,8 +1108,14 @@ struct ddpca_ldlt : Engine {
     int tail_T = 0, tail_stage = 0, tail_g0 = 0, tail_n1 = 0;
     double *tail_Minv = nullptr, *tail_rhs = nullptr;
     int *tail_k1 = nullptr;
+    // the staged solve is hundreds of tiny launches: replayed as ONE graph when called again with the same operands
+    cudaGraphExec_t solve_graph = nullptr;
+    const double *graph_b = nullptr;
+    double *graph_x = nullptr;
+    long graph_nodes = 0;
 };
 
+static void ldlt_solve_enqueue(Engine *e, ddpca_ldlt *s, const double *b_dev, double *x_dev, const int *done);
 static void ldlt_solve_on(Engine *e, ddpca_ldlt *s, const double *b_dev, double *x_dev, const int *done)
 {
     int n = s->n;
@@ -1117,6 +1123,30 @@ static void ldlt_solve_on(Engine *e, ddpca_ldlt *s, const double *b_dev, double 
         KL(e, DDPCA_K_COARSE, 0, 8.0 * n * (double)n + 16.0 * n, (k_dense_gemv<<<cdiv((long)n * 32, 256), 256, 0, e->stream>>>(n, s->Binv, b_dev, x_dev, done)));
         return;
     }
+    if (e->profile || e->capturing || done != nullptr || std::getenv("DDPCA_NO_LDLT_GRAPH")) { ldlt_solve_enqueue(e, s, b_dev, x_dev, done); return; }
+    if (s->solve_graph && (s->graph_b != b_dev || s->graph_x != x_dev)) { cudaGraphExecDestroy(s->solve_graph); s->solve_graph = nullptr; }
+    if (!s->solve_graph) {
+        cudaGraph_t g = nullptr;
+        e->capturing = true;
+        const long before = e->captured_nodes;
+        cudaError_t err = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+        if (err == cudaSuccess) {
+            ldlt_solve_enqueue(e, s, b_dev, x_dev, nullptr);
+            err = cudaStreamEndCapture(e->stream, &g);
+        }
+        e->capturing = false;
+        s->graph_nodes = e->captured_nodes - before;
+        if (err == cudaSuccess && cudaGraphInstantiate(&s->solve_graph, g, 0) == cudaSuccess) { s->graph_b = b_dev; s->graph_x = x_dev; }
+        else { s->solve_graph = nullptr; cudaGetLastError(); }
+        if (g) cudaGraphDestroy(g);
+        if (!s->solve_graph) { ldlt_solve_enqueue(e, s, b_dev, x_dev, nullptr); return; }
+    }
+    if (cudaGraphLaunch(s->solve_graph, e->stream) != cudaSuccess) { if (e->launch_err.empty()) e->launch_err = "ddpca_ldlt: graph launch failed"; return; }
+    e->launches += s->graph_nodes;
+}
+static void ldlt_solve_enqueue(Engine *e, ddpca_ldlt *s, const double *b_dev, double *x_dev, const int *done)
+{
+    int n = s->n;
     double tri_bytes = 12.0 * s->nnzL + 44.0 * n;
     KL(e, DDPCA_K_VECTOR, 0, 20.0 * n, (k_scatter<<<cdiv(n, 256), 256, 0, e->stream>>>(n, s->m_in, b_dev, s->lo.b)));
     (void)tri_bytes;
@@ -1162,6 +1192,7 @@ static void ldlt_free(ddpca_ldlt *s)
     if (!s) return;
     cudaSetDevice(s->device);
     free_level(s->lo); free_level(s->up);
+    if (s->solve_graph) cudaGraphExecDestroy(s->solve_graph);
     cudaFree(s->m_in); cudaFree(s->m_mid); cudaFree(s->m_out); cudaFree(s->dinv_lo); cudaFree(s->Binv); cudaFree(s->tail_Minv); cudaFree(s->tail_rhs); cudaFree(s->tail_k1);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
@@ -1229,7 +1260,9 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
         // (~0.1 ms) instead of 2 x 5 929 dependent steps, and 269 wide wavefronts remain.  The bounds keep
         // the set-up (an unblocked Gauss-Jordan inversion of the block, ~T^3 * 16 bytes of traffic) at seconds.
         const LevelPlan &pl = s->lo.plan;
-        const int kTailWidth = 16, kTailMaxRows = 9216;
+        // (up to 24 576 rows = 4.8 GB: BEAM DD with 3.5 M DOF has a coarse factor of 76 860 rows whose last 17 874 rows sit in
+        // 16 314 of its 16 632 wavefronts; with the round-1 limit of 9 216 rows 7 416 wavefronts remained and a solve took 36 ms)
+        const int kTailWidth = 16, kTailMaxRows = 24576;
         int ns = pl.nstages(), st = ns, T = 0;
         while (st > 0) {
             const int wdt = pl.stage_group[st] - pl.stage_group[st - 1];   // single_rows: groups are rows
