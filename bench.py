@@ -3,8 +3,9 @@
 solve, ADMM solve wall time, strong scaling over 1/2/4/8 GPUs (BASELINE.json metric).
 
 Workload (fixed, whatever --gpus says: STRONG scaling): the reference's BEAM example with domain decomposition
-(examples/BEAM.h:390-609), domaNumb 8x2x1 = 16 subdomains of ~58 k DOF joined by 22 tied interfaces, globLeve 3
-(0.93 M DOF, 4 multigrid levels per subdomain), macroscopic coarse problem.  The reference's own host C++ does
+(examples/BEAM.h:390-609), domaNumb 8x2x1 = 16 subdomains of ~217 k DOF joined by 22 tied interfaces, globLeve 3 on
+a coarsest mesh of 128x8x2 elements (synthetic refinement of the example's 64x4x2: 3.47 M DOF, 4 multigrid levels
+per subdomain), macroscopic coarse problem of 76 860 rows.  The reference's own host C++ does
 mesh, contact search, MULTIGRID::STIF_MATR/CONSTRAINT and MCONTACT::ESTABLISH (set-up, out of scope of the GPU
 path) through the prebuilt driver oracle/_ref/beam_admm, outside the timed region; the same process then runs
 the untouched reference loop for a few iterations on this box's host cores (the CPU baseline).
@@ -191,7 +192,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--glob", type=int, default=3, help="BEAM globLeve (3: 0.93 M DOF in all)")
     ap.add_argument("--doma", default="8,2,1", help="BEAM domaNumb (subdomains per direction)")
-    ap.add_argument("--divi", default="", help="BEAM diviNumb of the coarsest mesh (default 64,4,2)")
+    ap.add_argument("--divi", default="128,8,2", help="BEAM diviNumb of the coarsest mesh (the example's own is 64,4,2: a quarter of the DOF)")
     ap.add_argument("--musc", type=int, default=1, help="coarse-space correction: 1 macroscopic problem, 2 interface-eliminated, 3 both, 0 none")
     ap.add_argument("--cpu-iters", type=int, default=4, help="reference iterations run on the host cores for the CPU baseline")
     ap.add_argument("--smoother", default="mc", choices=["mc", "lex"])
@@ -361,7 +362,7 @@ def main():
             traffic = None
             try:
                 tr = json.load(open(os.path.join(ROOT, "profiles", "NCU_TRAFFIC.json")))
-                traffic = tr.get(f"beam_dd_g{args.glob}_{args.doma.replace(',', 'x')}_n{world}", {}).get(f"{kname}@L{lvl}")
+                traffic = tr.get(f"beam_dd_g{args.glob}_{args.doma.replace(',', 'x')}_d{args.divi.replace(',', 'x')}_n{world}", {}).get(f"{kname}@L{lvl}")
             except Exception:
                 pass
             roofline = {"bound": "hbm", "kernel": f"{kname}@L{lvl}", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
