@@ -1204,6 +1204,7 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail("no CUDA device: libddpca_b200 has no CPU fallback"); }
     if (device < 0 || device >= ndev) return fail("device index out of range");
     CU(cudaSetDevice(device));
+    StageTimer tm("ldlt");
     // T_lo = I + L (diagonal last in each row), T_up = I + L^T (diagonal first)
     CsrHost Tlo, Lh, Lt, Tup;
     Lh.rows = Lh.cols = n;
@@ -1239,6 +1240,7 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
     s->lo.wide_rows = s->up.wide_rows = ((double)Lrp[n] / n > 48.0);   // long fill-in rows
     if (setup_level(s->lo, n, Tlo.rp.data(), Tlo.ci.data(), Tlo.v.data(), DDPCA_SMOOTH_LEX, false, true) ||
         setup_level(s->up, n, Tup.rp.data(), Tup.ci.data(), Tup.v.data(), DDPCA_SMOOTH_LEX, false, true)) { ldlt_free(s); return 1; }
+    tm.lap("two staged triangular levels");
     s->single_rows = (s->lo.plan.ngroups() == n && s->up.plan.ngroups() == n);
     std::vector<int> m_in(n), m_mid(n), m_out(n);
     std::vector<double> dinv(n);
@@ -1288,6 +1290,7 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
                 k1[t] = kk;
                 D2[t] = D[pl.perm[i]];
             }
+            tm.lap("dense tail: host assembly");
             double *dL = nullptr, *dD = nullptr;
             bool ok = cudaMalloc(&dL, sizeof(double) * (size_t)T * T) == cudaSuccess && cudaMalloc(&dD, sizeof(double) * T) == cudaSuccess &&
                       cudaMalloc(&s->tail_Minv, sizeof(double) * (size_t)T * T) == cudaSuccess && cudaMalloc(&s->tail_rhs, sizeof(double) * T) == cudaSuccess;
@@ -1300,6 +1303,7 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
             }
             cudaFree(dL);
             cudaFree(dD);
+            tm.lap("dense tail: product + inverse");
             if (ok) { s->tail_T = T; s->tail_stage = st; s->tail_g0 = g0; s->tail_n1 = n1; }
             else { cudaFree(s->tail_Minv); cudaFree(s->tail_rhs); s->tail_Minv = s->tail_rhs = nullptr; cudaGetLastError(); }
         }
