@@ -75,7 +75,10 @@ def run_reference_driver(args, ref_iters, out):
         cmd += ["--divi", args.divi]
     cmd += ["--out", out] if out else ["--nomat"]
     t0 = time.time()
-    txt = subprocess.check_output(cmd, cwd=workload_cache_dir()).decode()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference is a host OpenMP code and gets the whole box
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = os.environ.get("DDPCA_REF_THREADS", str(os.cpu_count() or 1))
+    txt = subprocess.check_output(cmd, cwd=workload_cache_dir(), env=env).decode()
     meta = json.loads(txt.strip().splitlines()[-1])
     meta["driver_wall_s"] = time.time() - t0
     return meta
@@ -204,6 +207,10 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+
+    # host side of the upload (planning, layouts: OpenMP inside libddpca_b200): an even share of the cores per rank
+    # (torchrun's default of one thread per worker would serialise it); must be set before the library is loaded
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
 
     import numpy as np
     import torch

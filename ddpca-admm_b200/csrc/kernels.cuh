@@ -402,6 +402,32 @@ __global__ void __launch_bounds__(1024) k_tri_multi(LvlView A, const int *__rest
     }
 }
 
+// One WIDE wavefront of such a triangular solve: one CTA of 128 threads per row.  The fill-in rows of a factor hold
+// hundreds to thousands of entries and every wavefront is one step of a dependency chain, so what counts is the
+// latency of a row, not occupancy: 128 threads stream a 2 000-entry row in 8 steps where one warp needs 31.
+template <bool FWD>
+__global__ void __launch_bounds__(128) k_tri_stage(LvlView A, int g0, const double *__restrict__ b, double *x, const int *done)
+{
+    if (done && *done) return;
+    __shared__ double part[4];
+    const GroupMeta m = ld_meta(A.meta + g0 + blockIdx.x);
+    const int kb = FWD ? 0 : ((m.kd + 1) & ~1), ke = FWD ? m.kd : m.len;
+    const int *ci = A.ci + m.cptr;
+    const double *v = A.v + m.voff;
+    double acc = 0.0;
+#pragma unroll 2
+    for (int k = kb + 2 * (int)threadIdx.x; k < ke; k += 256) {
+        const int2 c = ld_stream2(ci + k);
+        const double2 a = ld_stream2(v + k);
+        if (FWD) { acc += a.x * x[c.x]; if (k + 1 < ke) acc += a.y * x[c.y]; }
+        else { if (k > m.kd) acc += a.x * x[c.x]; acc += a.y * x[c.y]; }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) x[m.row0] = b[m.row0] - ((part[0] + part[1]) + (part[2] + part[3]));
+}
+
 // K2: r = b - (p1 + L x)   (MGPIS.h:92) -- strictly-lower half only, one sub-warp per group
 __global__ void __launch_bounds__(256, DDPCA_MIN_BLOCKS) k_resid_lower(LvlView A, const double *__restrict__ b, const double *__restrict__ p1,
                                                      const double *__restrict__ x, double *__restrict__ r, const int *done)
@@ -746,6 +772,40 @@ __global__ void __launch_bounds__(256) k_bgj_update(int n, int k0, int nb, doubl
             if (i >= n) continue;
             if (colK) { if (tx * 4 + c < nb) A[(size_t)i * n + j] = -acc[r][c]; }
             else if (j < n) A[(size_t)i * n + j] -= acc[r][c];
+        }
+}
+// dense tail of a sparse LDL^T factor (set-up): M = L22 diag(D2) L22^T on 64x64 tiles with the 4x4 register blocks of the
+// inversion kernels.  L22 is unit lower triangular: only k-tiles up to the column tile contribute; lower tiles are
+// computed and mirrored.
+__global__ void __launch_bounds__(256) k_ldl_tail_product64(int T, const double *__restrict__ L22, const double *__restrict__ D2, double *__restrict__ M)
+{
+    if (blockIdx.x > blockIdx.y) return;   // lower triangle of tiles
+    extern __shared__ double gj_sm[];
+    double (*As)[kGjB + 1] = reinterpret_cast<double (*)[kGjB + 1]>(gj_sm);
+    double (*Bs)[kGjB + 1] = As + kGjB;
+    const int i0 = blockIdx.y * kGjB, j0 = blockIdx.x * kGjB, tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4] = {};
+    const int kmax = min(j0 + kGjB, T);
+    for (int k0 = 0; k0 < kmax; k0 += kGjB) {
+        for (int e = threadIdx.x; e < kGjB * kGjB; e += 256) {
+            const int r = e / kGjB, c = e % kGjB;
+            const int k = k0 + c;
+            As[r][c] = (i0 + r < T && k < T) ? L22[(size_t)(i0 + r) * T + k] * D2[k] : 0.0;      // (L22 D)[i, k]
+            Bs[c][r] = (j0 + r < T && k < T) ? L22[(size_t)(j0 + r) * T + k] : 0.0;              // L22^T[k, j]
+        }
+        __syncthreads();
+        gj_tile_mma(As, Bs, kGjB, ty, tx, acc);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int i = i0 + ty * 4 + r, j = j0 + tx * 4 + c;
+            if (i < T && j < T) {
+                M[(size_t)i * T + j] = acc[r][c];
+                if (blockIdx.x != blockIdx.y) M[(size_t)j * T + i] = acc[r][c];
+            }
         }
 }
 __global__ void k_symmetrize(int n, double *__restrict__ a)

@@ -1158,7 +1158,7 @@ static void ldlt_solve_enqueue(Engine *e, ddpca_ldlt *s, const double *b_dev, do
             if (sg.s0 >= slim) break;
             if (sg.s1 > slim) sg.s1 = slim;   // only multi segments can straddle the tail boundary (tail stages hold one row)
             if (sg.multi) KL(e, DDPCA_K_SWEEP_FWD, 0, sg.bytes_lo, (k_tri_multi<true><<<1, 1024, 0, e->stream>>>(s->lo.view(), s->lo.stage_group, sg.s0, sg.s1, s->lo.b, s->lo.x, done)));
-            else if (s->lo.wide_rows) KL(e, DDPCA_K_SWEEP_FWD, 0, sg.bytes_lo, (k_sweep_fwd_stage<true, 32><<<cdiv((long)(sg.g1 - sg.g0) * 32, 256), 256, 0, e->stream>>>(s->lo.view(), sg.g0, sg.g1, s->lo.b, s->lo.x, s->lo.p1, done)));
+            else if (s->lo.wide_rows) KL(e, DDPCA_K_SWEEP_FWD, 0, sg.bytes_lo, (k_tri_stage<true><<<sg.g1 - sg.g0, 128, 0, e->stream>>>(s->lo.view(), sg.g0, s->lo.b, s->lo.x, done)));
             else KL(e, DDPCA_K_SWEEP_FWD, 0, sg.bytes_lo, (k_sweep_fwd_stage<true><<<cdiv((long)(sg.g1 - sg.g0) * GL, 256), 256, 0, e->stream>>>(s->lo.view(), sg.g0, sg.g1, s->lo.b, s->lo.x, s->lo.p1, done)));
         }
     } else {
@@ -1178,7 +1178,7 @@ static void ldlt_solve_enqueue(Engine *e, ddpca_ldlt *s, const double *b_dev, do
             if (sg.s0 >= slim) continue;
             if (sg.s1 > slim) sg.s1 = slim;
             if (sg.multi) KL(e, DDPCA_K_SWEEP_BWD, 0, sg.bytes_up, (k_tri_multi<false><<<1, 1024, 0, e->stream>>>(s->up.view(), s->up.stage_group, sg.s0, sg.s1, s->up.p1, s->up.x, done)));
-            else if (s->up.wide_rows) KL(e, DDPCA_K_SWEEP_BWD, 0, sg.bytes_up, (k_sweep_bwd_stage<32><<<cdiv((long)(sg.g1 - sg.g0) * 32, 256), 256, 0, e->stream>>>(s->up.view(), sg.g0, sg.g1, s->up.p1, s->up.x, done)));
+            else if (s->up.wide_rows) KL(e, DDPCA_K_SWEEP_BWD, 0, sg.bytes_up, (k_tri_stage<false><<<sg.g1 - sg.g0, 128, 0, e->stream>>>(s->up.view(), sg.g0, s->up.p1, s->up.x, done)));
             else KL(e, DDPCA_K_SWEEP_BWD, 0, sg.bytes_up, (k_sweep_bwd_stage<<<cdiv((long)(sg.g1 - sg.g0) * GL, 256), 256, 0, e->stream>>>(s->up.view(), sg.g0, sg.g1, s->up.p1, s->up.x, done)));
         }
     } else {
@@ -1274,33 +1274,52 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
         }
         if (T >= 512) {
             int g0 = pl.stage_group[st], n1 = pl.group_start[g0];
-            // dense unit-lower L22 and the split position k1 of every tail row, from the permuted I+L
-            CsrHost Tp;
-            permute_csr(n, n, Tlo.rp.data(), Tlo.ci.data(), Tlo.v.data(), pl.perm, pl.iperm, Tp);
-            std::vector<double> L22((size_t)T * T, 0.0), D2(T);
+            // unit-lower L22 (the tail rows' couplings among themselves) as CSR and the number k1 of couplings of every tail
+            // row to the sparse part, from the permuted I+L -- only the T tail rows are visited; the dense form is
+            // assembled on the device
+            CsrHost Tail;
+            Tail.rows = Tail.cols = T;
+            Tail.rp.assign(T + 1, 0);
+            std::vector<double> D2(T);
             std::vector<int> k1(T);
+#pragma omp parallel for schedule(static)
             for (int t = 0; t < T; t++) {
-                int i = n1 + t;
-                int kk = 0;
-                for (int p = Tp.rp[i]; p < Tp.rp[i + 1]; p++) {
-                    int c = Tp.ci[p];
-                    if (c < n1) kk++;
-                    else L22[(size_t)t * T + (c - n1)] = Tp.v[p];   // includes the unit diagonal
-                }
+                const int old = pl.perm[n1 + t];
+                int kk = 0, in = 0;
+                for (int p = Tlo.rp[old]; p < Tlo.rp[old + 1]; p++) { if (pl.iperm[Tlo.ci[p]] < n1) kk++; else in++; }
                 k1[t] = kk;
-                D2[t] = D[pl.perm[i]];
+                Tail.rp[t + 1] = in;
+                D2[t] = D[old];
+            }
+            for (int t = 0; t < T; t++) Tail.rp[t + 1] += Tail.rp[t];
+            Tail.ci.resize(Tail.rp[T]);
+            Tail.v.resize(Tail.rp[T]);
+#pragma omp parallel for schedule(static)
+            for (int t = 0; t < T; t++) {
+                const int old = pl.perm[n1 + t];
+                int q = Tail.rp[t];
+                for (int p = Tlo.rp[old]; p < Tlo.rp[old + 1]; p++) {
+                    const int c = pl.iperm[Tlo.ci[p]];
+                    if (c >= n1) { Tail.ci[q] = c - n1; Tail.v[q] = Tlo.v[p]; q++; }   // includes the unit diagonal
+                }
             }
             tm.lap("dense tail: host assembly");
             double *dL = nullptr, *dD = nullptr;
+            DevCsr dTail;
             bool ok = cudaMalloc(&dL, sizeof(double) * (size_t)T * T) == cudaSuccess && cudaMalloc(&dD, sizeof(double) * T) == cudaSuccess &&
-                      cudaMalloc(&s->tail_Minv, sizeof(double) * (size_t)T * T) == cudaSuccess && cudaMalloc(&s->tail_rhs, sizeof(double) * T) == cudaSuccess;
+                      cudaMalloc(&s->tail_Minv, sizeof(double) * (size_t)T * T) == cudaSuccess && cudaMalloc(&s->tail_rhs, sizeof(double) * T) == cudaSuccess &&
+                      upload_csr(Tail, dTail) == 0;
             if (ok) {
-                cudaMemcpy(dL, L22.data(), sizeof(double) * (size_t)T * T, cudaMemcpyHostToDevice);
-                cudaMemcpy(dD, D2.data(), sizeof(double) * T, cudaMemcpyHostToDevice);
-                dim3 gt(cdiv(T, 32), cdiv(T, 32));
-                k_ldl_tail_product<<<gt, 1024, 0, s->stream>>>(T, dL, dD, s->tail_Minv);
-                ok = dense_invert_inplace(s->stream, T, s->tail_Minv) == 0 && upload_vec(k1, &s->tail_k1) == 0;
+                cudaMemsetAsync(dL, 0, sizeof(double) * (size_t)T * T, s->stream);
+                k_csr_to_dense<<<cdiv(T, 128), 128, 0, s->stream>>>(dTail.view(), 0, T, dL);
+                cudaMemcpyAsync(dD, D2.data(), sizeof(double) * T, cudaMemcpyHostToDevice, s->stream);
+                const size_t smem = sizeof(double) * 2 * kGjB * (kGjB + 1);
+                ok = cudaFuncSetAttribute(k_ldl_tail_product64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+                dim3 gt(cdiv(T, kGjB), cdiv(T, kGjB));
+                if (ok) k_ldl_tail_product64<<<gt, 256, smem, s->stream>>>(T, dL, dD, s->tail_Minv);
+                ok = ok && dense_invert_inplace(s->stream, T, s->tail_Minv) == 0 && upload_vec(k1, &s->tail_k1) == 0;
             }
+            free_csr(dTail);
             cudaFree(dL);
             cudaFree(dD);
             tm.lap("dense tail: product + inverse");
