@@ -935,11 +935,12 @@ static int build_segments(Level &L, const GroupLayoutHost &G)
 
 // Plan + permute + group layout + upload of one operator level (device must be current).
 static int setup_level(Level &L, int n, const int *rp, const int *ci, const double *v, int mode, bool keep_csr, bool group_layout,
-                       const std::vector<int> *sub_off = nullptr)
+                       const std::vector<int> *sub_off = nullptr, const LevelPlan *given_plan = nullptr)
 {
     L.n = n;
     std::string err;
-    if (sub_off && sub_off->size() > 2) { if (!build_level_plan_blocks(n, rp, ci, mode, *sub_off, L.plan, err)) return fail(err); }
+    if (given_plan) L.plan = *given_plan;
+    else if (sub_off && sub_off->size() > 2) { if (!build_level_plan_blocks(n, rp, ci, mode, *sub_off, L.plan, err)) return fail(err); }
     else if (!build_level_plan(n, rp, ci, mode, L.plan, err)) return fail(err);
     CsrHost Ap;
     permute_csr(n, n, rp, ci, v, L.plan.perm, L.plan.iperm, Ap);
@@ -1238,8 +1239,11 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
     if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail("stream creation failed"); }
     s->stream = s->own_stream;
     s->lo.wide_rows = s->up.wide_rows = ((double)Lrp[n] / n > 48.0);   // long fill-in rows
-    if (setup_level(s->lo, n, Tlo.rp.data(), Tlo.ci.data(), Tlo.v.data(), DDPCA_SMOOTH_LEX, false, true) ||
-        setup_level(s->up, n, Tup.rp.data(), Tup.ci.data(), Tup.v.data(), DDPCA_SMOOTH_LEX, false, true)) { ldlt_free(s); return 1; }
+    LevelPlan tri;
+    build_tri_plan(n, Lrp, Lci, tri);   // the wavefronts of both factors (DDPCA_LDLT_GENERIC_PLAN: through the general planner)
+    const LevelPlan *given = std::getenv("DDPCA_LDLT_GENERIC_PLAN") ? nullptr : &tri;
+    if (setup_level(s->lo, n, Tlo.rp.data(), Tlo.ci.data(), Tlo.v.data(), DDPCA_SMOOTH_LEX, false, true, nullptr, given) ||
+        setup_level(s->up, n, Tup.rp.data(), Tup.ci.data(), Tup.v.data(), DDPCA_SMOOTH_LEX, false, true, nullptr, given)) { ldlt_free(s); return 1; }
     tm.lap("two staged triangular levels");
     s->single_rows = (s->lo.plan.ngroups() == n && s->up.plan.ngroups() == n);
     std::vector<int> m_in(n), m_mid(n), m_out(n);
@@ -1361,6 +1365,17 @@ int ddpca_plan_create_blocks(int n, const int *rowptr, const int *colidx, int sm
     std::string err;
     std::vector<int> off(sub_off, sub_off + nsub + 1);
     if (!build_level_plan_blocks(n, rowptr, colidx, smoother_mode, off, pl->p, err)) { delete pl; return fail(err); }
+    *out = pl;
+    return 0;
+}
+int ddpca_plan_create_tri(int n, const int *L_rowptr, const int *L_colidx, ddpca_plan **out)
+{
+    if (!out || !L_rowptr || !L_colidx || n < 0) return fail("ddpca_plan_create_tri: bad argument");
+    for (int i = 0; i < n; i++)
+        for (int p = L_rowptr[i]; p < L_rowptr[i + 1]; p++)
+            if (L_colidx[p] < 0 || L_colidx[p] >= i) return fail("ddpca_plan_create_tri: L must be strictly lower");
+    ddpca_plan *pl = new ddpca_plan();
+    build_tri_plan(n, L_rowptr, L_colidx, pl->p);
     *out = pl;
     return 0;
 }

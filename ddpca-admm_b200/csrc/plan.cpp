@@ -204,6 +204,32 @@ bool build_level_plan_blocks(int n, const int *rp, const int *ci, int mode, cons
     return true;
 }
 
+// Wavefront plan of a unit triangular factor I + L (and of I + L^T, which has the same one): single-row groups,
+// stage[i] = 1 + max stage[j] over the strictly-lower couplings j of row i.  This is what build_level_plan(LEX)
+// returns for these operators, without building and symmetrising a 2 x nnz edge list.
+void build_tri_plan(int n, const int *Lrp, const int *Lci, LevelPlan &out)
+{
+    out = LevelPlan();
+    out.n = n;
+    std::vector<int> stage(n, 0);
+    int nstages = n ? 1 : 0;
+    for (int i = 0; i < n; i++) {
+        int lv = 0;
+        for (int p = Lrp[i]; p < Lrp[i + 1]; p++) lv = std::max(lv, stage[Lci[p]] + 1);
+        stage[i] = lv;
+        nstages = std::max(nstages, lv + 1);
+    }
+    out.stage_group.assign(nstages + 1, 0);
+    for (int i = 0; i < n; i++) out.stage_group[stage[i] + 1]++;
+    for (int s = 0; s < nstages; s++) out.stage_group[s + 1] += out.stage_group[s];
+    out.perm.resize(n);
+    out.iperm.resize(n);
+    std::vector<int> fill(out.stage_group.begin(), out.stage_group.end() - 1);
+    for (int i = 0; i < n; i++) { const int r = fill[stage[i]]++; out.perm[r] = i; out.iperm[i] = r; }
+    out.group_start.resize(n + 1);
+    std::iota(out.group_start.begin(), out.group_start.end(), 0);
+}
+
 void permute_csr(int rows, int cols, const int *rp, const int *ci, const double *v,
                  const std::vector<int> &prow, const std::vector<int> &icol, CsrHost &out)
 {

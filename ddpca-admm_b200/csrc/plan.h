@@ -49,6 +49,10 @@ bool build_level_plan(int n, const int *rp, const int *ci, int mode, LevelPlan &
 // in parallel and merged; identical to build_level_plan on the whole level.
 bool build_level_plan_blocks(int n, const int *rp, const int *ci, int mode, const std::vector<int> &sub_off, LevelPlan &out, std::string &err);
 
+// LEX plan of the unit triangular factors I + L and I + L^T of a sparse LDL^T (L strictly lower, CSR): the
+// dependency wavefronts, single-row groups; equal to build_level_plan(..., LEX, ...) on either operator.
+void build_tri_plan(int n, const int *Lrp, const int *Lci, LevelPlan &out);
+
 // B = Pr * A * Pc^T with sorted columns: row `i` of B is row prow[i] of A, column j of A
 // becomes icol[j].  prow has B.rows entries, icol has A.cols entries.
 void permute_csr(int rows, int cols, const int *rp, const int *ci, const double *v,

@@ -20,7 +20,7 @@ def library_path() -> str:
 # every symbol include/ddpca_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "ddpca_last_error", "ddpca_abi_version", "ddpca_device_count",
-    "ddpca_plan_create", "ddpca_plan_create_blocks", "ddpca_plan_sizes", "ddpca_plan_get", "ddpca_plan_destroy",
+    "ddpca_plan_create", "ddpca_plan_create_blocks", "ddpca_plan_create_tri", "ddpca_plan_sizes", "ddpca_plan_get", "ddpca_plan_destroy",
     "ddpca_mg_create", "ddpca_mg_create_batch", "ddpca_mg_batch_result", "ddpca_mg_destroy", "ddpca_mg_pcg", "ddpca_mg_pcg_dev",
     "ddpca_mg_vcycle", "ddpca_mg_spmv", "ddpca_mg_restrict", "ddpca_mg_prolong_add",
     "ddpca_mg_coarse_solve", "ddpca_mg_mult_solv", "ddpca_mg_bicgstab", "ddpca_mg_gmres",

@@ -28,10 +28,12 @@ def _f64(a):
 class Plan:
     """Host-side stage plan of one level (ddpca_plan_*): no GPU needed."""
 
-    def __init__(self, A: Csr, mode: int = SMOOTH_MC, sub_off=None):
+    def __init__(self, A: Csr, mode: int = SMOOTH_MC, sub_off=None, tri=False):
         lib = load_library()
         h = C.c_void_p()
-        if sub_off is None:
+        if tri:   # A = strictly lower factor L: wavefronts of I + L (and of I + L^T)
+            check(lib.ddpca_plan_create_tri(C.c_int(A.shape[0]), _pi(A.rowptr), _pi(A.colidx), C.byref(h)))
+        elif sub_off is None:
             check(lib.ddpca_plan_create(C.c_int(A.shape[0]), _pi(A.rowptr), _pi(A.colidx), C.c_int(mode), C.byref(h)))
         else:   # block-diagonal level: blocks planned in parallel and merged
             so = np.ascontiguousarray(sub_off, dtype=np.int32)

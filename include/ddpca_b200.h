@@ -68,6 +68,9 @@ int ddpca_plan_create(int n, const int *rowptr, const int *colidx, int smoother_
 /* the same for a block-diagonal level (a batch of subdomains, blocks = row ranges [sub_off[s], sub_off[s+1])): the
  * blocks are planned in parallel and merged; the result is identical to ddpca_plan_create on the whole level */
 int ddpca_plan_create_blocks(int n, const int *rowptr, const int *colidx, int smoother_mode, int nsub, const int *sub_off, ddpca_plan **out);
+/* wavefront plan of the unit triangular factors I + L and I + L^T of a sparse LDL^T factorisation (L strictly lower,
+ * CSR), as ddpca_ldlt_create uses it; equal to ddpca_plan_create(LEX) on either operator */
+int ddpca_plan_create_tri(int n, const int *L_rowptr, const int *L_colidx, ddpca_plan **out);
 int ddpca_plan_sizes(const ddpca_plan *, int *n, int *ngroups, int *nstages);
 /* perm[new] = old ; group_start[ngroups+1] and stage_start[nstages+1] are in NEW row numbering */
 int ddpca_plan_get(const ddpca_plan *, int *perm, int *group_start, int *stage_start);

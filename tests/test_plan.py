@@ -99,3 +99,23 @@ def test_block_diagonal_level_planned_by_blocks_equals_whole_level_plan(mode):
     assert np.array_equal(whole.perm, blocks.perm)
     assert np.array_equal(whole.group_start, blocks.group_start)
     assert np.array_equal(whole.stage_start, blocks.stage_start)
+
+
+def test_triangular_factor_plan_equals_lex_plan_of_both_factors():
+    """ddpca_ldlt_create plans the two triangular solves with a direct wavefront computation on L (build_tri_plan);
+    it must be the LEX plan of I + L and of I + L^T (same permutation, single-row groups, same stages)."""
+    import scipy.sparse as sp
+
+    n = 14
+    lap = sp.kronsum(sp.diags([-1, 2.5, -1], [-1, 0, 1], shape=(n, n)), sp.diags([-1, 2.5, -1], [-1, 0, 1], shape=(n, n))).toarray()
+    c = np.linalg.cholesky(lap)
+    Ls = sp.csr_matrix(np.tril(np.where(np.abs(c) > 1e-12, c, 0.0), -1))
+    Ls.sort_indices()
+    eye = sp.identity(n * n, format="csr")
+    tri = dd.Plan(ddpk.Csr.from_scipy(Ls), tri=True)
+    for T in (Ls + eye, Ls.T.tocsr() + eye):
+        T = T.tocsr()
+        T.sort_indices()
+        ref = dd.Plan(ddpk.Csr.from_scipy(T), dd.SMOOTH_LEX)
+        assert ref.ngroups == n * n == tri.ngroups and ref.nstages == tri.nstages
+        assert np.array_equal(ref.perm, tri.perm) and np.array_equal(ref.stage_start, tri.stage_start)
