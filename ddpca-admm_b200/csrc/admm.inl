@@ -31,6 +31,7 @@ struct HostSide {
     bool has[DDPCA_OP_COUNT] = {};
     ddpca_ldlt *mass = nullptr, *mass_pena = nullptr;
     int nc = 0;          // d * n_c
+    bool iterative = false;   // mass solves by Jacobi-PCG on the device instead of a factor (MCONTACT.h:2678-2683,2698-2703)
     bool local = true;   // side lives with its body
     int coff = -1;       // offset in the AUX / LAGR parts of STATE
 };
@@ -161,6 +162,11 @@ struct ddpca_admm : Engine {
     int *side_off_d = nullptr;
     double **mass_ptr_d = nullptr, **pena_ptr_d = nullptr;
     std::vector<std::pair<int, int>> sparse_mass, sparse_pena;   // (ts, tv) of sides whose solver is not dense
+    // sides without a factor (the reference: rows >= DIRE_MAXI, Eigen CG with the diagonal preconditioner): one batched
+    // Jacobi-PCG over all of them per update; they are numbered last, so their vectors are one contiguous range
+    ddpca_mg *pcg_mass = nullptr, *pcg_pena = nullptr;
+    int it_off = 0, it_rows = 0;
+    ddpca_mg *coar1_mg = nullptr;   // interface-eliminated problem by MG-PCG (globCoup_1 beyond DIRE_MAXI rows, MCONTACT.h:2593-2595)
     // coarse problems
     int nglob = 0;
     std::vector<long> baseReco;
@@ -207,6 +213,9 @@ static void admm_free(ddpca_admm *h)
     ldlt_free(h->coar);
     if (h->coar_mg) ddpca_mg_destroy(h->coar_mg);
     ldlt_free(h->coar1);
+    if (h->coar1_mg) ddpca_mg_destroy(h->coar1_mg);
+    if (h->pcg_mass) ddpca_mg_destroy(h->pcg_mass);
+    if (h->pcg_pena) ddpca_mg_destroy(h->pcg_pena);
     cudaFree(h->globForc); cudaFree(h->globSolu); cudaFree(h->globForc1_const); cudaFree(h->globSolu1);
     cudaFree(h->moni_chunks_d); cudaFree(h->slot_chunk_d); cudaFree(h->moni_part); cudaFree(h->moni_out);
     if (h->moni_host) cudaFreeHost(h->moni_host);
@@ -289,6 +298,8 @@ static double *moni_buf(ddpca_admm *h) { return h->x_moni ? h->x_moni : h->moni_
 // wait for the batched body solves of this iteration and account their CG iterations
 static int admm_bodies_finish(ddpca_admm *h)
 {
+    for (ddpca_mg *m : {h->pcg_pena, h->pcg_mass})
+        if (m) { if (pcg_finish(m, nullptr, nullptr, nullptr)) return 1; h->launches += ddpca_mg_launch_count(m, 1); }
     if (!h->bodies_pending) return 0;
     h->bodies_pending = false;
     for (Batch &b : h->batch) {
@@ -377,7 +388,7 @@ static int admm_macro_apply(ddpca_admm *h)
 // muscSett bit 1, :2576-2584: this rank's part of globForc - globForc_1
 static int admm_macro1_partial(ddpca_admm *h)
 {
-    if (!h->coar1) return fail("interface-eliminated coarse problem requested but not set");
+    if (!h->coar1 && !h->coar1_mg) return fail("interface-eliminated coarse problem requested but not set");
     ADMM_SPMV(h->OPG1, h->state, glob_buf(h), false, 1.0);   // :2579, :2583
     return 0;
 }
@@ -387,7 +398,16 @@ static int admm_macro1_apply(ddpca_admm *h)
     cudaStream_t st = h->stream;
     double *gf = glob_buf(h);
     KL(h, DDPCA_K_VECTOR, 15, 24.0 * h->nglob1, (k_axpy<<<cdiv(h->nglob1, 256), 256, 0, st>>>(h->nglob1, 1.0, h->globForc1_const, gf)));
-    ldlt_solve_on(h, h->coar1, gf, h->globSolu1, nullptr);   // :2588
+    if (h->coar1_mg) {
+        // :2593-2595  mgpi_1.CG_SOLV(1, globForc, globSolu)
+        long it = 0;
+        ddpca_mg_set_stream(h->coar1_mg, (void *)st);
+        if (pcg_device(h->coar1_mg, 1, gf, h->globSolu1, 1.0e-14, h->nglob1, &it, nullptr, nullptr)) return 1;
+        h->launches += ddpca_mg_launch_count(h->coar1_mg, 1);
+        h->macro_cg_iters += it;
+    } else {
+        ldlt_solve_on(h, h->coar1, gf, h->globSolu1, nullptr);   // :2588
+    }
     return admm_coarse_correction(h, h->globSolu1);
 }
 // t = inpoLagr0 l0 - inpoLagr1 l1 + pemaInpo_r0 u0 - pemaInpo_r1 u1 (:2632-2635); for cross-rank interfaces the local
@@ -415,9 +435,17 @@ static int admm_interface(ddpca_admm *h)
     ADMM_SPMV(h->OPF1, h->state, h->force, false, 1.0);                                 // :2671-2675
     KL(h, DDPCA_K_COARSE, 15, 0.0, (k_dense_gemv_batch<<<cdiv((long)h->NC * 32, 256), 256, 0, st>>>(h->nls, h->side_off_d, h->pena_ptr_d, h->force, aux, nullptr)));   // :2677
     for (auto &p : h->sparse_pena) { HostSide &s = h->iface[p.first].side[p.second]; ldlt_solve_on(h, s.mass_pena, h->force + s.coff, aux + s.coff, nullptr); }
+    if (h->pcg_pena) {   // :2678-2683: Eigen CG with its default diagonal preconditioner -> batched Jacobi-PCG
+        ddpca_mg_set_stream(h->pcg_pena, (void *)st);
+        if (pcg_device(h->pcg_pena, 0, h->force + h->it_off, aux + h->it_off, 1.0e-15, 0, nullptr, nullptr, nullptr, /*no_wait=*/true)) return 1;
+    }
     ADMM_SPMV(h->OPF2, h->state, h->force, false, 1.0);                                 // :2691-2694
     KL(h, DDPCA_K_COARSE, 15, 0.0, (k_dense_gemv_batch<<<cdiv((long)h->NC * 32, 256), 256, 0, st>>>(h->nls, h->side_off_d, h->mass_ptr_d, h->force, h->tmp, nullptr)));   // :2696
     for (auto &p : h->sparse_mass) { HostSide &s = h->iface[p.first].side[p.second]; ldlt_solve_on(h, s.mass, h->force + s.coff, h->tmp + s.coff, nullptr); }
+    if (h->pcg_mass) {   // :2698-2703
+        ddpca_mg_set_stream(h->pcg_mass, (void *)st);
+        if (pcg_device(h->pcg_mass, 0, h->force + h->it_off, h->tmp + h->it_off, 1.0e-15, 0, nullptr, nullptr, nullptr, /*no_wait=*/true)) return 1;
+    }
     KL(h, DDPCA_K_VECTOR, 15, 24.0 * h->NC, (k_axpy<<<cdiv(h->NC, 256), 256, 0, st>>>(h->NC, 1.0, h->tmp, lagr)));
     return 0;
 }
@@ -574,6 +602,15 @@ int ddpca_admm_set_side_solver(ddpca_admm *h, int ts, int tv, int which, ddpca_l
     return 0;
 }
 
+int ddpca_admm_set_side_iterative(ddpca_admm *h, int ts, int tv)
+{
+    if (!h || ts < 0 || ts >= h->ni || tv < 0 || tv > 1 || !h->iface[ts].set || h->finalized) return fail("ddpca_admm_set_side_iterative: bad argument");
+    HostSide &s = h->iface[ts].side[tv];
+    if (!s.local) return fail("ddpca_admm_set_side_iterative: this side belongs to another rank");
+    s.iterative = true;
+    return 0;
+}
+
 int ddpca_admm_set_macro(ddpca_admm *h, int nglob, const long *baseReco, ddpca_ldlt *coarSolv)
 {
     if (!h || nglob < 1 || !baseReco || !coarSolv) return fail("ddpca_admm_set_macro: bad argument");
@@ -620,6 +657,23 @@ int ddpca_admm_set_macro1(ddpca_admm *h, int nglob1, const long *baseReco, const
     return dev_vec(globForc_1, nglob1, &h->globForc1_const);
 }
 
+int ddpca_admm_set_macro1_mg(ddpca_admm *h, int nglob1, const long *baseReco, const double *globForc_1, ddpca_mg *mgpi_1)
+{
+    if (!h || nglob1 < 1 || !baseReco || !globForc_1 || !mgpi_1) return fail("ddpca_admm_set_macro1_mg: bad argument");
+    if (mgpi_1->nsub != 1 || mgpi_1->lev[mgpi_1->nlev - 1].n != nglob1) return fail("finest level of the hierarchy does not match globCoup_1");
+    if (mgpi_1->device != h->device) return fail("hierarchy lives on another device");
+    CU(cudaSetDevice(h->device));
+    h->nglob1 = nglob1;
+    h->baseReco.assign(baseReco, baseReco + h->nb + 1);
+    ldlt_free(h->coar1);
+    h->coar1 = nullptr;
+    if (h->coar1_mg && h->coar1_mg != mgpi_1) ddpca_mg_destroy(h->coar1_mg);
+    h->coar1_mg = mgpi_1;
+    cudaFree(h->globForc1_const);
+    h->globForc1_const = nullptr;
+    return dev_vec(globForc_1, nglob1, &h->globForc1_const);
+}
+
 // Builds the device side of the loop: batches of body hierarchies, concatenated state, stacked operators.
 int ddpca_admm_finalize(ddpca_admm *h)
 {
@@ -639,7 +693,7 @@ int ddpca_admm_finalize(ddpca_admm *h)
         if ((h->muscSett & 2) && (b.globTran_D_1.rp.empty() || b.globTran_D_1.rows != h->nglob1)) return fail("body " + std::to_string(v) + ": globTran_D_1 missing");
     }
     if ((h->muscSett & 1) && !h->coar && !h->coar_mg) return fail("macroscopic problem not set");
-    if ((h->muscSett & 2) && !h->coar1) return fail("interface-eliminated coarse problem not set");
+    if ((h->muscSett & 2) && !h->coar1 && !h->coar1_mg) return fail("interface-eliminated coarse problem not set");
     for (int ts = 0; ts < ni; ts++) {
         HostIface &f = h->iface[ts];
         if (!f.set) return fail("interface " + std::to_string(ts) + " not set");
@@ -651,11 +705,11 @@ int ddpca_admm_finalize(ddpca_admm *h)
             if (h->muscSett & 1)
                 for (int o : {DDPCA_OP_GLOBTRAN, DDPCA_OP_GLOBTRAN_PENA, DDPCA_OP_GLOBTRAN_D}) if (!s.has[o]) return fail("macroscopic transfer operator missing");
             if ((h->muscSett & 2) && !s.has[DDPCA_OP_GLOBTRAN_1]) return fail("globTran_1 missing");
-            if (!s.mass || !s.mass_pena) return fail("interface " + std::to_string(ts) + " side " + std::to_string(tv) + ": mass solvers missing");
+            if (!s.iterative && (!s.mass || !s.mass_pena)) return fail("interface " + std::to_string(ts) + " side " + std::to_string(tv) + ": mass solvers missing");
             int ng = f.d * f.nip, nfull = h->body[f.body[tv]].nfull;
             if (s.op[DDPCA_OP_SYSTTRAN].rows != nfull || s.op[DDPCA_OP_SYSTTRAN].cols != s.nc || s.op[DDPCA_OP_INPOLAGR].rows != ng ||
                 s.op[DDPCA_OP_INTEINPO].rows != s.nc || s.op[DDPCA_OP_INTEINPO].cols != ng || s.op[DDPCA_OP_PEMAINPO_R].rows != ng ||
-                s.op[DDPCA_OP_PEMAINPO_R].cols != nfull || s.mass->n != s.nc || s.mass_pena->n != s.nc)
+                s.op[DDPCA_OP_PEMAINPO_R].cols != nfull || (!s.iterative && (s.mass->n != s.nc || s.mass_pena->n != s.nc)))
                 return fail("interface " + std::to_string(ts) + " side " + std::to_string(tv) + ": operator shapes are inconsistent");
         }
     }
@@ -678,14 +732,19 @@ int ddpca_admm_finalize(ddpca_admm *h)
     }
     long NC = 0;
     h->nls = 0;
-    for (int ts = 0; ts < ni; ts++)
-        for (int tv = 0; tv < 2; tv++) {
-            HostSide &s = h->iface[ts].side[tv];
-            if (!s.local) continue;
-            s.coff = (int)NC;
-            NC += s.nc;
-            h->nls++;
-        }
+    std::vector<HostSide *> sorder;   // local sides in numbering order: those with a direct solver, then the iterative ones
+    for (int pass = 0; pass < 2; pass++)
+        for (int ts = 0; ts < ni; ts++)
+            for (int tv = 0; tv < 2; tv++) {
+                HostSide &s = h->iface[ts].side[tv];
+                if (!s.local || (int)s.iterative != pass) continue;
+                if (pass == 1 && h->it_rows == 0) h->it_off = (int)NC;
+                s.coff = (int)NC;
+                NC += s.nc;
+                if (pass == 1) h->it_rows += s.nc;
+                h->nls++;
+                sorder.push_back(&s);
+            }
     std::vector<int> act;   // active interfaces in T order
     for (int ts = 0; ts < ni; ts++) if (h->iface[ts].side[0].local && h->iface[ts].side[1].local) act.push_back(ts);
     long NG = 0;
@@ -805,17 +864,37 @@ int ddpca_admm_finalize(ddpca_admm *h)
         std::vector<int> off(h->nls + 1, 0);
         std::vector<double *> pm(std::max(1, h->nls), nullptr), pp(std::max(1, h->nls), nullptr);
         int k = 0;
+        std::vector<HostSide *> its;
+        for (HostSide *sp : sorder) {
+            HostSide &s = *sp;
+            off[k] = s.coff; off[k + 1] = s.coff + s.nc;
+            if (s.iterative) its.push_back(sp);
+            else { pm[k] = s.mass->Binv; pp[k] = s.mass_pena->Binv; }
+            k++;
+        }
         for (int ts = 0; ts < ni; ts++)
             for (int tv = 0; tv < 2; tv++) {
                 HostSide &s = h->iface[ts].side[tv];
-                if (!s.local) continue;
-                off[k] = s.coff; off[k + 1] = s.coff + s.nc;
-                pm[k] = s.mass->Binv; pp[k] = s.mass_pena->Binv;
+                if (!s.local || s.iterative) continue;
                 if (!s.mass->Binv) h->sparse_mass.push_back({ts, tv});
                 if (!s.mass_pena->Binv) h->sparse_pena.push_back({ts, tv});
-                k++;
             }
         if (upload_vec(off, &h->side_off_d) || upload_vec(pm, &h->mass_ptr_d) || upload_vec(pp, &h->pena_ptr_d)) return 1;
+        if (!its.empty()) {
+            // the mass matrices themselves, each a one-level "hierarchy", as two batches for Jacobi-PCG
+            for (int which = 0; which < 2; which++) {
+                const int op = which == 0 ? DDPCA_OP_INTEMASS : DDPCA_OP_INTEMASS_PENA;
+                std::vector<int> n(its.size());
+                std::vector<const int *> rp(its.size()), ci(its.size());
+                std::vector<const double *> vv(its.size());
+                for (size_t q = 0; q < its.size(); q++) { const CsrHost &M = its[q]->op[op]; n[q] = M.rows; rp[q] = M.rp.data(); ci[q] = M.ci.data(); vv[q] = M.v.data(); }
+                ddpca_mg **dst = which == 0 ? &h->pcg_mass : &h->pcg_pena;
+                if (mg_create_impl(h->device, (int)its.size(), 1, n.data(), rp.data(), ci.data(), vv.data(), nullptr, nullptr, nullptr, DDPCA_SMOOTH_MC, dst, /*no_direct=*/true)) {
+                    g_err = "iterative interface mass solvers: " + g_err;
+                    return 1;
+                }
+            }
+        }
     }
     // ---- MONITOR tables: slot of body v is v, of side (ts, tv) nb + 4 ts + 2 tv (aux) and + 1 (lagr), :2771 ---
     {

@@ -670,6 +670,7 @@ static int pcg_device(ddpca_mg *h, int prec, const double *b_ref, double *x_ref,
                       long *iters, double *resid, double *tol_abs, bool no_wait = false)
 {
     if (prec != 0 && prec != 1) return fail("prec must be 0 (Jacobi) or 1 (V-cycle)");
+    if (prec == 1 && !h->Binv) return fail("this hierarchy was built without a level-0 direct solver: Jacobi preconditioning only");
     int Lf = h->nlev - 1;
     Level &L = h->lev[Lf];
     int n = L.n;
@@ -1449,7 +1450,7 @@ static int concat_block_diag(int nsub, const int *r, const int *c, const int *co
 // nsub hierarchies of `nlevels` levels each; every array is indexed [s * nlevels + l] (prolongations [s * (nlevels-1) + l])
 static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const int *const *rowptr, const int *const *colidx,
                           const double *const *val, const int *const *P_rowptr, const int *const *P_colidx,
-                          const double *const *P_val, int smoother_mode, ddpca_mg **out)
+                          const double *const *P_val, int smoother_mode, ddpca_mg **out, bool no_direct = false)
 {
     if (!out || nsub < 1 || nlevels < 1 || nlevels > 16 || !n || !rowptr || !colidx || !val) return fail("ddpca_mg_create: bad argument");
     if (smoother_mode != DDPCA_SMOOTH_LEX && smoother_mode != DDPCA_SMOOTH_MC) return fail("unknown smoother mode");
@@ -1500,7 +1501,7 @@ static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const
         }
         double tb = StageTimer::now();
         t_cat += tb - ta;
-        if (setup_level(L, ntot, rp, ci, vv, mode, /*keep_csr=*/l == 0, /*group_layout=*/!coarse_only, &h->sub_off[l])) {
+        if (setup_level(L, ntot, rp, ci, vv, mode, /*keep_csr=*/l == 0 && !no_direct, /*group_layout=*/!coarse_only, &h->sub_off[l])) {
             g_err = "level " + std::to_string(l) + ": " + g_err;
             ddpca_mg_destroy(h);
             return 1;
@@ -1574,7 +1575,7 @@ static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const
             CUC(cudaMemset(h->partial[k], 0, sizeof(double) * std::max(h->nseg, kNumPart)));
         }
     }
-    {   // ---- level 0: dense inverse of every sub's block (the reference re-factorises in every CG_SOLV call, MGPIS.h:185) ----
+    if (!no_direct) {   // ---- level 0: dense inverse of every sub's block (the reference re-factorises in every CG_SOLV call, MGPIS.h:185) ----
         Level &L0 = h->lev[0];
         h->n0 = L0.n;
         std::vector<long long> boff(nsub);
@@ -1595,8 +1596,11 @@ static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const
     }
     tm.lap("level-0 dense inverses");
     // capture + instantiate the V-cycle-preconditioned solve graph now (set-up time), not in the first solve
-    build_solve_graph(h, 1);
-    if (h->while_state[1] != 1) FAILC(build_iter_graph(h, 1));
+    // (no_direct: a Jacobi-PCG-only handle, e.g. the interface mass matrices of the ADMM loop; its graph is built on first use)
+    if (!no_direct) {
+        build_solve_graph(h, 1);
+        if (h->while_state[1] != 1) FAILC(build_iter_graph(h, 1));
+    }
 #undef FAILC
 #undef CUC
     *out = h;

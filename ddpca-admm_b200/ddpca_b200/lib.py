@@ -32,7 +32,7 @@ EXPORTS = [
     "ddpca_admm_step", "ddpca_admm_row_length", "ddpca_admm_get_disp", "ddpca_admm_get_side", "ddpca_admm_get_gamma",
     "ddpca_admm_launch_count", "ddpca_admm_destroy", "ddpca_admm_set_partition", "ddpca_admm_exchange_sizes",
     "ddpca_admm_set_exchange", "ddpca_admm_exchange_peers", "ddpca_admm_set_stream", "ddpca_admm_phase", "ddpca_admm_monitor_row",
-    "ddpca_admm_set_smoother", "ddpca_admm_reset", "ddpca_admm_set_consforc", "ddpca_admm_body_iters", "ddpca_admm_profile", "ddpca_admm_profile_get", "ddpca_gamma_project",
+    "ddpca_admm_set_smoother", "ddpca_admm_reset", "ddpca_admm_set_consforc", "ddpca_admm_body_iters", "ddpca_admm_profile", "ddpca_admm_profile_get", "ddpca_gamma_project", "ddpca_admm_set_side_iterative", "ddpca_admm_set_macro1_mg",
     "ddpca_partition_bodies", "ddpca_admm_group_create", "ddpca_admm_group_size", "ddpca_admm_group_member", "ddpca_admm_group_owner",
     "ddpca_admm_group_device", "ddpca_admm_group_finalize", "ddpca_admm_group_step", "ddpca_admm_group_launch_count", "ddpca_admm_group_destroy",
 ]

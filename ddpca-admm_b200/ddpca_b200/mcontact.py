@@ -137,7 +137,7 @@ class MCONTACT:
     # ------------------------------------------------------------------------------------------
     @classmethod
     def from_ddpk(cls, d: dict, device: int = 0, smoother: int = SMOOTH_MC, muscSett=None, factorize=None,
-                  body_rank=None, rank: int = 0, comm=None, macro_mgpis=None):
+                  body_rank=None, rank: int = 0, comm=None, macro_mgpis=None, iterative_above=None, macro1_mgpis=None):
         """Upload everything MCONTACT::ESTABLISH built (dumped by oracle/ref_drivers/admm_hook.h).
 
         Multi-GPU (one process per GPU): `body_rank[v]` = owning rank (see partition.py), `rank` = this
@@ -146,7 +146,11 @@ class MCONTACT:
 
         `macro_mgpis`: an established MGPIS whose finest level is globCoup -- the macroscopic problem is then
         solved by mgpi.CG_SOLV(1, .) like the reference does beyond DIRE_MAXI rows (MCONTACT.h:2560-2562)
-        instead of the factor coarSolv_D; ownership of its device hierarchy moves to this object."""
+        instead of the factor coarSolv_D; ownership of its device hierarchy moves to this object.
+
+        `iterative_above`: interface sides whose mass matrices have more rows than this get no factor; their mass
+        systems are solved by batched Jacobi-PCG on the device (the reference: Eigen CG from DIRE_MAXI = 120 000 rows,
+        MCONTACT.h:2678-2683).  Default: only when the dump carries no factor for the side."""
         import time
 
         lib = load_library()
@@ -217,6 +221,11 @@ class MCONTACT:
                     check(lib.ddpca_admm_set_side_op(h, C.c_int(ts), C.c_int(tv), C.c_int(k), C.c_int(m.shape[0]), C.c_int(m.shape[1]), _pi(m.rowptr), _pi(m.colidx), _pd(m.val)))
                 tm["side_operators"] += time.time() - t_
                 t_ = time.time()
+                no_factor = (q + "inteDiso.perm") not in d and ncs[-1] > DIRE_SOLV.DENSE_MAX and factorize is None
+                if no_factor or (iterative_above is not None and ncs[-1] > iterative_above):
+                    check(lib.ddpca_admm_set_side_iterative(h, C.c_int(ts), C.c_int(tv)))
+                    tm["side_solvers"] += time.time() - t_
+                    continue
                 for which, nm, mat in ((SOLVER_MASS, "inteDiso", "inteMass"), (SOLVER_MASS_PENA, "inteDiso_pena", "inteMass_pena")):
                     s = _factor_from_dump(d, q + nm, device, ddpk.get_csr(d, q + mat), factorize)
                     check(lib.ddpca_admm_set_side_solver(h, C.c_int(ts), C.c_int(tv), C.c_int(which), s.release()))
@@ -234,9 +243,14 @@ class MCONTACT:
                 check(lib.ddpca_admm_set_macro(h, C.c_int(s.n), base.ctypes.data_as(C.POINTER(C.c_long)), s.release()))
         if self.muscSett & 2:   # MCONTACT::MULTISCALE_1 (MCONTACT.h:1672-2343), applied at :2575-2607
             base = np.ascontiguousarray(d["baseReco"], dtype=np.int64)
-            s1 = _factor_from_dump(d, "coarSolv_D_1", device, ddpk.get_csr(d, "globCoup_1"), factorize, DIRE_SOLV.DENSE_MAX_COARSE)
             gf1 = np.ascontiguousarray(d["globForc_1"], dtype=np.float64)
-            check(lib.ddpca_admm_set_macro1(h, C.c_int(s1.n), base.ctypes.data_as(C.POINTER(C.c_long)), _pd(gf1), s1.release()))
+            if macro1_mgpis is not None:   # MCONTACT.h:2593-2595: mgpi_1.CG_SOLV(1, .); ownership moves to the ADMM handle
+                n1 = int(ddpk.get_csr(d, "globCoup_1").shape[0])
+                check(lib.ddpca_admm_set_macro1_mg(h, C.c_int(n1), base.ctypes.data_as(C.POINTER(C.c_long)), _pd(gf1), macro1_mgpis._h))
+                macro1_mgpis._h = None
+            else:
+                s1 = _factor_from_dump(d, "coarSolv_D_1", device, ddpk.get_csr(d, "globCoup_1"), factorize, DIRE_SOLV.DENSE_MAX_COARSE)
+                check(lib.ddpca_admm_set_macro1(h, C.c_int(s1.n), base.ctypes.data_as(C.POINTER(C.c_long)), _pd(gf1), s1.release()))
         tm["coarse_solvers"] = time.time() - t_
         t_ = time.time()
         if comm is not None:

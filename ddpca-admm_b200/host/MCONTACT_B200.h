@@ -94,11 +94,6 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 	const long bodyNumb = mc.multGrid.size(), inteNumb = mc.searCont.size();
 	const bool macrSwit = ((mc.muscSett >> 0) % 2 == 1);
 	const bool elimSwit = ((mc.muscSett >> 1) % 2 == 1);// interface-eliminated coarse problem, MCONTACT.h:2575-2607
-	if(elimSwit && mc.globCoup_1.rows() >= DIRE_MAXI){// :2590-2595 (coarSolv_C_1 / mgpi_1)
-		std::cout << "MCONTACT::CONTACT_ANALYSIS (B200): ERROR interface-eliminated problem beyond DIRE_MAXI "
-			<< "is not offered by the B200 build" << std::endl;
-		return -1;
-	}
 	//bodies -> devices (balanced groups; the reference's omp loop over bodies, MCONTACT.h:2511)
 	std::vector<double> bodyWeig(bodyNumb);
 	std::vector<int> contPair(2 * inteNumb), bodyRank(bodyNumb, 0);
@@ -187,9 +182,12 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 				allGood = allGood && UPLOAD_OP(hand, ts, tv, DDPCA_OP_GLOBTRAN_1, mc.globTran_1[ts][tv]);// :2579
 			}
 			if(!allGood){ FAIL("set_side_op"); break; }
-			if(mc.inteMass[ts][tv].rows() >= DIRE_MAXI){// MCONTACT.h:2676-2683: per-iteration Eigen CG
-				std::cout << "MCONTACT::CONTACT_ANALYSIS (B200): ERROR interface beyond DIRE_MAXI" << std::endl;
-				allGood = false; break;
+			if(mc.inteMass[ts][tv].rows() >= DIRE_MAXI){// MCONTACT.h:2676-2683, :2698-2703: per-iteration Eigen CG with its
+				//diagonal preconditioner, no factor exists -> batched Jacobi-PCG on the device
+				if(ddpca_admm_set_side_iterative(hand, ts, tv) != 0){
+					allGood = FAIL("set_side_iterative");
+				}
+				continue;
 			}
 			ddpca_ldlt *soMa = UPLOAD_SOLVER(devi, mc.inteDiso[ts][tv], mc.inteMass[ts][tv]);
 			ddpca_ldlt *soPe = UPLOAD_SOLVER(devi, mc.inteDiso_pena[ts][tv], mc.inteMass_pena[ts][tv]);
@@ -223,10 +221,23 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 			}
 		}
 		if(allGood && elimSwit){// MCONTACT.h:2576,2588
-			ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D_1, mc.globCoup_1, 32768);
-			if(soCo == nullptr || ddpca_admm_set_macro1(hand, mc.globCoup_1.rows(), mc.baseReco.data(),
-				mc.globForc_1.data(), soCo) != 0){
-				allGood = FAIL("set_macro1");
+			if(mc.globCoup_1.rows() < DIRE_MAXI){
+				ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D_1, mc.globCoup_1, 32768);
+				if(soCo == nullptr || ddpca_admm_set_macro1(hand, mc.globCoup_1.rows(), mc.baseReco.data(),
+					mc.globForc_1.data(), soCo) != 0){
+					allGood = FAIL("set_macro1");
+				}
+			}
+			else{// MCONTACT.h:2593-2595: mgpi_1.CG_SOLV(1, globForc, globSolu) (COGR_MAXI < DIRE_MAXI: :2590-2592 unreachable)
+				MGPIS::POINTERS poin;
+				mc.mgpi_1.HIERARCHY_POINTERS(poin);
+				ddpca_mg *mgHand = nullptr;
+				if(ddpca_mg_create(devi, mc.mgpi_1.maxiLeve + 1, poin.n.data(), poin.rp.data(), poin.ci.data(),
+					poin.va.data(), poin.prp.data(), poin.pci.data(), poin.pva.data(), MGPIS::SMOOTHER(), &mgHand) != 0
+					|| ddpca_admm_set_macro1_mg(hand, mc.globCoup_1.rows(), mc.baseReco.data(),
+						mc.globForc_1.data(), mgHand) != 0){
+					allGood = FAIL("set_macro1_mg");
+				}
 			}
 		}
 	}

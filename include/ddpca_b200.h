@@ -201,6 +201,11 @@ int ddpca_admm_set_interface(ddpca_admm *, int ts, int body0, int body1, double 
 int ddpca_admm_set_side_op(ddpca_admm *, int ts, int tv, int op, int rows, int cols, const int *rowptr, const int *colidx, const double *val);
 /* takes ownership of the solver: inteDiso[ts][tv] / inteDiso_pena[ts][tv] (MCONTACT.h:837-847) */
 int ddpca_admm_set_side_solver(ddpca_admm *, int ts, int tv, int which, ddpca_ldlt *solver);
+/* No factor for this side: its two mass systems are solved by Jacobi-preconditioned CG on the device (all such sides of
+ * a rank in one batched solve per update) -- what the reference does with Eigen::ConjugateGradient and its default
+ * diagonal preconditioner when inteMass has DIRE_MAXI rows or more (MCONTACT.h:2678-2683, :2698-2703).  Replaces both
+ * ddpca_admm_set_side_solver calls of the side. */
+int ddpca_admm_set_side_iterative(ddpca_admm *, int ts, int tv);
 /* macroscopic problem: coarSolv_D (factorised globCoup, MCONTACT.h:1229-1230) and baseReco[nbody+1] (:850-857) */
 int ddpca_admm_set_macro(ddpca_admm *, int nglob, const long *baseReco, ddpca_ldlt *coarSolv);
 /* the same for a macroscopic problem beyond DIRE_MAXI rows (PREP.h:69): the reference then solves it with
@@ -213,6 +218,9 @@ int ddpca_admm_set_macro_mg(ddpca_admm *, int nglob, const long *baseReco, ddpca
  * globTran_1 is side operator DDPCA_OP_GLOBTRAN_1; accuProl is needed as for bit 0.  Takes ownership of the solver. */
 int ddpca_admm_set_body_globtran_d1(ddpca_admm *, int v, int rows, int cols, const int *rowptr, const int *colidx, const double *val);
 int ddpca_admm_set_macro1(ddpca_admm *, int nglob1, const long *baseReco, const double *globForc_1, ddpca_ldlt *coarSolv_D_1);
+/* the same with globCoup_1 beyond DIRE_MAXI rows: mgpi_1.CG_SOLV(1, globForc, globSolu) (MCONTACT.h:2593-2595); takes
+ * ownership of the hierarchy (finest level = globCoup_1) */
+int ddpca_admm_set_macro1_mg(ddpca_admm *, int nglob1, const long *baseReco, const double *globForc_1, ddpca_mg *mgpi_1);
 /* Multi-GPU, one process per GPU: body_rank[v] = owning rank; a rank uploads only
  * its own bodies and their interface sides (set_body / set_side_op / set_side_solver), but declares
  * EVERY interface (set_interface) and the macroscopic solver.  Call before ddpca_admm_set_body. */
