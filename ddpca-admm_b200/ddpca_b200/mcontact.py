@@ -33,10 +33,11 @@ class DIRE_SOLV:
     # up to this size an SPD operator is inverted densely on the device (8 n^2 bytes; all interface mass solves of a rank
     # are then ONE block-diagonal product per update); beyond: staged sparse triangular solves with the host factor
     DENSE_MAX = 8192
-    # The coarse problems (macroscopic / interface-eliminated) are solved once per ADMM iteration on EVERY rank: the staged
-    # sparse triangular solves cost ~2 ms of launch latency at 23 k rows, one 4.4 GB product 0.7 ms -- and it is the part
-    # of an iteration that does not shrink with more GPUs.  HBM is 180 GB; the dense form is used up to this size.
-    DENSE_MAX_COARSE = 32768
+    # The coarse problems (macroscopic / interface-eliminated) are solved once per ADMM iteration on EVERY rank.  One dense
+    # product is faster per solve than the staged sparse sweeps (0.9 ms against ~3 ms at 28 k rows), but the inversion
+    # costs 2 n^3 flops at set-up (5 s at 28 k rows against ~1.5 s for uploading the host factor): measured on BLOCK
+    # globLeve 3 the dense form only pays for itself below ~12 k rows or over many solves.
+    DENSE_MAX_COARSE = 12288
 
     @classmethod
     def dense(cls, A: ddpk.Csr, device: int = 0):

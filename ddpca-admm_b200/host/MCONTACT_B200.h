@@ -33,7 +33,8 @@ inline bool FAIL(const char *what){
 // a factorised DIRE_SOLV (Eigen::SimplicialLDLT) -> device solver; small SPD operators are
 // inverted densely on the device instead (no factor needed)
 // denseMaxi: interface mass matrices 8192; the coarse problems, solved on every device in every iteration and the
-// part of an iteration that does not shrink with more devices, 32768 (one product instead of staged sparse sweeps)
+// part of an iteration that does not shrink with more devices, 12288 (one product instead of staged sparse sweeps;
+// beyond, the 2 n^3 flops of the inversion cost more at set-up than the product saves over a few dozen iterations)
 inline ddpca_ldlt *UPLOAD_SOLVER(int devi, const DIRE_SOLV &solv, const SPM &matr, long denseMaxi = 8192){
 	ddpca_ldlt *resu = nullptr;
 	if(matr.rows() <= denseMaxi){
@@ -203,7 +204,7 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 		const int devi = ddpca_admm_group_device(grou, tk);
 		if(macrSwit){
 			if(mc.globCoup.rows() < DIRE_MAXI){// MCONTACT.h:2553-2555
-				ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D, mc.globCoup, 32768);
+				ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D, mc.globCoup, 12288);
 				if(soCo == nullptr || ddpca_admm_set_macro(hand, mc.globCoup.rows(), mc.baseReco.data(), soCo) != 0){
 					allGood = FAIL("set_macro");
 				}
@@ -222,7 +223,7 @@ inline long DDPCA_CONTACT_ANALYSIS(MCONTACT &mc){
 		}
 		if(allGood && elimSwit){// MCONTACT.h:2576,2588
 			if(mc.globCoup_1.rows() < DIRE_MAXI){
-				ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D_1, mc.globCoup_1, 32768);
+				ddpca_ldlt *soCo = UPLOAD_SOLVER(devi, mc.coarSolv_D_1, mc.globCoup_1, 12288);
 				if(soCo == nullptr || ddpca_admm_set_macro1(hand, mc.globCoup_1.rows(), mc.baseReco.data(),
 					mc.globForc_1.data(), soCo) != 0){
 					allGood = FAIL("set_macro1");
