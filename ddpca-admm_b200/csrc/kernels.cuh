@@ -688,7 +688,10 @@ __global__ void __launch_bounds__(1024) k_bgj_diag(int n, int k0, int nb, const 
     for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) Dinv[(e / nb) * kGjB + e % nb] = d[e / nb][e % nb];
 }
 // 64x64 (x64) tile product helper: acc[4][4] of thread (ty, tx) in a 16x16 thread block:
-// rows ty*4.., cols tx*4.. of  As (64 x kk, row-major in shared) times Bs (kk x 64)
+// rows ty*4 + r, columns tx + 16*c of  As (64 x kk, row-major in shared) times Bs (kk x 64).  The strided column
+// assignment makes the 16 lanes of a row read 16 CONSECUTIVE doubles of Bs (no bank conflicts; tx*4 + c gave a 4-way
+// conflict on every Bs load and held the kernel at ~3 TFLOP/s); the As reads are broadcasts.
+__device__ __forceinline__ int gj_col(int tx, int c) { return tx + 16 * c; }
 __device__ __forceinline__ void gj_tile_mma(const double (*As)[kGjB + 1], const double (*Bs)[kGjB + 1], int kk, int ty, int tx, double (&acc)[4][4])
 {
 #pragma unroll 4
@@ -697,7 +700,7 @@ __device__ __forceinline__ void gj_tile_mma(const double (*As)[kGjB + 1], const 
 #pragma unroll
         for (int r = 0; r < 4; r++) a[r] = As[ty * 4 + r][k];
 #pragma unroll
-        for (int c = 0; c < 4; c++) b[c] = Bs[k][tx * 4 + c];
+        for (int c = 0; c < 4; c++) b[c] = Bs[k][gj_col(tx, c)];
 #pragma unroll
         for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -730,7 +733,7 @@ __global__ void __launch_bounds__(256) k_bgj_panels(int n, int k0, int nb, const
     for (int r = 0; r < 4; r++)
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const int i = ty * 4 + r, j = t0 + tx * 4 + c;
+            const int i = ty * 4 + r, j = t0 + gj_col(tx, c);
             if (i < nb && j < n) R[(size_t)i * n + j] = acc[r][c];
         }
 }
@@ -768,9 +771,9 @@ __global__ void __launch_bounds__(256) k_bgj_update(int n, int k0, int nb, doubl
     for (int r = 0; r < 4; r++)
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const int i = i0 + ty * 4 + r, j = j0 + tx * 4 + c;
+            const int i = i0 + ty * 4 + r, j = j0 + gj_col(tx, c);
             if (i >= n) continue;
-            if (colK) { if (tx * 4 + c < nb) A[(size_t)i * n + j] = -acc[r][c]; }
+            if (colK) { if (gj_col(tx, c) < nb) A[(size_t)i * n + j] = -acc[r][c]; }
             else if (j < n) A[(size_t)i * n + j] -= acc[r][c];
         }
 }
@@ -801,7 +804,7 @@ __global__ void __launch_bounds__(256) k_ldl_tail_product64(int T, const double 
     for (int r = 0; r < 4; r++)
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const int i = i0 + ty * 4 + r, j = j0 + tx * 4 + c;
+            const int i = i0 + ty * 4 + r, j = j0 + gj_col(tx, c);
             if (i < T && j < T) {
                 M[(size_t)i * T + j] = acc[r][c];
                 if (blockIdx.x != blockIdx.y) M[(size_t)j * T + i] = acc[r][c];

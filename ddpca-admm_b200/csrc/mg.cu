@@ -741,8 +741,13 @@ struct GroupLayoutHost {
     std::vector<GroupMeta> meta;
     std::vector<int> ci;
     std::vector<double> v;
+    long pat_total = 0, val_total = 0;   // sizes of ci / v (the arrays are only filled when the level uses this layout)
 };
 
+static void fill_group_arrays(const CsrHost &Ap, GroupLayoutHost &out);
+// descriptors of the group layout; the pattern / value arrays are filled by fill_group_arrays when the level keeps this
+// layout (levels that go on to the split v2 layout only need the descriptors: skipping the copy saves a pass over the
+// whole operator at set-up)
 static bool build_group_layout(const CsrHost &Ap, const LevelPlan &pl, GroupLayoutHost &out, std::string &err)
 {
     int ng = pl.ngroups();
@@ -762,8 +767,15 @@ static bool build_group_layout(const CsrHost &Ap, const LevelPlan &pl, GroupLayo
         val += (long)gs * lenp;
         if (pat > 0x7fffffffL) { err = "pattern index overflow"; return false; }
     }
-    out.ci.resize(pat);
-    out.v.assign(val, 0.0);
+    out.pat_total = pat;
+    out.val_total = val;
+    return true;
+}
+static void fill_group_arrays(const CsrHost &Ap, GroupLayoutHost &out)
+{
+    const int ng = (int)out.meta.size();
+    out.ci.resize(out.pat_total);
+    out.v.assign(out.val_total, 0.0);
 #pragma omp parallel for schedule(static)
     for (int g = 0; g < ng; g++) {
         const GroupMeta &m = out.meta[g];
@@ -777,7 +789,6 @@ static bool build_group_layout(const CsrHost &Ap, const LevelPlan &pl, GroupLayo
             for (int k = 0; k < len; k++) dst[k] = vr[k];
         }
     }
-    return true;
 }
 
 // ---- v2 layout (kernels2.cuh): split lower / upper arrays in stage order + chunk table -----------
@@ -972,8 +983,8 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
         }
         L.v2 = want_v2;
         L.ng = (int)G.meta.size();
-        L.pat_entries = (long)G.ci.size();
-        L.val_entries = (long)G.v.size();
+        L.pat_entries = G.pat_total;
+        L.val_entries = G.val_total;
         for (const GroupMeta &m : G.meta) {
             double common = 32.0 + 8.0 * m.gs * m.gs + 32.0 * m.gs;
             L.bytes_lower += (8.0 * m.gs + 4.0) * m.kd + common;
@@ -1006,6 +1017,7 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
             if (upload_vec(H2.meta, &L.meta2) || upload_vec(H2.CL, &L.CL) || upload_vec(H2.CU, &L.CU) || upload_vec(H2.VL, &L.VL) ||
                 upload_vec(H2.VU, &L.VU) || upload_vec(H2.BD, &L.BD)) return 1;
         } else {
+            fill_group_arrays(Ap, G);
             if (upload_vec(G.meta, &L.meta) || upload_vec(G.ci, &L.gci) || upload_vec(G.v, &L.gv)) return 1;
         }
     }
