@@ -1100,6 +1100,283 @@ __global__ void __launch_bounds__(256) k_seg_update_p(const SegChunk *__restrict
     const double beta = st[c.sub].beta;
     for (int i = c.row0 + threadIdx.x; i < c.row0 + c.nrows; i += 256) p[i] = z[i] + beta * p[i];
 }
+// ---- the other MGPIS drivers with their scalars on the device --------------------
+// MULT_SOLV (MGPIS.h:130-160), GMRES_SOLV (:227-348) and BiCGSTAB_SOLV (:350-432) of ONE hierarchy
+// (nsub == 1): every reduction ends in the KrylovState below, every vector kernel reads its coefficients
+// from there, the stopping tests run in one-warp kernels that raise the same done flag the level kernels
+// honour (BatchFlags::done_all, and PcgState::done of sub 0 for the chunk producers).  The host only
+// enqueues iterations ahead and polls the flag with a lag (mg.cu: krylov_run).
+constexpr int kGmStag = 10;   // iterStag, MGPIS.h:255
+struct KrylovState {
+    double bb, rr, tol;
+    long long it, maxit;
+    // BiCGSTAB
+    double rho_old, rho_new, alph, omeg, beta;
+    int fin, pad;
+    // GMRES(10): supeHess, Q, R of MGPIS.h:288-316, y of :317-324, moniErro (also MULT_SOLV's 5 entries)
+    double normR0;
+    double H[kGmStag + 1][kGmStag], Q[kGmStag + 1][kGmStag], R[kGmStag][kGmStag], y[kGmStag], moni[kGmStag];
+};
+__device__ __forceinline__ void krylov_stop(PcgState *st, BatchFlags *fl) { st->done = 1; fl->done_all = 1; }
+
+// y = b - w (residual from a finished product); grid-stride
+__global__ void __launch_bounds__(256) k_kry_sub(int n, const double *__restrict__ b, const double *__restrict__ w, double *__restrict__ y, const int *done)
+{
+    if (*done) return;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) y[i] = b[i] - w[i];
+}
+// common start: bb = b.b, tol = rel_tol ||b||, it = 0, loop condition `it < maxit [&& ||r|| > tol]` at it = 0
+__global__ void __launch_bounds__(32) k_kry_init(KrylovState *ks, PcgState *st, BatchFlags *fl, const double *__restrict__ bb_partial, int np,
+                                                  double rel_tol, long long maxit, int test_norm)
+{
+    const double bb = warp_reduce_partials(bb_partial, np);
+    if (threadIdx.x == 0) {
+        ks->bb = bb; ks->rr = bb; ks->tol = rel_tol * sqrt(bb); ks->it = 0; ks->maxit = maxit;
+        ks->rho_old = 1.0; ks->rho_new = 1.0; ks->alph = 1.0; ks->omeg = 1.0; ks->beta = 0.0; ks->fin = 0;
+        ks->normR0 = 0.0;
+        for (int k = 0; k < kGmStag; k++) ks->moni[k] = 0.0;
+        const int dn = !(0 < maxit && (!test_norm || sqrt(bb) > ks->tol));
+        st->done = dn; st->it = 0; st->rr = bb; st->tol = ks->tol;
+        fl->done_all = dn; fl->it_max = 0;
+    }
+}
+
+// -- BiCGSTAB ------------------------------------------------------------------------------------
+// rho = rhat.r, leave when it vanishes (MGPIS.h:383-387); beta of :392-393
+__global__ void __launch_bounds__(32) k_bi_rho(KrylovState *ks, PcgState *st, BatchFlags *fl, const double *__restrict__ partial, int np)
+{
+    if (fl->done_all) return;
+    const double rho = warp_reduce_partials(partial, np);
+    if (threadIdx.x == 0) {
+        ks->rho_new = rho;
+        if (fabs(rho) == 0.0) krylov_stop(st, fl);
+        else ks->beta = ks->it == 0 ? 0.0 : (rho / ks->rho_old) * (ks->alph / ks->omeg);
+    }
+}
+// p = r in the first iteration, r + beta (p - omeg v) afterwards (MGPIS.h:388-395)
+__global__ void __launch_bounds__(256) k_bi_update_p(int n, const KrylovState *__restrict__ ks, const double *__restrict__ r,
+                                                     const double *__restrict__ v, double *__restrict__ p, const int *done)
+{
+    if (*done) return;
+    const bool first = ks->it == 0;
+    const double beta = ks->beta, omeg = ks->omeg;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) p[i] = first ? r[i] : r[i] + beta * (p[i] - omeg * v[i]);
+}
+// alph = rho / (rhat.v) (MGPIS.h:404)
+__global__ void __launch_bounds__(32) k_bi_alpha(KrylovState *ks, const BatchFlags *fl, const double *__restrict__ partial, int np)
+{
+    if (fl->done_all) return;
+    const double rv = warp_reduce_partials(partial, np);
+    if (threadIdx.x == 0) ks->alph = ks->rho_new / rv;
+}
+// s = r - alph v (MGPIS.h:405)
+__global__ void __launch_bounds__(256) k_bi_s(int n, const KrylovState *__restrict__ ks, const double *__restrict__ r,
+                                              const double *__restrict__ v, double *__restrict__ s, const int *done)
+{
+    if (*done) return;
+    const double alph = ks->alph;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) s[i] = r[i] - alph * v[i];
+}
+// ||s|| <= 0: the reference adds alph phat to x and leaves (MGPIS.h:406-409).  Here the iteration is finished with
+// omeg = 0 (shat = t = 0 then, so x += alph phat and r = 0 exactly) without counting it, and the loop ends.
+__global__ void __launch_bounds__(32) k_bi_scheck(KrylovState *ks, const BatchFlags *fl, const double *__restrict__ ss_partial, int np)
+{
+    if (fl->done_all) return;
+    const double ss = warp_reduce_partials(ss_partial, np);
+    if (threadIdx.x == 0) ks->fin = sqrt(ss) <= 0.0;
+}
+// omeg = t.s / t.t (MGPIS.h:418)
+__global__ void __launch_bounds__(64) k_bi_omega(KrylovState *ks, const BatchFlags *fl, const double *__restrict__ ts_partial,
+                                                 const double *__restrict__ tt_partial, int np)
+{
+    if (fl->done_all) return;
+    __shared__ double s_ts;
+    const double t = warp_reduce_partials(threadIdx.x < 32 ? ts_partial : tt_partial, np);
+    if (threadIdx.x == 0) s_ts = t;
+    __syncthreads();
+    if (threadIdx.x == 32) ks->omeg = ks->fin ? 0.0 : s_ts / t;
+}
+// x += alph phat + omeg shat ; r = s - omeg t ; partial = r.r (MGPIS.h:419-420 and the norm of :382), per chunk
+__global__ void __launch_bounds__(256) k_bi_update_xr(const SegChunk *__restrict__ ch, const KrylovState *__restrict__ ks,
+                                                      const double *__restrict__ phat, const double *__restrict__ shat,
+                                                      const double *__restrict__ s, const double *__restrict__ t,
+                                                      double *__restrict__ x, double *__restrict__ r, double *rr_partial, const int *done)
+{
+    if (*done) return;
+    const SegChunk c = ch[blockIdx.x];
+    const double alph = ks->alph, omeg = ks->omeg;
+    double acc = 0.0;
+    for (int i = c.row0 + threadIdx.x; i < c.row0 + c.nrows; i += 256) {
+        x[i] += alph * phat[i] + omeg * shat[i];
+        const double ri = s[i] - omeg * t[i];
+        r[i] = ri;
+        acc += ri * ri;
+    }
+    block_sum_to_partial(acc, rr_partial);
+}
+// rr = r.r ; rho_old = rho ; it++ ; loop condition of MGPIS.h:382
+__global__ void __launch_bounds__(32) k_bi_next(KrylovState *ks, PcgState *st, BatchFlags *fl, const double *__restrict__ rr_partial, int np)
+{
+    if (fl->done_all) return;
+    const double rr = warp_reduce_partials(rr_partial, np);
+    if (threadIdx.x == 0) {
+        ks->rr = rr; ks->rho_old = ks->rho_new;
+        if (!ks->fin) ks->it += 1;
+        fl->it_max = ks->it;
+        if (ks->fin || !(ks->it < ks->maxit && sqrt(rr) > ks->tol)) krylov_stop(st, fl);
+    }
+}
+
+// -- MULT_SOLV -----------------------------------------------------------------------------------
+// moniErro[it % 5] = ||b - A x|| ; stagnation test of MGPIS.h:147-153 (VECT_MEDI_OSCI, PREP.h:147-153) ; it++
+__global__ void __launch_bounds__(32) k_ms_next(KrylovState *ks, PcgState *st, BatchFlags *fl, const double *__restrict__ rr_partial, int np)
+{
+    if (fl->done_all) return;
+    const double rr = warp_reduce_partials(rr_partial, np);
+    if (threadIdx.x == 0) {
+        ks->rr = rr;
+        ks->moni[ks->it % 5] = sqrt(rr);
+        bool stop = false;
+        if (ks->it >= 4) {
+            double mx = ks->moni[0], mn = ks->moni[0];
+            for (int k = 1; k < 5; k++) { mx = fmax(mx, ks->moni[k]); mn = fmin(mn, ks->moni[k]); }
+            stop = mx - mn < 0.1 * ((mx + mn) / 2.0);
+        }
+        if (!stop) { ks->it += 1; stop = !(ks->it < ks->maxit); }
+        fl->it_max = ks->it;
+        if (stop) krylov_stop(st, fl);
+    }
+}
+
+// -- GMRES(10) -----------------------------------------------------------------------------------
+// restart (MGPIS.h:263-276): normR_0 = ||M^-1 (b - A x_0)||, empty Hessenberg / Q / R
+__global__ void __launch_bounds__(32) k_gm_restart(KrylovState *ks, const BatchFlags *fl, const double *__restrict__ ww_partial, int np)
+{
+    if (fl->done_all) return;
+    const double ww = warp_reduce_partials(ww_partial, np);
+    double *z = &ks->H[0][0];   // H, Q, R are contiguous members
+    const int nz = (kGmStag + 1) * kGmStag * 2 + kGmStag * kGmStag;
+    for (int k = threadIdx.x; k < nz; k += 32) z[k] = 0.0;
+    if (threadIdx.x == 0) ks->normR0 = sqrt(ww);
+}
+// dst = src / c with c = normR_0 (which == 0, MGPIS.h:275) or the new column's sub-diagonal entry H[k+1][k] (:294)
+__global__ void __launch_bounds__(256) k_gm_scale(int n, const KrylovState *__restrict__ ks, int which, int k, const double *__restrict__ src,
+                                                  double *__restrict__ dst, const int *done)
+{
+    if (*done) return;
+    const double c = which == 0 ? ks->normR0 : ks->H[k + 1][k];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) dst[i] = src[i] / c;
+}
+// partial[j * np + chunk] = sum_{i in chunk} V_j[i] w[i] for j = 0..k  (b_i = orthBasi^T precV, MGPIS.h:286)
+__global__ void __launch_bounds__(256) k_gm_dots(const SegChunk *__restrict__ ch, const double *__restrict__ V, size_t ldv, int k,
+                                                 const double *__restrict__ w, double *partial, int np, const int *done)
+{
+    if (*done) return;
+    __shared__ double sm[8];
+    const SegChunk c = ch[blockIdx.x];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    for (int j = 0; j <= k; j++) {
+        const double *vj = V + (size_t)j * ldv;
+        double acc = 0.0;
+        for (int i = c.row0 + threadIdx.x; i < c.row0 + c.nrows; i += 256) acc += vj[i] * w[i];
+        acc = warp_sum(acc);
+        if (lane == 0) sm[wp] = acc;
+        __syncthreads();
+        if (wp == 0) {
+            double t = lane < 8 ? sm[lane] : 0.0;
+            t = warp_sum(t);
+            if (lane == 0) partial[(size_t)j * np + blockIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+// H[j][k] = b_i(j), j = 0..k
+__global__ void __launch_bounds__(32) k_gm_hcol(KrylovState *ks, const BatchFlags *fl, const double *__restrict__ partial, int np, int k)
+{
+    if (fl->done_all) return;
+    for (int j = 0; j <= k; j++) {
+        const double t = warp_reduce_partials(partial + (size_t)j * np, np);
+        if (threadIdx.x == 0) ks->H[j][k] = t;
+    }
+}
+// w -= sum_j H[j][k] V_j  (q_ip1 = precV - orthBasi b_i, MGPIS.h:287)
+__global__ void __launch_bounds__(256) k_gm_orth(int n, const KrylovState *__restrict__ ks, const double *__restrict__ V, size_t ldv, int k,
+                                                 double *__restrict__ w, const int *done)
+{
+    if (*done) return;
+    double hk[kGmStag];
+#pragma unroll
+    for (int j = 0; j < kGmStag; j++) hk[j] = j <= k ? ks->H[j][k] : 0.0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < kGmStag; j++) if (j <= k) s += V[(size_t)j * ldv + i] * hk[j];
+        w[i] -= s;
+    }
+}
+// H[k+1][k] = ||q_ip1|| ; one Gram-Schmidt column of the QR of the Hessenberg matrix (MGPIS.h:297-316) ; back
+// substitution for y (:317-324)
+__global__ void __launch_bounds__(32) k_gm_hess(KrylovState *ks, const BatchFlags *fl, const double *__restrict__ qq_partial, int np, int k)
+{
+    if (fl->done_all) return;
+    const double qq = warp_reduce_partials(qq_partial, np);
+    if (threadIdx.x != 0) return;
+    ks->H[k + 1][k] = sqrt(qq);
+    double col[kGmStag + 1];
+    for (int i = 0; i <= k + 1; i++) col[i] = ks->H[i][k];
+    for (int j = 0; j < k; j++) {
+        double s = 0.0;
+        for (int i = 0; i <= k + 1; i++) s += ks->Q[i][j] * ks->H[i][k];
+        ks->R[j][k] = s;
+    }
+    for (int j = 0; j < k; j++) for (int i = 0; i <= k + 1; i++) col[i] -= ks->Q[i][j] * ks->R[j][k];
+    double nc = 0.0;
+    for (int i = 0; i <= k + 1; i++) nc += col[i] * col[i];
+    nc = sqrt(nc);
+    ks->R[k][k] = nc;
+    for (int i = 0; i <= k + 1; i++) ks->Q[i][k] = col[i] / nc;
+    for (int j = k; j >= 0; j--) {
+        double s = 0.0;
+        for (int c = j + 1; c <= k; c++) s += ks->R[j][c] * ks->y[c];
+        ks->y[j] = (ks->normR0 * ks->Q[0][j] - s) / ks->R[j][j];
+    }
+}
+// x = x_0 + sum_{j<=k} y_j V_j (MGPIS.h:325)
+__global__ void __launch_bounds__(256) k_gm_update_x(int n, const KrylovState *__restrict__ ks, const double *__restrict__ V, size_t ldv, int k,
+                                                     const double *__restrict__ x0, double *__restrict__ x, const int *done)
+{
+    if (*done) return;
+    double yk[kGmStag];
+#pragma unroll
+    for (int j = 0; j < kGmStag; j++) yk[j] = j <= k ? ks->y[j] : 0.0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < kGmStag; j++) if (j <= k) s += V[(size_t)j * ldv + i] * yk[j];
+        x[i] = x0[i] + s;
+    }
+}
+// moniErro[k] = ||b - A x|| ; stopping tests of MGPIS.h:333-341 ; it++ ; `it < maxiNumb` of :261
+__global__ void __launch_bounds__(32) k_gm_next(KrylovState *ks, PcgState *st, BatchFlags *fl, const double *__restrict__ rr_partial, int np, int k)
+{
+    if (fl->done_all) return;
+    const double rr = warp_reduce_partials(rr_partial, np);
+    if (threadIdx.x == 0) {
+        ks->rr = rr;
+        const double e = sqrt(rr);
+        ks->moni[k] = e;
+        bool stop = false;
+        if (ks->it >= kGmStag - 1) {
+            double mx = ks->moni[0], mn = ks->moni[0];
+            for (int c = 1; c < kGmStag; c++) { mx = fmax(mx, ks->moni[c]); mn = fmin(mn, ks->moni[c]); }
+            stop = e <= ks->tol || (e <= 1.0E2 * ks->tol && (mx - mn) < 0.1 * ((mx + mn) / 2.0));
+        }
+        if (!stop) { ks->it += 1; stop = !(ks->it < ks->maxit); }
+        fl->it_max = ks->it;
+        if (stop) krylov_stop(st, fl);
+    }
+}
+
 // Block-diagonal dense solves: y_s = Binv_s b_s for every block s (level-0 direct solves of a batch, interface
 // mass matrices of the ADMM loop).  One warp per row; off[s] = first row of block s, bptr[s] = its dense
 // inverse (n_s x n_s, row-major) or null: that block is handled elsewhere and its rows are left alone.

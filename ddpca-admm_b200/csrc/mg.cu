@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -212,6 +213,7 @@ struct ddpca_mg : Engine {
     BatchFlags *fl = nullptr;
     BatchFlags *fl_host = nullptr;   // pinned, ring of kDepth+2
     double *partial[3] = {nullptr, nullptr, nullptr};
+    KrylovState *ks = nullptr;    // scalars of MULT_SOLV / GMRES_SOLV / BiCGSTAB_SOLV (allocated on first use)
     cudaGraphExec_t iter_graph[2] = {nullptr, nullptr};  // per preconditioner
     long iter_graph_nodes[2] = {0, 0};
     // whole solve as ONE graph: set-up nodes + a WHILE conditional node around the iteration body
@@ -1424,6 +1426,7 @@ int ddpca_mg_destroy(ddpca_mg *h)
     if (h->st_host) cudaFreeHost(h->st_host);
     if (h->fl_host) cudaFreeHost(h->fl_host);
     for (int k = 0; k < 3; k++) cudaFree(h->partial[k]);
+    cudaFree(h->ks);
     for (int k = 0; k < 2; k++) if (h->iter_graph[k]) cudaGraphExecDestroy(h->iter_graph[k]);
     for (int k = 0; k < 2; k++) if (h->solve_graph[k]) cudaGraphExecDestroy(h->solve_graph[k]);
     for (int k = 0; k < 4; k++) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
@@ -1763,8 +1766,8 @@ int ddpca_mg_coarse_solve(ddpca_mg *h, const double *b, double *x)
     return to_host(h, 0, h->cg_q, x);
 }
 
-// ---- host-driven drivers on the same kernels: scalars come back to the host
-// after every reduction; these are not the throughput path.
+// ---- host-driven drivers on the same kernels: scalars come back to the host after every
+// reduction.  Kept as the cross-check of the device-resident drivers further down (DDPCA_KRYLOV_HOSTLOOP=1).
 static int dev_dot(ddpca_mg *h, int n, const double *a, const double *b, double *out)
 {
     int gv = vec_grid(h, n);
@@ -1783,10 +1786,8 @@ static void dev_axpby(ddpca_mg *h, int n, double a, const double *x, double b, d
 }
 
 // MGPIS::MULT_SOLV, MGPIS.h:130-160: V-cycle iteration until the residual norm stagnates
-int ddpca_mg_mult_solv(ddpca_mg *h, const double *b, double *x, long *iters, double *resid)
+static int mult_solv_hostloop(ddpca_mg *h, const double *b, double *x, long *iters, double *resid)
 {
-    if (!h || !b || !x) return fail("ddpca_mg_mult_solv: bad argument");
-    CU(cudaSetDevice(h->device));
     int Lf = h->nlev - 1;
     Level &L = h->lev[Lf];
     int n = L.n;
@@ -1818,10 +1819,8 @@ int ddpca_mg_mult_solv(ddpca_mg *h, const double *b, double *x, long *iters, dou
 
 // MGPIS::GMRES_SOLV, MGPIS.h:227-348: left-preconditioned restarted GMRES(10); Arnoldi vectors and
 // all matrix / preconditioner work on the device, the 11x10 Hessenberg algebra on the host.
-int ddpca_mg_gmres(ddpca_mg *h, int prec, const double *b, double *x, long *iters, double *resid, double *tol_abs)
+static int gmres_hostloop(ddpca_mg *h, int prec, const double *b, double *x, long *iters, double *resid, double *tol_abs)
 {
-    if (!h || !b || !x || (prec != 0 && prec != 1)) return fail("ddpca_mg_gmres: bad argument");
-    CU(cudaSetDevice(h->device));
     enum { STAG = 10 };
     int Lf = h->nlev - 1;
     Level &L = h->lev[Lf];
@@ -1918,11 +1917,9 @@ int ddpca_mg_gmres(ddpca_mg *h, int prec, const double *b, double *x, long *iter
 }
 
 // MGPIS::BiCGSTAB_SOLV, MGPIS.h:350-432
-int ddpca_mg_bicgstab(ddpca_mg *h, int prec, const double *b, double *x, double rel_tol, long maxit, long *iters,
-                      double *resid, double *tol_abs)
+static int bicgstab_hostloop(ddpca_mg *h, int prec, const double *b, double *x, double rel_tol, long maxit, long *iters,
+                             double *resid, double *tol_abs)
 {
-    if (!h || !b || !x || (prec != 0 && prec != 1)) return fail("ddpca_mg_bicgstab: bad argument");
-    CU(cudaSetDevice(h->device));
     int Lf = h->nlev - 1;
     Level &L = h->lev[Lf];
     int n = L.n;
@@ -1988,6 +1985,214 @@ int ddpca_mg_bicgstab(ddpca_mg *h, int prec, const double *b, double *x, double 
     int rc = to_host(h, Lf, xd, x);
     cleanup();
     return rc;
+}
+
+// ---- the same three drivers with every scalar on the device (kernels.cuh, KrylovState) -----------------------
+// The host enqueues whole iterations ahead and polls the done flag with a lag of kDepth iterations; launches
+// issued past the stop leave at their first instruction.  No reduction result crosses to the host inside the loop.
+static int krylov_run(ddpca_mg *h, const std::function<int(long)> &enqueue_iter)
+{
+    const int depth = h->profile ? 0 : kDepth;
+    cudaEvent_t evs[kDepth + 1];
+    for (int k = 0; k <= kDepth; k++) CU(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+    CU(cudaMemcpyAsync(&h->fl_host[0], h->fl, sizeof(BatchFlags), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(evs[0], h->stream));
+    CU(cudaEventSynchronize(evs[0]));
+    bool finished = h->fl_host[0].done_all != 0;
+    long issued = 0;
+    while (!finished) {
+        const int slot = (int)(issued % (kDepth + 1));
+        if (enqueue_iter(issued)) return 1;
+        CU(cudaMemcpyAsync(&h->fl_host[slot], h->fl, sizeof(BatchFlags), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventRecord(evs[slot], h->stream));
+        issued++;
+        if (issued >= depth) {
+            const int old = (int)((issued - std::max(depth, 1)) % (kDepth + 1));
+            CU(cudaEventSynchronize(evs[old]));
+            if (h->fl_host[old].done_all) finished = true;
+        }
+        if (h->profile && (issued % 8) == 0) h->prof_collect();
+    }
+    for (int k = 0; k <= kDepth; k++) cudaEventDestroy(evs[k]);
+    return 0;
+}
+static int krylov_prepare(ddpca_mg *h, int prec)
+{
+    if (h->nsub != 1) return fail("MULT_SOLV / GMRES_SOLV / BiCGSTAB_SOLV take one hierarchy (not a batch)");
+    if (prec == 1 && !h->Binv) return fail("this hierarchy was built without a level-0 direct solver: Jacobi preconditioning only");
+    Level &L = h->lev[h->nlev - 1];
+    if (prec == 0 && !L.dinv) {
+        CU(cudaMalloc(&L.dinv, sizeof(double) * L.n));
+        if (L.v2) k_extract_diag_inv2<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view2(), L.dinv);
+        else k_extract_diag_inv<<<cdiv(L.ng, 256), 256, 0, h->stream>>>(L.view(), L.dinv);
+    }
+    if (!h->ks) CU(cudaMalloc(&h->ks, sizeof(KrylovState)));
+    return 0;
+}
+static int krylov_finish(ddpca_mg *h, KrylovState *hs)
+{
+    CU(cudaMemcpyAsync(hs, h->ks, sizeof(KrylovState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (!h->launch_err.empty()) { std::string m = h->launch_err; h->launch_err.clear(); cudaGetLastError(); return fail(m); }
+    if (h->profile) h->prof_collect();
+    CU(cudaGetLastError());
+    return 0;
+}
+#define KSEGDOT(a, b, part, dn) KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_seg_dot<<<ns, 256, 0, h->stream>>>(h->seg_d, a, b, part, dn)))
+
+// MGPIS::MULT_SOLV, MGPIS.h:130-160
+static int mult_solv_device(ddpca_mg *h, const double *b, double *x, long *iters, double *resid)
+{
+    if (krylov_prepare(h, 1)) return 1;
+    const int Lf = h->nlev - 1;
+    Level &L = h->lev[Lf];
+    const int n = L.n, ns = h->nseg, gv = vec_grid(h, n);
+    const int *done = h->done_flag();
+    double *bd = h->cg_r, *xd = h->cg_x, *rd = h->cg_q, *ax = h->cg_p;
+    if (to_dev(h, Lf, b, bd)) return 1;
+    CU(cudaMemsetAsync(xd, 0, sizeof(double) * n, h->stream));                                           // :133
+    KSEGDOT(bd, bd, h->partial[0], nullptr);
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_kry_init<<<1, 32, 0, h->stream>>>(h->ks, h->st, h->fl, h->partial[0], ns, 0.0, 10000LL, 0)));   // :134
+    if (krylov_run(h, [&](long) -> int {
+            vcycle_dev(h, Lf, bd, xd, false, done);                                                      // :143
+            launch_level_spmv(h, L, Lf, xd, ax, nullptr, nullptr, done);
+            KL(h, DDPCA_K_VECTOR, Lf, 24.0 * n, (k_kry_sub<<<gv, 256, 0, h->stream>>>(n, bd, ax, rd, done)));    // :144
+            KSEGDOT(rd, rd, h->partial[0], done);
+            KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_ms_next<<<1, 32, 0, h->stream>>>(h->ks, h->st, h->fl, h->partial[0], ns)));   // :146-154
+            return 0;
+        })) return 1;
+    KrylovState hs;
+    if (krylov_finish(h, &hs)) return 1;
+    if (iters) *iters = (long)hs.it;
+    if (resid) *resid = hs.moni[hs.it % 5];
+    return to_host(h, Lf, xd, x);
+}
+
+// MGPIS::GMRES_SOLV, MGPIS.h:227-348: left-preconditioned restarted GMRES(10); the 11x10 Hessenberg algebra runs in
+// a one-warp kernel (k_gm_hess), the Arnoldi coefficients never leave the device
+static int gmres_device(ddpca_mg *h, int prec, const double *b, double *x, long *iters, double *resid, double *tol_abs)
+{
+    if (krylov_prepare(h, prec)) return 1;
+    const int Lf = h->nlev - 1;
+    Level &L = h->lev[Lf];
+    const int n = L.n, ns = h->nseg, gv = vec_grid(h, n);
+    const int *done = h->done_flag();
+    // Arnoldi vectors with stride n+1: each keeps the always-zero slot the padded gathers rely on (alloc_vec)
+    const size_t ldv = (size_t)n + 1;
+    double *V = nullptr, *x0 = nullptr, *bd = nullptr, *hp = nullptr;
+    auto cleanup = [&]() { cudaFree(V); cudaFree(x0); cudaFree(bd); cudaFree(hp); };
+    if (alloc_vec(&V, (long)(ldv * (kGmStag + 1)) - 1) || alloc_vec(&x0, n) || alloc_vec(&bd, n) || alloc_vec(&hp, (long)kGmStag * ns)) { cleanup(); return 1; }
+    double *r = h->cg_r, *w0 = h->cg_q, *w = h->cg_z, *xd = h->cg_x;
+    if (to_dev(h, Lf, b, bd)) { cleanup(); return 1; }
+    CUX(cudaMemsetAsync(xd, 0, sizeof(double) * n, h->stream));                                           // :248
+    KSEGDOT(bd, bd, h->partial[0], nullptr);
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_kry_init<<<1, 32, 0, h->stream>>>(h->ks, h->st, h->fl, h->partial[0], ns, 1.0E-12, (long long)n, 0)));   // :249-250
+    int rc = krylov_run(h, [&](long it) -> int {
+        const int k = (int)(it % kGmStag);
+        if (k == 0) {                                                                                     // restart, :263-276
+            if (cudaMemcpyAsync(x0, xd, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess) return fail("GMRES restart: device copy failed");
+            launch_level_spmv(h, L, Lf, x0, w0, nullptr, nullptr, done);
+            KL(h, DDPCA_K_VECTOR, Lf, 24.0 * n, (k_kry_sub<<<gv, 256, 0, h->stream>>>(n, bd, w0, r, done)));
+            precondition(h, prec, r, w, done);
+            KSEGDOT(w, w, h->partial[0], done);
+            KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_gm_restart<<<1, 32, 0, h->stream>>>(h->ks, h->fl, h->partial[0], ns)));
+            KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_gm_scale<<<gv, 256, 0, h->stream>>>(n, h->ks, 0, 0, w, V, done)));
+        }
+        launch_level_spmv(h, L, Lf, V + (size_t)k * ldv, w0, nullptr, nullptr, done);                     // :278
+        precondition(h, prec, w0, w, done);                                                               // :279-285
+        KL(h, DDPCA_K_VECTOR, Lf, 8.0 * n * (k + 2), (k_gm_dots<<<ns, 256, 0, h->stream>>>(h->seg_d, V, ldv, k, w, hp, ns, done)));   // :286
+        KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_gm_hcol<<<1, 32, 0, h->stream>>>(h->ks, h->fl, hp, ns, k)));
+        KL(h, DDPCA_K_VECTOR, Lf, 8.0 * n * (k + 3), (k_gm_orth<<<gv, 256, 0, h->stream>>>(n, h->ks, V, ldv, k, w, done)));            // :287
+        KSEGDOT(w, w, h->partial[0], done);                                                               // :288
+        KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_gm_hess<<<1, 32, 0, h->stream>>>(h->ks, h->fl, h->partial[0], ns, k)));                       // :289-324
+        KL(h, DDPCA_K_VECTOR, Lf, 16.0 * n, (k_gm_scale<<<gv, 256, 0, h->stream>>>(n, h->ks, 1, k, w, V + (size_t)(k + 1) * ldv, done)));   // :294-296
+        KL(h, DDPCA_K_VECTOR, Lf, 8.0 * n * (k + 3), (k_gm_update_x<<<gv, 256, 0, h->stream>>>(n, h->ks, V, ldv, k, x0, xd, done)));     // :325
+        launch_level_spmv(h, L, Lf, xd, w0, nullptr, nullptr, done);                                      // :326
+        KL(h, DDPCA_K_VECTOR, Lf, 24.0 * n, (k_kry_sub<<<gv, 256, 0, h->stream>>>(n, bd, w0, r, done)));
+        KSEGDOT(r, r, h->partial[0], done);
+        KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_gm_next<<<1, 32, 0, h->stream>>>(h->ks, h->st, h->fl, h->partial[0], ns, k)));               // :328-342
+        return 0;
+    });
+    KrylovState hs;
+    if (rc || krylov_finish(h, &hs)) { cleanup(); return 1; }
+    if (iters) *iters = (long)hs.it;
+    if (resid) *resid = hs.moni[hs.it % kGmStag];
+    if (tol_abs) *tol_abs = hs.tol;
+    rc = to_host(h, Lf, xd, x);
+    cleanup();
+    return rc;
+}
+
+// MGPIS::BiCGSTAB_SOLV, MGPIS.h:350-432
+static int bicgstab_device(ddpca_mg *h, int prec, const double *b, double *x, double rel_tol, long maxit, long *iters,
+                           double *resid, double *tol_abs)
+{
+    if (krylov_prepare(h, prec)) return 1;
+    const int Lf = h->nlev - 1;
+    Level &L = h->lev[Lf];
+    const int n = L.n, ns = h->nseg, gv = vec_grid(h, n);
+    const int *done = h->done_flag();
+    std::vector<double *> w(4, nullptr);
+    auto cleanup = [&]() { for (auto q : w) cudaFree(q); };
+    for (auto &p : w) if (alloc_vec(&p, n)) { cleanup(); return 1; }
+    double *r = h->cg_r, *rhat = w[0], *p = h->cg_p, *v = h->cg_q, *s = w[1], *t = w[2], *phat = h->cg_z, *shat = w[3], *xd = h->cg_x;
+    if (to_dev(h, Lf, b, r)) { cleanup(); return 1; }
+    CUX(cudaMemsetAsync(xd, 0, sizeof(double) * n, h->stream));                                           // :361
+    CUX(cudaMemcpyAsync(rhat, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));                // :378
+    KSEGDOT(r, r, h->partial[0], nullptr);
+    KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_kry_init<<<1, 32, 0, h->stream>>>(h->ks, h->st, h->fl, h->partial[0], ns, rel_tol, (long long)maxit, 1)));   // :362-363,382
+    int rc = krylov_run(h, [&](long) -> int {
+        KSEGDOT(rhat, r, h->partial[0], done);                                                            // :383
+        KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_bi_rho<<<1, 32, 0, h->stream>>>(h->ks, h->st, h->fl, h->partial[0], ns)));                   // :384-393
+        KL(h, DDPCA_K_VECTOR, Lf, 32.0 * n, (k_bi_update_p<<<gv, 256, 0, h->stream>>>(n, h->ks, r, v, p, done)));                     // :388-395
+        precondition(h, prec, p, phat, done);                                                             // :396-402
+        launch_level_spmv(h, L, Lf, phat, v, nullptr, nullptr, done);                                     // :403
+        KSEGDOT(rhat, v, h->partial[0], done);
+        KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_bi_alpha<<<1, 32, 0, h->stream>>>(h->ks, h->fl, h->partial[0], ns)));                        // :404
+        KL(h, DDPCA_K_VECTOR, Lf, 24.0 * n, (k_bi_s<<<gv, 256, 0, h->stream>>>(n, h->ks, r, v, s, done)));                            // :405
+        KSEGDOT(s, s, h->partial[0], done);
+        KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_bi_scheck<<<1, 32, 0, h->stream>>>(h->ks, h->fl, h->partial[0], ns)));                       // :406-409
+        precondition(h, prec, s, shat, done);                                                             // :410-416
+        launch_level_spmv(h, L, Lf, shat, t, nullptr, nullptr, done);                                     // :417
+        KSEGDOT(t, s, h->partial[0], done);
+        KSEGDOT(t, t, h->partial[1], done);
+        KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_bi_omega<<<1, 64, 0, h->stream>>>(h->ks, h->fl, h->partial[0], h->partial[1], ns)));         // :418
+        KL(h, DDPCA_K_VECTOR, Lf, 64.0 * n, (k_bi_update_xr<<<ns, 256, 0, h->stream>>>(h->seg_d, h->ks, phat, shat, s, t, xd, r, h->partial[2], done)));   // :419-420
+        KL(h, DDPCA_K_VECTOR, Lf, 0.0, (k_bi_next<<<1, 32, 0, h->stream>>>(h->ks, h->st, h->fl, h->partial[2], ns)));                  // :382
+        return 0;
+    });
+    KrylovState hs;
+    if (rc || krylov_finish(h, &hs)) { cleanup(); return 1; }
+    if (iters) *iters = (long)hs.it;
+    if (resid) *resid = std::sqrt(hs.rr);
+    if (tol_abs) *tol_abs = hs.tol;
+    rc = to_host(h, Lf, xd, x);
+    cleanup();
+    return rc;
+}
+#undef KSEGDOT
+
+static bool krylov_hostloop() { return std::getenv("DDPCA_KRYLOV_HOSTLOOP") != nullptr; }
+
+int ddpca_mg_mult_solv(ddpca_mg *h, const double *b, double *x, long *iters, double *resid)
+{
+    if (!h || !b || !x) return fail("ddpca_mg_mult_solv: bad argument");
+    CU(cudaSetDevice(h->device));
+    return krylov_hostloop() ? mult_solv_hostloop(h, b, x, iters, resid) : mult_solv_device(h, b, x, iters, resid);
+}
+int ddpca_mg_gmres(ddpca_mg *h, int prec, const double *b, double *x, long *iters, double *resid, double *tol_abs)
+{
+    if (!h || !b || !x || (prec != 0 && prec != 1)) return fail("ddpca_mg_gmres: bad argument");
+    CU(cudaSetDevice(h->device));
+    return krylov_hostloop() ? gmres_hostloop(h, prec, b, x, iters, resid, tol_abs) : gmres_device(h, prec, b, x, iters, resid, tol_abs);
+}
+int ddpca_mg_bicgstab(ddpca_mg *h, int prec, const double *b, double *x, double rel_tol, long maxit, long *iters,
+                      double *resid, double *tol_abs)
+{
+    if (!h || !b || !x || (prec != 0 && prec != 1)) return fail("ddpca_mg_bicgstab: bad argument");
+    CU(cudaSetDevice(h->device));
+    return krylov_hostloop() ? bicgstab_hostloop(h, prec, b, x, rel_tol, maxit, iters, resid, tol_abs)
+                             : bicgstab_device(h, prec, b, x, rel_tol, maxit, iters, resid, tol_abs);
 }
 
 int ddpca_ldlt_create(int device, int n, const int *perm, const int *L_rowptr, const int *L_colidx, const double *L_val,

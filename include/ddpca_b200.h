@@ -122,8 +122,11 @@ int ddpca_mg_prolong_add(ddpca_mg *, int level, const double *e_coarse, double *
 /* direSolv.solve(b) on consStif[0], MGPIS.h:58 */
 int ddpca_mg_coarse_solve(ddpca_mg *, const double *b, double *x);
 
-/* MGPIS::MULT_SOLV (MGPIS.h:130-160), BiCGSTAB_SOLV (:350-432), GMRES_SOLV (:227-348): the same
- * kernels under host-driven drivers (scalars return to the host after each reduction) */
+/* MGPIS::MULT_SOLV (MGPIS.h:130-160), BiCGSTAB_SOLV (:350-432), GMRES_SOLV (:227-348) on the same
+ * kernels, one hierarchy per handle (not a batch).  The recurrences are device-resident: every
+ * reduction, coefficient and stopping test (incl. the 11x10 Hessenberg QR of GMRES) stays on the
+ * device, the host enqueues iterations ahead and polls one flag.  DDPCA_KRYLOV_HOSTLOOP=1 selects
+ * the older drivers that read every scalar back (kept as a cross-check). */
 int ddpca_mg_mult_solv(ddpca_mg *, const double *b, double *x, long *iters, double *resid);
 int ddpca_mg_bicgstab(ddpca_mg *, int prec, const double *b, double *x, double rel_tol, long maxit,
                       long *iters, double *resid, double *tol_abs);

@@ -254,6 +254,50 @@ def test_gmres_matches_oracle(solvers):
         assert rel(x, d["gmres_mg_x"]) < 1e-8
 
 
+def test_device_resident_drivers_agree_with_the_host_looped_ones(monkeypatch):
+    """MULT_SOLV / BiCGSTAB_SOLV / GMRES_SOLV keep their scalars on the device (kernels.cuh, KrylovState); the older
+    drivers that read every dot product back are selected by DDPCA_KRYLOV_HOSTLOOP=1.  Same recurrences on the same
+    kernels: iteration counts agree (a stop decided on the residual floor may move by an iteration) and so do the
+    solutions; a zero right-hand side never enters the BiCGSTAB loop (MGPIS.h:382)."""
+    d, meta, A, P = load_golden("beam_2lev")
+    mg = dd.MGPIS.from_hierarchy(A, P, smoother=dd.SMOOTH_MC)
+    b = d["consForc"]
+    out = {}
+    for host in ("1", ""):
+        if host:
+            monkeypatch.setenv("DDPCA_KRYLOV_HOSTLOOP", host)
+        else:
+            monkeypatch.delenv("DDPCA_KRYLOV_HOSTLOOP", raising=False)
+        res = {}
+        x = mg.BiCGSTAB_SOLV(1, b)
+        res["bicgstab"] = (x, mg.last_iterNumb, mg.last_resid, mg.last_tol)
+        x = mg.GMRES_SOLV(1, b)
+        res["gmres"] = (x, mg.last_iterNumb, mg.last_resid, mg.last_tol)
+        x = mg.MULT_SOLV(b)
+        res["mult"] = (x, mg.last_iterNumb, mg.last_resid, None)
+        out[host] = res
+    for name in out[""]:
+        xh, ith, resh, tolh = out["1"][name]
+        xd, itd, resd, told = out[""][name]
+        if name != "mult" or ith < 100:   # beyond that MULT_SOLV's stagnation stop is decided by round-off noise
+            assert abs(itd - ith) <= max(1, ith // 20), (name, itd, ith)
+        assert rel(xd, xh) < 1e-8, name
+        if told is not None:
+            assert told == pytest.approx(tolh, rel=1e-12)
+    x, it, res, tol = out[""]["bicgstab"]
+    assert res <= tol and rel(x, d["cg_mg_x"]) < 1e-8
+    z = mg.BiCGSTAB_SOLV(1, np.zeros_like(b))
+    assert mg.last_iterNumb == 0 and not np.any(z)
+    # Jacobi preconditioning (precSwit 0, PREP.h:393-401) to a looser tolerance: converged by its own measure and
+    # by the true residual
+    x = mg.BiCGSTAB_SOLV(0, b, rel_tol=1e-8)
+    assert mg.last_resid <= mg.last_tol
+    assert np.linalg.norm(b - A[-1] @ x) <= 1e-6 * np.linalg.norm(b)
+    # the CG driver still works on the same handle afterwards (it re-arms the done flags the other drivers left set)
+    xc = mg.CG_SOLV(1, b)
+    assert rel(xc, d["cg_mg_x"]) < 1e-8
+
+
 def test_batched_hierarchies_advance_per_subdomain():
     """ddpca_mg_create_batch: three subdomain hierarchies as one block-diagonal device hierarchy.  Every
     subdomain keeps its own CG recurrence (MGPIS.h:163-225 is called once per subdomain by the body loop,
