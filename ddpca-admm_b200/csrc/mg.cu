@@ -255,8 +255,8 @@ static void free_csr(DevCsr &d)
     cudaFree(d.rp); cudaFree(d.ci); cudaFree(d.v);
     d = DevCsr();
 }
-template <class T>
-static int upload_vec(const std::vector<T> &h, T **d)
+template <class T, class Al>
+static int upload_vec(const std::vector<T, Al> &h, T **d)
 {
     CU(cudaMalloc(d, sizeof(T) * std::max<size_t>(1, h.size())));
     if (!h.empty()) CU(cudaMemcpy(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
@@ -288,13 +288,17 @@ struct StageTimer {
 // Node-triple form of a transfer operator: runs of three consecutive rows that are shifted copies of each other
 // (same length, same values, columns +1, +2) are stored once; everything else goes to the CSR remainder.  Worth it
 // when most rows are in triples (no nodal rotations); returns with t.ok == false otherwise.
-static int build_trip(const CsrHost &A, DevTrip &t)
-{
-    t.rows = A.rows; t.cols = A.cols;
-    std::vector<int> trow, tptr(1, 0), tcol, rest_row;
+struct TripHost {
+    bool ok = false;
+    std::vector<int> trow, tptr, tcol, rest_row;
     std::vector<double> tw;
     CsrHost R;
-    R.rp.push_back(0);
+};
+static void build_trip_host(const CsrHost &A, TripHost &T)
+{
+    T = TripHost();
+    T.tptr.assign(1, 0);
+    T.R.rp.push_back(0);
     long in_trip = 0;
     for (int i = 0; i < A.rows;) {
         bool trip = false;
@@ -308,27 +312,31 @@ static int build_trip(const CsrHost &A, DevTrip &t)
             }
         }
         if (trip) {
-            trow.push_back(i);
-            for (int p = A.rp[i]; p < A.rp[i + 1]; p++) { tcol.push_back(A.ci[p]); tw.push_back(A.v[p]); }
-            tptr.push_back((int)tcol.size());
+            T.trow.push_back(i);
+            for (int p = A.rp[i]; p < A.rp[i + 1]; p++) { T.tcol.push_back(A.ci[p]); T.tw.push_back(A.v[p]); }
+            T.tptr.push_back((int)T.tcol.size());
             in_trip += 3;
             i += 3;
         } else {
-            rest_row.push_back(i);
-            for (int p = A.rp[i]; p < A.rp[i + 1]; p++) { R.ci.push_back(A.ci[p]); R.v.push_back(A.v[p]); }
-            R.rp.push_back((int)R.ci.size());
+            T.rest_row.push_back(i);
+            for (int p = A.rp[i]; p < A.rp[i + 1]; p++) { T.R.ci.push_back(A.ci[p]); T.R.v.push_back(A.v[p]); }
+            T.R.rp.push_back((int)T.R.ci.size());
             i += 1;
         }
     }
-    if (A.rows == 0 || in_trip < 0.8 * A.rows || std::getenv("DDPCA_NO_TRIP")) return 0;
-    R.rows = (int)rest_row.size(); R.cols = A.cols;
-    t.ntrip = (int)trow.size(); t.nrest = R.rows; t.npairs = (long)tcol.size(); t.nnz_rest = R.nnz();
-    if (upload_vec(trow, &t.trow) || upload_vec(tptr, &t.tptr) || upload_vec(tcol, &t.tcol) || upload_vec(tw, &t.tw) ||
-        upload_vec(rest_row, &t.rest_row) || upload_csr(R, t.rest)) return 1;
+    T.R.rows = (int)T.rest_row.size(); T.R.cols = A.cols;
+    T.ok = !(A.rows == 0 || in_trip < 0.8 * A.rows || std::getenv("DDPCA_NO_TRIP"));
+}
+static int upload_trip(const CsrHost &A, const TripHost &T, DevTrip &t)
+{
+    t.rows = A.rows; t.cols = A.cols;
+    if (!T.ok) return 0;
+    t.ntrip = (int)T.trow.size(); t.nrest = T.R.rows; t.npairs = (long)T.tcol.size(); t.nnz_rest = T.R.nnz();
+    if (upload_vec(T.trow, &t.trow) || upload_vec(T.tptr, &t.tptr) || upload_vec(T.tcol, &t.tcol) || upload_vec(T.tw, &t.tw) ||
+        upload_vec(T.rest_row, &t.rest_row) || upload_csr(T.R, t.rest)) return 1;
     t.ok = true;
     return 0;
 }
-
 // ---- kernel launch helpers (all on h->stream) ----------------------------------------------
 static void launch_spmv(Engine *h, int kclass, int lvl, const DevCsr &A, const double *x, double *y, bool add,
                         const double *dotw, double *partial, const int *done, double alpha = 1.0)
@@ -796,8 +804,9 @@ static void fill_group_arrays(const CsrHost &Ap, GroupLayoutHost &out)
 // ---- v2 layout (kernels2.cuh): split lower / upper arrays in stage order + chunk table -----------
 struct Layout2Host {
     std::vector<GroupMeta2> meta;
-    std::vector<int> CL, CU;
-    std::vector<double> VL, VU, BD;
+    RawVec<int> CL, CU;       // written in full (pads included) by the parallel fill of build_layout2
+    RawVec<double> VL, VU;
+    std::vector<double> BD;
     // per chunk table (V2_TAB_*)
     std::vector<ChunkDesc> chunks[3];
     std::vector<int> stage_chunk[3];
@@ -881,8 +890,8 @@ static bool build_layout2(const CsrHost &Ap, const LevelPlan &pl, Layout2Host &o
         vl += (long)gs * m.nl / 2; vu += (long)gs * m.nu / 2;
         if (cl > 0x7ffffff0L || cu > 0x7ffffff0L || vl > 0x7ffffff0L || vu > 0x7ffffff0L) { err = "level too large for 32-bit chunk offsets"; return false; }
     }
-    out.CL.assign(cl, 0); out.CU.assign(cu, 0);
-    out.VL.assign(vl * 2, 0.0); out.VU.assign(vu * 2, 0.0);
+    out.CL.resize(cl); out.CU.resize(cu);
+    out.VL.resize(vl * 2); out.VU.resize(vu * 2);
     out.BD.assign((size_t)ng * kBlkStride, 0.0);
 #pragma omp parallel for schedule(static)
     for (int g = 0; g < ng; g++) {
@@ -901,7 +910,9 @@ static bool build_layout2(const CsrHost &Ap, const LevelPlan &pl, Layout2Host &o
             double *dl = out.VL.data() + (size_t)m.vl * 2 + (size_t)r * m.nl;
             double *du = out.VU.data() + (size_t)m.vu * 2 + (size_t)r * m.nu;
             for (int k = 0; k < nlr; k++) dl[k] = vr[k];
+            for (int k = nlr; k < m.nl; k++) dl[k] = 0.0;
             for (int k = 0; k < nur; k++) du[k] = vr[kd + gs + k];
+            for (int k = nur; k < m.nu; k++) du[k] = 0.0;
             for (int c = 0; c < gs; c++) out.BD[(size_t)g * kBlkStride + r * 3 + c] = vr[kd + c];
             out.BD[(size_t)g * kBlkStride + 9 + r] = 1.0 / vr[kd + r];
         }
@@ -947,27 +958,46 @@ static int build_segments(Level &L, const GroupLayoutHost &G)
     return 0;
 }
 
-// Plan + permute + group layout + upload of one operator level (device must be current).
-static int setup_level(Level &L, int n, const int *rp, const int *ci, const double *v, int mode, bool keep_csr, bool group_layout,
-                       const std::vector<int> *sub_off = nullptr, const LevelPlan *given_plan = nullptr)
+// Set-up of one operator level in two halves: everything the host computes (plan, permuted operator, layouts, chunk
+// tables, byte counts -- no CUDA call, also run by ddpca_mg_setup_dryrun) and the uploads (device must be current).
+struct SetupClock {   // seconds spent per stage of the hierarchy set-up (reported under DDPCA_VERBOSE and by the dry run)
+    double concat = 0, plan = 0, permute = 0, layout = 0, upload = 0, tr_permute = 0, tr_transpose = 0, tr_trip = 0, tr_upload = 0;
+};
+static thread_local SetupClock g_clock;
+struct LevelHost {
+    CsrHost Ap;   // operator in device numbering
+    GroupLayoutHost G;
+    Layout2Host H2;
+    bool group_layout = false;
+};
+static int setup_level_host(Level &L, const CsrBlocks &B, int mode, bool group_layout, const LevelPlan *given_plan, LevelHost &D,
+                            const std::vector<int> *whole_sub_off = nullptr)
 {
+    // whole_sub_off: B is ONE block holding an already concatenated batch whose subs start at these rows (cross-check path)
+    const int n = B.rows();
+    const std::vector<int> *sub_off = whole_sub_off ? whole_sub_off : (B.nsub > 1 ? &B.row_off : nullptr);
     L.n = n;
     std::string err;
+    double t0 = StageTimer::now();
     if (given_plan) L.plan = *given_plan;
-    else if (sub_off && sub_off->size() > 2) { if (!build_level_plan_blocks(n, rp, ci, mode, *sub_off, L.plan, err)) return fail(err); }
-    else if (!build_level_plan(n, rp, ci, mode, L.plan, err)) return fail(err);
-    CsrHost Ap;
-    permute_csr(n, n, rp, ci, v, L.plan.perm, L.plan.iperm, Ap);
+    else if (whole_sub_off) { if (!build_level_plan_blocks(n, B.rp[0], B.ci[0], mode, *whole_sub_off, L.plan, err)) return fail(err); }
+    else if (!build_level_plan_subs(B, mode, L.plan, err)) return fail(err);
+    double t1 = StageTimer::now();
+    g_clock.plan += t1 - t0;
+    CsrHost &Ap = D.Ap;
+    permute_csr_blocks(B, L.plan.perm, L.plan.iperm, Ap);
     L.nnz = Ap.nnz();
-    if (keep_csr) { if (upload_csr(Ap, L.A)) return 1; }
+    double t2 = StageTimer::now();
+    g_clock.permute += t2 - t1;
+    D.group_layout = group_layout;
     if (group_layout) {
-        GroupLayoutHost G;
+        GroupLayoutHost &G = D.G;
         if (!build_group_layout(Ap, L.plan, G, err)) return fail(err);
         if (mode >= 0) build_segments(L, G);
         // v2 (kernels2.cuh) when every stage is large enough to be worth a grid-wide pass
         bool want_v2 = mode >= 0 && !L.segs.empty() && !std::getenv("DDPCA_NO_V2");
         for (const Segment &sg : L.segs) if (sg.multi) want_v2 = false;
-        Layout2Host H2;
+        Layout2Host &H2 = D.H2;
         if (want_v2) {
             // subdomain of every row group (batched hierarchies: chunks are cut at subdomain boundaries)
             std::vector<int> group_sub;
@@ -995,23 +1025,37 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
         }
         if (L.v2) {
             // fwd -> bwd junction: the last colour has nothing above its groups (it is ordered last)
-            {
-                const int ns = L.plan.nstages();
-                bool none_above = ns >= 1 && !std::getenv("DDPCA_NO_FUSE_BWD");
-                for (int g = L.plan.stage_group[ns - 1]; none_above && g < L.plan.stage_group[ns]; g++) none_above = (H2.meta[g].nu == 0);
-                L.fuse_bwd_last = none_above ? 1 : 0;
-                if (none_above)
-                    for (int g = L.plan.stage_group[ns - 1]; g < L.plan.stage_group[ns]; g++) {
-                        const int gs = H2.meta[g].gs;
-                        L.bytes_bwd_skip += 32.0 + 8.0 * gs * gs + 32.0 * gs;
-                    }
-            }
+            const int ns = L.plan.nstages();
+            bool none_above = ns >= 1 && !std::getenv("DDPCA_NO_FUSE_BWD");
+            for (int g = L.plan.stage_group[ns - 1]; none_above && g < L.plan.stage_group[ns]; g++) none_above = (H2.meta[g].nu == 0);
+            L.fuse_bwd_last = none_above ? 1 : 0;
+            if (none_above)
+                for (int g = L.plan.stage_group[ns - 1]; g < L.plan.stage_group[ns]; g++) {
+                    const int gs = H2.meta[g].gs;
+                    L.bytes_bwd_skip += 32.0 + 8.0 * gs * gs + 32.0 * gs;
+                }
             for (int tab = 0; tab < 3; tab++) {
                 L.nchunks[tab] = (int)H2.chunks[tab].size();
                 L.max_stage_chunks[tab] = H2.max_stage_chunks[tab];
                 L.buf[tab] = H2.buf[tab];
-                if (upload_vec(H2.chunks[tab], &L.chunks[tab]) || upload_vec(H2.stage_chunk[tab], &L.stage_chunk[tab])) return 1;
             }
+        } else {
+            fill_group_arrays(Ap, G);
+        }
+    }
+    g_clock.layout += StageTimer::now() - t2;
+    return 0;
+}
+static int setup_level_upload(Level &L, const LevelHost &D, bool keep_csr)
+{
+    const double t0 = StageTimer::now();
+    const int n = L.n;
+    if (keep_csr) { if (upload_csr(D.Ap, L.A)) return 1; }
+    if (D.group_layout) {
+        if (L.v2) {
+            const Layout2Host &H2 = D.H2;
+            for (int tab = 0; tab < 3; tab++)
+                if (upload_vec(H2.chunks[tab], &L.chunks[tab]) || upload_vec(H2.stage_chunk[tab], &L.stage_chunk[tab])) return 1;
             CU(cudaMalloc(&L.empty_desc, sizeof(ChunkDesc)));
             CU(cudaMemset(L.empty_desc, 0, sizeof(ChunkDesc)));
             CU(cudaMalloc(&L.gbar, kGbarWords * sizeof(unsigned)));
@@ -1019,13 +1063,21 @@ static int setup_level(Level &L, int n, const int *rp, const int *ci, const doub
             if (upload_vec(H2.meta, &L.meta2) || upload_vec(H2.CL, &L.CL) || upload_vec(H2.CU, &L.CU) || upload_vec(H2.VL, &L.VL) ||
                 upload_vec(H2.VU, &L.VU) || upload_vec(H2.BD, &L.BD)) return 1;
         } else {
-            fill_group_arrays(Ap, G);
-            if (upload_vec(G.meta, &L.meta) || upload_vec(G.ci, &L.gci) || upload_vec(G.v, &L.gv)) return 1;
+            if (upload_vec(D.G.meta, &L.meta) || upload_vec(D.G.ci, &L.gci) || upload_vec(D.G.v, &L.gv)) return 1;
         }
     }
     if (upload_vec(L.plan.stage_group, &L.stage_group) || upload_vec(L.plan.perm, &L.perm)) return 1;
     if (alloc_vec(&L.x, n) || alloc_vec(&L.b, n) || alloc_vec(&L.p1, n) || alloc_vec(&L.r, n)) return 1;
+    g_clock.upload += StageTimer::now() - t0;
     return 0;
+}
+static int setup_level(Level &L, int n, const int *rp, const int *ci, const double *v, int mode, bool keep_csr, bool group_layout,
+                       const std::vector<int> *sub_off = nullptr, const LevelPlan *given_plan = nullptr)
+{
+    LevelHost D;
+    (void)sub_off;
+    if (setup_level_host(L, CsrBlocks::single(n, n, rp, ci, v), mode, group_layout, given_plan, D)) return 1;
+    return setup_level_upload(L, D, keep_csr);
 }
 static void free_trip(DevTrip &t)
 {
@@ -1078,16 +1130,32 @@ static int dense_invert_inplace(cudaStream_t st, int n, double *B)
     }
     double *Dinv = ws_buf[dev & 63], *C = Dinv + kGjB * kGjB, *R = C + (size_t)n * kGjB;
     const int nt = cdiv(n, kGjB);
+    // DDPCA_VERBOSE: device time per kernel class of this inversion (events around every launch)
+    const bool timed = std::getenv("DDPCA_VERBOSE") != nullptr && n >= 1024;
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() { if (timed) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); evs.push_back(e); } };
     for (int k0 = 0; k0 < n; k0 += kGjB) {
         const int nb = std::min(kGjB, n - k0);
+        mark();
         k_bgj_diag<<<1, 1024, 0, st>>>(n, k0, nb, B, Dinv);
+        mark();
         k_bgj_panels<<<nt, 256, smem, st>>>(n, k0, nb, B, Dinv, C, R);
+        mark();
         k_bgj_update<<<dim3(nt, nt), 256, smem, st>>>(n, k0, nb, B, Dinv, C, R);
     }
+    mark();
     dim3 g2(cdiv(n, 256), n);
     k_symmetrize<<<g2, 256, 0, st>>>(n, B);
     CUX(cudaStreamSynchronize(st));   // the workspace is free again when the lock is released
     CUX(cudaGetLastError());
+    if (timed) {
+        double t[3] = {0, 0, 0};
+        for (size_t k = 0; k + 1 < evs.size(); k++) { float ms = 0; cudaEventElapsedTime(&ms, evs[k], evs[k + 1]); t[k % 3] += ms; }
+        for (cudaEvent_t e : evs) cudaEventDestroy(e);
+        const double tot = t[0] + t[1] + t[2];
+        std::fprintf(stderr, "ddpca set-up [dense inverse] n %d: diagonal blocks %.2f ms, panels %.2f ms, updates %.2f ms (%.2f TFLOP/s over all)\n",
+                     n, t[0], t[1], t[2], tot > 0 ? 2.0 * n * (double)n * n / (tot * 1e9) : 0.0);
+    }
     return 0;
 }
 // Dense inverse of the diagonal block [r0, r0+n) of an SPD operator given as device CSR, written to Bblk (n x n)
@@ -1462,6 +1530,66 @@ static int concat_block_diag(int nsub, const int *r, const int *c, const int *co
     return 0;
 }
 
+// The caller's hierarchies as handed to ddpca_mg_create[_batch]: arrays indexed [s * nlevels + l] (prolongations [s * (nlevels-1) + l])
+struct HierInput {
+    int nsub, nlevels;
+    const int *n;
+    const int *const *rowptr, *const *colidx;
+    const double *const *val;
+    const int *const *P_rowptr, *const *P_colidx;
+    const double *const *P_val;
+};
+// host half of level l: the subs' operators as the blocks of one block-diagonal level (nothing is concatenated)
+static int level_host_pass(const HierInput &in, int l, int smoother_mode, const std::vector<std::vector<int>> &sub_off, Level &L, LevelHost &D)
+{
+    const int nsub = in.nsub, nlevels = in.nlevels;
+    const int mode = (l == 0) ? -1 : smoother_mode;   // level 0 is only ever solved directly
+    const bool coarse_only = (l == 0 && nlevels > 1);
+    CsrBlocks B;
+    B.nsub = nsub;
+    B.row_off = sub_off[l]; B.col_off = sub_off[l];
+    for (int s = 0; s < nsub; s++) { B.rp.push_back(in.rowptr[s * nlevels + l]); B.ci.push_back(in.colidx[s * nlevels + l]); B.v.push_back(in.val[s * nlevels + l]); }
+    if (B.nnz() > 0x7ffffff0L) return fail("batch too large for 32-bit indices: split it into several batches");
+    if (nsub > 1 && std::getenv("DDPCA_SETUP_CONCAT")) {   // cross-check: plan and permute the explicitly concatenated level
+        CsrHost cat;
+        std::vector<int> rs(nsub);
+        for (int s = 0; s < nsub; s++) rs[s] = in.n[s * nlevels + l];
+        const double ta = StageTimer::now();
+        if (concat_block_diag(nsub, rs.data(), rs.data(), B.rp.data(), B.ci.data(), B.v.data(), cat)) return 1;
+        g_clock.concat += StageTimer::now() - ta;
+        return setup_level_host(L, CsrBlocks::single(cat.rows, cat.cols, cat.rp.data(), cat.ci.data(), cat.v.data()), mode, !coarse_only, nullptr, D, &sub_off[l]);
+    }
+    return setup_level_host(L, B, mode, /*group_layout=*/!coarse_only, nullptr, D);
+}
+// host half of the transfer pair of level l >= 1: realProl[l-1] (n_l x n_{l-1}) with rows in level l's numbering and
+// columns in level l-1's, its transpose, and the node-triple forms of both
+struct TransferHost { CsrHost Pp, Rp; TripHost Pt, Rt; };
+static int transfer_host_pass(const HierInput &in, int l, const std::vector<std::vector<int>> &sub_off, const LevelPlan &fine, const LevelPlan &coarse, TransferHost &T)
+{
+    const int nsub = in.nsub, nlevels = in.nlevels;
+    const double t1 = StageTimer::now();
+    CsrBlocks B;
+    B.nsub = nsub;
+    B.row_off = sub_off[l]; B.col_off = sub_off[l - 1];
+    for (int s = 0; s < nsub; s++) {
+        B.rp.push_back(in.P_rowptr[s * (nlevels - 1) + l - 1]); B.ci.push_back(in.P_colidx[s * (nlevels - 1) + l - 1]); B.v.push_back(in.P_val[s * (nlevels - 1) + l - 1]);
+    }
+    if (B.nnz() > 0x7ffffff0L) return fail("batch too large for 32-bit indices: split it into several batches");
+    permute_csr_blocks(B, fine.perm, coarse.iperm, T.Pp);
+    // the reference stores realProl with explicit zeros (a 3x3 block per node pair, diagonal only
+    // non-zero unless the nodes carry rotations): x + 0 * y == x, so they are dropped
+    drop_zeros_csr(T.Pp);
+    const double t2 = StageTimer::now();
+    g_clock.tr_permute += t2 - t1;
+    transpose_csr(T.Pp, T.Rp);
+    const double t3 = StageTimer::now();
+    g_clock.tr_transpose += t3 - t2;
+    build_trip_host(T.Pp, T.Pt);
+    build_trip_host(T.Rp, T.Rt);
+    g_clock.tr_trip += StageTimer::now() - t3;
+    return 0;
+}
+
 // nsub hierarchies of `nlevels` levels each; every array is indexed [s * nlevels + l] (prolongations [s * (nlevels-1) + l])
 static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const int *const *rowptr, const int *const *colidx,
                           const double *const *val, const int *const *P_rowptr, const int *const *P_colidx,
@@ -1494,60 +1622,34 @@ static int mg_create_impl(int device, int nsub, int nlevels, const int *n, const
         h->sub_off[l][nsub] = (int)acc;
     }
     StageTimer tm("hierarchy");
-    double t_cat = 0, t_lvl = 0, t_p = 0;
+    g_clock = SetupClock();
     int nmax = 0;
-    std::vector<int> rs(nsub), cs(nsub);
-    std::vector<const int *> prp(nsub), pci(nsub);
-    std::vector<const double *> pv(nsub);
+    HierInput in{nsub, nlevels, n, rowptr, colidx, val, P_rowptr, P_colidx, P_val};
     for (int l = 0; l < nlevels; l++) {
         Level &L = h->lev[l];
-        const int ntot = h->sub_off[l][nsub];
-        nmax = std::max(nmax, ntot);
-        int mode = (l == 0) ? -1 : smoother_mode;   // level 0 is only ever solved directly
-        bool coarse_only = (l == 0 && nlevels > 1);
-        CsrHost cat;
-        const int *rp = rowptr[l], *ci = colidx[l];
-        const double *vv = val[l];
-        double ta = StageTimer::now();
-        if (nsub > 1) {
-            for (int s = 0; s < nsub; s++) { rs[s] = n[s * nlevels + l]; prp[s] = rowptr[s * nlevels + l]; pci[s] = colidx[s * nlevels + l]; pv[s] = val[s * nlevels + l]; }
-            FAILC(concat_block_diag(nsub, rs.data(), rs.data(), prp.data(), pci.data(), pv.data(), cat));
-            rp = cat.rp.data(); ci = cat.ci.data(); vv = cat.v.data();
-        }
-        double tb = StageTimer::now();
-        t_cat += tb - ta;
-        if (setup_level(L, ntot, rp, ci, vv, mode, /*keep_csr=*/l == 0 && !no_direct, /*group_layout=*/!coarse_only, &h->sub_off[l])) {
+        nmax = std::max(nmax, h->sub_off[l][nsub]);
+        LevelHost D;
+        if (level_host_pass(in, l, smoother_mode, h->sub_off, L, D)) {
             g_err = "level " + std::to_string(l) + ": " + g_err;
             ddpca_mg_destroy(h);
             return 1;
         }
-        double tc = StageTimer::now();
-        t_lvl += tc - tb;
+        FAILC(setup_level_upload(L, D, /*keep_csr=*/l == 0 && !no_direct));
         if (l >= 1) {
-            CsrHost Pcat, Pp, Rp;
-            const int *prp0 = P_rowptr[l - 1], *pci0 = P_colidx[l - 1];
-            const double *pv0 = P_val[l - 1];
-            if (nsub > 1) {
-                for (int s = 0; s < nsub; s++) {
-                    rs[s] = n[s * nlevels + l]; cs[s] = n[s * nlevels + l - 1];
-                    prp[s] = P_rowptr[s * (nlevels - 1) + l - 1]; pci[s] = P_colidx[s * (nlevels - 1) + l - 1]; pv[s] = P_val[s * (nlevels - 1) + l - 1];
-                }
-                FAILC(concat_block_diag(nsub, rs.data(), cs.data(), prp.data(), pci.data(), pv.data(), Pcat));
-                prp0 = Pcat.rp.data(); pci0 = Pcat.ci.data(); pv0 = Pcat.v.data();
-            }
-            // realProl[l-1]: n_l x n_{l-1}; rows follow level l's permutation, columns level l-1's
-            permute_csr(ntot, h->sub_off[l - 1][nsub], prp0, pci0, pv0, L.plan.perm, h->lev[l - 1].plan.iperm, Pp);
-            // the reference stores realProl with explicit zeros (a 3x3 block per node pair, diagonal only
-            // non-zero unless the nodes carry rotations): x + 0 * y == x, so they are dropped
-            drop_zeros_csr(Pp);
-            transpose_csr(Pp, Rp);
-            FAILC(upload_csr(Pp, L.P));
-            FAILC(upload_csr(Rp, L.R));
-            FAILC(build_trip(Pp, L.Pt) || build_trip(Rp, L.Rt));
-            t_p += StageTimer::now() - tc;
+            TransferHost T;
+            FAILC(transfer_host_pass(in, l, h->sub_off, L.plan, h->lev[l - 1].plan, T));
+            const double tu = StageTimer::now();
+            FAILC(upload_csr(T.Pp, L.P));
+            FAILC(upload_csr(T.Rp, L.R));
+            FAILC(upload_trip(T.Pp, T.Pt, L.Pt) || upload_trip(T.Rp, T.Rt, L.Rt));
+            g_clock.tr_upload += StageTimer::now() - tu;
         }
     }
-    if (tm.on) std::fprintf(stderr, "ddpca set-up [hierarchy] %d subs, %d levels, %d rows: concatenate %.3f s, plan+layout+upload %.3f s, transfers %.3f s\n", nsub, nlevels, nmax, t_cat, t_lvl, t_p);
+    if (tm.on) {
+        const SetupClock &c = g_clock;
+        std::fprintf(stderr, "ddpca set-up [hierarchy] %d subs, %d levels, %d rows: concatenate %.3f, plan %.3f, permute %.3f, layout %.3f, upload %.3f | transfers: permute %.3f, transpose %.3f, triples %.3f, upload %.3f s\n",
+                     nsub, nlevels, nmax, c.concat, c.plan, c.permute, c.layout, c.upload, c.tr_permute, c.tr_transpose, c.tr_trip, c.tr_upload);
+    }
     tm.lap("levels");
     FAILC(alloc_vec(&h->cg_r, nmax) || alloc_vec(&h->cg_p, nmax) || alloc_vec(&h->cg_q, nmax) || alloc_vec(&h->cg_z, nmax) ||
           alloc_vec(&h->cg_x, nmax) || alloc_vec(&h->stage_a, nmax) || alloc_vec(&h->stage_b, nmax));
@@ -1634,6 +1736,72 @@ int ddpca_mg_create_batch(int device, int nsub, int nlevels, const int *n, const
                           const double *const *P_val, int smoother_mode, ddpca_mg **out)
 {
     return mg_create_impl(device, nsub, nlevels, n, rowptr, colidx, val, P_rowptr, P_colidx, P_val, smoother_mode, out);
+}
+
+// The host half of ddpca_mg_create_batch without a device: plans, permuted operators, layouts, chunk tables and
+// transfer forms are built exactly as for a real handle and dropped.  Reports what would be uploaded and where the
+// host time goes; seconds[9] = concatenate, plan, permute, layout, (upload: 0), transfers: permute+drop, transpose,
+// triples, (upload: 0).
+int ddpca_mg_setup_dryrun(int nsub, int nlevels, const int *n, const int *const *rowptr, const int *const *colidx,
+                          const double *const *val, const int *const *P_rowptr, const int *const *P_colidx,
+                          const double *const *P_val, int smoother_mode, double *seconds, long *device_bytes, int *v2_levels,
+                          unsigned long long *checksum)
+{
+    if (nsub < 1 || nlevels < 1 || nlevels > 16 || !n || !rowptr || !colidx || !val) return fail("ddpca_mg_setup_dryrun: bad argument");
+    if (smoother_mode != DDPCA_SMOOTH_LEX && smoother_mode != DDPCA_SMOOTH_MC) return fail("unknown smoother mode");
+    if (nlevels > 1 && (!P_rowptr || !P_colidx || !P_val)) return fail("prolongation operators missing");
+    std::vector<std::vector<int>> sub_off(nlevels, std::vector<int>(nsub + 1, 0));
+    for (int l = 0; l < nlevels; l++) {
+        long acc = 0;
+        for (int s = 0; s < nsub; s++) { sub_off[l][s] = (int)acc; acc += n[s * nlevels + l]; }
+        if (acc > 0x7ffffff0L) return fail("batch too large for 32-bit indices: split it into several batches");
+        sub_off[l][nsub] = (int)acc;
+    }
+    g_clock = SetupClock();
+    HierInput in{nsub, nlevels, n, rowptr, colidx, val, P_rowptr, P_colidx, P_val};
+    std::vector<Level> lev(nlevels);
+    long bytes = 0;
+    int nv2 = 0;
+    unsigned long long hash = 1469598103934665603ULL;   // FNV-1a over everything that would be uploaded, 8 bytes at a time
+    auto vb = [&](const auto &v) {
+        const size_t nb = v.size() * sizeof(v[0]);
+        if (checksum) {
+            const unsigned char *p = reinterpret_cast<const unsigned char *>(v.data());
+            size_t k = 0;
+            for (; k + 8 <= nb; k += 8) { unsigned long long w; std::memcpy(&w, p + k, 8); hash = (hash ^ w) * 1099511628211ULL; }
+            for (; k < nb; k++) hash = (hash ^ p[k]) * 1099511628211ULL;
+        }
+        return (long)nb;
+    };
+    for (int l = 0; l < nlevels; l++) {
+        LevelHost D;
+        if (level_host_pass(in, l, smoother_mode, sub_off, lev[l], D)) { g_err = "level " + std::to_string(l) + ": " + g_err; return 1; }
+        if (D.group_layout) {
+            if (lev[l].v2) {
+                nv2++;
+                bytes += vb(D.H2.meta) + vb(D.H2.CL) + vb(D.H2.CU) + vb(D.H2.VL) + vb(D.H2.VU) + vb(D.H2.BD);
+                for (int tab = 0; tab < 3; tab++) bytes += vb(D.H2.chunks[tab]) + vb(D.H2.stage_chunk[tab]);
+            } else bytes += vb(D.G.meta) + vb(D.G.ci) + vb(D.G.v);
+        } else bytes += vb(D.Ap.rp) + vb(D.Ap.ci) + vb(D.Ap.v);
+        bytes += vb(lev[l].plan.perm) + vb(lev[l].plan.stage_group);
+        bytes += 4L * 8 * (lev[l].n + 1);
+        if (l >= 1) {
+            TransferHost T;
+            if (transfer_host_pass(in, l, sub_off, lev[l].plan, lev[l - 1].plan, T)) return 1;
+            bytes += vb(T.Pp.rp) + vb(T.Pp.ci) + vb(T.Pp.v) + vb(T.Rp.rp) + vb(T.Rp.ci) + vb(T.Rp.v);
+            for (const TripHost *t : {&T.Pt, &T.Rt})
+                if (t->ok) bytes += vb(t->trow) + vb(t->tptr) + vb(t->tcol) + vb(t->tw) + vb(t->rest_row) + vb(t->R.ci) + vb(t->R.v);
+        }
+    }
+    if (checksum) *checksum = hash;
+    if (seconds) {
+        const SetupClock &c = g_clock;
+        const double t[9] = {c.concat, c.plan, c.permute, c.layout, 0.0, c.tr_permute, c.tr_transpose, c.tr_trip, 0.0};
+        for (int k = 0; k < 9; k++) seconds[k] = t[k];
+    }
+    if (device_bytes) *device_bytes = bytes;
+    if (v2_levels) *v2_levels = nv2;
+    return 0;
 }
 
 int ddpca_mg_batch_result(const ddpca_mg *h, int *nsub, long *iters, double *resid, double *tol_abs)

@@ -153,25 +153,9 @@ bool build_level_plan(int n, const int *rp, const int *ci, int mode, LevelPlan &
 // stage s of the level is stage s of every block, block after block.  This is exactly the plan of the whole level
 // (the greedy colouring / the wavefronts of a block-diagonal pattern do not see the other blocks, and groups keep
 // their original order inside a stage), obtained nsub times faster.
-bool build_level_plan_blocks(int n, const int *rp, const int *ci, int mode, const std::vector<int> &sub_off, LevelPlan &out, std::string &err)
+static bool merge_sub_plans(int n, const std::vector<int> &sub_off, const std::vector<LevelPlan> &part, LevelPlan &out)
 {
-    const int nsub = (int)sub_off.size() - 1;
-    if (mode < 0 || nsub <= 1) return build_level_plan(n, rp, ci, mode, out, err);
-    std::vector<LevelPlan> part(nsub);
-    std::vector<std::string> errs(nsub);
-    std::vector<char> ok(nsub, 1);
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int s = 0; s < nsub; s++) {
-        const int r0 = sub_off[s], nr = sub_off[s + 1] - r0;
-        const int p0 = rp[r0];
-        std::vector<int> lrp(nr + 1), lci((size_t)(rp[r0 + nr] - p0));
-        for (int i = 0; i <= nr; i++) lrp[i] = rp[r0 + i] - p0;
-        bool inside = true;
-        for (size_t p = 0; p < lci.size(); p++) { lci[p] = ci[p0 + p] - r0; inside = inside && lci[p] >= 0 && lci[p] < nr; }
-        if (!inside) { ok[s] = 0; errs[s] = "subdomain " + std::to_string(s) + ": the level is not block diagonal"; continue; }
-        if (!build_level_plan(nr, lrp.data(), lci.data(), mode, part[s], errs[s])) ok[s] = 0;
-    }
-    for (int s = 0; s < nsub; s++) if (!ok[s]) { err = "subdomain " + std::to_string(s) + ": " + errs[s]; return false; }
+    const int nsub = (int)part.size();
     int nstages = 0;
     long ng = 0;
     for (const LevelPlan &p : part) { nstages = std::max(nstages, p.nstages()); ng += p.ngroups(); }
@@ -204,6 +188,53 @@ bool build_level_plan_blocks(int n, const int *rp, const int *ci, int mode, cons
     return true;
 }
 
+bool build_level_plan_blocks(int n, const int *rp, const int *ci, int mode, const std::vector<int> &sub_off, LevelPlan &out, std::string &err)
+{
+    const int nsub = (int)sub_off.size() - 1;
+    if (mode < 0 || nsub <= 1) return build_level_plan(n, rp, ci, mode, out, err);
+    std::vector<LevelPlan> part(nsub);
+    std::vector<std::string> errs(nsub);
+    std::vector<char> ok(nsub, 1);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int s = 0; s < nsub; s++) {
+        const int r0 = sub_off[s], nr = sub_off[s + 1] - r0;
+        const int p0 = rp[r0];
+        std::vector<int> lrp(nr + 1), lci((size_t)(rp[r0 + nr] - p0));
+        for (int i = 0; i <= nr; i++) lrp[i] = rp[r0 + i] - p0;
+        bool inside = true;
+        for (size_t p = 0; p < lci.size(); p++) { lci[p] = ci[p0 + p] - r0; inside = inside && lci[p] >= 0 && lci[p] < nr; }
+        if (!inside) { ok[s] = 0; errs[s] = "subdomain " + std::to_string(s) + ": the level is not block diagonal"; continue; }
+        if (!build_level_plan(nr, lrp.data(), lci.data(), mode, part[s], errs[s])) ok[s] = 0;
+    }
+    for (int s = 0; s < nsub; s++) if (!ok[s]) { err = "subdomain " + std::to_string(s) + ": " + errs[s]; return false; }
+    return merge_sub_plans(n, sub_off, part, out);
+}
+
+bool build_level_plan_subs(const CsrBlocks &B, int mode, LevelPlan &out, std::string &err)
+{
+    const int nsub = B.nsub, n = B.rows();
+    if (nsub == 1) return build_level_plan(n, B.rp[0], B.ci[0], mode, out, err);
+    if (mode < 0) {   // identity plan of the whole level: one stage, single-row groups (level 0)
+        out = LevelPlan();
+        out.n = n;
+        out.perm.resize(n); out.iperm.resize(n); out.group_start.resize(n + 1);
+        for (int i = 0; i < n; i++) out.perm[i] = out.iperm[i] = out.group_start[i] = i;
+        out.group_start[n] = n;
+        out.stage_group = {0, n};
+        return true;
+    }
+    std::vector<LevelPlan> part(nsub);
+    std::vector<std::string> errs(nsub);
+    std::vector<char> ok(nsub, 1);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int s = 0; s < nsub; s++) {
+        const int nr = B.row_off[s + 1] - B.row_off[s];
+        if (!build_level_plan(nr, B.rp[s], B.ci[s], mode, part[s], errs[s])) ok[s] = 0;
+    }
+    for (int s = 0; s < nsub; s++) if (!ok[s]) { err = "subdomain " + std::to_string(s) + ": " + errs[s]; return false; }
+    return merge_sub_plans(n, B.row_off, part, out);
+}
+
 // Wavefront plan of a unit triangular factor I + L (and of I + L^T, which has the same one): single-row groups,
 // stage[i] = 1 + max stage[j] over the strictly-lower couplings j of row i.  This is what build_level_plan(LEX)
 // returns for these operators, without building and symmetrising a 2 x nnz edge list.
@@ -230,31 +261,49 @@ void build_tri_plan(int n, const int *Lrp, const int *Lci, LevelPlan &out)
     std::iota(out.group_start.begin(), out.group_start.end(), 0);
 }
 
-void permute_csr(int rows, int cols, const int *rp, const int *ci, const double *v,
-                 const std::vector<int> &prow, const std::vector<int> &icol, CsrHost &out)
+void permute_csr_blocks(const CsrBlocks &B, const std::vector<int> &prow, const std::vector<int> &icol, CsrHost &out)
 {
-    (void)cols;
+    const int rows = B.rows(), nsub = B.nsub;
     out.rows = rows;
     out.cols = (int)icol.size();
     out.rp.assign(rows + 1, 0);
-    for (int i = 0; i < rows; i++) out.rp[i + 1] = out.rp[i] + (rp[prow[i] + 1] - rp[prow[i]]);
-    long nnz = out.rp[rows];
+    // block of every output row (prow[i] = row of the whole operator)
+    auto sub_of = [&](int old) { return nsub == 1 ? 0 : (int)(std::upper_bound(B.row_off.begin(), B.row_off.end(), old) - B.row_off.begin()) - 1; };
+    for (int i = 0; i < rows; i++) {
+        const int old = prow[i], s = sub_of(old), lr = old - B.row_off[s];
+        out.rp[i + 1] = out.rp[i] + (B.rp[s][lr + 1] - B.rp[s][lr]);
+    }
+    const long nnz = out.rp[rows];
     out.ci.resize(nnz);
     out.v.resize(nnz);
 #pragma omp parallel
     {
-        std::vector<std::pair<int, double>> tmp;
+        // keys = (new column << 32 | position in the row): one integer sort per row, the values follow by position
+        std::vector<unsigned long long> key;
 #pragma omp for schedule(dynamic, 1024)
         for (int i = 0; i < rows; i++) {
-            int o = prow[i];
-            int len = rp[o + 1] - rp[o];
-            tmp.resize(len);
-            for (int k = 0; k < len; k++) tmp[k] = {icol[ci[rp[o] + k]], v[rp[o] + k]};
-            std::sort(tmp.begin(), tmp.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; });
-            int base = out.rp[i];
-            for (int k = 0; k < len; k++) { out.ci[base + k] = tmp[k].first; out.v[base + k] = tmp[k].second; }
+            const int old = prow[i], s = sub_of(old), lr = old - B.row_off[s];
+            const int p0 = B.rp[s][lr], len = B.rp[s][lr + 1] - p0;
+            const int *cs = B.ci[s] + p0;
+            const double *vs = B.v[s] + p0;
+            const int coff = B.col_off[s];
+            key.resize(len);
+            bool sorted = true;
+            for (int k = 0; k < len; k++) {
+                key[k] = ((unsigned long long)(unsigned)icol[cs[k] + coff] << 32) | (unsigned)k;
+                sorted = sorted && (k == 0 || key[k - 1] < key[k]);
+            }
+            if (!sorted) std::sort(key.begin(), key.end());
+            const int base = out.rp[i];
+            for (int k = 0; k < len; k++) { out.ci[base + k] = (int)(key[k] >> 32); out.v[base + k] = vs[(unsigned)key[k]]; }
         }
     }
+}
+
+void permute_csr(int rows, int cols, const int *rp, const int *ci, const double *v,
+                 const std::vector<int> &prow, const std::vector<int> &icol, CsrHost &out)
+{
+    permute_csr_blocks(CsrBlocks::single(rows, cols, rp, ci, v), prow, icol, out);
 }
 
 void transpose_csr(const CsrHost &A, CsrHost &out)

@@ -21,7 +21,7 @@ def library_path() -> str:
 EXPORTS = [
     "ddpca_last_error", "ddpca_abi_version", "ddpca_device_count",
     "ddpca_plan_create", "ddpca_plan_create_blocks", "ddpca_plan_create_tri", "ddpca_plan_sizes", "ddpca_plan_get", "ddpca_plan_destroy",
-    "ddpca_mg_create", "ddpca_mg_create_batch", "ddpca_mg_batch_result", "ddpca_mg_destroy", "ddpca_mg_pcg", "ddpca_mg_pcg_dev",
+    "ddpca_mg_create", "ddpca_mg_create_batch", "ddpca_mg_setup_dryrun", "ddpca_mg_batch_result", "ddpca_mg_destroy", "ddpca_mg_pcg", "ddpca_mg_pcg_dev",
     "ddpca_mg_vcycle", "ddpca_mg_spmv", "ddpca_mg_restrict", "ddpca_mg_prolong_add",
     "ddpca_mg_coarse_solve", "ddpca_mg_mult_solv", "ddpca_mg_bicgstab", "ddpca_mg_gmres",
     "ddpca_mg_level_info", "ddpca_mg_launch_count", "ddpca_mg_set_stream",

@@ -68,6 +68,20 @@ def hierarchy_pointers(hiers):
             ipp2(*[_pi(p.rowptr) for p in Ps]), ipp2(*[_pi(p.colidx) for p in Ps]), dpp2(*[_pd(p.val) for p in Ps]))
 
 
+def setup_dryrun(hiers, smoother: int = SMOOTH_MC):
+    """ddpca_mg_setup_dryrun: the host half of the batched hierarchy set-up for [(A, P), ...] without a device.
+    Returns {"seconds": {stage: s}, "device_bytes": int, "v2_levels": int, "checksum": int}."""
+    nlev = len(hiers[0][0])
+    ptrs = hierarchy_pointers(hiers)
+    sec = (C.c_double * 9)()
+    nbytes, nv2, cs = C.c_long(), C.c_int(), C.c_ulonglong()
+    check(load_library().ddpca_mg_setup_dryrun(C.c_int(len(hiers)), C.c_int(nlev), *ptrs, C.c_int(smoother), sec,
+                                               C.byref(nbytes), C.byref(nv2), C.byref(cs)))
+    names = ["concatenate", "plan", "permute", "layout", "upload", "transfer_permute", "transfer_transpose", "transfer_triples",
+             "transfer_upload"]
+    return {"seconds": dict(zip(names, list(sec))), "device_bytes": nbytes.value, "v2_levels": nv2.value, "checksum": cs.value}
+
+
 class MGPIS:
     """Multigrid-preconditioned iterative solver on a B200.
 

@@ -96,6 +96,17 @@ int ddpca_mg_create_batch(int device, int nsub, int nlevels, const int *n,
                           const int *const *rowptr, const int *const *colidx, const double *const *val,
                           const int *const *P_rowptr, const int *const *P_colidx, const double *const *P_val,
                           int smoother_mode, ddpca_mg **out);
+/* The host half of ddpca_mg_create_batch without touching a device (no GPU needed): the sweep plans, the
+ * permuted operators, the kernel layouts, chunk tables and transfer forms are built exactly as for a real
+ * handle and dropped.  A planning / diagnostic aid: device_bytes = what the hierarchy would occupy in HBM,
+ * v2_levels = levels that qualify for the TMA-staged layout, seconds[9] = host time per set-up stage
+ * (concatenate, plan, permute, layout, 0, transfers: permute, transpose, triples, 0), checksum = a hash
+ * of every array that would be uploaded (regression anchor for the host code).  Outputs may be NULL. */
+int ddpca_mg_setup_dryrun(int nsub, int nlevels, const int *n,
+                          const int *const *rowptr, const int *const *colidx, const double *const *val,
+                          const int *const *P_rowptr, const int *const *P_colidx, const double *const *P_val,
+                          int smoother_mode, double *seconds, long *device_bytes, int *v2_levels,
+                          unsigned long long *checksum);
 /* per-subdomain results of the last ddpca_mg_pcg* call: iters[nsub], resid[nsub], tol_abs[nsub] (any may be null) */
 int ddpca_mg_batch_result(const ddpca_mg *, int *nsub, long *iters, double *resid, double *tol_abs);
 int ddpca_mg_destroy(ddpca_mg *);

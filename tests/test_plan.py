@@ -119,3 +119,43 @@ def test_triangular_factor_plan_equals_lex_plan_of_both_factors():
         ref = dd.Plan(ddpk.Csr.from_scipy(T), dd.SMOOTH_LEX)
         assert ref.ngroups == n * n == tri.ngroups and ref.nstages == tri.nstages
         assert np.array_equal(ref.perm, tri.perm) and np.array_equal(ref.stage_start, tri.stage_start)
+
+
+def test_host_half_of_the_hierarchy_set_up_runs_without_a_device():
+    """ddpca_mg_setup_dryrun: plans, permuted operators, kernel layouts, chunk tables and transfer forms of a batch of
+    hierarchies are built on the host exactly as ddpca_mg_create_batch does before its uploads.  Multicolour levels above
+    level 0 qualify for the TMA-staged layout, the lexicographic wavefronts of this small mesh do not (stages too
+    small); the HBM footprint of a batch is the sum over its members."""
+    d, meta, A, P = load_golden("beam_3lev")
+    one = dd.setup_dryrun([(A, P)])
+    three = dd.setup_dryrun([(A, P)] * 3)
+    # (a batch has larger colours: its level 1 reaches the grid-wide passes, one hierarchy alone stays on the v1 kernels there)
+    assert 1 <= one["v2_levels"] <= three["v2_levels"] == 2
+    nnz = sum(a.val.size for a in A[1:])
+    assert 8 * nnz < one["device_bytes"] < 40 * nnz
+    assert abs(three["device_bytes"] - 3 * one["device_bytes"]) < 0.1 * three["device_bytes"]
+    lex = dd.setup_dryrun([(A, P)], dd.SMOOTH_LEX)
+    assert lex["v2_levels"] == 0
+    assert set(one["seconds"]) >= {"plan", "permute", "layout", "transfer_permute"}
+    with pytest.raises(dd.DdpcaError):
+        dd.setup_dryrun([(A, P)], smoother=7)
+
+
+def test_block_wise_set_up_equals_the_concatenated_one(monkeypatch):
+    """A batch is planned and permuted straight from its members' arrays (no block-diagonal copy of the operators);
+    DDPCA_SETUP_CONCAT=1 selects the explicit concatenation the first implementation used.  Every array that would be
+    uploaded must be identical (hash over plans, layouts, chunk tables, transfer operators)."""
+    d, meta, A, P = load_golden("beam_3lev")
+    d2, meta2, A2, P2 = load_golden("beam_2lev")
+    for mode in (dd.SMOOTH_MC, dd.SMOOTH_LEX):
+        monkeypatch.delenv("DDPCA_SETUP_CONCAT", raising=False)
+        direct = dd.setup_dryrun([(A, P), (A, P), (A, P)], mode)
+        monkeypatch.setenv("DDPCA_SETUP_CONCAT", "1")
+        concat = dd.setup_dryrun([(A, P), (A, P), (A, P)], mode)
+        assert direct["checksum"] == concat["checksum"] and direct["device_bytes"] == concat["device_bytes"]
+    # members of different size
+    hs = [(A[1:], P[1:]), (A2, P2)] if len(A) - 1 == len(A2) else [(A, P), (A, P)]
+    monkeypatch.delenv("DDPCA_SETUP_CONCAT", raising=False)
+    direct = dd.setup_dryrun(hs)
+    monkeypatch.setenv("DDPCA_SETUP_CONCAT", "1")
+    assert dd.setup_dryrun(hs)["checksum"] == direct["checksum"]
