@@ -254,12 +254,16 @@ static int stack_blocks(int rows, int cols, const std::vector<OpBlock> &blocks, 
     std::vector<long> cnt(rows + 1, 0);
     std::vector<CsrHost> tr(blocks.size());
     std::vector<const CsrHost *> src(blocks.size());
+    // first entry of block k in every row it touches: blocks keep their order inside a row, the fill below is then
+    // independent per (block, row)
+    std::vector<std::vector<long>> first(blocks.size());
     for (size_t k = 0; k < blocks.size(); k++) {
         const OpBlock &b = blocks[k];
         if (b.transpose) { transpose_csr(*b.A, tr[k]); src[k] = &tr[k]; } else src[k] = b.A;
         const CsrHost &A = *src[k];
         if (b.row_off < 0 || b.col_off < 0 || b.row_off + A.rows > rows || b.col_off + A.cols > cols) return fail("stack_blocks: block outside the stacked operator");
-        for (int i = 0; i < A.rows; i++) cnt[b.row_off + i + 1] += A.rp[i + 1] - A.rp[i];
+        first[k].resize(A.rows);
+        for (int i = 0; i < A.rows; i++) { first[k][i] = cnt[b.row_off + i + 1]; cnt[b.row_off + i + 1] += A.rp[i + 1] - A.rp[i]; }
     }
     for (int i = 0; i < rows; i++) cnt[i + 1] += cnt[i];
     if (cnt[rows] > 0x7ffffff0L) return fail("stacked interface operator too large for 32-bit indices");
@@ -267,16 +271,18 @@ static int stack_blocks(int rows, int cols, const std::vector<OpBlock> &blocks, 
     for (int i = 0; i <= rows; i++) out.rp[i] = (int)cnt[i];
     out.ci.resize(cnt[rows]);
     out.v.resize(cnt[rows]);
-    std::vector<int> fill(out.rp.begin(), out.rp.end() - 1);
     for (size_t k = 0; k < blocks.size(); k++) {
         const OpBlock &b = blocks[k];
         const CsrHost &A = *src[k];
-        for (int i = 0; i < A.rows; i++)
-            for (int p = A.rp[i]; p < A.rp[i + 1]; p++) {
-                const int q = fill[b.row_off + i]++;
+        const std::vector<long> &f = first[k];
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < A.rows; i++) {
+            long q = cnt[b.row_off + i] + f[i];
+            for (int p = A.rp[i]; p < A.rp[i + 1]; p++, q++) {
                 out.ci[q] = A.ci[p] + b.col_off;
                 out.v[q] = b.scale * A.v[p];
             }
+        }
     }
     return 0;
 }

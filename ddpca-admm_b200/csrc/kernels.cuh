@@ -665,27 +665,39 @@ constexpr int kGjB = 64;
 // (a) Dinv = A[K,K]^-1, one CTA, scalar Gauss-Jordan in shared memory
 __global__ void __launch_bounds__(1024) k_bgj_diag(int n, int k0, int nb, const double *__restrict__ A, double *__restrict__ Dinv)
 {
-    __shared__ double d[kGjB][kGjB + 1];
-    __shared__ double rowk[kGjB], colk[kGjB];
-    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) d[e / nb][e % nb] = A[(size_t)(k0 + e / nb) * n + k0 + e % nb];
+    // The 64 x 64 block lives in registers (4 entries per thread: rows ib + 16 m of column j); a step needs the pivot
+    // row, the pivot column and the reciprocal pivot, which the owners of row / column k+1 publish while they apply
+    // step k -- double-buffered, ONE barrier per step (three barriers and a round trip through shared memory per
+    // step made this kernel half of the inversion time of small interface matrices).  A partial last block is
+    // padded with the identity.
+    __shared__ double rowb[2][kGjB], colb[2][kGjB], pivb[2];
+    const int j = threadIdx.x & (kGjB - 1), ib = threadIdx.x >> 6;
+    double v[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int i = ib + 16 * m;
+        v[m] = (i < nb && j < nb) ? A[(size_t)(k0 + i) * n + k0 + j] : (i == j ? 1.0 : 0.0);
+        if (i == 0) rowb[0][j] = v[m];
+        if (j == 0) { colb[0][i] = v[m]; if (i == 0) pivb[0] = 1.0 / v[m]; }
+    }
     __syncthreads();
     for (int k = 0; k < nb; k++) {
-        if ((int)threadIdx.x < nb) {
-            const double piv = 1.0 / d[k][k];
-            rowk[threadIdx.x] = ((int)threadIdx.x == k) ? piv : d[k][threadIdx.x] * piv;
-            colk[threadIdx.x] = d[threadIdx.x][k];
-        }
-        __syncthreads();
-        const double piv = rowk[k];
-        for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
-            const int i = e / nb, j = e % nb;
-            if (i == k) d[i][j] = rowk[j];
-            else if (j == k) d[i][j] = -colk[i] * piv;
-            else d[i][j] -= colk[i] * rowk[j];
+        const int cur = k & 1, nxt = cur ^ 1;
+        const double piv = pivb[cur];
+        const double rj = (j == k) ? piv : rowb[cur][j] * piv;
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const int i = ib + 16 * m;
+            const double c = colb[cur][i];
+            const double nv = (i == k) ? rj : ((j == k) ? -c * piv : v[m] - c * rj);
+            v[m] = nv;
+            if (i == k + 1) rowb[nxt][j] = nv;
+            if (j == k + 1) { colb[nxt][i] = nv; if (i == k + 1) pivb[nxt] = 1.0 / nv; }
         }
         __syncthreads();
     }
-    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) Dinv[(e / nb) * kGjB + e % nb] = d[e / nb][e % nb];
+#pragma unroll
+    for (int m = 0; m < 4; m++) Dinv[(ib + 16 * m) * kGjB + j] = v[m];
 }
 // 64x64 (x64) tile product helper: acc[4][4] of thread (ty, tx) in a 16x16 thread block:
 // rows ty*4 + r, columns tx + 16*c of  As (64 x kk, row-major in shared) times Bs (kk x 64).  The strided column

@@ -1165,13 +1165,6 @@ static int dense_spd_inverse_block(cudaStream_t st, const DevCsr &A, int r0, int
     k_csr_to_dense<<<cdiv(n, 128), 128, 0, st>>>(A.view(), r0, n, Bblk);
     return dense_invert_inplace(st, n, Bblk);
 }
-static int dense_spd_inverse(cudaStream_t st, const DevCsr &A, double **Binv)
-{
-    int n = A.rows;
-    CU(cudaMalloc(Binv, sizeof(double) * (size_t)n * n));
-    return dense_spd_inverse_block(st, A, 0, n, *Binv);
-}
-
 // ------------------------------------------------------------------------------------------
 // Sparse direct solver with a host-computed factorisation: x = P^T L^-T D^-1 L^-1 P b, the
 // solve phase of Eigen::SimplicialLDLT (SimplicialCholesky.h:148-171) that the reference uses
@@ -2376,6 +2369,7 @@ int ddpca_ldlt_create_dense(int device, int n, const int *rowptr, const int *col
     if (ndev == 0) return fail("no CUDA device: libddpca_b200 has no CPU fallback");
     if (device < 0 || device >= ndev) return fail("device index out of range");
     CU(cudaSetDevice(device));
+    StageTimer tm("dense solver");
     CsrHost A;
     A.rows = A.cols = n;
     A.rp.assign(rowptr, rowptr + n + 1);
@@ -2389,10 +2383,16 @@ int ddpca_ldlt_create_dense(int device, int n, const int *rowptr, const int *col
     if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail("stream creation failed"); }
     s->stream = s->own_stream;
     DevCsr dA;
-    if (upload_csr(A, dA) || dense_spd_inverse(s->stream, dA, &s->Binv)) { free_csr(dA); ldlt_free(s); return 1; }
+    if (upload_csr(A, dA)) { free_csr(dA); ldlt_free(s); return 1; }
+    tm.lap("stream + operator upload");
+    if (cudaMalloc(&s->Binv, sizeof(double) * (size_t)n * n) != cudaSuccess) { free_csr(dA); ldlt_free(s); cudaGetLastError(); return fail("out of device memory"); }
+    tm.lap("allocation of the inverse");
+    if (dense_spd_inverse_block(s->stream, dA, 0, n, s->Binv)) { free_csr(dA); ldlt_free(s); return 1; }
+    tm.lap("inversion");
     free_csr(dA);
     // work vectors for the host-pointer entry point
     if (cudaMalloc(&s->lo.r, sizeof(double) * n) != cudaSuccess || cudaMalloc(&s->up.r, sizeof(double) * n) != cudaSuccess) { ldlt_free(s); return fail("out of device memory"); }
+    tm.lap("release + work vectors");
     *out = s;
     return 0;
 }

@@ -2,6 +2,9 @@
 #include "plan.h"
 
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cstring>
 #include <numeric>
 
@@ -310,10 +313,58 @@ void transpose_csr(const CsrHost &A, CsrHost &out)
 {
     out.rows = A.cols;
     out.cols = A.rows;
-    out.rp.assign(A.cols + 1, 0);
-    long nnz = A.nnz();
+    const long nnz = A.nnz();
+    const int ncol = A.cols;
+    int T = 1;
+#ifdef _OPENMP
+    T = omp_get_max_threads();
+#endif
+    // Row ranges of A go to threads; each counts its entries per column, a prefix over (column, thread) turns the
+    // counts into write positions, each thread then scatters its rows in order: columns of the result come out sorted
+    // and the result does not depend on the thread count.  The histograms cost T * ncol ints: only when the operator
+    // is large enough to pay for them.
+    if (T > 1 && nnz >= (1L << 16) && (long)T * ncol <= 4 * nnz) {
+        std::vector<int> rbeg(T + 1);
+        for (int t = 0; t <= T; t++) rbeg[t] = (int)((long)A.rows * t / T);
+        RawVec<int> cnt((size_t)T * ncol);
+#pragma omp parallel num_threads(T)
+        {
+            const int t = omp_get_thread_num();
+            int *c = cnt.data() + (size_t)t * ncol;
+            std::memset(c, 0, sizeof(int) * (size_t)ncol);
+            for (long p = A.rp[rbeg[t]]; p < A.rp[rbeg[t + 1]]; p++) c[A.ci[p]]++;
+        }
+        out.rp.assign(ncol + 1, 0);
+#pragma omp parallel for schedule(static)
+        for (int j = 0; j < ncol; j++) {
+            int tot = 0;
+            for (int t = 0; t < T; t++) tot += cnt[(size_t)t * ncol + j];
+            out.rp[j + 1] = tot;
+        }
+        for (int j = 0; j < ncol; j++) out.rp[j + 1] += out.rp[j];
+#pragma omp parallel for schedule(static)
+        for (int j = 0; j < ncol; j++) {
+            int run = out.rp[j];
+            for (int t = 0; t < T; t++) { const int c = cnt[(size_t)t * ncol + j]; cnt[(size_t)t * ncol + j] = run; run += c; }
+        }
+        out.ci.resize(nnz);
+        out.v.resize(nnz);
+#pragma omp parallel num_threads(T)
+        {
+            const int t = omp_get_thread_num();
+            int *pos = cnt.data() + (size_t)t * ncol;
+            for (int i = rbeg[t]; i < rbeg[t + 1]; i++)
+                for (int p = A.rp[i]; p < A.rp[i + 1]; p++) {
+                    const int q = pos[A.ci[p]]++;
+                    out.ci[q] = i;
+                    out.v[q] = A.v[p];
+                }
+        }
+        return;
+    }
+    out.rp.assign(ncol + 1, 0);
     for (long p = 0; p < nnz; p++) out.rp[A.ci[p] + 1]++;
-    for (int j = 0; j < A.cols; j++) out.rp[j + 1] += out.rp[j];
+    for (int j = 0; j < ncol; j++) out.rp[j + 1] += out.rp[j];
     out.ci.resize(nnz);
     out.v.resize(nnz);
     std::vector<int> fill(out.rp.begin(), out.rp.end() - 1);
@@ -327,17 +378,30 @@ void transpose_csr(const CsrHost &A, CsrHost &out)
 
 long drop_zeros_csr(CsrHost &A)
 {
-    long w = 0, nnz = A.nnz();
-    int start = 0;
-    for (int i = 0; i < A.rows; i++) {
-        const int end = A.rp[i + 1];
-        for (int p = start; p < end; p++)
-            if (A.v[p] != 0.0) { A.ci[w] = A.ci[p]; A.v[w] = A.v[p]; w++; }
-        start = end;
-        A.rp[i + 1] = (int)w;
+    const long nnz = A.nnz();
+    const int n = A.rows;
+    // count per row, prefix, compact into fresh arrays (parallel over rows)
+    std::vector<int> nrp(n + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        int c = 0;
+        for (int p = A.rp[i]; p < A.rp[i + 1]; p++) c += (A.v[p] != 0.0);
+        nrp[i + 1] = c;
     }
-    A.ci.resize(w);
-    A.v.resize(w);
+    for (int i = 0; i < n; i++) nrp[i + 1] += nrp[i];
+    const long w = nrp[n];
+    if (w == nnz) return 0;
+    RawVec<int> ci(w);
+    RawVec<double> v(w);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        int q = nrp[i];
+        for (int p = A.rp[i]; p < A.rp[i + 1]; p++)
+            if (A.v[p] != 0.0) { ci[q] = A.ci[p]; v[q] = A.v[p]; q++; }
+    }
+    A.rp.swap(nrp);
+    A.ci.swap(ci);
+    A.v.swap(v);
     return nnz - w;
 }
 

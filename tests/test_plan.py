@@ -159,3 +159,15 @@ def test_block_wise_set_up_equals_the_concatenated_one(monkeypatch):
     direct = dd.setup_dryrun(hs)
     monkeypatch.setenv("DDPCA_SETUP_CONCAT", "1")
     assert dd.setup_dryrun(hs)["checksum"] == direct["checksum"]
+
+
+def test_host_set_up_arrays_are_pinned_by_checksum():
+    """Regression anchor of the host half (plans, permutation, layouts, chunk tables, transfer operators and their
+    node-triple forms): hashes recorded with the first, serial implementation of the CSR helpers.  A batch of 8 is
+    large enough for the threaded transpose / compaction paths (plan.cpp)."""
+    d, meta, A, P = load_golden("beam_3lev")
+    assert dd.setup_dryrun([(A, P)] * 3, dd.SMOOTH_MC)["checksum"] == 9101311763389178906
+    assert dd.setup_dryrun([(A, P)], dd.SMOOTH_MC)["checksum"] == 5640188810714335141
+    assert dd.setup_dryrun([(A, P)] * 3, dd.SMOOTH_LEX)["checksum"] == 2724131200358734289
+    assert dd.setup_dryrun([(A, P)] * 8, dd.SMOOTH_MC)["checksum"] == 16331060792140387340
+    assert dd.setup_dryrun([(A, P)] * 8, dd.SMOOTH_LEX)["checksum"] == 8606172048292588632
