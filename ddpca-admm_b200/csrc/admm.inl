@@ -688,6 +688,8 @@ int ddpca_admm_finalize(ddpca_admm *h)
     CU(cudaSetDevice(h->device));
     const int nb = h->nb, ni = h->ni;
     StageTimer tm("admm finalize");
+    if (setup_stream_sync(h->device)) return 1;   // the dense inverses of the side / coarse solvers (enqueued at their creation)
+    tm.lap("pending dense inversions");
     // ---- completeness --------------------------------------------------------------------------
     for (int v = 0; v < nb; v++) {
         HostBody &b = h->body[v];

@@ -1098,9 +1098,31 @@ static void free_level(Level &L)
     L.x = L.b = L.p1 = L.r = L.dinv = nullptr;
 }
 
+// One set-up stream per device: the dense inversions of an ADMM set-up (tens of interface mass matrices) are enqueued
+// on it back to back and share one panel workspace in stream order.  The host does not wait for an inversion: while
+// the device works, it allocates and uploads the next operator.  Consumers order themselves behind the stream with
+// an event (ddpca_ldlt_create_dense) or wait for it (setup_stream_sync: ddpca_admm_finalize, ddpca_ldlt_solve*).
+static cudaStream_t setup_stream(int dev)
+{
+    static std::mutex m;
+    static cudaStream_t st[64] = {nullptr};
+    std::lock_guard<std::mutex> lk(m);
+    if (!st[dev & 63] && cudaStreamCreateWithFlags(&st[dev & 63], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return st[dev & 63];
+}
+static int setup_stream_sync(int dev)
+{
+    cudaStream_t st = setup_stream(dev);
+    if (!st) return fail("stream creation failed");
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // In-place inversion + symmetrisation of a dense SPD matrix already on the device (set-up only):
-// blocked Gauss-Jordan, three launches per 64-wide panel (kernels.cuh).
-static int dense_invert_inplace(cudaStream_t st, int n, double *B)
+// blocked Gauss-Jordan, three launches per 64-wide panel (kernels.cuh).  `wait`: return when the result is there;
+// otherwise the work is only enqueued -- allowed on the device's set-up stream alone, whose order protects the workspace.
+static int dense_invert_inplace(cudaStream_t st, int n, double *B, bool wait = true)
 {
     static std::atomic<unsigned long long> attr_set{0};
     int dev = 0;
@@ -1122,7 +1144,7 @@ static int dense_invert_inplace(cudaStream_t st, int n, double *B)
     auto cleanup = [&]() {};
     const size_t need = (size_t)kGjB * kGjB + 2 * (size_t)n * kGjB;
     if (ws_len[dev & 63] < need) {
-        CUX(cudaStreamSynchronize(st));
+        CUX(cudaDeviceSynchronize());   // nothing may still be using the old workspace
         cudaFree(ws_buf[dev & 63]);
         ws_buf[dev & 63] = nullptr; ws_len[dev & 63] = 0;
         CUX(cudaMalloc(&ws_buf[dev & 63], sizeof(double) * need));
@@ -1132,6 +1154,9 @@ static int dense_invert_inplace(cudaStream_t st, int n, double *B)
     const int nt = cdiv(n, kGjB);
     // DDPCA_VERBOSE: device time per kernel class of this inversion (events around every launch)
     const bool timed = std::getenv("DDPCA_VERBOSE") != nullptr && n >= 1024;
+    cudaStream_t sst = setup_stream(dev);
+    if (st != sst || timed) wait = true;
+    if (st != sst && sst) CUX(cudaStreamSynchronize(sst));   // inversions still pending there use the same workspace
     std::vector<cudaEvent_t> evs;
     auto mark = [&]() { if (timed) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); evs.push_back(e); } };
     for (int k0 = 0; k0 < n; k0 += kGjB) {
@@ -1146,6 +1171,8 @@ static int dense_invert_inplace(cudaStream_t st, int n, double *B)
     mark();
     dim3 g2(cdiv(n, 256), n);
     k_symmetrize<<<g2, 256, 0, st>>>(n, B);
+    CUX(cudaGetLastError());
+    if (!wait) return 0;
     CUX(cudaStreamSynchronize(st));   // the workspace is free again when the lock is released
     CUX(cudaGetLastError());
     if (timed) {
@@ -1159,11 +1186,11 @@ static int dense_invert_inplace(cudaStream_t st, int n, double *B)
     return 0;
 }
 // Dense inverse of the diagonal block [r0, r0+n) of an SPD operator given as device CSR, written to Bblk (n x n)
-static int dense_spd_inverse_block(cudaStream_t st, const DevCsr &A, int r0, int n, double *Bblk)
+static int dense_spd_inverse_block(cudaStream_t st, const DevCsr &A, int r0, int n, double *Bblk, bool wait = true)
 {
     CU(cudaMemsetAsync(Bblk, 0, sizeof(double) * (size_t)n * n, st));
     k_csr_to_dense<<<cdiv(n, 128), 128, 0, st>>>(A.view(), r0, n, Bblk);
-    return dense_invert_inplace(st, n, Bblk);
+    return dense_invert_inplace(st, n, Bblk, wait);
 }
 // ------------------------------------------------------------------------------------------
 // Sparse direct solver with a host-computed factorisation: x = P^T L^-T D^-1 L^-1 P b, the
@@ -1288,9 +1315,12 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
     Lh.rp.assign(Lrp, Lrp + n + 1);
     Lh.ci.assign(Lci, Lci + Lrp[n]);
     Lh.v.assign(Lv, Lv + Lrp[n]);
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
     for (int i = 0; i < n; i++)
         for (int p = Lrp[i]; p < Lrp[i + 1]; p++)
-            if (Lci[p] >= i || Lci[p] < 0 || (p > Lrp[i] && Lci[p] <= Lci[p - 1])) return fail("ddpca_ldlt_create: L must be strictly lower with sorted rows");
+            if (Lci[p] >= i || Lci[p] < 0 || (p > Lrp[i] && Lci[p] <= Lci[p - 1])) bad |= 1;
+    if (bad) return fail("ddpca_ldlt_create: L must be strictly lower with sorted rows");
     transpose_csr(Lh, Lt);
     auto add_diag = [&](const CsrHost &T, bool diag_last, CsrHost &o) {
         o.rows = o.cols = n;
@@ -1298,6 +1328,7 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
         for (int i = 0; i < n; i++) o.rp[i + 1] = o.rp[i] + (T.rp[i + 1] - T.rp[i]) + 1;
         o.ci.resize(o.rp[n]);
         o.v.resize(o.rp[n]);
+#pragma omp parallel for schedule(static)
         for (int i = 0; i < n; i++) {
             int q = o.rp[i];
             if (!diag_last) { o.ci[q] = i; o.v[q] = 1.0; q++; }
@@ -1318,6 +1349,7 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
     LevelPlan tri;
     build_tri_plan(n, Lrp, Lci, tri);   // the wavefronts of both factors (DDPCA_LDLT_GENERIC_PLAN: through the general planner)
     const LevelPlan *given = std::getenv("DDPCA_LDLT_GENERIC_PLAN") ? nullptr : &tri;
+    tm.lap("triangular operators + wavefront plan");
     if (setup_level(s->lo, n, Tlo.rp.data(), Tlo.ci.data(), Tlo.v.data(), DDPCA_SMOOTH_LEX, false, true, nullptr, given) ||
         setup_level(s->up, n, Tup.rp.data(), Tup.ci.data(), Tup.v.data(), DDPCA_SMOOTH_LEX, false, true, nullptr, given)) { ldlt_free(s); return 1; }
     tm.lap("two staged triangular levels");
@@ -2382,14 +2414,33 @@ int ddpca_ldlt_create_dense(int device, int n, const int *rowptr, const int *col
     cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device);
     if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail("stream creation failed"); }
     s->stream = s->own_stream;
+    // operator upload, inversion and release of the upload are enqueued on the device's set-up stream; this solver's own
+    // stream is ordered behind them by an event, the host goes on to the next operator
+    cudaStream_t sst = setup_stream(device);
+    if (!sst) { ldlt_free(s); return fail("stream creation failed"); }
     DevCsr dA;
-    if (upload_csr(A, dA)) { free_csr(dA); ldlt_free(s); return 1; }
-    tm.lap("stream + operator upload");
-    if (cudaMalloc(&s->Binv, sizeof(double) * (size_t)n * n) != cudaSuccess) { free_csr(dA); ldlt_free(s); cudaGetLastError(); return fail("out of device memory"); }
+    dA.rows = dA.cols = n; dA.nnz = A.nnz();
+    const size_t nnz = (size_t)A.nnz();
+    bool ok = cudaMallocAsync((void **)&dA.rp, sizeof(int) * (n + 1), sst) == cudaSuccess &&
+              cudaMallocAsync((void **)&dA.ci, sizeof(int) * std::max<size_t>(1, nnz), sst) == cudaSuccess &&
+              cudaMallocAsync((void **)&dA.v, sizeof(double) * std::max<size_t>(1, nnz), sst) == cudaSuccess &&
+              cudaMemcpyAsync(dA.rp, A.rp.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, sst) == cudaSuccess &&
+              (nnz == 0 || (cudaMemcpyAsync(dA.ci, A.ci.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, sst) == cudaSuccess &&
+                            cudaMemcpyAsync(dA.v, A.v.data(), sizeof(double) * nnz, cudaMemcpyHostToDevice, sst) == cudaSuccess));
+    auto drop_upload = [&]() { if (dA.rp) cudaFreeAsync(dA.rp, sst); if (dA.ci) cudaFreeAsync(dA.ci, sst); if (dA.v) cudaFreeAsync(dA.v, sst); dA = DevCsr(); };
+    if (!ok) { drop_upload(); ldlt_free(s); cudaGetLastError(); return fail("operator upload failed (out of device memory?)"); }
+    tm.lap("operator upload (enqueued)");
+    if (cudaMalloc(&s->Binv, sizeof(double) * (size_t)n * n) != cudaSuccess) { drop_upload(); ldlt_free(s); cudaGetLastError(); return fail("out of device memory"); }
     tm.lap("allocation of the inverse");
-    if (dense_spd_inverse_block(s->stream, dA, 0, n, s->Binv)) { free_csr(dA); ldlt_free(s); return 1; }
-    tm.lap("inversion");
-    free_csr(dA);
+    if (dense_spd_inverse_block(sst, dA, 0, n, s->Binv, /*wait=*/false)) { drop_upload(); ldlt_free(s); return 1; }
+    drop_upload();
+    {
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev, sst) != cudaSuccess ||
+            cudaStreamWaitEvent(s->stream, ev, 0) != cudaSuccess) { ldlt_free(s); cudaGetLastError(); return fail("event set-up failed"); }
+        cudaEventDestroy(ev);   // released by the runtime once the wait has been satisfied
+    }
+    tm.lap("inversion (enqueued)");
     // work vectors for the host-pointer entry point
     if (cudaMalloc(&s->lo.r, sizeof(double) * n) != cudaSuccess || cudaMalloc(&s->up.r, sizeof(double) * n) != cudaSuccess) { ldlt_free(s); return fail("out of device memory"); }
     tm.lap("release + work vectors");
