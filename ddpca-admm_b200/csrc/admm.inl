@@ -688,8 +688,6 @@ int ddpca_admm_finalize(ddpca_admm *h)
     CU(cudaSetDevice(h->device));
     const int nb = h->nb, ni = h->ni;
     StageTimer tm("admm finalize");
-    if (setup_stream_sync(h->device)) return 1;   // the dense inverses of the side / coarse solvers (enqueued at their creation)
-    tm.lap("pending dense inversions");
     // ---- completeness --------------------------------------------------------------------------
     for (int v = 0; v < nb; v++) {
         HostBody &b = h->body[v];
@@ -931,6 +929,10 @@ int ddpca_admm_finalize(ddpca_admm *h)
     // host copies of the operators are no longer needed
     for (auto &f : h->iface) for (auto &s : f.side) for (auto &o : s.op) o = CsrHost();
     for (auto &b : h->body) { b.F = CsrHost(); b.accuProl = CsrHost(); b.globTran_D_1 = CsrHost(); b.rp.clear(); b.ci.clear(); b.v.clear(); b.prp.clear(); b.pci.clear(); b.pv.clear(); }
+    // the dense inverses of the side / coarse solvers were only enqueued at their creation (mg.cu, setup_stream): the
+    // device has been working on them while the host built the hierarchies and the stacked operators above
+    if (setup_stream_sync(h->device)) return 1;
+    tm.lap("pending dense inversions");
     h->finalized = true;
     return 0;
 }

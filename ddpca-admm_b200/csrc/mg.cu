@@ -1416,25 +1416,48 @@ static int ldlt_build(int device, int n, const int *perm, const int *Lrp, const 
                 }
             }
             tm.lap("dense tail: host assembly");
+            // assembled, multiplied and inverted on the device's set-up stream without waiting for it (the host goes on
+            // with the rest of the set-up); this solver's stream is ordered behind the result by an event, temporaries are
+            // stream-ordered allocations
             double *dL = nullptr, *dD = nullptr;
             DevCsr dTail;
-            bool ok = cudaMalloc(&dL, sizeof(double) * (size_t)T * T) == cudaSuccess && cudaMalloc(&dD, sizeof(double) * T) == cudaSuccess &&
+            cudaStream_t sst = setup_stream(device);
+            const size_t tnnz = (size_t)Tail.nnz();
+            dTail.rows = dTail.cols = T; dTail.nnz = (long)tnnz;
+            bool ok = sst != nullptr &&
                       cudaMalloc(&s->tail_Minv, sizeof(double) * (size_t)T * T) == cudaSuccess && cudaMalloc(&s->tail_rhs, sizeof(double) * T) == cudaSuccess &&
-                      upload_csr(Tail, dTail) == 0;
+                      cudaMallocAsync((void **)&dL, sizeof(double) * (size_t)T * T, sst) == cudaSuccess && cudaMallocAsync((void **)&dD, sizeof(double) * T, sst) == cudaSuccess &&
+                      cudaMallocAsync((void **)&dTail.rp, sizeof(int) * (T + 1), sst) == cudaSuccess &&
+                      cudaMallocAsync((void **)&dTail.ci, sizeof(int) * std::max<size_t>(1, tnnz), sst) == cudaSuccess &&
+                      cudaMallocAsync((void **)&dTail.v, sizeof(double) * std::max<size_t>(1, tnnz), sst) == cudaSuccess &&
+                      cudaMemcpyAsync(dTail.rp, Tail.rp.data(), sizeof(int) * (T + 1), cudaMemcpyHostToDevice, sst) == cudaSuccess &&
+                      cudaMemcpyAsync(dTail.ci, Tail.ci.data(), sizeof(int) * tnnz, cudaMemcpyHostToDevice, sst) == cudaSuccess &&
+                      cudaMemcpyAsync(dTail.v, Tail.v.data(), sizeof(double) * tnnz, cudaMemcpyHostToDevice, sst) == cudaSuccess;
             if (ok) {
-                cudaMemsetAsync(dL, 0, sizeof(double) * (size_t)T * T, s->stream);
-                k_csr_to_dense<<<cdiv(T, 128), 128, 0, s->stream>>>(dTail.view(), 0, T, dL);
-                cudaMemcpyAsync(dD, D2.data(), sizeof(double) * T, cudaMemcpyHostToDevice, s->stream);
+                cudaMemsetAsync(dL, 0, sizeof(double) * (size_t)T * T, sst);
+                k_csr_to_dense<<<cdiv(T, 128), 128, 0, sst>>>(dTail.view(), 0, T, dL);
+                cudaMemcpyAsync(dD, D2.data(), sizeof(double) * T, cudaMemcpyHostToDevice, sst);
                 const size_t smem = sizeof(double) * 2 * kGjB * (kGjB + 1);
                 ok = cudaFuncSetAttribute(k_ldl_tail_product64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
                 dim3 gt(cdiv(T, kGjB), cdiv(T, kGjB));
-                if (ok) k_ldl_tail_product64<<<gt, 256, smem, s->stream>>>(T, dL, dD, s->tail_Minv);
-                ok = ok && dense_invert_inplace(s->stream, T, s->tail_Minv) == 0 && upload_vec(k1, &s->tail_k1) == 0;
+                if (ok) k_ldl_tail_product64<<<gt, 256, smem, sst>>>(T, dL, dD, s->tail_Minv);
+                ok = ok && dense_invert_inplace(sst, T, s->tail_Minv, /*wait=*/false) == 0 && upload_vec(k1, &s->tail_k1) == 0;
             }
-            free_csr(dTail);
-            cudaFree(dL);
-            cudaFree(dD);
-            tm.lap("dense tail: product + inverse");
+            if (sst) {
+                if (dTail.rp) cudaFreeAsync(dTail.rp, sst);
+                if (dTail.ci) cudaFreeAsync(dTail.ci, sst);
+                if (dTail.v) cudaFreeAsync(dTail.v, sst);
+                if (dL) cudaFreeAsync(dL, sst);
+                if (dD) cudaFreeAsync(dD, sst);
+                cudaEvent_t ev;
+                if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+                    ok = ok && cudaEventRecord(ev, sst) == cudaSuccess && cudaStreamWaitEvent(s->stream, ev, 0) == cudaSuccess;
+                    cudaEventDestroy(ev);
+                } else ok = false;
+            }
+            dTail = DevCsr();
+            if (!ok && sst) cudaStreamSynchronize(sst);   // before the buffers of a failed attempt are released below
+            tm.lap("dense tail: product + inverse (enqueued)");
             if (ok) { s->tail_T = T; s->tail_stage = st; s->tail_g0 = g0; s->tail_n1 = n1; }
             else { cudaFree(s->tail_Minv); cudaFree(s->tail_rhs); s->tail_Minv = s->tail_rhs = nullptr; cudaGetLastError(); }
         }
