@@ -8,8 +8,8 @@
 // reference is this class.  The public surface is kept verbatim (members maxiLeve, realProl,
 // consStif, consLowe, consDiag, consUppe are read and written by MULTIGRID.h:102,133-138,
 // 1214-1251 and MCONTACT.h:830,853,1539-1542; method signatures as MGPIS.h:16-37); the bodies
-// forward to the C ABI of include/ddpca_b200.h.  No CPU fallback: if the device call fails the
-// error is printed in the reference's style ("ERROR") and -1 is returned.
+// forward to the C ABI of include/ddpca_b200.h.  No CPU fallback: if a device call fails the error is
+// printed in the reference's style ("ERROR") and the process ends (MGPIS::DEVICE_FAILURE below).
 #ifndef _MGPIS_H
 #define _MGPIS_H
 
@@ -71,6 +71,21 @@ public:
 		return (e && (e[0] == 'l' || e[0] == 'L')) ? DDPCA_SMOOTH_LEX : DDPCA_SMOOTH_MC;
 	}
 	long lastIterNumb = 0;      // iterNumb of the last CG_SOLV / BiCGSTAB_SOLV (the reference only prints it)
+	// A device call failed.  The reference's callers ignore return values and would go on with a
+	// zero "solution" -- MCONTACT::LAGRANGE's active-set loop (MCONTACT.h:3690-3698) then never ends.  There is no
+	// CPU fallback, so the message goes to std::cout in the reference's style and to std::cerr, and the process
+	// ends with status 3 unless DDPCA_CONTINUE_ON_ERROR=1 asks for the reference's "print and return -1".
+	static long DEVICE_FAILURE(const char *where){
+		std::cout << where << " (B200): ERROR " << ddpca_last_error() << std::endl;
+		const char *e = std::getenv("DDPCA_CONTINUE_ON_ERROR");
+		if(!(e && e[0] == '1')){
+			std::cerr << where << " (B200): ERROR " << ddpca_last_error()
+				<< " -- no CPU fallback, terminating (DDPCA_CONTINUE_ON_ERROR=1 to return -1 instead)" << std::endl;
+			std::cout.flush();
+			std::exit(3);
+		}
+		return -1;
+	}
 private:
 	struct DEVI{
 		ddpca_mg *h = nullptr;
@@ -138,8 +153,7 @@ ddpca_mg *MGPIS::DEVICE_HANDLE(){
 	ddpca_mg *h = nullptr;
 	if(ddpca_mg_create(DEVICE(), nlev, poin.n.data(), poin.rp.data(), poin.ci.data(), poin.va.data(),
 		poin.prp.data(), poin.pci.data(), poin.pva.data(), SMOOTHER(), &h) != 0){
-		std::cout << "MGPIS (B200): ERROR " << ddpca_last_error() << std::endl;
-		return nullptr;
+		return nullptr;   // the caller reports (DEVICE_FAILURE)
 	}
 	devi = std::make_shared<DEVI>();
 	devi->h = h;
@@ -151,8 +165,7 @@ long MGPIS::MULT_VCYC(long tempLeve, const Eigen::VectorXd &righHand,
 	(void)direSolv;// level 0 is solved with the factorisation held on the device
 	ddpca_mg *h = DEVICE_HANDLE();
 	if(h == nullptr || ddpca_mg_vcycle(h, tempLeve, righHand.data(), resuSolu.data()) != 0){
-		std::cout << "MGPIS::MULT_VCYC (B200): ERROR " << ddpca_last_error() << std::endl;
-		return -1;
+		return DEVICE_FAILURE("MGPIS::MULT_VCYC");
 	}
 	return 1;
 }
@@ -172,8 +185,7 @@ long MGPIS::CG_SOLV(long precSwit, const Eigen::VectorXd &totaForc, Eigen::Vecto
 	double resiNorm = 0.0, toleLimi = 0.0;
 	if(h == nullptr || ddpca_mg_pcg(h, precSwit, totaForc.data(), resuSolu.data(), 1.0E-14,
 		resuSolu.rows(), &iterNumb, &resiNorm, &toleLimi) != 0){
-		std::cout << "MGPIS::CG_SOLV (B200): ERROR " << ddpca_last_error() << std::endl;
-		return -1;
+		return DEVICE_FAILURE("MGPIS::CG_SOLV");
 	}
 	lastIterNumb = iterNumb;
 	std::cout << "#Iteration: " << iterNumb - 1
@@ -198,8 +210,7 @@ long MGPIS::BiCGSTAB_SOLV(long precSwit,
 	double resiNorm = 0.0, toleLimi = 0.0;
 	if(h == nullptr || ddpca_mg_bicgstab(h, precSwit, totaForc.data(), resuSolu.data(), 1.0E-14,
 		resuSolu.rows(), &iterNumb, &resiNorm, &toleLimi) != 0){
-		std::cout << "MGPIS::BiCGSTAB_SOLV (B200): ERROR " << ddpca_last_error() << std::endl;
-		return -1;
+		return DEVICE_FAILURE("MGPIS::BiCGSTAB_SOLV");
 	}
 	lastIterNumb = iterNumb;
 	std::cout << "#Iteration: " << iterNumb - 1
@@ -215,8 +226,7 @@ long MGPIS::MULT_SOLV(const Eigen::VectorXd &totaForc, Eigen::VectorXd &resuSolu
 	long iterNumb = 0;
 	double resiNorm = 0.0;
 	if(h == nullptr || ddpca_mg_mult_solv(h, totaForc.data(), resuSolu.data(), &iterNumb, &resiNorm) != 0){
-		std::cout << "MGPIS::MULT_SOLV (B200): ERROR " << ddpca_last_error() << std::endl;
-		return -1;
+		return DEVICE_FAILURE("MGPIS::MULT_SOLV");
 	}
 	std::cout << "#Iteration: " << iterNumb << ", residual: "
 		<< resiNorm << "/" << 1.0E-14 * totaForc.norm();
@@ -239,8 +249,7 @@ long MGPIS::GMRES_SOLV(long precSwit, const Eigen::VectorXd &totaForc, Eigen::Ve
 	double resiNorm = 0.0, toleLimi = 0.0;
 	if(h == nullptr || ddpca_mg_gmres(h, precSwit, totaForc.data(), resuSolu.data(),
 		&iterNumb, &resiNorm, &toleLimi) != 0){
-		std::cout << "MGPIS::GMRES_SOLV (B200): ERROR " << ddpca_last_error() << std::endl;
-		return -1;
+		return DEVICE_FAILURE("MGPIS::GMRES_SOLV");
 	}
 	lastIterNumb = iterNumb;
 	std::cout << "#Iteration: " << iterNumb << ", residual: " << resiNorm << "/" << toleLimi;

@@ -16,3 +16,11 @@ gzip -9 -n -c "$tmp/beam_3lev.ddpk" > "$here/beam_3lev.ddpk.gz"
 rm -rf "$tmp"
 ls -la "$here"
 python "$here/make_block_fixture.py"
+# BLOCK on the dual-mortar path (examples/BLOCK.cpp:96-102 -> MCONTACT::LAGRANGE(1), MCONTACT.h:2847-3701): the
+# condensed system of the first active-set step, its rebuilt 3-level hierarchy and the reference's own
+# `mgpi.BiCGSTAB_SOLV(1, F, U_1)` result (:3561-3562)
+tmp="$(mktemp -d)"
+cd "$tmp"
+"$ref/block_lagrange" --glob 2 --divi 1,1,1 --out "$tmp/block_lagrange.ddpk" > "$here/block_lagrange.json"
+gzip -9 -n -c "$tmp/block_lagrange.ddpk" > "$here/block_lagrange.ddpk.gz"
+rm -rf "$tmp"

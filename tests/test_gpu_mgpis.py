@@ -345,3 +345,32 @@ def test_solve_after_a_non_finite_right_hand_side_is_clean():
         x1 = mg.CG_SOLV(1, b)
         assert mg.last_iterNumb == it0 and np.array_equal(x0, x1)
         mg.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_bicgstab_on_the_condensed_dual_mortar_system(mode):
+    """SURVEY.md §8 row f-3: the solve inside MCONTACT::LAGRANGE(1) -- `mgpi.ESTABLISH(); mgpi.BiCGSTAB_SOLV(1, F, U_1)`
+    (MCONTACT.h:3561-3562) on the hierarchy the reference rebuilds for the condensed system of BLOCK's first active-set
+    step (fixture tapped from the reference's own run by oracle/ref_drivers/block_lagrange.cpp).  Rows of up to 213
+    entries where the mortar rows were eliminated, ragged row groups, a pattern that is not exactly symmetric."""
+    d, meta, A, P = load_golden("block_lagrange")
+    mg = dd.MGPIS.from_hierarchy(A, P, smoother=mode)
+    rng = np.random.default_rng(5)
+    for l, a in enumerate(A):
+        v = rng.standard_normal(a.shape[0])
+        assert rel(mg.spmv(l, v), orc.spmv(a, v)) < 1e-13
+    x = mg.BiCGSTAB_SOLV(1, d["F"])
+    assert mg.last_resid <= mg.last_tol
+    assert rel(x, d["U_1"]) < 1e-8                       # the reference's own solution
+    ref_it = meta["bicgstab_iters"][0]
+    if mode == dd.SMOOTH_LEX:                            # the reference's sweeps row for row
+        assert abs(mg.last_iterNumb - ref_it) <= 1
+        z = mg.MULT_VCYC(len(A) - 1, d["F"])
+        assert rel(z, orc.OracleMG(A, P).vcycle(len(A) - 1, d["F"])) < 1e-9
+    else:
+        assert mg.last_iterNumb <= 2 * ref_it
+    r = d["F"] - orc.spmv(A[-1], x)
+    assert np.linalg.norm(r) <= 1e-11 * np.linalg.norm(d["F"])
+    xc = mg.CG_SOLV(1, d["F"])                           # symmetric to rounding without friction: CG agrees
+    assert rel(xc, d["U_1"]) < 1e-8
+    mg.close()

@@ -23,6 +23,7 @@ def _run(exe, args, env=None):
     moni = os.path.join(tmp, "Beam", "resuMoni.txt")
     if os.path.exists(moni):
         out["resuMoni"] = open(moni).read()
+    out["cwd"] = tmp
     return out
 
 
@@ -75,6 +76,61 @@ def test_beam_dd_example_through_the_overlay(musc):
     assert gpu["iterNumbReco"] == ref["ref_iterNumbReco"]
     for a, b in zip(gpu["disp_norm"], ref["ref_disp_norm"]):
         assert abs(a - b) <= 1e-8 * b
+
+
+@pytest.mark.skipif(not (os.access(os.path.join(BIN, "block_lagrange_b200"), os.X_OK) and os.access(os.path.join(REF, "block_lagrange"), os.X_OK)),
+                    reason="overlay / reference binaries not built")
+def test_block_example_on_the_dual_mortar_path_through_the_overlay():
+    """SURVEY.md §8 row f-3: examples/BLOCK.cpp:96-102 (menu 3) -> SOLVE(2) -> MCONTACT::LAGRANGE(1)
+    (MCONTACT.h:2847-3701), the reference's host code unchanged: boundary-consistent dual mortar operators, active-set
+    loop, condensation and the hierarchy rebuilt for the condensed system stay on the host; the solve of every
+    active-set step, `mgpi.ESTABLISH(); mgpi.BiCGSTAB_SOLV(1, F, U_1)` (:3561-3562), runs on the device through the
+    MGPIS overlay.  Compared with the pure-reference binary of the same source: active-set steps, displacements of all
+    nine bodies, and the multipliers the reference writes to resuLagr_*.txt (:3618-3635), 1e-8."""
+    import numpy as np
+
+    args = ["--glob", "2", "--divi", "2,2,2"]
+    ref = _run(os.path.join(REF, "block_lagrange"), args)
+    gpu = _run(os.path.join(BIN, "block_lagrange_b200"), args)
+    assert gpu["impl"] == "b200" and ref["impl"] == "reference"
+    assert gpu["error"] is False
+    assert gpu["active_set_steps"] == ref["active_set_steps"] >= 1
+    for it_g, it_r in zip(gpu["bicgstab_iters"], ref["bicgstab_iters"]):
+        assert 1 <= it_g <= 2 * it_r                       # multicolour ordering: other inner count
+    for a, b in zip(gpu["disp_norm"], ref["disp_norm"]):
+        assert abs(a - b) <= 1e-8 * b
+    nlagr = 0
+    for name in sorted(os.listdir(os.path.join(ref["cwd"], "Block"))):
+        if not (name.startswith("resuLagr_") or name.startswith("resuDisp_")):
+            continue
+        a = np.loadtxt(os.path.join(ref["cwd"], "Block", name), ndmin=2)
+        b = np.loadtxt(os.path.join(gpu["cwd"], "Block", name), ndmin=2)
+        assert a.shape == b.shape
+        if a.size:
+            assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(a), name
+            nlagr += name.startswith("resuLagr_")
+    assert nlagr >= 2                                      # the two contact interfaces carry pressure
+    # the patch test's analytic answer: uniform contact pressure = the applied 1e7 Pa (examples/BLOCK.h:46)
+    for ts in (0, 1):
+        lam = np.loadtxt(os.path.join(gpu["cwd"], "Block", f"resuLagr_{ts}.txt"), ndmin=2)
+        assert np.all(lam[:, 1] == 2) and np.abs(lam[:, 2] - 1.0e7).max() <= 1e-8 * 1.0e7
+
+
+@pytest.mark.skipif(os.environ.get("DDPCA_SLOW_TESTS") != "1", reason="100 s of reference host code per run: DDPCA_SLOW_TESTS=1 (tools/lagrange_bench.py runs the same check)")
+@pytest.mark.skipif(not os.access(os.path.join(BIN, "cylinder_lagrange_b200"), os.X_OK), reason="overlay binaries not built")
+def test_cylinder_example_on_the_dual_mortar_path_through_the_overlay():
+    """examples/CYLINDER.cpp:85-90 (menu 3): CYLINDER_1, Hertzian contact, MCONTACT::LAGRANGE(1) with a changing active
+    set (two steps at locaLeve 5, 504 036 rows, 1 026 constraints change status after the first), every step's
+    BiCGSTAB_SOLV on the device; against the reference's own run (tests/golden/cylinder_lagrange.json, made by
+    tests/golden/make_lagrange_golden.py): same active-set history, displacements and contact tractions to 1e-8."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import lagrange_bench as lb
+
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "cylinder_lagrange.json")))
+    gpu = lb.run(os.path.join(BIN, "cylinder_lagrange_b200"), ["--loca", "5"], "Cylinder")
+    assert lb.compare(gpu, ref)["failures"] == []
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs at least 2 GPUs")

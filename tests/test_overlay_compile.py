@@ -29,3 +29,27 @@ def test_reference_examples_compile_against_the_overlay():
         if p.returncode != 0:
             failed[e] = out[-2000:]
     assert not failed, failed
+
+
+def _has_device():
+    try:
+        import ddpca_b200 as dd
+
+        return dd.device_count() > 0
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(not os.access(os.path.join(HOST, "_bin", "block_lagrange_b200"), os.X_OK), reason="overlay binaries not built")
+@pytest.mark.skipif(_has_device(), reason="a device is present: the solve succeeds (tests/test_gpu_overlay.py)")
+def test_overlay_solver_without_a_device_ends_the_process_loudly():
+    """No CPU fallback behind the class surface either.  The reference's callers ignore return values:
+    MCONTACT::LAGRANGE would take the untouched zero vector for a solution and its active-set loop
+    (MCONTACT.h:3690-3698) would never end.  The overlay therefore prints the error and terminates with status 3."""
+    import tempfile
+
+    tmp = tempfile.mkdtemp(prefix="ddpca_nodev_")
+    p = subprocess.run([os.path.join(HOST, "_bin", "block_lagrange_b200"), "--glob", "1", "--divi", "2,2,2"], cwd=tmp,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert p.returncode == 3
+    assert b"MGPIS::BiCGSTAB_SOLV (B200): ERROR" in p.stderr and b"no CPU fallback" in p.stderr

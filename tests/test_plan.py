@@ -13,7 +13,7 @@ def _pattern_rows(a, i):
 
 
 @pytest.mark.parametrize("mode", [dd.SMOOTH_LEX, dd.SMOOTH_MC])
-@pytest.mark.parametrize("name", ["beam_2lev", "beam_3lev"])
+@pytest.mark.parametrize("name", ["beam_2lev", "beam_3lev", "block_lagrange"])
 def test_plan_is_valid(name, mode):
     d, meta, A, P = load_golden(name)
     for a in A:
