@@ -17,6 +17,7 @@
 #include "ddpca_b200.h"
 
 #include <cstdlib>
+#include <omp.h>
 #include <memory>
 
 class MGPIS{
@@ -96,21 +97,73 @@ private:
 
 long MGPIS::ESTABLISH(){
 	// the L/D/U members stay available to the reference code that copies them by name
-	// (MULTIGRID.h:136-138); the device keeps its own single-copy layout
+	// (MULTIGRID.h:136-138); the device keeps its own single-copy layout.  Same result as
+	// MGPIS.h:40-53 array for array (tests/cpp/establish_parity.cpp) -- strictly-lower and
+	// strictly-upper entries of every row in their stored order, one diagonal entry per row
+	// (0.0 where none is stored: coeff(tj,tj)) -- but written straight into the compressed
+	// arrays in one counting and one filling pass per level, rows in parallel unless the
+	// caller is already inside a parallel region (MCONTACT::ESTABLISH loops over bodies,
+	// MCONTACT.h:812-825), instead of two triangular views, n binary searches and a triplet sort.
+	typedef Eigen::SparseMatrix<double,Eigen::RowMajor> SPMA;
 	consLowe.resize(maxiLeve + 1);
 	consDiag.resize(maxiLeve + 1);
 	consUppe.resize(maxiLeve + 1);
+	const bool rowsPara = !omp_in_parallel();
 	for(long ti = 0; ti <= maxiLeve; ti ++){
-		consStif[ti].makeCompressed();
-		consLowe[ti] = consStif[ti].triangularView<Eigen::StrictlyLower>();
-		consUppe[ti] = consStif[ti].triangularView<Eigen::StrictlyUpper>();
-		std::vector<Eigen::Triplet<double>> diagList;
-		diagList.reserve(consStif[ti].rows());
-		for(long tj = 0; tj < consStif[ti].rows(); tj ++){
-			diagList.emplace_back(tj, tj, consStif[ti].coeff(tj,tj));
+		SPMA &stif = consStif[ti];
+		stif.makeCompressed();
+		const long rowNumb = stif.rows();
+		const int *outeStif = stif.outerIndexPtr();
+		const int *inneStif = stif.innerIndexPtr();
+		const double *valuStif = stif.valuePtr();
+		SPMA lowe(rowNumb, stif.cols()), diag(rowNumb, stif.cols()), uppe(rowNumb, stif.cols());
+		//entries below / above the diagonal per row, then prefix sums
+		int *outeLowe = lowe.outerIndexPtr(), *outeDiag = diag.outerIndexPtr(), *outeUppe = uppe.outerIndexPtr();
+		outeLowe[0] = 0; outeDiag[0] = 0; outeUppe[0] = 0;
+		#pragma omp parallel for schedule(static) if(rowsPara)
+		for(long tj = 0; tj < rowNumb; tj ++){
+			int loweNumb = 0, uppeNumb = 0;
+			for(int tk = outeStif[tj]; tk < outeStif[tj + 1]; tk ++){
+				loweNumb += (inneStif[tk] < tj);
+				uppeNumb += (inneStif[tk] > tj);
+			}
+			outeLowe[tj + 1] = loweNumb;
+			outeUppe[tj + 1] = uppeNumb;
+			outeDiag[tj + 1] = 1;
 		}
-		consDiag[ti].resize(consStif[ti].rows(), consStif[ti].cols());
-		consDiag[ti].setFromTriplets(diagList.begin(), diagList.end());
+		for(long tj = 0; tj < rowNumb; tj ++){
+			outeLowe[tj + 1] += outeLowe[tj];
+			outeUppe[tj + 1] += outeUppe[tj];
+			outeDiag[tj + 1] += outeDiag[tj];
+		}
+		lowe.resizeNonZeros(outeLowe[rowNumb]);
+		uppe.resizeNonZeros(outeUppe[rowNumb]);
+		diag.resizeNonZeros(rowNumb);
+		int *inneLowe = lowe.innerIndexPtr(), *inneDiag = diag.innerIndexPtr(), *inneUppe = uppe.innerIndexPtr();
+		double *valuLowe = lowe.valuePtr(), *valuDiag = diag.valuePtr(), *valuUppe = uppe.valuePtr();
+		#pragma omp parallel for schedule(static) if(rowsPara)
+		for(long tj = 0; tj < rowNumb; tj ++){
+			int loweCurs = outeLowe[tj], uppeCurs = outeUppe[tj];
+			double diagValu = 0.0;
+			for(int tk = outeStif[tj]; tk < outeStif[tj + 1]; tk ++){
+				if(inneStif[tk] < tj){
+					inneLowe[loweCurs] = inneStif[tk];
+					valuLowe[loweCurs ++] = valuStif[tk];
+				}
+				else if(inneStif[tk] > tj){
+					inneUppe[uppeCurs] = inneStif[tk];
+					valuUppe[uppeCurs ++] = valuStif[tk];
+				}
+				else{
+					diagValu = valuStif[tk];
+				}
+			}
+			inneDiag[tj] = tj;
+			valuDiag[tj] = diagValu;
+		}
+		consLowe[ti].swap(lowe);
+		consDiag[ti].swap(diag);
+		consUppe[ti].swap(uppe);
 	}
 	for(long ti = 0; ti < maxiLeve; ti ++){
 		realProl[ti].makeCompressed();

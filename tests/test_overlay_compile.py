@@ -53,3 +53,17 @@ def test_overlay_solver_without_a_device_ends_the_process_loudly():
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
     assert p.returncode == 3
     assert b"MGPIS::BiCGSTAB_SOLV (B200): ERROR" in p.stderr and b"no CPU fallback" in p.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "examples")) or CXX is None, reason="reference sources or g++ not available")
+def test_overlay_establish_fills_the_members_exactly_as_the_reference(tmp_path):
+    """SURVEY.md §8 row a2 on the CPU: the reference's MGPIS::ESTABLISH (MGPIS.h:40-53) and the overlay's, compiled into
+    one program under different class names (tests/cpp/establish_parity.cpp), give bit-identical consLowe / consDiag /
+    consUppe on random hierarchies with ragged rows, stored zeros and rows without a stored diagonal."""
+    exe = str(tmp_path / "establish_parity")
+    lib = os.path.join(ROOT, "ddpca-admm_b200", "lib")
+    subprocess.check_call([CXX, "-O1", "-std=c++17", "-fopenmp", "-I" + REF, "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "establish_parity.cpp"), "-o", exe,
+                           "-L" + lib, "-lddpca_b200", "-Wl,-rpath," + lib], cwd=os.path.join(ROOT, "tests", "cpp"))
+    out = subprocess.check_output([exe], timeout=120).decode()
+    assert out.startswith("OK levels compared: 10")
