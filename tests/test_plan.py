@@ -171,3 +171,32 @@ def test_host_set_up_arrays_are_pinned_by_checksum():
     assert dd.setup_dryrun([(A, P)] * 3, dd.SMOOTH_LEX)["checksum"] == 2724131200358734289
     assert dd.setup_dryrun([(A, P)] * 8, dd.SMOOTH_MC)["checksum"] == 16331060792140387340
     assert dd.setup_dryrun([(A, P)] * 8, dd.SMOOTH_LEX)["checksum"] == 8606172048292588632
+
+
+@pytest.mark.parametrize("name", ["beam_3lev", "block_lagrange"])
+def test_planning_code_is_clean_under_address_and_ub_sanitizers(tmp_path, name):
+    """tests/cpp/plan_sanitize.cpp: every planning / permutation / transpose / compaction routine of csrc/plan.cpp over
+    every level of a reference-written hierarchy, compiled with -fsanitize=address,undefined (the BEAM hierarchy and the
+    condensed dual-mortar system with its wide ragged rows); the native run re-checks the plan invariants as well."""
+    import gzip
+    import os
+    import shutil
+    import subprocess
+
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if cxx is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "plan_sanitize")
+    r = subprocess.run([cxx, "-O1", "-g", "-std=c++17", "-fopenmp", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+                        os.path.join(root, "tests", "cpp", "plan_sanitize.cpp"), os.path.join(root, "ddpca-admm_b200", "csrc", "plan.cpp"), "-o", exe],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if r.returncode != 0 and b"asan" in r.stdout.lower():
+        pytest.skip("sanitizer runtime not installed")
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    raw = str(tmp_path / (name + ".ddpk"))
+    with gzip.open(os.path.join(root, "tests", "golden", name + ".ddpk.gz"), "rb") as f, open(raw, "wb") as g:
+        shutil.copyfileobj(f, g)
+    p = subprocess.run([exe, raw], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, env=dict(os.environ, UBSAN_OPTIONS="halt_on_error=1"))
+    assert p.returncode == 0, p.stderr.decode()[-3000:]
+    assert p.stdout.decode().startswith("OK levels 3")
