@@ -82,10 +82,10 @@ def test_two_rank_admm_with_the_interface_eliminated_coarse_problem(musc):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_pairwise_trace_swap_and_allreduce_over_gloo(world):
+def test_pairwise_trace_swap_and_allreduce_over_gloo(world, tmp_path):
     """ddpca_b200.comm.TorchComm (the exchange layer of the multi-GPU loop): ranges of the send buffer go to their peers
     and the same ranges of the receive buffer come back (grouped isend/irecv, no reduction), all-reduce sums."""
-    out = tempfile.mkdtemp(prefix="ddpca_comm_")
+    out = str(tmp_path)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29617", os.path.join(ROOT, "tests", "dist_comm_worker.py"), out]
     subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
