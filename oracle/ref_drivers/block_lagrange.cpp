@@ -11,7 +11,7 @@
 // solution become a fixture for the oracle / device parity tests (tests/golden/block_lagrange.ddpk.gz is the
 // reference build's).  Both builds time the two MGPIS calls of every active-set step.
 //
-// usage: block_lagrange --glob G [--divi a,b,c] [--out f.ddpk]
+// usage: block_lagrange --glob G [--divi a,b,c] [--out f.ddpk [--skew s]]   (--skew: lagrange_tap.h, SKEW_VARIANT)
 #include "lagrange_tap.h"
 #include "MCONTACT.h"
 #include "examples/BLOCK.h"
@@ -27,6 +27,7 @@ int main(int argc, char **argv) {
 		if (a == "--glob") glob = std::stol(next());
 		else if (a == "--divi") { std::stringstream ss(next()); std::string t; while (std::getline(ss, t, ',')) divi.push_back(std::stol(t)); }
 		else if (a == "--out") g_lagrOut = next();
+		else if (a == "--skew") g_lagrSkew = std::stod(next());
 		else { std::cerr << "unknown arg " << a << std::endl; return 2; }
 	}
 	double t0 = now_s();

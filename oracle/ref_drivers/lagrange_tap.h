@@ -12,13 +12,17 @@
 #include "MGPIS.h"
 #undef MGPIS
 #define LAGR_IMPL "reference"
+#define LAGR_REFERENCE_BUILD 1
 #else                                  // overlay build: host/Makefile passes -DMGPIS=MGPIS_BASE ahead of the force-include
 #undef MGPIS
 #define LAGR_IMPL "b200"
 #endif
 #include <chrono>
 #include "ddpk_io.h"
+#include <mutex>
+#include <sstream>
 static std::string g_lagrOut;
+static double g_lagrSkew = 0.0;   // --skew s (reference build, with --out): also dump a non-symmetric variant of the system
 static long g_lagrCalls = 0, g_lagrRows = 0;
 static std::vector<double> g_lagrEstaSecs, g_lagrSolvSecs;   // per active-set step: ESTABLISH, BiCGSTAB_SOLV wall time
 static inline double lagr_now() {
@@ -50,9 +54,55 @@ public:
 			for (long tl = 0; tl < maxiLeve; tl++) w.csr("realProl" + std::to_string(tl), realProl[tl]);
 			w.vec("F", totaForc);
 			w.vec("U_1", resuSolu);
+#ifdef LAGR_REFERENCE_BUILD
+			if (g_lagrSkew != 0.0) SKEW_VARIANT(w, totaForc);
+#endif
 		}
 		return r;
 	}
+#ifdef LAGR_REFERENCE_BUILD
+	// A non-symmetric system of the same kind, solved by the UNTOUCHED reference: with sliding friction the condensed
+	// matrix of MCONTACT::LAGRANGE loses its symmetry (MCONTACT.h:3376-3413) -- no reduced example reaches that state
+	// (BLOCK and CYLINDER_1 are frictionless, DEHW's flanks only touch after hours), so the fixture carries a synthetic
+	// one: every strictly-upper entry of K scaled by (1 + s), every strictly-lower one by (1 - s) (symmetric part
+	// unchanged, still positive definite), coarse levels by the same Galerkin products as MCONTACT.h:3557-3559, then
+	// MGPIS::ESTABLISH, one MULT_VCYC and BiCGSTAB_SOLV(1, F, .) of the reference class.  What it pins: the sweeps with
+	// lower != upper^T, and level 0 -- SimplicialLDLT reads only the lower triangle of consStif[0] (PREP.h:107).
+	void SKEW_VARIANT(DDPK_WRITER &w, const Eigen::VectorXd &totaForc) {
+		typedef Eigen::SparseMatrix<double,Eigen::RowMajor> SPMA;
+		MGPIS_BASE skew;
+		skew.maxiLeve = maxiLeve;
+		skew.realProl = realProl;
+		skew.consStif.resize(maxiLeve + 1);
+		SPMA fine = consStif[maxiLeve];
+		fine.makeCompressed();
+		for (long ti = 0; ti < fine.rows(); ti++)
+			for (SPMA::InnerIterator iter(fine, ti); iter; ++iter) {
+				if (iter.col() > ti) iter.valueRef() = iter.value() * (1.0 + g_lagrSkew);
+				else if (iter.col() < ti) iter.valueRef() = iter.value() * (1.0 - g_lagrSkew);
+			}
+		skew.consStif[maxiLeve] = fine;
+		for (long tl = maxiLeve - 1; tl >= 0; tl--)
+			skew.consStif[tl] = skew.realProl[tl].transpose() * skew.consStif[tl + 1] * skew.realProl[tl];
+		skew.ESTABLISH();
+		std::ostringstream text;                       // main thread only: the solver's own log lines
+		std::streambuf *prev = std::cout.rdbuf(text.rdbuf());
+		Eigen::VectorXd soluSkew;
+		skew.BiCGSTAB_SOLV(1, totaForc, soluSkew);
+		DIRE_SOLV direSolv;
+		direSolv.compute(skew.consStif[0]);
+		Eigen::VectorXd vcycSkew = Eigen::VectorXd::Zero(totaForc.rows());
+		skew.MULT_VCYC(maxiLeve, totaForc, vcycSkew, direSolv);
+		std::cout.rdbuf(prev);
+		const std::string log = text.str();
+		const size_t p = log.rfind("#Iteration: ");
+		w.scalar_f64("skew.s", g_lagrSkew);
+		w.scalar_i64("skew.bicgstab_iters", p == std::string::npos ? -1 : std::stol(log.substr(p + 12)) + 1);
+		for (long tl = 0; tl < maxiLeve; tl++) w.csr("skew.consStif" + std::to_string(tl), skew.consStif[tl]);
+		w.vec("skew.U", soluSkew);
+		w.vec("skew.vcyc_of_F", vcycSkew);
+	}
+#endif
 private:
 	double lastEsta_ = 0.0;
 };

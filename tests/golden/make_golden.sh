@@ -21,6 +21,7 @@ python "$here/make_block_fixture.py"
 # `mgpi.BiCGSTAB_SOLV(1, F, U_1)` result (:3561-3562)
 tmp="$(mktemp -d)"
 cd "$tmp"
-"$ref/block_lagrange" --glob 2 --divi 1,1,1 --out "$tmp/block_lagrange.ddpk" > "$here/block_lagrange.json"
+# (--skew 0.2 adds a non-symmetric variant of the same system solved by the reference class: lagrange_tap.h, SKEW_VARIANT)
+"$ref/block_lagrange" --glob 2 --divi 1,1,1 --skew 0.2 --out "$tmp/block_lagrange.ddpk" > "$here/block_lagrange.json"
 gzip -9 -n -c "$tmp/block_lagrange.ddpk" > "$here/block_lagrange.ddpk.gz"
 rm -rf "$tmp"
