@@ -25,8 +25,19 @@ namespace ddpca_host {
 
 typedef Eigen::SparseMatrix<double,Eigen::RowMajor> SPM;
 
+// A device call failed: there is no CPU fallback, and the reference's examples ignore the return value of
+// CONTACT_ANALYSIS() and would go on to write result files of an all-zero state.  Same policy as the MGPIS overlay
+// (MGPIS::DEVICE_FAILURE): the reference-style ERROR line on std::cout, the same on std::cerr, exit status 3 --
+// unless DDPCA_CONTINUE_ON_ERROR=1 asks for the reference's "print and return -1".
 inline bool FAIL(const char *what){
 	std::cout << "MCONTACT::CONTACT_ANALYSIS (B200): ERROR " << what << ": " << ddpca_last_error() << std::endl;
+	const char *e = std::getenv("DDPCA_CONTINUE_ON_ERROR");
+	if(!(e && e[0] == '1')){
+		std::cerr << "MCONTACT::CONTACT_ANALYSIS (B200): ERROR " << what << ": " << ddpca_last_error()
+			<< " -- no CPU fallback, terminating (DDPCA_CONTINUE_ON_ERROR=1 to return -1 instead)" << std::endl;
+		std::cout.flush();
+		std::exit(3);
+	}
 	return false;
 }
 

@@ -53,6 +53,14 @@ def test_overlay_solver_without_a_device_ends_the_process_loudly():
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
     assert p.returncode == 3
     assert b"MGPIS::BiCGSTAB_SOLV (B200): ERROR" in p.stderr and b"no CPU fallback" in p.stderr
+    # the ADMM loop's overlay follows the same policy (an example would otherwise write result files of a zero state)
+    exe = os.path.join(HOST, "_bin", "block_b200")
+    if os.access(exe, os.X_OK):
+        p = subprocess.run([exe, "--glob", "2", "--divi", "2,2,2"], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        assert p.returncode == 3 and b"MCONTACT::CONTACT_ANALYSIS (B200): ERROR" in p.stderr
+        p = subprocess.run([exe, "--glob", "2", "--divi", "2,2,2"], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300,
+                           env=dict(os.environ, DDPCA_CONTINUE_ON_ERROR="1"))
+        assert p.returncode == 1 and b'"error":true' in p.stdout      # the reference's convention: printed, -1 returned, the driver reports it
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "examples")) or CXX is None, reason="reference sources or g++ not available")
