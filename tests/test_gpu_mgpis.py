@@ -374,3 +374,27 @@ def test_bicgstab_on_the_condensed_dual_mortar_system(mode):
     xc = mg.CG_SOLV(1, d["F"])                           # symmetric to rounding without friction: CG agrees
     assert rel(xc, d["U_1"]) < 1e-8
     mg.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_bicgstab_on_a_non_symmetric_system(mode):
+    """Sliding friction makes the condensed system of MCONTACT::LAGRANGE non-symmetric (MCONTACT.h:3376-3413).  The
+    fixture carries a 16 % non-symmetric variant of the condensed BLOCK system solved by the untouched reference class
+    (oracle/ref_drivers/lagrange_tap.h, SKEW_VARIANT; the oracle is pinned to it in tests/test_oracle_golden.py).
+    Products, sweeps and transfers store lower and upper parts separately, so BiCGSTAB_SOLV reaches the reference's
+    solution in about the reference's 10 iterations.  One MULT_VCYC is NOT compared: the reference factorises the lower
+    triangle of consStif[0] only, the device inverts the whole block (tools/skew_check.py)."""
+    from tests.test_oracle_golden import skewed_hierarchy
+
+    d, meta, A, P = load_golden("block_lagrange")
+    As = skewed_hierarchy(d, A)
+    mg = dd.MGPIS.from_hierarchy(As, P, smoother=mode)
+    rng = np.random.default_rng(6)
+    v = rng.standard_normal(As[-1].shape[0])
+    assert rel(mg.spmv(len(As) - 1, v), orc.spmv(As[-1], v)) < 1e-13
+    x = mg.BiCGSTAB_SOLV(1, d["F"])
+    assert mg.last_resid <= mg.last_tol
+    assert rel(x, d["skew.U"]) < 1e-8
+    assert mg.last_iterNumb <= 2 * int(d["skew.bicgstab_iters"][0])
+    assert np.linalg.norm(d["F"] - orc.spmv(As[-1], x)) <= 1e-11 * np.linalg.norm(d["F"])
+    mg.close()
